@@ -1,0 +1,187 @@
+/*
+ * cvs_ntsc.h -- C ABI of the B200-native NTSC/VHS composite-video scanline engine.
+ *
+ * This header is the drop-in boundary for ONE path of
+ * joncampbell123/composite-video-simulator: the per-field scanline DSP
+ *
+ *     composite_layer(AVFrame *dst, AVFrame *src, InputFile&, unsigned field,
+ *                     unsigned long long fieldno)        ffmpeg_ntsc.cpp:1570-1921
+ *
+ * called from the reference's main loop at ffmpeg_ntsc.cpp:2229, with the ~30
+ * file-scope globals it reads (ffmpeg_ntsc.cpp:205-214, 756-809) as an implicit
+ * parameter block.  The reference has no plugin/FFI interface; the seam is that
+ * direct call, so the ABI below mirrors it 1:1 (cvs_composite_layer) and adds a
+ * batched, device-resident form (cvs_composite_fields*) for throughput.
+ *
+ * Plain C: pointers, sizes, PODs.  No torch / C++ types cross this boundary.
+ * Every entry point returns 0 on success or a negative cvs_status; nothing throws.
+ * There is NO CPU fallback: without a usable CUDA device every compute call
+ * fails with CVS_ERR_CUDA.
+ */
+#ifndef CVS_NTSC_H
+#define CVS_NTSC_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CVS_ABI_VERSION 1
+
+typedef enum cvs_status {
+    CVS_OK = 0,
+    CVS_ERR_INVALID_ARG = -1,   /* NULL pointer, bad geometry, stride < 4*w (ffmpeg_ntsc.cpp:1578-1583) */
+    CVS_ERR_BAD_SWITCH = -2,    /* unknown / malformed argv switch (ffmpeg_ntsc.cpp:1221-1228)          */
+    CVS_ERR_CUDA = -3,          /* CUDA runtime failure or no device                                    */
+    CVS_ERR_NOMEM = -4,
+    CVS_ERR_CAPACITY = -5,      /* w/h/batch larger than the context was created for                    */
+    CVS_ERR_HELP = -6,          /* -h/-help seen (reference prints help and exits 1, :981-984)          */
+    CVS_ERR_NOISE_SYNC = -7,    /* internal: noise warm-up did not converge (retried by the host)       */
+    CVS_ERR_UNSUPPORTED = -8
+} cvs_status;
+
+enum { CVS_VHS_SP = 0, CVS_VHS_LP = 1, CVS_VHS_EP = 2 };  /* ffmpeg_ntsc.cpp:803-807 */
+
+/*
+ * POD copy of the live globals composite_layer() reads.  Field names are the
+ * reference's global names; the comment gives the defining line in
+ * ffmpeg_ntsc.cpp and the CLI switch that sets it.
+ */
+typedef struct cvs_params {
+    int32_t struct_size;                         /* = sizeof(cvs_params), ABI guard                     */
+    int32_t output_ntsc;                         /* :209  -tvstd ntsc|pal (PAL => 0)                    */
+    int32_t output_width;                        /* :207  -width                                        */
+    int32_t output_height;                       /* :208  480 NTSC / 576 PAL (:815-831)                 */
+    int32_t video_scanline_phase_shift;          /* :213  -comp-phase 0|90|180|270                      */
+    int32_t video_scanline_phase_shift_offset;   /* :214  -comp-phase-offset                            */
+    int32_t composite_in_chroma_lowpass;         /* :766  -in-composite-lowpass                         */
+    int32_t composite_out_chroma_lowpass;        /* :767  -out-composite-lowpass                        */
+    int32_t composite_out_chroma_lowpass_lite;   /* :768  -out-composite-lowpass-lite                   */
+    int32_t video_noise;                         /* :775  -noise                                        */
+    int32_t video_chroma_noise;                  /* :772  -chroma-noise                                 */
+    int32_t video_chroma_phase_noise;            /* :773  -chroma-phase-noise                           */
+    int32_t video_chroma_loss;                   /* :774  -chroma-dropout                               */
+    int32_t subcarrier_amplitude;                /* :776  -subcarrier-amp                               */
+    int32_t subcarrier_amplitude_back;           /* :777  (+ pre-emphasis term, :1264-1265)             */
+    int32_t emulating_vhs;                       /* :791  -vhs / -vhs-speed / -vhs-hifi                 */
+    int32_t output_vhs_tape_speed;               /* :809  -vhs-speed sp|lp|ep                           */
+    int32_t vhs_head_switching;                  /* :761  -vhs / -vhs-head-switching                    */
+    int32_t vhs_chroma_vert_blend;               /* :796  -vhs-chroma-vblend                            */
+    int32_t vhs_svideo_out;                      /* :797  -vhs-svideo                                   */
+    int32_t nocolor_subcarrier;                  /* :794  -nocolor-subcarrier                           */
+    int32_t reserved0;
+    double  composite_preemphasis;               /* :756  -comp-pre / -comp-catv*                       */
+    double  composite_preemphasis_cut;           /* :757  -comp-cut / -comp-catv*                       */
+    double  vhs_out_sharpen;                     /* :759  (no switch)                                   */
+    double  vhs_head_switching_point;            /* :762  -vhs-head-switching-point                     */
+    double  vhs_head_switching_phase;            /* :763  -vhs-head-switching-phase                     */
+    double  vhs_head_switching_phase_noise;      /* :764  -vhs-head-switching-noise-level               */
+    /* Parsed by the reference CLI but never read by composite_layer(); kept so that
+       cvs_params_apply_argv() accepts exactly the switches parse_argv() accepts. */
+    int32_t use_422_colorspace;                  /* :205  -422 / -420                                   */
+    int32_t output_frame_delay;                  /* -d <1..256> (:1003-1011)                            */
+    int32_t enable_composite_emulation;          /* :798  -nocomp (never read by the video path)        */
+    int32_t enable_audio_emulation;              /* :799                                                */
+    int32_t emulating_preemphasis;               /* :792  audio                                         */
+    int32_t emulating_deemphasis;                /* :793  audio                                         */
+    int32_t output_vhs_hifi;                     /* :788  audio                                         */
+    int32_t output_vhs_linear_audio;             /* :790  audio                                         */
+    int32_t nocolor_subcarrier_after_yc_sep;     /* :795  parsed, unused                                */
+    int32_t video_yc_recombine;                  /* :770  parsed, unused                                */
+    double  output_audio_hiss_db;                /* :778  audio                                         */
+    double  output_audio_linear_buzz;            /* :779  audio                                         */
+    double  vhs_linear_high_boost;               /* :782  audio                                         */
+} cvs_params;
+
+typedef struct cvs_ctx cvs_ctx;   /* opaque: device buffers, streams, RNG position, tables */
+
+/* ---- parameter block ------------------------------------------------------------------- */
+
+/* == the global initialisers (ffmpeg_ntsc.cpp:205-214,756-809) + preset_NTSC() (:824-831). */
+int cvs_params_default_ntsc(cvs_params *p);
+/* == preset_PAL() (:815-822) applied on top of *p. */
+int cvs_params_preset_pal(cvs_params *p);
+/*
+ * Same order-dependent semantics as parse_argv() (ffmpeg_ntsc.cpp:972-1282) for every
+ * switch it accepts (argv[0] is skipped, leading dashes stripped greedily, :980).
+ * -i/-o take and ignore one argument (media I/O is outside the path).  The post-parse
+ * derivation of subcarrier_amplitude_back (:1264-1265) is applied once per call.
+ * Returns CVS_ERR_BAD_SWITCH for an unknown switch / bad value, CVS_ERR_HELP for -h.
+ */
+int cvs_params_apply_argv(cvs_params *p, int argc, const char *const *argv);
+
+/* ---- context ---------------------------------------------------------------------------- */
+
+/*
+ * Create an engine on CUDA device `device` for pictures up to max_w x max_h and batches of
+ * up to max_batch fields.  The RNG stream starts where an un-seeded glibc rand() starts
+ * (the reference never calls srand()).
+ */
+int  cvs_create(cvs_ctx **out, const cvs_params *p, int device, int max_w, int max_h, int max_batch);
+void cvs_destroy(cvs_ctx *ctx);
+int  cvs_set_params(cvs_ctx *ctx, const cvs_params *p);
+
+/* ---- the seam: exact analogue of the call at ffmpeg_ntsc.cpp:2229 ------------------------- */
+
+/*
+ * HOST pointers, BGRA8 (uint32 = A<<24|R<<16|G<<8|B), strides in bytes.  Reads the field
+ * rows of src, writes ONLY dst rows y == field (mod 2) (alpha byte = 0, :1914), leaves the
+ * other rows untouched.  Advances the context's RNG position by exactly the number of
+ * rand() draws the reference call makes.  Synchronous.  Invalid geometry returns
+ * CVS_ERR_INVALID_ARG and leaves dst untouched (the reference returns silently, :1578-1583).
+ */
+int cvs_composite_layer(cvs_ctx *ctx,
+                        uint8_t *dst, int dst_stride,
+                        const uint8_t *src, int src_stride,
+                        int w, int h, int src_interlaced, int src_top_field_first,
+                        unsigned field, unsigned long long fieldno);
+
+/* ---- throughput forms -------------------------------------------------------------------- */
+
+/*
+ * n consecutive calls of the seam in one launch: picture k (k = 0..n-1) lives at
+ * src + k*src_pic_stride / dst + k*dst_pic_stride, is processed with
+ * field = ((first_fieldno + k) & 1) ^ 1 and fieldno = first_fieldno + k  (the schedule of
+ * the reference loop, ffmpeg_ntsc.cpp:2229) and consumes the RNG stream in call order, so
+ * the result is byte-identical to n sequential cvs_composite_layer() calls.
+ *
+ * cvs_composite_fields_device: src/dst are DEVICE pointers (any stream-visible memory);
+ * the launch is asynchronous on the context stream (see cvs_synchronize).
+ * cvs_composite_fields_host: src/dst are HOST pointers (pinned recommended); the call
+ * copies in, computes, copies the field rows back and returns when done.
+ */
+int cvs_composite_fields_device(cvs_ctx *ctx,
+                                void *dst, size_t dst_pic_stride, int dst_stride,
+                                const void *src, size_t src_pic_stride, int src_stride,
+                                int w, int h, int src_interlaced, int src_top_field_first,
+                                int n, unsigned long long first_fieldno);
+int cvs_composite_fields_host(cvs_ctx *ctx,
+                              void *dst, size_t dst_pic_stride, int dst_stride,
+                              const void *src, size_t src_pic_stride, int src_stride,
+                              int w, int h, int src_interlaced, int src_top_field_first,
+                              int n, unsigned long long first_fieldno);
+int cvs_synchronize(cvs_ctx *ctx);
+
+/* ---- RNG stream (hidden state of the reference: the libc rand() position) ------------------ */
+
+/* Absolute position: number of rand() draws consumed since program start (seed 1). */
+int cvs_rng_seek(cvs_ctx *ctx, unsigned long long draws_consumed);
+int cvs_rng_tell(const cvs_ctx *ctx, unsigned long long *draws_consumed);
+/* Draws one composite_layer() call consumes for this geometry/params. */
+unsigned long long cvs_draws_per_field(const cvs_params *p, int w, int h, unsigned field);
+
+/* ---- introspection -------------------------------------------------------------------------- */
+
+const char *cvs_strerror(int status);
+int         cvs_abi_version(void);
+/* Number of kernel launches issued by this context so far (bench.py's gpu_launches). */
+unsigned long long cvs_kernel_launches(const cvs_ctx *ctx);
+/* Device time in ms of the most recent cvs_composite_fields_* kernel region (CUDA events). */
+int cvs_last_kernel_ms(cvs_ctx *ctx, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CVS_NTSC_H */
