@@ -1,0 +1,853 @@
+// lane_pipeline.cuh -- the fused scanline pipeline, one lane = one field scanline.
+//
+// What it computes: every stage of the reference's composite_layer()
+// (ffmpeg_ntsc.cpp:1570-1921) for ONE scanline, as a single streaming pass in x.
+// The reference sweeps three int32 heap planes ~14 times per field; here a scanline never
+// leaves registers between the BGRA load and the BGRA store (8 algorithmic bytes/pixel).
+//
+// Mapping: a warp owns 32 consecutive field rows (lane 0 is a halo row for
+// the vertical chroma blend), all lanes advance through x in lock-step in blocks of 8
+// pixels, so every x-dependent condition (line start/end quirks) is warp-uniform, the
+// vertical blend (ffmpeg_ntsc.cpp:1843-1863) is one __shfl_up per value, and the one-pole
+// IIR cascades run in the reference's own sequential order (no re-association).  Stage
+// look-ahead (QAM demodulation needs C[x+7], the VHS chroma delay is 9..14 samples, ...)
+// is absorbed by running later stages on older 8-pixel blocks; all block lags are
+// compile-time so every delay line is a statically indexed register array.
+//
+// The file is host/device portable on purpose: tests/ compile it with g++ and run all 32
+// lanes of a warp in lock-step on the CPU (tests/emu_harness.cpp), where R = double gives
+// the reference's arithmetic bit for bit and R = float is the production arithmetic.
+//
+// Timeline (T = 8 px per step; B(k) = pixels [8k, 8k+8); s = step):
+//   load  B(s)          BGRA block (prefetched one step ahead)
+//   A1    B(s)          RGB->YIQ, input chroma lowpass cascades          (:1375, :1429)
+//   A2    B(s-1)        composite C = Y + QAM(I',Q'), pre-emphasis, luma noise (:1460,:1613,:1631)
+//   HS    B(s-1)        head-switch rows take C from the pre-shifted scratch row (:1646)
+//   B     B(s-2)        Y/C separation + demod, chroma noise, phase noise (:1497,:1718,:1736)
+//         VHS:          luma lowpass+HF boost, sharpen -> Y3 B(s-2); chroma lowpass (:1793-1883)
+//   B2    B(s-4)        (VHS) delayed chroma block complete -> vertical blend -> remodulate C2
+//   C     B(s-5)        (VHS) second demod                                (:1885-1888)
+//   F     B(k)          dropout, output chroma lowpass, YIQ->RGB          (:1891-1916)
+//                       k = s-5 (VHS) / s-4 (VHS s-video) / s-2 (composite only)
+//   store B(k-1)
+#ifndef CVS_LANE_PIPELINE_CUH
+#define CVS_LANE_PIPELINE_CUH
+
+#include <stdint.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define CVS_HD __host__ __device__ __forceinline__
+#define CVS_UNROLL _Pragma("unroll")
+#else
+#define CVS_HD inline __attribute__((always_inline))
+#define CVS_UNROLL _Pragma("GCC unroll 16")
+#endif
+
+namespace cvs {
+
+constexpr int kT = 8;            // pixels per step
+constexpr int kRngSlots = 32;    // per-lane ring of raw generator words (>= 31)
+constexpr int kTailSlots = 16;   // per-lane stash of pre-filter chroma for the delay tail (>= max chroma delay)
+constexpr uint32_t kRngBase = 128;  // ring index of the first in-line draw (multiple of 32, > max warm-up + 31)
+
+// ---- flags (uniform per launch) ------------------------------------------------------------
+enum : uint32_t {
+    F_IN_LP = 1u << 0,        // composite_in_chroma_lowpass
+    F_OUT_LP = 1u << 1,       // composite_out_chroma_lowpass
+    F_PREEMPH = 1u << 2,      // composite_preemphasis != 0 && cut > 0
+    F_NOCOLOR = 1u << 3,      // nocolor_subcarrier
+    F_VBLEND = 1u << 4,       // vhs_chroma_vert_blend && output_ntsc
+    F_SVIDEO = 1u << 5,       // vhs_svideo_out
+    F_PHASE = 1u << 6,        // video_chroma_phase_noise != 0
+    F_GENERAL = 1u << 7,      // any non-default switch: run the general (edge) variant everywhere
+};
+
+// per-row flags (host side table)
+enum : uint32_t {
+    RF_DROPOUT = 1u << 0,     // chroma dropout hit this row (:1896)
+    RF_HEADSW = 1u << 1,      // row is rotated by the head switch; C comes from scratch
+};
+
+// ---- launch-uniform constants -------------------------------------------------------------
+template <typename R>
+struct KConst {
+    R a_inI, b_inI, a_inQ, b_inQ;         // input chroma lowpass 1.3 MHz / 0.6 MHz   (:1442)
+    R a_pre, b_pre, preemph;              // composite pre-emphasis                    (:1621)
+    R a_luma, b_luma;                     // VHS luma lowpass                          (:1800)
+    R a_chroma, b_chroma;                 // VHS chroma lowpass                        (:1821)
+    R a_sharp, b_sharp, sharpen;          // VHS sharpen lowpass (4x luma cut), gain   (:1874,:1880)
+    R a_outI, b_outI, a_outQ, b_outQ;     // output chroma lowpass                     (:1411 / :1442)
+    const R *phase_lut;                   // [2*pnoise+1][2] = {sin, cos} of state*pi/100, state = -p..p (:1746-1749)
+    uint32_t flags;
+    int32_t pnoise;                       // video_chroma_phase_noise
+    int32_t phase_shift, phase_offset;    // video_scanline_phase_shift(_offset)
+    int32_t field;                        // field parity of this launch
+    int32_t amp, amp_back;                // subcarrier_amplitude, _back
+    int32_t vnoise, cnoise;               // video_noise, video_chroma_noise
+    uint32_t vmagic, vshift, cmagic, cshift;   // exact n % (2v+1) for 31-bit n: q = umulhi(n,magic) >> shift
+    int32_t w, h, nl;
+};
+
+// ---- numeric policy -------------------------------------------------------------------------
+// R = double: the reference's arithmetic, operation for operation (three roundings per pole
+// step, ffmpeg_ntsc.cpp:90-94; colour matrices as written).  Needs no FMA contraction
+// (host: -ffp-contract=off; device: explicit __dmul_rn/__dadd_rn).
+// R = float: production arithmetic; explicit fmaf where fused, everything else unfused, so the
+// CPU emulation and the GPU produce identical bits.
+template <typename R> struct Num;
+
+template <> struct Num<double> {
+    static CVS_HD double mul(double a, double b) {
+#if defined(__CUDA_ARCH__)
+        return __dmul_rn(a, b);
+#else
+        return a * b;
+#endif
+    }
+    static CVS_HD double add(double a, double b) {
+#if defined(__CUDA_ARCH__)
+        return __dadd_rn(a, b);
+#else
+        return a + b;
+#endif
+    }
+    static CVS_HD double sub(double a, double b) { return add(a, -b); }
+    static CVS_HD double fma_(double a, double b, double c) { return add(mul(a, b), c); }   // never fused
+    static CVS_HD double trunc_(double a) { return ::trunc(a); }
+    static CVS_HD double floor_(double a) { return ::floor(a); }
+    // lowpass(), :90-94
+    static CVS_HD double pole(double &prev, double s, double alpha, double /*beta*/) {
+        const double stage1 = mul(s, alpha);
+        const double stage2 = sub(prev, mul(prev, alpha));
+        prev = add(stage1, stage2);
+        return prev;
+    }
+    static CVS_HD void rgb2yiq(int r, int g, int b, double &Y, double &I, double &Q) {   // :1375-1383
+        const double dY = add(add(mul(0.30, r), mul(0.59, g)), mul(0.11, b));
+        Y = trunc_(mul(256, dY));
+        I = trunc_(mul(256, add(mul(-0.27, sub(b, dY)), mul(0.74, sub(r, dY)))));
+        Q = trunc_(mul(256, add(mul(0.41, sub(b, dY)), mul(0.48, sub(r, dY)))));
+    }
+    static CVS_HD double mix3(double Y, double ci, double I, double cq, double Q) {      // :1387-1389
+        return trunc_(add(add(mul(1.000, Y), mul(ci, I)), mul(cq, Q)) / 256);
+    }
+    static CVS_HD double rot_a(double u, double c, double v, double s) { return trunc_(sub(mul(u, c), mul(v, s))); }  // :1756
+    static CVS_HD double rot_b(double u, double s, double v, double c) { return trunc_(add(mul(u, s), mul(v, c))); }  // :1757
+    static CVS_HD double boost(double s, double hp, double g) { return trunc_(add(s, mul(hp, g))); }                  // :1808-1810
+    static CVS_HD double sharpen(double s, double ts, double g) { return trunc_(add(s, mul(mul(sub(s, ts), g), 2))); } // :1880
+    static CVS_HD double preemph(double s, double hp, double g) { return trunc_(add(s, mul(hp, g))); }                // :1626-1627
+};
+
+template <> struct Num<float> {
+    static CVS_HD float mul(float a, float b) {
+#if defined(__CUDA_ARCH__)
+        return __fmul_rn(a, b);
+#else
+        return a * b;
+#endif
+    }
+    static CVS_HD float add(float a, float b) {
+#if defined(__CUDA_ARCH__)
+        return __fadd_rn(a, b);
+#else
+        return a + b;
+#endif
+    }
+    static CVS_HD float sub(float a, float b) { return add(a, -b); }
+    static CVS_HD float fma_(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+        return __fmaf_rn(a, b, c);
+#else
+        return ::fmaf(a, b, c);
+#endif
+    }
+    static CVS_HD float trunc_(float a) { return ::truncf(a); }
+    static CVS_HD float floor_(float a) { return ::floorf(a); }
+    static CVS_HD float pole(float &prev, float s, float alpha, float beta) {
+        prev = fma_(beta, prev, mul(alpha, s));      // one FFMA on the recurrence path
+        return prev;
+    }
+    static CVS_HD void rgb2yiq(int r, int g, int b, float &Y, float &I, float &Q) {
+        const float rf = (float)r, gf = (float)g, bf = (float)b;
+        const float dY = fma_(0.11f, bf, fma_(0.59f, gf, mul(0.30f, rf)));
+        const float bd = sub(bf, dY), rd = sub(rf, dY);
+        Y = trunc_(mul(256.0f, dY));
+        I = trunc_(mul(256.0f, fma_(0.74f, rd, mul(-0.27f, bd))));
+        Q = trunc_(mul(256.0f, fma_(0.48f, rd, mul(0.41f, bd))));
+    }
+    static CVS_HD float mix3(float Y, float ci, float I, float cq, float Q) {
+        return trunc_(mul(fma_(cq, Q, fma_(ci, I, Y)), 0.00390625f));
+    }
+    static CVS_HD float rot_a(float u, float c, float v, float s) { return trunc_(fma_(u, c, -mul(v, s))); }
+    static CVS_HD float rot_b(float u, float s, float v, float c) { return trunc_(fma_(u, s, mul(v, c))); }
+    static CVS_HD float boost(float s, float hp, float g) { return trunc_(fma_(hp, g, s)); }
+    static CVS_HD float sharpen(float s, float ts, float g) { return trunc_(fma_(mul(sub(s, ts), g), 2.0f, s)); }
+    static CVS_HD float preemph(float s, float hp, float g) { return trunc_(fma_(hp, g, s)); }
+};
+
+// integer helpers on integer-valued reals (all plane values are integers, |v| < 2^24)
+template <typename R> CVS_HD R div4_trunc(R s) { return Num<R>::trunc_(Num<R>::mul(s, (R)0.25)); }   // C int '/ 4'
+template <typename R> CVS_HD R shr1_floor(R s) { return Num<R>::floor_(Num<R>::mul(s, (R)0.5)); }   // C int '>> 1'
+
+CVS_HD int clamp255(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
+
+// (v * num) / den on C ints (truncation toward zero); |v*num| < 2^31 by construction
+CVS_HD int muldiv_trunc(int v, int num, int den) { return (v * num) / den; }
+
+// ---- per-lane RNG + noise ---------------------------------------------------------------------
+// Ring layout in shared memory: word (slot, lane) at ring[slot * stride + lane]; stride = number
+// of lanes sharing the buffer, so a warp access is conflict-free.  On the host stride = 1.
+struct LaneRng {
+    uint32_t *ring;      // already offset by the lane index
+    int stride;
+    uint32_t l1, l2, l3; // q[n-1], q[n-2], q[n-3] (short-lag taps stay in registers)
+
+    // hist[i] = q[n0 - 31 + i], i = 0..30: the 31 raw words preceding ring index n0
+    CVS_HD void init(uint32_t *ring_, int stride_, const uint32_t hist[31], uint32_t n0) {
+        ring = ring_;
+        stride = stride_;
+        for (int i = 0; i < 31; i++) ring[((n0 - 31 + i) & (kRngSlots - 1)) * stride] = hist[i];
+        l1 = hist[30]; l2 = hist[29]; l3 = hist[28];
+    }
+    // q[n] = q[n-31] + q[n-3].  The caller supplies n (same for every lane of a warp, so the slot
+    // arithmetic is warp-uniform); draws must be requested in increasing n without gaps.
+    CVS_HD uint32_t next_raw(uint32_t n) {
+        const uint32_t v = ring[((n + 1) & (kRngSlots - 1)) * stride] + l3;     // (n-31) & 31 == (n+1) & 31
+        ring[(n & (kRngSlots - 1)) * stride] = v;
+        l3 = l2; l2 = l1; l1 = v;
+        return v;
+    }
+};
+
+// n % m for n < 2^31 and 1 < m < 2^16 via q = umulhi(n, magic) >> shift (exact)
+CVS_HD uint32_t umulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+CVS_HD int draw_mod(uint32_t raw, uint32_t m, uint32_t magic, uint32_t shift) {
+    const uint32_t n = raw >> 1;                       // rand() = q >> 1
+    const uint32_t q = umulhi32(n, magic) >> shift;
+    return (int)(n - q * m);
+}
+// noise += rand() % (2v+1) - v; noise /= 2   (:1640-1641, :1729-1732)
+CVS_HD int noise_step(int noise, int d, int v) {
+    int t = noise + d - v;
+    t += (int)((uint32_t)t >> 31);                     // C '/ 2' truncates toward zero
+    return t >> 1;
+}
+
+// ---- per-row constants --------------------------------------------------------------------------
+template <typename R>
+struct RowConst {
+    R mI[4], mQ[4];      // QAM carrier taps for (x & 3): Umult/Vmult rotated by the line phase xi (:1465-1466)
+    R sgA;               // demod sign for even x with (x & 2) == 0; the (x & 2) != 0 sign is -sgA
+    R sinp, cosp;        // chroma phase noise rotation of this row (:1748-1749)
+    int xi;              // subcarrier phase index (:1473-1480)
+    uint32_t rflags;
+    int row;             // field row index (y = field + 2*row)
+};
+
+template <typename R>
+CVS_HD void rowconst_set_phase(RowConst<R> &rc, int xi) {
+    rc.xi = xi;
+    CVS_UNROLL
+    for (int j = 0; j < 4; j++) {
+        const int ph = (xi + j) & 3;
+        rc.mI[j] = (R)((ph == 0) ? 1 : (ph == 2) ? -1 : 0);
+        rc.mQ[j] = (R)((ph == 1) ? 1 : (ph == 3) ? -1 : 0);
+    }
+    // I[x] = -flip(x+xi) * chroma[x+xi]; for even x with (x&3)==0 the carrier is flipped iff xi is odd
+    rc.sgA = (R)((xi & 1) ? 1 : -1);
+}
+
+// ---- the lane ----------------------------------------------------------------------------------
+template <typename R, bool VHS, int CD, bool OUTFULL>
+struct Lane {
+    static constexpr int OD = OUTFULL ? 4 : 1;    // output lowpass: max(delayI, delayQ)
+    static constexpr int ODI = OUTFULL ? 2 : 1;   // I delay
+    static constexpr int ODQ = OUTFULL ? 4 : 1;   // Q delay
+    static constexpr int LAG = VHS ? 6 : 3;       // steps between loading B(s) and storing B(s-LAG)
+
+    // --- carried state (all statically indexed) ---
+    // A
+    uint32_t pxprev[kT];             // BGRA of B(s-1) (raw I/Q are recomputed from it on the tail path)
+    R Yprev[kT];                     // Y of B(s-1)
+    R oIprev[kT], oQprev[kT];        // input-lowpass cascade outputs for t in B(s-1)
+    R pI[3], pQ[3];                  // cascade poles
+    R pPre;                          // pre-emphasis pole
+    int nY;                          // luma noise accumulator (:1633)
+    // B
+    R Cm1;                           // C[8(s-2)-1]
+    R Cprev[kT];                     // C of B(s-2)
+    int nU, nV;                      // chroma noise accumulators (:1720)
+    R pL[3], pLpre;                  // VHS luma poles (:1800-1805)
+    R pS[3];                         // sharpen poles (:1873-1876)
+    R pU[3], pV[3];                  // VHS chroma poles (:1821-1826)
+    R oUprev[kT], oVprev[kT];        // chroma cascade outputs for t in B(s-3)
+    R Y3a[kT], Y3b[kT];              // Y3 of B(s-3), B(s-4)
+    // B2 / C
+    R C2m1;                          // C2[8(s-5)-1]
+    R C2prev[kT];                    // C2 of B(s-5)
+    // F
+    R pOI[3], pOQ[3];                // output lowpass poles
+    R Ytail[OD], Itail[OD], Qtail[OD];      // last OD values of Y4 / raw I4 / raw Q4 of the previous F block
+    R oOItail[OD], oOQtail[OD];             // last OD cascade outputs of the previous F block
+    uint32_t outprev[kT];            // packed pixels of positions [8(k-1), 8k-OD) in slots 0..7-OD
+
+    LaneRng rngL, rngC;
+    R *tailU, *tailV;                // per-lane stash (kTailSlots each), stride tail_stride
+    int tail_stride;
+
+    CVS_HD void reset(const KConst<R> &K) {
+        CVS_UNROLL
+        for (int j = 0; j < kT; j++) {
+            pxprev[j] = 0; Yprev[j] = 0; oIprev[j] = 0; oQprev[j] = 0; Cprev[j] = 0;
+            oUprev[j] = 0; oVprev[j] = 0; Y3a[j] = 0; Y3b[j] = 0; C2prev[j] = 0; outprev[j] = 0;
+        }
+        CVS_UNROLL
+        for (int k = 0; k < 3; k++) {
+            pI[k] = 0; pQ[k] = 0;           // resetFilter(0), :1447
+            pL[k] = 16;                     // resetFilter(16), :1802
+            pS[k] = 0;                      // :1875
+            pU[k] = 0; pV[k] = 0;           // :1823,:1825
+            pOI[k] = 0; pOQ[k] = 0;         // :1416
+        }
+        pLpre = 16;                         // :1805
+        pPre = 16;                          // :1622
+        Cm1 = 0; C2m1 = 0;
+        CVS_UNROLL
+        for (int k = 0; k < OD; k++) { Ytail[k] = 0; Itail[k] = 0; Qtail[k] = 0; oOItail[k] = 0; oOQtail[k] = 0; }
+        (void)K;
+    }
+};
+
+// three cascaded poles (no truncation between stages, :1420/:1451/:1807/:1828/:1878)
+template <typename R>
+CVS_HD R cascade3(R p[3], R s, R a, R b) {
+    s = Num<R>::pole(p[0], s, a, b);
+    s = Num<R>::pole(p[1], s, a, b);
+    return Num<R>::pole(p[2], s, a, b);
+}
+
+// QAM modulation of one sample (chroma_into_luma, :1486-1490).  amp == 50 makes (v*50)/50 == v.
+template <typename R, bool EDGE>
+CVS_HD R modulate(R Yv, R Iv, R Qv, R mI, R mQ, int amp) {
+    if (!EDGE || amp == 50) {
+        // exactly one of mI, mQ is +-1, the other 0: the sum is exact
+        return Num<R>::fma_(Iv, mI, Num<R>::fma_(Qv, mQ, Yv));
+    } else {
+        const int chroma = (int)Iv * amp * (int)mI + (int)Qv * amp * (int)mQ;
+        return Num<R>::add(Yv, (R)(chroma / 50));
+    }
+}
+
+// Y/C separation + QAM demodulation of block B(k) (chroma_from_luma, :1497-1567).
+//   cm1      = C[8k-1]
+//   c[0..15] = C[8k .. 8k+15]   (only c[0..14] are read; zero beyond the line end)
+// outputs Yb (box-filtered luma), Ib, Qb for the 8 pixels of the block.
+template <typename R, bool EDGE>
+CVS_HD void demod_block(const RowConst<R> &rc, int k, int w, int amp, R cm1, const R c[2 * kT],
+                        R Yb[kT], R Ib[kT], R Qb[kT]) {
+    const int x0 = k * kT;
+    // box[m] = (C[m-1] + C[m] + C[m+1] + C[m+2]) / 4 ; chroma[m] = C[m+2] - box[m], m = 0..12
+    R ch[13];
+    CVS_UNROLL
+    for (int m = 0; m < 13; m++) {
+        const R a = (m == 0) ? cm1 : c[m - 1];
+        const R sum = Num<R>::add(Num<R>::add(a, c[m]), Num<R>::add(c[m + 1], c[m + 2]));
+        const R box = div4_trunc<R>(sum);
+        if (m < kT) Yb[m] = box;
+        ch[m] = Num<R>::sub(c[m + 2], box);
+    }
+    if (EDGE) {
+        // carrier sign flips with their line-end / line-start conditions (:1539-1542), then the
+        // amplitude rescale (:1544-1546).  In the interior the flip folds into sgA below.
+        CVS_UNROLL
+        for (int m = 0; m < 13; m++) {
+            const int q = x0 + m;
+            const int ph = (q + rc.xi) & 3;
+            const int g = q - ph;                      // start of this carrier period
+            const bool flip = (ph >= 2) && (g >= 0) && (g + 3 < w);
+            R v = flip ? -ch[m] : ch[m];
+            if (amp != 50) v = (R)muldiv_trunc((int)v, 50, amp);
+            ch[m] = v;
+        }
+    }
+    // even pixels: I = -chroma[x+xi], Q = -chroma[x+xi+1]  (:1549-1552); 5 even positions: 4 in
+    // the block plus the first of the next block (needed by the odd-pixel interpolation)
+    const bool x1 = (rc.xi & 1) != 0, x2 = (rc.xi & 2) != 0;
+    R Ie[5], Qe[5];
+    CVS_UNROLL
+    for (int e = 0; e < 5; e++) {
+        const int j = 2 * e;
+        const R i01 = x1 ? ch[j + 1] : ch[j];
+        const R i23 = x1 ? ch[j + 3] : ch[j + 2];
+        const R q01 = x1 ? ch[j + 2] : ch[j + 1];
+        const R q23 = x1 ? ch[j + 4] : ch[j + 3];
+        R iv = x2 ? i23 : i01;
+        R qv = x2 ? q23 : q01;
+        if (EDGE) {
+            const int x = x0 + j;
+            const bool ok = (x + rc.xi + 1) < w;        // :1549, else zero (:1553-1556)
+            iv = ok ? -iv : (R)0;
+            qv = ok ? -qv : (R)0;
+        } else {
+            const R sg = (j & 2) ? -rc.sgA : rc.sgA;    // -(flip ? -1 : 1) folded
+            iv = Num<R>::mul(iv, sg);
+            qv = Num<R>::mul(qv, sg);
+        }
+        Ie[e] = iv;
+        Qe[e] = qv;
+    }
+    // odd pixels: average of the even neighbours, arithmetic >> 1 (:1557-1560)
+    CVS_UNROLL
+    for (int e = 0; e < 4; e++) {
+        Ib[2 * e] = Ie[e];
+        Qb[2 * e] = Qe[e];
+        Ib[2 * e + 1] = shr1_floor<R>(Num<R>::add(Ie[e], Ie[e + 1]));
+        Qb[2 * e + 1] = shr1_floor<R>(Num<R>::add(Qe[e], Qe[e + 1]));
+    }
+    if (EDGE) {
+        // after the interpolation the last pixels lose their chroma (:1561-1564); an odd pixel is
+        // only interpolated while x+1 < w (:1557)
+        const int zstart = (w - 1) & ~1;
+        CVS_UNROLL
+        for (int j = 0; j < kT; j++) {
+            const int x = x0 + j;
+            if (x >= zstart || ((j & 1) && (x + 1 >= w))) { Ib[j] = 0; Qb[j] = 0; }
+        }
+    }
+}
+
+// ---- the step ------------------------------------------------------------------------------------
+// Exchange buffer for the vertical chroma blend: each lane publishes its pre-blend chroma block and
+// receives the block of the row above (lane - 1).  On the GPU this is 16 __shfl_up_sync.
+template <typename R>
+struct BlendXchg {
+    R u[kT], v[kT];
+};
+
+template <typename R, bool VHS, int CD, bool OUTFULL>
+struct Pipeline {
+    typedef Lane<R, VHS, CD, OUTFULL> L;
+    typedef Num<R> N;
+
+    // ---- A1 + A2 (+ head-switch substitution): returns C block B(s-1) in Cnew --------------------
+    template <bool EDGE>
+    static CVS_HD void stage_a(const KConst<R> &K, const RowConst<R> &rc, L &ln, int s,
+                               const uint32_t px[kT], const int32_t *hs_row, R Cnew[kT]) {
+        const int w = K.w;
+        const int p = s * kT;
+        R Ycur[kT], oIcur[kT], oQcur[kT];
+        // A1: RGB -> YIQ and the input chroma lowpass cascades on B(s)
+        CVS_UNROLL
+        for (int j = 0; j < kT; j++) {
+            const int t = p + j;
+            if (!EDGE || t < w) {
+                R y, i, q;
+                N::rgb2yiq((int)((px[j] >> 16) & 0xFF), (int)((px[j] >> 8) & 0xFF), (int)(px[j] & 0xFF), y, i, q);
+                Ycur[j] = y;
+                oIcur[j] = N::trunc_(cascade3<R>(ln.pI, i, K.a_inI, K.b_inI));   // P[x-delay] = s, :1453
+                oQcur[j] = N::trunc_(cascade3<R>(ln.pQ, q, K.a_inQ, K.b_inQ));
+            } else {
+                Ycur[j] = 0; oIcur[j] = 0; oQcur[j] = 0;
+            }
+        }
+        // A2: composite block B(s-1)
+        if (!EDGE || s >= 1) {
+            const bool in_lp = !EDGE || (K.flags & F_IN_LP);
+            CVS_UNROLL
+            for (int j = 0; j < kT; j++) {
+                const int x = p - kT + j;
+                R c = 0;
+                if (!EDGE || x < w) {
+                    // filtered chroma arrives early by the filter delay; the last `delay` samples of
+                    // a line keep their unfiltered values (:1453)
+                    R iv = (j + 2 < kT) ? ln.oIprev[(j + 2) % kT] : oIcur[(j + 2) % kT];
+                    R qv = (j + 4 < kT) ? ln.oQprev[(j + 4) % kT] : oQcur[(j + 4) % kT];
+                    if (EDGE) {
+                        const bool rawI = !in_lp || (x + 2 >= w), rawQ = !in_lp || (x + 4 >= w);
+                        if (rawI || rawQ) {
+                            R y, i, q;
+                            N::rgb2yiq((int)((ln.pxprev[j] >> 16) & 0xFF), (int)((ln.pxprev[j] >> 8) & 0xFF),
+                                       (int)(ln.pxprev[j] & 0xFF), y, i, q);
+                            if (rawI) iv = i;
+                            if (rawQ) qv = q;
+                        }
+                    }
+                    c = modulate<R, EDGE>(ln.Yprev[j], iv, qv, rc.mI[j & 3], rc.mQ[j & 3], K.amp);   // :1611
+                    if (EDGE && (K.flags & F_PREEMPH)) {                                             // :1613-1629
+                        const R lp = N::pole(ln.pPre, c, K.a_pre, K.b_pre);
+                        c = N::preemph(c, N::sub(c, lp), K.preemph);
+                    }
+                    if (K.vnoise != 0) {                                                             // :1631-1644
+                        c = N::add(c, (R)ln.nY);
+                        const int d = draw_mod(ln.rngL.next_raw(kRngBase + (uint32_t)x), (uint32_t)(2 * K.vnoise + 1), K.vmagic, K.vshift);
+                        ln.nY = noise_step(ln.nY, d, K.vnoise);
+                    }
+                    if (hs_row && (rc.rflags & RF_HEADSW)) c = (R)hs_row[x];                         // :1646-1713
+                }
+                Cnew[j] = c;
+            }
+        } else {
+            CVS_UNROLL
+            for (int j = 0; j < kT; j++) Cnew[j] = 0;
+        }
+        CVS_UNROLL
+        for (int j = 0; j < kT; j++) {
+            ln.pxprev[j] = px[j];
+            ln.Yprev[j] = Ycur[j];
+            ln.oIprev[j] = oIcur[j];
+            ln.oQprev[j] = oQcur[j];
+        }
+    }
+
+    // ---- B: demod of B(s-2), noise, phase; VHS luma/chroma filters ---------------------------------
+    // Outputs: Yb/Ib/Qb of B(s-2) for the non-VHS path; for VHS publishes the completed delayed chroma
+    // block B(s-4) in xo (pre-blend) and leaves Y3 of B(s-2) in y3new.
+    template <bool EDGE>
+    static CVS_HD void stage_b(const KConst<R> &K, const RowConst<R> &rc, L &ln, int s, const R Cnew[kT],
+                               R Yb[kT], R Ib[kT], R Qb[kT], BlendXchg<R> &xo) {
+        const int w = K.w;
+        const int k = s - 2;
+        if (EDGE && k < 0) {
+            CVS_UNROLL
+            for (int j = 0; j < kT; j++) { Yb[j] = 0; Ib[j] = 0; Qb[j] = 0; xo.u[j] = 0; xo.v[j] = 0; }
+            ln.Cm1 = ln.Cprev[kT - 1];
+            CVS_UNROLL
+            for (int j = 0; j < kT; j++) ln.Cprev[j] = Cnew[j];
+            return;
+        }
+        R c[2 * kT];
+        CVS_UNROLL
+        for (int j = 0; j < kT; j++) { c[j] = ln.Cprev[j]; c[kT + j] = Cnew[j]; }
+        if (EDGE && (K.flags & F_NOCOLOR)) {                       // :1715: no demod, chroma stays zero
+            CVS_UNROLL
+            for (int j = 0; j < kT; j++) { Yb[j] = c[j]; Ib[j] = 0; Qb[j] = 0; }
+        } else {
+            demod_block<R, EDGE>(rc, k, w, K.amp_back, ln.Cm1, c, Yb, Ib, Qb);   // :1716
+        }
+        ln.Cm1 = ln.Cprev[kT - 1];
+        CVS_UNROLL
+        for (int j = 0; j < kT; j++) ln.Cprev[j] = Cnew[j];
+
+        const int x0 = k * kT;
+        if (K.cnoise != 0) {                                       // :1718-1735
+            CVS_UNROLL
+            for (int j = 0; j < kT; j++) {
+                if (!EDGE || x0 + j < w) {
+                    Ib[j] = N::add(Ib[j], (R)ln.nU);
+                    Qb[j] = N::add(Qb[j], (R)ln.nV);
+                    const uint32_t m = (uint32_t)(2 * K.cnoise + 1);
+                    const int dU = draw_mod(ln.rngC.next_raw(kRngBase + 2u * (uint32_t)(x0 + j)), m, K.cmagic, K.cshift);
+                    ln.nU = noise_step(ln.nU, dU, K.cnoise);
+                    const int dV = draw_mod(ln.rngC.next_raw(kRngBase + 2u * (uint32_t)(x0 + j) + 1u), m, K.cmagic, K.cshift);
+                    ln.nV = noise_step(ln.nV, dV, K.cnoise);
+                }
+            }
+        }
+        if (K.flags & F_PHASE) {                                   // :1736-1764
+            CVS_UNROLL
+            for (int j = 0; j < kT; j++) {
+                const R u = Ib[j], v = Qb[j];
+                Ib[j] = N::rot_a(u, rc.cosp, v, rc.sinp);
+                Qb[j] = N::rot_b(u, rc.sinp, v, rc.cosp);
+            }
+        }
+        if (!VHS) return;
+
+        // VHS luma: 3 poles @ luma_cut reset 16, + 1.6 x highpass, then sharpen (:1793-1812, :1865-1883)
+        // VHS chroma: 3 poles @ chroma_cut, output CD samples early (:1814-1836)
+        R oUcur[kT], oVcur[kT];
+        CVS_UNROLL
+        for (int j = 0; j < kT; j++) {
+            if (!EDGE || x0 + j < w) {
+                R sv = cascade3<R>(ln.pL, Yb[j], K.a_luma, K.b_luma);
+                const R lp = N::pole(ln.pLpre, sv, K.a_luma, K.b_luma);
+                const R y2 = N::boost(sv, N::sub(sv, lp), (R)1.6);
+                const R ts = cascade3<R>(ln.pS, y2, K.a_sharp, K.b_sharp);
+                Yb[j] = N::sharpen(y2, ts, K.sharpen);
+                oUcur[j] = N::trunc_(cascade3<R>(ln.pU, Ib[j], K.a_chroma, K.b_chroma));
+                oVcur[j] = N::trunc_(cascade3<R>(ln.pV, Qb[j], K.a_chroma, K.b_chroma));
+                if (EDGE && (x0 + j >= w - CD) && (x0 + j - (w - CD)) < kTailSlots) {
+                    // the last CD samples keep their pre-filter values (:1830,:1834): stash them
+                    ln.tailU[(x0 + j - (w - CD)) * ln.tail_stride] = Ib[j];
+                    ln.tailV[(x0 + j - (w - CD)) * ln.tail_stride] = Qb[j];
+                }
+            } else {
+                Yb[j] = 0; oUcur[j] = 0; oVcur[j] = 0;
+            }
+        }
+        // delayed chroma block B(s-4): position x' = 8(s-4)+j was produced at time x'+CD
+        CVS_UNROLL
+        for (int j = 0; j < kT; j++) {
+            const int rel = j + CD - 2 * kT;                // index into the current outputs (time in B(s-2))
+            R u = (rel >= 0) ? oUcur[(rel + 2 * kT) % kT] : ln.oUprev[(rel + kT) % kT];
+            R v = (rel >= 0) ? oVcur[(rel + 2 * kT) % kT] : ln.oVprev[(rel + kT) % kT];
+            if (EDGE) {
+                const int xp = (s - 4) * kT + j;
+                if (xp >= w - CD && xp < w && xp >= 0 && (xp - (w - CD)) < kTailSlots) {
+                    u = ln.tailU[(xp - (w - CD)) * ln.tail_stride];
+                    v = ln.tailV[(xp - (w - CD)) * ln.tail_stride];
+                }
+            }
+            xo.u[j] = u;
+            xo.v[j] = v;
+        }
+        CVS_UNROLL
+        for (int j = 0; j < kT; j++) { ln.oUprev[j] = oUcur[j]; ln.oVprev[j] = oVcur[j]; }
+    }
+
+    // ---- B2 + C: vertical blend of B(s-4), remodulate, second demod of B(s-5) -----------------------
+    // xi_ = block received from the row above (pre-blend).  Y3new = Y3 of B(s-2) (from stage_b).
+    // Produces the F-stage input block: B(s-5) (recombine) or B(s-4) (s-video).
+    template <bool EDGE>
+    static CVS_HD void stage_c(const KConst<R> &K, const RowConst<R> &rc, L &ln, int s, const R Y3new[kT],
+                               const BlendXchg<R> &own, const BlendXchg<R> &above,
+                               R Yf[kT], R If[kT], R Qf[kT], int &kf) {
+        const int w = K.w;
+        R U[kT], V[kT];
+        const bool blend = (K.flags & F_VBLEND) && rc.row >= 1;       // loop starts at field+2, :1849
+        const bool have_above = rc.row >= 2;                          // row field+2 blends with zero
+        CVS_UNROLL
+        for (int j = 0; j < kT; j++) {
+            R u = own.u[j], v = own.v[j];
+            if (blend) {                                              // (delay + cur + 1) >> 1, :1857-1858
+                const R au = have_above ? above.u[j] : (R)0, av = have_above ? above.v[j] : (R)0;
+                u = shr1_floor<R>(N::add(N::add(au, u), (R)1));
+                v = shr1_floor<R>(N::add(N::add(av, v), (R)1));
+            }
+            U[j] = u;
+            V[j] = v;
+        }
+        const bool svideo = EDGE && (K.flags & F_SVIDEO);
+        if (svideo) {                                                 // :1885: no recombine
+            kf = s - 4;
+            CVS_UNROLL
+            for (int j = 0; j < kT; j++) { Yf[j] = ln.Y3b[j]; If[j] = U[j]; Qf[j] = V[j]; }
+        } else {
+            kf = s - 5;
+            // C2 of B(s-4) = Y3 + QAM(U,V) with subcarrier_amplitude (:1886)
+            R c[2 * kT];
+            CVS_UNROLL
+            for (int j = 0; j < kT; j++) {
+                const int x = (s - 4) * kT + j;
+                R cv = 0;
+                if (!EDGE || (x >= 0 && x < w))
+                    cv = modulate<R, EDGE>(ln.Y3b[j], U[j], V[j], rc.mI[j & 3], rc.mQ[j & 3], K.amp);
+                c[kT + j] = cv;
+                c[j] = ln.C2prev[j];
+            }
+            if (!EDGE || kf >= 0) {
+                demod_block<R, EDGE>(rc, kf, w, K.amp, ln.C2m1, c, Yf, If, Qf);      // :1887
+            } else {
+                CVS_UNROLL
+                for (int j = 0; j < kT; j++) { Yf[j] = 0; If[j] = 0; Qf[j] = 0; }
+            }
+            ln.C2m1 = ln.C2prev[kT - 1];
+            CVS_UNROLL
+            for (int j = 0; j < kT; j++) ln.C2prev[j] = c[kT + j];
+        }
+        CVS_UNROLL
+        for (int j = 0; j < kT; j++) { ln.Y3b[j] = ln.Y3a[j]; ln.Y3a[j] = Y3new[j]; }
+    }
+
+    // ---- F: dropout, output chroma lowpass, YIQ -> RGB; completes output block B(kf-1) ----------------
+    // Returns true when `out` holds a complete block B(kf-1) (kf >= 1).
+    template <bool EDGE>
+    static CVS_HD bool stage_f(const KConst<R> &K, const RowConst<R> &rc, L &ln, int kf,
+                               R Yf[kT], R If[kT], R Qf[kT], uint32_t out[kT]) {
+        constexpr int OD = L::OD, ODI = L::ODI, ODQ = L::ODQ;
+        const int w = K.w;
+        if (EDGE && kf < 0) return false;
+        const int x0 = kf * kT;
+        if (rc.rflags & RF_DROPOUT) {                                 // :1891-1901
+            CVS_UNROLL
+            for (int j = 0; j < kT; j++) { If[j] = 0; Qf[j] = 0; }
+        }
+        R oI[kT], oQ[kT];
+        CVS_UNROLL
+        for (int j = 0; j < kT; j++) {
+            if (!EDGE || x0 + j < w) {
+                oI[j] = N::trunc_(cascade3<R>(ln.pOI, If[j], K.a_outI, K.b_outI));   // :1420-1422
+                oQ[j] = N::trunc_(cascade3<R>(ln.pOQ, Qf[j], K.a_outQ, K.b_outQ));
+            } else {
+                oI[j] = 0; oQ[j] = 0;
+            }
+        }
+        const bool out_lp = !EDGE || (K.flags & F_OUT_LP);
+        // pixels [x0-OD, x0+8-OD): Y and raw chroma delayed by OD, filtered I by OD-ODI, filtered Q by OD-ODQ
+        uint32_t pk[kT];
+        CVS_UNROLL
+        for (int j = 0; j < kT; j++) {
+            const int pos = x0 - OD + j;
+            // value of an array at absolute offset (j - OD + d) relative to the current block
+            const int iy = j - OD;                // Y / raw chroma index
+            const int ii = j - OD + ODI;          // filtered I index (time = pos + ODI)
+            const int iq = j - OD + ODQ;
+            const R yv = (iy >= 0) ? Yf[(iy + kT) % kT] : ln.Ytail[(iy + OD) % OD];
+            R iv = (ii >= 0) ? oI[(ii + kT) % kT] : ln.oOItail[(ii + OD) % OD];
+            R qv = (iq >= 0) ? oQ[(iq + kT) % kT] : ln.oOQtail[(iq + OD) % OD];
+            if (EDGE) {
+                const R ir = (iy >= 0) ? If[(iy + kT) % kT] : ln.Itail[(iy + OD) % OD];
+                const R qr = (iy >= 0) ? Qf[(iy + kT) % kT] : ln.Qtail[(iy + OD) % OD];
+                if (!out_lp || pos + ODI >= w) iv = ir;       // tail keeps pre-filter values (:1422)
+                if (!out_lp || pos + ODQ >= w) qv = qr;
+            }
+            // YIQ -> RGB (:1385-1396), alpha = 0 (:1914)
+            const int r = clamp255((int)N::mix3(yv, (R)0.956, iv, (R)0.621, qv));
+            const int g = clamp255((int)N::mix3(yv, (R)-0.272, iv, (R)-0.647, qv));
+            const int b = clamp255((int)N::mix3(yv, (R)-1.106, iv, (R)1.703, qv));
+            pk[j] = ((uint32_t)r << 16) | ((uint32_t)g << 8) | (uint32_t)b;
+        }
+        // out block B(kf-1): slots 0..7-OD carried from the previous step, slots 8-OD..7 are pk[0..OD-1]
+        CVS_UNROLL
+        for (int j = 0; j < kT; j++) out[j] = (j < kT - OD) ? ln.outprev[j] : pk[(j - (kT - OD) + kT) % kT];
+        CVS_UNROLL
+        for (int j = 0; j < kT - OD; j++) ln.outprev[j] = pk[j + OD];
+        CVS_UNROLL
+        for (int d = 0; d < OD; d++) {
+            ln.Ytail[d] = Yf[kT - OD + d];
+            ln.Itail[d] = If[kT - OD + d];
+            ln.Qtail[d] = Qf[kT - OD + d];
+            ln.oOItail[d] = oI[kT - OD + d];
+            ln.oOQtail[d] = oQ[kT - OD + d];
+        }
+        return kf >= 1;
+    }
+};
+
+// number of steps a line of width w takes
+template <bool VHS>
+CVS_HD int line_steps(int w) { return (w + kT - 1) / kT + (VHS ? 6 : 3); }
+
+// [s_lo, s_hi): steps in which every touched block is interior, so the fast (non-EDGE) variant
+// is valid: the oldest block B(s-LAG) must have index >= 1 and the newest reads must stay
+// 16 pixels clear of the line end.
+template <bool VHS>
+CVS_HD void interior_steps(int w, int &s_lo, int &s_hi) {
+    s_lo = (VHS ? 6 : 3) + 1;
+    s_hi = (w - 24) / kT;        // 8*s + 8 + 16 <= w
+    if (s_hi < s_lo) s_hi = s_lo;
+}
+
+// ---- row / lane set-up ------------------------------------------------------------------------------
+constexpr int kWarmPx = 64;   // noise warm-up length in pixels (luma: 64 draws, chroma: 128 draws)
+
+// packed per-row side info written by the host (field_plan.cpp): phase-noise state in the low 16 bits
+// (two's complement), row flags in bits 16..23
+CVS_HD uint32_t rowinfo_pack(int phase_state, uint32_t rflags) {
+    return ((uint32_t)phase_state & 0xFFFFu) | (rflags << 16);
+}
+
+// subcarrier phase index of a scanline, ffmpeg_ntsc.cpp:1473-1480
+CVS_HD int line_phase(int phase_shift, int off, unsigned long long fieldno, unsigned y) {
+    if (phase_shift == 90) return (int)((fieldno + (unsigned long long)(long long)off + (y >> 1)) & 3);
+    if (phase_shift == 180) return (int)((((fieldno + y) & 2) + (unsigned long long)(long long)off) & 3);
+    if (phase_shift == 270) return (int)((fieldno + (unsigned long long)(long long)off - (y >> 1)) & 3);
+    return off & 3;
+}
+
+template <typename R>
+CVS_HD void row_setup(const KConst<R> &K, unsigned long long fieldno, int row, uint32_t rowinfo, RowConst<R> &rc) {
+    rc.row = row;
+    rc.rflags = (rowinfo >> 16) & 0xFFu;
+    rowconst_set_phase<R>(rc, line_phase(K.phase_shift, K.phase_offset, fieldno, (unsigned)(K.field + 2 * row)));
+    if (K.flags & F_PHASE) {
+        const int st = (int)(int16_t)(rowinfo & 0xFFFFu);
+        rc.sinp = K.phase_lut[2 * (st + K.pnoise)];
+        rc.cosp = K.phase_lut[2 * (st + K.pnoise) + 1];
+    } else {
+        rc.sinp = 0;
+        rc.cosp = 1;
+    }
+}
+
+// hist_out[k] = sum_i poly[i] * window[k + i]: the 31 raw words preceding position base + J, where
+// poly = x^J and window[i] = q[base - 31 + i]   (glibc_rand.h)
+CVS_HD void rng_rebase(const uint32_t *window, const uint32_t *poly, uint32_t hist_out[31]) {
+    for (int k = 0; k < 31; k++) {
+        uint32_t acc = 0;
+        for (int i = 0; i < 31; i++) acc += poly[i] * window[k + i];
+        hist_out[k] = acc;
+    }
+}
+
+// The noise accumulators carry across rows (:1633,:1720) but each lane starts its row cold.  The
+// update n' = trunc((n + d)/2) is monotone in n, so running it from both ends of the state range
+// [-v, v] over the draws preceding the row brackets the true state; after a few dozen draws the two
+// runs coincide (they merge with probability 1/2 per draw once adjacent) and the state is exact.
+// Returns false if they did not merge (the host then retries from further back).
+CVS_HD bool warm_luma(const uint32_t mod, uint32_t magic, uint32_t shift, int v, LaneRng &g, int ndraws,
+                      bool from_field_start, int &state) {
+    int lo = from_field_start ? 0 : -v, hi = from_field_start ? 0 : v;
+    for (int i = 0; i < ndraws; i++) {
+        const int d = draw_mod(g.next_raw(kRngBase - (uint32_t)ndraws + (uint32_t)i), mod, magic, shift);
+        lo = noise_step(lo, d, v);
+        hi = noise_step(hi, d, v);
+    }
+    state = lo;
+    return lo == hi;
+}
+CVS_HD bool warm_chroma(const uint32_t mod, uint32_t magic, uint32_t shift, int v, LaneRng &g, int npx,
+                        bool from_field_start, int &su, int &sv) {
+    int lou = from_field_start ? 0 : -v, hiu = from_field_start ? 0 : v, lov = lou, hiv = hiu;
+    for (int i = 0; i < npx; i++) {
+        const uint32_t n = kRngBase - 2u * (uint32_t)npx + 2u * (uint32_t)i;
+        const int du = draw_mod(g.next_raw(n), mod, magic, shift);
+        const int dv = draw_mod(g.next_raw(n + 1), mod, magic, shift);
+        lou = noise_step(lou, du, v); hiu = noise_step(hiu, du, v);
+        lov = noise_step(lov, dv, v); hiv = noise_step(hiv, dv, v);
+    }
+    su = lou; sv = lov;
+    return lou == hiu && lov == hiv;
+}
+
+// 8 BGRA pixels of B(k) of a source row; zero beyond the line end
+CVS_HD void load_block_scalar(const uint32_t *srow, int k, int w, uint32_t px[kT]) {
+    CVS_UNROLL
+    for (int j = 0; j < kT; j++) {
+        const int x = k * kT + j;
+        px[j] = (x < w) ? srow[x] : 0u;
+    }
+}
+
+// Head-switch pre-pass (ffmpeg_ntsc.cpp:1683-1700): a rotated row needs random access to the whole
+// composite row, so rows with a non-zero shift get their composite signal (stages A1/A2, including
+// the exact luma noise) computed up front and written, already rotated, to a scratch row; the main
+// pass substitutes it for its own C.  dest[(k - shif) mod twidth] = C[k]; everything else is the
+// zero padding of the reference's tmp[] ring.
+template <typename R>
+CVS_HD void headswitch_row(const KConst<R> &K, const RowConst<R> &rc_in, Lane<R, false, 9, false> &ln,
+                           const uint32_t *srow, int32_t *scratch, int shif) {
+    typedef Pipeline<R, false, 9, false> P;
+    const int w = K.w;
+    const int tw = w + w / 10;
+    RowConst<R> rc = rc_in;
+    rc.rflags &= ~(uint32_t)RF_HEADSW;                 // compute, do not substitute
+    for (int x = 0; x < w; x++) scratch[x] = 0;
+    const int nb = (w + kT - 1) / kT;
+    for (int s = 0; s <= nb; s++) {
+        uint32_t px[kT];
+        load_block_scalar(srow, s, w, px);
+        R C[kT];
+        P::template stage_a<true>(K, rc, ln, s, px, (const int32_t *)0, C);
+        if (s >= 1) {
+            for (int j = 0; j < kT; j++) {
+                const int x = (s - 1) * kT + j;
+                if (x < w) {
+                    int xd = (x - shif) % tw;
+                    if (xd < 0) xd += tw;
+                    if (xd < w) scratch[xd] = (int32_t)C[j];
+                }
+            }
+        }
+    }
+}
+
+}  // namespace cvs
+#endif

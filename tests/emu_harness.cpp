@@ -1,0 +1,191 @@
+// emu_harness.cpp -- TEST INFRASTRUCTURE: runs the product's lane pipeline on the CPU.
+//
+// composite_video_simulator_b200/csrc/lane_pipeline.cuh is host/device portable; this harness
+// drives it exactly the way the CUDA kernels do (one lane per field row, 32 lanes per warp in
+// lock-step, lane 0 = halo row, the vertical-blend exchange done between the two halves of a
+// step) so the kernel LOGIC -- block lags, line-edge quirks, RNG seeking, noise warm-up, the
+// head-switch pre-pass, the host-side planning in field_plan.cpp -- can be checked against the
+// oracle without a GPU: precision 1 (double) must match the oracle bit for bit, precision 0
+// (float) is the production arithmetic and must stay within +-1 LSB.
+// It is never linked into libcvs_ntsc.so and no product entry point reaches it.
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../composite_video_simulator_b200/csrc/field_plan.h"
+#include "../composite_video_simulator_b200/csrc/lane_pipeline.cuh"
+
+using namespace cvs;
+
+namespace {
+
+template <typename R, bool VHS, int CD, bool OUTFULL>
+int run_field(const cvs_params &p, RandCursor &cur, uint8_t *dst, int dst_stride, const uint8_t *src,
+              int src_stride, int w, int h, int interlaced, int tff, unsigned field,
+              unsigned long long fieldno, int force_general) {
+    typedef Lane<R, VHS, CD, OUTFULL> L;
+    typedef Pipeline<R, VHS, CD, OUTFULL> P;
+    GeomPlan g;
+    build_geom_plan(p, w, h, field, g);
+    FieldSide fs;
+    build_field_side(p, g, cur, fs);
+    KConst<R> K;
+    std::vector<R> lut;
+    make_kconst<R>(p, w, h, field, OUTFULL, K, lut);
+    if (force_general) K.flags |= F_GENERAL;
+    const int nl = g.nl;
+    const int opposite = interlaced ? (tff ? 1 : 0) : 0;
+    auto src_row = [&](int row) {
+        int sy = (int)field + 2 * row + opposite;
+        if (sy > h - 1) sy = h - 1;
+        return (const uint32_t *)(src + (size_t)src_stride * (size_t)sy);
+    };
+
+    // head-switch pre-pass
+    std::vector<int32_t> scratch((size_t)(fs.hs_count > 0 ? fs.hs_count : 1) * (size_t)w);
+    for (int i = 0; i < fs.hs_count; i++) {
+        const int row = fs.hs_first + i;
+        Lane<R, false, 9, false> ln;
+        ln.reset(K);
+        RowConst<R> rc;
+        row_setup<R>(K, fieldno, row, fs.rowinfo[(size_t)row], rc);
+        uint32_t ring[kRngSlots];
+        if (K.vnoise != 0) {
+            uint32_t hist[31];
+            rng_rebase(fs.window, &g.seek[(size_t)row * 62], hist);
+            const int nd = warm_draws_luma(row, w);
+            ln.rngL.init(ring, 1, hist, kRngBase - (uint32_t)nd);
+            ln.nY = 0;
+            if (!warm_luma((uint32_t)(2 * K.vnoise + 1), K.vmagic, K.vshift, K.vnoise, ln.rngL, nd,
+                           (long long)row * w <= kWarmPx, ln.nY))
+                return CVS_ERR_NOISE_SYNC;
+        }
+        headswitch_row<R>(K, rc, ln, src_row(row), &scratch[(size_t)i * w], fs.hs_shift[(size_t)i]);
+    }
+
+    const int nwarps = (nl + 30) / 31;
+    const int nsteps = line_steps<VHS>(w);
+    int s_lo, s_hi;
+    interior_steps<VHS>(w, s_lo, s_hi);
+    std::vector<uint32_t> rings((size_t)32 * 2 * kRngSlots);
+    std::vector<R> tails((size_t)32 * 2 * kTailSlots);
+    for (int wp = 0; wp < nwarps; wp++) {
+        L lane[32];
+        RowConst<R> rc[32];
+        const uint32_t *srow[32];
+        uint32_t *drow[32];
+        const int32_t *hsrow[32];
+        bool valid[32];
+        for (int l = 0; l < 32; l++) {
+            int row = 31 * wp + l - 1;
+            valid[l] = (l >= 1) && row < nl;
+            if (row < 0) row = 0;
+            if (row > nl - 1) row = nl - 1;
+            L &ln = lane[l];
+            ln.reset(K);
+            row_setup<R>(K, fieldno, row, fs.rowinfo[(size_t)row], rc[l]);
+            srow[l] = src_row(row);
+            drow[l] = (uint32_t *)(dst + (size_t)dst_stride * (size_t)((int)field + 2 * row));
+            hsrow[l] = (rc[l].rflags & RF_HEADSW) ? &scratch[(size_t)(row - fs.hs_first) * w] : (const int32_t *)0;
+            ln.tailU = &tails[(size_t)l * 2 * kTailSlots];
+            ln.tailV = ln.tailU + kTailSlots;
+            ln.tail_stride = 1;
+            ln.nY = ln.nU = ln.nV = 0;
+            const int nd = warm_draws_luma(row, w);
+            const bool from_start = (long long)row * w <= kWarmPx;
+            uint32_t hist[31];
+            if (K.vnoise != 0) {
+                rng_rebase(fs.window, &g.seek[(size_t)row * 62], hist);
+                ln.rngL.init(&rings[(size_t)l * 2 * kRngSlots], 1, hist, kRngBase - (uint32_t)nd);
+                if (!warm_luma((uint32_t)(2 * K.vnoise + 1), K.vmagic, K.vshift, K.vnoise, ln.rngL, nd, from_start, ln.nY))
+                    return CVS_ERR_NOISE_SYNC;
+            }
+            if (K.cnoise != 0) {
+                rng_rebase(fs.window, &g.seek[(size_t)row * 62 + 31], hist);
+                ln.rngC.init(&rings[(size_t)l * 2 * kRngSlots + kRngSlots], 1, hist, kRngBase - 2u * (uint32_t)nd);
+                if (!warm_chroma((uint32_t)(2 * K.cnoise + 1), K.cmagic, K.cshift, K.cnoise, ln.rngC, nd, from_start, ln.nU, ln.nV))
+                    return CVS_ERR_NOISE_SYNC;
+            }
+        }
+        for (int s = 0; s < nsteps; s++) {
+            const bool fast = !(K.flags & F_GENERAL) && s >= s_lo && s < s_hi;
+            BlendXchg<R> xo[32];
+            R Yb[32][kT], Ib[32][kT], Qb[32][kT];
+            for (int l = 0; l < 32; l++) {
+                uint32_t px[kT];
+                load_block_scalar(srow[l], s, w, px);
+                R C[kT];
+                if (fast) {
+                    P::template stage_a<false>(K, rc[l], lane[l], s, px, hsrow[l], C);
+                    P::template stage_b<false>(K, rc[l], lane[l], s, C, Yb[l], Ib[l], Qb[l], xo[l]);
+                } else {
+                    P::template stage_a<true>(K, rc[l], lane[l], s, px, hsrow[l], C);
+                    P::template stage_b<true>(K, rc[l], lane[l], s, C, Yb[l], Ib[l], Qb[l], xo[l]);
+                }
+            }
+            for (int l = 0; l < 32; l++) {
+                R Yf[kT], If[kT], Qf[kT];
+                int kf;
+                uint32_t out[kT];
+                bool have;
+                if (VHS) {
+                    const BlendXchg<R> &above = xo[l > 0 ? l - 1 : 0];
+                    if (fast) {
+                        P::template stage_c<false>(K, rc[l], lane[l], s, Yb[l], xo[l], above, Yf, If, Qf, kf);
+                        have = P::template stage_f<false>(K, rc[l], lane[l], kf, Yf, If, Qf, out);
+                    } else {
+                        P::template stage_c<true>(K, rc[l], lane[l], s, Yb[l], xo[l], above, Yf, If, Qf, kf);
+                        have = P::template stage_f<true>(K, rc[l], lane[l], kf, Yf, If, Qf, out);
+                    }
+                } else {
+                    kf = s - 2;
+                    if (fast) have = P::template stage_f<false>(K, rc[l], lane[l], kf, Yb[l], Ib[l], Qb[l], out);
+                    else have = P::template stage_f<true>(K, rc[l], lane[l], kf, Yb[l], Ib[l], Qb[l], out);
+                }
+                if (have && valid[l]) {
+                    const int x0 = (kf - 1) * kT;
+                    for (int j = 0; j < kT; j++)
+                        if (x0 + j < w) drow[l][x0 + j] = out[j];
+                }
+            }
+        }
+    }
+    return 0;
+}
+
+template <typename R>
+int dispatch(const cvs_params &p, RandCursor &cur, uint8_t *dst, int dst_stride, const uint8_t *src,
+             int src_stride, int w, int h, int interlaced, int tff, unsigned field,
+             unsigned long long fieldno, int force_general) {
+    const Variant v = pick_variant(p);
+#define CVS_RUN(VHS, CD, OF) \
+    return run_field<R, VHS, CD, OF>(p, cur, dst, dst_stride, src, src_stride, w, h, interlaced, tff, field, fieldno, force_general)
+    if (!v.vhs) { if (v.outfull) CVS_RUN(false, 9, true); else CVS_RUN(false, 9, false); }
+    if (v.cd == 9) { if (v.outfull) CVS_RUN(true, 9, true); else CVS_RUN(true, 9, false); }
+    if (v.cd == 12) { if (v.outfull) CVS_RUN(true, 12, true); else CVS_RUN(true, 12, false); }
+    if (v.outfull) CVS_RUN(true, 14, true); else CVS_RUN(true, 14, false);
+#undef CVS_RUN
+}
+
+}  // namespace
+
+extern "C" {
+
+// precision: 0 = float (production arithmetic), 1 = double (reference arithmetic).
+// rng_pos in/out: absolute rand() position (draws since the default seed).
+int emu_composite_layer(const cvs_params *p, int precision, unsigned long long *rng_pos,
+                        uint8_t *dst, int dst_stride, const uint8_t *src, int src_stride,
+                        int w, int h, int interlaced, int tff, unsigned field, unsigned long long fieldno,
+                        int force_general) {
+    if (!p || !dst || !src || w <= 0 || h <= 0 || dst_stride < 4 * w || src_stride < 4 * w) return CVS_ERR_INVALID_ARG;
+    static RandCursor cur;
+    cur.seek(*rng_pos);
+    int rc;
+    if (precision) rc = dispatch<double>(*p, cur, dst, dst_stride, src, src_stride, w, h, interlaced, tff, field, fieldno, force_general);
+    else rc = dispatch<float>(*p, cur, dst, dst_stride, src, src_stride, w, h, interlaced, tff, field, fieldno, force_general);
+    *rng_pos = cur.pos();
+    return rc;
+}
+
+}  // extern "C"
