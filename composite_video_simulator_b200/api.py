@@ -1,0 +1,145 @@
+"""Host-side mirror of the reference's interface for the composite_layer() path.
+
+The reference exposes no API; its seam is the call
+``composite_layer(dst, src, inputfile, field, fieldno)`` (ffmpeg_ntsc.cpp:2229) configured by CLI
+switches (parse_argv, ffmpeg_ntsc.cpp:972-1282).  ``Engine`` mirrors exactly that: it is built from
+an argv list with the reference's switch names, ``composite_layer`` takes the same arguments (BGRA
+pictures as ``uint32[h, w]`` arrays instead of AVFrames) and writes only the rows of the requested
+field, and the hidden libc ``rand()`` position is an explicit ``rng_seek``/``rng_tell``.
+
+Everything is a thin ctypes call into libcvs_ntsc.so (the CUDA engine); nothing is computed here.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .params import CvsParams
+
+
+class CvsError(RuntimeError):
+    def __init__(self, status, what=""):
+        self.status = status
+        msg = _lib.load().cvs_strerror(status).decode()
+        super().__init__("%s%s (status %d)" % (what + ": " if what else "", msg, status))
+
+
+def _check(status, what=""):
+    if status != 0:
+        raise CvsError(status, what)
+
+
+def default_params():
+    """preset_NTSC() + the global initialisers of ffmpeg_ntsc.cpp."""
+    p = CvsParams()
+    _check(_lib.load().cvs_params_default_ntsc(C.byref(p)), "cvs_params_default_ntsc")
+    return p
+
+
+def params_from_argv(argv, base=None):
+    """Apply reference CLI switches (e.g. ``["-vhs", "-vhs-speed", "ep"]``) in order."""
+    p = base.copy() if base is not None else default_params()
+    args = [b"ffmpeg_ntsc"] + [a.encode() if isinstance(a, str) else a for a in argv]
+    arr = (C.c_char_p * len(args))(*args)
+    _check(_lib.load().cvs_params_apply_argv(C.byref(p), len(args), arr), "cvs_params_apply_argv")
+    return p
+
+
+def draws_per_field(params, w, h, field):
+    return int(_lib.load().cvs_draws_per_field(C.byref(params), w, h, field))
+
+
+def _ptr(a):
+    """Raw address of a numpy array, a torch tensor or an int."""
+    if isinstance(a, int):
+        return a
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    raise TypeError("expected a numpy array, a torch tensor or an address")
+
+
+class Engine:
+    """One CUDA scanline engine (context of the C ABI) bound to one device."""
+
+    def __init__(self, argv=(), params=None, device=0, max_w=1920, max_h=1080, max_batch=64):
+        self.lib = _lib.load()
+        self.params = params.copy() if params is not None else params_from_argv(list(argv))
+        self._ctx = C.c_void_p()
+        _check(self.lib.cvs_create(C.byref(self._ctx), C.byref(self.params), device, max_w, max_h, max_batch),
+               "cvs_create")
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx:
+            self.lib.cvs_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- configuration -------------------------------------------------------------------------
+    def set_params(self, params):
+        _check(self.lib.cvs_set_params(self._ctx, C.byref(params)), "cvs_set_params")
+        self.params = params.copy()
+
+    def set_precision(self, use_double):
+        _check(self.lib.cvs_set_precision(self._ctx, 1 if use_double else 0), "cvs_set_precision")
+
+    def rng_seek(self, draws_consumed):
+        _check(self.lib.cvs_rng_seek(self._ctx, draws_consumed), "cvs_rng_seek")
+
+    def rng_tell(self):
+        v = C.c_ulonglong()
+        _check(self.lib.cvs_rng_tell(self._ctx, C.byref(v)), "cvs_rng_tell")
+        return v.value
+
+    # -- the seam ---------------------------------------------------------------------------------
+    def composite_layer(self, dst, src, field, fieldno, src_interlaced=False, src_top_field_first=False,
+                        dst_stride=None, src_stride=None):
+        """ffmpeg_ntsc.cpp:2229: dst/src are uint32[h, w] BGRA host pictures; writes rows y = field (mod 2)."""
+        h, w = src.shape[:2]
+        _check(self.lib.cvs_composite_layer(self._ctx, _ptr(dst), dst_stride or dst.strides[0], _ptr(src),
+                                            src_stride or src.strides[0], w, h, int(src_interlaced),
+                                            int(src_top_field_first), field, fieldno), "cvs_composite_layer")
+
+    # -- throughput forms -----------------------------------------------------------------------------
+    def composite_fields_host(self, dst, src, first_fieldno, src_interlaced=False, src_top_field_first=False):
+        """dst/src: uint32[n, h, w] host arrays (pinned for full PCIe speed)."""
+        n, h, w = src.shape
+        _check(self.lib.cvs_composite_fields_host(self._ctx, _ptr(dst), dst.strides[0], dst.strides[1], _ptr(src),
+                                                  src.strides[0], src.strides[1], w, h, int(src_interlaced),
+                                                  int(src_top_field_first), n, first_fieldno),
+               "cvs_composite_fields_host")
+
+    def composite_fields_device(self, dst, src, n, h, w, first_fieldno, dst_pic_stride=None, dst_stride=None,
+                                src_pic_stride=None, src_stride=None, src_interlaced=False,
+                                src_top_field_first=False):
+        """dst/src: device addresses (or torch CUDA tensors) of n packed BGRA pictures; asynchronous."""
+        ss = src_stride or 4 * w
+        ds = dst_stride or 4 * w
+        _check(self.lib.cvs_composite_fields_device(self._ctx, _ptr(dst), dst_pic_stride or ds * h, ds, _ptr(src),
+                                                    src_pic_stride or ss * h, ss, w, h, int(src_interlaced),
+                                                    int(src_top_field_first), n, first_fieldno),
+               "cvs_composite_fields_device")
+
+    def synchronize(self):
+        _check(self.lib.cvs_synchronize(self._ctx), "cvs_synchronize")
+
+    def kernel_launches(self):
+        return int(self.lib.cvs_kernel_launches(self._ctx))
+
+    def last_kernel_ms(self):
+        v = C.c_float()
+        _check(self.lib.cvs_last_kernel_ms(self._ctx, C.byref(v)), "cvs_last_kernel_ms")
+        return v.value

@@ -1,0 +1,463 @@
+// cvs_api.cu -- the C ABI of include/cvs_ntsc.h on top of the scanline kernels.
+//
+// Host side of the drop-in boundary: owns the CUDA stream, the device-side tables and the
+// position in the libc rand() stream (the reference's only hidden state across
+// composite_layer() calls), plans each batch (field_plan.cpp) and
+// launches k_headswitch + k_fields.  Nothing here computes pixels on the CPU: if CUDA is not
+// usable every compute entry point fails with CVS_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <new>
+#include <vector>
+
+#include "../../include/cvs_ntsc.h"
+#include "field_plan.h"
+#include "glibc_rand.h"
+#include "scanline_kernels.cuh"
+
+using namespace cvs;
+
+namespace {
+
+constexpr int kStagingSlots = 3;
+
+struct DevPlan {
+    int w = 0, h = 0;
+    unsigned field = 0;
+    GeomPlan g;
+    uint32_t *d_seek = nullptr;
+};
+
+struct Staging {
+    FieldDesc *h_fields = nullptr;     // pinned
+    uint32_t *h_rowinfo = nullptr;
+    int32_t *h_hsshift = nullptr;
+    HsItem *h_items = nullptr;
+    cudaEvent_t consumed = nullptr;    // the H2D copies that read this slot have finished
+    bool in_flight = false;
+};
+
+template <typename T>
+cudaError_t dev_alloc(T **p, size_t n) { return cudaMalloc((void **)p, n * sizeof(T)); }
+template <typename T>
+cudaError_t pin_alloc(T **p, size_t n) { return cudaMallocHost((void **)p, n * sizeof(T)); }
+
+}  // namespace
+
+struct cvs_ctx {
+    cvs_params p;
+    int device = 0;
+    int max_w = 0, max_h = 0, max_batch = 0, nl_max = 0, hs_max = 0;
+    int precision = 0;                         // 0 = float (production), 1 = double (reference arithmetic)
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ev_valid = false;
+    RandCursor cur;
+    std::vector<std::unique_ptr<DevPlan>> plans;
+    Staging slots[kStagingSlots];
+    int next_slot = 0;
+    // device side tables (single copy: all writers/readers are ordered on `stream`)
+    FieldDesc *d_fields = nullptr;
+    uint32_t *d_rowinfo = nullptr;
+    int32_t *d_hsshift = nullptr;
+    HsItem *d_items = nullptr;
+    int32_t *d_scratch = nullptr;
+    int32_t *d_status = nullptr;
+    int32_t *h_status = nullptr;               // pinned
+    float *d_lut_f = nullptr;
+    double *d_lut_d = nullptr;
+    size_t lut_cap = 0;
+    bool lut_dirty = true;
+    // device pictures for the host-pointer entry points
+    uint8_t *d_src = nullptr, *d_dst = nullptr;
+    size_t d_pic_cap = 0;
+    unsigned long long launches = 0;
+};
+
+namespace {
+
+#define CVS_CUDA(x)                                  \
+    do {                                             \
+        cudaError_t e_ = (x);                        \
+        if (e_ != cudaSuccess) return CVS_ERR_CUDA;  \
+    } while (0)
+
+int head_switch_rows_bound(int w) {
+    // rows rotated by one head switch: the shift starts at |ishif| <= twidth/2 and decays by 7/8
+    // (truncating) per row until it reaches zero, ffmpeg_ntsc.cpp:1704-1707
+    int shif = (w + w / 10) / 2 + 1, n = 0;
+    while (shif != 0) { shif = (shif * 7) / 8; n++; }
+    return n + 1;
+}
+
+void free_all(cvs_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (auto &pl : c->plans) if (pl && pl->d_seek) cudaFree(pl->d_seek);
+    c->plans.clear();
+    for (auto &s : c->slots) {
+        if (s.h_fields) cudaFreeHost(s.h_fields);
+        if (s.h_rowinfo) cudaFreeHost(s.h_rowinfo);
+        if (s.h_hsshift) cudaFreeHost(s.h_hsshift);
+        if (s.h_items) cudaFreeHost(s.h_items);
+        if (s.consumed) cudaEventDestroy(s.consumed);
+        s = Staging();
+    }
+    cudaFree(c->d_fields); cudaFree(c->d_rowinfo); cudaFree(c->d_hsshift); cudaFree(c->d_items);
+    cudaFree(c->d_scratch); cudaFree(c->d_status); cudaFree(c->d_lut_f); cudaFree(c->d_lut_d);
+    cudaFree(c->d_src); cudaFree(c->d_dst);
+    if (c->h_status) cudaFreeHost(c->h_status);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+}
+
+int get_plan(cvs_ctx *c, int w, int h, unsigned field, DevPlan **out) {
+    for (auto &pl : c->plans)
+        if (pl->w == w && pl->h == h && pl->field == field) { *out = pl.get(); return CVS_OK; }
+    std::unique_ptr<DevPlan> pl(new (std::nothrow) DevPlan());
+    if (!pl) return CVS_ERR_NOMEM;
+    pl->w = w; pl->h = h; pl->field = field;
+    build_geom_plan(c->p, w, h, field, pl->g);
+    const size_t words = pl->g.seek.size() > 0 ? pl->g.seek.size() : 1;
+    CVS_CUDA(dev_alloc(&pl->d_seek, words));
+    if (!pl->g.seek.empty())
+        CVS_CUDA(cudaMemcpyAsync(pl->d_seek, pl->g.seek.data(), pl->g.seek.size() * sizeof(uint32_t),
+                                 cudaMemcpyHostToDevice, c->stream));
+    CVS_CUDA(cudaStreamSynchronize(c->stream));     // g.seek is pageable: finish before anyone can drop it
+    *out = pl.get();
+    c->plans.push_back(std::move(pl));
+    return CVS_OK;
+}
+
+template <typename R>
+cudaError_t launch_variant(const Variant &v, const LaunchArgs<R> &a, cudaStream_t st);
+
+template <>
+cudaError_t launch_variant<float>(const Variant &v, const LaunchArgs<float> &a, cudaStream_t st) {
+    if (!v.vhs) return v.outfull ? launch_fields<float, false, 9, true>(a, st) : launch_fields<float, false, 9, false>(a, st);
+    if (v.cd == 9) return v.outfull ? launch_fields<float, true, 9, true>(a, st) : launch_fields<float, true, 9, false>(a, st);
+    if (v.cd == 12) return v.outfull ? launch_fields<float, true, 12, true>(a, st) : launch_fields<float, true, 12, false>(a, st);
+    return v.outfull ? launch_fields<float, true, 14, true>(a, st) : launch_fields<float, true, 14, false>(a, st);
+}
+template <>
+cudaError_t launch_variant<double>(const Variant &v, const LaunchArgs<double> &a, cudaStream_t st) {
+    if (!v.vhs) return v.outfull ? launch_fields<double, false, 9, true>(a, st) : launch_fields<double, false, 9, false>(a, st);
+    if (v.cd == 9) return v.outfull ? launch_fields<double, true, 9, true>(a, st) : launch_fields<double, true, 9, false>(a, st);
+    if (v.cd == 12) return v.outfull ? launch_fields<double, true, 12, true>(a, st) : launch_fields<double, true, 12, false>(a, st);
+    return v.outfull ? launch_fields<double, true, 14, true>(a, st) : launch_fields<double, true, 14, false>(a, st);
+}
+
+template <typename R> R *&lut_ptr(cvs_ctx *c);
+template <> float *&lut_ptr<float>(cvs_ctx *c) { return c->d_lut_f; }
+template <> double *&lut_ptr<double>(cvs_ctx *c) { return c->d_lut_d; }
+
+template <typename R>
+int launch_batch(cvs_ctx *c, const Variant &v, int w, int h, int nfields, int max_nl, int nitems,
+                 int src_stride, int dst_stride, int opposite, bool vec_src, bool vec_dst) {
+    LaunchArgs<R> a;
+    std::vector<R> lut;
+    make_kconst<R>(c->p, w, h, v.outfull, a.K, lut);
+    if (lut.size() > c->lut_cap || !lut_ptr<R>(c)) {
+        if (lut_ptr<R>(c)) { CVS_CUDA(cudaStreamSynchronize(c->stream)); cudaFree(lut_ptr<R>(c)); lut_ptr<R>(c) = nullptr; }
+        CVS_CUDA(dev_alloc(&lut_ptr<R>(c), lut.size() + 2));
+        c->lut_cap = lut.size() + 2;
+        c->lut_dirty = true;
+    }
+    if (c->lut_dirty) {
+        CVS_CUDA(cudaMemcpyAsync(lut_ptr<R>(c), lut.data(), lut.size() * sizeof(R), cudaMemcpyHostToDevice, c->stream));
+        CVS_CUDA(cudaStreamSynchronize(c->stream));   // `lut` is a pageable temporary
+        c->lut_dirty = false;
+    }
+    a.K.phase_lut = lut_ptr<R>(c);
+    a.fields = c->d_fields;
+    a.nfields = nfields;
+    a.warps_per_field = (max_nl + kRowsPerWarp - 1) / kRowsPerWarp;
+    a.total_warps = a.warps_per_field * nfields;
+    a.src_stride = src_stride;
+    a.dst_stride = dst_stride;
+    a.opposite = opposite;
+    a.vec_src = vec_src;
+    a.vec_dst = vec_dst;
+    a.status = c->d_status;
+    CVS_CUDA(cudaEventRecord(c->ev0, c->stream));
+    if (nitems > 0) {
+        CVS_CUDA(launch_headswitch<R>(a, c->d_items, nitems, c->stream));
+        c->launches++;
+    }
+    CVS_CUDA(launch_variant<R>(v, a, c->stream));
+    c->launches++;
+    CVS_CUDA(cudaEventRecord(c->ev1, c->stream));
+    c->ev_valid = true;
+    return CVS_OK;
+}
+
+// Plan + launch n fields whose pictures are device-resident.  explicit_field < 0 => the
+// reference loop's schedule field = ((fieldno) & 1) ^ 1  (ffmpeg_ntsc.cpp:2229).
+int run_device(cvs_ctx *c, uint8_t *dst, size_t dst_pic_stride, int dst_stride, const uint8_t *src,
+               size_t src_pic_stride, int src_stride, int w, int h, int interlaced, int tff, int n,
+               unsigned long long first_fieldno, int explicit_field) {
+    if (!c || !dst || !src) return CVS_ERR_INVALID_ARG;
+    if (w <= 0 || h <= 0 || n < 0) return CVS_ERR_INVALID_ARG;
+    if (dst_stride < 4 * w || src_stride < 4 * w) return CVS_ERR_INVALID_ARG;          // :1580-1581
+    if ((dst_stride & 3) || (src_stride & 3) || ((uintptr_t)dst & 3) || ((uintptr_t)src & 3)) return CVS_ERR_INVALID_ARG;
+    if (w > c->max_w || h > c->max_h || n > c->max_batch) return CVS_ERR_CAPACITY;
+    if (n == 0) return CVS_OK;
+    if (cudaSetDevice(c->device) != cudaSuccess) return CVS_ERR_CUDA;
+
+    const Variant v = pick_variant(c->p);
+    Staging &sl = c->slots[c->next_slot];
+    c->next_slot = (c->next_slot + 1) % kStagingSlots;
+    if (sl.in_flight) { CVS_CUDA(cudaEventSynchronize(sl.consumed)); sl.in_flight = false; }
+
+    const int opposite = interlaced ? (tff ? 1 : 0) : 0;                               // :1585-1588
+    int nitems = 0, max_nl = 0;
+    FieldSide fs;
+    for (int k = 0; k < n; k++) {
+        const unsigned long long fieldno = first_fieldno + (unsigned long long)k;
+        const unsigned field = explicit_field >= 0 ? (unsigned)explicit_field : (unsigned)((fieldno & 1) ^ 1);
+        FieldDesc &fd = sl.h_fields[k];
+        std::memset(&fd, 0, sizeof(fd));
+        fd.src = src + (size_t)k * src_pic_stride;
+        fd.dst = dst + (size_t)k * dst_pic_stride;
+        fd.fieldno = fieldno;
+        fd.field = (int32_t)field;
+        if ((int)field >= h) { fd.nl = 0; continue; }      // no rows of this parity: nothing drawn, nothing written
+        DevPlan *pl = nullptr;
+        int rc = get_plan(c, w, h, field, &pl);
+        if (rc != CVS_OK) return rc;
+        build_field_side(c->p, pl->g, c->cur, fs);
+        fd.nl = pl->g.nl;
+        if (fd.nl > max_nl) max_nl = fd.nl;
+        fd.seek = pl->d_seek;
+        fd.rowinfo = c->d_rowinfo + (size_t)k * c->nl_max;
+        std::memcpy(sl.h_rowinfo + (size_t)k * c->nl_max, fs.rowinfo.data(), fs.rowinfo.size() * sizeof(uint32_t));
+        std::memcpy(fd.window, fs.window, sizeof(fs.window));
+        fd.hs_first = fs.hs_first;
+        fd.hs_count = fs.hs_count;
+        if (fs.hs_count > c->hs_max) return CVS_ERR_CAPACITY;
+        fd.hs_scratch = c->d_scratch + (size_t)k * c->hs_max * (size_t)c->max_w;
+        fd.hs_shift = c->d_hsshift + (size_t)k * c->hs_max;
+        for (int i = 0; i < fs.hs_count; i++) {
+            sl.h_hsshift[(size_t)k * c->hs_max + i] = fs.hs_shift[(size_t)i];
+            sl.h_items[nitems].field_idx = k;
+            sl.h_items[nitems].slot = i;
+            nitems++;
+        }
+    }
+    if (max_nl == 0) return CVS_OK;
+
+    CVS_CUDA(cudaMemcpyAsync(c->d_fields, sl.h_fields, (size_t)n * sizeof(FieldDesc), cudaMemcpyHostToDevice, c->stream));
+    CVS_CUDA(cudaMemcpyAsync(c->d_rowinfo, sl.h_rowinfo, (size_t)n * c->nl_max * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    if (nitems > 0) {
+        CVS_CUDA(cudaMemcpyAsync(c->d_hsshift, sl.h_hsshift, (size_t)n * c->hs_max * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        CVS_CUDA(cudaMemcpyAsync(c->d_items, sl.h_items, (size_t)nitems * sizeof(HsItem), cudaMemcpyHostToDevice, c->stream));
+    }
+    CVS_CUDA(cudaEventRecord(sl.consumed, c->stream));
+    sl.in_flight = true;
+
+    const bool vec_src = ((uintptr_t)src % 16 == 0) && (src_stride % 16 == 0) && (src_pic_stride % 16 == 0);
+    const bool vec_dst = ((uintptr_t)dst % 16 == 0) && (dst_stride % 16 == 0) && (dst_pic_stride % 16 == 0);
+    if (c->precision)
+        return launch_batch<double>(c, v, w, h, n, max_nl, nitems, src_stride, dst_stride, opposite, vec_src, vec_dst);
+    return launch_batch<float>(c, v, w, h, n, max_nl, nitems, src_stride, dst_stride, opposite, vec_src, vec_dst);
+}
+
+int check_status(cvs_ctx *c) {
+    CVS_CUDA(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CVS_CUDA(cudaStreamSynchronize(c->stream));
+    if (*c->h_status != 0) {
+        CVS_CUDA(cudaMemsetAsync(c->d_status, 0, sizeof(int32_t), c->stream));
+        return CVS_ERR_NOISE_SYNC;
+    }
+    return CVS_OK;
+}
+
+int run_host(cvs_ctx *c, uint8_t *dst, size_t dst_pic_stride, int dst_stride, const uint8_t *src,
+             size_t src_pic_stride, int src_stride, int w, int h, int interlaced, int tff, int n,
+             unsigned long long first_fieldno, int explicit_field) {
+    if (!c || !dst || !src) return CVS_ERR_INVALID_ARG;
+    if (w <= 0 || h <= 0 || n < 0) return CVS_ERR_INVALID_ARG;
+    if (dst_stride < 4 * w || src_stride < 4 * w) return CVS_ERR_INVALID_ARG;
+    if (w > c->max_w || h > c->max_h || n > c->max_batch) return CVS_ERR_CAPACITY;
+    if (n == 0) return CVS_OK;
+    if (cudaSetDevice(c->device) != cudaSuccess) return CVS_ERR_CUDA;
+    // device pictures: rows padded to 16 bytes, full height (only the field rows are transferred)
+    const int dstride = ((4 * w + 15) / 16) * 16;
+    const size_t dpic = (size_t)dstride * (size_t)h;
+    if (dpic * (size_t)n > c->d_pic_cap) {
+        CVS_CUDA(cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_src); cudaFree(c->d_dst);
+        c->d_src = c->d_dst = nullptr;
+        c->d_pic_cap = 0;
+        CVS_CUDA(cudaMalloc((void **)&c->d_src, dpic * (size_t)n));
+        CVS_CUDA(cudaMalloc((void **)&c->d_dst, dpic * (size_t)n));
+        c->d_pic_cap = dpic * (size_t)n;
+    }
+    const int opposite = interlaced ? (tff ? 1 : 0) : 0;
+    for (int k = 0; k < n; k++) {
+        const unsigned long long fieldno = first_fieldno + (unsigned long long)k;
+        const int field = explicit_field >= 0 ? explicit_field : (int)((fieldno & 1) ^ 1);
+        if (field >= h) continue;
+        const int nl = (h - field + 1) / 2;
+        // source rows min(field + 2r + opposite, h-1): a stride-2 run, plus the clamped last row (:1599)
+        const int y0 = field + opposite;
+        int nreg = nl;
+        if (y0 + 2 * (nl - 1) > h - 1) nreg = nl - 1;
+        const uint8_t *hs = src + (size_t)k * src_pic_stride;
+        uint8_t *ds = c->d_src + (size_t)k * dpic;
+        if (nreg > 0)
+            CVS_CUDA(cudaMemcpy2DAsync(ds + (size_t)y0 * dstride, (size_t)2 * dstride, hs + (size_t)y0 * src_stride,
+                                       (size_t)2 * src_stride, (size_t)4 * w, (size_t)nreg, cudaMemcpyHostToDevice, c->stream));
+        if (nreg < nl)
+            CVS_CUDA(cudaMemcpyAsync(ds + (size_t)(h - 1) * dstride, hs + (size_t)(h - 1) * src_stride, (size_t)4 * w,
+                                     cudaMemcpyHostToDevice, c->stream));
+    }
+    int rc = run_device(c, c->d_dst, dpic, dstride, c->d_src, dpic, dstride, w, h, interlaced, tff, n, first_fieldno, explicit_field);
+    if (rc != CVS_OK) return rc;
+    for (int k = 0; k < n; k++) {
+        const unsigned long long fieldno = first_fieldno + (unsigned long long)k;
+        const int field = explicit_field >= 0 ? explicit_field : (int)((fieldno & 1) ^ 1);
+        if (field >= h) continue;
+        const int nl = (h - field + 1) / 2;
+        CVS_CUDA(cudaMemcpy2DAsync(dst + (size_t)k * dst_pic_stride + (size_t)field * dst_stride, (size_t)2 * dst_stride,
+                                   c->d_dst + (size_t)k * dpic + (size_t)field * dstride, (size_t)2 * dstride,
+                                   (size_t)4 * w, (size_t)nl, cudaMemcpyDeviceToHost, c->stream));
+    }
+    return check_status(c);
+}
+
+}  // namespace
+
+extern "C" {
+
+int cvs_create(cvs_ctx **out, const cvs_params *p, int device, int max_w, int max_h, int max_batch) {
+    if (!out || !p || max_w <= 0 || max_h <= 0 || max_batch <= 0) return CVS_ERR_INVALID_ARG;
+    if (p->struct_size != (int32_t)sizeof(cvs_params)) return CVS_ERR_INVALID_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return CVS_ERR_CUDA;   // no CPU fallback
+    if (device < 0 || device >= ndev) return CVS_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return CVS_ERR_CUDA;
+    cvs_ctx *c = new (std::nothrow) cvs_ctx();
+    if (!c) return CVS_ERR_NOMEM;
+    c->p = *p;
+    c->device = device;
+    c->max_w = max_w; c->max_h = max_h; c->max_batch = max_batch;
+    c->nl_max = (max_h + 1) / 2;
+    c->hs_max = head_switch_rows_bound(max_w);
+    if (c->hs_max > c->nl_max) c->hs_max = c->nl_max;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    for (auto &s : c->slots) {
+        if (e == cudaSuccess) e = pin_alloc(&s.h_fields, (size_t)max_batch);
+        if (e == cudaSuccess) e = pin_alloc(&s.h_rowinfo, (size_t)max_batch * c->nl_max);
+        if (e == cudaSuccess) e = pin_alloc(&s.h_hsshift, (size_t)max_batch * c->hs_max);
+        if (e == cudaSuccess) e = pin_alloc(&s.h_items, (size_t)max_batch * c->hs_max);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = dev_alloc(&c->d_fields, (size_t)max_batch);
+    if (e == cudaSuccess) e = dev_alloc(&c->d_rowinfo, (size_t)max_batch * c->nl_max);
+    if (e == cudaSuccess) e = dev_alloc(&c->d_hsshift, (size_t)max_batch * c->hs_max);
+    if (e == cudaSuccess) e = dev_alloc(&c->d_items, (size_t)max_batch * c->hs_max);
+    if (e == cudaSuccess) e = dev_alloc(&c->d_scratch, (size_t)max_batch * c->hs_max * (size_t)max_w);
+    if (e == cudaSuccess) e = dev_alloc(&c->d_status, 1);
+    if (e == cudaSuccess) e = pin_alloc(&c->h_status, 1);
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->d_status, 0, sizeof(int32_t), c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) {
+        free_all(c);
+        delete c;
+        return e == cudaErrorMemoryAllocation ? CVS_ERR_NOMEM : CVS_ERR_CUDA;
+    }
+    *out = c;
+    return CVS_OK;
+}
+
+void cvs_destroy(cvs_ctx *ctx) {
+    if (!ctx) return;
+    free_all(ctx);
+    delete ctx;
+}
+
+int cvs_set_params(cvs_ctx *ctx, const cvs_params *p) {
+    if (!ctx || !p || p->struct_size != (int32_t)sizeof(cvs_params)) return CVS_ERR_INVALID_ARG;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return CVS_ERR_CUDA;
+    CVS_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->p = *p;
+    for (auto &pl : ctx->plans) if (pl && pl->d_seek) cudaFree(pl->d_seek);
+    ctx->plans.clear();                      // draw layout depends on the enabled stages
+    ctx->lut_dirty = true;
+    return CVS_OK;
+}
+
+int cvs_set_precision(cvs_ctx *ctx, int use_double) {
+    if (!ctx) return CVS_ERR_INVALID_ARG;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return CVS_ERR_CUDA;
+    CVS_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->precision = use_double ? 1 : 0;
+    ctx->lut_dirty = true;
+    return CVS_OK;
+}
+
+int cvs_composite_layer(cvs_ctx *ctx, uint8_t *dst, int dst_stride, const uint8_t *src, int src_stride,
+                        int w, int h, int src_interlaced, int src_top_field_first,
+                        unsigned field, unsigned long long fieldno) {
+    if (field > 1) {
+        // the reference accepts any `field` (rows y = field, field+2, ...); only 0/1 occur (:2229)
+        return CVS_ERR_INVALID_ARG;
+    }
+    return run_host(ctx, dst, 0, dst_stride, src, 0, src_stride, w, h, src_interlaced, src_top_field_first, 1,
+                    fieldno, (int)field);
+}
+
+int cvs_composite_fields_device(cvs_ctx *ctx, void *dst, size_t dst_pic_stride, int dst_stride, const void *src,
+                                size_t src_pic_stride, int src_stride, int w, int h, int src_interlaced,
+                                int src_top_field_first, int n, unsigned long long first_fieldno) {
+    return run_device(ctx, (uint8_t *)dst, dst_pic_stride, dst_stride, (const uint8_t *)src, src_pic_stride, src_stride,
+                      w, h, src_interlaced, src_top_field_first, n, first_fieldno, -1);
+}
+
+int cvs_composite_fields_host(cvs_ctx *ctx, void *dst, size_t dst_pic_stride, int dst_stride, const void *src,
+                              size_t src_pic_stride, int src_stride, int w, int h, int src_interlaced,
+                              int src_top_field_first, int n, unsigned long long first_fieldno) {
+    return run_host(ctx, (uint8_t *)dst, dst_pic_stride, dst_stride, (const uint8_t *)src, src_pic_stride, src_stride,
+                    w, h, src_interlaced, src_top_field_first, n, first_fieldno, -1);
+}
+
+int cvs_synchronize(cvs_ctx *ctx) {
+    if (!ctx) return CVS_ERR_INVALID_ARG;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return CVS_ERR_CUDA;
+    return check_status(ctx);
+}
+
+int cvs_rng_seek(cvs_ctx *ctx, unsigned long long draws_consumed) {
+    if (!ctx) return CVS_ERR_INVALID_ARG;
+    ctx->cur.seek(draws_consumed);
+    return CVS_OK;
+}
+
+int cvs_rng_tell(const cvs_ctx *ctx, unsigned long long *draws_consumed) {
+    if (!ctx || !draws_consumed) return CVS_ERR_INVALID_ARG;
+    *draws_consumed = ctx->cur.pos();
+    return CVS_OK;
+}
+
+unsigned long long cvs_kernel_launches(const cvs_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int cvs_last_kernel_ms(cvs_ctx *ctx, float *ms) {
+    if (!ctx || !ms) return CVS_ERR_INVALID_ARG;
+    if (!ctx->ev_valid) return CVS_ERR_INVALID_ARG;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return CVS_ERR_CUDA;
+    CVS_CUDA(cudaEventSynchronize(ctx->ev1));
+    CVS_CUDA(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    return CVS_OK;
+}
+
+}  // extern "C"

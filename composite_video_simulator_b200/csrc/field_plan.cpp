@@ -41,7 +41,7 @@ static double pole_alpha(double hz) {              // LowpassFilter::setFilter, 
 }
 
 template <typename R>
-void make_kconst(const cvs_params &p, int w, int h, unsigned field, bool outfull, KConst<R> &K, std::vector<R> &lut) {
+void make_kconst(const cvs_params &p, int w, int h, bool outfull, KConst<R> &K, std::vector<R> &lut) {
     std::memset(&K, 0, sizeof(K));
     auto set = [](R &a, R &b, double alpha) { a = (R)alpha; b = (R)(1.0 - alpha); };
     set(K.a_inI, K.b_inI, pole_alpha(1300000));            // :1442
@@ -78,7 +78,6 @@ void make_kconst(const cvs_params &p, int w, int h, unsigned field, bool outfull
     K.pnoise = p.video_chroma_phase_noise < 0 ? -p.video_chroma_phase_noise : p.video_chroma_phase_noise;
     K.phase_shift = p.video_scanline_phase_shift;
     K.phase_offset = p.video_scanline_phase_shift_offset;
-    K.field = (int32_t)field;
     K.amp = p.subcarrier_amplitude;
     K.amp_back = p.subcarrier_amplitude_back;
     K.vnoise = p.video_noise;
@@ -87,7 +86,6 @@ void make_kconst(const cvs_params &p, int w, int h, unsigned field, bool outfull
     if (K.cnoise != 0) mod_magic((uint32_t)(2 * K.cnoise + 1), K.cmagic, K.cshift);
     K.w = w;
     K.h = h;
-    K.nl = (h > (int)field) ? (h - (int)field + 1) / 2 : 0;
     // {sin, cos}(state * pi / 100) for every reachable phase-noise state (:1746-1749); libm on the
     // host, in double, exactly as the reference evaluates them
     lut.clear();
@@ -98,8 +96,8 @@ void make_kconst(const cvs_params &p, int w, int h, unsigned field, bool outfull
     }
     K.phase_lut = lut.data();
 }
-template void make_kconst<float>(const cvs_params &, int, int, unsigned, bool, KConst<float> &, std::vector<float> &);
-template void make_kconst<double>(const cvs_params &, int, int, unsigned, bool, KConst<double> &, std::vector<double> &);
+template void make_kconst<float>(const cvs_params &, int, int, bool, KConst<float> &, std::vector<float> &);
+template void make_kconst<double>(const cvs_params &, int, int, bool, KConst<double> &, std::vector<double> &);
 
 void build_geom_plan(const cvs_params &p, int w, int h, unsigned field, GeomPlan &g) {
     g.w = w;

@@ -53,7 +53,7 @@ void mod_magic(uint32_t m, uint32_t &magic, uint32_t &shift);
 
 // launch constants; `lut` receives the {sin, cos} table K.phase_lut must point at (host copy)
 template <typename R>
-void make_kconst(const cvs_params &p, int w, int h, unsigned field, bool outfull, KConst<R> &K, std::vector<R> &lut);
+void make_kconst(const cvs_params &p, int w, int h, bool outfull, KConst<R> &K, std::vector<R> &lut);
 
 // which kernel instantiation a parameter block needs
 struct Variant {

@@ -1,0 +1,6 @@
+// kern_d_comp_full.cu -- one instantiation of the fused scanline kernel (see scanline_kernels.cuh).
+// R = double; <VHS, chroma delay, full output lowpass> = <false, 9, true>.
+#include "scanline_kernels.cuh"
+namespace cvs {
+CVS_DEFINE_LAUNCH_FIELDS(double, false, 9, true)
+}

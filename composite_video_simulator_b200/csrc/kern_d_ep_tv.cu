@@ -1,0 +1,6 @@
+// kern_d_ep_tv.cu -- one instantiation of the fused scanline kernel (see scanline_kernels.cuh).
+// R = double; <VHS, chroma delay, full output lowpass> = <true, 14, false>.
+#include "scanline_kernels.cuh"
+namespace cvs {
+CVS_DEFINE_LAUNCH_FIELDS(double, true, 14, false)
+}

@@ -1,0 +1,6 @@
+// kern_d_lp_full.cu -- one instantiation of the fused scanline kernel (see scanline_kernels.cuh).
+// R = double; <VHS, chroma delay, full output lowpass> = <true, 12, true>.
+#include "scanline_kernels.cuh"
+namespace cvs {
+CVS_DEFINE_LAUNCH_FIELDS(double, true, 12, true)
+}

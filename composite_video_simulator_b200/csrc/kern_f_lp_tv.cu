@@ -1,0 +1,6 @@
+// kern_f_lp_tv.cu -- one instantiation of the fused scanline kernel (see scanline_kernels.cuh).
+// R = float; <VHS, chroma delay, full output lowpass> = <true, 12, false>.
+#include "scanline_kernels.cuh"
+namespace cvs {
+CVS_DEFINE_LAUNCH_FIELDS(float, true, 12, false)
+}

@@ -1,0 +1,6 @@
+// kern_f_sp_full.cu -- one instantiation of the fused scanline kernel (see scanline_kernels.cuh).
+// R = float; <VHS, chroma delay, full output lowpass> = <true, 9, true>.
+#include "scanline_kernels.cuh"
+namespace cvs {
+CVS_DEFINE_LAUNCH_FIELDS(float, true, 9, true)
+}

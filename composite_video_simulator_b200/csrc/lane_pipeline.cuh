@@ -82,11 +82,10 @@ struct KConst {
     uint32_t flags;
     int32_t pnoise;                       // video_chroma_phase_noise
     int32_t phase_shift, phase_offset;    // video_scanline_phase_shift(_offset)
-    int32_t field;                        // field parity of this launch
     int32_t amp, amp_back;                // subcarrier_amplitude, _back
     int32_t vnoise, cnoise;               // video_noise, video_chroma_noise
     uint32_t vmagic, vshift, cmagic, cshift;   // exact n % (2v+1) for 31-bit n: q = umulhi(n,magic) >> shift
-    int32_t w, h, nl;
+    int32_t w, h;
 };
 
 // ---- numeric policy -------------------------------------------------------------------------
@@ -558,7 +557,7 @@ struct Pipeline {
                 Qb[j] = N::rot_b(u, rc.sinp, v, rc.cosp);
             }
         }
-        if (!VHS) return;
+        if constexpr (VHS) {
 
         // VHS luma: 3 poles @ luma_cut reset 16, + 1.6 x highpass, then sharpen (:1793-1812, :1865-1883)
         // VHS chroma: 3 poles @ chroma_cut, output CD samples early (:1814-1836)
@@ -600,6 +599,7 @@ struct Pipeline {
         }
         CVS_UNROLL
         for (int j = 0; j < kT; j++) { ln.oUprev[j] = oUcur[j]; ln.oVprev[j] = oVcur[j]; }
+        }
     }
 
     // ---- B2 + C: vertical blend of B(s-4), remodulate, second demod of B(s-5) -----------------------
@@ -753,10 +753,11 @@ CVS_HD int line_phase(int phase_shift, int off, unsigned long long fieldno, unsi
 }
 
 template <typename R>
-CVS_HD void row_setup(const KConst<R> &K, unsigned long long fieldno, int row, uint32_t rowinfo, RowConst<R> &rc) {
+CVS_HD void row_setup(const KConst<R> &K, unsigned field, unsigned long long fieldno, int row, uint32_t rowinfo,
+                      RowConst<R> &rc) {
     rc.row = row;
     rc.rflags = (rowinfo >> 16) & 0xFFu;
-    rowconst_set_phase<R>(rc, line_phase(K.phase_shift, K.phase_offset, fieldno, (unsigned)(K.field + 2 * row)));
+    rowconst_set_phase<R>(rc, line_phase(K.phase_shift, K.phase_offset, fieldno, field + 2u * (unsigned)row));
     if (K.flags & F_PHASE) {
         const int st = (int)(int16_t)(rowinfo & 0xFFFFu);
         rc.sinp = K.phase_lut[2 * (st + K.pnoise)];

@@ -1,0 +1,270 @@
+// scanline_kernels.cuh -- sm_100a kernels around lane_pipeline.cuh.
+//
+//   k_fields<R,VHS,CD,OUTFULL>   the fused scanline kernel: one launch processes a batch of
+//                                 fields; a warp owns 31 consecutive rows of one field (+1 halo
+//                                 lane), a lane streams its row through every stage of
+//                                 composite_layer() (ffmpeg_ntsc.cpp:1570-1921) in registers.
+//                                 HBM traffic = one BGRA read + one BGRA write per pixel.
+//   k_headswitch<R>               pre-pass for the few rows per field that the VHS head switch
+//                                 rotates (ffmpeg_ntsc.cpp:1683-1700): writes their composite
+//                                 signal, already rotated, to a scratch row.
+//
+// Shared memory per CTA (NT threads): the per-lane glibc-rand rings for the luma and chroma
+// noise streams ([2][32][NT] words, slot-major so a warp access is conflict-free), the per-lane
+// chroma tail stash ([2][16][NT] R) and one 64-word generator window per warp.
+#ifndef CVS_SCANLINE_KERNELS_CUH
+#define CVS_SCANLINE_KERNELS_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "lane_pipeline.cuh"
+
+namespace cvs {
+
+constexpr int kNT = 128;                 // threads per CTA (4 warps)
+constexpr int kWarpsPerCta = kNT / 32;
+constexpr int kRowsPerWarp = 31;         // lane 0 is the halo row of the vertical chroma blend
+
+struct FieldDesc {
+    const uint8_t *src;                  // picture base (device)
+    uint8_t *dst;
+    const uint32_t *rowinfo;             // nl packed row records (rowinfo_pack)
+    const uint32_t *seek;                // nl * 62 jump-polynomial words for this field parity
+    int32_t *hs_scratch;                 // hs_count rows of w int32 (rotated composite rows)
+    const int32_t *hs_shift;             // hs_count shifts
+    unsigned long long fieldno;
+    int32_t field, nl, hs_first, hs_count;
+    uint32_t window[64];                 // q[base-31 .. base+29] (61 used)
+};
+
+struct HsItem {
+    int32_t field_idx, slot;
+};
+
+template <typename R>
+struct LaunchArgs {
+    KConst<R> K;
+    const FieldDesc *fields;
+    int32_t nfields, warps_per_field, total_warps;
+    int32_t src_stride, dst_stride, opposite;
+    int32_t vec_src, vec_dst;            // rows are 16-byte aligned: use 128-bit loads / stores
+    int32_t *status;                     // sticky error word (CVS_ERR_NOISE_SYNC)
+};
+
+template <typename R>
+constexpr size_t fields_smem_bytes() {
+    return (size_t)2 * kRngSlots * kNT * sizeof(uint32_t) + (size_t)2 * kTailSlots * kNT * sizeof(R) +
+           (size_t)kWarpsPerCta * 64 * sizeof(uint32_t);
+}
+
+__device__ __forceinline__ const uint32_t *row_ptr(const uint8_t *base, int stride, int y) {
+    return (const uint32_t *)(base + (size_t)stride * (size_t)y);
+}
+
+// 31 raw words preceding the lane's noise segment: hist[k] = sum_i poly[i] * window[k+i]
+__device__ __forceinline__ void rebase_dev(const uint32_t *win_smem, const uint32_t *__restrict__ poly_g,
+                                           uint32_t hist[31]) {
+    uint32_t poly[31];
+#pragma unroll
+    for (int i = 0; i < 31; i++) poly[i] = __ldg(poly_g + i);
+#pragma unroll 1
+    for (int k = 0; k < 31; k++) {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int i = 0; i < 31; i++) acc += poly[i] * win_smem[k + i];
+        hist[k] = acc;
+    }
+}
+
+template <typename R, bool VHS, int CD, bool OUTFULL>
+struct Stepper {
+    typedef Lane<R, VHS, CD, OUTFULL> L;
+    typedef Pipeline<R, VHS, CD, OUTFULL> P;
+
+    template <bool EDGE>
+    static __device__ __forceinline__ void step(const KConst<R> &K, const RowConst<R> &rc, L &ln, int s,
+                                                const uint32_t px[kT], const int32_t *hsrow, bool valid,
+                                                uint32_t *drow, bool vec_dst) {
+        R C[kT], Yb[kT], Ib[kT], Qb[kT];
+        BlendXchg<R> xo;
+        P::template stage_a<EDGE>(K, rc, ln, s, px, hsrow, C);
+        P::template stage_b<EDGE>(K, rc, ln, s, C, Yb, Ib, Qb, xo);
+        uint32_t out[kT];
+        bool have;
+        int kf;
+        if (VHS) {
+            BlendXchg<R> above;
+#pragma unroll
+            for (int j = 0; j < kT; j++) {
+                above.u[j] = __shfl_up_sync(0xffffffffu, xo.u[j], 1);
+                above.v[j] = __shfl_up_sync(0xffffffffu, xo.v[j], 1);
+            }
+            R Yf[kT], If[kT], Qf[kT];
+            P::template stage_c<EDGE>(K, rc, ln, s, Yb, xo, above, Yf, If, Qf, kf);
+            have = P::template stage_f<EDGE>(K, rc, ln, kf, Yf, If, Qf, out);
+        } else {
+            kf = s - 2;
+            have = P::template stage_f<EDGE>(K, rc, ln, kf, Yb, Ib, Qb, out);
+        }
+        if (have && valid) {
+            const int x0 = (kf - 1) * kT;
+            if (vec_dst && (!EDGE || x0 + kT <= K.w)) {
+                uint4 *d = reinterpret_cast<uint4 *>(drow + x0);
+                d[0] = make_uint4(out[0], out[1], out[2], out[3]);
+                d[1] = make_uint4(out[4], out[5], out[6], out[7]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < kT; j++)
+                    if (x0 + j < K.w) drow[x0 + j] = out[j];
+            }
+        }
+    }
+};
+
+__device__ __forceinline__ void load_block_dev(const uint32_t *srow, int k, int w, bool vec, uint32_t px[kT]) {
+    const int x0 = k * kT;
+    if (vec && x0 + kT <= w) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(srow + x0);
+        const uint4 a = __ldcs(p), b = __ldcs(p + 1);       // streamed once: evict-first
+        px[0] = a.x; px[1] = a.y; px[2] = a.z; px[3] = a.w;
+        px[4] = b.x; px[5] = b.y; px[6] = b.z; px[7] = b.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < kT; j++) px[j] = (x0 + j < w) ? __ldcs(srow + x0 + j) : 0u;
+    }
+}
+
+template <typename R, bool VHS, int CD, bool OUTFULL>
+__global__ void __launch_bounds__(kNT) k_fields(const __grid_constant__ LaunchArgs<R> a) {
+    typedef Lane<R, VHS, CD, OUTFULL> L;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t *rings = reinterpret_cast<uint32_t *>(smem_raw);
+    R *tails = reinterpret_cast<R *>(smem_raw + (size_t)2 * kRngSlots * kNT * sizeof(uint32_t));
+    uint32_t *wins = reinterpret_cast<uint32_t *>(smem_raw + (size_t)2 * kRngSlots * kNT * sizeof(uint32_t) +
+                                                  (size_t)2 * kTailSlots * kNT * sizeof(R));
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gw = blockIdx.x * kWarpsPerCta + warp;
+    if (gw >= a.total_warps) return;
+    const int fi = gw / a.warps_per_field, wp = gw - fi * a.warps_per_field;
+    const FieldDesc &fd = a.fields[fi];
+    const int nl = fd.nl;
+    if (kRowsPerWarp * wp >= nl) return;                 // (odd heights: the short parity has fewer rows)
+    const KConst<R> &K = a.K;
+    const int w = K.w, h = K.h;
+
+    uint32_t *win = wins + warp * 64;
+    win[lane] = fd.window[lane];
+    win[lane + 32] = fd.window[lane + 32];
+    __syncwarp();
+
+    int row = kRowsPerWarp * wp + lane - 1;
+    const bool valid = (lane >= 1) && row < nl;
+    row = row < 0 ? 0 : (row > nl - 1 ? nl - 1 : row);
+
+    L ln;
+    ln.reset(K);
+    RowConst<R> rc;
+    row_setup<R>(K, (unsigned)fd.field, fd.fieldno, row, __ldg(fd.rowinfo + row), rc);
+    int sy = fd.field + 2 * row + a.opposite;            // source row, ffmpeg_ntsc.cpp:1599
+    sy = sy > h - 1 ? h - 1 : sy;
+    const uint32_t *srow = row_ptr(fd.src, a.src_stride, sy);
+    uint32_t *drow = const_cast<uint32_t *>(row_ptr(fd.dst, a.dst_stride, fd.field + 2 * row));
+    const int32_t *hsrow = (rc.rflags & RF_HEADSW) ? fd.hs_scratch + (size_t)(row - fd.hs_first) * (size_t)w : nullptr;
+    ln.tailU = tails + tid;
+    ln.tailV = tails + (size_t)kTailSlots * kNT + tid;
+    ln.tail_stride = kNT;
+    ln.nY = ln.nU = ln.nV = 0;
+    {
+        const long long full = (long long)row * w;
+        const int nd = (int)(full < kWarmPx ? full : kWarmPx);
+        const bool from_start = full <= kWarmPx;
+        bool ok = true;
+        uint32_t hist[31];
+        if (K.vnoise != 0) {
+            rebase_dev(win, fd.seek + (size_t)row * 62, hist);
+            ln.rngL.init(rings + tid, kNT, hist, kRngBase - (uint32_t)nd);
+            ok &= warm_luma((uint32_t)(2 * K.vnoise + 1), K.vmagic, K.vshift, K.vnoise, ln.rngL, nd, from_start, ln.nY);
+        }
+        if (K.cnoise != 0) {
+            rebase_dev(win, fd.seek + (size_t)row * 62 + 31, hist);
+            ln.rngC.init(rings + (size_t)kRngSlots * kNT + tid, kNT, hist, kRngBase - 2u * (uint32_t)nd);
+            ok &= warm_chroma((uint32_t)(2 * K.cnoise + 1), K.cmagic, K.cshift, K.cnoise, ln.rngC, nd, from_start, ln.nU, ln.nV);
+        }
+        if (!ok) atomicOr(a.status, 1);
+    }
+
+    const int nsteps = line_steps<VHS>(w);
+    int s_lo, s_hi;
+    interior_steps<VHS>(w, s_lo, s_hi);
+    if (K.flags & F_GENERAL) s_hi = s_lo;
+    const bool vec_src = a.vec_src != 0, vec_dst = a.vec_dst != 0;
+
+    uint32_t px[kT];
+    load_block_dev(srow, 0, w, vec_src, px);
+#pragma unroll 1
+    for (int s = 0; s < nsteps; s++) {
+        uint32_t pxn[kT];
+        load_block_dev(srow, s + 1, w, vec_src, pxn);            // prefetch the next block
+        if (s >= s_lo && s < s_hi)
+            Stepper<R, VHS, CD, OUTFULL>::template step<false>(K, rc, ln, s, px, hsrow, valid, drow, vec_dst);
+        else
+            Stepper<R, VHS, CD, OUTFULL>::template step<true>(K, rc, ln, s, px, hsrow, valid, drow, vec_dst);
+#pragma unroll
+        for (int j = 0; j < kT; j++) px[j] = pxn[j];
+    }
+}
+
+constexpr int kHsNT = 64;
+
+template <typename R>
+__global__ void __launch_bounds__(kHsNT) k_headswitch(const __grid_constant__ LaunchArgs<R> a,
+                                                      const HsItem *__restrict__ items, int nitems) {
+    __shared__ uint32_t ring[kRngSlots * kHsNT];
+    const int it = blockIdx.x * kHsNT + threadIdx.x;
+    if (it >= nitems) return;
+    const HsItem item = items[it];
+    const FieldDesc &fd = a.fields[item.field_idx];
+    const KConst<R> &K = a.K;
+    const int w = K.w, h = K.h;
+    const int row = fd.hs_first + item.slot;
+    Lane<R, false, 9, false> ln;
+    ln.reset(K);
+    RowConst<R> rc;
+    row_setup<R>(K, (unsigned)fd.field, fd.fieldno, row, __ldg(fd.rowinfo + row), rc);
+    ln.nY = 0;
+    if (K.vnoise != 0) {
+        const long long full = (long long)row * w;
+        const int nd = (int)(full < kWarmPx ? full : kWarmPx);
+        uint32_t hist[31];
+        rng_rebase(fd.window, fd.seek + (size_t)row * 62, hist);
+        ln.rngL.init(ring + threadIdx.x, kHsNT, hist, kRngBase - (uint32_t)nd);
+        if (!warm_luma((uint32_t)(2 * K.vnoise + 1), K.vmagic, K.vshift, K.vnoise, ln.rngL, nd, full <= kWarmPx, ln.nY))
+            atomicOr(a.status, 1);
+    }
+    int sy = fd.field + 2 * row + a.opposite;
+    sy = sy > h - 1 ? h - 1 : sy;
+    headswitch_row<R>(K, rc, ln, row_ptr(fd.src, a.src_stride, sy), fd.hs_scratch + (size_t)item.slot * (size_t)w,
+                      __ldg(fd.hs_shift + item.slot));
+}
+
+// host-callable launchers (one translation unit per instantiation, see kern_*.cu)
+template <typename R, bool VHS, int CD, bool OUTFULL>
+cudaError_t launch_fields(const LaunchArgs<R> &a, cudaStream_t st);
+template <typename R>
+cudaError_t launch_headswitch(const LaunchArgs<R> &a, const HsItem *items, int nitems, cudaStream_t st);
+
+#define CVS_DEFINE_LAUNCH_FIELDS(R, VHS, CD, OUTFULL)                                                          \
+    template <>                                                                                                \
+    cudaError_t launch_fields<R, VHS, CD, OUTFULL>(const LaunchArgs<R> &a, cudaStream_t st) {                  \
+        const size_t smem = fields_smem_bytes<R>();                                                            \
+        cudaError_t e = cudaFuncSetAttribute(k_fields<R, VHS, CD, OUTFULL>,                                    \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
+        if (e != cudaSuccess) return e;                                                                        \
+        const int ctas = (a.total_warps + kWarpsPerCta - 1) / kWarpsPerCta;                                    \
+        k_fields<R, VHS, CD, OUTFULL><<<ctas, kNT, smem, st>>>(a);                                             \
+        return cudaGetLastError();                                                                             \
+    }
+
+}  // namespace cvs
+#endif

@@ -122,6 +122,12 @@ int cvs_params_apply_argv(cvs_params *p, int argc, const char *const *argv);
 int  cvs_create(cvs_ctx **out, const cvs_params *p, int device, int max_w, int max_h, int max_batch);
 void cvs_destroy(cvs_ctx *ctx);
 int  cvs_set_params(cvs_ctx *ctx, const cvs_params *p);
+/*
+ * Arithmetic of the scanline kernels: 0 (default) = fp32 with explicit FMAs, the production
+ * path (within +-1 LSB of the reference); 1 = fp64 evaluated operation for operation like the
+ * reference's double code (bit-exact with the reference; a validation mode, about 3x slower).
+ */
+int  cvs_set_precision(cvs_ctx *ctx, int use_double);
 
 /* ---- the seam: exact analogue of the call at ffmpeg_ntsc.cpp:2229 ------------------------- */
 

@@ -32,7 +32,7 @@ int run_field(const cvs_params &p, RandCursor &cur, uint8_t *dst, int dst_stride
     build_field_side(p, g, cur, fs);
     KConst<R> K;
     std::vector<R> lut;
-    make_kconst<R>(p, w, h, field, OUTFULL, K, lut);
+    make_kconst<R>(p, w, h, OUTFULL, K, lut);
     if (force_general) K.flags |= F_GENERAL;
     const int nl = g.nl;
     const int opposite = interlaced ? (tff ? 1 : 0) : 0;
@@ -49,7 +49,7 @@ int run_field(const cvs_params &p, RandCursor &cur, uint8_t *dst, int dst_stride
         Lane<R, false, 9, false> ln;
         ln.reset(K);
         RowConst<R> rc;
-        row_setup<R>(K, fieldno, row, fs.rowinfo[(size_t)row], rc);
+        row_setup<R>(K, field, fieldno, row, fs.rowinfo[(size_t)row], rc);
         uint32_t ring[kRngSlots];
         if (K.vnoise != 0) {
             uint32_t hist[31];
@@ -84,7 +84,7 @@ int run_field(const cvs_params &p, RandCursor &cur, uint8_t *dst, int dst_stride
             if (row > nl - 1) row = nl - 1;
             L &ln = lane[l];
             ln.reset(K);
-            row_setup<R>(K, fieldno, row, fs.rowinfo[(size_t)row], rc[l]);
+            row_setup<R>(K, field, fieldno, row, fs.rowinfo[(size_t)row], rc[l]);
             srow[l] = src_row(row);
             drow[l] = (uint32_t *)(dst + (size_t)dst_stride * (size_t)((int)field + 2 * row));
             hsrow[l] = (rc[l].rflags & RF_HEADSW) ? &scratch[(size_t)(row - fs.hs_first) * w] : (const int32_t *)0;

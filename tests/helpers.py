@@ -1,0 +1,141 @@
+"""Shared test helpers: checker libraries, synthetic streams, hashing, comparison.
+
+Only tests (and bench.py / __graft_entry__.smoke) may touch oracle/; the product never does.
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import composite_video_simulator_b200 as cvs  # noqa: E402
+from composite_video_simulator_b200 import build as cvs_build  # noqa: E402
+from composite_video_simulator_b200.params import CvsParams  # noqa: E402
+
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+class OracleRng(C.Structure):
+    _fields_ = [("r", C.c_uint32 * 31), ("f", C.c_int), ("b", C.c_int), ("pos", C.c_ulonglong)]
+
+
+def load_oracle():
+    path = os.path.join(ORACLE_DIR, "liboracle.so")
+    src = os.path.join(ORACLE_DIR, "ntsc_oracle.c")
+    if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+        subprocess.check_call(["make", "liboracle.so"], cwd=ORACLE_DIR, stdout=subprocess.DEVNULL)
+    lib = C.CDLL(path)
+    lib.oracle_draws_per_field.restype = C.c_ulonglong
+    lib.oracle_rng_next.restype = C.c_uint32
+    return lib
+
+
+def load_ref():
+    """The reference's own composite_layer(), extracted at build time (never committed)."""
+    path = os.path.join(ORACLE_DIR, "_ref", "libref.so")
+    if not os.path.exists(path):
+        if os.path.exists("/root/reference/ffmpeg_ntsc.cpp"):
+            subprocess.check_call(["make", "ref"], cwd=ORACLE_DIR, stdout=subprocess.DEVNULL)
+        else:
+            return None
+    lib = C.CDLL(path)
+    return lib
+
+
+def load_emu():
+    lib = C.CDLL(cvs_build.build_emu())
+    return lib
+
+
+def params(*argv):
+    return cvs.params_from_argv(list(argv))
+
+
+BARS = [0xC0C0C0, 0xC0C000, 0x00C0C0, 0x00C000, 0xC000C0, 0xC00000, 0x0000C0, 0x000000]   # 75% bars
+
+
+def bars_frame(w, h):
+    x = np.arange(w)
+    row = np.array(BARS, dtype=np.uint32)[(x * 8) // w]
+    return np.ascontiguousarray(np.broadcast_to(row, (h, w))).copy()
+
+
+def stream_frame(w, h, k):
+    """Parity stream of SURVEY.md 8(d): bars rotated by 7k px plus a per-pixel hash perturbation."""
+    x = np.arange(w, dtype=np.uint32)[None, :]
+    y = np.arange(h, dtype=np.uint32)[:, None]
+    xs = (x + np.uint32(7 * k)) % np.uint32(w)
+    base = np.broadcast_to(np.array(BARS, dtype=np.uint32)[(xs * np.uint32(8)) // np.uint32(w)], (h, w))
+    pert = ((x * np.uint32(2654435761)) ^ (y * np.uint32(40503)) ^ np.uint32((k * 97) & 0xFFFFFFFF)) >> np.uint32(29)
+    out = np.zeros((h, w), dtype=np.uint32)
+    for sh in (0, 8, 16):
+        c = ((base >> np.uint32(sh)) & np.uint32(0xFF)) + pert
+        out |= np.minimum(c, 255).astype(np.uint32) << np.uint32(sh)
+    return out
+
+
+def noise_frame(w, h, seed):
+    rng = np.random.RandomState(seed)
+    return (rng.randint(0, 1 << 24, size=(h, w), dtype=np.int64)).astype(np.uint32)
+
+
+def fnv1a64(arr):
+    """FNV-1a-64 of the bytes of arr (the hash of SURVEY.md App. D), vectorised per 64 KiB in C-free numpy."""
+    h = 1469598103934665603
+    prime = 1099511628211
+    mask = (1 << 64) - 1
+    for b in arr.tobytes():
+        h = ((h ^ b) * prime) & mask
+    return h
+
+
+def run_oracle(lib, p, frames, n, w, h, dst=None, g=None, interlaced=0, tff=0, field_fn=None):
+    """n sequential composite_layer() calls on the oracle; frames(k) -> uint32[h,w]."""
+    if dst is None:
+        dst = np.zeros((h, w), dtype=np.uint32)
+    if g is None:
+        g = OracleRng()
+        lib.oracle_rng_seed(C.byref(g), 1)
+    for k in range(n):
+        src = frames(k)
+        field = field_fn(k) if field_fn else (k & 1) ^ 1
+        rc = lib.oracle_composite_layer(C.byref(p), C.byref(g), dst.ctypes.data_as(C.c_void_p), dst.strides[0],
+                                        src.ctypes.data_as(C.c_void_p), src.strides[0], w, h, interlaced, tff,
+                                        field, C.c_ulonglong(k))
+        assert rc == 0
+    return dst, g
+
+
+def run_ref(lib, p, frames, n, w, h, interlaced=0, tff=0):
+    dst = np.zeros((h, w), dtype=np.uint32)
+    lib.ref_set_params(C.byref(p))
+    lib.ref_srand(1)
+    for k in range(n):
+        src = frames(k)
+        lib.ref_composite_layer(dst.ctypes.data_as(C.c_void_p), 4 * w, src.ctypes.data_as(C.c_void_p), 4 * w,
+                                w, h, interlaced, tff, (k & 1) ^ 1, C.c_ulonglong(k))
+    return dst
+
+
+def run_emu(lib, p, frames, n, w, h, precision, general=0, interlaced=0, tff=0):
+    dst = np.zeros((h, w), dtype=np.uint32)
+    pos = C.c_ulonglong(0)
+    for k in range(n):
+        src = frames(k)
+        rc = lib.emu_composite_layer(C.byref(p), precision, C.byref(pos), dst.ctypes.data_as(C.c_void_p), 4 * w,
+                                     src.ctypes.data_as(C.c_void_p), 4 * w, w, h, interlaced, tff, (k & 1) ^ 1,
+                                     C.c_ulonglong(k), general)
+        assert rc == 0, rc
+    return dst, pos.value
+
+
+def channel_diff(a, b):
+    """(max |delta|, #values differing, #values differing by > 1) over the 8-bit channels."""
+    d = np.abs(a.view(np.uint8).astype(np.int16) - b.view(np.uint8).astype(np.int16))
+    return int(d.max()) if d.size else 0, int((d > 0).sum()), int((d > 1).sum())
