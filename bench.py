@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 scanline engine (contract: see DESIGN.md "Measurement").
+
+    python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path
+    python bench.py --impl reference --gpus N ...          # the reference's own CPU code, host cores
+
+Metric (BASELINE.json): fields/s at 1920x1080, VHS-SP preset (`-vhs -vhs-speed sp`).  One "frame"
+of the reference's output is one FIELD: one composite_layer() call (ffmpeg_ntsc.cpp:2229) = one
+output picture of ffmpeg_ntsc (540 processed scanlines, then line-doubled).  full-frames/s = value/2.
+
+A step = one pass of the hot path over one batch of synthetic pictures:
+  value  device-resident: `batch` pictures already in HBM, one cvs_composite_fields_device call/step
+         (k_headswitch + k_fields), timed with CUDA events on the launching stream, max over ranks.
+         The working set (batch x 8.3 MB x 2) is far larger than L2, so no L2 flush is needed.
+  e2e    same metric through the C ABI with HOST (pinned) buffers: cvs_composite_fields_host, H2D
+         and D2H copies inside the timed region.
+  roofline  k_fields alone: algorithmic bytes (8 B per processed pixel) / mean launch duration from
+         CUDA events recorded around every launch in the timed region (cvs_kernel_time_query).
+  cpu_baseline  the reference's own composite_layer() (oracle/_ref/libref.so, extracted at build
+         time) on ONE host thread -- the reference is single-threaded -- on a bounded sample.
+Multi-GPU: fields are independent given the rand() position (closed-form seek), so rank r of N takes
+the r-th contiguous chunk of every step's N*batch fields; no data-path collective.  The only
+collective is one NCCL broadcast of the parameter block at start-up.  scaling = weak.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H = 1920, 1080
+ARGV = ["-vhs", "-vhs-speed", "sp"]
+METRIC = "fields/s at 1920x1080 VHS-SP (1 field = 1 composite_layer call = 1 output picture of ffmpeg_ntsc)"
+BARS = [0xC0C0C0, 0xC0C000, 0x00C0C0, 0x00C000, 0xC000C0, 0xC00000, 0x0000C0, 0x000000]
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks (B200_PROFILING.md recipe), sampled during the timed region
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# the reference's own CPU code (oracle/_ref) -- cpu_baseline leg and --impl reference arm
+# ----------------------------------------------------------------------------------------------
+def _load_cpu_checker():
+    """(lib, kind): the extracted reference if it was built, else the oracle port."""
+    import composite_video_simulator_b200  # noqa: F401  (params struct)
+    ref = os.path.join(ROOT, "oracle", "_ref", "libref.so")
+    if os.path.exists(ref):
+        return C.CDLL(ref), "reference"
+    orc = os.path.join(ROOT, "oracle", "liboracle.so")
+    if not os.path.exists(orc):
+        subprocess.check_call(["make", "liboracle.so"], cwd=os.path.join(ROOT, "oracle"), stdout=subprocess.DEVNULL)
+    return C.CDLL(orc), "port"
+
+
+def _cpu_stream_frame(k):
+    import numpy as np
+    x = np.arange(W, dtype=np.uint32)[None, :]
+    y = np.arange(H, dtype=np.uint32)[:, None]
+    xs = (x + np.uint32(7 * k)) % np.uint32(W)
+    base = np.broadcast_to(np.array(BARS, dtype=np.uint32)[(xs * np.uint32(8)) // np.uint32(W)], (H, W))
+    pert = ((x * np.uint32(2654435761)) ^ (y * np.uint32(40503)) ^ np.uint32((k * 97) & 0xFFFFFFFF)) >> np.uint32(29)
+    out = np.zeros((H, W), dtype=np.uint32)
+    for sh in (0, 8, 16):
+        c = ((base >> np.uint32(sh)) & np.uint32(0xFF)) + pert
+        out |= np.minimum(c, 255).astype(np.uint32) << np.uint32(sh)
+    return out
+
+
+def _cpu_run_fields(nfields, first=0):
+    """Run nfields composite_layer() calls of the CPU checker on one thread; returns seconds."""
+    import numpy as np
+    import composite_video_simulator_b200 as cvs
+    lib, kind = _load_cpu_checker()
+    p = cvs.params_from_argv(ARGV)
+    frames = [_cpu_stream_frame(first + k) for k in range(min(nfields, 4))]
+    dst = np.zeros((H, W), dtype=np.uint32)
+    if kind == "reference":
+        lib.ref_set_params(C.byref(p))
+        t0 = time.perf_counter()
+        for k in range(nfields):
+            src = frames[k % len(frames)]
+            lib.ref_composite_layer(dst.ctypes.data_as(C.c_void_p), 4 * W, src.ctypes.data_as(C.c_void_p), 4 * W,
+                                    W, H, 0, 0, ((first + k) & 1) ^ 1, C.c_ulonglong(first + k))
+        return time.perf_counter() - t0, kind
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    g = helpers.OracleRng()
+    lib.oracle_rng_seed(C.byref(g), 1)
+    t0 = time.perf_counter()
+    for k in range(nfields):
+        src = frames[k % len(frames)]
+        lib.oracle_composite_layer(C.byref(p), C.byref(g), dst.ctypes.data_as(C.c_void_p), 4 * W,
+                                   src.ctypes.data_as(C.c_void_p), 4 * W, W, H, 0, 0, ((first + k) & 1) ^ 1,
+                                   C.c_ulonglong(first + k))
+    return time.perf_counter() - t0, kind
+
+
+def _ref_worker(arg):
+    nfields, first = arg
+    dt, kind = _cpu_run_fields(nfields, first)
+    return dt, kind
+
+
+def run_reference_arm(args):
+    """The reference's CPU implementation on all host cores: P independent single-threaded processes
+    (the reference has no threading), each a bounded sample of the same workload per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    per_proc = args.ref_fields_per_proc
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        kind = "reference"
+        for _ in range(args.warmup):
+            pool.map(_ref_worker, [(1, 0)] * cores)
+        t0 = time.perf_counter()
+        for s in range(args.steps):
+            res = pool.map(_ref_worker, [(per_proc, s * per_proc)] * cores)
+            kind = res[0][1]
+        dt = time.perf_counter() - t0
+    total = cores * per_proc * args.steps
+    val = total / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "fields/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "1920x1080 VHS-SP (-vhs -vhs-speed sp), synthetic perturbed colour bars",
+                   "fields_per_step": cores * per_proc, "processes": cores},
+        "cpu_baseline": {"value": val, "unit": "fields/s", "cores": cores, "kind": kind,
+                         "sample": "%d processes x %d fields per step, %d steps, 1080p VHS-SP" % (cores, per_proc, args.steps)},
+        "e2e": {"value": val, "unit": "fields/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------
+# this repo's arm
+# ----------------------------------------------------------------------------------------------
+def make_device_stream(torch, n, first, device):
+    """Synthetic parity stream generated on the device: int32 BGRA, alpha 0."""
+    x = torch.arange(W, device=device, dtype=torch.int64)[None, :]
+    y = torch.arange(H, device=device, dtype=torch.int64)[:, None]
+    bars = torch.tensor(BARS, device=device, dtype=torch.int64)
+    out = torch.empty((n, H, W), device=device, dtype=torch.int32)
+    for i in range(n):
+        k = first + i
+        xs = (x + 7 * k) % W
+        base = bars[(xs * 8) // W].expand(H, W)
+        pert = (((x * 2654435761) & 0xFFFFFFFF) ^ ((y * 40503) & 0xFFFFFFFF) ^ ((k * 97) & 0xFFFFFFFF)) >> 29
+        pic = torch.zeros((H, W), device=device, dtype=torch.int64)
+        for sh in (0, 8, 16):
+            c = torch.clamp(((base >> sh) & 0xFF) + pert, max=255)
+            pic |= c << sh
+        out[i] = pic.to(torch.int32)
+    return out
+
+
+def run_own_arm(args):
+    import numpy as np
+    import torch
+    import composite_video_simulator_b200 as cvs
+    from composite_video_simulator_b200.params import CvsParams
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    # the only collective of the whole job: rank 0 broadcasts the parameter block (the preset tables)
+    pbytes = torch.zeros(C.sizeof(CvsParams), dtype=torch.uint8, device=dev)
+    if rank == 0:
+        p0 = cvs.params_from_argv(ARGV)
+        pbytes.copy_(torch.frombuffer(bytearray(bytes(p0)), dtype=torch.uint8))
+    if dist is not None:
+        dist.broadcast(pbytes, src=0)
+    params = CvsParams.from_buffer_copy(bytes(pbytes.cpu().numpy().tobytes()))
+
+    B = args.batch
+    nl = (H + 1) // 2
+    eng = cvs.Engine(params=params, device=local_rank, max_w=W, max_h=H, max_batch=max(B, args.e2e_batch))
+    stream = torch.cuda.Stream(device=dev)
+    eng.set_stream(stream.cuda_stream)
+    from composite_video_simulator_b200 import sharding
+
+    src = make_device_stream(torch, B, rank * B, dev)
+    dst = torch.zeros_like(src)
+    torch.cuda.synchronize()
+
+    def step(i):
+        base, _ = sharding.chunk(i, rank, world, B)   # this rank's contiguous chunk of the global field stream
+        eng.rng_seek(sharding.stream_position(params, W, H, base))
+        eng.composite_fields_device(dst, src, B, H, W, base)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    eng.synchronize()
+    barrier()
+    eng.kernel_time_reset()
+    launches0 = eng.kernel_launches()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        step(args.warmup + i)
+    e1.record(stream)
+    e1.synchronize()
+    eng.synchronize()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    launches = eng.kernel_launches() - launches0
+    kms, kn = eng.kernel_time_query()
+    t = torch.tensor([ms, kms / max(kn, 1)], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max, kernel_ms = float(t[0]), float(t[1])
+    value = world * B * args.steps / (ms_max / 1e3)
+
+    # ---- e2e: host buffers through the C ABI (H2D + kernels + D2H inside the timed region) ----
+    Be = args.e2e_batch
+    hsrc = torch.empty((Be, H, W), dtype=torch.int32).pin_memory()
+    hdst = torch.zeros((Be, H, W), dtype=torch.int32).pin_memory()
+    hsrc.copy_(src[:Be].cpu() if Be <= B else make_device_stream(torch, Be, rank * Be, dev).cpu())
+    hs_np, hd_np = hsrc.numpy().view(np.uint32), hdst.numpy().view(np.uint32)
+
+    def e2e_step(i):
+        base, _ = sharding.chunk(i, rank, world, Be)
+        eng.rng_seek(sharding.stream_position(params, W, H, base))
+        eng.composite_fields_host(hd_np, hs_np, base)      # synchronous
+
+    for i in range(max(1, args.warmup // 2)):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, args.steps)
+    for i in range(e2e_steps):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * Be * e2e_steps / float(t[0])
+    e2e_checksum = int(hd_np[0, 1::2].sum() & 0xFFFFFFFF)    # the step's result is read on the host
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (k_fields) ----
+    peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak = float(json.load(f)["hbm_gbs"])
+            peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        pass
+    alg_bytes = 8.0 * W * nl * B                               # 4 B read + 4 B written per processed pixel
+    achieved = alg_bytes / (kernel_ms / 1e3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            traffic = json.load(f).get("k_fields_sp_dram_bytes_per_launch")
+    except Exception:
+        pass
+
+    # ---- CPU baseline: the reference's own code, one thread, bounded sample ----
+    cpu = None
+    if world == 1 and args.cpu_fields > 0:
+        dtc, kind = _cpu_run_fields(args.cpu_fields)
+        cpu = {"value": args.cpu_fields / dtc, "unit": "fields/s", "cores": 1, "kind": kind,
+               "sample": "%d consecutive 1080p VHS-SP fields of the synthetic stream, 1 thread, %.1f s" % (args.cpu_fields, dtc)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "fields/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "1920x1080 VHS-SP (-vhs -vhs-speed sp), %d fields per GPU per step, synthetic "
+                               "perturbed colour bars generated on device" % B,
+                   "fields_per_step_per_gpu": B, "full_frames_per_s": value / 2,
+                   "l2": "inputs larger than L2 (%.0f MB read + %.0f MB written per step)" % (alg_bytes / 2e6, alg_bytes / 2e6),
+                   "noise": "exact glibc rand() replay", "parallelism": "fields sharded by contiguous chunk, no data-path collective"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "fields/s", "h2d_bytes_per_step": Be * nl * 4 * W,
+                "d2h_bytes_per_step": Be * nl * 4 * W, "fields_per_step_per_gpu": Be, "result_checksum": e2e_checksum},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": "k_fields<float,VHS,9,tv>", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms_per_launch": kernel_ms},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="fields per GPU per step (device-resident)")
+    ap.add_argument("--e2e-batch", type=int, default=64, help="fields per GPU per step (host buffers)")
+    ap.add_argument("--cpu-fields", type=int, default=64, help="fields of the single-thread CPU baseline sample")
+    ap.add_argument("--ref-fields-per-proc", type=int, default=4)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "own":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_own_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -46,7 +46,9 @@ def load():
         "cvs_rng_seek": (C.c_int, [vp, C.c_ulonglong]),
         "cvs_rng_tell": (C.c_int, [vp, C.POINTER(C.c_ulonglong)]),
         "cvs_kernel_launches": (C.c_ulonglong, [vp]),
-        "cvs_last_kernel_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
+        "cvs_kernel_time_reset": (C.c_int, [vp]),
+        "cvs_kernel_time_query": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+        "cvs_set_stream": (C.c_int, [vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)          # AttributeError if the ABI lost a symbol
@@ -60,5 +62,6 @@ EXPORTED_SYMBOLS = [
     "cvs_abi_version", "cvs_strerror", "cvs_params_default_ntsc", "cvs_params_preset_pal",
     "cvs_params_apply_argv", "cvs_draws_per_field", "cvs_create", "cvs_destroy", "cvs_set_params",
     "cvs_set_precision", "cvs_composite_layer", "cvs_composite_fields_device", "cvs_composite_fields_host",
-    "cvs_synchronize", "cvs_rng_seek", "cvs_rng_tell", "cvs_kernel_launches", "cvs_last_kernel_ms",
+    "cvs_synchronize", "cvs_rng_seek", "cvs_rng_tell", "cvs_kernel_launches", "cvs_kernel_time_reset",
+    "cvs_kernel_time_query", "cvs_set_stream",
 ]

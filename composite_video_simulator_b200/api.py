@@ -139,7 +139,15 @@ class Engine:
     def kernel_launches(self):
         return int(self.lib.cvs_kernel_launches(self._ctx))
 
-    def last_kernel_ms(self):
-        v = C.c_float()
-        _check(self.lib.cvs_last_kernel_ms(self._ctx, C.byref(v)), "cvs_last_kernel_ms")
-        return v.value
+    def kernel_time_reset(self):
+        _check(self.lib.cvs_kernel_time_reset(self._ctx), "cvs_kernel_time_reset")
+
+    def kernel_time_query(self):
+        """(sum of k_fields device durations in ms, number of launches) since the last reset."""
+        ms, n = C.c_double(), C.c_int()
+        _check(self.lib.cvs_kernel_time_query(self._ctx, C.byref(ms), C.byref(n)), "cvs_kernel_time_query")
+        return ms.value, n.value
+
+    def set_stream(self, cuda_stream):
+        """Run on a caller-owned stream (raw cudaStream_t handle, e.g. torch's ``stream.cuda_stream``)."""
+        _check(self.lib.cvs_set_stream(self._ctx, cuda_stream), "cvs_set_stream")

@@ -24,6 +24,7 @@ using namespace cvs;
 namespace {
 
 constexpr int kStagingSlots = 3;
+constexpr size_t kMaxEventPairs = 4096;
 
 struct DevPlan {
     int w = 0, h = 0;
@@ -54,8 +55,10 @@ struct cvs_ctx {
     int max_w = 0, max_h = 0, max_batch = 0, nl_max = 0, hs_max = 0;
     int precision = 0;                         // 0 = float (production), 1 = double (reference arithmetic)
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    bool ev_valid = false;
+    bool own_stream = true;
+    // CUDA-event pairs around every k_fields launch since the last cvs_kernel_time_reset()
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+    size_t ev_used = 0;
     RandCursor cur;
     std::vector<std::unique_ptr<DevPlan>> plans;
     Staging slots[kStagingSlots];
@@ -112,9 +115,9 @@ void free_all(cvs_ctx *c) {
     cudaFree(c->d_scratch); cudaFree(c->d_status); cudaFree(c->d_lut_f); cudaFree(c->d_lut_d);
     cudaFree(c->d_src); cudaFree(c->d_dst);
     if (c->h_status) cudaFreeHost(c->h_status);
-    if (c->ev0) cudaEventDestroy(c->ev0);
-    if (c->ev1) cudaEventDestroy(c->ev1);
-    if (c->stream) cudaStreamDestroy(c->stream);
+    for (auto &pr : c->ev_pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    c->ev_pool.clear();
+    if (c->stream && c->own_stream) cudaStreamDestroy(c->stream);
 }
 
 int get_plan(cvs_ctx *c, int w, int h, unsigned field, DevPlan **out) {
@@ -185,15 +188,21 @@ int launch_batch(cvs_ctx *c, const Variant &v, int w, int h, int nfields, int ma
     a.vec_src = vec_src;
     a.vec_dst = vec_dst;
     a.status = c->d_status;
-    CVS_CUDA(cudaEventRecord(c->ev0, c->stream));
     if (nitems > 0) {
         CVS_CUDA(launch_headswitch<R>(a, c->d_items, nitems, c->stream));
         c->launches++;
     }
+    if (c->ev_used == c->ev_pool.size() && c->ev_pool.size() < kMaxEventPairs) {
+        cudaEvent_t e0, e1;
+        CVS_CUDA(cudaEventCreate(&e0));
+        CVS_CUDA(cudaEventCreate(&e1));
+        c->ev_pool.push_back(std::make_pair(e0, e1));
+    }
+    const bool timed = c->ev_used < c->ev_pool.size();
+    if (timed) CVS_CUDA(cudaEventRecord(c->ev_pool[c->ev_used].first, c->stream));
     CVS_CUDA(launch_variant<R>(v, a, c->stream));
     c->launches++;
-    CVS_CUDA(cudaEventRecord(c->ev1, c->stream));
-    c->ev_valid = true;
+    if (timed) { CVS_CUDA(cudaEventRecord(c->ev_pool[c->ev_used].second, c->stream)); c->ev_used++; }
     return CVS_OK;
 }
 
@@ -353,8 +362,6 @@ int cvs_create(cvs_ctx **out, const cvs_params *p, int device, int max_w, int ma
     c->hs_max = head_switch_rows_bound(max_w);
     if (c->hs_max > c->nl_max) c->hs_max = c->nl_max;
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
-    if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
     for (auto &s : c->slots) {
         if (e == cudaSuccess) e = pin_alloc(&s.h_fields, (size_t)max_batch);
         if (e == cudaSuccess) e = pin_alloc(&s.h_rowinfo, (size_t)max_batch * c->nl_max);
@@ -451,12 +458,38 @@ int cvs_rng_tell(const cvs_ctx *ctx, unsigned long long *draws_consumed) {
 
 unsigned long long cvs_kernel_launches(const cvs_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
-int cvs_last_kernel_ms(cvs_ctx *ctx, float *ms) {
-    if (!ctx || !ms) return CVS_ERR_INVALID_ARG;
-    if (!ctx->ev_valid) return CVS_ERR_INVALID_ARG;
+int cvs_set_stream(cvs_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return CVS_ERR_INVALID_ARG;
     if (cudaSetDevice(ctx->device) != cudaSuccess) return CVS_ERR_CUDA;
-    CVS_CUDA(cudaEventSynchronize(ctx->ev1));
-    CVS_CUDA(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    CVS_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = (cudaStream_t)cuda_stream;
+    ctx->own_stream = false;
+    for (auto &s : ctx->slots) s.in_flight = false;
+    ctx->ev_used = 0;
+    return CVS_OK;
+}
+
+int cvs_kernel_time_reset(cvs_ctx *ctx) {
+    if (!ctx) return CVS_ERR_INVALID_ARG;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return CVS_ERR_CUDA;
+    CVS_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->ev_used = 0;
+    return CVS_OK;
+}
+
+int cvs_kernel_time_query(cvs_ctx *ctx, double *total_ms, int *launches) {
+    if (!ctx || !total_ms || !launches) return CVS_ERR_INVALID_ARG;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return CVS_ERR_CUDA;
+    CVS_CUDA(cudaStreamSynchronize(ctx->stream));
+    double sum = 0;
+    for (size_t i = 0; i < ctx->ev_used; i++) {
+        float ms = 0;
+        CVS_CUDA(cudaEventElapsedTime(&ms, ctx->ev_pool[i].first, ctx->ev_pool[i].second));
+        sum += ms;
+    }
+    *total_ms = sum;
+    *launches = (int)ctx->ev_used;
     return CVS_OK;
 }
 

@@ -184,8 +184,19 @@ const char *cvs_strerror(int status);
 int         cvs_abi_version(void);
 /* Number of kernel launches issued by this context so far (bench.py's gpu_launches). */
 unsigned long long cvs_kernel_launches(const cvs_ctx *ctx);
-/* Device time in ms of the most recent cvs_composite_fields_* kernel region (CUDA events). */
-int cvs_last_kernel_ms(cvs_ctx *ctx, float *ms);
+/*
+ * Device time of the fused scanline kernel (k_fields), measured with CUDA events recorded on
+ * the context stream around every launch since the last reset (up to 4096 launches).  The query
+ * synchronises the stream and returns the sum of the per-launch durations and their count.
+ */
+int cvs_kernel_time_reset(cvs_ctx *ctx);
+int cvs_kernel_time_query(cvs_ctx *ctx, double *total_ms, int *launches);
+/*
+ * Run on a caller-owned CUDA stream (a cudaStream_t / CUstream handle, e.g. torch's
+ * torch.cuda.current_stream().cuda_stream) instead of the context's private stream, so the
+ * caller's own events and allocations order with the engine's work.
+ */
+int cvs_set_stream(cvs_ctx *ctx, void *cuda_stream);
 
 #ifdef __cplusplus
 }

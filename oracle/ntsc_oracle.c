@@ -57,6 +57,14 @@ uint32_t oracle_rng_next(oracle_rng *g) {
 
 /* ------------------------------------------------------------------------------------------ */
 
+/* FNV-1a-64 over a byte buffer: the known-answer hash of SURVEY.md App. D. */
+unsigned long long oracle_fnv1a64(const void *buf, unsigned long long n) {
+    const unsigned char *b = (const unsigned char *)buf;
+    unsigned long long h = 1469598103934665603ULL, i;
+    for (i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ULL; }
+    return h;
+}
+
 static oracle_tap_fn g_tap = 0;
 static void *g_tap_user = 0;
 void oracle_set_tap(oracle_tap_fn fn, void *user) { g_tap = fn; g_tap_user = user; }

@@ -30,6 +30,8 @@ typedef struct oracle_rng {
 void     oracle_rng_seed(oracle_rng *g, unsigned seed);   /* == srand(seed); seed 1 == never seeded */
 uint32_t oracle_rng_next(oracle_rng *g);                   /* == (unsigned)rand()                    */
 
+unsigned long long oracle_fnv1a64(const void *buf, unsigned long long n);
+
 /* Number of rand() draws one composite_layer() call makes. */
 unsigned long long oracle_draws_per_field(const cvs_params *p, int w, int h, unsigned field);
 

@@ -188,4 +188,53 @@ int emu_composite_layer(const cvs_params *p, int precision, unsigned long long *
     return rc;
 }
 
+// ---- small probes of the product's host-side code (glibc_rand.cpp, field_plan.cpp) -------------------
+
+// (unsigned)rand() value number `pos` (0-based) of the default-seeded stream, by jump-ahead
+unsigned emu_rand_at(unsigned long long pos) {
+    RandCursor c;
+    c.seek(pos);
+    return c.next();
+}
+
+// sequential draws from position `pos` into out[n]
+void emu_rand_run(unsigned long long pos, int n, unsigned *out) {
+    RandCursor c;
+    c.seek(pos);
+    for (int i = 0; i < n; i++) out[i] = c.next();
+}
+
+// returns the number of n in the probe set for which the multiply-shift reduction disagrees with n % m
+int emu_mod_magic_mismatches(unsigned m) {
+    uint32_t magic, shift;
+    mod_magic(m, magic, shift);
+    int bad = 0;
+    auto check = [&](uint32_t raw) {
+        const uint32_t n = raw >> 1;
+        if ((uint32_t)draw_mod(raw, m, magic, shift) != n % m) bad++;
+    };
+    for (uint32_t i = 0; i < 200000; i++) {
+        check(i);
+        check(0xFFFFFFFFu - i);
+        check(i * 2654435761u);
+        check((uint32_t)(((uint64_t)i * m) << 1));          // multiples of m
+        check((uint32_t)((((uint64_t)i * m) << 1) - 2));    // just below a multiple
+    }
+    return bad;
+}
+
+// head-switch schedule of one field at absolute rand() position pos: returns hs_count, fills first/shifts
+int emu_head_switch(const cvs_params *p, int w, int h, unsigned field, unsigned long long pos, int *first,
+                    int *shifts, int cap) {
+    GeomPlan g;
+    build_geom_plan(*p, w, h, field, g);
+    RandCursor c;
+    c.seek(pos);
+    FieldSide fs;
+    build_field_side(*p, g, c, fs);
+    *first = fs.hs_first;
+    for (int i = 0; i < fs.hs_count && i < cap; i++) shifts[i] = fs.hs_shift[(size_t)i];
+    return fs.hs_count;
+}
+
 }  // extern "C"

@@ -32,6 +32,8 @@ def load_oracle():
         subprocess.check_call(["make", "liboracle.so"], cwd=ORACLE_DIR, stdout=subprocess.DEVNULL)
     lib = C.CDLL(path)
     lib.oracle_draws_per_field.restype = C.c_ulonglong
+    lib.oracle_fnv1a64.restype = C.c_ulonglong
+    lib.oracle_fnv1a64.argtypes = [C.c_void_p, C.c_ulonglong]
     lib.oracle_rng_next.restype = C.c_uint32
     return lib
 
@@ -86,13 +88,19 @@ def noise_frame(w, h, seed):
 
 
 def fnv1a64(arr):
-    """FNV-1a-64 of the bytes of arr (the hash of SURVEY.md App. D), vectorised per 64 KiB in C-free numpy."""
-    h = 1469598103934665603
-    prime = 1099511628211
-    mask = (1 << 64) - 1
-    for b in arr.tobytes():
-        h = ((h ^ b) * prime) & mask
-    return h
+    """FNV-1a-64 of the bytes of arr (the known-answer hash of SURVEY.md App. D)."""
+    a = np.ascontiguousarray(arr)
+    return int(load_oracle().oracle_fnv1a64(a.ctypes.data, a.nbytes))
+
+
+def load_golden():
+    """name -> (argv, w, h, n, dst) fixtures produced by the reference's own code (make_golden.py)."""
+    out = {}
+    for fn in sorted(os.listdir(GOLDEN_DIR)):
+        if fn.endswith(".npz"):
+            z = np.load(os.path.join(GOLDEN_DIR, fn))
+            out[fn[:-4]] = ([str(a) for a in z["argv"]], int(z["w"]), int(z["h"]), int(z["n"]), z["dst"])
+    return out
 
 
 def run_oracle(lib, p, frames, n, w, h, dst=None, g=None, interlaced=0, tff=0, field_fn=None):

@@ -58,3 +58,117 @@ def test_batch_equals_sequential(oracle):
         eng.composite_fields_host(bat, src, 0)
         assert eng.rng_tell() == pos
     assert np.array_equal(seq, bat)
+
+
+@pytest.mark.parametrize("name", sorted(helpers.load_golden().keys()))
+def test_golden_fixtures(name):
+    """Fixtures produced by the reference's own code (tests/golden/make_golden.py)."""
+    argv, w, h, n, want = helpers.load_golden()[name]
+    for use_double in (True, False):
+        got = np.zeros((h, w), dtype=np.uint32)
+        with cvs.Engine(argv=argv, max_w=w, max_h=h, max_batch=2) as eng:
+            eng.set_precision(use_double)
+            for k in range(n):
+                eng.composite_layer(got, helpers.stream_frame(w, h, k), (k & 1) ^ 1, k)
+        mx, nd, n2 = helpers.channel_diff(want, got)
+        assert (mx == 0) if use_double else (mx <= 1 and n2 == 0), (use_double, mx, nd, n2)
+
+
+def test_untouched_rows_and_alpha():
+    w, h = 160, 120
+    src = helpers.stream_frame(w, h, 0) | np.uint32(0xFF000000)       # alpha set in the source
+    dst = np.full((h, w), 0xDEADBEEF, dtype=np.uint32)
+    with cvs.Engine(["-vhs"], max_w=w, max_h=h, max_batch=1) as eng:
+        eng.composite_layer(dst, src, 1, 0)
+    assert (dst[0::2] == 0xDEADBEEF).all()                            # other parity untouched (:1910)
+    assert (dst[1::2] >> 24 == 0).all()                               # alpha = 0 (:1914)
+
+
+def test_invalid_geometry_leaves_dst_untouched():
+    w, h = 64, 32
+    src = helpers.stream_frame(w, h, 0)
+    dst = np.full((h, w), 7, dtype=np.uint32)
+    with cvs.Engine([], max_w=w, max_h=h, max_batch=1) as eng:
+        with pytest.raises(cvs.CvsError) as e:
+            eng.composite_layer(dst, src, 0, 0, dst_stride=4 * w - 4)   # stride < 4*w, :1580
+        assert e.value.status == -1
+        assert eng.rng_tell() == 0
+        with pytest.raises(cvs.CvsError) as e:
+            eng.composite_layer(np.zeros((h * 2, w), np.uint32), np.zeros((h * 2, w), np.uint32), 0, 0)
+        assert e.value.status == -5                                   # larger than the context capacity
+    assert (dst == 7).all()
+
+
+def test_interlaced_source_rows(oracle):
+    w, h, n = 160, 121, 3
+    p = helpers.params("-vhs")
+    frames = lambda k: helpers.noise_frame(w, h, k)
+    want, _ = helpers.run_oracle(oracle, p, frames, n, w, h, interlaced=1, tff=1)
+    got = np.zeros((h, w), dtype=np.uint32)
+    with cvs.Engine(params=p, max_w=w, max_h=h, max_batch=1) as eng:
+        eng.set_precision(True)
+        for k in range(n):
+            eng.composite_layer(got, frames(k), (k & 1) ^ 1, k, src_interlaced=True, src_top_field_first=True)
+    assert np.array_equal(want, got)
+
+
+def test_device_pointers_and_batch_split():
+    """Device-resident form with torch tensors on a torch stream; one batch == several smaller batches;
+    unaligned row strides take the scalar load/store path and give the same pixels."""
+    import torch
+    w, h, n = 720, 480, 8
+    p = helpers.params("-vhs", "-vhs-speed", "lp")
+    src = torch.from_numpy(np.stack([helpers.stream_frame(w, h, k) for k in range(n)]).view(np.int32)).cuda()
+    a = torch.zeros_like(src)
+    b = torch.zeros_like(src)
+    st = torch.cuda.Stream()
+    with cvs.Engine(params=p, max_w=w, max_h=h, max_batch=n) as eng:
+        eng.set_stream(st.cuda_stream)
+        eng.composite_fields_device(a, src, n, h, w, 0)
+        pos = eng.rng_tell()
+        eng.rng_seek(0)
+        for k0 in range(0, n, 3):
+            m = min(3, n - k0)
+            eng.composite_fields_device(b[k0:], src[k0:], m, h, w, k0)
+        assert eng.rng_tell() == pos
+        eng.synchronize()
+        assert torch.equal(a, b)
+        # misaligned: pictures of width w-1 viewed inside the same buffers (stride 4*w, base + 4 bytes)
+        eng.rng_seek(0)
+        c = torch.zeros_like(src)
+        eng.composite_fields_device(c.data_ptr() + 4, src.data_ptr() + 4, n, h, w - 1, 0, dst_pic_stride=4 * w * h,
+                                    dst_stride=4 * w, src_pic_stride=4 * w * h, src_stride=4 * w)
+        eng.synchronize()
+    host = np.zeros((h, w - 1), dtype=np.uint32)
+    srcn = src.cpu().numpy().view(np.uint32)
+    with cvs.Engine(params=p, max_w=w, max_h=h, max_batch=1) as eng:
+        eng.composite_layer(host, np.ascontiguousarray(srcn[0][:, 1:]), 1, 0)
+    assert np.array_equal(c.cpu().numpy().view(np.uint32)[0][1::2, 1:], host[1::2])
+
+
+def test_1080p_vhs_sp_256_fields(oracle):
+    """BASELINE config 2: 1920x1080 VHS-SP, +-1 LSB vs the CPU path on 256 synthetic frames.  The oracle
+    runs the 256 calls serially into one reused picture; the GPU runs them as 4 batches."""
+    import ctypes as C
+    w, h, n, B = 1920, 1080, 256, 64
+    p = helpers.params("-vhs", "-vhs-speed", "sp")
+    g = helpers.OracleRng()
+    oracle.oracle_rng_seed(C.byref(g), 1)
+    want = np.zeros((h, w), dtype=np.uint32)
+    hist = np.zeros(3, dtype=np.int64)
+    with cvs.Engine(params=p, max_w=w, max_h=h, max_batch=B) as eng:
+        for k0 in range(0, n, B):
+            src = np.stack([helpers.stream_frame(w, h, k) for k in range(k0, k0 + B)])
+            got = np.zeros_like(src)
+            eng.composite_fields_host(got, src, k0)
+            for i in range(B):
+                k = k0 + i
+                f = (k & 1) ^ 1
+                oracle.oracle_composite_layer(C.byref(p), C.byref(g), want.ctypes.data_as(C.c_void_p), 4 * w,
+                                              src[i].ctypes.data_as(C.c_void_p), 4 * w, w, h, 0, 0, f, C.c_ulonglong(k))
+                d = np.abs(want[f::2].view(np.uint8).astype(np.int16) - got[i][f::2].view(np.uint8).astype(np.int16))
+                hist += np.bincount(np.minimum(d.ravel(), 2), minlength=3)
+        assert eng.rng_tell() == g.pos
+    print("delta histogram (0, 1, >=2):", hist.tolist())
+    assert hist[2] == 0
+    assert hist[1] <= 0.002 * hist.sum()
