@@ -9,7 +9,7 @@ import os
 from .params import CvsParams
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcvs_ntsc.so")
+LIB_PATH = os.environ.get("CVS_NTSC_LIB") or os.path.join(_HERE, "libcvs_ntsc.so")   # override: experiments only
 
 _lib = None
 

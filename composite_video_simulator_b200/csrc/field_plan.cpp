@@ -43,25 +43,26 @@ static double pole_alpha(double hz) {              // LowpassFilter::setFilter, 
 template <typename R>
 void make_kconst(const cvs_params &p, int w, int h, bool outfull, KConst<R> &K, std::vector<R> &lut) {
     std::memset(&K, 0, sizeof(K));
-    auto set = [](R &a, R &b, double alpha) { a = (R)alpha; b = (R)(1.0 - alpha); };
-    set(K.a_inI, K.b_inI, pole_alpha(1300000));            // :1442
-    set(K.a_inQ, K.b_inQ, pole_alpha(600000));
+    auto set = [](R &a, R &b, R &c, double alpha) { a = (R)alpha; b = (R)(1.0 - alpha); c = (R)(alpha * alpha * alpha); };
+    R unused_c;
+    set(K.a_inI, K.b_inI, K.c_inI, pole_alpha(1300000));   // :1442
+    set(K.a_inQ, K.b_inQ, K.c_inQ, pole_alpha(600000));
     const bool pre = p.composite_preemphasis != 0 && p.composite_preemphasis_cut > 0;   // :1614
-    if (pre) set(K.a_pre, K.b_pre, pole_alpha(p.composite_preemphasis_cut));
+    if (pre) set(K.a_pre, K.b_pre, unused_c, pole_alpha(p.composite_preemphasis_cut));
     K.preemph = (R)p.composite_preemphasis;
     double luma_cut = 2400000, chroma_cut = 320000;         // :1773-1791
     if (p.output_vhs_tape_speed == CVS_VHS_LP) { luma_cut = 1900000; chroma_cut = 300000; }
     if (p.output_vhs_tape_speed == CVS_VHS_EP) { luma_cut = 1400000; chroma_cut = 280000; }
-    set(K.a_luma, K.b_luma, pole_alpha(luma_cut));
-    set(K.a_chroma, K.b_chroma, pole_alpha(chroma_cut));
-    set(K.a_sharp, K.b_sharp, pole_alpha(luma_cut * 4));    // :1874
+    set(K.a_luma, K.b_luma, K.c_luma, pole_alpha(luma_cut));
+    set(K.a_chroma, K.b_chroma, K.c_chroma, pole_alpha(chroma_cut));
+    set(K.a_sharp, K.b_sharp, K.c_sharp, pole_alpha(luma_cut * 4));    // :1874
     K.sharpen = (R)p.vhs_out_sharpen;
     if (outfull) {                                          // composite_lowpass, :1442
-        set(K.a_outI, K.b_outI, pole_alpha(1300000));
-        set(K.a_outQ, K.b_outQ, pole_alpha(600000));
+        set(K.a_outI, K.b_outI, K.c_outI, pole_alpha(1300000));
+        set(K.a_outQ, K.b_outQ, K.c_outQ, pole_alpha(600000));
     } else {                                                // composite_lowpass_tv, :1411
-        set(K.a_outI, K.b_outI, pole_alpha(2600000));
-        set(K.a_outQ, K.b_outQ, pole_alpha(2600000));
+        set(K.a_outI, K.b_outI, K.c_outI, pole_alpha(2600000));
+        set(K.a_outQ, K.b_outQ, K.c_outQ, pole_alpha(2600000));
     }
     uint32_t f = 0;
     if (p.composite_in_chroma_lowpass) f |= F_IN_LP;
@@ -73,6 +74,11 @@ void make_kconst(const cvs_params &p, int w, int h, bool outfull, KConst<R> &K, 
     if (p.video_chroma_phase_noise != 0) f |= F_PHASE;
     if (!(f & F_IN_LP) || !(f & F_OUT_LP) || (f & (F_PREEMPH | F_NOCOLOR | F_SVIDEO)) ||
         p.subcarrier_amplitude != 50 || p.subcarrier_amplitude_back != 50)
+        f |= F_GENERAL;
+    // the fast path also assumes each noise source is in its preset state (luma noise on; chroma
+    // noise and phase noise on exactly when emulating VHS); anything else takes the general path
+    const bool vhs = p.emulating_vhs != 0;
+    if (p.video_noise == 0 || (p.video_chroma_noise != 0) != vhs || (p.video_chroma_phase_noise != 0) != vhs)
         f |= F_GENERAL;
     K.flags = f;
     K.pnoise = p.video_chroma_phase_noise < 0 ? -p.video_chroma_phase_noise : p.video_chroma_phase_noise;

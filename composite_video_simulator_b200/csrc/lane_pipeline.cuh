@@ -72,12 +72,13 @@ enum : uint32_t {
 // ---- launch-uniform constants -------------------------------------------------------------
 template <typename R>
 struct KConst {
-    R a_inI, b_inI, a_inQ, b_inQ;         // input chroma lowpass 1.3 MHz / 0.6 MHz   (:1442)
-    R a_pre, b_pre, preemph;              // composite pre-emphasis                    (:1621)
-    R a_luma, b_luma;                     // VHS luma lowpass                          (:1800)
-    R a_chroma, b_chroma;                 // VHS chroma lowpass                        (:1821)
-    R a_sharp, b_sharp, sharpen;          // VHS sharpen lowpass (4x luma cut), gain   (:1874,:1880)
-    R a_outI, b_outI, a_outQ, b_outQ;     // output chroma lowpass                     (:1411 / :1442)
+    // per filter: a = alpha, b = 1 - alpha, c = alpha^3 (gain of the scaled fp32 cascade, see Num<float>)
+    R a_inI, b_inI, c_inI, a_inQ, b_inQ, c_inQ;   // input chroma lowpass 1.3 MHz / 0.6 MHz   (:1442)
+    R a_pre, b_pre, preemph;                      // composite pre-emphasis                    (:1621)
+    R a_luma, b_luma, c_luma;                     // VHS luma lowpass                          (:1800)
+    R a_chroma, b_chroma, c_chroma;               // VHS chroma lowpass                        (:1821)
+    R a_sharp, b_sharp, c_sharp, sharpen;         // VHS sharpen lowpass (4x luma cut), gain   (:1874,:1880)
+    R a_outI, b_outI, c_outI, a_outQ, b_outQ, c_outQ;   // output chroma lowpass               (:1411 / :1442)
     const R *phase_lut;                   // [2*pnoise+1][2] = {sin, cos} of state*pi/100, state = -p..p (:1746-1749)
     uint32_t flags;
     int32_t pnoise;                       // video_chroma_phase_noise
@@ -122,6 +123,33 @@ template <> struct Num<double> {
         prev = add(stage1, stage2);
         return prev;
     }
+    // three cascaded poles; no truncation between stages (:1420/:1451/:1807/:1828/:1878)
+    static CVS_HD void cascade_reset(double p[3], double v, double /*alpha*/) { p[0] = v; p[1] = v; p[2] = v; }
+    static CVS_HD double cascade3(double p[3], double s, double a, double b, double /*c*/) {
+        s = pole(p[0], s, a, b);
+        s = pole(p[1], s, a, b);
+        return pole(p[2], s, a, b);
+    }
+    static CVS_HD double cascade3_trunc(double p[3], double s, double a, double b, double c) {
+        return trunc_(cascade3(p, s, a, b, c));
+    }
+    static CVS_HD double floor_half(double s) { return ::floor(mul(s, 0.5)); }          // C int '>> 1'
+    static CVS_HD double trunc_quarter(double s) { return ::trunc(mul(s, 0.25)); }     // C int '/ 4'
+    static CVS_HD void unpack_rgb(uint32_t px, int &r, int &g, int &b) {
+        r = (int)((px >> 16) & 0xFF); g = (int)((px >> 8) & 0xFF); b = (int)(px & 0xFF);
+    }
+    static CVS_HD void rgb2yiq(uint32_t px, double &Y, double &I, double &Q) {
+        int r, g, b;
+        unpack_rgb(px, r, g, b);
+        rgb2yiq(r, g, b, Y, I, Q);
+    }
+    static CVS_HD uint32_t yiq2bgra(double Y, double I, double Q) {                    // :1385-1396, :1914
+        const int r = clamp_(mix3(Y, 0.956, I, 0.621, Q));
+        const int g = clamp_(mix3(Y, -0.272, I, -0.647, Q));
+        const int b = clamp_(mix3(Y, -1.106, I, 1.703, Q));
+        return ((uint32_t)r << 16) | ((uint32_t)g << 8) | (uint32_t)b;
+    }
+    static CVS_HD int clamp_(double v) { const int i = (int)v; return i < 0 ? 0 : (i > 255 ? 255 : i); }
     static CVS_HD void rgb2yiq(int r, int g, int b, double &Y, double &I, double &Q) {   // :1375-1383
         const double dY = add(add(mul(0.30, r), mul(0.59, g)), mul(0.11, b));
         Y = trunc_(mul(256, dY));
@@ -138,7 +166,17 @@ template <> struct Num<double> {
     static CVS_HD double preemph(double s, double hp, double g) { return trunc_(add(s, mul(hp, g))); }                // :1626-1627
 };
 
+// fp32 notes.
+//  * Truncation / floor without the conversion (XU) pipe, which runs at 1/8 of the FP32 rate on
+//    sm_100: for |x| < 2^22, x + 1.5*2^23 lands where the fp32 ulp is 1, so an add with directed
+//    rounding IS the integer rounding:  floor(x) = (x +rd M) - M,  trunc(x) = (x +rz Ms) - Ms with
+//    Ms = copysign(M, x).  The product/sum inside an FFMA is exact before that single rounding, so
+//    trunc_mul(a, b) truncates the exact product; the host emulation reproduces it in double.
+//  * Scaled cascade: with P_k = p_k / alpha^k the recurrence p_k' = beta p_k + alpha p_(k-1)' becomes
+//    P_k' = beta P_k + P_(k-1)'  (one FFMA per pole) and the output is alpha^3 P_3' (one FMUL per
+//    cascade instead of one per pole).  Same sequential order as the reference, no re-association.
 template <> struct Num<float> {
+    static constexpr float kMagic = 12582912.0f;        // 1.5 * 2^23
     static CVS_HD float mul(float a, float b) {
 #if defined(__CUDA_ARCH__)
         return __fmul_rn(a, b);
@@ -161,22 +199,93 @@ template <> struct Num<float> {
         return ::fmaf(a, b, c);
 #endif
     }
-    static CVS_HD float trunc_(float a) { return ::truncf(a); }
-    static CVS_HD float floor_(float a) { return ::floorf(a); }
+    // trunc(x) for an fp32 value
+    static CVS_HD float trunc_(float a) {
+#if defined(__CUDA_ARCH__)
+        const float ms = __uint_as_float((__float_as_uint(a) & 0x80000000u) | 0x4B400000u);
+        return __fadd_rn(__fadd_rz(a, ms), -ms);
+#else
+        return ::truncf(a);
+#endif
+    }
+    // trunc(a * b) of the EXACT product, b > 0
+    static CVS_HD float trunc_mul_pos(float a, float b) {
+#if defined(__CUDA_ARCH__)
+        const float ms = __uint_as_float((__float_as_uint(a) & 0x80000000u) | 0x4B400000u);
+        return __fadd_rn(__fmaf_rz(a, b, ms), -ms);
+#else
+        return (float)::trunc((double)a * (double)b);
+#endif
+    }
+    static CVS_HD float floor_(float a) {
+#if defined(__CUDA_ARCH__)
+        return __fadd_rn(__fadd_rd(a, kMagic), -kMagic);
+#else
+        return ::floorf(a);
+#endif
+    }
+    static CVS_HD float floor_half(float s) {            // floor(s / 2), C int '>> 1'
+#if defined(__CUDA_ARCH__)
+        return __fadd_rn(__fmaf_rd(s, 0.5f, kMagic), -kMagic);
+#else
+        return ::floorf(s * 0.5f);
+#endif
+    }
+    static CVS_HD float trunc_quarter(float s) { return trunc_mul_pos(s, 0.25f); }   // C int '/ 4'
+
     static CVS_HD float pole(float &prev, float s, float alpha, float beta) {
-        prev = fma_(beta, prev, mul(alpha, s));      // one FFMA on the recurrence path
+        prev = fma_(beta, prev, mul(alpha, s));
         return prev;
     }
-    static CVS_HD void rgb2yiq(int r, int g, int b, float &Y, float &I, float &Q) {
-        const float rf = (float)r, gf = (float)g, bf = (float)b;
+    static CVS_HD void cascade_reset(float p[3], float v, float alpha) {
+        p[0] = v / alpha;
+        p[1] = p[0] / alpha;
+        p[2] = p[1] / alpha;
+    }
+    static CVS_HD float cascade3_raw(float p[3], float s, float b) {
+        p[0] = fma_(b, p[0], s);
+        p[1] = fma_(b, p[1], p[0]);
+        p[2] = fma_(b, p[2], p[1]);
+        return p[2];
+    }
+    static CVS_HD float cascade3(float p[3], float s, float /*a*/, float b, float c) { return mul(cascade3_raw(p, s, b), c); }
+    static CVS_HD float cascade3_trunc(float p[3], float s, float /*a*/, float b, float c) {
+        return trunc_mul_pos(cascade3_raw(p, s, b), c);
+    }
+    static CVS_HD void rgb2yiq(uint32_t px, float &Y, float &I, float &Q) {
+#if defined(__CUDA_ARCH__)
+        // 0x4B0000bb is the float 2^23 + bb: one PRMT + one FADD per channel instead of an I2F
+        const float rf = __fadd_rn(__uint_as_float(__byte_perm(px, 0x4B000000u, 0x7442)), -8388608.0f);
+        const float gf = __fadd_rn(__uint_as_float(__byte_perm(px, 0x4B000000u, 0x7441)), -8388608.0f);
+        const float bf = __fadd_rn(__uint_as_float(__byte_perm(px, 0x4B000000u, 0x7440)), -8388608.0f);
+#else
+        const float rf = (float)((px >> 16) & 0xFF), gf = (float)((px >> 8) & 0xFF), bf = (float)(px & 0xFF);
+#endif
         const float dY = fma_(0.11f, bf, fma_(0.59f, gf, mul(0.30f, rf)));
         const float bd = sub(bf, dY), rd = sub(rf, dY);
-        Y = trunc_(mul(256.0f, dY));
-        I = trunc_(mul(256.0f, fma_(0.74f, rd, mul(-0.27f, bd))));
-        Q = trunc_(mul(256.0f, fma_(0.48f, rd, mul(0.41f, bd))));
+        Y = trunc_mul_pos(dY, 256.0f);
+        I = trunc_mul_pos(fma_(0.74f, rd, mul(-0.27f, bd)), 256.0f);
+        Q = trunc_mul_pos(fma_(0.48f, rd, mul(0.41f, bd)), 256.0f);
     }
-    static CVS_HD float mix3(float Y, float ci, float I, float cq, float Q) {
-        return trunc_(mul(fma_(cq, Q, fma_(ci, I, Y)), 0.00390625f));
+    // one colour channel: clamp((Y + ci I + cq Q) / 256) truncated, returned as M + value (low byte = value)
+    static CVS_HD uint32_t chan_(float Y, float ci, float I, float cq, float Q) {
+        float v = mul(fma_(cq, Q, fma_(ci, I, Y)), 0.00390625f);
+        v = fminf(fmaxf(v, 0.0f), 255.0f);
+#if defined(__CUDA_ARCH__)
+        return __float_as_uint(__fadd_rz(v, kMagic));
+#else
+        return 0x4B400000u + (uint32_t)(int)v;
+#endif
+    }
+    static CVS_HD uint32_t yiq2bgra(float Y, float I, float Q) {
+        const uint32_t r = chan_(Y, 0.956f, I, 0.621f, Q);
+        const uint32_t g = chan_(Y, -0.272f, I, -0.647f, Q);
+        const uint32_t b = chan_(Y, -1.106f, I, 1.703f, Q);
+#if defined(__CUDA_ARCH__)
+        return __byte_perm(__byte_perm(b, g, 0x7740), r, 0x5410);   // r byte 1 is 0x00: alpha = 0
+#else
+        return ((r & 0xFF) << 16) | ((g & 0xFF) << 8) | (b & 0xFF);
+#endif
     }
     static CVS_HD float rot_a(float u, float c, float v, float s) { return trunc_(fma_(u, c, -mul(v, s))); }
     static CVS_HD float rot_b(float u, float s, float v, float c) { return trunc_(fma_(u, s, mul(v, c))); }
@@ -186,10 +295,9 @@ template <> struct Num<float> {
 };
 
 // integer helpers on integer-valued reals (all plane values are integers, |v| < 2^24)
-template <typename R> CVS_HD R div4_trunc(R s) { return Num<R>::trunc_(Num<R>::mul(s, (R)0.25)); }   // C int '/ 4'
-template <typename R> CVS_HD R shr1_floor(R s) { return Num<R>::floor_(Num<R>::mul(s, (R)0.5)); }   // C int '>> 1'
+template <typename R> CVS_HD R div4_trunc(R s) { return Num<R>::trunc_quarter(s); }   // C int '/ 4'
+template <typename R> CVS_HD R shr1_floor(R s) { return Num<R>::floor_half(s); }      // C int '>> 1'
 
-CVS_HD int clamp255(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
 
 // (v * num) / den on C ints (truncation toward zero); |v*num| < 2^31 by construction
 CVS_HD int muldiv_trunc(int v, int num, int den) { return (v * num) / den; }
@@ -310,27 +418,18 @@ struct Lane {
         CVS_UNROLL
         for (int k = 0; k < 3; k++) {
             pI[k] = 0; pQ[k] = 0;           // resetFilter(0), :1447
-            pL[k] = 16;                     // resetFilter(16), :1802
             pS[k] = 0;                      // :1875
             pU[k] = 0; pV[k] = 0;           // :1823,:1825
             pOI[k] = 0; pOQ[k] = 0;         // :1416
         }
+        Num<R>::cascade_reset(pL, (R)16, K.a_luma);   // resetFilter(16), :1802
         pLpre = 16;                         // :1805
         pPre = 16;                          // :1622
         Cm1 = 0; C2m1 = 0;
         CVS_UNROLL
         for (int k = 0; k < OD; k++) { Ytail[k] = 0; Itail[k] = 0; Qtail[k] = 0; oOItail[k] = 0; oOQtail[k] = 0; }
-        (void)K;
     }
 };
-
-// three cascaded poles (no truncation between stages, :1420/:1451/:1807/:1828/:1878)
-template <typename R>
-CVS_HD R cascade3(R p[3], R s, R a, R b) {
-    s = Num<R>::pole(p[0], s, a, b);
-    s = Num<R>::pole(p[1], s, a, b);
-    return Num<R>::pole(p[2], s, a, b);
-}
 
 // QAM modulation of one sample (chroma_into_luma, :1486-1490).  amp == 50 makes (v*50)/50 == v.
 template <typename R, bool EDGE>
@@ -448,10 +547,10 @@ struct Pipeline {
             const int t = p + j;
             if (!EDGE || t < w) {
                 R y, i, q;
-                N::rgb2yiq((int)((px[j] >> 16) & 0xFF), (int)((px[j] >> 8) & 0xFF), (int)(px[j] & 0xFF), y, i, q);
+                N::rgb2yiq(px[j], y, i, q);
                 Ycur[j] = y;
-                oIcur[j] = N::trunc_(cascade3<R>(ln.pI, i, K.a_inI, K.b_inI));   // P[x-delay] = s, :1453
-                oQcur[j] = N::trunc_(cascade3<R>(ln.pQ, q, K.a_inQ, K.b_inQ));
+                oIcur[j] = N::cascade3_trunc(ln.pI, i, K.a_inI, K.b_inI, K.c_inI);   // P[x-delay] = s, :1453
+                oQcur[j] = N::cascade3_trunc(ln.pQ, q, K.a_inQ, K.b_inQ, K.c_inQ);
             } else {
                 Ycur[j] = 0; oIcur[j] = 0; oQcur[j] = 0;
             }
@@ -472,8 +571,7 @@ struct Pipeline {
                         const bool rawI = !in_lp || (x + 2 >= w), rawQ = !in_lp || (x + 4 >= w);
                         if (rawI || rawQ) {
                             R y, i, q;
-                            N::rgb2yiq((int)((ln.pxprev[j] >> 16) & 0xFF), (int)((ln.pxprev[j] >> 8) & 0xFF),
-                                       (int)(ln.pxprev[j] & 0xFF), y, i, q);
+                            N::rgb2yiq(ln.pxprev[j], y, i, q);
                             if (rawI) iv = i;
                             if (rawQ) qv = q;
                         }
@@ -483,12 +581,12 @@ struct Pipeline {
                         const R lp = N::pole(ln.pPre, c, K.a_pre, K.b_pre);
                         c = N::preemph(c, N::sub(c, lp), K.preemph);
                     }
-                    if (K.vnoise != 0) {                                                             // :1631-1644
+                    if (!EDGE || K.vnoise != 0) {                                                    // :1631-1644
                         c = N::add(c, (R)ln.nY);
                         const int d = draw_mod(ln.rngL.next_raw(kRngBase + (uint32_t)x), (uint32_t)(2 * K.vnoise + 1), K.vmagic, K.vshift);
                         ln.nY = noise_step(ln.nY, d, K.vnoise);
                     }
-                    if (hs_row && (rc.rflags & RF_HEADSW)) c = (R)hs_row[x];                         // :1646-1713
+                    if (EDGE && hs_row && (rc.rflags & RF_HEADSW)) c = (R)hs_row[x];                 // :1646-1713
                 }
                 Cnew[j] = c;
             }
@@ -535,7 +633,7 @@ struct Pipeline {
         for (int j = 0; j < kT; j++) ln.Cprev[j] = Cnew[j];
 
         const int x0 = k * kT;
-        if (K.cnoise != 0) {                                       // :1718-1735
+        if (EDGE ? (K.cnoise != 0) : VHS) {                        // :1718-1735
             CVS_UNROLL
             for (int j = 0; j < kT; j++) {
                 if (!EDGE || x0 + j < w) {
@@ -549,7 +647,7 @@ struct Pipeline {
                 }
             }
         }
-        if (K.flags & F_PHASE) {                                   // :1736-1764
+        if (EDGE ? ((K.flags & F_PHASE) != 0) : VHS) {             // :1736-1764
             CVS_UNROLL
             for (int j = 0; j < kT; j++) {
                 const R u = Ib[j], v = Qb[j];
@@ -565,13 +663,13 @@ struct Pipeline {
         CVS_UNROLL
         for (int j = 0; j < kT; j++) {
             if (!EDGE || x0 + j < w) {
-                R sv = cascade3<R>(ln.pL, Yb[j], K.a_luma, K.b_luma);
+                R sv = N::cascade3(ln.pL, Yb[j], K.a_luma, K.b_luma, K.c_luma);
                 const R lp = N::pole(ln.pLpre, sv, K.a_luma, K.b_luma);
                 const R y2 = N::boost(sv, N::sub(sv, lp), (R)1.6);
-                const R ts = cascade3<R>(ln.pS, y2, K.a_sharp, K.b_sharp);
+                const R ts = N::cascade3(ln.pS, y2, K.a_sharp, K.b_sharp, K.c_sharp);
                 Yb[j] = N::sharpen(y2, ts, K.sharpen);
-                oUcur[j] = N::trunc_(cascade3<R>(ln.pU, Ib[j], K.a_chroma, K.b_chroma));
-                oVcur[j] = N::trunc_(cascade3<R>(ln.pV, Qb[j], K.a_chroma, K.b_chroma));
+                oUcur[j] = N::cascade3_trunc(ln.pU, Ib[j], K.a_chroma, K.b_chroma, K.c_chroma);
+                oVcur[j] = N::cascade3_trunc(ln.pV, Qb[j], K.a_chroma, K.b_chroma, K.c_chroma);
                 if (EDGE && (x0 + j >= w - CD) && (x0 + j - (w - CD)) < kTailSlots) {
                     // the last CD samples keep their pre-filter values (:1830,:1834): stash them
                     ln.tailU[(x0 + j - (w - CD)) * ln.tail_stride] = Ib[j];
@@ -665,16 +763,15 @@ struct Pipeline {
         const int w = K.w;
         if (EDGE && kf < 0) return false;
         const int x0 = kf * kT;
-        if (rc.rflags & RF_DROPOUT) {                                 // :1891-1901
-            CVS_UNROLL
-            for (int j = 0; j < kT; j++) { If[j] = 0; Qf[j] = 0; }
-        }
+        const bool drop = (rc.rflags & RF_DROPOUT) != 0;              // :1891-1901
+        CVS_UNROLL
+        for (int j = 0; j < kT; j++) { If[j] = drop ? (R)0 : If[j]; Qf[j] = drop ? (R)0 : Qf[j]; }
         R oI[kT], oQ[kT];
         CVS_UNROLL
         for (int j = 0; j < kT; j++) {
             if (!EDGE || x0 + j < w) {
-                oI[j] = N::trunc_(cascade3<R>(ln.pOI, If[j], K.a_outI, K.b_outI));   // :1420-1422
-                oQ[j] = N::trunc_(cascade3<R>(ln.pOQ, Qf[j], K.a_outQ, K.b_outQ));
+                oI[j] = N::cascade3_trunc(ln.pOI, If[j], K.a_outI, K.b_outI, K.c_outI);   // :1420-1422
+                oQ[j] = N::cascade3_trunc(ln.pOQ, Qf[j], K.a_outQ, K.b_outQ, K.c_outQ);
             } else {
                 oI[j] = 0; oQ[j] = 0;
             }
@@ -699,10 +796,7 @@ struct Pipeline {
                 if (!out_lp || pos + ODQ >= w) qv = qr;
             }
             // YIQ -> RGB (:1385-1396), alpha = 0 (:1914)
-            const int r = clamp255((int)N::mix3(yv, (R)0.956, iv, (R)0.621, qv));
-            const int g = clamp255((int)N::mix3(yv, (R)-0.272, iv, (R)-0.647, qv));
-            const int b = clamp255((int)N::mix3(yv, (R)-1.106, iv, (R)1.703, qv));
-            pk[j] = ((uint32_t)r << 16) | ((uint32_t)g << 8) | (uint32_t)b;
+            pk[j] = N::yiq2bgra(yv, iv, qv);
         }
         // out block B(kf-1): slots 0..7-OD carried from the previous step, slots 8-OD..7 are pk[0..OD-1]
         CVS_UNROLL
@@ -720,6 +814,16 @@ struct Pipeline {
         return kf >= 1;
     }
 };
+
+// Head-switch substitution of a finished composite block B(k) (fast path; the general path does it
+// inline): rows rotated by the head switch read their composite signal from the scratch row.
+template <typename R>
+CVS_HD void headswitch_substitute(const RowConst<R> &rc, const int32_t *hs_row, int k, R C[kT]) {
+    if (hs_row && (rc.rflags & RF_HEADSW)) {
+        CVS_UNROLL
+        for (int j = 0; j < kT; j++) C[j] = (R)hs_row[k * kT + j];
+    }
+}
 
 // number of steps a line of width w takes
 template <bool VHS>

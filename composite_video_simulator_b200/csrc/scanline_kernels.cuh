@@ -24,6 +24,9 @@ namespace cvs {
 
 constexpr int kNT = 128;                 // threads per CTA (4 warps)
 constexpr int kWarpsPerCta = kNT / 32;
+#ifndef CVS_MIN_CTAS
+#define CVS_MIN_CTAS 2              // CTAs per SM the register allocator must leave room for
+#endif
 constexpr int kRowsPerWarp = 31;         // lane 0 is the halo row of the vertical chroma blend
 
 struct FieldDesc {
@@ -84,11 +87,12 @@ struct Stepper {
 
     template <bool EDGE>
     static __device__ __forceinline__ void step(const KConst<R> &K, const RowConst<R> &rc, L &ln, int s,
-                                                const uint32_t px[kT], const int32_t *hsrow, bool valid,
-                                                uint32_t *drow, bool vec_dst) {
+                                                const uint32_t px[kT], const int32_t *hsrow, bool warp_hs,
+                                                bool valid, uint32_t *drow, bool vec_dst) {
         R C[kT], Yb[kT], Ib[kT], Qb[kT];
         BlendXchg<R> xo;
         P::template stage_a<EDGE>(K, rc, ln, s, px, hsrow, C);
+        if (!EDGE && warp_hs) headswitch_substitute<R>(rc, hsrow, s - 1, C);
         P::template stage_b<EDGE>(K, rc, ln, s, C, Yb, Ib, Qb, xo);
         uint32_t out[kT];
         bool have;
@@ -136,7 +140,7 @@ __device__ __forceinline__ void load_block_dev(const uint32_t *srow, int k, int 
 }
 
 template <typename R, bool VHS, int CD, bool OUTFULL>
-__global__ void __launch_bounds__(kNT) k_fields(const __grid_constant__ LaunchArgs<R> a) {
+__global__ void __launch_bounds__(kNT, CVS_MIN_CTAS) k_fields(const __grid_constant__ LaunchArgs<R> a) {
     typedef Lane<R, VHS, CD, OUTFULL> L;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t *rings = reinterpret_cast<uint32_t *>(smem_raw);
@@ -199,6 +203,7 @@ __global__ void __launch_bounds__(kNT) k_fields(const __grid_constant__ LaunchAr
     interior_steps<VHS>(w, s_lo, s_hi);
     if (K.flags & F_GENERAL) s_hi = s_lo;
     const bool vec_src = a.vec_src != 0, vec_dst = a.vec_dst != 0;
+    const bool warp_hs = __any_sync(0xffffffffu, hsrow != nullptr);
 
     uint32_t px[kT];
     load_block_dev(srow, 0, w, vec_src, px);
@@ -207,9 +212,9 @@ __global__ void __launch_bounds__(kNT) k_fields(const __grid_constant__ LaunchAr
         uint32_t pxn[kT];
         load_block_dev(srow, s + 1, w, vec_src, pxn);            // prefetch the next block
         if (s >= s_lo && s < s_hi)
-            Stepper<R, VHS, CD, OUTFULL>::template step<false>(K, rc, ln, s, px, hsrow, valid, drow, vec_dst);
+            Stepper<R, VHS, CD, OUTFULL>::template step<false>(K, rc, ln, s, px, hsrow, warp_hs, valid, drow, vec_dst);
         else
-            Stepper<R, VHS, CD, OUTFULL>::template step<true>(K, rc, ln, s, px, hsrow, valid, drow, vec_dst);
+            Stepper<R, VHS, CD, OUTFULL>::template step<true>(K, rc, ln, s, px, hsrow, warp_hs, valid, drow, vec_dst);
 #pragma unroll
         for (int j = 0; j < kT; j++) px[j] = pxn[j];
     }

@@ -118,6 +118,7 @@ int run_field(const cvs_params &p, RandCursor &cur, uint8_t *dst, int dst_stride
                 R C[kT];
                 if (fast) {
                     P::template stage_a<false>(K, rc[l], lane[l], s, px, hsrow[l], C);
+                    headswitch_substitute<R>(rc[l], hsrow[l], s - 1, C);
                     P::template stage_b<false>(K, rc[l], lane[l], s, C, Yb[l], Ib[l], Qb[l], xo[l]);
                 } else {
                     P::template stage_a<true>(K, rc[l], lane[l], s, px, hsrow[l], C);

@@ -172,3 +172,19 @@ def test_1080p_vhs_sp_256_fields(oracle):
     print("delta histogram (0, 1, >=2):", hist.tolist())
     assert hist[2] == 0
     assert hist[1] <= 0.002 * hist.sum()
+
+
+@pytest.mark.parametrize("w,h,n,argv", [(720, 480, 3, ["-vhs"]), (724, 482, 2, ["-vhs", "-vhs-speed", "ep"]),
+                                        (720, 480, 2, []), (101, 67, 2, ["-vhs", "-comp-catv", "-vhs-svideo", "1"])])
+def test_gpu_fp32_is_bit_identical_to_cpu_emulation(emu, w, h, n, argv):
+    """The fp32 kernels fuse exactly where lane_pipeline.cuh says so (-fmad=false), so the GPU and the
+    host emulation of the same source agree bit for bit -- the CPU parity suite therefore speaks for
+    the GPU arithmetic as well."""
+    p = helpers.params(*argv)
+    frames = lambda k: helpers.stream_frame(w, h, k)
+    want, _ = helpers.run_emu(emu, p, frames, n, w, h, precision=0)
+    got = np.zeros((h, w), dtype=np.uint32)
+    with cvs.Engine(params=p, max_w=w, max_h=h, max_batch=1) as eng:
+        for k in range(n):
+            eng.composite_layer(got, frames(k), (k & 1) ^ 1, k)
+    assert np.array_equal(want, got)
