@@ -281,7 +281,6 @@ def run_own_arm(args):
     e1.synchronize()
     eng.synchronize()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)
     launches = eng.kernel_launches() - launches0
     kms, kn = eng.kernel_time_query()
@@ -303,11 +302,11 @@ def run_own_arm(args):
         eng.rng_seek(sharding.stream_position(params, W, H, base))
         eng.composite_fields_host(hd_np, hs_np, base)      # synchronous
 
-    for i in range(max(1, args.warmup // 2)):
+    for i in range(2):
         e2e_step(i)
     barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(1, args.steps)
+    e2e_steps = max(2, args.steps // 2)
     for i in range(e2e_steps):
         e2e_step(i)
     torch.cuda.synchronize()
@@ -317,6 +316,7 @@ def run_own_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * Be * e2e_steps / float(t[0])
     e2e_checksum = int(hd_np[0, 1::2].sum() & 0xFFFFFFFF)    # the step's result is read on the host
+    clocks = sampler.stop() if rank == 0 else None           # sampled over both timed regions
 
     if rank != 0:
         if dist is not None:
@@ -336,7 +336,8 @@ def run_own_arm(args):
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            traffic = json.load(f).get("k_fields_sp_dram_bytes_per_launch")
+            tj = json.load(f)        # measured by one `ncu --set full` capture, scaled to this launch size
+            traffic = tj["k_fields_sp_dram_bytes_per_launch_64_fields"] / tj["fields_per_launch_in_capture"] * B
     except Exception:
         pass
 
@@ -374,11 +375,11 @@ def run_own_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="fields per GPU per step (device-resident)")
-    ap.add_argument("--e2e-batch", type=int, default=64, help="fields per GPU per step (host buffers)")
+    ap.add_argument("--e2e-batch", type=int, default=256, help="fields per GPU per step (host buffers)")
     ap.add_argument("--cpu-fields", type=int, default=64, help="fields of the single-thread CPU baseline sample")
     ap.add_argument("--ref-fields-per-proc", type=int, default=4)
     args = ap.parse_args()

@@ -25,6 +25,7 @@ namespace {
 
 constexpr int kStagingSlots = 3;
 constexpr size_t kMaxEventPairs = 4096;
+constexpr int kHostChunk = 16;              // fields per pipeline stage of the host-pointer entry points
 
 struct DevPlan {
     int w = 0, h = 0;
@@ -56,6 +57,8 @@ struct cvs_ctx {
     int precision = 0;                         // 0 = float (production), 1 = double (reference arithmetic)
     cudaStream_t stream = nullptr;
     bool own_stream = true;
+    cudaStream_t s_in = nullptr, s_out = nullptr;      // upload / download streams of the host-pointer path
+    std::vector<cudaEvent_t> ev_in, ev_k;              // per chunk: upload done / kernels done
     // CUDA-event pairs around every k_fields launch since the last cvs_kernel_time_reset()
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
     size_t ev_used = 0;
@@ -116,6 +119,11 @@ void free_all(cvs_ctx *c) {
     cudaFree(c->d_src); cudaFree(c->d_dst);
     if (c->h_status) cudaFreeHost(c->h_status);
     for (auto &pr : c->ev_pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    for (auto e : c->ev_in) cudaEventDestroy(e);
+    for (auto e : c->ev_k) cudaEventDestroy(e);
+    c->ev_in.clear(); c->ev_k.clear();
+    if (c->s_in) cudaStreamDestroy(c->s_in);
+    if (c->s_out) cudaStreamDestroy(c->s_out);
     c->ev_pool.clear();
     if (c->stream && c->own_stream) cudaStreamDestroy(c->stream);
 }
@@ -287,6 +295,11 @@ int check_status(cvs_ctx *c) {
     return CVS_OK;
 }
 
+// Host-pointer form.  The batch is cut into chunks of kHostChunk fields and pipelined over three
+// streams: chunk i+1 is uploaded (copy engine 1) while chunk i is computed and chunk i-1 is
+// downloaded (copy engine 2), so PCIe runs full duplex and the kernels hide behind it.  Only the rows
+// of the requested field cross the bus: source rows min(field + 2r + opposite, h-1) (:1599) in, dst
+// rows field + 2r out; every other dst row stays untouched on the host, as in the reference (:1910).
 int run_host(cvs_ctx *c, uint8_t *dst, size_t dst_pic_stride, int dst_stride, const uint8_t *src,
              size_t src_pic_stride, int src_stride, int w, int h, int interlaced, int tff, int n,
              unsigned long long first_fieldno, int explicit_field) {
@@ -308,36 +321,54 @@ int run_host(cvs_ctx *c, uint8_t *dst, size_t dst_pic_stride, int dst_stride, co
         CVS_CUDA(cudaMalloc((void **)&c->d_dst, dpic * (size_t)n));
         c->d_pic_cap = dpic * (size_t)n;
     }
+    const int nchunks = (n + kHostChunk - 1) / kHostChunk;
+    while ((int)c->ev_in.size() < nchunks) {
+        cudaEvent_t a, b;
+        CVS_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        CVS_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        c->ev_in.push_back(a);
+        c->ev_k.push_back(b);
+    }
     const int opposite = interlaced ? (tff ? 1 : 0) : 0;
-    for (int k = 0; k < n; k++) {
+    auto field_of = [&](int k) {
         const unsigned long long fieldno = first_fieldno + (unsigned long long)k;
-        const int field = explicit_field >= 0 ? explicit_field : (int)((fieldno & 1) ^ 1);
-        if (field >= h) continue;
-        const int nl = (h - field + 1) / 2;
-        // source rows min(field + 2r + opposite, h-1): a stride-2 run, plus the clamped last row (:1599)
-        const int y0 = field + opposite;
-        int nreg = nl;
-        if (y0 + 2 * (nl - 1) > h - 1) nreg = nl - 1;
-        const uint8_t *hs = src + (size_t)k * src_pic_stride;
-        uint8_t *ds = c->d_src + (size_t)k * dpic;
-        if (nreg > 0)
-            CVS_CUDA(cudaMemcpy2DAsync(ds + (size_t)y0 * dstride, (size_t)2 * dstride, hs + (size_t)y0 * src_stride,
-                                       (size_t)2 * src_stride, (size_t)4 * w, (size_t)nreg, cudaMemcpyHostToDevice, c->stream));
-        if (nreg < nl)
-            CVS_CUDA(cudaMemcpyAsync(ds + (size_t)(h - 1) * dstride, hs + (size_t)(h - 1) * src_stride, (size_t)4 * w,
-                                     cudaMemcpyHostToDevice, c->stream));
+        return explicit_field >= 0 ? explicit_field : (int)((fieldno & 1) ^ 1);
+    };
+    for (int ci = 0; ci < nchunks; ci++) {
+        const int k0 = ci * kHostChunk, k1 = (k0 + kHostChunk < n) ? k0 + kHostChunk : n;
+        for (int k = k0; k < k1; k++) {                       // upload, stream s_in
+            const int field = field_of(k);
+            if (field >= h) continue;
+            const int nl = (h - field + 1) / 2;
+            const int y0 = field + opposite;
+            int nreg = nl;                                    // stride-2 run, plus the clamped last row
+            if (y0 + 2 * (nl - 1) > h - 1) nreg = nl - 1;
+            const uint8_t *hs = src + (size_t)k * src_pic_stride;
+            uint8_t *ds = c->d_src + (size_t)k * dpic;
+            if (nreg > 0)
+                CVS_CUDA(cudaMemcpy2DAsync(ds + (size_t)y0 * dstride, (size_t)2 * dstride, hs + (size_t)y0 * src_stride,
+                                           (size_t)2 * src_stride, (size_t)4 * w, (size_t)nreg, cudaMemcpyHostToDevice, c->s_in));
+            if (nreg < nl)
+                CVS_CUDA(cudaMemcpyAsync(ds + (size_t)(h - 1) * dstride, hs + (size_t)(h - 1) * src_stride, (size_t)4 * w,
+                                         cudaMemcpyHostToDevice, c->s_in));
+        }
+        CVS_CUDA(cudaEventRecord(c->ev_in[ci], c->s_in));
+        CVS_CUDA(cudaStreamWaitEvent(c->stream, c->ev_in[ci], 0));
+        int rc = run_device(c, c->d_dst + (size_t)k0 * dpic, dpic, dstride, c->d_src + (size_t)k0 * dpic, dpic, dstride, w, h,
+                            interlaced, tff, k1 - k0, first_fieldno + (unsigned long long)k0, explicit_field);
+        if (rc != CVS_OK) { cudaStreamSynchronize(c->s_in); cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->s_out); return rc; }
+        CVS_CUDA(cudaEventRecord(c->ev_k[ci], c->stream));
+        CVS_CUDA(cudaStreamWaitEvent(c->s_out, c->ev_k[ci], 0));
+        for (int k = k0; k < k1; k++) {                       // download, stream s_out
+            const int field = field_of(k);
+            if (field >= h) continue;
+            const int nl = (h - field + 1) / 2;
+            CVS_CUDA(cudaMemcpy2DAsync(dst + (size_t)k * dst_pic_stride + (size_t)field * dst_stride, (size_t)2 * dst_stride,
+                                       c->d_dst + (size_t)k * dpic + (size_t)field * dstride, (size_t)2 * dstride,
+                                       (size_t)4 * w, (size_t)nl, cudaMemcpyDeviceToHost, c->s_out));
+        }
     }
-    int rc = run_device(c, c->d_dst, dpic, dstride, c->d_src, dpic, dstride, w, h, interlaced, tff, n, first_fieldno, explicit_field);
-    if (rc != CVS_OK) return rc;
-    for (int k = 0; k < n; k++) {
-        const unsigned long long fieldno = first_fieldno + (unsigned long long)k;
-        const int field = explicit_field >= 0 ? explicit_field : (int)((fieldno & 1) ^ 1);
-        if (field >= h) continue;
-        const int nl = (h - field + 1) / 2;
-        CVS_CUDA(cudaMemcpy2DAsync(dst + (size_t)k * dst_pic_stride + (size_t)field * dst_stride, (size_t)2 * dst_stride,
-                                   c->d_dst + (size_t)k * dpic + (size_t)field * dstride, (size_t)2 * dstride,
-                                   (size_t)4 * w, (size_t)nl, cudaMemcpyDeviceToHost, c->stream));
-    }
+    CVS_CUDA(cudaStreamSynchronize(c->s_out));
     return check_status(c);
 }
 
@@ -362,6 +393,8 @@ int cvs_create(cvs_ctx **out, const cvs_params *p, int device, int max_w, int ma
     c->hs_max = head_switch_rows_bound(max_w);
     if (c->hs_max > c->nl_max) c->hs_max = c->nl_max;
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking);
     for (auto &s : c->slots) {
         if (e == cudaSuccess) e = pin_alloc(&s.h_fields, (size_t)max_batch);
         if (e == cudaSuccess) e = pin_alloc(&s.h_rowinfo, (size_t)max_batch * c->nl_max);

@@ -174,21 +174,34 @@ void build_field_side(const cvs_params &p, const GeomPlan &g, RandCursor &cur, F
         y -= p.output_ntsc ? (262 - 240) * 2 : (312 - 288) * 2;
         const int ishif = (hx >= twidth / 2) ? (int)hx - (int)twidth : (int)hx;
         int shif = 0, shy = 0;
+        std::vector<int> rows, shifts;
         while (y < h) {
             // the first affected row has shif == 0, so its start column never matters (:1683-1711)
             if (y >= 0 && shif != 0) {
-                const int row = (y - (int)field) / 2;
-                if (fs.hs_count == 0) fs.hs_first = row;
-                // rows are consecutive until the shift decays to zero
-                fs.hs_shift.push_back(shif);
-                fs.hs_count++;
-                fs.rowinfo[(size_t)row] |= (uint32_t)RF_HEADSW << 16;
-            } else if (fs.hs_count != 0 && shif == 0) {
+                rows.push_back((y - (int)field) / 2);
+                shifts.push_back(shif);
+            } else if (!rows.empty() && shif == 0) {
                 break;              // decayed: no later row is shifted
             }
             shif = (shy == 0) ? ishif : (shif * 7) / 8;
             y += 2;
             shy++;
+        }
+        // A negative shift -d moves the row right by d; the pixels that wrap in come from
+        // tmp[twidth - d + x], which is zero padding for every x when d <= w/10.  Then the rotation is
+        // a plain delay and k_fields does it in shared memory; anything else goes through the pre-pass.
+        bool inline_ok = !rows.empty();
+        for (int sh : shifts)
+            if (!(sh < 0 && -sh <= kHsMaxDelay && -sh <= w / 10)) inline_ok = false;
+        for (size_t i = 0; i < rows.size(); i++) {
+            if (inline_ok) {
+                fs.rowinfo[(size_t)rows[i]] |= ((uint32_t)RF_HEADSW_INLINE << 16) | ((uint32_t)(-shifts[i]) << 24);
+            } else {
+                if (fs.hs_count == 0) fs.hs_first = rows[i];       // rows are consecutive
+                fs.hs_shift.push_back(shifts[i]);
+                fs.hs_count++;
+                fs.rowinfo[(size_t)rows[i]] |= (uint32_t)RF_HEADSW << 16;
+            }
         }
     }
 

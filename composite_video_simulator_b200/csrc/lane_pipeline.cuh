@@ -66,8 +66,11 @@ enum : uint32_t {
 // per-row flags (host side table)
 enum : uint32_t {
     RF_DROPOUT = 1u << 0,     // chroma dropout hit this row (:1896)
-    RF_HEADSW = 1u << 1,      // row is rotated by the head switch; C comes from scratch
+    RF_HEADSW = 1u << 1,      // row is rotated by the head switch; C comes from the scratch row (pre-pass)
+    RF_HEADSW_INLINE = 1u << 2,   // row is rotated by a small right shift with zero fill: delayed in-kernel
 };
+constexpr int kHsRing = 64;               // per-lane delay ring of the in-kernel head switch
+constexpr int kHsMaxDelay = kHsRing - kT; // largest shift the ring can express
 
 // ---- launch-uniform constants -------------------------------------------------------------
 template <typename R>
@@ -356,6 +359,7 @@ struct RowConst {
     int xi;              // subcarrier phase index (:1473-1480)
     uint32_t rflags;
     int row;             // field row index (y = field + 2*row)
+    int hs_delay;        // RF_HEADSW_INLINE: C'[x] = C[x - hs_delay], 0 for x < hs_delay
 };
 
 template <typename R>
@@ -825,6 +829,23 @@ CVS_HD void headswitch_substitute(const RowConst<R> &rc, const int32_t *hs_row, 
     }
 }
 
+// In-kernel head switch for the common case (ffmpeg_ntsc.cpp:1683-1700 with a small negative shift
+// whose wrapped-in part is entirely zero padding): Y'[x] = Y[x - d] for x >= d, 0 below.  The finished
+// composite block B(k) goes through a per-lane ring (ring[(x & 63) * stride], already offset by the
+// lane) and comes back delayed by the lane's own d (0 for rows that are not rotated).
+template <typename R>
+CVS_HD void headswitch_delay_block(R *ring, int stride, int k, int w, int d, R C[kT]) {
+    const int x0 = k * kT;
+    CVS_UNROLL
+    for (int j = 0; j < kT; j++) ring[((x0 + j) & (kHsRing - 1)) * stride] = C[j];
+    CVS_UNROLL
+    for (int j = 0; j < kT; j++) {
+        const int xs = x0 + j - d;
+        const R v = ring[(xs & (kHsRing - 1)) * stride];
+        C[j] = (xs >= 0 && x0 + j < w) ? v : (R)0;          // the composite signal is zero beyond the line end
+    }
+}
+
 // number of steps a line of width w takes
 template <bool VHS>
 CVS_HD int line_steps(int w) { return (w + kT - 1) / kT + (VHS ? 6 : 3); }
@@ -843,9 +864,9 @@ CVS_HD void interior_steps(int w, int &s_lo, int &s_hi) {
 constexpr int kWarmPx = 64;   // noise warm-up length in pixels (luma: 64 draws, chroma: 128 draws)
 
 // packed per-row side info written by the host (field_plan.cpp): phase-noise state in the low 16 bits
-// (two's complement), row flags in bits 16..23
-CVS_HD uint32_t rowinfo_pack(int phase_state, uint32_t rflags) {
-    return ((uint32_t)phase_state & 0xFFFFu) | (rflags << 16);
+// (two's complement), row flags in bits 16..23, in-kernel head-switch delay in bits 24..31
+CVS_HD uint32_t rowinfo_pack(int phase_state, uint32_t rflags, int hs_delay) {
+    return ((uint32_t)phase_state & 0xFFFFu) | (rflags << 16) | ((uint32_t)hs_delay << 24);
 }
 
 // subcarrier phase index of a scanline, ffmpeg_ntsc.cpp:1473-1480
@@ -861,6 +882,7 @@ CVS_HD void row_setup(const KConst<R> &K, unsigned field, unsigned long long fie
                       RowConst<R> &rc) {
     rc.row = row;
     rc.rflags = (rowinfo >> 16) & 0xFFu;
+    rc.hs_delay = (rc.rflags & RF_HEADSW_INLINE) ? (int)(rowinfo >> 24) : 0;
     rowconst_set_phase<R>(rc, line_phase(K.phase_shift, K.phase_offset, fieldno, field + 2u * (unsigned)row));
     if (K.flags & F_PHASE) {
         const int st = (int)(int16_t)(rowinfo & 0xFFFFu);

@@ -11,7 +11,8 @@
 //
 // Shared memory per CTA (NT threads): the per-lane glibc-rand rings for the luma and chroma
 // noise streams ([2][32][NT] words, slot-major so a warp access is conflict-free), the per-lane
-// chroma tail stash ([2][16][NT] R) and one 64-word generator window per warp.
+// chroma tail stash ([2][16][NT] R), one 64-word generator window per warp and the per-lane delay
+// ring of the in-kernel head switch ([64][NT] R).
 #ifndef CVS_SCANLINE_KERNELS_CUH
 #define CVS_SCANLINE_KERNELS_CUH
 
@@ -58,7 +59,7 @@ struct LaunchArgs {
 template <typename R>
 constexpr size_t fields_smem_bytes() {
     return (size_t)2 * kRngSlots * kNT * sizeof(uint32_t) + (size_t)2 * kTailSlots * kNT * sizeof(R) +
-           (size_t)kWarpsPerCta * 64 * sizeof(uint32_t);
+           (size_t)kWarpsPerCta * 64 * sizeof(uint32_t) + (size_t)kHsRing * kNT * sizeof(R);
 }
 
 __device__ __forceinline__ const uint32_t *row_ptr(const uint8_t *base, int stride, int y) {
@@ -88,11 +89,12 @@ struct Stepper {
     template <bool EDGE>
     static __device__ __forceinline__ void step(const KConst<R> &K, const RowConst<R> &rc, L &ln, int s,
                                                 const uint32_t px[kT], const int32_t *hsrow, bool warp_hs,
-                                                bool valid, uint32_t *drow, bool vec_dst) {
+                                                R *hsring, bool warp_inl, bool valid, uint32_t *drow, bool vec_dst) {
         R C[kT], Yb[kT], Ib[kT], Qb[kT];
         BlendXchg<R> xo;
         P::template stage_a<EDGE>(K, rc, ln, s, px, hsrow, C);
         if (!EDGE && warp_hs) headswitch_substitute<R>(rc, hsrow, s - 1, C);
+        if (warp_inl && (!EDGE || s >= 1)) headswitch_delay_block<R>(hsring, kNT, s - 1, K.w, rc.hs_delay, C);
         P::template stage_b<EDGE>(K, rc, ln, s, C, Yb, Ib, Qb, xo);
         uint32_t out[kT];
         bool have;
@@ -126,16 +128,26 @@ struct Stepper {
     }
 };
 
+// Each lane reads its own row, 32 bytes (one sector) per step; four consecutive steps share one
+// 128-byte line.  The L2::128B hint makes the first touch bring the whole line into L2, so DRAM sees
+// every line exactly once (the first ncu capture, taken with evict-first loads, showed 1.7x the
+// algorithmic read traffic).
+__device__ __forceinline__ uint4 ld_row16(const uint4 *p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L2::128B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
 __device__ __forceinline__ void load_block_dev(const uint32_t *srow, int k, int w, bool vec, uint32_t px[kT]) {
     const int x0 = k * kT;
     if (vec && x0 + kT <= w) {
         const uint4 *p = reinterpret_cast<const uint4 *>(srow + x0);
-        const uint4 a = __ldcs(p), b = __ldcs(p + 1);       // streamed once: evict-first
+        const uint4 a = ld_row16(p), b = ld_row16(p + 1);
         px[0] = a.x; px[1] = a.y; px[2] = a.z; px[3] = a.w;
         px[4] = b.x; px[5] = b.y; px[6] = b.z; px[7] = b.w;
     } else {
 #pragma unroll
-        for (int j = 0; j < kT; j++) px[j] = (x0 + j < w) ? __ldcs(srow + x0 + j) : 0u;
+        for (int j = 0; j < kT; j++) px[j] = (x0 + j < w) ? __ldg(srow + x0 + j) : 0u;
     }
 }
 
@@ -204,6 +216,8 @@ __global__ void __launch_bounds__(kNT, CVS_MIN_CTAS) k_fields(const __grid_const
     if (K.flags & F_GENERAL) s_hi = s_lo;
     const bool vec_src = a.vec_src != 0, vec_dst = a.vec_dst != 0;
     const bool warp_hs = __any_sync(0xffffffffu, hsrow != nullptr);
+    const bool warp_inl = __any_sync(0xffffffffu, rc.hs_delay > 0);
+    R *hsring = reinterpret_cast<R *>(wins + kWarpsPerCta * 64) + tid;
 
     uint32_t px[kT];
     load_block_dev(srow, 0, w, vec_src, px);
@@ -212,9 +226,9 @@ __global__ void __launch_bounds__(kNT, CVS_MIN_CTAS) k_fields(const __grid_const
         uint32_t pxn[kT];
         load_block_dev(srow, s + 1, w, vec_src, pxn);            // prefetch the next block
         if (s >= s_lo && s < s_hi)
-            Stepper<R, VHS, CD, OUTFULL>::template step<false>(K, rc, ln, s, px, hsrow, warp_hs, valid, drow, vec_dst);
+            Stepper<R, VHS, CD, OUTFULL>::template step<false>(K, rc, ln, s, px, hsrow, warp_hs, hsring, warp_inl, valid, drow, vec_dst);
         else
-            Stepper<R, VHS, CD, OUTFULL>::template step<true>(K, rc, ln, s, px, hsrow, warp_hs, valid, drow, vec_dst);
+            Stepper<R, VHS, CD, OUTFULL>::template step<true>(K, rc, ln, s, px, hsrow, warp_hs, hsring, warp_inl, valid, drow, vec_dst);
 #pragma unroll
         for (int j = 0; j < kT; j++) px[j] = pxn[j];
     }

@@ -70,6 +70,7 @@ int run_field(const cvs_params &p, RandCursor &cur, uint8_t *dst, int dst_stride
     interior_steps<VHS>(w, s_lo, s_hi);
     std::vector<uint32_t> rings((size_t)32 * 2 * kRngSlots);
     std::vector<R> tails((size_t)32 * 2 * kTailSlots);
+    std::vector<R> hsring((size_t)32 * kHsRing);
     for (int wp = 0; wp < nwarps; wp++) {
         L lane[32];
         RowConst<R> rc[32];
@@ -108,6 +109,8 @@ int run_field(const cvs_params &p, RandCursor &cur, uint8_t *dst, int dst_stride
                     return CVS_ERR_NOISE_SYNC;
             }
         }
+        bool warp_inl = false;
+        for (int l = 0; l < 32; l++) warp_inl |= rc[l].hs_delay > 0;
         for (int s = 0; s < nsteps; s++) {
             const bool fast = !(K.flags & F_GENERAL) && s >= s_lo && s < s_hi;
             BlendXchg<R> xo[32];
@@ -119,9 +122,11 @@ int run_field(const cvs_params &p, RandCursor &cur, uint8_t *dst, int dst_stride
                 if (fast) {
                     P::template stage_a<false>(K, rc[l], lane[l], s, px, hsrow[l], C);
                     headswitch_substitute<R>(rc[l], hsrow[l], s - 1, C);
+                    if (warp_inl) headswitch_delay_block<R>(&hsring[(size_t)l * kHsRing], 1, s - 1, w, rc[l].hs_delay, C);
                     P::template stage_b<false>(K, rc[l], lane[l], s, C, Yb[l], Ib[l], Qb[l], xo[l]);
                 } else {
                     P::template stage_a<true>(K, rc[l], lane[l], s, px, hsrow[l], C);
+                    if (warp_inl && s >= 1) headswitch_delay_block<R>(&hsring[(size_t)l * kHsRing], 1, s - 1, w, rc[l].hs_delay, C);
                     P::template stage_b<true>(K, rc[l], lane[l], s, C, Yb[l], Ib[l], Qb[l], xo[l]);
                 }
             }
