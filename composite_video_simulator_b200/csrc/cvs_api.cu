@@ -25,7 +25,7 @@ namespace {
 
 constexpr int kStagingSlots = 3;
 constexpr size_t kMaxEventPairs = 4096;
-constexpr int kHostChunk = 16;              // fields per pipeline stage of the host-pointer entry points
+constexpr int kHostChunkDefault = 16;       // fields per pipeline stage of the host-pointer entry points
 
 struct DevPlan {
     int w = 0, h = 0;
@@ -55,6 +55,7 @@ struct cvs_ctx {
     int device = 0;
     int max_w = 0, max_h = 0, max_batch = 0, nl_max = 0, hs_max = 0;
     int precision = 0;                         // 0 = float (production), 1 = double (reference arithmetic)
+    int host_chunk = kHostChunkDefault;
     cudaStream_t stream = nullptr;
     bool own_stream = true;
     cudaStream_t s_in = nullptr, s_out = nullptr;      // upload / download streams of the host-pointer path
@@ -321,6 +322,7 @@ int run_host(cvs_ctx *c, uint8_t *dst, size_t dst_pic_stride, int dst_stride, co
         CVS_CUDA(cudaMalloc((void **)&c->d_dst, dpic * (size_t)n));
         c->d_pic_cap = dpic * (size_t)n;
     }
+    const int kHostChunk = c->host_chunk;
     const int nchunks = (n + kHostChunk - 1) / kHostChunk;
     while ((int)c->ev_in.size() < nchunks) {
         cudaEvent_t a, b;
@@ -390,6 +392,10 @@ int cvs_create(cvs_ctx **out, const cvs_params *p, int device, int max_w, int ma
     c->device = device;
     c->max_w = max_w; c->max_h = max_h; c->max_batch = max_batch;
     c->nl_max = (max_h + 1) / 2;
+    if (const char *e = std::getenv("CVS_HOST_CHUNK")) {      // tuning knob for experiments
+        const int v = std::atoi(e);
+        if (v >= 1 && v <= 1024) c->host_chunk = v;
+    }
     c->hs_max = head_switch_rows_bound(max_w);
     if (c->hs_max > c->nl_max) c->hs_max = c->nl_max;
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);

@@ -270,20 +270,24 @@ template <> struct Num<float> {
         I = trunc_mul_pos(fma_(0.74f, rd, mul(-0.27f, bd)), 256.0f);
         Q = trunc_mul_pos(fma_(0.48f, rd, mul(0.41f, bd)), 256.0f);
     }
-    // one colour channel: clamp((Y + ci I + cq Q) / 256) truncated, returned as M + value (low byte = value)
-    static CVS_HD uint32_t chan_(float Y, float ci, float I, float cq, float Q) {
-        float v = mul(fma_(cq, Q, fma_(ci, I, Y)), 0.00390625f);
-        v = fminf(fmaxf(v, 0.0f), 255.0f);
+    // one colour channel of YIQ_to_RGB (:1387-1395): trunc((Y + ci I + cq Q) / 256) clamped to 0..255.
+    // The /256 is folded into the operands (exact: power of two), the truncation is the RZ add against
+    // M = 1.5*2^23 and the clamp is done on the resulting bit pattern, whose low byte is the value.
+    static CVS_HD uint32_t chan_(float Yp, float ci, float I, float cq, float Q) {
+        const float v = fma_(cq, Q, fma_(ci, I, Yp));
 #if defined(__CUDA_ARCH__)
-        return __float_as_uint(__fadd_rz(v, kMagic));
+        const uint32_t bits = __float_as_uint(__fadd_rz(v, kMagic));
+        return min(max(bits, 0x4B400000u), 0x4B4000FFu);
 #else
-        return 0x4B400000u + (uint32_t)(int)v;
+        const int k = (v < 0.0f) ? 0 : (v > 255.0f ? 255 : (int)v);
+        return 0x4B400000u + (uint32_t)k;
 #endif
     }
     static CVS_HD uint32_t yiq2bgra(float Y, float I, float Q) {
-        const uint32_t r = chan_(Y, 0.956f, I, 0.621f, Q);
-        const uint32_t g = chan_(Y, -0.272f, I, -0.647f, Q);
-        const uint32_t b = chan_(Y, -1.106f, I, 1.703f, Q);
+        const float Yp = mul(Y, 0.00390625f);
+        const uint32_t r = chan_(Yp, 0.956f * 0.00390625f, I, 0.621f * 0.00390625f, Q);
+        const uint32_t g = chan_(Yp, -0.272f * 0.00390625f, I, -0.647f * 0.00390625f, Q);
+        const uint32_t b = chan_(Yp, -1.106f * 0.00390625f, I, 1.703f * 0.00390625f, Q);
 #if defined(__CUDA_ARCH__)
         return __byte_perm(__byte_perm(b, g, 0x7740), r, 0x5410);   // r byte 1 is 0x00: alpha = 0
 #else
@@ -325,6 +329,18 @@ struct LaneRng {
     CVS_HD uint32_t next_raw(uint32_t n) {
         const uint32_t v = ring[((n + 1) & (kRngSlots - 1)) * stride] + l3;     // (n-31) & 31 == (n+1) & 31
         ring[(n & (kRngSlots - 1)) * stride] = v;
+        l3 = l2; l2 = l1; l1 = v;
+        return v;
+    }
+    // Group form used by the pipeline: a step draws `count` consecutive words starting at a ring index
+    // that is a multiple of `count` (8 luma / 16 chroma draws per 8-pixel step, kRngBase % 32 == 0), so
+    // the group never wraps: word i is written at grp + i*stride and its long-lag tap q[n-31] sits one
+    // slot further, i.e. at grp + (i+1)*stride, or at the start of the NEXT group for the last word.
+    // grp/grp_next are computed once per step; every access is base + compile-time offset.
+    CVS_HD uint32_t *group_ptr(uint32_t n_first) const { return ring + (n_first & (kRngSlots - 1)) * stride; }
+    CVS_HD uint32_t next_in_group(uint32_t *grp, const uint32_t *grp_next, int i, int count) {
+        const uint32_t v = ((i + 1 < count) ? grp[(i + 1) * stride] : grp_next[0]) + l3;
+        grp[i * stride] = v;
         l3 = l2; l2 = l1; l1 = v;
         return v;
     }
@@ -385,7 +401,6 @@ struct Lane {
 
     // --- carried state (all statically indexed) ---
     // A
-    uint32_t pxprev[kT];             // BGRA of B(s-1) (raw I/Q are recomputed from it on the tail path)
     R Yprev[kT];                     // Y of B(s-1)
     R oIprev[kT], oQprev[kT];        // input-lowpass cascade outputs for t in B(s-1)
     R pI[3], pQ[3];                  // cascade poles
@@ -416,7 +431,7 @@ struct Lane {
     CVS_HD void reset(const KConst<R> &K) {
         CVS_UNROLL
         for (int j = 0; j < kT; j++) {
-            pxprev[j] = 0; Yprev[j] = 0; oIprev[j] = 0; oQprev[j] = 0; Cprev[j] = 0;
+            Yprev[j] = 0; oIprev[j] = 0; oQprev[j] = 0; Cprev[j] = 0;
             oUprev[j] = 0; oVprev[j] = 0; Y3a[j] = 0; Y3b[j] = 0; C2prev[j] = 0; outprev[j] = 0;
         }
         CVS_UNROLL
@@ -436,9 +451,9 @@ struct Lane {
 };
 
 // QAM modulation of one sample (chroma_into_luma, :1486-1490).  amp == 50 makes (v*50)/50 == v.
-template <typename R, bool EDGE>
+template <typename R, int MODE>
 CVS_HD R modulate(R Yv, R Iv, R Qv, R mI, R mQ, int amp) {
-    if (!EDGE || amp == 50) {
+    if (MODE != 2 || amp == 50) {
         // exactly one of mI, mQ is +-1, the other 0: the sum is exact
         return Num<R>::fma_(Iv, mI, Num<R>::fma_(Qv, mQ, Yv));
     } else {
@@ -451,16 +466,18 @@ CVS_HD R modulate(R Yv, R Iv, R Qv, R mI, R mQ, int amp) {
 //   cm1      = C[8k-1]
 //   c[0..15] = C[8k .. 8k+15]   (only c[0..14] are read; zero beyond the line end)
 // outputs Yb (box-filtered luma), Ib, Qb for the 8 pixels of the block.
-template <typename R, bool EDGE>
+template <typename R, int MODE>
 CVS_HD void demod_block(const RowConst<R> &rc, int k, int w, int amp, R cm1, const R c[2 * kT],
                         R Yb[kT], R Ib[kT], R Qb[kT]) {
+    constexpr bool EDGE = MODE >= 1, GEN = MODE == 2;
     const int x0 = k * kT;
     // box[m] = (C[m-1] + C[m] + C[m+1] + C[m+2]) / 4 ; chroma[m] = C[m+2] - box[m], m = 0..12
+    // (all values are integers < 2^24, so the running sum is exact in any order)
     R ch[13];
+    R sum = Num<R>::add(Num<R>::add(cm1, c[0]), Num<R>::add(c[1], c[2]));
     CVS_UNROLL
     for (int m = 0; m < 13; m++) {
-        const R a = (m == 0) ? cm1 : c[m - 1];
-        const R sum = Num<R>::add(Num<R>::add(a, c[m]), Num<R>::add(c[m + 1], c[m + 2]));
+        if (m > 0) sum = Num<R>::add(Num<R>::sub(sum, (m == 1) ? cm1 : c[m - 2]), c[m + 2]);
         const R box = div4_trunc<R>(sum);
         if (m < kT) Yb[m] = box;
         ch[m] = Num<R>::sub(c[m + 2], box);
@@ -475,7 +492,7 @@ CVS_HD void demod_block(const RowConst<R> &rc, int k, int w, int amp, R cm1, con
             const int g = q - ph;                      // start of this carrier period
             const bool flip = (ph >= 2) && (g >= 0) && (g + 3 < w);
             R v = flip ? -ch[m] : ch[m];
-            if (amp != 50) v = (R)muldiv_trunc((int)v, 50, amp);
+            if (GEN && amp != 50) v = (R)muldiv_trunc((int)v, 50, amp);
             ch[m] = v;
         }
     }
@@ -525,6 +542,16 @@ CVS_HD void demod_block(const RowConst<R> &rc, int k, int w, int amp, R cm1, con
     }
 }
 
+// ---- code variants ---------------------------------------------------------------------------------
+// Every stage is instantiated three ways (template int MODE):
+//   MODE_FAST     interior steps of a default-switch configuration: no per-pixel predicates at all
+//   MODE_EDGE     steps that touch a line start/end, default switches
+//   MODE_GENERAL  any non-default switch (F_GENERAL): every run-time flag honoured, on every step
+// Keeping MODE_EDGE free of the rarely used switches keeps the code that every line start/end pulls
+// through the instruction cache small (the first ncu capture showed 17% of the kernel time waiting on
+// instruction fetch in the then-combined edge+general body).
+enum { MODE_FAST = 0, MODE_EDGE = 1, MODE_GENERAL = 2 };
+
 // ---- the step ------------------------------------------------------------------------------------
 // Exchange buffer for the vertical chroma blend: each lane publishes its pre-blend chroma block and
 // receives the block of the row above (lane - 1).  On the GPU this is 16 __shfl_up_sync.
@@ -539,9 +566,12 @@ struct Pipeline {
     typedef Num<R> N;
 
     // ---- A1 + A2 (+ head-switch substitution): returns C block B(s-1) in Cnew --------------------
-    template <bool EDGE>
+    // pxprev = BGRA of B(s-1): read only on the tail path (raw chroma of the last `delay` pixels), so
+    // the fast variant never carries it; the edge variants re-read it from memory (an L2 hit).
+    template <int MODE>
     static CVS_HD void stage_a(const KConst<R> &K, const RowConst<R> &rc, L &ln, int s,
-                               const uint32_t px[kT], const int32_t *hs_row, R Cnew[kT]) {
+                               const uint32_t px[kT], const uint32_t pxprev[kT], const int32_t *hs_row, R Cnew[kT]) {
+        constexpr bool EDGE = MODE >= 1, GEN = MODE == 2;
         const int w = K.w;
         const int p = s * kT;
         R Ycur[kT], oIcur[kT], oQcur[kT];
@@ -561,7 +591,9 @@ struct Pipeline {
         }
         // A2: composite block B(s-1)
         if (!EDGE || s >= 1) {
-            const bool in_lp = !EDGE || (K.flags & F_IN_LP);
+            const bool in_lp = !GEN || (K.flags & F_IN_LP);
+            uint32_t *gL = ln.rngL.group_ptr(kRngBase + (uint32_t)(p - kT));          // luma draws of B(s-1)
+            const uint32_t *gLn = ln.rngL.group_ptr(kRngBase + (uint32_t)p);
             CVS_UNROLL
             for (int j = 0; j < kT; j++) {
                 const int x = p - kT + j;
@@ -575,19 +607,19 @@ struct Pipeline {
                         const bool rawI = !in_lp || (x + 2 >= w), rawQ = !in_lp || (x + 4 >= w);
                         if (rawI || rawQ) {
                             R y, i, q;
-                            N::rgb2yiq(ln.pxprev[j], y, i, q);
+                            N::rgb2yiq(pxprev[j], y, i, q);
                             if (rawI) iv = i;
                             if (rawQ) qv = q;
                         }
                     }
-                    c = modulate<R, EDGE>(ln.Yprev[j], iv, qv, rc.mI[j & 3], rc.mQ[j & 3], K.amp);   // :1611
-                    if (EDGE && (K.flags & F_PREEMPH)) {                                             // :1613-1629
+                    c = modulate<R, MODE>(ln.Yprev[j], iv, qv, rc.mI[j & 3], rc.mQ[j & 3], K.amp);   // :1611
+                    if (GEN && (K.flags & F_PREEMPH)) {                                              // :1613-1629
                         const R lp = N::pole(ln.pPre, c, K.a_pre, K.b_pre);
                         c = N::preemph(c, N::sub(c, lp), K.preemph);
                     }
-                    if (!EDGE || K.vnoise != 0) {                                                    // :1631-1644
+                    if (!GEN || K.vnoise != 0) {                                                     // :1631-1644
                         c = N::add(c, (R)ln.nY);
-                        const int d = draw_mod(ln.rngL.next_raw(kRngBase + (uint32_t)x), (uint32_t)(2 * K.vnoise + 1), K.vmagic, K.vshift);
+                        const int d = draw_mod(ln.rngL.next_in_group(gL, gLn, j, kT), (uint32_t)(2 * K.vnoise + 1), K.vmagic, K.vshift);
                         ln.nY = noise_step(ln.nY, d, K.vnoise);
                     }
                     if (EDGE && hs_row && (rc.rflags & RF_HEADSW)) c = (R)hs_row[x];                 // :1646-1713
@@ -600,7 +632,6 @@ struct Pipeline {
         }
         CVS_UNROLL
         for (int j = 0; j < kT; j++) {
-            ln.pxprev[j] = px[j];
             ln.Yprev[j] = Ycur[j];
             ln.oIprev[j] = oIcur[j];
             ln.oQprev[j] = oQcur[j];
@@ -610,9 +641,10 @@ struct Pipeline {
     // ---- B: demod of B(s-2), noise, phase; VHS luma/chroma filters ---------------------------------
     // Outputs: Yb/Ib/Qb of B(s-2) for the non-VHS path; for VHS publishes the completed delayed chroma
     // block B(s-4) in xo (pre-blend) and leaves Y3 of B(s-2) in y3new.
-    template <bool EDGE>
+    template <int MODE>
     static CVS_HD void stage_b(const KConst<R> &K, const RowConst<R> &rc, L &ln, int s, const R Cnew[kT],
                                R Yb[kT], R Ib[kT], R Qb[kT], BlendXchg<R> &xo) {
+        constexpr bool EDGE = MODE >= 1, GEN = MODE == 2;
         const int w = K.w;
         const int k = s - 2;
         if (EDGE && k < 0) {
@@ -626,32 +658,34 @@ struct Pipeline {
         R c[2 * kT];
         CVS_UNROLL
         for (int j = 0; j < kT; j++) { c[j] = ln.Cprev[j]; c[kT + j] = Cnew[j]; }
-        if (EDGE && (K.flags & F_NOCOLOR)) {                       // :1715: no demod, chroma stays zero
+        if (GEN && (K.flags & F_NOCOLOR)) {                        // :1715: no demod, chroma stays zero
             CVS_UNROLL
             for (int j = 0; j < kT; j++) { Yb[j] = c[j]; Ib[j] = 0; Qb[j] = 0; }
         } else {
-            demod_block<R, EDGE>(rc, k, w, K.amp_back, ln.Cm1, c, Yb, Ib, Qb);   // :1716
+            demod_block<R, MODE>(rc, k, w, K.amp_back, ln.Cm1, c, Yb, Ib, Qb);   // :1716
         }
         ln.Cm1 = ln.Cprev[kT - 1];
         CVS_UNROLL
         for (int j = 0; j < kT; j++) ln.Cprev[j] = Cnew[j];
 
         const int x0 = k * kT;
-        if (EDGE ? (K.cnoise != 0) : VHS) {                        // :1718-1735
+        if (GEN ? (K.cnoise != 0) : VHS) {                         // :1718-1735
+            uint32_t *gC = ln.rngC.group_ptr(kRngBase + 2u * (uint32_t)x0);           // 16 chroma draws of B(s-2)
+            const uint32_t *gCn = ln.rngC.group_ptr(kRngBase + 2u * (uint32_t)(x0 + kT));
             CVS_UNROLL
             for (int j = 0; j < kT; j++) {
                 if (!EDGE || x0 + j < w) {
                     Ib[j] = N::add(Ib[j], (R)ln.nU);
                     Qb[j] = N::add(Qb[j], (R)ln.nV);
                     const uint32_t m = (uint32_t)(2 * K.cnoise + 1);
-                    const int dU = draw_mod(ln.rngC.next_raw(kRngBase + 2u * (uint32_t)(x0 + j)), m, K.cmagic, K.cshift);
+                    const int dU = draw_mod(ln.rngC.next_in_group(gC, gCn, 2 * j, 2 * kT), m, K.cmagic, K.cshift);
                     ln.nU = noise_step(ln.nU, dU, K.cnoise);
-                    const int dV = draw_mod(ln.rngC.next_raw(kRngBase + 2u * (uint32_t)(x0 + j) + 1u), m, K.cmagic, K.cshift);
+                    const int dV = draw_mod(ln.rngC.next_in_group(gC, gCn, 2 * j + 1, 2 * kT), m, K.cmagic, K.cshift);
                     ln.nV = noise_step(ln.nV, dV, K.cnoise);
                 }
             }
         }
-        if (EDGE ? ((K.flags & F_PHASE) != 0) : VHS) {             // :1736-1764
+        if (GEN ? ((K.flags & F_PHASE) != 0) : VHS) {              // :1736-1764
             CVS_UNROLL
             for (int j = 0; j < kT; j++) {
                 const R u = Ib[j], v = Qb[j];
@@ -707,10 +741,11 @@ struct Pipeline {
     // ---- B2 + C: vertical blend of B(s-4), remodulate, second demod of B(s-5) -----------------------
     // xi_ = block received from the row above (pre-blend).  Y3new = Y3 of B(s-2) (from stage_b).
     // Produces the F-stage input block: B(s-5) (recombine) or B(s-4) (s-video).
-    template <bool EDGE>
+    template <int MODE>
     static CVS_HD void stage_c(const KConst<R> &K, const RowConst<R> &rc, L &ln, int s, const R Y3new[kT],
                                const BlendXchg<R> &own, const BlendXchg<R> &above,
                                R Yf[kT], R If[kT], R Qf[kT], int &kf) {
+        constexpr bool EDGE = MODE >= 1, GEN = MODE == 2;
         const int w = K.w;
         R U[kT], V[kT];
         const bool blend = (K.flags & F_VBLEND) && rc.row >= 1;       // loop starts at field+2, :1849
@@ -726,7 +761,7 @@ struct Pipeline {
             U[j] = u;
             V[j] = v;
         }
-        const bool svideo = EDGE && (K.flags & F_SVIDEO);
+        const bool svideo = GEN && (K.flags & F_SVIDEO);
         if (svideo) {                                                 // :1885: no recombine
             kf = s - 4;
             CVS_UNROLL
@@ -740,12 +775,12 @@ struct Pipeline {
                 const int x = (s - 4) * kT + j;
                 R cv = 0;
                 if (!EDGE || (x >= 0 && x < w))
-                    cv = modulate<R, EDGE>(ln.Y3b[j], U[j], V[j], rc.mI[j & 3], rc.mQ[j & 3], K.amp);
+                    cv = modulate<R, MODE>(ln.Y3b[j], U[j], V[j], rc.mI[j & 3], rc.mQ[j & 3], K.amp);
                 c[kT + j] = cv;
                 c[j] = ln.C2prev[j];
             }
             if (!EDGE || kf >= 0) {
-                demod_block<R, EDGE>(rc, kf, w, K.amp, ln.C2m1, c, Yf, If, Qf);      // :1887
+                demod_block<R, MODE>(rc, kf, w, K.amp, ln.C2m1, c, Yf, If, Qf);      // :1887
             } else {
                 CVS_UNROLL
                 for (int j = 0; j < kT; j++) { Yf[j] = 0; If[j] = 0; Qf[j] = 0; }
@@ -760,9 +795,10 @@ struct Pipeline {
 
     // ---- F: dropout, output chroma lowpass, YIQ -> RGB; completes output block B(kf-1) ----------------
     // Returns true when `out` holds a complete block B(kf-1) (kf >= 1).
-    template <bool EDGE>
+    template <int MODE>
     static CVS_HD bool stage_f(const KConst<R> &K, const RowConst<R> &rc, L &ln, int kf,
                                R Yf[kT], R If[kT], R Qf[kT], uint32_t out[kT]) {
+        constexpr bool EDGE = MODE >= 1, GEN = MODE == 2;
         constexpr int OD = L::OD, ODI = L::ODI, ODQ = L::ODQ;
         const int w = K.w;
         if (EDGE && kf < 0) return false;
@@ -780,7 +816,7 @@ struct Pipeline {
                 oI[j] = 0; oQ[j] = 0;
             }
         }
-        const bool out_lp = !EDGE || (K.flags & F_OUT_LP);
+        const bool out_lp = !GEN || (K.flags & F_OUT_LP);
         // pixels [x0-OD, x0+8-OD): Y and raw chroma delayed by OD, filtered I by OD-ODI, filtered Q by OD-ODQ
         uint32_t pk[kT];
         CVS_UNROLL
@@ -958,11 +994,16 @@ CVS_HD void headswitch_row(const KConst<R> &K, const RowConst<R> &rc_in, Lane<R,
     rc.rflags &= ~(uint32_t)RF_HEADSW;                 // compute, do not substitute
     for (int x = 0; x < w; x++) scratch[x] = 0;
     const int nb = (w + kT - 1) / kT;
+    uint32_t pxprev[kT];
+    CVS_UNROLL
+    for (int j = 0; j < kT; j++) pxprev[j] = 0;
     for (int s = 0; s <= nb; s++) {
         uint32_t px[kT];
         load_block_scalar(srow, s, w, px);
         R C[kT];
-        P::template stage_a<true>(K, rc, ln, s, px, (const int32_t *)0, C);
+        P::template stage_a<MODE_GENERAL>(K, rc, ln, s, px, pxprev, (const int32_t *)0, C);
+        CVS_UNROLL
+        for (int j = 0; j < kT; j++) pxprev[j] = px[j];
         if (s >= 1) {
             for (int j = 0; j < kT; j++) {
                 const int x = (s - 1) * kT + j;

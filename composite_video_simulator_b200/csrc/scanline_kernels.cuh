@@ -23,7 +23,10 @@
 
 namespace cvs {
 
-constexpr int kNT = 128;                 // threads per CTA (4 warps)
+#ifndef CVS_NT
+#define CVS_NT 128
+#endif
+constexpr int kNT = CVS_NT;              // threads per CTA
 constexpr int kWarpsPerCta = kNT / 32;
 #ifndef CVS_MIN_CTAS
 #define CVS_MIN_CTAS 2              // CTAs per SM the register allocator must leave room for
@@ -81,53 +84,6 @@ __device__ __forceinline__ void rebase_dev(const uint32_t *win_smem, const uint3
     }
 }
 
-template <typename R, bool VHS, int CD, bool OUTFULL>
-struct Stepper {
-    typedef Lane<R, VHS, CD, OUTFULL> L;
-    typedef Pipeline<R, VHS, CD, OUTFULL> P;
-
-    template <bool EDGE>
-    static __device__ __forceinline__ void step(const KConst<R> &K, const RowConst<R> &rc, L &ln, int s,
-                                                const uint32_t px[kT], const int32_t *hsrow, bool warp_hs,
-                                                R *hsring, bool warp_inl, bool valid, uint32_t *drow, bool vec_dst) {
-        R C[kT], Yb[kT], Ib[kT], Qb[kT];
-        BlendXchg<R> xo;
-        P::template stage_a<EDGE>(K, rc, ln, s, px, hsrow, C);
-        if (!EDGE && warp_hs) headswitch_substitute<R>(rc, hsrow, s - 1, C);
-        if (warp_inl && (!EDGE || s >= 1)) headswitch_delay_block<R>(hsring, kNT, s - 1, K.w, rc.hs_delay, C);
-        P::template stage_b<EDGE>(K, rc, ln, s, C, Yb, Ib, Qb, xo);
-        uint32_t out[kT];
-        bool have;
-        int kf;
-        if (VHS) {
-            BlendXchg<R> above;
-#pragma unroll
-            for (int j = 0; j < kT; j++) {
-                above.u[j] = __shfl_up_sync(0xffffffffu, xo.u[j], 1);
-                above.v[j] = __shfl_up_sync(0xffffffffu, xo.v[j], 1);
-            }
-            R Yf[kT], If[kT], Qf[kT];
-            P::template stage_c<EDGE>(K, rc, ln, s, Yb, xo, above, Yf, If, Qf, kf);
-            have = P::template stage_f<EDGE>(K, rc, ln, kf, Yf, If, Qf, out);
-        } else {
-            kf = s - 2;
-            have = P::template stage_f<EDGE>(K, rc, ln, kf, Yb, Ib, Qb, out);
-        }
-        if (have && valid) {
-            const int x0 = (kf - 1) * kT;
-            if (vec_dst && (!EDGE || x0 + kT <= K.w)) {
-                uint4 *d = reinterpret_cast<uint4 *>(drow + x0);
-                d[0] = make_uint4(out[0], out[1], out[2], out[3]);
-                d[1] = make_uint4(out[4], out[5], out[6], out[7]);
-            } else {
-#pragma unroll
-                for (int j = 0; j < kT; j++)
-                    if (x0 + j < K.w) drow[x0 + j] = out[j];
-            }
-        }
-    }
-};
-
 // Each lane reads its own row, 32 bytes (one sector) per step; four consecutive steps share one
 // 128-byte line.  The L2::128B hint makes the first touch bring the whole line into L2, so DRAM sees
 // every line exactly once (the first ncu capture, taken with evict-first loads, showed 1.7x the
@@ -150,6 +106,65 @@ __device__ __forceinline__ void load_block_dev(const uint32_t *srow, int k, int 
         for (int j = 0; j < kT; j++) px[j] = (x0 + j < w) ? __ldg(srow + x0 + j) : 0u;
     }
 }
+
+template <typename R, bool VHS, int CD, bool OUTFULL>
+struct Stepper {
+    typedef Lane<R, VHS, CD, OUTFULL> L;
+    typedef Pipeline<R, VHS, CD, OUTFULL> P;
+
+    template <int MODE>
+    static __device__ __forceinline__ void step(const KConst<R> &K, const RowConst<R> &rc, L &ln, int s,
+                                                const uint32_t px[kT], const uint32_t *srow, bool vec_src,
+                                                const int32_t *hsrow, bool warp_hs,
+                                                R *hsring, bool warp_inl, bool valid, uint32_t *drow, bool vec_dst) {
+        constexpr bool EDGE = MODE >= 1;
+        R C[kT], Yb[kT], Ib[kT], Qb[kT];
+        BlendXchg<R> xo;
+        uint32_t pxprev[kT];
+        if (EDGE) {
+            // the tail path needs the raw chroma of the previous block: re-read it (L2 hit) instead of
+            // carrying 8 registers through every interior step
+            if (s >= 1) load_block_dev(srow, s - 1, K.w, vec_src, pxprev);
+            else {
+#pragma unroll
+                for (int j = 0; j < kT; j++) pxprev[j] = 0;
+            }
+        }
+        P::template stage_a<MODE>(K, rc, ln, s, px, pxprev, hsrow, C);
+        if (!EDGE && warp_hs) headswitch_substitute<R>(rc, hsrow, s - 1, C);
+        if (warp_inl && (!EDGE || s >= 1)) headswitch_delay_block<R>(hsring, kNT, s - 1, K.w, rc.hs_delay, C);
+        P::template stage_b<MODE>(K, rc, ln, s, C, Yb, Ib, Qb, xo);
+        uint32_t out[kT];
+        bool have;
+        int kf;
+        if (VHS) {
+            BlendXchg<R> above;
+#pragma unroll
+            for (int j = 0; j < kT; j++) {
+                above.u[j] = __shfl_up_sync(0xffffffffu, xo.u[j], 1);
+                above.v[j] = __shfl_up_sync(0xffffffffu, xo.v[j], 1);
+            }
+            R Yf[kT], If[kT], Qf[kT];
+            P::template stage_c<MODE>(K, rc, ln, s, Yb, xo, above, Yf, If, Qf, kf);
+            have = P::template stage_f<MODE>(K, rc, ln, kf, Yf, If, Qf, out);
+        } else {
+            kf = s - 2;
+            have = P::template stage_f<MODE>(K, rc, ln, kf, Yb, Ib, Qb, out);
+        }
+        if (have && valid) {
+            const int x0 = (kf - 1) * kT;
+            if (vec_dst && (!EDGE || x0 + kT <= K.w)) {
+                uint4 *d = reinterpret_cast<uint4 *>(drow + x0);
+                d[0] = make_uint4(out[0], out[1], out[2], out[3]);
+                d[1] = make_uint4(out[4], out[5], out[6], out[7]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < kT; j++)
+                    if (x0 + j < K.w) drow[x0 + j] = out[j];
+            }
+        }
+    }
+};
 
 template <typename R, bool VHS, int CD, bool OUTFULL>
 __global__ void __launch_bounds__(kNT, CVS_MIN_CTAS) k_fields(const __grid_constant__ LaunchArgs<R> a) {
@@ -213,7 +228,8 @@ __global__ void __launch_bounds__(kNT, CVS_MIN_CTAS) k_fields(const __grid_const
     const int nsteps = line_steps<VHS>(w);
     int s_lo, s_hi;
     interior_steps<VHS>(w, s_lo, s_hi);
-    if (K.flags & F_GENERAL) s_hi = s_lo;
+    const bool general = (K.flags & F_GENERAL) != 0;
+    if (general) s_hi = s_lo;
     const bool vec_src = a.vec_src != 0, vec_dst = a.vec_dst != 0;
     const bool warp_hs = __any_sync(0xffffffffu, hsrow != nullptr);
     const bool warp_inl = __any_sync(0xffffffffu, rc.hs_delay > 0);
@@ -226,9 +242,11 @@ __global__ void __launch_bounds__(kNT, CVS_MIN_CTAS) k_fields(const __grid_const
         uint32_t pxn[kT];
         load_block_dev(srow, s + 1, w, vec_src, pxn);            // prefetch the next block
         if (s >= s_lo && s < s_hi)
-            Stepper<R, VHS, CD, OUTFULL>::template step<false>(K, rc, ln, s, px, hsrow, warp_hs, hsring, warp_inl, valid, drow, vec_dst);
+            Stepper<R, VHS, CD, OUTFULL>::template step<MODE_FAST>(K, rc, ln, s, px, srow, vec_src, hsrow, warp_hs, hsring, warp_inl, valid, drow, vec_dst);
+        else if (!general)
+            Stepper<R, VHS, CD, OUTFULL>::template step<MODE_EDGE>(K, rc, ln, s, px, srow, vec_src, hsrow, warp_hs, hsring, warp_inl, valid, drow, vec_dst);
         else
-            Stepper<R, VHS, CD, OUTFULL>::template step<true>(K, rc, ln, s, px, hsrow, warp_hs, hsring, warp_inl, valid, drow, vec_dst);
+            Stepper<R, VHS, CD, OUTFULL>::template step<MODE_GENERAL>(K, rc, ln, s, px, srow, vec_src, hsrow, warp_hs, hsring, warp_inl, valid, drow, vec_dst);
 #pragma unroll
         for (int j = 0; j < kT; j++) px[j] = pxn[j];
     }

@@ -33,7 +33,7 @@ int run_field(const cvs_params &p, RandCursor &cur, uint8_t *dst, int dst_stride
     KConst<R> K;
     std::vector<R> lut;
     make_kconst<R>(p, w, h, OUTFULL, K, lut);
-    if (force_general) K.flags |= F_GENERAL;
+    if (force_general == 1) K.flags |= F_GENERAL;
     const int nl = g.nl;
     const int opposite = interlaced ? (tff ? 1 : 0) : 0;
     auto src_row = [&](int row) {
@@ -112,22 +112,32 @@ int run_field(const cvs_params &p, RandCursor &cur, uint8_t *dst, int dst_stride
         bool warp_inl = false;
         for (int l = 0; l < 32; l++) warp_inl |= rc[l].hs_delay > 0;
         for (int s = 0; s < nsteps; s++) {
-            const bool fast = !(K.flags & F_GENERAL) && s >= s_lo && s < s_hi;
+            // the kernel's choice of code variant for this step (force_general: 1 = general everywhere,
+            // 2 = edge variant everywhere, to exercise those variants on interior blocks as well)
+            int mode = (K.flags & F_GENERAL) ? MODE_GENERAL : ((s >= s_lo && s < s_hi) ? MODE_FAST : MODE_EDGE);
+            if (force_general == 2 && mode == MODE_FAST) mode = MODE_EDGE;
             BlendXchg<R> xo[32];
             R Yb[32][kT], Ib[32][kT], Qb[32][kT];
             for (int l = 0; l < 32; l++) {
-                uint32_t px[kT];
+                uint32_t px[kT], pxprev[kT];
                 load_block_scalar(srow[l], s, w, px);
+                if (s >= 1) load_block_scalar(srow[l], s - 1, w, pxprev);
+                else for (int j = 0; j < kT; j++) pxprev[j] = 0;
                 R C[kT];
-                if (fast) {
-                    P::template stage_a<false>(K, rc[l], lane[l], s, px, hsrow[l], C);
+                R *ring = &hsring[(size_t)l * kHsRing];
+                if (mode == MODE_FAST) {
+                    P::template stage_a<MODE_FAST>(K, rc[l], lane[l], s, px, pxprev, hsrow[l], C);
                     headswitch_substitute<R>(rc[l], hsrow[l], s - 1, C);
-                    if (warp_inl) headswitch_delay_block<R>(&hsring[(size_t)l * kHsRing], 1, s - 1, w, rc[l].hs_delay, C);
-                    P::template stage_b<false>(K, rc[l], lane[l], s, C, Yb[l], Ib[l], Qb[l], xo[l]);
+                    if (warp_inl) headswitch_delay_block<R>(ring, 1, s - 1, w, rc[l].hs_delay, C);
+                    P::template stage_b<MODE_FAST>(K, rc[l], lane[l], s, C, Yb[l], Ib[l], Qb[l], xo[l]);
+                } else if (mode == MODE_EDGE) {
+                    P::template stage_a<MODE_EDGE>(K, rc[l], lane[l], s, px, pxprev, hsrow[l], C);
+                    if (warp_inl && s >= 1) headswitch_delay_block<R>(ring, 1, s - 1, w, rc[l].hs_delay, C);
+                    P::template stage_b<MODE_EDGE>(K, rc[l], lane[l], s, C, Yb[l], Ib[l], Qb[l], xo[l]);
                 } else {
-                    P::template stage_a<true>(K, rc[l], lane[l], s, px, hsrow[l], C);
-                    if (warp_inl && s >= 1) headswitch_delay_block<R>(&hsring[(size_t)l * kHsRing], 1, s - 1, w, rc[l].hs_delay, C);
-                    P::template stage_b<true>(K, rc[l], lane[l], s, C, Yb[l], Ib[l], Qb[l], xo[l]);
+                    P::template stage_a<MODE_GENERAL>(K, rc[l], lane[l], s, px, pxprev, hsrow[l], C);
+                    if (warp_inl && s >= 1) headswitch_delay_block<R>(ring, 1, s - 1, w, rc[l].hs_delay, C);
+                    P::template stage_b<MODE_GENERAL>(K, rc[l], lane[l], s, C, Yb[l], Ib[l], Qb[l], xo[l]);
                 }
             }
             for (int l = 0; l < 32; l++) {
@@ -135,20 +145,19 @@ int run_field(const cvs_params &p, RandCursor &cur, uint8_t *dst, int dst_stride
                 int kf;
                 uint32_t out[kT];
                 bool have;
-                if (VHS) {
-                    const BlendXchg<R> &above = xo[l > 0 ? l - 1 : 0];
-                    if (fast) {
-                        P::template stage_c<false>(K, rc[l], lane[l], s, Yb[l], xo[l], above, Yf, If, Qf, kf);
-                        have = P::template stage_f<false>(K, rc[l], lane[l], kf, Yf, If, Qf, out);
-                    } else {
-                        P::template stage_c<true>(K, rc[l], lane[l], s, Yb[l], xo[l], above, Yf, If, Qf, kf);
-                        have = P::template stage_f<true>(K, rc[l], lane[l], kf, Yf, If, Qf, out);
-                    }
-                } else {
-                    kf = s - 2;
-                    if (fast) have = P::template stage_f<false>(K, rc[l], lane[l], kf, Yb[l], Ib[l], Qb[l], out);
-                    else have = P::template stage_f<true>(K, rc[l], lane[l], kf, Yb[l], Ib[l], Qb[l], out);
-                }
+                const BlendXchg<R> &above = xo[l > 0 ? l - 1 : 0];
+#define CVS_TAIL(M)                                                                                          \
+    if (VHS) {                                                                                               \
+        P::template stage_c<M>(K, rc[l], lane[l], s, Yb[l], xo[l], above, Yf, If, Qf, kf);                   \
+        have = P::template stage_f<M>(K, rc[l], lane[l], kf, Yf, If, Qf, out);                               \
+    } else {                                                                                                 \
+        kf = s - 2;                                                                                          \
+        have = P::template stage_f<M>(K, rc[l], lane[l], kf, Yb[l], Ib[l], Qb[l], out);                      \
+    }
+                if (mode == MODE_FAST) { CVS_TAIL(MODE_FAST) }
+                else if (mode == MODE_EDGE) { CVS_TAIL(MODE_EDGE) }
+                else { CVS_TAIL(MODE_GENERAL) }
+#undef CVS_TAIL
                 if (have && valid[l]) {
                     const int x0 = (kf - 1) * kT;
                     for (int j = 0; j < kT; j++)

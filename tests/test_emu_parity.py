@@ -1,7 +1,7 @@
 """The product's lane pipeline (csrc/lane_pipeline.cuh) + host planning (field_plan.cpp, glibc_rand.cpp)
 executed on the CPU, 32 lanes in lock-step exactly as the kernels run them (tests/emu_harness.cpp),
-against the oracle.  fp64 = the reference's arithmetic: must be bit-exact, on both the interior
-(fast) and the general (edge) code paths.  fp32 = production arithmetic: within +-1 LSB."""
+against the oracle.  fp64 = the reference's arithmetic: must be bit-exact, on all three code variants
+(fast interior, edge, general).  fp32 = production arithmetic: within +-1 LSB."""
 import numpy as np
 import pytest
 
@@ -38,7 +38,7 @@ def test_lane_pipeline_matches_oracle(oracle, emu, w, h, n, argv):
     p = helpers.params(*argv)
     frames = lambda k: helpers.stream_frame(w, h, k)
     want, g = helpers.run_oracle(oracle, p, frames, n, w, h)
-    for general in (0, 1):
+    for general in (0, 1, 2):       # 0 = the kernel's own choice, 1 = general variant everywhere, 2 = edge variant everywhere
         got, pos = helpers.run_emu(emu, p, frames, n, w, h, precision=1, general=general)
         assert np.array_equal(want, got), ("fp64", general, helpers.channel_diff(want, got))
         assert pos == g.pos
