@@ -382,7 +382,12 @@ def main():
     ap.add_argument("--e2e-batch", type=int, default=256, help="fields per GPU per step (host buffers)")
     ap.add_argument("--cpu-fields", type=int, default=64, help="fields of the single-thread CPU baseline sample")
     ap.add_argument("--ref-fields-per-proc", type=int, default=4)
+    ap.add_argument("--preset", default="sp", choices=["sp", "ep", "lp", "comp"],
+                    help="sp = the headline VHS-SP workload; the others are for kernel experiments")
     args = ap.parse_args()
+    global ARGV
+    ARGV = {"sp": ["-vhs", "-vhs-speed", "sp"], "ep": ["-vhs", "-vhs-speed", "ep"], "lp": ["-vhs", "-vhs-speed", "lp"],
+            "comp": []}[args.preset]
     if args.warmup < 3 and args.impl == "own":
         args.warmup = 3
     if args.impl == "reference":

@@ -45,8 +45,8 @@ void make_kconst(const cvs_params &p, int w, int h, bool outfull, KConst<R> &K, 
     std::memset(&K, 0, sizeof(K));
     auto set = [](R &a, R &b, R &c, double alpha) { a = (R)alpha; b = (R)(1.0 - alpha); c = (R)(alpha * alpha * alpha); };
     R unused_c;
-    set(K.a_inI, K.b_inI, K.c_inI, pole_alpha(1300000));   // :1442
-    set(K.a_inQ, K.b_inQ, K.c_inQ, pole_alpha(600000));
+    set(K.a_in.x, K.b_in.x, K.c_in.x, pole_alpha(1300000));   // I, :1442
+    set(K.a_in.y, K.b_in.y, K.c_in.y, pole_alpha(600000));     // Q
     const bool pre = p.composite_preemphasis != 0 && p.composite_preemphasis_cut > 0;   // :1614
     if (pre) set(K.a_pre, K.b_pre, unused_c, pole_alpha(p.composite_preemphasis_cut));
     K.preemph = (R)p.composite_preemphasis;
@@ -54,15 +54,16 @@ void make_kconst(const cvs_params &p, int w, int h, bool outfull, KConst<R> &K, 
     if (p.output_vhs_tape_speed == CVS_VHS_LP) { luma_cut = 1900000; chroma_cut = 300000; }
     if (p.output_vhs_tape_speed == CVS_VHS_EP) { luma_cut = 1400000; chroma_cut = 280000; }
     set(K.a_luma, K.b_luma, K.c_luma, pole_alpha(luma_cut));
-    set(K.a_chroma, K.b_chroma, K.c_chroma, pole_alpha(chroma_cut));
+    set(K.a_ch.x, K.b_ch.x, K.c_ch.x, pole_alpha(chroma_cut));
+    K.a_ch.y = K.a_ch.x; K.b_ch.y = K.b_ch.x; K.c_ch.y = K.c_ch.x;
     set(K.a_sharp, K.b_sharp, K.c_sharp, pole_alpha(luma_cut * 4));    // :1874
     K.sharpen = (R)p.vhs_out_sharpen;
     if (outfull) {                                          // composite_lowpass, :1442
-        set(K.a_outI, K.b_outI, K.c_outI, pole_alpha(1300000));
-        set(K.a_outQ, K.b_outQ, K.c_outQ, pole_alpha(600000));
+        set(K.a_out.x, K.b_out.x, K.c_out.x, pole_alpha(1300000));
+        set(K.a_out.y, K.b_out.y, K.c_out.y, pole_alpha(600000));
     } else {                                                // composite_lowpass_tv, :1411
-        set(K.a_outI, K.b_outI, K.c_outI, pole_alpha(2600000));
-        set(K.a_outQ, K.b_outQ, K.c_outQ, pole_alpha(2600000));
+        set(K.a_out.x, K.b_out.x, K.c_out.x, pole_alpha(2600000));
+        set(K.a_out.y, K.b_out.y, K.c_out.y, pole_alpha(2600000));
     }
     uint32_t f = 0;
     if (p.composite_in_chroma_lowpass) f |= F_IN_LP;
@@ -190,7 +191,8 @@ void build_field_side(const cvs_params &p, const GeomPlan &g, RandCursor &cur, F
         // A negative shift -d moves the row right by d; the pixels that wrap in come from
         // tmp[twidth - d + x], which is zero padding for every x when d <= w/10.  Then the rotation is
         // a plain delay and k_fields does it in shared memory; anything else goes through the pre-pass.
-        bool inline_ok = !rows.empty();
+        // (only the VHS kernels carry the delay ring: -vhs-head-switching without -vhs takes the pre-pass)
+        bool inline_ok = !rows.empty() && p.emulating_vhs != 0;
         for (int sh : shifts)
             if (!(sh < 0 && -sh <= kHsMaxDelay && -sh <= w / 10)) inline_ok = false;
         for (size_t i = 0; i < rows.size(); i++) {

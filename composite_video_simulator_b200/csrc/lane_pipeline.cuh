@@ -72,16 +72,25 @@ enum : uint32_t {
 constexpr int kHsRing = 64;               // per-lane delay ring of the in-kernel head switch
 constexpr int kHsMaxDelay = kHsRing - kT; // largest shift the ring can express
 
+// ---- pairs --------------------------------------------------------------------------------------
+// The two chroma planes (I/Q, later U/V) go through identical arithmetic, so they travel as a pair.
+// On sm_100 an fp32 pair in an aligned register pair is one operand of the packed FFMA2/FADD2/FMUL2
+// instructions (CUDA 12.9 __ffma2_rn/_rz/_rd, __fadd2_*, __fmul2_*): one issue slot does both planes.
+// The kernel is issue-bound (profiles/ncu_kfields_r1.md), so this is where Blackwell's packed fp32
+// pays.  Host code and the fp64 path see a plain struct and operate per component.
+template <typename R> struct alignas(2 * sizeof(R)) V2 { R x, y; };
+template <typename R> CVS_HD V2<R> mk2(R a, R b) { V2<R> v; v.x = a; v.y = b; return v; }
+
 // ---- launch-uniform constants -------------------------------------------------------------
 template <typename R>
 struct KConst {
     // per filter: a = alpha, b = 1 - alpha, c = alpha^3 (gain of the scaled fp32 cascade, see Num<float>)
-    R a_inI, b_inI, c_inI, a_inQ, b_inQ, c_inQ;   // input chroma lowpass 1.3 MHz / 0.6 MHz   (:1442)
+    V2<R> a_in, b_in, c_in;                       // input chroma lowpass: x = I 1.3 MHz, y = Q 0.6 MHz (:1442)
     R a_pre, b_pre, preemph;                      // composite pre-emphasis                    (:1621)
     R a_luma, b_luma, c_luma;                     // VHS luma lowpass                          (:1800)
-    R a_chroma, b_chroma, c_chroma;               // VHS chroma lowpass                        (:1821)
+    V2<R> a_ch, b_ch, c_ch;                       // VHS chroma lowpass (U and V alike)         (:1821)
     R a_sharp, b_sharp, c_sharp, sharpen;         // VHS sharpen lowpass (4x luma cut), gain   (:1874,:1880)
-    R a_outI, b_outI, c_outI, a_outQ, b_outQ, c_outQ;   // output chroma lowpass               (:1411 / :1442)
+    V2<R> a_out, b_out, c_out;                    // output chroma lowpass: x = I, y = Q        (:1411 / :1442)
     const R *phase_lut;                   // [2*pnoise+1][2] = {sin, cos} of state*pi/100, state = -p..p (:1746-1749)
     uint32_t flags;
     int32_t pnoise;                       // video_chroma_phase_noise
@@ -136,6 +145,19 @@ template <> struct Num<double> {
     static CVS_HD double cascade3_trunc(double p[3], double s, double a, double b, double c) {
         return trunc_(cascade3(p, s, a, b, c));
     }
+    // pair forms: per component, in the reference's operation order
+    typedef V2<double> P;
+    static CVS_HD void cascade_reset2(P p[3], double v) { p[0] = mk2(v, v); p[1] = p[0]; p[2] = p[0]; }
+    static CVS_HD P cascade3_trunc2(P p[3], P s, P a, P b, P /*c*/) {
+        double x = pole(p[0].x, s.x, a.x, b.x); x = pole(p[1].x, x, a.x, b.x); x = pole(p[2].x, x, a.x, b.x);
+        double y = pole(p[0].y, s.y, a.y, b.y); y = pole(p[1].y, y, a.y, b.y); y = pole(p[2].y, y, a.y, b.y);
+        return mk2(trunc_(x), trunc_(y));
+    }
+    static CVS_HD P add2(P a, P b) { return mk2(add(a.x, b.x), add(a.y, b.y)); }
+    static CVS_HD P scale2(P a, double k) { return mk2(mul(a.x, k), mul(a.y, k)); }
+    static CVS_HD P floor_half2(P s) { return mk2(floor_half(s.x), floor_half(s.y)); }
+    static CVS_HD P rot2(P uv, double c, double s, double /*ns*/) { return mk2(rot_a(uv.x, c, uv.y, s), rot_b(uv.x, s, uv.y, c)); }
+    static CVS_HD void rgb2yiq2(uint32_t px, double &Y, P &IQ) { rgb2yiq(px, Y, IQ.x, IQ.y); }
     static CVS_HD double floor_half(double s) { return ::floor(mul(s, 0.5)); }          // C int '>> 1'
     static CVS_HD double trunc_quarter(double s) { return ::trunc(mul(s, 0.25)); }     // C int '/ 4'
     static CVS_HD void unpack_rgb(uint32_t px, int &r, int &g, int &b) {
@@ -255,6 +277,84 @@ template <> struct Num<float> {
     static CVS_HD float cascade3_trunc(float p[3], float s, float /*a*/, float b, float c) {
         return trunc_mul_pos(cascade3_raw(p, s, b), c);
     }
+    // ---- pair forms: packed FFMA2/FADD2/FMUL2 on the device, the same per-component arithmetic on the host
+    typedef V2<float> P;
+#if defined(__CUDA_ARCH__)
+    static __device__ __forceinline__ float2 f2(P a) { return make_float2(a.x, a.y); }
+    static __device__ __forceinline__ P pp(float2 a) { return mk2(a.x, a.y); }
+    static __device__ __forceinline__ float2 msign2(float2 a) {      // copysign(1.5*2^23, a) per component
+        return make_float2(__uint_as_float((__float_as_uint(a.x) & 0x80000000u) | 0x4B400000u),
+                           __uint_as_float((__float_as_uint(a.y) & 0x80000000u) | 0x4B400000u));
+    }
+#endif
+    static CVS_HD void cascade_reset2(P p[3], float v) { (void)v; p[0] = mk2(0.0f, 0.0f); p[1] = p[0]; p[2] = p[0]; }   // chroma resets to 0
+    static CVS_HD P cascade3_trunc2(P p[3], P s, P /*a*/, P b, P c) {
+#if defined(__CUDA_ARCH__)
+        const float2 bb = f2(b);
+        float2 q0 = __ffma2_rn(bb, f2(p[0]), f2(s));
+        float2 q1 = __ffma2_rn(bb, f2(p[1]), q0);
+        float2 q2 = __ffma2_rn(bb, f2(p[2]), q1);
+        p[0] = pp(q0); p[1] = pp(q1); p[2] = pp(q2);
+        const float2 ms = msign2(q2);                               // sign(q2 * c) == sign(q2): c > 0
+        return pp(__fadd2_rn(__ffma2_rz(q2, f2(c), ms), make_float2(-ms.x, -ms.y)));
+#else
+        float px_[3] = {p[0].x, p[1].x, p[2].x}, py_[3] = {p[0].y, p[1].y, p[2].y};
+        const float x = trunc_mul_pos(cascade3_raw(px_, s.x, b.x), c.x);
+        const float y = trunc_mul_pos(cascade3_raw(py_, s.y, b.y), c.y);
+        for (int k = 0; k < 3; k++) p[k] = mk2(px_[k], py_[k]);
+        return mk2(x, y);
+#endif
+    }
+    static CVS_HD P add2(P a, P b) {
+#if defined(__CUDA_ARCH__)
+        return pp(__fadd2_rn(f2(a), f2(b)));
+#else
+        return mk2(a.x + b.x, a.y + b.y);
+#endif
+    }
+    static CVS_HD P scale2(P a, float k) {                          // both components times k
+#if defined(__CUDA_ARCH__)
+        return pp(__fmul2_rn(f2(a), make_float2(k, k)));
+#else
+        return mk2(a.x * k, a.y * k);
+#endif
+    }
+    static CVS_HD P floor_half2(P s) {
+#if defined(__CUDA_ARCH__)
+        const float2 m = make_float2(kMagic, kMagic);
+        return pp(__fadd2_rn(__ffma2_rd(f2(s), make_float2(0.5f, 0.5f), m), make_float2(-kMagic, -kMagic)));
+#else
+        return mk2(floor_half(s.x), floor_half(s.y));
+#endif
+    }
+    // (u, v) -> trunc(u c - v s, u s + v c); ns = -s  (:1756-1757)
+    static CVS_HD P rot2(P uv, float c, float s, float ns) {
+#if defined(__CUDA_ARCH__)
+        const float2 t = __fmul2_rn(make_float2(uv.y, uv.y), make_float2(ns, c));
+        const float2 r = __ffma2_rn(make_float2(uv.x, uv.x), make_float2(c, s), t);
+        const float2 ms = msign2(r);
+        return pp(__fadd2_rn(__fadd2_rz(r, ms), make_float2(-ms.x, -ms.y)));
+#else
+        (void)ns;
+        return mk2(rot_a(uv.x, c, uv.y, s), rot_b(uv.x, s, uv.y, c));
+#endif
+    }
+    static CVS_HD void rgb2yiq2(uint32_t px, float &Y, P &IQ) {
+#if defined(__CUDA_ARCH__)
+        const float rf = __fadd_rn(__uint_as_float(__byte_perm(px, 0x4B000000u, 0x7442)), -8388608.0f);
+        const float gf = __fadd_rn(__uint_as_float(__byte_perm(px, 0x4B000000u, 0x7441)), -8388608.0f);
+        const float bf = __fadd_rn(__uint_as_float(__byte_perm(px, 0x4B000000u, 0x7440)), -8388608.0f);
+        const float dY = fma_(0.11f, bf, fma_(0.59f, gf, mul(0.30f, rf)));
+        const float bd = sub(bf, dY), rd = sub(rf, dY);
+        Y = trunc_mul_pos(dY, 256.0f);
+        const float2 t = __fmul2_rn(make_float2(-0.27f, 0.41f), make_float2(bd, bd));
+        const float2 iq = __ffma2_rn(make_float2(0.74f, 0.48f), make_float2(rd, rd), t);
+        const float2 ms = msign2(iq);
+        IQ = pp(__fadd2_rn(__ffma2_rz(iq, make_float2(256.0f, 256.0f), ms), make_float2(-ms.x, -ms.y)));
+#else
+        rgb2yiq(px, Y, IQ.x, IQ.y);
+#endif
+    }
     static CVS_HD void rgb2yiq(uint32_t px, float &Y, float &I, float &Q) {
 #if defined(__CUDA_ARCH__)
         // 0x4B0000bb is the float 2^23 + bb: one PRMT + one FADD per channel instead of an I2F
@@ -371,7 +471,7 @@ template <typename R>
 struct RowConst {
     R mI[4], mQ[4];      // QAM carrier taps for (x & 3): Umult/Vmult rotated by the line phase xi (:1465-1466)
     R sgA;               // demod sign for even x with (x & 2) == 0; the (x & 2) != 0 sign is -sgA
-    R sinp, cosp;        // chroma phase noise rotation of this row (:1748-1749)
+    R sinp, cosp, nsinp; // chroma phase noise rotation of this row (:1748-1749); nsinp = -sinp
     int xi;              // subcarrier phase index (:1473-1480)
     uint32_t rflags;
     int row;             // field row index (y = field + 2*row)
@@ -402,8 +502,8 @@ struct Lane {
     // --- carried state (all statically indexed) ---
     // A
     R Yprev[kT];                     // Y of B(s-1)
-    R oIprev[kT], oQprev[kT];        // input-lowpass cascade outputs for t in B(s-1)
-    R pI[3], pQ[3];                  // cascade poles
+    V2<R> oIQprev[kT];               // input-lowpass cascade outputs (I, Q) for t in B(s-1)
+    V2<R> pIQ[3];                    // cascade poles
     R pPre;                          // pre-emphasis pole
     int nY;                          // luma noise accumulator (:1633)
     // B
@@ -412,16 +512,16 @@ struct Lane {
     int nU, nV;                      // chroma noise accumulators (:1720)
     R pL[3], pLpre;                  // VHS luma poles (:1800-1805)
     R pS[3];                         // sharpen poles (:1873-1876)
-    R pU[3], pV[3];                  // VHS chroma poles (:1821-1826)
-    R oUprev[kT], oVprev[kT];        // chroma cascade outputs for t in B(s-3)
+    V2<R> pUV[3];                    // VHS chroma poles (:1821-1826)
+    V2<R> oUVprev[kT];               // chroma cascade outputs (U, V) for t in B(s-3)
     R Y3a[kT], Y3b[kT];              // Y3 of B(s-3), B(s-4)
     // B2 / C
     R C2m1;                          // C2[8(s-5)-1]
     R C2prev[kT];                    // C2 of B(s-5)
     // F
-    R pOI[3], pOQ[3];                // output lowpass poles
-    R Ytail[OD], Itail[OD], Qtail[OD];      // last OD values of Y4 / raw I4 / raw Q4 of the previous F block
-    R oOItail[OD], oOQtail[OD];             // last OD cascade outputs of the previous F block
+    V2<R> pOIQ[3];                   // output lowpass poles
+    R Ytail[OD];                     // last OD values of Y4 of the previous F block
+    V2<R> IQtail[OD], oOIQtail[OD];  // ... of the raw (I4, Q4) and of the cascade outputs
     uint32_t outprev[kT];            // packed pixels of positions [8(k-1), 8k-OD) in slots 0..7-OD
 
     LaneRng rngL, rngC;
@@ -431,22 +531,20 @@ struct Lane {
     CVS_HD void reset(const KConst<R> &K) {
         CVS_UNROLL
         for (int j = 0; j < kT; j++) {
-            Yprev[j] = 0; oIprev[j] = 0; oQprev[j] = 0; Cprev[j] = 0;
-            oUprev[j] = 0; oVprev[j] = 0; Y3a[j] = 0; Y3b[j] = 0; C2prev[j] = 0; outprev[j] = 0;
+            Yprev[j] = 0; oIQprev[j] = mk2((R)0, (R)0); Cprev[j] = 0;
+            oUVprev[j] = mk2((R)0, (R)0); Y3a[j] = 0; Y3b[j] = 0; C2prev[j] = 0; outprev[j] = 0;
         }
         CVS_UNROLL
-        for (int k = 0; k < 3; k++) {
-            pI[k] = 0; pQ[k] = 0;           // resetFilter(0), :1447
-            pS[k] = 0;                      // :1875
-            pU[k] = 0; pV[k] = 0;           // :1823,:1825
-            pOI[k] = 0; pOQ[k] = 0;         // :1416
-        }
+        for (int k = 0; k < 3; k++) pS[k] = 0;    // :1875
+        Num<R>::cascade_reset2(pIQ, (R)0);        // resetFilter(0), :1447
+        Num<R>::cascade_reset2(pUV, (R)0);        // :1823,:1825
+        Num<R>::cascade_reset2(pOIQ, (R)0);       // :1416
         Num<R>::cascade_reset(pL, (R)16, K.a_luma);   // resetFilter(16), :1802
         pLpre = 16;                         // :1805
         pPre = 16;                          // :1622
         Cm1 = 0; C2m1 = 0;
         CVS_UNROLL
-        for (int k = 0; k < OD; k++) { Ytail[k] = 0; Itail[k] = 0; Qtail[k] = 0; oOItail[k] = 0; oOQtail[k] = 0; }
+        for (int k = 0; k < OD; k++) { Ytail[k] = 0; IQtail[k] = mk2((R)0, (R)0); oOIQtail[k] = mk2((R)0, (R)0); }
     }
 };
 
@@ -468,7 +566,7 @@ CVS_HD R modulate(R Yv, R Iv, R Qv, R mI, R mQ, int amp) {
 // outputs Yb (box-filtered luma), Ib, Qb for the 8 pixels of the block.
 template <typename R, int MODE>
 CVS_HD void demod_block(const RowConst<R> &rc, int k, int w, int amp, R cm1, const R c[2 * kT],
-                        R Yb[kT], R Ib[kT], R Qb[kT]) {
+                        R Yb[kT], V2<R> IQb[kT]) {
     constexpr bool EDGE = MODE >= 1, GEN = MODE == 2;
     const int x0 = k * kT;
     // box[m] = (C[m-1] + C[m] + C[m+1] + C[m+2]) / 4 ; chroma[m] = C[m+2] - box[m], m = 0..12
@@ -499,7 +597,7 @@ CVS_HD void demod_block(const RowConst<R> &rc, int k, int w, int amp, R cm1, con
     // even pixels: I = -chroma[x+xi], Q = -chroma[x+xi+1]  (:1549-1552); 5 even positions: 4 in
     // the block plus the first of the next block (needed by the odd-pixel interpolation)
     const bool x1 = (rc.xi & 1) != 0, x2 = (rc.xi & 2) != 0;
-    R Ie[5], Qe[5];
+    V2<R> IQe[5];
     CVS_UNROLL
     for (int e = 0; e < 5; e++) {
         const int j = 2 * e;
@@ -512,23 +610,17 @@ CVS_HD void demod_block(const RowConst<R> &rc, int k, int w, int amp, R cm1, con
         if (EDGE) {
             const int x = x0 + j;
             const bool ok = (x + rc.xi + 1) < w;        // :1549, else zero (:1553-1556)
-            iv = ok ? -iv : (R)0;
-            qv = ok ? -qv : (R)0;
+            IQe[e] = mk2(ok ? -iv : (R)0, ok ? -qv : (R)0);
         } else {
             const R sg = (j & 2) ? -rc.sgA : rc.sgA;    // -(flip ? -1 : 1) folded
-            iv = Num<R>::mul(iv, sg);
-            qv = Num<R>::mul(qv, sg);
+            IQe[e] = Num<R>::scale2(mk2(iv, qv), sg);
         }
-        Ie[e] = iv;
-        Qe[e] = qv;
     }
     // odd pixels: average of the even neighbours, arithmetic >> 1 (:1557-1560)
     CVS_UNROLL
     for (int e = 0; e < 4; e++) {
-        Ib[2 * e] = Ie[e];
-        Qb[2 * e] = Qe[e];
-        Ib[2 * e + 1] = shr1_floor<R>(Num<R>::add(Ie[e], Ie[e + 1]));
-        Qb[2 * e + 1] = shr1_floor<R>(Num<R>::add(Qe[e], Qe[e + 1]));
+        IQb[2 * e] = IQe[e];
+        IQb[2 * e + 1] = Num<R>::floor_half2(Num<R>::add2(IQe[e], IQe[e + 1]));
     }
     if (EDGE) {
         // after the interpolation the last pixels lose their chroma (:1561-1564); an odd pixel is
@@ -537,7 +629,7 @@ CVS_HD void demod_block(const RowConst<R> &rc, int k, int w, int amp, R cm1, con
         CVS_UNROLL
         for (int j = 0; j < kT; j++) {
             const int x = x0 + j;
-            if (x >= zstart || ((j & 1) && (x + 1 >= w))) { Ib[j] = 0; Qb[j] = 0; }
+            if (x >= zstart || ((j & 1) && (x + 1 >= w))) IQb[j] = mk2((R)0, (R)0);
         }
     }
 }
@@ -557,7 +649,7 @@ enum { MODE_FAST = 0, MODE_EDGE = 1, MODE_GENERAL = 2 };
 // receives the block of the row above (lane - 1).  On the GPU this is 16 __shfl_up_sync.
 template <typename R>
 struct BlendXchg {
-    R u[kT], v[kT];
+    V2<R> uv[kT];
 };
 
 template <typename R, bool VHS, int CD, bool OUTFULL>
@@ -574,19 +666,20 @@ struct Pipeline {
         constexpr bool EDGE = MODE >= 1, GEN = MODE == 2;
         const int w = K.w;
         const int p = s * kT;
-        R Ycur[kT], oIcur[kT], oQcur[kT];
+        R Ycur[kT];
+        V2<R> oIQcur[kT];
         // A1: RGB -> YIQ and the input chroma lowpass cascades on B(s)
         CVS_UNROLL
         for (int j = 0; j < kT; j++) {
             const int t = p + j;
             if (!EDGE || t < w) {
-                R y, i, q;
-                N::rgb2yiq(px[j], y, i, q);
+                R y;
+                V2<R> iq;
+                N::rgb2yiq2(px[j], y, iq);
                 Ycur[j] = y;
-                oIcur[j] = N::cascade3_trunc(ln.pI, i, K.a_inI, K.b_inI, K.c_inI);   // P[x-delay] = s, :1453
-                oQcur[j] = N::cascade3_trunc(ln.pQ, q, K.a_inQ, K.b_inQ, K.c_inQ);
+                oIQcur[j] = N::cascade3_trunc2(ln.pIQ, iq, K.a_in, K.b_in, K.c_in);   // P[x-delay] = s, :1453
             } else {
-                Ycur[j] = 0; oIcur[j] = 0; oQcur[j] = 0;
+                Ycur[j] = 0; oIQcur[j] = mk2((R)0, (R)0);
             }
         }
         // A2: composite block B(s-1)
@@ -601,8 +694,8 @@ struct Pipeline {
                 if (!EDGE || x < w) {
                     // filtered chroma arrives early by the filter delay; the last `delay` samples of
                     // a line keep their unfiltered values (:1453)
-                    R iv = (j + 2 < kT) ? ln.oIprev[(j + 2) % kT] : oIcur[(j + 2) % kT];
-                    R qv = (j + 4 < kT) ? ln.oQprev[(j + 4) % kT] : oQcur[(j + 4) % kT];
+                    R iv = (j + 2 < kT) ? ln.oIQprev[(j + 2) % kT].x : oIQcur[(j + 2) % kT].x;
+                    R qv = (j + 4 < kT) ? ln.oIQprev[(j + 4) % kT].y : oIQcur[(j + 4) % kT].y;
                     if (EDGE) {
                         const bool rawI = !in_lp || (x + 2 >= w), rawQ = !in_lp || (x + 4 >= w);
                         if (rawI || rawQ) {
@@ -633,8 +726,7 @@ struct Pipeline {
         CVS_UNROLL
         for (int j = 0; j < kT; j++) {
             ln.Yprev[j] = Ycur[j];
-            ln.oIprev[j] = oIcur[j];
-            ln.oQprev[j] = oQcur[j];
+            ln.oIQprev[j] = oIQcur[j];
         }
     }
 
@@ -643,13 +735,13 @@ struct Pipeline {
     // block B(s-4) in xo (pre-blend) and leaves Y3 of B(s-2) in y3new.
     template <int MODE>
     static CVS_HD void stage_b(const KConst<R> &K, const RowConst<R> &rc, L &ln, int s, const R Cnew[kT],
-                               R Yb[kT], R Ib[kT], R Qb[kT], BlendXchg<R> &xo) {
+                               R Yb[kT], V2<R> IQb[kT], BlendXchg<R> &xo) {
         constexpr bool EDGE = MODE >= 1, GEN = MODE == 2;
         const int w = K.w;
         const int k = s - 2;
         if (EDGE && k < 0) {
             CVS_UNROLL
-            for (int j = 0; j < kT; j++) { Yb[j] = 0; Ib[j] = 0; Qb[j] = 0; xo.u[j] = 0; xo.v[j] = 0; }
+            for (int j = 0; j < kT; j++) { Yb[j] = 0; IQb[j] = mk2((R)0, (R)0); xo.uv[j] = mk2((R)0, (R)0); }
             ln.Cm1 = ln.Cprev[kT - 1];
             CVS_UNROLL
             for (int j = 0; j < kT; j++) ln.Cprev[j] = Cnew[j];
@@ -660,9 +752,9 @@ struct Pipeline {
         for (int j = 0; j < kT; j++) { c[j] = ln.Cprev[j]; c[kT + j] = Cnew[j]; }
         if (GEN && (K.flags & F_NOCOLOR)) {                        // :1715: no demod, chroma stays zero
             CVS_UNROLL
-            for (int j = 0; j < kT; j++) { Yb[j] = c[j]; Ib[j] = 0; Qb[j] = 0; }
+            for (int j = 0; j < kT; j++) { Yb[j] = c[j]; IQb[j] = mk2((R)0, (R)0); }
         } else {
-            demod_block<R, MODE>(rc, k, w, K.amp_back, ln.Cm1, c, Yb, Ib, Qb);   // :1716
+            demod_block<R, MODE>(rc, k, w, K.amp_back, ln.Cm1, c, Yb, IQb);   // :1716
         }
         ln.Cm1 = ln.Cprev[kT - 1];
         CVS_UNROLL
@@ -675,8 +767,7 @@ struct Pipeline {
             CVS_UNROLL
             for (int j = 0; j < kT; j++) {
                 if (!EDGE || x0 + j < w) {
-                    Ib[j] = N::add(Ib[j], (R)ln.nU);
-                    Qb[j] = N::add(Qb[j], (R)ln.nV);
+                    IQb[j] = N::add2(IQb[j], mk2((R)ln.nU, (R)ln.nV));
                     const uint32_t m = (uint32_t)(2 * K.cnoise + 1);
                     const int dU = draw_mod(ln.rngC.next_in_group(gC, gCn, 2 * j, 2 * kT), m, K.cmagic, K.cshift);
                     ln.nU = noise_step(ln.nU, dU, K.cnoise);
@@ -688,16 +779,14 @@ struct Pipeline {
         if (GEN ? ((K.flags & F_PHASE) != 0) : VHS) {              // :1736-1764
             CVS_UNROLL
             for (int j = 0; j < kT; j++) {
-                const R u = Ib[j], v = Qb[j];
-                Ib[j] = N::rot_a(u, rc.cosp, v, rc.sinp);
-                Qb[j] = N::rot_b(u, rc.sinp, v, rc.cosp);
+                IQb[j] = N::rot2(IQb[j], rc.cosp, rc.sinp, rc.nsinp);
             }
         }
         if constexpr (VHS) {
 
         // VHS luma: 3 poles @ luma_cut reset 16, + 1.6 x highpass, then sharpen (:1793-1812, :1865-1883)
         // VHS chroma: 3 poles @ chroma_cut, output CD samples early (:1814-1836)
-        R oUcur[kT], oVcur[kT];
+        V2<R> oUVcur[kT];
         CVS_UNROLL
         for (int j = 0; j < kT; j++) {
             if (!EDGE || x0 + j < w) {
@@ -706,35 +795,31 @@ struct Pipeline {
                 const R y2 = N::boost(sv, N::sub(sv, lp), (R)1.6);
                 const R ts = N::cascade3(ln.pS, y2, K.a_sharp, K.b_sharp, K.c_sharp);
                 Yb[j] = N::sharpen(y2, ts, K.sharpen);
-                oUcur[j] = N::cascade3_trunc(ln.pU, Ib[j], K.a_chroma, K.b_chroma, K.c_chroma);
-                oVcur[j] = N::cascade3_trunc(ln.pV, Qb[j], K.a_chroma, K.b_chroma, K.c_chroma);
+                oUVcur[j] = N::cascade3_trunc2(ln.pUV, IQb[j], K.a_ch, K.b_ch, K.c_ch);
                 if (EDGE && (x0 + j >= w - CD) && (x0 + j - (w - CD)) < kTailSlots) {
                     // the last CD samples keep their pre-filter values (:1830,:1834): stash them
-                    ln.tailU[(x0 + j - (w - CD)) * ln.tail_stride] = Ib[j];
-                    ln.tailV[(x0 + j - (w - CD)) * ln.tail_stride] = Qb[j];
+                    ln.tailU[(x0 + j - (w - CD)) * ln.tail_stride] = IQb[j].x;
+                    ln.tailV[(x0 + j - (w - CD)) * ln.tail_stride] = IQb[j].y;
                 }
             } else {
-                Yb[j] = 0; oUcur[j] = 0; oVcur[j] = 0;
+                Yb[j] = 0; oUVcur[j] = mk2((R)0, (R)0);
             }
         }
         // delayed chroma block B(s-4): position x' = 8(s-4)+j was produced at time x'+CD
         CVS_UNROLL
         for (int j = 0; j < kT; j++) {
             const int rel = j + CD - 2 * kT;                // index into the current outputs (time in B(s-2))
-            R u = (rel >= 0) ? oUcur[(rel + 2 * kT) % kT] : ln.oUprev[(rel + kT) % kT];
-            R v = (rel >= 0) ? oVcur[(rel + 2 * kT) % kT] : ln.oVprev[(rel + kT) % kT];
+            V2<R> uv = (rel >= 0) ? oUVcur[(rel + 2 * kT) % kT] : ln.oUVprev[(rel + kT) % kT];
             if (EDGE) {
                 const int xp = (s - 4) * kT + j;
                 if (xp >= w - CD && xp < w && xp >= 0 && (xp - (w - CD)) < kTailSlots) {
-                    u = ln.tailU[(xp - (w - CD)) * ln.tail_stride];
-                    v = ln.tailV[(xp - (w - CD)) * ln.tail_stride];
+                    uv = mk2(ln.tailU[(xp - (w - CD)) * ln.tail_stride], ln.tailV[(xp - (w - CD)) * ln.tail_stride]);
                 }
             }
-            xo.u[j] = u;
-            xo.v[j] = v;
+            xo.uv[j] = uv;
         }
         CVS_UNROLL
-        for (int j = 0; j < kT; j++) { ln.oUprev[j] = oUcur[j]; ln.oVprev[j] = oVcur[j]; }
+        for (int j = 0; j < kT; j++) ln.oUVprev[j] = oUVcur[j];
         }
     }
 
@@ -744,28 +829,26 @@ struct Pipeline {
     template <int MODE>
     static CVS_HD void stage_c(const KConst<R> &K, const RowConst<R> &rc, L &ln, int s, const R Y3new[kT],
                                const BlendXchg<R> &own, const BlendXchg<R> &above,
-                               R Yf[kT], R If[kT], R Qf[kT], int &kf) {
+                               R Yf[kT], V2<R> IQf[kT], int &kf) {
         constexpr bool EDGE = MODE >= 1, GEN = MODE == 2;
         const int w = K.w;
-        R U[kT], V[kT];
+        V2<R> UV[kT];
         const bool blend = (K.flags & F_VBLEND) && rc.row >= 1;       // loop starts at field+2, :1849
         const bool have_above = rc.row >= 2;                          // row field+2 blends with zero
         CVS_UNROLL
         for (int j = 0; j < kT; j++) {
-            R u = own.u[j], v = own.v[j];
+            V2<R> uv = own.uv[j];
             if (blend) {                                              // (delay + cur + 1) >> 1, :1857-1858
-                const R au = have_above ? above.u[j] : (R)0, av = have_above ? above.v[j] : (R)0;
-                u = shr1_floor<R>(N::add(N::add(au, u), (R)1));
-                v = shr1_floor<R>(N::add(N::add(av, v), (R)1));
+                const V2<R> a = have_above ? above.uv[j] : mk2((R)0, (R)0);
+                uv = N::floor_half2(N::add2(N::add2(a, uv), mk2((R)1, (R)1)));
             }
-            U[j] = u;
-            V[j] = v;
+            UV[j] = uv;
         }
         const bool svideo = GEN && (K.flags & F_SVIDEO);
         if (svideo) {                                                 // :1885: no recombine
             kf = s - 4;
             CVS_UNROLL
-            for (int j = 0; j < kT; j++) { Yf[j] = ln.Y3b[j]; If[j] = U[j]; Qf[j] = V[j]; }
+            for (int j = 0; j < kT; j++) { Yf[j] = ln.Y3b[j]; IQf[j] = UV[j]; }
         } else {
             kf = s - 5;
             // C2 of B(s-4) = Y3 + QAM(U,V) with subcarrier_amplitude (:1886)
@@ -775,15 +858,15 @@ struct Pipeline {
                 const int x = (s - 4) * kT + j;
                 R cv = 0;
                 if (!EDGE || (x >= 0 && x < w))
-                    cv = modulate<R, MODE>(ln.Y3b[j], U[j], V[j], rc.mI[j & 3], rc.mQ[j & 3], K.amp);
+                    cv = modulate<R, MODE>(ln.Y3b[j], UV[j].x, UV[j].y, rc.mI[j & 3], rc.mQ[j & 3], K.amp);
                 c[kT + j] = cv;
                 c[j] = ln.C2prev[j];
             }
             if (!EDGE || kf >= 0) {
-                demod_block<R, MODE>(rc, kf, w, K.amp, ln.C2m1, c, Yf, If, Qf);      // :1887
+                demod_block<R, MODE>(rc, kf, w, K.amp, ln.C2m1, c, Yf, IQf);      // :1887
             } else {
                 CVS_UNROLL
-                for (int j = 0; j < kT; j++) { Yf[j] = 0; If[j] = 0; Qf[j] = 0; }
+                for (int j = 0; j < kT; j++) { Yf[j] = 0; IQf[j] = mk2((R)0, (R)0); }
             }
             ln.C2m1 = ln.C2prev[kT - 1];
             CVS_UNROLL
@@ -797,23 +880,22 @@ struct Pipeline {
     // Returns true when `out` holds a complete block B(kf-1) (kf >= 1).
     template <int MODE>
     static CVS_HD bool stage_f(const KConst<R> &K, const RowConst<R> &rc, L &ln, int kf,
-                               R Yf[kT], R If[kT], R Qf[kT], uint32_t out[kT]) {
+                               R Yf[kT], V2<R> IQf[kT], uint32_t out[kT]) {
         constexpr bool EDGE = MODE >= 1, GEN = MODE == 2;
         constexpr int OD = L::OD, ODI = L::ODI, ODQ = L::ODQ;
         const int w = K.w;
         if (EDGE && kf < 0) return false;
         const int x0 = kf * kT;
-        const bool drop = (rc.rflags & RF_DROPOUT) != 0;              // :1891-1901
+        const R keep = (rc.rflags & RF_DROPOUT) ? (R)0 : (R)1;       // :1891-1901: the row loses its chroma
         CVS_UNROLL
-        for (int j = 0; j < kT; j++) { If[j] = drop ? (R)0 : If[j]; Qf[j] = drop ? (R)0 : Qf[j]; }
-        R oI[kT], oQ[kT];
+        for (int j = 0; j < kT; j++) IQf[j] = N::scale2(IQf[j], keep);
+        V2<R> oIQ[kT];
         CVS_UNROLL
         for (int j = 0; j < kT; j++) {
             if (!EDGE || x0 + j < w) {
-                oI[j] = N::cascade3_trunc(ln.pOI, If[j], K.a_outI, K.b_outI, K.c_outI);   // :1420-1422
-                oQ[j] = N::cascade3_trunc(ln.pOQ, Qf[j], K.a_outQ, K.b_outQ, K.c_outQ);
+                oIQ[j] = N::cascade3_trunc2(ln.pOIQ, IQf[j], K.a_out, K.b_out, K.c_out);   // :1420-1422
             } else {
-                oI[j] = 0; oQ[j] = 0;
+                oIQ[j] = mk2((R)0, (R)0);
             }
         }
         const bool out_lp = !GEN || (K.flags & F_OUT_LP);
@@ -827,11 +909,11 @@ struct Pipeline {
             const int ii = j - OD + ODI;          // filtered I index (time = pos + ODI)
             const int iq = j - OD + ODQ;
             const R yv = (iy >= 0) ? Yf[(iy + kT) % kT] : ln.Ytail[(iy + OD) % OD];
-            R iv = (ii >= 0) ? oI[(ii + kT) % kT] : ln.oOItail[(ii + OD) % OD];
-            R qv = (iq >= 0) ? oQ[(iq + kT) % kT] : ln.oOQtail[(iq + OD) % OD];
+            R iv = (ii >= 0) ? oIQ[(ii + kT) % kT].x : ln.oOIQtail[(ii + OD) % OD].x;
+            R qv = (iq >= 0) ? oIQ[(iq + kT) % kT].y : ln.oOIQtail[(iq + OD) % OD].y;
             if (EDGE) {
-                const R ir = (iy >= 0) ? If[(iy + kT) % kT] : ln.Itail[(iy + OD) % OD];
-                const R qr = (iy >= 0) ? Qf[(iy + kT) % kT] : ln.Qtail[(iy + OD) % OD];
+                const R ir = (iy >= 0) ? IQf[(iy + kT) % kT].x : ln.IQtail[(iy + OD) % OD].x;
+                const R qr = (iy >= 0) ? IQf[(iy + kT) % kT].y : ln.IQtail[(iy + OD) % OD].y;
                 if (!out_lp || pos + ODI >= w) iv = ir;       // tail keeps pre-filter values (:1422)
                 if (!out_lp || pos + ODQ >= w) qv = qr;
             }
@@ -846,10 +928,8 @@ struct Pipeline {
         CVS_UNROLL
         for (int d = 0; d < OD; d++) {
             ln.Ytail[d] = Yf[kT - OD + d];
-            ln.Itail[d] = If[kT - OD + d];
-            ln.Qtail[d] = Qf[kT - OD + d];
-            ln.oOItail[d] = oI[kT - OD + d];
-            ln.oOQtail[d] = oQ[kT - OD + d];
+            ln.IQtail[d] = IQf[kT - OD + d];
+            ln.oOIQtail[d] = oIQ[kT - OD + d];
         }
         return kf >= 1;
     }
@@ -928,6 +1008,7 @@ CVS_HD void row_setup(const KConst<R> &K, unsigned field, unsigned long long fie
         rc.sinp = 0;
         rc.cosp = 1;
     }
+    rc.nsinp = -rc.sinp;
 }
 
 // hist_out[k] = sum_i poly[i] * window[k + i]: the 31 raw words preceding position base + J, where

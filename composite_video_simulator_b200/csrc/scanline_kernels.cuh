@@ -59,11 +59,18 @@ struct LaunchArgs {
     int32_t *status;                     // sticky error word (CVS_ERR_NOISE_SYNC)
 };
 
-template <typename R>
-constexpr size_t fields_smem_bytes() {
-    return (size_t)2 * kRngSlots * kNT * sizeof(uint32_t) + (size_t)2 * kTailSlots * kNT * sizeof(R) +
-           (size_t)kWarpsPerCta * 64 * sizeof(uint32_t) + (size_t)kHsRing * kNT * sizeof(R);
-}
+// Shared memory layout of k_fields (bytes): [rng rings: 1 (luma) or 2 (luma+chroma) x 32 x NT words]
+// [generator windows: 64 words per warp] and, for the VHS kernels only, [chroma tail stash 2 x 16 x NT R]
+// [head-switch delay ring 64 x NT R].  The composite-only kernels need a third of the VHS footprint.
+template <typename R, bool VHS>
+struct SmemLayout {
+    static constexpr size_t rings = (size_t)2 * kRngSlots * kNT * sizeof(uint32_t);
+    static constexpr size_t wins = (size_t)kWarpsPerCta * 64 * sizeof(uint32_t);
+    static constexpr size_t tails = VHS ? (size_t)2 * kTailSlots * kNT * sizeof(R) : 0;
+    static constexpr size_t hsring = VHS ? (size_t)kHsRing * kNT * sizeof(R) : 0;
+    static constexpr size_t off_wins = rings, off_tails = rings + wins, off_hsring = rings + wins + tails;
+    static constexpr size_t total = rings + wins + tails + hsring;
+};
 
 __device__ __forceinline__ const uint32_t *row_ptr(const uint8_t *base, int stride, int y) {
     return (const uint32_t *)(base + (size_t)stride * (size_t)y);
@@ -118,7 +125,8 @@ struct Stepper {
                                                 const int32_t *hsrow, bool warp_hs,
                                                 R *hsring, bool warp_inl, bool valid, uint32_t *drow, bool vec_dst) {
         constexpr bool EDGE = MODE >= 1;
-        R C[kT], Yb[kT], Ib[kT], Qb[kT];
+        R C[kT], Yb[kT];
+        V2<R> IQb[kT];
         BlendXchg<R> xo;
         uint32_t pxprev[kT];
         if (EDGE) {
@@ -133,7 +141,7 @@ struct Stepper {
         P::template stage_a<MODE>(K, rc, ln, s, px, pxprev, hsrow, C);
         if (!EDGE && warp_hs) headswitch_substitute<R>(rc, hsrow, s - 1, C);
         if (warp_inl && (!EDGE || s >= 1)) headswitch_delay_block<R>(hsring, kNT, s - 1, K.w, rc.hs_delay, C);
-        P::template stage_b<MODE>(K, rc, ln, s, C, Yb, Ib, Qb, xo);
+        P::template stage_b<MODE>(K, rc, ln, s, C, Yb, IQb, xo);
         uint32_t out[kT];
         bool have;
         int kf;
@@ -141,15 +149,16 @@ struct Stepper {
             BlendXchg<R> above;
 #pragma unroll
             for (int j = 0; j < kT; j++) {
-                above.u[j] = __shfl_up_sync(0xffffffffu, xo.u[j], 1);
-                above.v[j] = __shfl_up_sync(0xffffffffu, xo.v[j], 1);
+                above.uv[j].x = __shfl_up_sync(0xffffffffu, xo.uv[j].x, 1);
+                above.uv[j].y = __shfl_up_sync(0xffffffffu, xo.uv[j].y, 1);
             }
-            R Yf[kT], If[kT], Qf[kT];
-            P::template stage_c<MODE>(K, rc, ln, s, Yb, xo, above, Yf, If, Qf, kf);
-            have = P::template stage_f<MODE>(K, rc, ln, kf, Yf, If, Qf, out);
+            R Yf[kT];
+            V2<R> IQf[kT];
+            P::template stage_c<MODE>(K, rc, ln, s, Yb, xo, above, Yf, IQf, kf);
+            have = P::template stage_f<MODE>(K, rc, ln, kf, Yf, IQf, out);
         } else {
             kf = s - 2;
-            have = P::template stage_f<MODE>(K, rc, ln, kf, Yb, Ib, Qb, out);
+            have = P::template stage_f<MODE>(K, rc, ln, kf, Yb, IQb, out);
         }
         if (have && valid) {
             const int x0 = (kf - 1) * kT;
@@ -171,9 +180,9 @@ __global__ void __launch_bounds__(kNT, CVS_MIN_CTAS) k_fields(const __grid_const
     typedef Lane<R, VHS, CD, OUTFULL> L;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t *rings = reinterpret_cast<uint32_t *>(smem_raw);
-    R *tails = reinterpret_cast<R *>(smem_raw + (size_t)2 * kRngSlots * kNT * sizeof(uint32_t));
-    uint32_t *wins = reinterpret_cast<uint32_t *>(smem_raw + (size_t)2 * kRngSlots * kNT * sizeof(uint32_t) +
-                                                  (size_t)2 * kTailSlots * kNT * sizeof(R));
+    typedef SmemLayout<R, VHS> SL;
+    uint32_t *wins = reinterpret_cast<uint32_t *>(smem_raw + SL::off_wins);
+    R *tails = reinterpret_cast<R *>(smem_raw + SL::off_tails);          // VHS only
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gw = blockIdx.x * kWarpsPerCta + warp;
     if (gw >= a.total_warps) return;
@@ -232,8 +241,8 @@ __global__ void __launch_bounds__(kNT, CVS_MIN_CTAS) k_fields(const __grid_const
     if (general) s_hi = s_lo;
     const bool vec_src = a.vec_src != 0, vec_dst = a.vec_dst != 0;
     const bool warp_hs = __any_sync(0xffffffffu, hsrow != nullptr);
-    const bool warp_inl = __any_sync(0xffffffffu, rc.hs_delay > 0);
-    R *hsring = reinterpret_cast<R *>(wins + kWarpsPerCta * 64) + tid;
+    const bool warp_inl = VHS && __any_sync(0xffffffffu, rc.hs_delay > 0);   // (the host only plans it for VHS kernels)
+    R *hsring = reinterpret_cast<R *>(smem_raw + SL::off_hsring) + tid;   // VHS only (head switching needs -vhs)
 
     uint32_t px[kT];
     load_block_dev(srow, 0, w, vec_src, px);
@@ -294,7 +303,7 @@ cudaError_t launch_headswitch(const LaunchArgs<R> &a, const HsItem *items, int n
 #define CVS_DEFINE_LAUNCH_FIELDS(R, VHS, CD, OUTFULL)                                                          \
     template <>                                                                                                \
     cudaError_t launch_fields<R, VHS, CD, OUTFULL>(const LaunchArgs<R> &a, cudaStream_t st) {                  \
-        const size_t smem = fields_smem_bytes<R>();                                                            \
+        const size_t smem = SmemLayout<R, VHS>::total;                                                         \
         cudaError_t e = cudaFuncSetAttribute(k_fields<R, VHS, CD, OUTFULL>,                                    \
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
         if (e != cudaSuccess) return e;                                                                        \

@@ -110,14 +110,15 @@ int run_field(const cvs_params &p, RandCursor &cur, uint8_t *dst, int dst_stride
             }
         }
         bool warp_inl = false;
-        for (int l = 0; l < 32; l++) warp_inl |= rc[l].hs_delay > 0;
+        for (int l = 0; l < 32; l++) warp_inl |= VHS && rc[l].hs_delay > 0;
         for (int s = 0; s < nsteps; s++) {
             // the kernel's choice of code variant for this step (force_general: 1 = general everywhere,
             // 2 = edge variant everywhere, to exercise those variants on interior blocks as well)
             int mode = (K.flags & F_GENERAL) ? MODE_GENERAL : ((s >= s_lo && s < s_hi) ? MODE_FAST : MODE_EDGE);
             if (force_general == 2 && mode == MODE_FAST) mode = MODE_EDGE;
             BlendXchg<R> xo[32];
-            R Yb[32][kT], Ib[32][kT], Qb[32][kT];
+            R Yb[32][kT];
+            V2<R> IQb[32][kT];
             for (int l = 0; l < 32; l++) {
                 uint32_t px[kT], pxprev[kT];
                 load_block_scalar(srow[l], s, w, px);
@@ -129,30 +130,31 @@ int run_field(const cvs_params &p, RandCursor &cur, uint8_t *dst, int dst_stride
                     P::template stage_a<MODE_FAST>(K, rc[l], lane[l], s, px, pxprev, hsrow[l], C);
                     headswitch_substitute<R>(rc[l], hsrow[l], s - 1, C);
                     if (warp_inl) headswitch_delay_block<R>(ring, 1, s - 1, w, rc[l].hs_delay, C);
-                    P::template stage_b<MODE_FAST>(K, rc[l], lane[l], s, C, Yb[l], Ib[l], Qb[l], xo[l]);
+                    P::template stage_b<MODE_FAST>(K, rc[l], lane[l], s, C, Yb[l], IQb[l], xo[l]);
                 } else if (mode == MODE_EDGE) {
                     P::template stage_a<MODE_EDGE>(K, rc[l], lane[l], s, px, pxprev, hsrow[l], C);
                     if (warp_inl && s >= 1) headswitch_delay_block<R>(ring, 1, s - 1, w, rc[l].hs_delay, C);
-                    P::template stage_b<MODE_EDGE>(K, rc[l], lane[l], s, C, Yb[l], Ib[l], Qb[l], xo[l]);
+                    P::template stage_b<MODE_EDGE>(K, rc[l], lane[l], s, C, Yb[l], IQb[l], xo[l]);
                 } else {
                     P::template stage_a<MODE_GENERAL>(K, rc[l], lane[l], s, px, pxprev, hsrow[l], C);
                     if (warp_inl && s >= 1) headswitch_delay_block<R>(ring, 1, s - 1, w, rc[l].hs_delay, C);
-                    P::template stage_b<MODE_GENERAL>(K, rc[l], lane[l], s, C, Yb[l], Ib[l], Qb[l], xo[l]);
+                    P::template stage_b<MODE_GENERAL>(K, rc[l], lane[l], s, C, Yb[l], IQb[l], xo[l]);
                 }
             }
             for (int l = 0; l < 32; l++) {
-                R Yf[kT], If[kT], Qf[kT];
+                R Yf[kT];
+                V2<R> IQf[kT];
                 int kf;
                 uint32_t out[kT];
                 bool have;
                 const BlendXchg<R> &above = xo[l > 0 ? l - 1 : 0];
 #define CVS_TAIL(M)                                                                                          \
     if (VHS) {                                                                                               \
-        P::template stage_c<M>(K, rc[l], lane[l], s, Yb[l], xo[l], above, Yf, If, Qf, kf);                   \
-        have = P::template stage_f<M>(K, rc[l], lane[l], kf, Yf, If, Qf, out);                               \
+        P::template stage_c<M>(K, rc[l], lane[l], s, Yb[l], xo[l], above, Yf, IQf, kf);                      \
+        have = P::template stage_f<M>(K, rc[l], lane[l], kf, Yf, IQf, out);                                  \
     } else {                                                                                                 \
         kf = s - 2;                                                                                          \
-        have = P::template stage_f<M>(K, rc[l], lane[l], kf, Yb[l], Ib[l], Qb[l], out);                      \
+        have = P::template stage_f<M>(K, rc[l], lane[l], kf, Yb[l], IQb[l], out);                            \
     }
                 if (mode == MODE_FAST) { CVS_TAIL(MODE_FAST) }
                 else if (mode == MODE_EDGE) { CVS_TAIL(MODE_EDGE) }
