@@ -114,6 +114,20 @@ __device__ __forceinline__ void load_block_dev(const uint32_t *srow, int k, int 
     }
 }
 
+// interior blocks: the whole block is inside the line
+__device__ __forceinline__ void load_block_fast(const uint32_t *srow, int k, bool vec, uint32_t px[kT]) {
+    const int x0 = k * kT;
+    if (vec) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(srow + x0);
+        const uint4 a = ld_row16(p), b = ld_row16(p + 1);
+        px[0] = a.x; px[1] = a.y; px[2] = a.z; px[3] = a.w;
+        px[4] = b.x; px[5] = b.y; px[6] = b.z; px[7] = b.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < kT; j++) px[j] = __ldg(srow + x0 + j);
+    }
+}
+
 template <typename R, bool VHS, int CD, bool OUTFULL>
 struct Stepper {
     typedef Lane<R, VHS, CD, OUTFULL> L;
@@ -244,20 +258,38 @@ __global__ void __launch_bounds__(kNT, CVS_MIN_CTAS) k_fields(const __grid_const
     const bool warp_inl = VHS && __any_sync(0xffffffffu, rc.hs_delay > 0);   // (the host only plans it for VHS kernels)
     R *hsring = reinterpret_cast<R *>(smem_raw + SL::off_hsring) + tid;   // VHS only (head switching needs -vhs)
 
+    // Step loop.  The interior (fast) steps get a loop of their own: if the three code variants shared
+    // one loop the compiler would have to bring ~85 carried registers back to a common allocation at
+    // every iteration (the r1e ncu capture showed exactly those moves at the loop head, 10 per pixel).
+    // The edge/general loop runs twice, for the steps before and after the interior.
+    typedef Stepper<R, VHS, CD, OUTFULL> St;
     uint32_t px[kT];
     load_block_dev(srow, 0, w, vec_src, px);
+    int s = 0;
 #pragma unroll 1
-    for (int s = 0; s < nsteps; s++) {
-        uint32_t pxn[kT];
-        load_block_dev(srow, s + 1, w, vec_src, pxn);            // prefetch the next block
-        if (s >= s_lo && s < s_hi)
-            Stepper<R, VHS, CD, OUTFULL>::template step<MODE_FAST>(K, rc, ln, s, px, srow, vec_src, hsrow, warp_hs, hsring, warp_inl, valid, drow, vec_dst);
-        else if (!general)
-            Stepper<R, VHS, CD, OUTFULL>::template step<MODE_EDGE>(K, rc, ln, s, px, srow, vec_src, hsrow, warp_hs, hsring, warp_inl, valid, drow, vec_dst);
-        else
-            Stepper<R, VHS, CD, OUTFULL>::template step<MODE_GENERAL>(K, rc, ln, s, px, srow, vec_src, hsrow, warp_hs, hsring, warp_inl, valid, drow, vec_dst);
+    for (int pass = 0; pass < 2; pass++) {
+        const int s_end = (pass == 0) ? s_lo : nsteps;
+#pragma unroll 1
+        for (; s < s_end; s++) {
+            uint32_t pxn[kT];
+            load_block_dev(srow, s + 1, w, vec_src, pxn);            // prefetch the next block
+            if (!general)
+                St::template step<MODE_EDGE>(K, rc, ln, s, px, srow, vec_src, hsrow, warp_hs, hsring, warp_inl, valid, drow, vec_dst);
+            else
+                St::template step<MODE_GENERAL>(K, rc, ln, s, px, srow, vec_src, hsrow, warp_hs, hsring, warp_inl, valid, drow, vec_dst);
 #pragma unroll
-        for (int j = 0; j < kT; j++) px[j] = pxn[j];
+            for (int j = 0; j < kT; j++) px[j] = pxn[j];
+        }
+        if (pass == 0) {
+#pragma unroll 1
+            for (; s < s_hi; s++) {
+                uint32_t pxn[kT];
+                load_block_fast(srow, s + 1, vec_src, pxn);          // interior: always in range
+                St::template step<MODE_FAST>(K, rc, ln, s, px, srow, vec_src, hsrow, warp_hs, hsring, warp_inl, valid, drow, vec_dst);
+#pragma unroll
+                for (int j = 0; j < kT; j++) px[j] = pxn[j];
+            }
+        }
     }
 }
 
