@@ -96,6 +96,10 @@ class Engine:
     def set_precision(self, use_double):
         _check(self.lib.cvs_set_precision(self._ctx, 1 if use_double else 0), "cvs_set_precision")
 
+    def set_bob(self, enable):
+        """Fuse the reference's line doubling (ffmpeg_ntsc.cpp:2232-2257) into the field call."""
+        _check(self.lib.cvs_set_bob(self._ctx, 1 if enable else 0), "cvs_set_bob")
+
     def rng_seek(self, draws_consumed):
         _check(self.lib.cvs_rng_seek(self._ctx, draws_consumed), "cvs_rng_seek")
 

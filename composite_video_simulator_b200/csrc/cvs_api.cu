@@ -56,6 +56,7 @@ struct cvs_ctx {
     int max_w = 0, max_h = 0, max_batch = 0, nl_max = 0, hs_max = 0;
     int precision = 0;                         // 0 = float (production), 1 = double (reference arithmetic)
     int host_chunk = kHostChunkDefault;
+    int bob = 0;                               // fused line doubling (cvs_set_bob)
     cudaStream_t stream = nullptr;
     bool own_stream = true;
     cudaStream_t s_in = nullptr, s_out = nullptr;      // upload / download streams of the host-pointer path
@@ -196,6 +197,7 @@ int launch_batch(cvs_ctx *c, const Variant &v, int w, int h, int nfields, int ma
     a.opposite = opposite;
     a.vec_src = vec_src;
     a.vec_dst = vec_dst;
+    a.bob = c->bob;
     a.status = c->d_status;
     if (nitems > 0) {
         CVS_CUDA(launch_headswitch<R>(a, c->d_items, nitems, c->stream));
@@ -365,9 +367,18 @@ int run_host(cvs_ctx *c, uint8_t *dst, size_t dst_pic_stride, int dst_stride, co
             const int field = field_of(k);
             if (field >= h) continue;
             const int nl = (h - field + 1) / 2;
-            CVS_CUDA(cudaMemcpy2DAsync(dst + (size_t)k * dst_pic_stride + (size_t)field * dst_stride, (size_t)2 * dst_stride,
-                                       c->d_dst + (size_t)k * dpic + (size_t)field * dstride, (size_t)2 * dstride,
-                                       (size_t)4 * w, (size_t)nl, cudaMemcpyDeviceToHost, c->s_out));
+            if (!c->bob) {
+                CVS_CUDA(cudaMemcpy2DAsync(dst + (size_t)k * dst_pic_stride + (size_t)field * dst_stride, (size_t)2 * dst_stride,
+                                           c->d_dst + (size_t)k * dpic + (size_t)field * dstride, (size_t)2 * dstride,
+                                           (size_t)4 * w, (size_t)nl, cudaMemcpyDeviceToHost, c->s_out));
+            } else {
+                // line-doubled picture: rows 0 .. field + 2(nl-1) are all written (for field 0 and even h the
+                // last row is not, and keeps what the host buffer held: ffmpeg_ntsc.cpp:2247)
+                const int rows = field + 2 * (nl - 1) + 1;
+                CVS_CUDA(cudaMemcpy2DAsync(dst + (size_t)k * dst_pic_stride, (size_t)dst_stride,
+                                           c->d_dst + (size_t)k * dpic, (size_t)dstride,
+                                           (size_t)4 * w, (size_t)rows, cudaMemcpyDeviceToHost, c->s_out));
+            }
         }
     }
     CVS_CUDA(cudaStreamSynchronize(c->s_out));
@@ -440,6 +451,14 @@ int cvs_set_params(cvs_ctx *ctx, const cvs_params *p) {
     for (auto &pl : ctx->plans) if (pl && pl->d_seek) cudaFree(pl->d_seek);
     ctx->plans.clear();                      // draw layout depends on the enabled stages
     ctx->lut_dirty = true;
+    return CVS_OK;
+}
+
+int cvs_set_bob(cvs_ctx *ctx, int enable) {
+    if (!ctx) return CVS_ERR_INVALID_ARG;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return CVS_ERR_CUDA;
+    CVS_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->bob = enable ? 1 : 0;
     return CVS_OK;
 }
 

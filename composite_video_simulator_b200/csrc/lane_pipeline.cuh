@@ -966,14 +966,23 @@ CVS_HD void headswitch_delay_block(R *ring, int stride, int k, int w, int d, R C
 template <bool VHS>
 CVS_HD int line_steps(int w) { return (w + kT - 1) / kT + (VHS ? 6 : 3); }
 
-// [s_lo, s_hi): steps in which every touched block is interior, so the fast (non-EDGE) variant
-// is valid: the oldest block B(s-LAG) must have index >= 1 and the newest reads must stay
-// 16 pixels clear of the line end.
+// [s_lo, s_hi): steps whose every stage works on an interior block, so the fast variant is valid.
+// Line start: the first demodulated block of each demod (k = 0) has the carrier-period condition
+// g >= 0, so demod 1 (block s-2) needs s >= 3 and, with VHS, demod 2 (block s-5) needs s >= 6.
+// Line end, for step s:  A1 reads B(s) whole: 8s+8 <= w;  A2 builds B(s-1) and must stay clear of
+// the raw-chroma tail (x+4 >= w): 8s+3 < w;  the VHS chroma stash starts at x >= w-CD for x in
+// B(s-2): 8s-9 < w-CD.  Everything downstream is older and weaker.
 template <bool VHS>
-CVS_HD void interior_steps(int w, int &s_lo, int &s_hi) {
-    s_lo = (VHS ? 6 : 3) + 1;
-    s_hi = (w - 24) / kT;        // 8*s + 8 + 16 <= w
-    if (s_hi < s_lo) s_hi = s_lo;
+CVS_HD void interior_steps(int w, int cd, int &s_lo, int &s_hi) {
+    s_lo = VHS ? 6 : 3;
+    int hi = (w - kT) / kT + 1;                          // 8s + 8 <= w
+    const int a2 = (w - 3 + kT - 1) / kT;                // 8s < w - 3
+    if (a2 < hi) hi = a2;
+    if (VHS) {
+        const int st = (w - cd + 9 + kT - 1) / kT;       // 8s < w - cd + 9
+        if (st < hi) hi = st;
+    }
+    s_hi = hi < s_lo ? s_lo : hi;
 }
 
 // ---- row / lane set-up ------------------------------------------------------------------------------
@@ -1100,3 +1109,4 @@ CVS_HD void headswitch_row(const KConst<R> &K, const RowConst<R> &rc_in, Lane<R,
 
 }  // namespace cvs
 #endif
+

@@ -56,6 +56,7 @@ struct LaunchArgs {
     int32_t nfields, warps_per_field, total_warps;
     int32_t src_stride, dst_stride, opposite;
     int32_t vec_src, vec_dst;            // rows are 16-byte aligned: use 128-bit loads / stores
+    int32_t bob;                         // also write every processed row y >= 1 into row y-1 (ffmpeg_ntsc.cpp:2232-2257)
     int32_t *status;                     // sticky error word (CVS_ERR_NOISE_SYNC)
 };
 
@@ -137,7 +138,7 @@ struct Stepper {
     static __device__ __forceinline__ void step(const KConst<R> &K, const RowConst<R> &rc, L &ln, int s,
                                                 const uint32_t px[kT], const uint32_t *srow, bool vec_src,
                                                 const int32_t *hsrow, bool warp_hs,
-                                                R *hsring, bool warp_inl, bool valid, uint32_t *drow, bool vec_dst) {
+                                                R *hsring, bool warp_inl, bool valid, uint32_t *drow, uint32_t *drow_bob, bool vec_dst) {
         constexpr bool EDGE = MODE >= 1;
         R C[kT], Yb[kT];
         V2<R> IQb[kT];
@@ -180,10 +181,18 @@ struct Stepper {
                 uint4 *d = reinterpret_cast<uint4 *>(drow + x0);
                 d[0] = make_uint4(out[0], out[1], out[2], out[3]);
                 d[1] = make_uint4(out[4], out[5], out[6], out[7]);
+                if (drow_bob) {                            // line doubling: the same pixels one row up
+                    uint4 *d2 = reinterpret_cast<uint4 *>(drow_bob + x0);
+                    d2[0] = make_uint4(out[0], out[1], out[2], out[3]);
+                    d2[1] = make_uint4(out[4], out[5], out[6], out[7]);
+                }
             } else {
 #pragma unroll
                 for (int j = 0; j < kT; j++)
-                    if (x0 + j < K.w) drow[x0 + j] = out[j];
+                    if (x0 + j < K.w) {
+                        drow[x0 + j] = out[j];
+                        if (drow_bob) drow_bob[x0 + j] = out[j];
+                    }
             }
         }
     }
@@ -224,6 +233,10 @@ __global__ void __launch_bounds__(kNT, CVS_MIN_CTAS) k_fields(const __grid_const
     sy = sy > h - 1 ? h - 1 : sy;
     const uint32_t *srow = row_ptr(fd.src, a.src_stride, sy);
     uint32_t *drow = const_cast<uint32_t *>(row_ptr(fd.dst, a.dst_stride, fd.field + 2 * row));
+    // bob (ffmpeg_ntsc.cpp:2232-2257): field 1 copies row y onto y-1, field 0 copies row y+1 onto y for
+    // y = 1,3,.. < h-1: either way every processed row except row 0 is duplicated one row up
+    uint32_t *drow_bob = (a.bob && (fd.field + 2 * row) >= 1)
+                             ? const_cast<uint32_t *>(row_ptr(fd.dst, a.dst_stride, fd.field + 2 * row - 1)) : nullptr;
     const int32_t *hsrow = (rc.rflags & RF_HEADSW) ? fd.hs_scratch + (size_t)(row - fd.hs_first) * (size_t)w : nullptr;
     ln.tailU = tails + tid;
     ln.tailV = tails + (size_t)kTailSlots * kNT + tid;
@@ -250,7 +263,7 @@ __global__ void __launch_bounds__(kNT, CVS_MIN_CTAS) k_fields(const __grid_const
 
     const int nsteps = line_steps<VHS>(w);
     int s_lo, s_hi;
-    interior_steps<VHS>(w, s_lo, s_hi);
+    interior_steps<VHS>(w, CD, s_lo, s_hi);
     const bool general = (K.flags & F_GENERAL) != 0;
     if (general) s_hi = s_lo;
     const bool vec_src = a.vec_src != 0, vec_dst = a.vec_dst != 0;
@@ -274,9 +287,9 @@ __global__ void __launch_bounds__(kNT, CVS_MIN_CTAS) k_fields(const __grid_const
             uint32_t pxn[kT];
             load_block_dev(srow, s + 1, w, vec_src, pxn);            // prefetch the next block
             if (!general)
-                St::template step<MODE_EDGE>(K, rc, ln, s, px, srow, vec_src, hsrow, warp_hs, hsring, warp_inl, valid, drow, vec_dst);
+                St::template step<MODE_EDGE>(K, rc, ln, s, px, srow, vec_src, hsrow, warp_hs, hsring, warp_inl, valid, drow, drow_bob, vec_dst);
             else
-                St::template step<MODE_GENERAL>(K, rc, ln, s, px, srow, vec_src, hsrow, warp_hs, hsring, warp_inl, valid, drow, vec_dst);
+                St::template step<MODE_GENERAL>(K, rc, ln, s, px, srow, vec_src, hsrow, warp_hs, hsring, warp_inl, valid, drow, drow_bob, vec_dst);
 #pragma unroll
             for (int j = 0; j < kT; j++) px[j] = pxn[j];
         }
@@ -285,7 +298,7 @@ __global__ void __launch_bounds__(kNT, CVS_MIN_CTAS) k_fields(const __grid_const
             for (; s < s_hi; s++) {
                 uint32_t pxn[kT];
                 load_block_fast(srow, s + 1, vec_src, pxn);          // interior: always in range
-                St::template step<MODE_FAST>(K, rc, ln, s, px, srow, vec_src, hsrow, warp_hs, hsring, warp_inl, valid, drow, vec_dst);
+                St::template step<MODE_FAST>(K, rc, ln, s, px, srow, vec_src, hsrow, warp_hs, hsring, warp_inl, valid, drow, drow_bob, vec_dst);
 #pragma unroll
                 for (int j = 0; j < kT; j++) px[j] = pxn[j];
             }

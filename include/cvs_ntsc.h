@@ -128,6 +128,13 @@ int  cvs_set_params(cvs_ctx *ctx, const cvs_params *p);
  * reference's double code (bit-exact with the reference; a validation mode, about 3x slower).
  */
 int  cvs_set_precision(cvs_ctx *ctx, int use_double);
+/*
+ * Fuse the step that follows composite_layer() in the reference's field loop, the "field
+ * deinterlace" line doubling (ffmpeg_ntsc.cpp:2232-2257): when enabled, every processed row y >= 1
+ * is also written to row y-1 of the same picture (field 1: rows y-1 <- y for odd y; field 0: rows
+ * y <- y+1 for y = 1,3,.. with y+1 < h, so for even h the last row is left as it was).  Off by default.
+ */
+int  cvs_set_bob(cvs_ctx *ctx, int enable);
 
 /* ---- the seam: exact analogue of the call at ffmpeg_ntsc.cpp:2229 ------------------------- */
 

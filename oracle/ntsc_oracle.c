@@ -65,6 +65,19 @@ unsigned long long oracle_fnv1a64(const void *buf, unsigned long long n) {
     return h;
 }
 
+/* "field deinterlace" of the reference's main loop (ffmpeg_ntsc.cpp:2232-2257): line-double the field
+ * that composite_layer() just wrote, in place. */
+void oracle_bob(uint8_t *pic, int stride, int w, int h, unsigned field) {
+    int y;
+    if (field) {
+        for (y = (int)field; y < h; y += 2)                           /* :2237-2245 */
+            memcpy(pic + (size_t)stride * (size_t)(y - 1), pic + (size_t)stride * (size_t)y, (size_t)w * 4);
+    } else {
+        for (y = 1; y + 1 < h; y += 2)                                /* :2247-2255 */
+            memcpy(pic + (size_t)stride * (size_t)y, pic + (size_t)stride * (size_t)(y + 1), (size_t)w * 4);
+    }
+}
+
 static oracle_tap_fn g_tap = 0;
 static void *g_tap_user = 0;
 void oracle_set_tap(oracle_tap_fn fn, void *user) { g_tap = fn; g_tap_user = user; }

@@ -47,6 +47,9 @@ int oracle_composite_layer(const cvs_params *p, oracle_rng *g,
                            int w, int h, int src_interlaced, int src_tff,
                            unsigned field, unsigned long long fieldno);
 
+/* Restatement of the line doubling that follows composite_layer() (ffmpeg_ntsc.cpp:2232-2257). */
+void oracle_bob(uint8_t *pic, int stride, int w, int h, unsigned field);
+
 /* Optional stage taps for debugging: if non-NULL, receives the int planes (nl*w each, field
    rows packed) after the named stage.  stage ids: 1 = composite signal after luma noise
    (pre head-switch), 2 = after first demod+chroma noise+phase noise, 3 = after the VHS block,

@@ -67,7 +67,7 @@ int run_field(const cvs_params &p, RandCursor &cur, uint8_t *dst, int dst_stride
     const int nwarps = (nl + 30) / 31;
     const int nsteps = line_steps<VHS>(w);
     int s_lo, s_hi;
-    interior_steps<VHS>(w, s_lo, s_hi);
+    interior_steps<VHS>(w, CD, s_lo, s_hi);
     std::vector<uint32_t> rings((size_t)32 * 2 * kRngSlots);
     std::vector<R> tails((size_t)32 * 2 * kTailSlots);
     std::vector<R> hsring((size_t)32 * kHsRing);

@@ -188,3 +188,35 @@ def test_gpu_fp32_is_bit_identical_to_cpu_emulation(emu, w, h, n, argv):
         for k in range(n):
             eng.composite_layer(got, frames(k), (k & 1) ^ 1, k)
     assert np.array_equal(want, got)
+
+
+@pytest.mark.parametrize("w,h", [(160, 120), (164, 121)])
+def test_fused_bob_matches_reference_loop(oracle, w, h):
+    """composite_layer + the line doubling of the main loop (ffmpeg_ntsc.cpp:2229-2257) over a reused
+    picture, against the engine with the doubling fused into the store (host and device forms)."""
+    import ctypes as C
+    import torch
+    n = 4
+    p = helpers.params("-vhs")
+    frames = [helpers.stream_frame(w, h, k) for k in range(n)]
+    g = helpers.OracleRng()
+    oracle.oracle_rng_seed(C.byref(g), 1)
+    want = np.full((h, w), 0x00123456, dtype=np.uint32)
+    got = want.copy()
+    dev = torch.from_numpy(want.view(np.int32).copy()).cuda()
+    with cvs.Engine(params=p, max_w=w, max_h=h, max_batch=1) as eng, cvs.Engine(params=p, max_w=w, max_h=h, max_batch=1) as eng2:
+        eng.set_precision(True)
+        eng2.set_precision(True)
+        eng.set_bob(True)
+        eng2.set_bob(True)
+        for k in range(n):
+            f = (k & 1) ^ 1
+            oracle.oracle_composite_layer(C.byref(p), C.byref(g), want.ctypes.data_as(C.c_void_p), 4 * w,
+                                          frames[k].ctypes.data_as(C.c_void_p), 4 * w, w, h, 0, 0, f, C.c_ulonglong(k))
+            oracle.oracle_bob(want.ctypes.data_as(C.c_void_p), 4 * w, w, h, f)
+            eng.composite_layer(got, frames[k], f, k)
+            assert np.array_equal(want, got), k
+            src = torch.from_numpy(frames[k].view(np.int32)).cuda()
+            eng2.composite_fields_device(dev, src, 1, h, w, k)
+            eng2.synchronize()
+            assert np.array_equal(want, dev.cpu().numpy().view(np.uint32)), k
