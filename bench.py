@@ -335,6 +335,8 @@ def run_own_arm(args):
     achieved = alg_bytes / (kernel_ms / 1e3) / 1e9
     traffic = None
     try:
+        if args.preset != "sp" or (W, H) != (1920, 1080):
+            raise KeyError("the ncu traffic capture is of the headline workload only")
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             tj = json.load(f)        # measured by one `ncu --set full` capture, scaled to this launch size
             traffic = tj["k_fields_sp_dram_bytes_per_launch_64_fields"] / tj["fields_per_launch_in_capture"] * B
@@ -352,8 +354,9 @@ def run_own_arm(args):
         "metric": METRIC, "value": value, "unit": "fields/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "1920x1080 VHS-SP (-vhs -vhs-speed sp), %d fields per GPU per step, synthetic "
-                               "perturbed colour bars generated on device" % B,
+        "config": {"workload": "%dx%d %s (%s), %d fields per GPU per step, synthetic perturbed colour bars "
+                               "generated on device" % (W, H, "VHS-" + args.preset.upper() if args.preset != "comp" else "composite only",
+                                                        " ".join(ARGV) or "no switches", B),
                    "fields_per_step_per_gpu": B, "full_frames_per_s": value / 2,
                    "l2": "inputs larger than L2 (%.0f MB read + %.0f MB written per step)" % (alg_bytes / 2e6, alg_bytes / 2e6),
                    "noise": "exact glibc rand() replay", "parallelism": "fields sharded by contiguous chunk, no data-path collective"},
@@ -361,7 +364,7 @@ def run_own_arm(args):
         "e2e": {"value": e2e_value, "unit": "fields/s", "h2d_bytes_per_step": Be * nl * 4 * W,
                 "d2h_bytes_per_step": Be * nl * 4 * W, "fields_per_step_per_gpu": Be, "result_checksum": e2e_checksum},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": "k_fields<float,VHS,9,tv>", "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "hbm", "kernel": "k_fields<float, %s, tv>" % {"sp": "VHS, 9", "lp": "VHS, 12", "ep": "VHS, 14", "comp": "composite"}[args.preset], "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms_per_launch": kernel_ms},
         "cpu_baseline": cpu,
@@ -382,10 +385,13 @@ def main():
     ap.add_argument("--e2e-batch", type=int, default=256, help="fields per GPU per step (host buffers)")
     ap.add_argument("--cpu-fields", type=int, default=64, help="fields of the single-thread CPU baseline sample")
     ap.add_argument("--ref-fields-per-proc", type=int, default=4)
+    ap.add_argument("--width", type=int, default=1920, help="experiments only: the headline metric is 1920x1080")
+    ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--preset", default="sp", choices=["sp", "ep", "lp", "comp"],
                     help="sp = the headline VHS-SP workload; the others are for kernel experiments")
     args = ap.parse_args()
-    global ARGV
+    global ARGV, W, H
+    W, H = args.width, args.height
     ARGV = {"sp": ["-vhs", "-vhs-speed", "sp"], "ep": ["-vhs", "-vhs-speed", "ep"], "lp": ["-vhs", "-vhs-speed", "lp"],
             "comp": []}[args.preset]
     if args.warmup < 3 and args.impl == "own":

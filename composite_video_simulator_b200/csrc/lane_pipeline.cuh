@@ -476,6 +476,7 @@ struct RowConst {
     uint32_t rflags;
     int row;             // field row index (y = field + 2*row)
     int hs_delay;        // RF_HEADSW_INLINE: C'[x] = C[x - hs_delay], 0 for x < hs_delay
+    bool odd_any;        // warp-uniform: some row of this warp has an odd phase index (set by the caller; default true)
 };
 
 template <typename R>
@@ -597,16 +598,31 @@ CVS_HD void demod_block(const RowConst<R> &rc, int k, int w, int amp, R cm1, con
     // even pixels: I = -chroma[x+xi], Q = -chroma[x+xi+1]  (:1549-1552); 5 even positions: 4 in
     // the block plus the first of the next block (needed by the odd-pixel interpolation)
     const bool x1 = (rc.xi & 1) != 0, x2 = (rc.xi & 2) != 0;
+    // With the default 180-degree line phase every row has xi in {0, 2}: the first level of the 4-way
+    // selection is then the identity for the whole warp and is skipped under a warp-uniform branch.
+    R s01[10], s23[10];              // [2e] = I candidate, [2e+1] = Q candidate
+    if (MODE == 0 && !rc.odd_any) {     // MODE_FAST
+        CVS_UNROLL
+        for (int e = 0; e < 5; e++) {
+            s01[2 * e] = ch[2 * e]; s23[2 * e] = ch[2 * e + 2];
+            s01[2 * e + 1] = ch[2 * e + 1]; s23[2 * e + 1] = ch[2 * e + 3];
+        }
+    } else {
+        CVS_UNROLL
+        for (int e = 0; e < 5; e++) {
+            const int j = 2 * e;
+            s01[2 * e] = x1 ? ch[j + 1] : ch[j];
+            s23[2 * e] = x1 ? ch[j + 3] : ch[j + 2];
+            s01[2 * e + 1] = x1 ? ch[j + 2] : ch[j + 1];
+            s23[2 * e + 1] = x1 ? ch[j + 4] : ch[j + 3];
+        }
+    }
     V2<R> IQe[5];
     CVS_UNROLL
     for (int e = 0; e < 5; e++) {
         const int j = 2 * e;
-        const R i01 = x1 ? ch[j + 1] : ch[j];
-        const R i23 = x1 ? ch[j + 3] : ch[j + 2];
-        const R q01 = x1 ? ch[j + 2] : ch[j + 1];
-        const R q23 = x1 ? ch[j + 4] : ch[j + 3];
-        R iv = x2 ? i23 : i01;
-        R qv = x2 ? q23 : q01;
+        R iv = x2 ? s23[2 * e] : s01[2 * e];
+        R qv = x2 ? s23[2 * e + 1] : s01[2 * e + 1];
         if (EDGE) {
             const int x = x0 + j;
             const bool ok = (x + rc.xi + 1) < w;        // :1549, else zero (:1553-1556)
@@ -1008,6 +1024,7 @@ CVS_HD void row_setup(const KConst<R> &K, unsigned field, unsigned long long fie
     rc.row = row;
     rc.rflags = (rowinfo >> 16) & 0xFFu;
     rc.hs_delay = (rc.rflags & RF_HEADSW_INLINE) ? (int)(rowinfo >> 24) : 0;
+    rc.odd_any = true;
     rowconst_set_phase<R>(rc, line_phase(K.phase_shift, K.phase_offset, fieldno, field + 2u * (unsigned)row));
     if (K.flags & F_PHASE) {
         const int st = (int)(int16_t)(rowinfo & 0xFFFFu);

@@ -267,6 +267,7 @@ __global__ void __launch_bounds__(kNT, CVS_MIN_CTAS) k_fields(const __grid_const
     const bool general = (K.flags & F_GENERAL) != 0;
     if (general) s_hi = s_lo;
     const bool vec_src = a.vec_src != 0, vec_dst = a.vec_dst != 0;
+    rc.odd_any = __any_sync(0xffffffffu, (rc.xi & 1) != 0);
     const bool warp_hs = __any_sync(0xffffffffu, hsrow != nullptr);
     const bool warp_inl = VHS && __any_sync(0xffffffffu, rc.hs_delay > 0);   // (the host only plans it for VHS kernels)
     R *hsring = reinterpret_cast<R *>(smem_raw + SL::off_hsring) + tid;   // VHS only (head switching needs -vhs)

@@ -111,6 +111,9 @@ int run_field(const cvs_params &p, RandCursor &cur, uint8_t *dst, int dst_stride
         }
         bool warp_inl = false;
         for (int l = 0; l < 32; l++) warp_inl |= VHS && rc[l].hs_delay > 0;
+        bool odd_any = false;
+        for (int l = 0; l < 32; l++) odd_any |= (rc[l].xi & 1) != 0;
+        for (int l = 0; l < 32; l++) rc[l].odd_any = odd_any;
         for (int s = 0; s < nsteps; s++) {
             // the kernel's choice of code variant for this step (force_general: 1 = general everywhere,
             // 2 = edge variant everywhere, to exercise those variants on interior blocks as well)

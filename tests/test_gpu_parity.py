@@ -21,6 +21,9 @@ CASES = [
     (720, 480, 2, ["-vhs", "-vhs-svideo", "1", "-comp-phase", "90"]),
     (720, 480, 2, ["-vhs", "-vhs-head-switching-phase", "0.001", "-vhs-head-switching-point", "0.5"]),
     (1920, 1080, 2, ["-vhs", "-vhs-speed", "sp"]),
+    (1920, 1080, 2, ["-vhs", "-vhs-speed", "ep"]),          # BASELINE config 3
+    (3840, 2160, 2, []),                                    # BASELINE config 4: composite only, 4K
+    (3840, 2160, 1, ["-vhs", "-vhs-speed", "lp"]),          # head-switch shift beyond the in-kernel ring: pre-pass
 ]
 
 
