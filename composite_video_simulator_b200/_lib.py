@@ -43,6 +43,8 @@ def load():
                                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_ulonglong]),
         "cvs_composite_fields_host": (C.c_int, [vp, vp, C.c_size_t, C.c_int, vp, C.c_size_t, C.c_int, C.c_int,
                                                 C.c_int, C.c_int, C.c_int, C.c_int, C.c_ulonglong]),
+        "cvs_composite_fields_host_async": (C.c_int, [vp, vp, C.c_size_t, C.c_int, vp, C.c_size_t, C.c_int, C.c_int,
+                                                      C.c_int, C.c_int, C.c_int, C.c_int, C.c_ulonglong]),
         "cvs_synchronize": (C.c_int, [vp]),
         "cvs_rng_seek": (C.c_int, [vp, C.c_ulonglong]),
         "cvs_rng_tell": (C.c_int, [vp, C.POINTER(C.c_ulonglong)]),
@@ -63,6 +65,7 @@ EXPORTED_SYMBOLS = [
     "cvs_abi_version", "cvs_strerror", "cvs_params_default_ntsc", "cvs_params_preset_pal",
     "cvs_params_apply_argv", "cvs_draws_per_field", "cvs_create", "cvs_destroy", "cvs_set_params",
     "cvs_set_precision", "cvs_set_bob", "cvs_composite_layer", "cvs_composite_fields_device", "cvs_composite_fields_host",
+    "cvs_composite_fields_host_async",
     "cvs_synchronize", "cvs_rng_seek", "cvs_rng_tell", "cvs_kernel_launches", "cvs_kernel_time_reset",
     "cvs_kernel_time_query", "cvs_set_stream",
 ]

@@ -126,6 +126,15 @@ class Engine:
                                                   int(src_top_field_first), n, first_fieldno),
                "cvs_composite_fields_host")
 
+    def composite_fields_host_async(self, dst, src, first_fieldno, src_interlaced=False, src_top_field_first=False):
+        """As composite_fields_host but only queues the work; dst is complete after synchronize().
+        Consecutive calls overlap; do not reuse dst/src before the synchronize (use two buffer sets)."""
+        n, h, w = src.shape
+        _check(self.lib.cvs_composite_fields_host_async(self._ctx, _ptr(dst), dst.strides[0], dst.strides[1], _ptr(src),
+                                                        src.strides[0], src.strides[1], w, h, int(src_interlaced),
+                                                        int(src_top_field_first), n, first_fieldno),
+               "cvs_composite_fields_host_async")
+
     def composite_fields_device(self, dst, src, n, h, w, first_fieldno, dst_pic_stride=None, dst_stride=None,
                                 src_pic_stride=None, src_stride=None, src_interlaced=False,
                                 src_top_field_first=False):

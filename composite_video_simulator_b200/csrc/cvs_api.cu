@@ -81,8 +81,11 @@ struct cvs_ctx {
     size_t lut_cap = 0;
     bool lut_dirty = true;
     // device pictures for the host-pointer entry points
-    uint8_t *d_src = nullptr, *d_dst = nullptr;
-    size_t d_pic_cap = 0;
+    // two sets, alternating per call, so an asynchronous call can upload while the previous one drains
+    uint8_t *d_src[2] = {nullptr, nullptr}, *d_dst[2] = {nullptr, nullptr};
+    size_t d_pic_cap[2] = {0, 0};
+    cudaEvent_t host_call_done[2] = {nullptr, nullptr};   // recorded on s_out when a call's last download is queued
+    int host_call_parity = 0;
     unsigned long long launches = 0;
 };
 
@@ -118,7 +121,7 @@ void free_all(cvs_ctx *c) {
     }
     cudaFree(c->d_fields); cudaFree(c->d_rowinfo); cudaFree(c->d_hsshift); cudaFree(c->d_items);
     cudaFree(c->d_scratch); cudaFree(c->d_status); cudaFree(c->d_lut_f); cudaFree(c->d_lut_d);
-    cudaFree(c->d_src); cudaFree(c->d_dst);
+    for (int i = 0; i < 2; i++) { cudaFree(c->d_src[i]); cudaFree(c->d_dst[i]); if (c->host_call_done[i]) cudaEventDestroy(c->host_call_done[i]); }
     if (c->h_status) cudaFreeHost(c->h_status);
     for (auto &pr : c->ev_pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (auto e : c->ev_in) cudaEventDestroy(e);
@@ -305,7 +308,7 @@ int check_status(cvs_ctx *c) {
 // rows field + 2r out; every other dst row stays untouched on the host, as in the reference (:1910).
 int run_host(cvs_ctx *c, uint8_t *dst, size_t dst_pic_stride, int dst_stride, const uint8_t *src,
              size_t src_pic_stride, int src_stride, int w, int h, int interlaced, int tff, int n,
-             unsigned long long first_fieldno, int explicit_field) {
+             unsigned long long first_fieldno, int explicit_field, bool async) {
     if (!c || !dst || !src) return CVS_ERR_INVALID_ARG;
     if (w <= 0 || h <= 0 || n < 0) return CVS_ERR_INVALID_ARG;
     if (dst_stride < 4 * w || src_stride < 4 * w) return CVS_ERR_INVALID_ARG;
@@ -315,15 +318,23 @@ int run_host(cvs_ctx *c, uint8_t *dst, size_t dst_pic_stride, int dst_stride, co
     // device pictures: rows padded to 16 bytes, full height (only the field rows are transferred)
     const int dstride = ((4 * w + 15) / 16) * 16;
     const size_t dpic = (size_t)dstride * (size_t)h;
-    if (dpic * (size_t)n > c->d_pic_cap) {
+    const int set = c->host_call_parity;
+    c->host_call_parity ^= 1;
+    if (!c->host_call_done[set]) CVS_CUDA(cudaEventCreateWithFlags(&c->host_call_done[set], cudaEventDisableTiming));
+    if (dpic * (size_t)n > c->d_pic_cap[set]) {
+        CVS_CUDA(cudaStreamSynchronize(c->s_in));
         CVS_CUDA(cudaStreamSynchronize(c->stream));
-        cudaFree(c->d_src); cudaFree(c->d_dst);
-        c->d_src = c->d_dst = nullptr;
-        c->d_pic_cap = 0;
-        CVS_CUDA(cudaMalloc((void **)&c->d_src, dpic * (size_t)n));
-        CVS_CUDA(cudaMalloc((void **)&c->d_dst, dpic * (size_t)n));
-        c->d_pic_cap = dpic * (size_t)n;
+        CVS_CUDA(cudaStreamSynchronize(c->s_out));
+        cudaFree(c->d_src[set]); cudaFree(c->d_dst[set]);
+        c->d_src[set] = c->d_dst[set] = nullptr;
+        c->d_pic_cap[set] = 0;
+        CVS_CUDA(cudaMalloc((void **)&c->d_src[set], dpic * (size_t)n));
+        CVS_CUDA(cudaMalloc((void **)&c->d_dst[set], dpic * (size_t)n));
+        c->d_pic_cap[set] = dpic * (size_t)n;
     }
+    uint8_t *const d_src = c->d_src[set], *const d_dst = c->d_dst[set];
+    // this buffer set was last used two calls ago: its downloads must have drained before we overwrite it
+    CVS_CUDA(cudaStreamWaitEvent(c->s_in, c->host_call_done[set], 0));
     const int kHostChunk = c->host_chunk;
     const int nchunks = (n + kHostChunk - 1) / kHostChunk;
     while ((int)c->ev_in.size() < nchunks) {
@@ -348,7 +359,7 @@ int run_host(cvs_ctx *c, uint8_t *dst, size_t dst_pic_stride, int dst_stride, co
             int nreg = nl;                                    // stride-2 run, plus the clamped last row
             if (y0 + 2 * (nl - 1) > h - 1) nreg = nl - 1;
             const uint8_t *hs = src + (size_t)k * src_pic_stride;
-            uint8_t *ds = c->d_src + (size_t)k * dpic;
+            uint8_t *ds = d_src + (size_t)k * dpic;
             if (nreg > 0)
                 CVS_CUDA(cudaMemcpy2DAsync(ds + (size_t)y0 * dstride, (size_t)2 * dstride, hs + (size_t)y0 * src_stride,
                                            (size_t)2 * src_stride, (size_t)4 * w, (size_t)nreg, cudaMemcpyHostToDevice, c->s_in));
@@ -358,7 +369,7 @@ int run_host(cvs_ctx *c, uint8_t *dst, size_t dst_pic_stride, int dst_stride, co
         }
         CVS_CUDA(cudaEventRecord(c->ev_in[ci], c->s_in));
         CVS_CUDA(cudaStreamWaitEvent(c->stream, c->ev_in[ci], 0));
-        int rc = run_device(c, c->d_dst + (size_t)k0 * dpic, dpic, dstride, c->d_src + (size_t)k0 * dpic, dpic, dstride, w, h,
+        int rc = run_device(c, d_dst + (size_t)k0 * dpic, dpic, dstride, d_src + (size_t)k0 * dpic, dpic, dstride, w, h,
                             interlaced, tff, k1 - k0, first_fieldno + (unsigned long long)k0, explicit_field);
         if (rc != CVS_OK) { cudaStreamSynchronize(c->s_in); cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->s_out); return rc; }
         CVS_CUDA(cudaEventRecord(c->ev_k[ci], c->stream));
@@ -369,18 +380,20 @@ int run_host(cvs_ctx *c, uint8_t *dst, size_t dst_pic_stride, int dst_stride, co
             const int nl = (h - field + 1) / 2;
             if (!c->bob) {
                 CVS_CUDA(cudaMemcpy2DAsync(dst + (size_t)k * dst_pic_stride + (size_t)field * dst_stride, (size_t)2 * dst_stride,
-                                           c->d_dst + (size_t)k * dpic + (size_t)field * dstride, (size_t)2 * dstride,
+                                           d_dst + (size_t)k * dpic + (size_t)field * dstride, (size_t)2 * dstride,
                                            (size_t)4 * w, (size_t)nl, cudaMemcpyDeviceToHost, c->s_out));
             } else {
                 // line-doubled picture: rows 0 .. field + 2(nl-1) are all written (for field 0 and even h the
                 // last row is not, and keeps what the host buffer held: ffmpeg_ntsc.cpp:2247)
                 const int rows = field + 2 * (nl - 1) + 1;
                 CVS_CUDA(cudaMemcpy2DAsync(dst + (size_t)k * dst_pic_stride, (size_t)dst_stride,
-                                           c->d_dst + (size_t)k * dpic, (size_t)dstride,
+                                           d_dst + (size_t)k * dpic, (size_t)dstride,
                                            (size_t)4 * w, (size_t)rows, cudaMemcpyDeviceToHost, c->s_out));
             }
         }
     }
+    CVS_CUDA(cudaEventRecord(c->host_call_done[set], c->s_out));
+    if (async) return CVS_OK;
     CVS_CUDA(cudaStreamSynchronize(c->s_out));
     return check_status(c);
 }
@@ -479,7 +492,7 @@ int cvs_composite_layer(cvs_ctx *ctx, uint8_t *dst, int dst_stride, const uint8_
         return CVS_ERR_INVALID_ARG;
     }
     return run_host(ctx, dst, 0, dst_stride, src, 0, src_stride, w, h, src_interlaced, src_top_field_first, 1,
-                    fieldno, (int)field);
+                    fieldno, (int)field, false);
 }
 
 int cvs_composite_fields_device(cvs_ctx *ctx, void *dst, size_t dst_pic_stride, int dst_stride, const void *src,
@@ -493,13 +506,23 @@ int cvs_composite_fields_host(cvs_ctx *ctx, void *dst, size_t dst_pic_stride, in
                               size_t src_pic_stride, int src_stride, int w, int h, int src_interlaced,
                               int src_top_field_first, int n, unsigned long long first_fieldno) {
     return run_host(ctx, (uint8_t *)dst, dst_pic_stride, dst_stride, (const uint8_t *)src, src_pic_stride, src_stride,
-                    w, h, src_interlaced, src_top_field_first, n, first_fieldno, -1);
+                    w, h, src_interlaced, src_top_field_first, n, first_fieldno, -1, false);
+}
+
+int cvs_composite_fields_host_async(cvs_ctx *ctx, void *dst, size_t dst_pic_stride, int dst_stride, const void *src,
+                                    size_t src_pic_stride, int src_stride, int w, int h, int src_interlaced,
+                                    int src_top_field_first, int n, unsigned long long first_fieldno) {
+    return run_host(ctx, (uint8_t *)dst, dst_pic_stride, dst_stride, (const uint8_t *)src, src_pic_stride, src_stride,
+                    w, h, src_interlaced, src_top_field_first, n, first_fieldno, -1, true);
 }
 
 int cvs_synchronize(cvs_ctx *ctx) {
     if (!ctx) return CVS_ERR_INVALID_ARG;
     if (cudaSetDevice(ctx->device) != cudaSuccess) return CVS_ERR_CUDA;
-    return check_status(ctx);
+    CVS_CUDA(cudaStreamSynchronize(ctx->s_in));
+    const int rc = check_status(ctx);          // synchronises the compute stream
+    CVS_CUDA(cudaStreamSynchronize(ctx->s_out));
+    return rc;
 }
 
 int cvs_rng_seek(cvs_ctx *ctx, unsigned long long draws_consumed) {

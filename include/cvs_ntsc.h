@@ -175,6 +175,18 @@ int cvs_composite_fields_host(cvs_ctx *ctx,
                               const void *src, size_t src_pic_stride, int src_stride,
                               int w, int h, int src_interlaced, int src_top_field_first,
                               int n, unsigned long long first_fieldno);
+/*
+ * cvs_composite_fields_host_async: as _host, but returns as soon as the work is queued; the pictures
+ * in dst are complete after cvs_synchronize().  Consecutive asynchronous calls overlap (the upload of
+ * one call runs while the previous one computes and downloads), so a stream of batches keeps both PCIe
+ * directions busy without the fill/drain gap of a synchronous call.  The caller must not reuse src/dst
+ * of a call before the synchronize that follows it (use two buffer sets).  Host memory should be pinned.
+ */
+int cvs_composite_fields_host_async(cvs_ctx *ctx,
+                                    void *dst, size_t dst_pic_stride, int dst_stride,
+                                    const void *src, size_t src_pic_stride, int src_stride,
+                                    int w, int h, int src_interlaced, int src_top_field_first,
+                                    int n, unsigned long long first_fieldno);
 int cvs_synchronize(cvs_ctx *ctx);
 
 /* ---- RNG stream (hidden state of the reference: the libc rand() position) ------------------ */

@@ -223,3 +223,24 @@ def test_fused_bob_matches_reference_loop(oracle, w, h):
             eng2.composite_fields_device(dev, src, 1, h, w, k)
             eng2.synchronize()
             assert np.array_equal(want, dev.cpu().numpy().view(np.uint32)), k
+
+
+def test_async_host_calls_overlap_correctly():
+    """A stream of cvs_composite_fields_host_async batches (two host buffer sets, device buffers
+    alternate inside the engine) equals the synchronous calls."""
+    w, h, n, calls = 320, 240, 5, 5
+    p = helpers.params("-vhs")
+    src = [np.stack([helpers.stream_frame(w, h, c * n + k) for k in range(n)]) for c in range(calls)]
+    want = [np.zeros((n, h, w), dtype=np.uint32) for _ in range(calls)]
+    got = [np.zeros((n, h, w), dtype=np.uint32) for _ in range(calls)]
+    with cvs.Engine(params=p, max_w=w, max_h=h, max_batch=n) as eng:
+        for c in range(calls):
+            eng.composite_fields_host(want[c], src[c], c * n)
+        pos = eng.rng_tell()
+        eng.rng_seek(0)
+        for c in range(calls):
+            eng.composite_fields_host_async(got[c], src[c], c * n)
+        eng.synchronize()
+        assert eng.rng_tell() == pos
+    for c in range(calls):
+        assert np.array_equal(want[c], got[c]), c
