@@ -25,7 +25,8 @@ namespace {
 
 constexpr int kStagingSlots = 3;
 constexpr size_t kMaxEventPairs = 4096;
-constexpr int kHostChunkDefault = 16;       // fields per pipeline stage of the host-pointer entry points
+constexpr int kHostChunkDefault = 32;       // fields per pipeline stage of the host-pointer entry points
+                                            // (measured: 16 -> 8.6k, 32 -> 9.5k, 64 -> 9.6k fields/s at 1080p)
 
 struct DevPlan {
     int w = 0, h = 0;
@@ -335,8 +336,20 @@ int run_host(cvs_ctx *c, uint8_t *dst, size_t dst_pic_stride, int dst_stride, co
     uint8_t *const d_src = c->d_src[set], *const d_dst = c->d_dst[set];
     // this buffer set was last used two calls ago: its downloads must have drained before we overwrite it
     CVS_CUDA(cudaStreamWaitEvent(c->s_in, c->host_call_done[set], 0));
-    const int kHostChunk = c->host_chunk;
-    const int nchunks = (n + kHostChunk - 1) / kHostChunk;
+    // chunk boundaries: a synchronous call ramps up (8, 8, 16, then full chunks) so the first kernel
+    // starts early and the pipeline fills fast; an asynchronous call is already overlapped with its
+    // predecessor and uses full chunks throughout
+    std::vector<int> bounds;
+    bounds.push_back(0);
+    {
+        int ramp[3] = {8, 8, 16}, ri = 0;
+        while (bounds.back() < n) {
+            int sz = c->host_chunk;
+            if (!async && ri < 3 && ramp[ri] < sz) sz = ramp[ri++];
+            bounds.push_back(bounds.back() + sz < n ? bounds.back() + sz : n);
+        }
+    }
+    const int nchunks = (int)bounds.size() - 1;
     while ((int)c->ev_in.size() < nchunks) {
         cudaEvent_t a, b;
         CVS_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
@@ -350,7 +363,7 @@ int run_host(cvs_ctx *c, uint8_t *dst, size_t dst_pic_stride, int dst_stride, co
         return explicit_field >= 0 ? explicit_field : (int)((fieldno & 1) ^ 1);
     };
     for (int ci = 0; ci < nchunks; ci++) {
-        const int k0 = ci * kHostChunk, k1 = (k0 + kHostChunk < n) ? k0 + kHostChunk : n;
+        const int k0 = bounds[(size_t)ci], k1 = bounds[(size_t)ci + 1];
         for (int k = k0; k < k1; k++) {                       // upload, stream s_in
             const int field = field_of(k);
             if (field >= h) continue;
