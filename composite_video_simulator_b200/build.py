@@ -29,16 +29,16 @@ def build_oracle():
     return _run(["make"], os.path.join(ROOT, "oracle"))
 
 
-def build_emu():
+def build_emu(extra=()):
     out_dir = os.path.join(ROOT, "tests", "_build")
     os.makedirs(out_dir, exist_ok=True)
-    out = os.path.join(out_dir, "libemu.so")
+    out = os.path.join(out_dir, "libemu%s.so" % "".join(e.replace("-D", "_").replace("=", "") for e in extra))
     srcs = [os.path.join(ROOT, "tests", "emu_harness.cpp")] + [
         os.path.join(CSRC, f) for f in ("field_plan.cpp", "glibc_rand.cpp", "cvs_params.cpp")]
     deps = srcs + [os.path.join(CSRC, f) for f in ("lane_pipeline.cuh", "field_plan.h", "glibc_rand.h")]
     if os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
         return out
-    _run(["g++", "-O1", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-o", out] + srcs, ROOT)
+    _run(["g++", "-O1", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared"] + list(extra) + ["-o", out] + srcs, ROOT)
     return out
 
 

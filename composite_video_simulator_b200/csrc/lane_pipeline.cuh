@@ -46,7 +46,18 @@
 
 namespace cvs {
 
-constexpr int kT = 8;            // pixels per step
+// Measured on B200 (1080p VHS-SP, 256 fields): kT = 8 / 2 CTAs per SM (243 registers) 2.55 ms;
+// kT = 4 / 3 CTAs per SM (164 registers, no spills, 15 KB interior loop) 2.26 ms.
+#ifndef CVS_KT
+#define CVS_KT 4
+#endif
+constexpr int kT = CVS_KT;       // pixels per step (8 or 4); every block lag below is derived from it
+static_assert(kT == 4 || kT == 8, "kT must be 4 or 8");
+constexpr int kLB = (7 + kT - 1) / kT;        // a demodulation of B(k) reads C up to x+7: kLB blocks of look-ahead
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+constexpr int lag_blocks(int px) { return (px + kT - 1) / kT; }
 constexpr int kRngSlots = 32;    // per-lane ring of raw generator words (>= 31)
 constexpr int kTailSlots = 16;   // per-lane stash of pre-filter chroma for the delay tail (>= max chroma delay)
 constexpr uint32_t kRngBase = 128;  // ring index of the first in-line draw (multiple of 32, > max warm-up + 31)
@@ -69,7 +80,9 @@ enum : uint32_t {
     RF_HEADSW = 1u << 1,      // row is rotated by the head switch; C comes from the scratch row (pre-pass)
     RF_HEADSW_INLINE = 1u << 2,   // row is rotated by a small right shift with zero fill: delayed in-kernel
 };
-constexpr int kHsRing = 64;               // per-lane delay ring of the in-kernel head switch
+constexpr int kHsRing = 48;               // per-lane delay ring of the in-kernel head switch (a multiple of kT; not a
+                                          // power of two on purpose: 3 CTAs/SM must fit in shared memory; the default
+                                          // 1080p shift is -22 +-4 px of jitter; bigger shifts take the pre-pass)
 constexpr int kHsMaxDelay = kHsRing - kT; // largest shift the ring can express
 
 // ---- pairs --------------------------------------------------------------------------------------
@@ -498,7 +511,9 @@ struct Lane {
     static constexpr int OD = OUTFULL ? 4 : 1;    // output lowpass: max(delayI, delayQ)
     static constexpr int ODI = OUTFULL ? 2 : 1;   // I delay
     static constexpr int ODQ = OUTFULL ? 4 : 1;   // Q delay
-    static constexpr int LAG = VHS ? 6 : 3;       // steps between loading B(s) and storing B(s-LAG)
+    static constexpr int LD = lag_blocks(CD);     // blocks by which the delayed (VHS) chroma lags its filter input
+    static constexpr int LAG = VHS ? 2 + 2 * kLB + LD : 2 + kLB;   // steps between loading B(s) and storing B(s-LAG)
+    static_assert(OD <= kT, "output lowpass delay must fit one block");
 
     // --- carried state (all statically indexed) ---
     // A
@@ -508,22 +523,22 @@ struct Lane {
     R pPre;                          // pre-emphasis pole
     int nY;                          // luma noise accumulator (:1633)
     // B
-    R Cm1;                           // C[8(s-2)-1]
-    R Cprev[kT];                     // C of B(s-2)
+    R Cm1;                           // C[kT*kB - 1], kB = s-1-kLB
+    R Cwin[kLB][kT];                 // C of B(kB) .. B(s-2)
     int nU, nV;                      // chroma noise accumulators (:1720)
     R pL[3], pLpre;                  // VHS luma poles (:1800-1805)
     R pS[3];                         // sharpen poles (:1873-1876)
     V2<R> pUV[3];                    // VHS chroma poles (:1821-1826)
     V2<R> oUVprev[kT];               // chroma cascade outputs (U, V) for t in B(s-3)
-    R Y3a[kT], Y3b[kT];              // Y3 of B(s-3), B(s-4)
+    R Y3hist[LD][kT];                // Y3 of B(kB-LD) .. B(kB-1)   ([0] is the oldest)
     // B2 / C
-    R C2m1;                          // C2[8(s-5)-1]
-    R C2prev[kT];                    // C2 of B(s-5)
+    R C2m1;                          // C2[kT*kC - 1], kC = kD - kLB, kD = kB - LD
+    R C2win[kLB][kT];                // C2 of B(kC) .. B(kD-1)
     // F
     V2<R> pOIQ[3];                   // output lowpass poles
     R Ytail[OD];                     // last OD values of Y4 of the previous F block
     V2<R> IQtail[OD], oOIQtail[OD];  // ... of the raw (I4, Q4) and of the cascade outputs
-    uint32_t outprev[kT];            // packed pixels of positions [8(k-1), 8k-OD) in slots 0..7-OD
+    uint32_t outprev[kT - OD > 0 ? kT - OD : 1];   // packed pixels of positions [kT(k-1), kT k - OD)
 
     LaneRng rngL, rngC;
     R *tailU, *tailV;                // per-lane stash (kTailSlots each), stride tail_stride
@@ -532,8 +547,10 @@ struct Lane {
     CVS_HD void reset(const KConst<R> &K) {
         CVS_UNROLL
         for (int j = 0; j < kT; j++) {
-            Yprev[j] = 0; oIQprev[j] = mk2((R)0, (R)0); Cprev[j] = 0;
-            oUVprev[j] = mk2((R)0, (R)0); Y3a[j] = 0; Y3b[j] = 0; C2prev[j] = 0; outprev[j] = 0;
+            Yprev[j] = 0; oIQprev[j] = mk2((R)0, (R)0);
+            oUVprev[j] = mk2((R)0, (R)0);
+            for (int i = 0; i < kLB; i++) { Cwin[i][j] = 0; C2win[i][j] = 0; }
+            for (int i = 0; i < LD; i++) Y3hist[i][j] = 0;
         }
         CVS_UNROLL
         for (int k = 0; k < 3; k++) pS[k] = 0;    // :1875
@@ -544,6 +561,7 @@ struct Lane {
         pLpre = 16;                         // :1805
         pPre = 16;                          // :1622
         Cm1 = 0; C2m1 = 0;
+        for (int j = 0; j < (kT - OD > 0 ? kT - OD : 1); j++) outprev[j] = 0;
         CVS_UNROLL
         for (int k = 0; k < OD; k++) { Ytail[k] = 0; IQtail[k] = mk2((R)0, (R)0); oOIQtail[k] = mk2((R)0, (R)0); }
     }
@@ -563,19 +581,20 @@ CVS_HD R modulate(R Yv, R Iv, R Qv, R mI, R mQ, int amp) {
 
 // Y/C separation + QAM demodulation of block B(k) (chroma_from_luma, :1497-1567).
 //   cm1      = C[8k-1]
-//   c[0..15] = C[8k .. 8k+15]   (only c[0..14] are read; zero beyond the line end)
+//   c[i]     = C[kT k + i], i < (kLB+1) kT   (read up to kT+6; zero beyond the line end)
 // outputs Yb (box-filtered luma), Ib, Qb for the 8 pixels of the block.
 template <typename R, int MODE>
-CVS_HD void demod_block(const RowConst<R> &rc, int k, int w, int amp, R cm1, const R c[2 * kT],
+CVS_HD void demod_block(const RowConst<R> &rc, int k, int w, int amp, R cm1, const R c[(kLB + 1) * kT],
                         R Yb[kT], V2<R> IQb[kT]) {
     constexpr bool EDGE = MODE >= 1, GEN = MODE == 2;
     const int x0 = k * kT;
     // box[m] = (C[m-1] + C[m] + C[m+1] + C[m+2]) / 4 ; chroma[m] = C[m+2] - box[m], m = 0..12
     // (all values are integers < 2^24, so the running sum is exact in any order)
-    R ch[13];
+    constexpr int NCH = kT + 5;       // chroma samples needed: up to (first even pixel of the next block) + xi + 1
+    R ch[NCH];
     R sum = Num<R>::add(Num<R>::add(cm1, c[0]), Num<R>::add(c[1], c[2]));
     CVS_UNROLL
-    for (int m = 0; m < 13; m++) {
+    for (int m = 0; m < NCH; m++) {
         if (m > 0) sum = Num<R>::add(Num<R>::sub(sum, (m == 1) ? cm1 : c[m - 2]), c[m + 2]);
         const R box = div4_trunc<R>(sum);
         if (m < kT) Yb[m] = box;
@@ -585,7 +604,7 @@ CVS_HD void demod_block(const RowConst<R> &rc, int k, int w, int amp, R cm1, con
         // carrier sign flips with their line-end / line-start conditions (:1539-1542), then the
         // amplitude rescale (:1544-1546).  In the interior the flip folds into sgA below.
         CVS_UNROLL
-        for (int m = 0; m < 13; m++) {
+        for (int m = 0; m < NCH; m++) {
             const int q = x0 + m;
             const int ph = (q + rc.xi) & 3;
             const int g = q - ph;                      // start of this carrier period
@@ -600,16 +619,17 @@ CVS_HD void demod_block(const RowConst<R> &rc, int k, int w, int amp, R cm1, con
     const bool x1 = (rc.xi & 1) != 0, x2 = (rc.xi & 2) != 0;
     // With the default 180-degree line phase every row has xi in {0, 2}: the first level of the 4-way
     // selection is then the identity for the whole warp and is skipped under a warp-uniform branch.
-    R s01[10], s23[10];              // [2e] = I candidate, [2e+1] = Q candidate
+    constexpr int NE = kT / 2 + 1;    // even positions: kT/2 in the block plus the first of the next block
+    R s01[2 * NE], s23[2 * NE];      // [2e] = I candidate, [2e+1] = Q candidate
     if (MODE == 0 && !rc.odd_any) {     // MODE_FAST
         CVS_UNROLL
-        for (int e = 0; e < 5; e++) {
+        for (int e = 0; e < NE; e++) {
             s01[2 * e] = ch[2 * e]; s23[2 * e] = ch[2 * e + 2];
             s01[2 * e + 1] = ch[2 * e + 1]; s23[2 * e + 1] = ch[2 * e + 3];
         }
     } else {
         CVS_UNROLL
-        for (int e = 0; e < 5; e++) {
+        for (int e = 0; e < NE; e++) {
             const int j = 2 * e;
             s01[2 * e] = x1 ? ch[j + 1] : ch[j];
             s23[2 * e] = x1 ? ch[j + 3] : ch[j + 2];
@@ -617,9 +637,9 @@ CVS_HD void demod_block(const RowConst<R> &rc, int k, int w, int amp, R cm1, con
             s23[2 * e + 1] = x1 ? ch[j + 4] : ch[j + 3];
         }
     }
-    V2<R> IQe[5];
+    V2<R> IQe[NE];
     CVS_UNROLL
-    for (int e = 0; e < 5; e++) {
+    for (int e = 0; e < NE; e++) {
         const int j = 2 * e;
         R iv = x2 ? s23[2 * e] : s01[2 * e];
         R qv = x2 ? s23[2 * e + 1] : s01[2 * e + 1];
@@ -634,7 +654,7 @@ CVS_HD void demod_block(const RowConst<R> &rc, int k, int w, int amp, R cm1, con
     }
     // odd pixels: average of the even neighbours, arithmetic >> 1 (:1557-1560)
     CVS_UNROLL
-    for (int e = 0; e < 4; e++) {
+    for (int e = 0; e < kT / 2; e++) {
         IQb[2 * e] = IQe[e];
         IQb[2 * e + 1] = Num<R>::floor_half2(Num<R>::add2(IQe[e], IQe[e + 1]));
     }
@@ -667,6 +687,19 @@ template <typename R>
 struct BlendXchg {
     V2<R> uv[kT];
 };
+
+// slide a window of kLB carried blocks by one block: m1 <- last sample leaving, win <- win[1..], newest
+template <typename R>
+CVS_HD void window_push(R &m1, R win[kLB][kT], const R newest[kT]) {
+    m1 = win[0][kT - 1];
+    CVS_UNROLL
+    for (int i = 0; i + 1 < kLB; i++) {
+        CVS_UNROLL
+        for (int j = 0; j < kT; j++) win[i][j] = win[i + 1][j];
+    }
+    CVS_UNROLL
+    for (int j = 0; j < kT; j++) win[kLB - 1][j] = newest[j];
+}
 
 template <typename R, bool VHS, int CD, bool OUTFULL>
 struct Pipeline {
@@ -754,27 +787,29 @@ struct Pipeline {
                                R Yb[kT], V2<R> IQb[kT], BlendXchg<R> &xo) {
         constexpr bool EDGE = MODE >= 1, GEN = MODE == 2;
         const int w = K.w;
-        const int k = s - 2;
+        constexpr int LD = L::LD;
+        const int k = s - 1 - kLB;                                 // kB
         if (EDGE && k < 0) {
             CVS_UNROLL
             for (int j = 0; j < kT; j++) { Yb[j] = 0; IQb[j] = mk2((R)0, (R)0); xo.uv[j] = mk2((R)0, (R)0); }
-            ln.Cm1 = ln.Cprev[kT - 1];
-            CVS_UNROLL
-            for (int j = 0; j < kT; j++) ln.Cprev[j] = Cnew[j];
+            window_push<R>(ln.Cm1, ln.Cwin, Cnew);
             return;
         }
-        R c[2 * kT];
+        R c[(kLB + 1) * kT];                                       // C of B(kB) .. B(s-1)
         CVS_UNROLL
-        for (int j = 0; j < kT; j++) { c[j] = ln.Cprev[j]; c[kT + j] = Cnew[j]; }
+        for (int i = 0; i < kLB; i++) {
+            CVS_UNROLL
+            for (int j = 0; j < kT; j++) c[i * kT + j] = ln.Cwin[i][j];
+        }
+        CVS_UNROLL
+        for (int j = 0; j < kT; j++) c[kLB * kT + j] = Cnew[j];
         if (GEN && (K.flags & F_NOCOLOR)) {                        // :1715: no demod, chroma stays zero
             CVS_UNROLL
             for (int j = 0; j < kT; j++) { Yb[j] = c[j]; IQb[j] = mk2((R)0, (R)0); }
         } else {
             demod_block<R, MODE>(rc, k, w, K.amp_back, ln.Cm1, c, Yb, IQb);   // :1716
         }
-        ln.Cm1 = ln.Cprev[kT - 1];
-        CVS_UNROLL
-        for (int j = 0; j < kT; j++) ln.Cprev[j] = Cnew[j];
+        window_push<R>(ln.Cm1, ln.Cwin, Cnew);
 
         const int x0 = k * kT;
         if (GEN ? (K.cnoise != 0) : VHS) {                         // :1718-1735
@@ -821,13 +856,15 @@ struct Pipeline {
                 Yb[j] = 0; oUVcur[j] = mk2((R)0, (R)0);
             }
         }
-        // delayed chroma block B(s-4): position x' = 8(s-4)+j was produced at time x'+CD
+        // delayed chroma block B(kD), kD = kB - LD: position x' = kT kD + j was produced at time x' + CD,
+        // which lies in B(kB) (this step's outputs) or B(kB-1) (carried)
         CVS_UNROLL
         for (int j = 0; j < kT; j++) {
-            const int rel = j + CD - 2 * kT;                // index into the current outputs (time in B(s-2))
-            V2<R> uv = (rel >= 0) ? oUVcur[(rel + 2 * kT) % kT] : ln.oUVprev[(rel + kT) % kT];
+            constexpr int LDT = LD * kT;
+            const int rel = j + CD - LDT;                   // index into the current outputs (time in B(kB))
+            V2<R> uv = (rel >= 0) ? oUVcur[(rel + LDT) % kT] : ln.oUVprev[(rel + kT) % kT];
             if (EDGE) {
-                const int xp = (s - 4) * kT + j;
+                const int xp = (k - LD) * kT + j;
                 if (xp >= w - CD && xp < w && xp >= 0 && (xp - (w - CD)) < kTailSlots) {
                     uv = mk2(ln.tailU[(xp - (w - CD)) * ln.tail_stride], ln.tailV[(xp - (w - CD)) * ln.tail_stride]);
                 }
@@ -847,7 +884,9 @@ struct Pipeline {
                                const BlendXchg<R> &own, const BlendXchg<R> &above,
                                R Yf[kT], V2<R> IQf[kT], int &kf) {
         constexpr bool EDGE = MODE >= 1, GEN = MODE == 2;
+        constexpr int LD = L::LD;
         const int w = K.w;
+        const int kD = s - 1 - kLB - LD;                              // delayed chroma / C2 block
         V2<R> UV[kT];
         const bool blend = (K.flags & F_VBLEND) && rc.row >= 1;       // loop starts at field+2, :1849
         const bool have_above = rc.row >= 2;                          // row field+2 blends with zero
@@ -862,21 +901,26 @@ struct Pipeline {
         }
         const bool svideo = GEN && (K.flags & F_SVIDEO);
         if (svideo) {                                                 // :1885: no recombine
-            kf = s - 4;
+            kf = kD;
             CVS_UNROLL
-            for (int j = 0; j < kT; j++) { Yf[j] = ln.Y3b[j]; IQf[j] = UV[j]; }
+            for (int j = 0; j < kT; j++) { Yf[j] = ln.Y3hist[0][j]; IQf[j] = UV[j]; }
         } else {
-            kf = s - 5;
-            // C2 of B(s-4) = Y3 + QAM(U,V) with subcarrier_amplitude (:1886)
-            R c[2 * kT];
+            kf = kD - kLB;                                            // kC
+            // C2 of B(kD) = Y3 + QAM(U,V) with subcarrier_amplitude (:1886)
+            R c[(kLB + 1) * kT], c2new[kT];
+            CVS_UNROLL
+            for (int i = 0; i < kLB; i++) {
+                CVS_UNROLL
+                for (int j = 0; j < kT; j++) c[i * kT + j] = ln.C2win[i][j];
+            }
             CVS_UNROLL
             for (int j = 0; j < kT; j++) {
-                const int x = (s - 4) * kT + j;
+                const int x = kD * kT + j;
                 R cv = 0;
                 if (!EDGE || (x >= 0 && x < w))
-                    cv = modulate<R, MODE>(ln.Y3b[j], UV[j].x, UV[j].y, rc.mI[j & 3], rc.mQ[j & 3], K.amp);
-                c[kT + j] = cv;
-                c[j] = ln.C2prev[j];
+                    cv = modulate<R, MODE>(ln.Y3hist[0][j], UV[j].x, UV[j].y, rc.mI[j & 3], rc.mQ[j & 3], K.amp);
+                c[kLB * kT + j] = cv;
+                c2new[j] = cv;
             }
             if (!EDGE || kf >= 0) {
                 demod_block<R, MODE>(rc, kf, w, K.amp, ln.C2m1, c, Yf, IQf);      // :1887
@@ -884,12 +928,15 @@ struct Pipeline {
                 CVS_UNROLL
                 for (int j = 0; j < kT; j++) { Yf[j] = 0; IQf[j] = mk2((R)0, (R)0); }
             }
-            ln.C2m1 = ln.C2prev[kT - 1];
-            CVS_UNROLL
-            for (int j = 0; j < kT; j++) ln.C2prev[j] = c[kT + j];
+            window_push<R>(ln.C2m1, ln.C2win, c2new);
         }
         CVS_UNROLL
-        for (int j = 0; j < kT; j++) { ln.Y3b[j] = ln.Y3a[j]; ln.Y3a[j] = Y3new[j]; }
+        for (int i = 0; i + 1 < LD; i++) {
+            CVS_UNROLL
+            for (int j = 0; j < kT; j++) ln.Y3hist[i][j] = ln.Y3hist[i + 1][j];
+        }
+        CVS_UNROLL
+        for (int j = 0; j < kT; j++) ln.Y3hist[LD - 1][j] = Y3new[j];
     }
 
     // ---- F: dropout, output chroma lowpass, YIQ -> RGB; completes output block B(kf-1) ----------------
@@ -938,7 +985,7 @@ struct Pipeline {
         }
         // out block B(kf-1): slots 0..7-OD carried from the previous step, slots 8-OD..7 are pk[0..OD-1]
         CVS_UNROLL
-        for (int j = 0; j < kT; j++) out[j] = (j < kT - OD) ? ln.outprev[j] : pk[(j - (kT - OD) + kT) % kT];
+        for (int j = 0; j < kT; j++) out[j] = (j < kT - OD) ? ln.outprev[j % (kT - OD > 0 ? kT - OD : 1)] : pk[(j - (kT - OD) + kT) % kT];
         CVS_UNROLL
         for (int j = 0; j < kT - OD; j++) ln.outprev[j] = pk[j + OD];
         CVS_UNROLL
@@ -967,35 +1014,39 @@ CVS_HD void headswitch_substitute(const RowConst<R> &rc, const int32_t *hs_row, 
 // lane) and comes back delayed by the lane's own d (0 for rows that are not rotated).
 template <typename R>
 CVS_HD void headswitch_delay_block(R *ring, int stride, int k, int w, int d, R C[kT]) {
+    static_assert(kHsRing % kT == 0, "a block never wraps inside the ring");
     const int x0 = k * kT;
+    const int b0 = x0 % kHsRing;
     CVS_UNROLL
-    for (int j = 0; j < kT; j++) ring[((x0 + j) & (kHsRing - 1)) * stride] = C[j];
+    for (int j = 0; j < kT; j++) ring[(b0 + j) * stride] = C[j];
     CVS_UNROLL
     for (int j = 0; j < kT; j++) {
         const int xs = x0 + j - d;
-        const R v = ring[(xs & (kHsRing - 1)) * stride];
+        const R v = ring[(((xs % kHsRing) + kHsRing) % kHsRing) * stride];
         C[j] = (xs >= 0 && x0 + j < w) ? v : (R)0;          // the composite signal is zero beyond the line end
     }
 }
 
-// number of steps a line of width w takes
-template <bool VHS>
-CVS_HD int line_steps(int w) { return (w + kT - 1) / kT + (VHS ? 6 : 3); }
+// number of steps a line of width w takes: its blocks plus the pipeline depth
+template <bool VHS, int CD>
+CVS_HD int line_steps(int w) { return (w + kT - 1) / kT + (VHS ? 2 + 2 * kLB + lag_blocks(CD) : 2 + kLB); }
 
 // [s_lo, s_hi): steps whose every stage works on an interior block, so the fast variant is valid.
-// Line start: the first demodulated block of each demod (k = 0) has the carrier-period condition
-// g >= 0, so demod 1 (block s-2) needs s >= 3 and, with VHS, demod 2 (block s-5) needs s >= 6.
-// Line end, for step s:  A1 reads B(s) whole: 8s+8 <= w;  A2 builds B(s-1) and must stay clear of
-// the raw-chroma tail (x+4 >= w): 8s+3 < w;  the VHS chroma stash starts at x >= w-CD for x in
-// B(s-2): 8s-9 < w-CD.  Everything downstream is older and weaker.
-template <bool VHS>
-CVS_HD void interior_steps(int w, int cd, int &s_lo, int &s_hi) {
-    s_lo = VHS ? 6 : 3;
-    int hi = (w - kT) / kT + 1;                          // 8s + 8 <= w
-    const int a2 = (w - 3 + kT - 1) / kT;                // 8s < w - 3
+// Block indices at step s: kB = s-1-kLB (first demod, VHS filters), kD = kB-LD (delayed chroma, C2),
+// kC = kD-kLB (second demod).  Line start: the first block of each demodulation (index 0) has the
+// carrier-period condition g >= 0, so kB >= 1 and, with VHS, kC >= 1.  Line end, for step s: A1 reads
+// B(s) whole: kT(s+1) <= w;  A2 builds B(s-1) and must stay clear of the raw-chroma tail (x+4 >= w):
+// kT s + 3 < w;  the VHS chroma stash starts at x >= w-CD for x in B(kB): kT(s-kLB) - 1 < w - CD.
+// Everything downstream is older and weaker.
+template <bool VHS, int CD>
+CVS_HD void interior_steps(int w, int &s_lo, int &s_hi) {
+    constexpr int LD = lag_blocks(CD);
+    s_lo = VHS ? 2 + 2 * kLB + LD : 2 + kLB;
+    int hi = (w - kT) / kT + 1;                          // kT(s+1) <= w
+    const int a2 = (w - 3 + kT - 1) / kT;                // kT s < w - 3
     if (a2 < hi) hi = a2;
     if (VHS) {
-        const int st = (w - cd + 9 + kT - 1) / kT;       // 8s < w - cd + 9
+        const int st = (w - CD + 1 + kT - 1) / kT + kLB; // kT (s - kLB) < w - CD + 1
         if (st < hi) hi = st;
     }
     s_hi = hi < s_lo ? s_lo : hi;

@@ -29,7 +29,7 @@ namespace cvs {
 constexpr int kNT = CVS_NT;              // threads per CTA
 constexpr int kWarpsPerCta = kNT / 32;
 #ifndef CVS_MIN_CTAS
-#define CVS_MIN_CTAS 2              // CTAs per SM the register allocator must leave room for
+#define CVS_MIN_CTAS 3              // CTAs per SM the register allocator must leave room for (168 registers)
 #endif
 constexpr int kRowsPerWarp = 31;         // lane 0 is the halo row of the vertical chroma blend
 
@@ -106,9 +106,11 @@ __device__ __forceinline__ void load_block_dev(const uint32_t *srow, int k, int 
     const int x0 = k * kT;
     if (vec && x0 + kT <= w) {
         const uint4 *p = reinterpret_cast<const uint4 *>(srow + x0);
-        const uint4 a = ld_row16(p), b = ld_row16(p + 1);
-        px[0] = a.x; px[1] = a.y; px[2] = a.z; px[3] = a.w;
-        px[4] = b.x; px[5] = b.y; px[6] = b.z; px[7] = b.w;
+#pragma unroll
+        for (int v = 0; v < kT / 4; v++) {
+            const uint4 a = ld_row16(p + v);
+            px[4 * v] = a.x; px[4 * v + 1] = a.y; px[4 * v + 2] = a.z; px[4 * v + 3] = a.w;
+        }
     } else {
 #pragma unroll
         for (int j = 0; j < kT; j++) px[j] = (x0 + j < w) ? __ldg(srow + x0 + j) : 0u;
@@ -120,9 +122,11 @@ __device__ __forceinline__ void load_block_fast(const uint32_t *srow, int k, boo
     const int x0 = k * kT;
     if (vec) {
         const uint4 *p = reinterpret_cast<const uint4 *>(srow + x0);
-        const uint4 a = ld_row16(p), b = ld_row16(p + 1);
-        px[0] = a.x; px[1] = a.y; px[2] = a.z; px[3] = a.w;
-        px[4] = b.x; px[5] = b.y; px[6] = b.z; px[7] = b.w;
+#pragma unroll
+        for (int v = 0; v < kT / 4; v++) {
+            const uint4 a = ld_row16(p + v);
+            px[4 * v] = a.x; px[4 * v + 1] = a.y; px[4 * v + 2] = a.z; px[4 * v + 3] = a.w;
+        }
     } else {
 #pragma unroll
         for (int j = 0; j < kT; j++) px[j] = __ldg(srow + x0 + j);
@@ -172,19 +176,19 @@ struct Stepper {
             P::template stage_c<MODE>(K, rc, ln, s, Yb, xo, above, Yf, IQf, kf);
             have = P::template stage_f<MODE>(K, rc, ln, kf, Yf, IQf, out);
         } else {
-            kf = s - 2;
+            kf = s - 1 - kLB;
             have = P::template stage_f<MODE>(K, rc, ln, kf, Yb, IQb, out);
         }
         if (have && valid) {
             const int x0 = (kf - 1) * kT;
             if (vec_dst && (!EDGE || x0 + kT <= K.w)) {
                 uint4 *d = reinterpret_cast<uint4 *>(drow + x0);
-                d[0] = make_uint4(out[0], out[1], out[2], out[3]);
-                d[1] = make_uint4(out[4], out[5], out[6], out[7]);
+#pragma unroll
+                for (int v = 0; v < kT / 4; v++) d[v] = make_uint4(out[4 * v], out[4 * v + 1], out[4 * v + 2], out[4 * v + 3]);
                 if (drow_bob) {                            // line doubling: the same pixels one row up
                     uint4 *d2 = reinterpret_cast<uint4 *>(drow_bob + x0);
-                    d2[0] = make_uint4(out[0], out[1], out[2], out[3]);
-                    d2[1] = make_uint4(out[4], out[5], out[6], out[7]);
+#pragma unroll
+                    for (int v = 0; v < kT / 4; v++) d2[v] = make_uint4(out[4 * v], out[4 * v + 1], out[4 * v + 2], out[4 * v + 3]);
                 }
             } else {
 #pragma unroll
@@ -261,9 +265,9 @@ __global__ void __launch_bounds__(kNT, CVS_MIN_CTAS) k_fields(const __grid_const
         if (!ok) atomicOr(a.status, 1);
     }
 
-    const int nsteps = line_steps<VHS>(w);
+    const int nsteps = line_steps<VHS, CD>(w);
     int s_lo, s_hi;
-    interior_steps<VHS>(w, CD, s_lo, s_hi);
+    interior_steps<VHS, CD>(w, s_lo, s_hi);
     const bool general = (K.flags & F_GENERAL) != 0;
     if (general) s_hi = s_lo;
     const bool vec_src = a.vec_src != 0, vec_dst = a.vec_dst != 0;

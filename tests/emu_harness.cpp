@@ -65,9 +65,9 @@ int run_field(const cvs_params &p, RandCursor &cur, uint8_t *dst, int dst_stride
     }
 
     const int nwarps = (nl + 30) / 31;
-    const int nsteps = line_steps<VHS>(w);
+    const int nsteps = line_steps<VHS, CD>(w);
     int s_lo, s_hi;
-    interior_steps<VHS>(w, CD, s_lo, s_hi);
+    interior_steps<VHS, CD>(w, s_lo, s_hi);
     std::vector<uint32_t> rings((size_t)32 * 2 * kRngSlots);
     std::vector<R> tails((size_t)32 * 2 * kTailSlots);
     std::vector<R> hsring((size_t)32 * kHsRing);
@@ -156,7 +156,7 @@ int run_field(const cvs_params &p, RandCursor &cur, uint8_t *dst, int dst_stride
         P::template stage_c<M>(K, rc[l], lane[l], s, Yb[l], xo[l], above, Yf, IQf, kf);                      \
         have = P::template stage_f<M>(K, rc[l], lane[l], kf, Yf, IQf, out);                                  \
     } else {                                                                                                 \
-        kf = s - 2;                                                                                          \
+        kf = s - 1 - kLB;                                                                                          \
         have = P::template stage_f<M>(K, rc[l], lane[l], kf, Yb[l], IQb[l], out);                            \
     }
                 if (mode == MODE_FAST) { CVS_TAIL(MODE_FAST) }

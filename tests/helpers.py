@@ -51,7 +51,9 @@ def load_ref():
 
 
 def load_emu():
-    lib = C.CDLL(cvs_build.build_emu())
+    """CPU emulation of the lane pipeline.  CVS_EMU_KT=4 builds it with the 4-pixel step (experiments)."""
+    kt = os.environ.get("CVS_EMU_KT")
+    lib = C.CDLL(cvs_build.build_emu(("-DCVS_KT=%s" % kt,) if kt else ()))
     return lib
 
 
