@@ -203,7 +203,7 @@ struct Stepper {
 };
 
 template <typename R, bool VHS, int CD, bool OUTFULL>
-__global__ void __launch_bounds__(kNT, CVS_MIN_CTAS) k_fields(const __grid_constant__ LaunchArgs<R> a) {
+__global__ void __launch_bounds__(kNT, (sizeof(R) == 4 ? CVS_MIN_CTAS : 1)) k_fields(const __grid_constant__ LaunchArgs<R> a) {
     typedef Lane<R, VHS, CD, OUTFULL> L;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t *rings = reinterpret_cast<uint32_t *>(smem_raw);
