@@ -242,9 +242,11 @@ def run_own_arm(args):
         dist.broadcast(pbytes, src=0)
     params = CvsParams.from_buffer_copy(bytes(pbytes.cpu().numpy().tobytes()))
 
-    B = args.batch
     nl = (H + 1) // 2
-    eng = cvs.Engine(params=params, device=local_rank, max_w=W, max_h=H, max_batch=max(B, args.e2e_batch))
+    eng = cvs.Engine(params=params, device=local_rank, max_w=W, max_h=H, max_batch=max(args.batch, args.e2e_batch))
+    # fields per step: the largest batch <= --batch that fills whole waves of the GPU (a lane = a scanline,
+    # all tasks equally long: a partial last wave is pure loss); identical on every rank
+    B = eng.preferred_batch(W, H, args.batch) if args.wave_align else args.batch
     stream = torch.cuda.Stream(device=dev)
     eng.set_stream(stream.cuda_stream)
     from composite_video_simulator_b200 import sharding
@@ -392,7 +394,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="fields per GPU per step (device-resident)")
+    ap.add_argument("--batch", type=int, default=320, help="upper bound of fields per GPU per step (device-resident)")
+    ap.add_argument("--no-wave-align", dest="wave_align", action="store_false",
+                    help="use --batch as is instead of the wave-aligned batch cvs_preferred_batch() suggests")
     ap.add_argument("--e2e-batch", type=int, default=256, help="fields per GPU per step (host buffers)")
     ap.add_argument("--cpu-fields", type=int, default=64, help="fields of the single-thread CPU baseline sample")
     ap.add_argument("--ref-fields-per-proc", type=int, default=4)

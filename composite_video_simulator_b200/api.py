@@ -100,6 +100,13 @@ class Engine:
         """Fuse the reference's line doubling (ffmpeg_ntsc.cpp:2232-2257) into the field call."""
         _check(self.lib.cvs_set_bob(self._ctx, 1 if enable else 0), "cvs_set_bob")
 
+    def preferred_batch(self, w, h, max_batch):
+        """Largest batch <= max_batch that fills whole waves of the device (see cvs_preferred_batch)."""
+        n = self.lib.cvs_preferred_batch(self._ctx, w, h, max_batch)
+        if n <= 0:
+            raise CvsError(n, "cvs_preferred_batch")
+        return n
+
     def rng_seek(self, draws_consumed):
         _check(self.lib.cvs_rng_seek(self._ctx, draws_consumed), "cvs_rng_seek")
 

@@ -170,6 +170,14 @@ cudaError_t launch_variant<double>(const Variant &v, const LaunchArgs<double> &a
     return v.outfull ? launch_fields<double, true, 14, true>(a, st) : launch_fields<double, true, 14, false>(a, st);
 }
 
+template <typename R>
+cudaError_t occupancy_variant(const Variant &v, int *n) {
+    if (!v.vhs) return v.outfull ? occupancy_fields<R, false, 9, true>(n) : occupancy_fields<R, false, 9, false>(n);
+    if (v.cd == 9) return v.outfull ? occupancy_fields<R, true, 9, true>(n) : occupancy_fields<R, true, 9, false>(n);
+    if (v.cd == 12) return v.outfull ? occupancy_fields<R, true, 12, true>(n) : occupancy_fields<R, true, 12, false>(n);
+    return v.outfull ? occupancy_fields<R, true, 14, true>(n) : occupancy_fields<R, true, 14, false>(n);
+}
+
 template <typename R> R *&lut_ptr(cvs_ctx *c);
 template <> float *&lut_ptr<float>(cvs_ctx *c) { return c->d_lut_f; }
 template <> double *&lut_ptr<double>(cvs_ctx *c) { return c->d_lut_d; }
@@ -478,6 +486,27 @@ int cvs_set_params(cvs_ctx *ctx, const cvs_params *p) {
     ctx->plans.clear();                      // draw layout depends on the enabled stages
     ctx->lut_dirty = true;
     return CVS_OK;
+}
+
+int cvs_preferred_batch(cvs_ctx *ctx, int w, int h, int max_batch) {
+    // A field is ceil(nl/31) warp-tasks of equal length (one scanline per lane), so a launch runs in
+    // waves of (SMs x resident CTAs x warps per CTA) tasks; a batch that fills whole waves wastes none.
+    if (!ctx || w <= 0 || h <= 0 || max_batch <= 0) return CVS_ERR_INVALID_ARG;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return CVS_ERR_CUDA;
+    int sms = 0, ctas = 0;
+    CVS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+    const Variant v = pick_variant(ctx->p);
+    if (ctx->precision) CVS_CUDA(occupancy_variant<double>(v, &ctas));
+    else CVS_CUDA(occupancy_variant<float>(v, &ctas));
+    if (max_batch > ctx->max_batch) max_batch = ctx->max_batch;
+    const long long slots = (long long)sms * ctas * kWarpsPerCta;
+    const long long tasks_per_field = ((h + 1) / 2 + kRowsPerWarp - 1) / kRowsPerWarp;
+    if (slots <= 0) return max_batch;
+    // largest batch <= max_batch whose task count is at most a whole number of waves
+    const long long waves = ((long long)max_batch * tasks_per_field) / slots;
+    if (waves < 1) return max_batch;
+    const long long b = (waves * slots) / tasks_per_field;
+    return (int)(b < 1 ? 1 : b);
 }
 
 int cvs_set_bob(cvs_ctx *ctx, int enable) {

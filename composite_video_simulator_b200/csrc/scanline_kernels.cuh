@@ -347,6 +347,9 @@ __global__ void __launch_bounds__(kHsNT) k_headswitch(const __grid_constant__ La
 // host-callable launchers (one translation unit per instantiation, see kern_*.cu)
 template <typename R, bool VHS, int CD, bool OUTFULL>
 cudaError_t launch_fields(const LaunchArgs<R> &a, cudaStream_t st);
+// resident CTAs per SM of an instantiation (for wave-aligned batch sizes)
+template <typename R, bool VHS, int CD, bool OUTFULL>
+cudaError_t occupancy_fields(int *ctas_per_sm);
 template <typename R>
 cudaError_t launch_headswitch(const LaunchArgs<R> &a, const HsItem *items, int nitems, cudaStream_t st);
 
@@ -360,6 +363,14 @@ cudaError_t launch_headswitch(const LaunchArgs<R> &a, const HsItem *items, int n
         const int ctas = (a.total_warps + kWarpsPerCta - 1) / kWarpsPerCta;                                    \
         k_fields<R, VHS, CD, OUTFULL><<<ctas, kNT, smem, st>>>(a);                                             \
         return cudaGetLastError();                                                                             \
+    }                                                                                                          \
+    template <>                                                                                                \
+    cudaError_t occupancy_fields<R, VHS, CD, OUTFULL>(int *ctas_per_sm) {                                      \
+        const size_t smem = SmemLayout<R, VHS>::total;                                                         \
+        cudaError_t e = cudaFuncSetAttribute(k_fields<R, VHS, CD, OUTFULL>,                                    \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
+        if (e != cudaSuccess) return e;                                                                        \
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_fields<R, VHS, CD, OUTFULL>, kNT, smem); \
     }
 
 }  // namespace cvs

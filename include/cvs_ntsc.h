@@ -197,6 +197,15 @@ int cvs_rng_tell(const cvs_ctx *ctx, unsigned long long *draws_consumed);
 /* Draws one composite_layer() call consumes for this geometry/params. */
 unsigned long long cvs_draws_per_field(const cvs_params *p, int w, int h, unsigned field);
 
+/*
+ * Largest batch size <= max_batch (and <= the context's capacity) whose scanline tasks fill a whole
+ * number of waves of the device for this geometry and parameter block: every lane processes one
+ * scanline, all tasks take the same time, so a partial last wave is pure loss (a 256-field batch of
+ * 1080p on a B200 runs 2.6 waves in the time of 3; 296 fields fill 3).  Returns the batch size (> 0)
+ * or a negative cvs_status.
+ */
+int cvs_preferred_batch(cvs_ctx *ctx, int w, int h, int max_batch);
+
 /* ---- introspection -------------------------------------------------------------------------- */
 
 const char *cvs_strerror(int status);
