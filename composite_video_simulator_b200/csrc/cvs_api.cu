@@ -12,6 +12,7 @@
 #include <cstring>
 #include <memory>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "../../include/cvs_ntsc.h"
@@ -58,6 +59,7 @@ struct cvs_ctx {
     int precision = 0;                         // 0 = float (production), 1 = double (reference arithmetic)
     int host_chunk = kHostChunkDefault;
     int bob = 0;                               // fused line doubling (cvs_set_bob)
+    int plan_threads = 4;                      // host threads that build the per-row side tables of a batch
     cudaStream_t stream = nullptr;
     bool own_stream = true;
     cudaStream_t s_in = nullptr, s_out = nullptr;      // upload / download streams of the host-pointer path
@@ -248,8 +250,13 @@ int run_device(cvs_ctx *c, uint8_t *dst, size_t dst_pic_stride, int dst_stride, 
     if (sl.in_flight) { CVS_CUDA(cudaEventSynchronize(sl.consumed)); sl.in_flight = false; }
 
     const int opposite = interlaced ? (tff ? 1 : 0) : 0;                               // :1585-1588
+    // Planning.  Pass 1 (serial, cheap): per field, its plan and a copy of the rand() cursor at its first
+    // draw (one 31x31 jump per field).  Pass 2 (a few host threads): the per-row side tables, which is
+    // where the time goes (5.8 us per 1080p field on one thread).  Pass 3 (serial): the head-switch
+    // pre-pass work list.
     int nitems = 0, max_nl = 0;
-    FieldSide fs;
+    struct Job { DevPlan *pl; RandCursor at; int hs_count; };
+    std::vector<Job> jobs((size_t)n);
     for (int k = 0; k < n; k++) {
         const unsigned long long fieldno = first_fieldno + (unsigned long long)k;
         const unsigned field = explicit_field >= 0 ? (unsigned)explicit_field : (unsigned)((fieldno & 1) ^ 1);
@@ -259,29 +266,57 @@ int run_device(cvs_ctx *c, uint8_t *dst, size_t dst_pic_stride, int dst_stride, 
         fd.dst = dst + (size_t)k * dst_pic_stride;
         fd.fieldno = fieldno;
         fd.field = (int32_t)field;
+        jobs[(size_t)k].pl = nullptr;
+        jobs[(size_t)k].hs_count = 0;
         if ((int)field >= h) { fd.nl = 0; continue; }      // no rows of this parity: nothing drawn, nothing written
         DevPlan *pl = nullptr;
         int rc = get_plan(c, w, h, field, &pl);
         if (rc != CVS_OK) return rc;
-        build_field_side(c->p, pl->g, c->cur, fs);
+        jobs[(size_t)k].pl = pl;
+        jobs[(size_t)k].at = c->cur;
+        c->cur.jump(pl->g.jumpN, pl->g.ndraws);
         fd.nl = pl->g.nl;
         if (fd.nl > max_nl) max_nl = fd.nl;
         fd.seek = pl->d_seek;
         fd.rowinfo = c->d_rowinfo + (size_t)k * c->nl_max;
-        std::memcpy(sl.h_rowinfo + (size_t)k * c->nl_max, fs.rowinfo.data(), fs.rowinfo.size() * sizeof(uint32_t));
-        std::memcpy(fd.window, fs.window, sizeof(fs.window));
-        fd.hs_first = fs.hs_first;
-        fd.hs_count = fs.hs_count;
-        if (fs.hs_count > c->hs_max) return CVS_ERR_CAPACITY;
         fd.hs_scratch = c->d_scratch + (size_t)k * c->hs_max * (size_t)c->max_w;
         fd.hs_shift = c->d_hsshift + (size_t)k * c->hs_max;
-        for (int i = 0; i < fs.hs_count; i++) {
-            sl.h_hsshift[(size_t)k * c->hs_max + i] = fs.hs_shift[(size_t)i];
+    }
+    bool capacity_error = false;
+    auto plan_range = [&](int k0, int k1) {
+        FieldSide fs;
+        for (int k = k0; k < k1; k++) {
+            Job &jb = jobs[(size_t)k];
+            if (!jb.pl) continue;
+            FieldDesc &fd = sl.h_fields[k];
+            build_field_side_at(c->p, jb.pl->g, jb.at, fs);
+            std::memcpy(sl.h_rowinfo + (size_t)k * c->nl_max, fs.rowinfo.data(), fs.rowinfo.size() * sizeof(uint32_t));
+            std::memcpy(fd.window, fs.window, sizeof(fs.window));
+            fd.hs_first = fs.hs_first;
+            fd.hs_count = fs.hs_count;
+            if (fs.hs_count > c->hs_max) { capacity_error = true; fd.hs_count = 0; continue; }
+            for (int i = 0; i < fs.hs_count; i++) sl.h_hsshift[(size_t)k * c->hs_max + i] = fs.hs_shift[(size_t)i];
+            jb.hs_count = fs.hs_count;
+        }
+    };
+    const int nthreads = (n >= 64) ? c->plan_threads : 1;
+    if (nthreads <= 1) {
+        plan_range(0, n);
+    } else {
+        std::vector<std::thread> pool;
+        const int per = (n + nthreads - 1) / nthreads;
+        for (int t = 1; t < nthreads; t++)
+            if (t * per < n) pool.emplace_back(plan_range, t * per, (t + 1) * per < n ? (t + 1) * per : n);
+        plan_range(0, per < n ? per : n);
+        for (auto &th : pool) th.join();
+    }
+    if (capacity_error) return CVS_ERR_CAPACITY;
+    for (int k = 0; k < n; k++)
+        for (int i = 0; i < jobs[(size_t)k].hs_count; i++) {
             sl.h_items[nitems].field_idx = k;
             sl.h_items[nitems].slot = i;
             nitems++;
         }
-    }
     if (max_nl == 0) return CVS_OK;
 
     CVS_CUDA(cudaMemcpyAsync(c->d_fields, sl.h_fields, (size_t)n * sizeof(FieldDesc), cudaMemcpyHostToDevice, c->stream));
@@ -440,6 +475,14 @@ int cvs_create(cvs_ctx **out, const cvs_params *p, int device, int max_w, int ma
     if (const char *e = std::getenv("CVS_HOST_CHUNK")) {      // tuning knob for experiments
         const int v = std::atoi(e);
         if (v >= 1 && v <= 1024) c->host_chunk = v;
+    }
+    {
+        unsigned hw = std::thread::hardware_concurrency();
+        if (hw > 0 && (int)hw < c->plan_threads) c->plan_threads = (int)hw;
+        if (const char *e = std::getenv("CVS_PLAN_THREADS")) {  // tuning knob
+            const int v = std::atoi(e);
+            if (v >= 1 && v <= 64) c->plan_threads = v;
+        }
     }
     c->hs_max = head_switch_rows_bound(max_w);
     if (c->hs_max > c->nl_max) c->hs_max = c->nl_max;

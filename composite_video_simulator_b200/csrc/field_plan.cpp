@@ -147,6 +147,11 @@ void build_geom_plan(const cvs_params &p, int w, int h, unsigned field, GeomPlan
 }
 
 void build_field_side(const cvs_params &p, const GeomPlan &g, RandCursor &cur, FieldSide &fs) {
+    build_field_side_at(p, g, cur, fs);
+    cur.jump(g.jumpN, g.ndraws);
+}
+
+void build_field_side_at(const cvs_params &p, const GeomPlan &g, const RandCursor &cur, FieldSide &fs) {
     cur.window(fs.window);
     fs.rowinfo.assign((size_t)g.nl, 0);
     fs.hs_first = 0;
@@ -227,7 +232,6 @@ void build_field_side(const cvs_params &p, const GeomPlan &g, RandCursor &cur, F
         for (int r = 0; r < g.nl; r++)
             if ((c.next() % 100000U) < (unsigned)p.video_chroma_loss) fs.rowinfo[(size_t)r] |= (uint32_t)RF_DROPOUT << 16;
     }
-    cur.jump(g.jumpN, g.ndraws);
 }
 
 }  // namespace cvs

@@ -47,6 +47,9 @@ void build_geom_plan(const cvs_params &p, int w, int h, unsigned field, GeomPlan
 
 // `cur` must sit at the field's first draw; on return it sits at the next field's first draw.
 void build_field_side(const cvs_params &p, const GeomPlan &g, RandCursor &cur, FieldSide &fs);
+// The same without moving the cursor (for planning several fields of a batch on several host threads:
+// the caller advances a cursor of its own by g.jumpN per field and hands out copies).
+void build_field_side_at(const cvs_params &p, const GeomPlan &g, const RandCursor &at, FieldSide &fs);
 
 // exact n % m for n < 2^31: q = umulhi(n, magic) >> shift
 void mod_magic(uint32_t m, uint32_t &magic, uint32_t &shift);

@@ -31,6 +31,10 @@ constexpr int kWarpsPerCta = kNT / 32;
 #ifndef CVS_MIN_CTAS
 #define CVS_MIN_CTAS 3              // CTAs per SM the register allocator must leave room for (168 registers)
 #endif
+#ifndef CVS_FAST_UNROLL
+#define CVS_FAST_UNROLL 1
+#endif
+constexpr int kFastUnroll = CVS_FAST_UNROLL;   // unroll factor of the interior loop (experiments)
 constexpr int kRowsPerWarp = 31;         // lane 0 is the halo row of the vertical chroma blend
 
 struct FieldDesc {
@@ -299,7 +303,7 @@ __global__ void __launch_bounds__(kNT, (sizeof(R) == 4 ? CVS_MIN_CTAS : 1)) k_fi
             for (int j = 0; j < kT; j++) px[j] = pxn[j];
         }
         if (pass == 0) {
-#pragma unroll 1
+#pragma unroll(kFastUnroll)
             for (; s < s_hi; s++) {
                 uint32_t pxn[kT];
                 load_block_fast(srow, s + 1, vec_src, pxn);          // interior: always in range
