@@ -41,7 +41,15 @@ struct Staging {
     uint32_t *h_rowinfo = nullptr;
     int32_t *h_hsshift = nullptr;
     HsItem *h_items = nullptr;
-    cudaEvent_t consumed = nullptr;    // the H2D copies that read this slot have finished
+    // device copies of the same tables: one set per slot, uploaded on the table stream while the previous
+    // batch is still computing (with a single set the upload had to queue behind the previous kernel and
+    // left the GPU idle for ~0.1 ms per batch)
+    FieldDesc *d_fields = nullptr;
+    uint32_t *d_rowinfo = nullptr;
+    int32_t *d_hsshift = nullptr;
+    HsItem *d_items = nullptr;
+    cudaEvent_t consumed = nullptr;    // the H2D copies that read this slot have finished (= tables ready)
+    cudaEvent_t kernel_done = nullptr; // the kernels that read this slot's device tables have finished
     bool in_flight = false;
 };
 
@@ -71,12 +79,8 @@ struct cvs_ctx {
     std::vector<std::unique_ptr<DevPlan>> plans;
     Staging slots[kStagingSlots];
     int next_slot = 0;
-    // device side tables (single copy: all writers/readers are ordered on `stream`)
-    FieldDesc *d_fields = nullptr;
-    uint32_t *d_rowinfo = nullptr;
-    int32_t *d_hsshift = nullptr;
-    HsItem *d_items = nullptr;
-    int32_t *d_scratch = nullptr;
+    cudaStream_t s_tab = nullptr;              // uploads the per-batch side tables
+    int32_t *d_scratch = nullptr;              // head-switch pre-pass rows (written and read on `stream`)
     int32_t *d_status = nullptr;
     int32_t *h_status = nullptr;               // pinned
     float *d_lut_f = nullptr;
@@ -120,9 +124,11 @@ void free_all(cvs_ctx *c) {
         if (s.h_hsshift) cudaFreeHost(s.h_hsshift);
         if (s.h_items) cudaFreeHost(s.h_items);
         if (s.consumed) cudaEventDestroy(s.consumed);
+        if (s.kernel_done) cudaEventDestroy(s.kernel_done);
+        cudaFree(s.d_fields); cudaFree(s.d_rowinfo); cudaFree(s.d_hsshift); cudaFree(s.d_items);
         s = Staging();
     }
-    cudaFree(c->d_fields); cudaFree(c->d_rowinfo); cudaFree(c->d_hsshift); cudaFree(c->d_items);
+    if (c->s_tab) cudaStreamDestroy(c->s_tab);
     cudaFree(c->d_scratch); cudaFree(c->d_status); cudaFree(c->d_lut_f); cudaFree(c->d_lut_d);
     for (int i = 0; i < 2; i++) { cudaFree(c->d_src[i]); cudaFree(c->d_dst[i]); if (c->host_call_done[i]) cudaEventDestroy(c->host_call_done[i]); }
     if (c->h_status) cudaFreeHost(c->h_status);
@@ -185,7 +191,7 @@ template <> float *&lut_ptr<float>(cvs_ctx *c) { return c->d_lut_f; }
 template <> double *&lut_ptr<double>(cvs_ctx *c) { return c->d_lut_d; }
 
 template <typename R>
-int launch_batch(cvs_ctx *c, const Variant &v, int w, int h, int nfields, int max_nl, int nitems,
+int launch_batch(cvs_ctx *c, const Staging &sl, const Variant &v, int w, int h, int nfields, int max_nl, int nitems,
                  int src_stride, int dst_stride, int opposite, bool vec_src, bool vec_dst) {
     LaunchArgs<R> a;
     std::vector<R> lut;
@@ -202,7 +208,7 @@ int launch_batch(cvs_ctx *c, const Variant &v, int w, int h, int nfields, int ma
         c->lut_dirty = false;
     }
     a.K.phase_lut = lut_ptr<R>(c);
-    a.fields = c->d_fields;
+    a.fields = sl.d_fields;
     a.nfields = nfields;
     a.warps_per_field = (max_nl + kRowsPerWarp - 1) / kRowsPerWarp;
     a.total_warps = a.warps_per_field * nfields;
@@ -214,7 +220,7 @@ int launch_batch(cvs_ctx *c, const Variant &v, int w, int h, int nfields, int ma
     a.bob = c->bob;
     a.status = c->d_status;
     if (nitems > 0) {
-        CVS_CUDA(launch_headswitch<R>(a, c->d_items, nitems, c->stream));
+        CVS_CUDA(launch_headswitch<R>(a, sl.d_items, nitems, c->stream));
         c->launches++;
     }
     if (c->ev_used == c->ev_pool.size() && c->ev_pool.size() < kMaxEventPairs) {
@@ -278,9 +284,9 @@ int run_device(cvs_ctx *c, uint8_t *dst, size_t dst_pic_stride, int dst_stride, 
         fd.nl = pl->g.nl;
         if (fd.nl > max_nl) max_nl = fd.nl;
         fd.seek = pl->d_seek;
-        fd.rowinfo = c->d_rowinfo + (size_t)k * c->nl_max;
+        fd.rowinfo = sl.d_rowinfo + (size_t)k * c->nl_max;
         fd.hs_scratch = c->d_scratch + (size_t)k * c->hs_max * (size_t)c->max_w;
-        fd.hs_shift = c->d_hsshift + (size_t)k * c->hs_max;
+        fd.hs_shift = sl.d_hsshift + (size_t)k * c->hs_max;
     }
     bool capacity_error = false;
     auto plan_range = [&](int k0, int k1) {
@@ -319,20 +325,27 @@ int run_device(cvs_ctx *c, uint8_t *dst, size_t dst_pic_stride, int dst_stride, 
         }
     if (max_nl == 0) return CVS_OK;
 
-    CVS_CUDA(cudaMemcpyAsync(c->d_fields, sl.h_fields, (size_t)n * sizeof(FieldDesc), cudaMemcpyHostToDevice, c->stream));
-    CVS_CUDA(cudaMemcpyAsync(c->d_rowinfo, sl.h_rowinfo, (size_t)n * c->nl_max * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    // tables go up on their own stream, behind the kernels that last read this slot's device copies,
+    // and the compute stream picks them up through an event: the upload overlaps the previous batch
+    CVS_CUDA(cudaStreamWaitEvent(c->s_tab, sl.kernel_done, 0));
+    CVS_CUDA(cudaMemcpyAsync(sl.d_fields, sl.h_fields, (size_t)n * sizeof(FieldDesc), cudaMemcpyHostToDevice, c->s_tab));
+    CVS_CUDA(cudaMemcpyAsync(sl.d_rowinfo, sl.h_rowinfo, (size_t)n * c->nl_max * sizeof(uint32_t), cudaMemcpyHostToDevice, c->s_tab));
     if (nitems > 0) {
-        CVS_CUDA(cudaMemcpyAsync(c->d_hsshift, sl.h_hsshift, (size_t)n * c->hs_max * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-        CVS_CUDA(cudaMemcpyAsync(c->d_items, sl.h_items, (size_t)nitems * sizeof(HsItem), cudaMemcpyHostToDevice, c->stream));
+        CVS_CUDA(cudaMemcpyAsync(sl.d_hsshift, sl.h_hsshift, (size_t)n * c->hs_max * sizeof(int32_t), cudaMemcpyHostToDevice, c->s_tab));
+        CVS_CUDA(cudaMemcpyAsync(sl.d_items, sl.h_items, (size_t)nitems * sizeof(HsItem), cudaMemcpyHostToDevice, c->s_tab));
     }
-    CVS_CUDA(cudaEventRecord(sl.consumed, c->stream));
+    CVS_CUDA(cudaEventRecord(sl.consumed, c->s_tab));
     sl.in_flight = true;
+    CVS_CUDA(cudaStreamWaitEvent(c->stream, sl.consumed, 0));
 
     const bool vec_src = ((uintptr_t)src % 16 == 0) && (src_stride % 16 == 0) && (src_pic_stride % 16 == 0);
     const bool vec_dst = ((uintptr_t)dst % 16 == 0) && (dst_stride % 16 == 0) && (dst_pic_stride % 16 == 0);
-    if (c->precision)
-        return launch_batch<double>(c, v, w, h, n, max_nl, nitems, src_stride, dst_stride, opposite, vec_src, vec_dst);
-    return launch_batch<float>(c, v, w, h, n, max_nl, nitems, src_stride, dst_stride, opposite, vec_src, vec_dst);
+    const int rc = c->precision
+        ? launch_batch<double>(c, sl, v, w, h, n, max_nl, nitems, src_stride, dst_stride, opposite, vec_src, vec_dst)
+        : launch_batch<float>(c, sl, v, w, h, n, max_nl, nitems, src_stride, dst_stride, opposite, vec_src, vec_dst);
+    if (rc != CVS_OK) return rc;
+    CVS_CUDA(cudaEventRecord(sl.kernel_done, c->stream));
+    return CVS_OK;
 }
 
 int check_status(cvs_ctx *c) {
@@ -495,11 +508,13 @@ int cvs_create(cvs_ctx **out, const cvs_params *p, int device, int max_w, int ma
         if (e == cudaSuccess) e = pin_alloc(&s.h_hsshift, (size_t)max_batch * c->hs_max);
         if (e == cudaSuccess) e = pin_alloc(&s.h_items, (size_t)max_batch * c->hs_max);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.kernel_done, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = dev_alloc(&s.d_fields, (size_t)max_batch);
+        if (e == cudaSuccess) e = dev_alloc(&s.d_rowinfo, (size_t)max_batch * c->nl_max);
+        if (e == cudaSuccess) e = dev_alloc(&s.d_hsshift, (size_t)max_batch * c->hs_max);
+        if (e == cudaSuccess) e = dev_alloc(&s.d_items, (size_t)max_batch * c->hs_max);
     }
-    if (e == cudaSuccess) e = dev_alloc(&c->d_fields, (size_t)max_batch);
-    if (e == cudaSuccess) e = dev_alloc(&c->d_rowinfo, (size_t)max_batch * c->nl_max);
-    if (e == cudaSuccess) e = dev_alloc(&c->d_hsshift, (size_t)max_batch * c->hs_max);
-    if (e == cudaSuccess) e = dev_alloc(&c->d_items, (size_t)max_batch * c->hs_max);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_tab, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = dev_alloc(&c->d_scratch, (size_t)max_batch * c->hs_max * (size_t)max_w);
     if (e == cudaSuccess) e = dev_alloc(&c->d_status, 1);
     if (e == cudaSuccess) e = pin_alloc(&c->h_status, 1);
