@@ -169,8 +169,12 @@ def run_reference_arm(args):
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores) as pool:
         kind = "reference"
-        for _ in range(args.warmup):
+        t_w = time.perf_counter()
+        for _ in range(max(1, args.warmup)):
             pool.map(_ref_worker, [(1, 0)] * cores)
+        t_field = (time.perf_counter() - t_w) / max(1, args.warmup)      # one field per process, all cores busy
+        # bounded sample: keep the K timed steps within about two minutes of CPU wall time
+        per_proc = max(1, min(per_proc, int(120.0 / (max(1, args.steps) * max(t_field, 1e-3)))))
         t0 = time.perf_counter()
         for s in range(args.steps):
             res = pool.map(_ref_worker, [(per_proc, s * per_proc)] * cores)
