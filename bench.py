@@ -401,7 +401,7 @@ def main():
     ap.add_argument("--batch", type=int, default=320, help="upper bound of fields per GPU per step (device-resident)")
     ap.add_argument("--no-wave-align", dest="wave_align", action="store_false",
                     help="use --batch as is instead of the wave-aligned batch cvs_preferred_batch() suggests")
-    ap.add_argument("--e2e-batch", type=int, default=256, help="fields per GPU per step (host buffers)")
+    ap.add_argument("--e2e-batch", type=int, default=128, help="fields per GPU per step (host buffers; 4 pinned buffers of this many pictures per rank)")
     ap.add_argument("--cpu-fields", type=int, default=64, help="fields of the single-thread CPU baseline sample")
     ap.add_argument("--ref-fields-per-proc", type=int, default=4)
     ap.add_argument("--width", type=int, default=1920, help="experiments only: the headline metric is 1920x1080")
@@ -417,7 +417,13 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         return run_reference_arm(args)
-    return run_own_arm(args)
+    try:
+        return run_own_arm(args)
+    except BaseException:
+        import traceback
+        sys.stderr.write("bench.py rank %s failed:\n%s\n" % (os.environ.get("RANK", "0"), traceback.format_exc()))
+        sys.stderr.flush()
+        raise
 
 
 if __name__ == "__main__":
