@@ -193,7 +193,7 @@ def run_reference_arm(args):
         "e2e": {"value": val, "unit": "fields/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -386,13 +386,34 @@ def run_own_arm(args):
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms_per_launch": kernel_ms},
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """Exactly ONE line may reach stdout (the JSON result).  Libraries print there too (NCCL's version
+    banner does), so file descriptor 1 is pointed at stderr for the whole run and the result line is
+    written to the saved descriptor at the end."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
