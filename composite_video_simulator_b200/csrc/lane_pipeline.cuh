@@ -6,30 +6,31 @@
 // leaves registers between the BGRA load and the BGRA store (8 algorithmic bytes/pixel).
 //
 // Mapping: a warp owns 32 consecutive field rows (lane 0 is a halo row for
-// the vertical chroma blend), all lanes advance through x in lock-step in blocks of 8
+// the vertical chroma blend), all lanes advance through x in lock-step in blocks of kT (4 or 8)
 // pixels, so every x-dependent condition (line start/end quirks) is warp-uniform, the
 // vertical blend (ffmpeg_ntsc.cpp:1843-1863) is one __shfl_up per value, and the one-pole
 // IIR cascades run in the reference's own sequential order (no re-association).  Stage
 // look-ahead (QAM demodulation needs C[x+7], the VHS chroma delay is 9..14 samples, ...)
-// is absorbed by running later stages on older 8-pixel blocks; all block lags are
-// compile-time so every delay line is a statically indexed register array.
+// is absorbed by running later stages on older blocks; all block lags are compile-time
+// so every delay line is a statically indexed register array.
 //
 // The file is host/device portable on purpose: tests/ compile it with g++ and run all 32
 // lanes of a warp in lock-step on the CPU (tests/emu_harness.cpp), where R = double gives
 // the reference's arithmetic bit for bit and R = float is the production arithmetic.
 //
-// Timeline (T = 8 px per step; B(k) = pixels [8k, 8k+8); s = step):
-//   load  B(s)          BGRA block (prefetched one step ahead)
-//   A1    B(s)          RGB->YIQ, input chroma lowpass cascades          (:1375, :1429)
-//   A2    B(s-1)        composite C = Y + QAM(I',Q'), pre-emphasis, luma noise (:1460,:1613,:1631)
-//   HS    B(s-1)        head-switch rows take C from the pre-shifted scratch row (:1646)
-//   B     B(s-2)        Y/C separation + demod, chroma noise, phase noise (:1497,:1718,:1736)
-//         VHS:          luma lowpass+HF boost, sharpen -> Y3 B(s-2); chroma lowpass (:1793-1883)
-//   B2    B(s-4)        (VHS) delayed chroma block complete -> vertical blend -> remodulate C2
-//   C     B(s-5)        (VHS) second demod                                (:1885-1888)
-//   F     B(k)          dropout, output chroma lowpass, YIQ->RGB          (:1891-1916)
-//                       k = s-5 (VHS) / s-4 (VHS s-video) / s-2 (composite only)
-//   store B(k-1)
+// Timeline of step s (B(k) = pixels [kT k, kT k + kT); kLB = ceil(7/kT) blocks of demodulation
+// look-ahead, LD = ceil(chroma delay/kT); in brackets the block for kT = 8 / kT = 4 with delay 9):
+//   load  B(s)                BGRA block (prefetched one step ahead)
+//   A1    B(s)                RGB->YIQ, input chroma lowpass cascades             (:1375, :1429)
+//   A2    B(s-1)              composite C = Y + QAM(I',Q'), pre-emphasis, luma noise (:1460,:1613,:1631)
+//   HS    B(s-1)              head switch: per-lane delay ring, or the pre-shifted scratch row (:1646)
+//   B     B(kB), kB = s-1-kLB [s-2 / s-3]   Y/C separation + demod, chroma noise, phase noise (:1497,:1718,:1736)
+//         VHS:                luma lowpass+HF boost, sharpen -> Y3 B(kB); chroma lowpass      (:1793-1883)
+//   B2    B(kD), kD = kB-LD   [s-4 / s-6]   (VHS) delayed chroma block complete -> vertical blend -> remodulate C2
+//   C     B(kC), kC = kD-kLB  [s-5 / s-8]   (VHS) second demod                               (:1885-1888)
+//   F     B(kf)               dropout, output chroma lowpass, YIQ->RGB             (:1891-1916)
+//                             kf = kC (VHS) / kD (VHS s-video) / kB (composite only)
+//   store B(kf-1)
 #ifndef CVS_LANE_PIPELINE_CUH
 #define CVS_LANE_PIPELINE_CUH
 

