@@ -149,3 +149,91 @@ def channel_diff(a, b):
     """(max |delta|, #values differing, #values differing by > 1) over the 8-bit channels."""
     d = np.abs(a.view(np.uint8).astype(np.int16) - b.view(np.uint8).astype(np.int16))
     return int(d.max()) if d.size else 0, int((d > 0).sum()), int((d > 1).sum())
+
+
+# ---- the 4:2:2 sibling path (include/cvs_yuv422.h) ----------------------------------------------
+
+def load_oracle422():
+    path = os.path.join(ORACLE_DIR, "libyuv422oracle.so")
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("yuv422_oracle.c", "yuv422_oracle.h", "ntsc_oracle.c")]
+    if not os.path.exists(path) or os.path.getmtime(path) < max(os.path.getmtime(s) for s in srcs):
+        subprocess.check_call(["make", "libyuv422oracle.so"], cwd=ORACLE_DIR, stdout=subprocess.DEVNULL)
+    lib = C.CDLL(path)
+    lib.oracle422_draws_per_field.restype = C.c_ulonglong
+    return lib
+
+
+def load_ref422():
+    """The reference's own composite_video_process() / render_field(), extracted at build time."""
+    path = os.path.join(ORACLE_DIR, "_ref", "libref422.so")
+    if not os.path.exists(path):
+        if os.path.exists("/root/reference/ffmpeg_to_composite.cpp"):
+            subprocess.check_call(["make", "ref"], cwd=ORACLE_DIR, stdout=subprocess.DEVNULL)
+        else:
+            return None
+    return C.CDLL(path)
+
+
+def params422(*argv):
+    from composite_video_simulator_b200 import yuv422
+    return yuv422.params_from_argv(list(argv))
+
+
+def yuv422_frame(w, h, k, pad=0):
+    """Synthetic 4:2:2 picture k: (Y[h, w+pad], U[h, w/2+pad], V[h, w/2+pad]) uint8.  Luma = bars rotated
+    by 7k px with a hash perturbation, chroma = saturated bars + perturbation; the pad columns hold a
+    recognisable pattern (the reference reads two luma bytes past each row)."""
+    x = np.arange(w + pad, dtype=np.uint32)[None, :]
+    y = np.arange(h, dtype=np.uint32)[:, None]
+    xs = (x + np.uint32(7 * k)) % np.uint32(max(w, 1))
+    bar = (xs * np.uint32(8)) // np.uint32(max(w, 1))
+    ylev = np.array([180, 162, 131, 112, 84, 65, 35, 16], dtype=np.uint32)
+    ulev = np.array([128, 44, 156, 72, 184, 100, 212, 128], dtype=np.uint32)
+    vlev = np.array([128, 142, 44, 58, 198, 212, 114, 128], dtype=np.uint32)
+    h1 = ((x * np.uint32(2654435761)) ^ (y * np.uint32(40503)) ^ np.uint32((k * 97) & 0xFFFFFFFF)) >> np.uint32(28)
+    Y = np.clip(ylev[bar] + h1, 0, 255).astype(np.uint8)
+    cw = w // 2
+    xc = np.arange(cw + pad, dtype=np.uint32)[None, :]
+    cbar = (((2 * xc + np.uint32(7 * k)) % np.uint32(max(w, 1))) * np.uint32(8)) // np.uint32(max(w, 1))
+    h2 = ((xc * np.uint32(2246822519)) ^ (y * np.uint32(3266489917)) ^ np.uint32((k * 131) & 0xFFFFFFFF)) >> np.uint32(29)
+    U = np.clip(ulev[cbar] + h2, 0, 255).astype(np.uint8)
+    V = np.clip(vlev[cbar] + (h2 ^ np.uint32(5)), 0, 255).astype(np.uint8)
+    return np.ascontiguousarray(Y), np.ascontiguousarray(U), np.ascontiguousarray(V)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def run_ref422(ref, p, w, h, n, pad=2, first=0, seed=1, frames=None):
+    """n fields through the reference's composite_video_process(); each field works on a fresh picture
+    (frame k); returns the list of (Y, U, V) after processing."""
+    ref.ref422_set_params(C.byref(p))
+    ref.ref422_srand(seed)
+    out = []
+    for k in range(first, first + n):
+        Y, U, V = (frames(k) if frames else yuv422_frame(w, h, k, pad))
+        # slack after the last row: the reference reads 2 bytes past it
+        Yb = np.zeros(Y.size + 16, dtype=np.uint8)
+        Yb[:Y.size] = Y.ravel()
+        ref.ref422_composite_video_process(_ptr(Yb), C.c_int(Y.shape[1]), _ptr(U), C.c_int(U.shape[1]),
+                                           _ptr(V), C.c_int(V.shape[1]), C.c_int(w), C.c_int(h),
+                                           C.c_uint((k & 1) ^ 1), C.c_ulonglong(k))
+        out.append((Yb[:Y.size].reshape(Y.shape).copy(), U, V))
+    return out
+
+
+def run_oracle422(orc, p, w, h, n, pad=2, first=0, frames=None, rng=None):
+    g = rng
+    if g is None:
+        g = OracleRng()
+        orc.oracle_rng_seed(C.byref(g), 1)
+    out = []
+    for k in range(first, first + n):
+        Y, U, V = (frames(k) if frames else yuv422_frame(w, h, k, pad))
+        rc = orc.oracle422_composite_video_process(C.byref(p), C.byref(g), _ptr(Y), C.c_int(Y.shape[1]),
+                                                   _ptr(U), C.c_int(U.shape[1]), _ptr(V), C.c_int(V.shape[1]),
+                                                   C.c_int(w), C.c_int(h), C.c_uint((k & 1) ^ 1), C.c_ulonglong(k))
+        assert rc == 0
+        out.append((Y, U, V))
+    return out, g
