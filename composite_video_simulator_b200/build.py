@@ -4,6 +4,7 @@
 ``build_oracle()``   gcc  -> oracle/liboracle.so, and oracle/_ref/libref.so when the reference
                      tree is present (test infrastructure only)
 ``build_emu()``      g++  -> tests/_build/libemu.so (CPU emulation of the lane pipeline; tests only)
+``build_emu422()``   g++  -> tests/_build/libemu422.so (the same for the 4:2:2 pipeline)
 """
 import os
 import subprocess
@@ -39,6 +40,21 @@ def build_emu(extra=()):
     if os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
         return out
     _run(["g++", "-O1", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared"] + list(extra) + ["-o", out] + srcs, ROOT)
+    return out
+
+
+def build_emu422():
+    """CPU emulation of the 4:2:2 lane pipeline (tests only)."""
+    out_dir = os.path.join(ROOT, "tests", "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    out = os.path.join(out_dir, "libemu422.so")
+    srcs = [os.path.join(ROOT, "tests", "emu422_harness.cpp")] + [
+        os.path.join(CSRC, f) for f in ("yuv422_plan.cpp", "field_plan.cpp", "glibc_rand.cpp")]
+    deps = srcs + [os.path.join(CSRC, f) for f in ("yuv422_pipeline.cuh", "yuv422_plan.h", "lane_pipeline.cuh",
+                                                   "field_plan.h", "glibc_rand.h")]
+    if os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
+        return out
+    _run(["g++", "-O1", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-o", out] + srcs, ROOT)
     return out
 
 

@@ -1,0 +1,656 @@
+// yuv422_pipeline.cuh -- the reference's 4:2:2 scanline path, composite_video_process()
+// (ffmpeg_to_composite.cpp:629-952), as a per-lane streaming pipeline.
+//
+// Same mapping as lane_pipeline.cuh: one lane owns one field scanline, a warp owns 31 consecutive rows
+// plus a halo lane for the vertical chroma blend, all lanes advance through x in lock-step, 8 luma
+// pixels (4 chroma samples) per step.  What differs is the arithmetic domain: this path quantises to
+// 8 bits after EVERY stage (clampu8, :335-342) and works in place on the picture, so the stages
+// communicate through small per-lane byte rings in shared memory that play the role of the reference's
+// in-place planes -- including its quirks (the last `delay` samples of a delayed filter keep their
+// unfiltered values because nobody overwrites them).  A stage with look-ahead or write delay simply runs
+// on an older block; block lags are launch constants (K422::lag_*).
+//
+// Arithmetic: the reference's filters are IEEE doubles and their results are truncated to 8 bits, so a
+// cheaper float evaluation would flip visible LSBs.  B200 runs FP64 at half the FP32 rate, which this
+// path can afford (~110 FP64 operations per pixel): every filter is evaluated in double, in the
+// reference's operation order, and the output is BIT-EXACT.  The two XU-pipe conversions per stage are
+// avoided: u8 -> double is an exponent splice, double -> u8 is one directed-rounding add.
+//
+// Host/device portable like lane_pipeline.cuh: tests/emu422_harness.cpp runs the same code on the CPU.
+//
+// Step s (blocks of 8 px; bM = s-1, bD = s-2, bV = bD - lagV, ...):
+//   G0  B(s)      load Y,U,V block into the rings (and the two luma bytes past the row, :496)
+//   G1  B(s)      input chroma lowpass, written at c-2 (U) / c-4 (V)                         (:353-393)
+//   G2  B(s-1)    modulate chroma onto luma, pre-emphasis, luma noise, head-switch delay     (:434-477,:636-733)
+//   G3  B(s-2)    Y/C separation + demodulation, chroma noise, phase noise;                  (:480-553,:738-783)
+//                 VHS: luma lowpass + boost, luma sharpen, chroma lowpass written at c-cd    (:810-851,:888-901)
+//   G4  B(bV)     VHS: vertical chroma blend (lane above via shuffle), chroma sharpen,       (:858-925)
+//                 re-modulation                                                              (:927-930)
+//   G5  B(bV-1)   VHS: second demodulation
+//   GE  B(bE)     chroma dropout, -yc-recomb rounds (one block of lag each)                  (:932-946)
+//   GO  B(bF)     output chroma lowpass (full or lite)                                       (:948-951)
+//   ST  B(bF-1)   store
+#ifndef CVS_YUV422_PIPELINE_CUH
+#define CVS_YUV422_PIPELINE_CUH
+
+#include "lane_pipeline.cuh"
+
+namespace cvs422 {
+
+using cvs::LaneRng;
+using cvs::draw_mod;
+using cvs::noise_step;
+using cvs::kRngBase;
+using cvs::kRngSlots;
+using cvs::umulhi32;
+
+constexpr int kB = 8;                    // luma pixels per block
+constexpr int kBC = 4;                   // chroma samples per block
+constexpr int kRingY = 128;              // per-lane luma ring (bytes, power of two)
+constexpr int kRingC = 64;               // per-lane chroma rings
+constexpr int kMaxRecombine = 4;         // -yc-recomb rounds the rings have room for
+constexpr int kHsMaxDelay = kRingY - 2 * kB;   // largest head-switch delay the composite ring can express
+constexpr int kWarm = 64;                // noise warm-up length (samples), see cvs::warm_luma
+
+enum : uint32_t {
+    G_IN_LP = 1u << 0,        // composite_in_chroma_lowpass
+    G_OUT_FULL = 1u << 1,     // composite_out_chroma_lowpass
+    G_OUT_LITE = 1u << 2,     // !full && composite_out_chroma_lowpass_lite
+    G_PREEMPH = 1u << 3,
+    G_NOCOLOR = 1u << 4,      // nocolor_subcarrier
+    G_NOCOLOR_YC = 1u << 5,   // nocolor_subcarrier_after_yc_sep
+    G_VHS = 1u << 6,
+    G_VBLEND = 1u << 7,       // vhs_chroma_vert_blend && output_ntsc
+    G_SVIDEO = 1u << 8,
+    G_PHASE = 1u << 9,        // video_chroma_phase_noise != 0
+};
+
+// per-row flags in the host side table (same packing as cvs::rowinfo_pack)
+enum : uint32_t {
+    RG_DROPOUT = 1u << 0,
+    RG_HEADSW_PRE = 1u << 1,  // row is rotated by the head switch; its composite luma comes from the pre-pass scratch row
+    RG_HEADSW = 1u << 2,      // row is delayed by hs_delay pixels with fill 16 (:697-731): done in the ring
+};
+
+struct K422 {
+    double a_in[2], a_inhp[2];            // input lowpass poles / its boost highpass, [0] = U, [1] = V   (:377-383)
+    double a_out[2], a_outhp[2];          // output lowpass (full: as input; lite: rate/8, no boost)     (:412-416)
+    double a_pre, preemph;                // composite pre-emphasis                                       (:642-647)
+    double a_luma;                        // VHS luma lowpass and boost                                   (:817-821)
+    double a_lsharp, sharpen;             // VHS luma sharpen (2x luma cut)                               (:894-899)
+    double a_ch;                          // VHS chroma lowpass                                           (:837-841)
+    double a_csharp, sharpen_c;           // VHS chroma sharpen (2x chroma cut)                           (:910-921)
+    const double *phase_lut;              // [2*pnoise+1][2] = {cos, sin}(state*pi/100)                   (:765,:772-773)
+    uint32_t flags;
+    int32_t d_in[2], d_out[2];            // write delays of the input / output lowpass (samples)
+    int32_t cd;                           // VHS chroma delay 4 / 5 / 6                                   (:793-803)
+    int32_t amp, amp_back;                // subcarrier_amplitude, _back
+    int32_t vnoise, cnoise, pnoise;
+    uint32_t vmagic, vshift, cmagic, cshift;
+    int32_t ntsc, phase_shift, phase_offset;
+    int32_t recombine;                    // video_yc_recombine (<= kMaxRecombine)
+    int32_t lagV;                         // blocks between G3 and G4: 1 (cd = 4) or 2
+    int32_t w, h, cw;
+};
+
+// block lags of a configuration (blocks behind the load front)
+struct Lags {
+    int bM, bD, bV, bD2, bE, bF, bS;      // as offsets: block = s - lag
+};
+CVS_HD Lags lags_of(const K422 &K) {
+    Lags L;
+    L.bM = 1;
+    L.bD = 2;
+    L.bV = L.bD + K.lagV;
+    L.bD2 = L.bV + 1;
+    const bool vhs = (K.flags & G_VHS) != 0, sv = (K.flags & G_SVIDEO) != 0;
+    L.bE = vhs ? (sv ? L.bV : L.bD2) : L.bD;
+    L.bF = L.bE + K.recombine;
+    L.bS = L.bF + 1;
+    return L;
+}
+CVS_HD int line_steps(const K422 &K) {
+    const int nb = (K.w + 2 + kB - 1) / kB;          // blocks that carry data (incl. the two bytes past the row)
+    return nb + lags_of(K).bS + 1;
+}
+
+// ---- arithmetic ------------------------------------------------------------------------------------
+CVS_HD double dmul(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+CVS_HD double dadd(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+CVS_HD double dsub(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dsub_rn(a, b);
+#else
+    return a - b;
+#endif
+}
+// exact (double)v for 0 <= v < 2^31 without a conversion instruction: splice v into the mantissa of 2^52
+CVS_HD double u2d(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __dsub_rn(__hiloint2double(0x43300000, (int)v), 4503599627370496.0);
+#else
+    return (double)v;
+#endif
+}
+CVS_HD double i2d(int v) {               // small signed values (|v| < 2^31)
+#if defined(__CUDA_ARCH__)
+    return __dsub_rn(__hiloint2double(0x43300000, (int)((uint32_t)v ^ 0x80000000u)), 4503601774854144.0);   // 2^52 + 2^31
+#else
+    return (double)v;
+#endif
+}
+CVS_HD int clamp8(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
+// clampu8((int)s): truncation and floor agree once the result is clamped at 0, and floor is one
+// round-down add of 1.5 * 2^52 whose low word is the integer (|s| < 2^31)
+CVS_HD int q8(double s) {
+#if defined(__CUDA_ARCH__)
+    return clamp8(__double2loint(__dadd_rd(s, 6755399441055744.0)));
+#else
+    return clamp8((int)s);
+#endif
+}
+// LowpassFilter::lowpass (:114-118): prev = s*alpha + (prev - prev*alpha), three roundings
+CVS_HD double pole(double &p, double s, double a) {
+    const double t = dmul(s, a);
+    const double u = dsub(p, dmul(p, a));
+    p = dadd(t, u);
+    return p;
+}
+CVS_HD int div_trunc(int v, int den, uint32_t magic, uint32_t shift) {     // C '/' for |v| < 2^31, den > 0
+    const uint32_t a = (uint32_t)(v < 0 ? -v : v);
+    const uint32_t q = umulhi32(a, magic) >> shift;
+    (void)den;
+    return v < 0 ? -(int)q : (int)q;
+}
+CVS_HD int div50(int v) {                // exact for every 32-bit magnitude
+    const uint32_t a = (uint32_t)(v < 0 ? -v : v);
+    const uint32_t q = umulhi32(a, 0x51EB851Fu) >> 4;
+    return v < 0 ? -(int)q : (int)q;
+}
+
+// ---- per-row constants -------------------------------------------------------------------------------
+struct Row422 {
+    int xi;                // subcarrier phase index of the line (:449-459)
+    int row;               // field row index
+    uint32_t rflags;
+    int hs_delay;          // RG_HEADSW: Y[x] = Y[x - hs_delay], 16 for x < hs_delay
+    double cosp, sinp;     // phase noise rotation of this row
+};
+
+CVS_HD int line_phase(const K422 &K, unsigned long long fieldno, unsigned y) {
+    if (!K.ntsc) return (int)((fieldno + y) & 3);
+    if (K.phase_shift == 90) return (int)((fieldno + (unsigned long long)(long long)K.phase_offset + (y >> 1)) & 3);
+    if (K.phase_shift == 180) return (int)((((fieldno + y) & 2) + (unsigned long long)(long long)K.phase_offset) & 3);
+    if (K.phase_shift == 270) return (int)((fieldno + (unsigned long long)(long long)K.phase_offset - (y >> 1)) & 3);
+    return 0;
+}
+
+CVS_HD void row_setup(const K422 &K, unsigned field, unsigned long long fieldno, int row, uint32_t rowinfo, Row422 &rc) {
+    rc.row = row;
+    rc.rflags = (rowinfo >> 16) & 0xFFu;
+    rc.hs_delay = (rc.rflags & RG_HEADSW) ? (int)(rowinfo >> 24) : 0;
+    rc.xi = line_phase(K, fieldno, field + 2u * (unsigned)row);
+    if (K.flags & G_PHASE) {
+        const int st = (int)(int16_t)(rowinfo & 0xFFFFu);
+        rc.cosp = K.phase_lut[2 * (st + K.pnoise)];
+        rc.sinp = K.phase_lut[2 * (st + K.pnoise) + 1];
+    } else {
+        rc.cosp = 1;
+        rc.sinp = 0;
+    }
+}
+
+// ---- per-lane state -----------------------------------------------------------------------------------
+struct Demod {               // the three luma samples before x+2 of the 4-tap box (:487-499)
+    int o1, o2, o3;
+    CVS_HD void reset(int y0, int y1) { o1 = 16; o2 = y0; o3 = y1; }
+};
+
+struct Lane422 {
+    double inU[4], inV[4];   // [0] boost highpass, [1..3] lowpass
+    double pre;
+    double lum[4];           // three lowpass poles + boost
+    double lsh[3];
+    double chU[3], chV[3];
+    double csU[3], csV[3];
+    double outU[4], outV[4];
+    Demod dm1, dm2;
+    int nY, nU, nV;
+    LaneRng rngL, rngC;
+    uint8_t *ry, *ru, *rv, *rya;     // lane-private rings (kRingY / kRingC / kRingC / kRingY bytes)
+    int32_t *rcomb;                  // 3 ints per -yc-recomb round (lane-private, 3 * kMaxRecombine ints)
+
+    CVS_HD void reset() {
+        for (int i = 0; i < 4; i++) { inU[i] = inV[i] = 128; outU[i] = outV[i] = 128; lum[i] = 16; }
+        for (int i = 0; i < 3; i++) { lsh[i] = 16; chU[i] = chV[i] = 128; csU[i] = csV[i] = 128; }
+        pre = 16;
+        nY = nU = nV = 0;
+        dm1.reset(16, 16);
+        dm2.reset(16, 16);
+    }
+};
+
+CVS_HD uint32_t pack4(int a, int b, int c, int d) {
+    return (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)c << 16) | ((uint32_t)d << 24);
+}
+CVS_HD int byte_of(uint32_t w, int k) { return (int)((w >> (8 * k)) & 0xFFu); }
+
+template <bool EDGE>
+struct Pipe422 {
+    static CVS_HD bool in(int x, int lim) { return !EDGE || x < lim; }
+
+    // composite_video_chroma_lowpass / _lite on one block of one plane: reads P[c], writes P[c - d]
+    static CVS_HD void chroma_lp_block(const K422 &K, uint8_t *ring, int b, double st[4], double a_lp, double a_hp,
+                                       bool boost, int d) {
+        const int c0 = b * kBC;
+        CVS_UNROLL
+        for (int k = 0; k < kBC; k++) {
+            const int c = c0 + k;
+            if (in(c, K.cw)) {
+                double s = u2d(ring[c & (kRingC - 1)]);
+                if (boost) {
+                    const double lpv = pole(st[0], s, a_hp);         // s += hp.highpass(s)
+                    s = dadd(s, dsub(s, lpv));
+                }
+                s = pole(st[1], s, a_lp);
+                s = pole(st[2], s, a_lp);
+                s = pole(st[3], s, a_lp);
+                if (!EDGE || c >= d) ring[(c - d) & (kRingC - 1)] = (uint8_t)q8(s);
+            }
+        }
+    }
+
+    // composite_video_yuv_to_ntsc on one block: Y += chroma / 50                     (:434-477)
+    static CVS_HD void modulate_px(const K422 &K, int xi, int j, int u, int v, int &y) {
+        const int ph = (xi + j) & 3;
+        int t = (ph & 1) ? (v - 128) : (u - 128);
+        int q;
+        if (K.amp == 50) q = t;
+        else q = div50(t * K.amp);
+        if (ph & 2) q = -q;
+        y = clamp8(y + q);
+    }
+
+    // G2: block b of the composite signal
+    static CVS_HD void stage_compose(const K422 &K, const Row422 &rc, Lane422 &ln, int b, bool warp_hs,
+                                     const uint8_t *hsrow) {
+        const int x0 = b * kB, c0 = b * kBC;
+        uint32_t *grp = nullptr, *grp_next = nullptr;
+        if (K.vnoise != 0) {
+            grp = ln.rngL.group_ptr(kRngBase + (uint32_t)x0);
+            grp_next = ln.rngL.group_ptr(kRngBase + (uint32_t)x0 + kB);
+        }
+        CVS_UNROLL
+        for (int j = 0; j < kB; j++) {
+            const int x = x0 + j, c = c0 + (j >> 1);
+            if (in(x, K.w)) {
+                const int u = ln.ru[c & (kRingC - 1)], v = ln.rv[c & (kRingC - 1)];
+                int y = ln.ry[x & (kRingY - 1)];
+                modulate_px(K, rc.xi, j, u, v, y);
+                if ((j & 1) && (K.flags & G_NOCOLOR)) ln.ru[c & (kRingC - 1)] = ln.rv[c & (kRingC - 1)] = 128;
+                if (K.flags & G_PREEMPH) {                                     // (:636-650)
+                    double s = u2d((uint32_t)y);
+                    const double lpv = pole(ln.pre, s, K.a_pre);
+                    s = dadd(s, dmul(dsub(s, lpv), K.preemph));
+                    y = q8(s);
+                }
+                if (K.vnoise != 0) {                                           // (:653-665)
+                    y = clamp8(y + ln.nY);
+                    const int d = draw_mod(ln.rngL.next_in_group(grp, grp_next, j, kB), (uint32_t)(2 * K.vnoise + 1), K.vmagic, K.vshift);
+                    ln.nY = noise_step(ln.nY, d, K.vnoise);
+                }
+                if (warp_hs) {                                                 // (:697-731) as a delay line
+                    ln.rya[x & (kRingY - 1)] = (uint8_t)y;
+                    if (rc.hs_delay > 0) y = (x >= rc.hs_delay) ? ln.rya[(x - rc.hs_delay) & (kRingY - 1)] : 16;
+                }
+                if (hsrow) y = hsrow[x];                                       // rotated row from the pre-pass
+                ln.ry[x & (kRingY - 1)] = (uint8_t)y;
+            }
+        }
+    }
+
+    // re-modulation of a block whose luma is already final in the ring (VHS recombine, -yc-recomb)
+    static CVS_HD void stage_remodulate(const K422 &K, const Row422 &rc, Lane422 &ln, int b) {
+        const int x0 = b * kB, c0 = b * kBC;
+        CVS_UNROLL
+        for (int j = 0; j < kB; j++) {
+            const int x = x0 + j, c = c0 + (j >> 1);
+            if (in(x, K.w)) {
+                const int u = ln.ru[c & (kRingC - 1)], v = ln.rv[c & (kRingC - 1)];
+                int y = ln.ry[x & (kRingY - 1)];
+                modulate_px(K, rc.xi, j, u, v, y);
+                if ((j & 1) && (K.flags & G_NOCOLOR)) ln.ru[c & (kRingC - 1)] = ln.rv[c & (kRingC - 1)] = 128;
+                ln.ry[x & (kRingY - 1)] = (uint8_t)y;
+            }
+        }
+    }
+
+    // composite_ntsc_to_yuv on one block (:480-553): box-filtered luma back into the ring, demodulated
+    // chroma returned in U[], V[] (the caller continues with them)
+    static CVS_HD void demod_block(const K422 &K, const Row422 &rc, Lane422 &ln, Demod &dm, int b, int divisor,
+                                   uint32_t dmagic, uint32_t dshift, int U[kBC], int V[kBC]) {
+        const int x0 = b * kB;
+        int ch[kB];
+        if (EDGE && b == 0) dm.reset(ln.ry[0], ln.ry[1]);
+        const int xflip0 = ((4 - rc.xi) & 3) + 2;          // first flipped index (:527)
+        CVS_UNROLL
+        for (int j = 0; j < kB; j++) {
+            const int x = x0 + j;
+            ch[j] = 128;
+            if (in(x, K.w)) {
+                const int c = ln.ry[(x + 2) & (kRingY - 1)];
+                const int sum = dm.o1 + dm.o2 + dm.o3 + c;
+                dm.o1 = dm.o2; dm.o2 = dm.o3; dm.o3 = c;
+                const int yn = sum >> 2;
+                int cv = clamp8(c + 128 - yn);
+                if (K.flags & G_NOCOLOR_YC) {
+                    ln.ry[x & (kRingY - 1)] = (uint8_t)cv;
+                } else {
+                    ln.ry[x & (kRingY - 1)] = (uint8_t)yn;
+                    const bool flip = (((j + rc.xi + 2) & 3) < 2) && (!EDGE || x >= xflip0);
+                    if (flip) cv = 255 - cv;
+                    if (divisor != 50) cv = clamp8(div_trunc((cv - 128) * 50, divisor, dmagic, dshift) + 128);
+                }
+                ch[j] = cv;
+            }
+        }
+        const int odd = rc.xi & 1;
+        CVS_UNROLL
+        for (int k = 0; k < kBC; k++) {
+            if (K.flags & G_NOCOLOR_YC) { U[k] = 128; V[k] = 128; }
+            else {
+                const int a = 255 - ch[2 * k], bq = 255 - ch[2 * k + 1];
+                U[k] = odd ? bq : a;
+                V[k] = odd ? a : bq;
+            }
+        }
+    }
+
+    // G3: first demodulation of block b and everything pointwise after it
+    static CVS_HD void stage_separate(const K422 &K, const Row422 &rc, Lane422 &ln, int b,
+                                      uint32_t amag, uint32_t ashift) {
+        const int x0 = b * kB, c0 = b * kBC;
+        int U[kBC], V[kBC];
+        if (!(K.flags & G_NOCOLOR)) {
+            demod_block(K, rc, ln, ln.dm1, b, K.amp_back, amag, ashift, U, V);
+        } else {
+            CVS_UNROLL
+            for (int k = 0; k < kBC; k++) { U[k] = ln.ru[(c0 + k) & (kRingC - 1)]; V[k] = ln.rv[(c0 + k) & (kRingC - 1)]; }
+        }
+        if (K.cnoise != 0) {                                                   // (:738-754)
+            uint32_t *grp = ln.rngC.group_ptr(kRngBase + (uint32_t)(2 * c0));
+            uint32_t *grp_next = ln.rngC.group_ptr(kRngBase + (uint32_t)(2 * c0) + 2 * kBC);
+            CVS_UNROLL
+            for (int k = 0; k < kBC; k++) {
+                if (in(c0 + k, K.cw)) {
+                    U[k] = clamp8(U[k] + ln.nU);
+                    V[k] = clamp8(V[k] + ln.nV);
+                    const int du = draw_mod(ln.rngC.next_in_group(grp, grp_next, 2 * k, 2 * kBC), (uint32_t)(2 * K.cnoise + 1), K.cmagic, K.cshift);
+                    ln.nU = noise_step(ln.nU, du, K.cnoise);
+                    const int dv = draw_mod(ln.rngC.next_in_group(grp, grp_next, 2 * k + 1, 2 * kBC), (uint32_t)(2 * K.cnoise + 1), K.cmagic, K.cshift);
+                    ln.nV = noise_step(ln.nV, dv, K.cnoise);
+                }
+            }
+        }
+        if (K.flags & G_PHASE) {                                               // (:755-783), rotation as written there
+            CVS_UNROLL
+            for (int k = 0; k < kBC; k++) {
+                const double u = i2d(U[k] - 128), v = i2d(V[k] - 128);
+                const double u_ = dsub(dmul(u, rc.cosp), dmul(u, rc.sinp));
+                const double v_ = dadd(dmul(v, rc.cosp), dmul(v, rc.sinp));
+                U[k] = q8(dadd(u_, 128.0));
+                V[k] = q8(dadd(v_, 128.0));
+            }
+        }
+        // the unfiltered values stay in the ring: a delayed filter never overwrites the last `delay` samples
+        CVS_UNROLL
+        for (int k = 0; k < kBC; k++) {
+            if (in(c0 + k, K.cw)) {
+                ln.ru[(c0 + k) & (kRingC - 1)] = (uint8_t)U[k];
+                ln.rv[(c0 + k) & (kRingC - 1)] = (uint8_t)V[k];
+            }
+        }
+        if (K.flags & G_VHS) {
+            CVS_UNROLL
+            for (int j = 0; j < kB; j++) {                                     // luma lowpass + boost, then sharpen
+                const int x = x0 + j;
+                if (in(x, K.w)) {
+                    double s = u2d(ln.ry[x & (kRingY - 1)]);
+                    s = pole(ln.lum[0], s, K.a_luma);
+                    s = pole(ln.lum[1], s, K.a_luma);
+                    s = pole(ln.lum[2], s, K.a_luma);
+                    const double lpv = pole(ln.lum[3], s, K.a_luma);
+                    s = dadd(s, dmul(dsub(s, lpv), 1.6));
+                    const double y1 = u2d((uint32_t)q8(s));
+                    double ts = pole(ln.lsh[0], y1, K.a_lsharp);
+                    ts = pole(ln.lsh[1], ts, K.a_lsharp);
+                    ts = pole(ln.lsh[2], ts, K.a_lsharp);
+                    ln.ry[x & (kRingY - 1)] = (uint8_t)q8(dadd(y1, dmul(dsub(y1, ts), K.sharpen)));
+                }
+            }
+            CVS_UNROLL
+            for (int k = 0; k < kBC; k++) {                                    // chroma lowpass, written cd samples back
+                const int c = c0 + k;
+                if (in(c, K.cw)) {
+                    double s = u2d((uint32_t)U[k]);
+                    s = pole(ln.chU[0], s, K.a_ch); s = pole(ln.chU[1], s, K.a_ch); s = pole(ln.chU[2], s, K.a_ch);
+                    if (!EDGE || c >= K.cd) ln.ru[(c - K.cd) & (kRingC - 1)] = (uint8_t)q8(s);
+                    s = u2d((uint32_t)V[k]);
+                    s = pole(ln.chV[0], s, K.a_ch); s = pole(ln.chV[1], s, K.a_ch); s = pole(ln.chV[2], s, K.a_ch);
+                    if (!EDGE || c >= K.cd) ln.rv[(c - K.cd) & (kRingC - 1)] = (uint8_t)q8(s);
+                }
+            }
+        }
+    }
+
+    // G4 part 1: the lane's own chroma of block b before the vertical blend (what the lane below needs)
+    static CVS_HD void blend_fetch(const Lane422 &ln, int b, uint32_t &pu, uint32_t &pv) {
+        const int c0 = b * kBC;
+        pu = pack4(ln.ru[c0 & (kRingC - 1)], ln.ru[(c0 + 1) & (kRingC - 1)], ln.ru[(c0 + 2) & (kRingC - 1)], ln.ru[(c0 + 3) & (kRingC - 1)]);
+        pv = pack4(ln.rv[c0 & (kRingC - 1)], ln.rv[(c0 + 1) & (kRingC - 1)], ln.rv[(c0 + 2) & (kRingC - 1)], ln.rv[(c0 + 3) & (kRingC - 1)]);
+    }
+    // G4 part 2: blend with the row above (:858-883), chroma sharpen (:904-925), re-modulate (:927-930)
+    static CVS_HD void stage_vhs_chroma(const K422 &K, const Row422 &rc, Lane422 &ln, int b, uint32_t pu, uint32_t pv,
+                                        uint32_t au, uint32_t av) {
+        const int c0 = b * kBC;
+        CVS_UNROLL
+        for (int k = 0; k < kBC; k++) {
+            const int c = c0 + k;
+            if (in(c, K.cw)) {
+                int u = byte_of(pu, k), v = byte_of(pv, k);
+                if ((K.flags & G_VBLEND) && rc.row >= 1) {
+                    // the delay line starts at 128 and row 0 never enters it
+                    const int ua = (rc.row == 1) ? 128 : byte_of(au, k), va = (rc.row == 1) ? 128 : byte_of(av, k);
+                    u = (ua + u + 1) >> 1;
+                    v = (va + v + 1) >> 1;
+                }
+                double s = u2d((uint32_t)u), ts;
+                ts = pole(ln.csU[0], s, K.a_csharp); ts = pole(ln.csU[1], ts, K.a_csharp); ts = pole(ln.csU[2], ts, K.a_csharp);
+                ln.ru[c & (kRingC - 1)] = (uint8_t)q8(dadd(s, dmul(dsub(s, ts), K.sharpen_c)));
+                s = u2d((uint32_t)v);
+                ts = pole(ln.csV[0], s, K.a_csharp); ts = pole(ln.csV[1], ts, K.a_csharp); ts = pole(ln.csV[2], ts, K.a_csharp);
+                ln.rv[c & (kRingC - 1)] = (uint8_t)q8(dadd(s, dmul(dsub(s, ts), K.sharpen_c)));
+            }
+        }
+        if (!(K.flags & G_SVIDEO)) stage_remodulate(K, rc, ln, b);
+    }
+
+    // a demodulation whose result goes straight back into the rings (VHS recombine, -yc-recomb)
+    static CVS_HD void stage_redemod(const K422 &K, const Row422 &rc, Lane422 &ln, Demod &dm, int b,
+                                     uint32_t amag, uint32_t ashift) {
+        const int c0 = b * kBC;
+        int U[kBC], V[kBC];
+        demod_block(K, rc, ln, dm, b, K.amp, amag, ashift, U, V);
+        CVS_UNROLL
+        for (int k = 0; k < kBC; k++) {
+            if (in(c0 + k, K.cw)) {
+                ln.ru[(c0 + k) & (kRingC - 1)] = (uint8_t)U[k];
+                ln.rv[(c0 + k) & (kRingC - 1)] = (uint8_t)V[k];
+            }
+        }
+    }
+
+    static CVS_HD void stage_dropout(const K422 &K, Lane422 &ln, int b) {       // (:932-941)
+        const int c0 = b * kBC;
+        CVS_UNROLL
+        for (int k = 0; k < kBC; k++)
+            if (in(c0 + k, K.cw)) ln.ru[(c0 + k) & (kRingC - 1)] = ln.rv[(c0 + k) & (kRingC - 1)] = 128;
+    }
+};
+
+// the division constants of the two demodulator gains (amp_back for the first, amp for the others)
+struct DivPair {
+    uint32_t back_magic, back_shift, amp_magic, amp_shift;
+};
+
+// What one step exchanges with its caller: block s of the source row comes in, the pre-blend chroma of
+// block bV goes to the lane below between front() and back(), block bS comes out.
+struct StepIO {
+    uint32_t y0, y1, u, v;        // in: block s (bytes beyond the data are don't-care); out: block bS
+};
+
+// G0..G3 (+ the fetch of G4).  `load` = block s carries data for this row.
+template <bool EDGE>
+CVS_HD void step_front(const K422 &K, const DivPair &dv, const Row422 &rc, Lane422 &ln, int s, const StepIO &in,
+                       bool warp_hs, const uint8_t *hsrow, uint32_t &pu, uint32_t &pv) {
+    typedef Pipe422<EDGE> P;
+    const Lags L = lags_of(K);
+    const int nb = (K.w + kB - 1) / kB;               // blocks with pixels
+    const int nbl = (K.w + 2 + kB - 1) / kB;          // blocks the ring must hold (two bytes past the row)
+    if (!EDGE || s < nbl) {
+        const int x0 = s * kB, c0 = s * kBC;
+        CVS_UNROLL
+        for (int j = 0; j < 4; j++) {
+            ln.ry[(x0 + j) & (kRingY - 1)] = (uint8_t)byte_of(in.y0, j);
+            ln.ry[(x0 + 4 + j) & (kRingY - 1)] = (uint8_t)byte_of(in.y1, j);
+            ln.ru[(c0 + j) & (kRingC - 1)] = (uint8_t)byte_of(in.u, j);
+            ln.rv[(c0 + j) & (kRingC - 1)] = (uint8_t)byte_of(in.v, j);
+        }
+    }
+    if ((K.flags & G_IN_LP) && (!EDGE || s < nb)) {
+        P::chroma_lp_block(K, ln.ru, s, ln.inU, K.a_in[0], K.a_inhp[0], true, K.d_in[0]);
+        P::chroma_lp_block(K, ln.rv, s, ln.inV, K.a_in[1], K.a_inhp[1], true, K.d_in[1]);
+    }
+    const int bM = s - L.bM;
+    if (!EDGE || (bM >= 0 && bM < nb)) P::stage_compose(K, rc, ln, bM, warp_hs, hsrow);
+    const int bD = s - L.bD;
+    if (!EDGE || (bD >= 0 && bD < nb)) P::stage_separate(K, rc, ln, bD, dv.back_magic, dv.back_shift);
+    pu = pv = 0;
+    if (K.flags & G_VHS) {
+        const int bV = s - L.bV;
+        if (!EDGE || (bV >= 0 && bV < nb)) P::blend_fetch(ln, bV, pu, pv);
+    }
+}
+
+// G4..store.  Returns true when `out` holds block *bs of the finished row.
+template <bool EDGE>
+CVS_HD bool step_back(const K422 &K, const DivPair &dv, const Row422 &rc, Lane422 &ln, int s,
+                      uint32_t pu, uint32_t pv, uint32_t au, uint32_t av, StepIO &out, int &bs) {
+    typedef Pipe422<EDGE> P;
+    const Lags L = lags_of(K);
+    const int nb = (K.w + kB - 1) / kB;
+    if (K.flags & G_VHS) {
+        const int bV = s - L.bV;
+        if (!EDGE || (bV >= 0 && bV < nb)) P::stage_vhs_chroma(K, rc, ln, bV, pu, pv, au, av);
+        if (!(K.flags & G_SVIDEO)) {
+            const int b2 = s - L.bD2;
+            if (!EDGE || (b2 >= 0 && b2 < nb)) P::stage_redemod(K, rc, ln, ln.dm2, b2, dv.amp_magic, dv.amp_shift);
+        }
+    }
+    const int bE = s - L.bE;
+    if ((rc.rflags & RG_DROPOUT) && (!EDGE || (bE >= 0 && bE < nb))) P::stage_dropout(K, ln, bE);
+    for (int i = 0; i < K.recombine; i++) {            // -yc-recomb: rare, state lives in shared memory
+        const int bm = bE - i, bd = bE - i - 1;
+        if (bm >= 0 && bm < nb) Pipe422<true>::stage_remodulate(K, rc, ln, bm);
+        if (bd >= 0 && bd < nb) {
+            Demod dm;
+            dm.o1 = ln.rcomb[3 * i]; dm.o2 = ln.rcomb[3 * i + 1]; dm.o3 = ln.rcomb[3 * i + 2];
+            Pipe422<true>::stage_redemod(K, rc, ln, dm, bd, dv.amp_magic, dv.amp_shift);
+            ln.rcomb[3 * i] = dm.o1; ln.rcomb[3 * i + 1] = dm.o2; ln.rcomb[3 * i + 2] = dm.o3;
+        }
+    }
+    const int bF = s - L.bF;
+    if (!EDGE || (bF >= 0 && bF < nb)) {
+        if (K.flags & G_OUT_FULL) {
+            P::chroma_lp_block(K, ln.ru, bF, ln.outU, K.a_out[0], K.a_outhp[0], true, K.d_out[0]);
+            P::chroma_lp_block(K, ln.rv, bF, ln.outV, K.a_out[1], K.a_outhp[1], true, K.d_out[1]);
+        } else if (K.flags & G_OUT_LITE) {
+            P::chroma_lp_block(K, ln.ru, bF, ln.outU, K.a_out[0], 0.0, false, K.d_out[0]);
+            P::chroma_lp_block(K, ln.rv, bF, ln.outV, K.a_out[1], 0.0, false, K.d_out[1]);
+        }
+    }
+    bs = s - L.bS;
+    if (EDGE && (bs < 0 || bs >= nb)) return false;
+    const int x0 = bs * kB, c0 = bs * kBC;
+    out.y0 = pack4(ln.ry[x0 & (kRingY - 1)], ln.ry[(x0 + 1) & (kRingY - 1)], ln.ry[(x0 + 2) & (kRingY - 1)], ln.ry[(x0 + 3) & (kRingY - 1)]);
+    out.y1 = pack4(ln.ry[(x0 + 4) & (kRingY - 1)], ln.ry[(x0 + 5) & (kRingY - 1)], ln.ry[(x0 + 6) & (kRingY - 1)], ln.ry[(x0 + 7) & (kRingY - 1)]);
+    out.u = pack4(ln.ru[c0 & (kRingC - 1)], ln.ru[(c0 + 1) & (kRingC - 1)], ln.ru[(c0 + 2) & (kRingC - 1)], ln.ru[(c0 + 3) & (kRingC - 1)]);
+    out.v = pack4(ln.rv[c0 & (kRingC - 1)], ln.rv[(c0 + 1) & (kRingC - 1)], ln.rv[(c0 + 2) & (kRingC - 1)], ln.rv[(c0 + 3) & (kRingC - 1)]);
+    return true;
+}
+
+// Head-switch pre-pass (:697-731) for rotations the in-ring delay cannot express (shift to the left, or
+// further than the ring / the 10 % padding): the row's composite luma (G0..G2, with its exact noise) is
+// computed up front and written, already rotated, into a scratch row: dest[(x - shif) mod twidth] =
+// Y[x], everything not hit is the reference's padding value 16.
+CVS_HD void headswitch_row(const K422 &K, const Row422 &rc_in, Lane422 &ln, const uint8_t *yrow, const uint8_t *urow,
+                           const uint8_t *vrow, uint8_t *scratch, int shif) {
+    typedef Pipe422<true> P;
+    Row422 rc = rc_in;
+    rc.rflags &= ~(uint32_t)(RG_HEADSW | RG_HEADSW_PRE);
+    rc.hs_delay = 0;
+    const int w = K.w, tw = w + w / 10, nb = (w + kB - 1) / kB;
+    for (int x = 0; x < w; x++) scratch[x] = 16;
+    for (int s = 0; s <= nb; s++) {
+        if (s < nb) {
+            for (int j = 0; j < kB; j++)
+                if (s * kB + j < w) ln.ry[(s * kB + j) & (kRingY - 1)] = yrow[s * kB + j];
+            for (int k = 0; k < kBC; k++)
+                if (s * kBC + k < K.cw) {
+                    ln.ru[(s * kBC + k) & (kRingC - 1)] = urow[s * kBC + k];
+                    ln.rv[(s * kBC + k) & (kRingC - 1)] = vrow[s * kBC + k];
+                }
+            if (K.flags & G_IN_LP) {
+                P::chroma_lp_block(K, ln.ru, s, ln.inU, K.a_in[0], K.a_inhp[0], true, K.d_in[0]);
+                P::chroma_lp_block(K, ln.rv, s, ln.inV, K.a_in[1], K.a_inhp[1], true, K.d_in[1]);
+            }
+        }
+        const int bM = s - 1;
+        if (bM >= 0 && bM < nb) {
+            P::stage_compose(K, rc, ln, bM, false, nullptr);
+            for (int j = 0; j < kB; j++) {
+                const int x = bM * kB + j;
+                if (x < w) {
+                    int xd = (x - shif) % tw;
+                    if (xd < 0) xd += tw;
+                    if (xd < w) scratch[xd] = ln.ry[x & (kRingY - 1)];
+                }
+            }
+        }
+    }
+}
+
+// steps [s_lo, s_hi) touch only whole interior blocks in every stage (no line start / end special cases)
+CVS_HD void interior_steps(const K422 &K, int &s_lo, int &s_hi) {
+    const Lags L = lags_of(K);
+    const int nb_full = K.w / kB;                     // complete blocks
+    s_lo = L.bS + 2;                                  // the oldest stage is past block 1 (c >= max delay, x >= first flip)
+    s_hi = nb_full;                                   // the load front is a complete block inside the row
+    if (s_hi < s_lo) s_hi = s_lo;
+    if (K.recombine != 0) s_hi = s_lo;                // -yc-recomb runs the general path
+}
+
+}  // namespace cvs422
+#endif

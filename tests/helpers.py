@@ -237,3 +237,22 @@ def run_oracle422(orc, p, w, h, n, pad=2, first=0, frames=None, rng=None):
         assert rc == 0
         out.append((Y, U, V))
     return out, g
+
+
+def load_emu422():
+    return C.CDLL(cvs_build.build_emu422())
+
+
+def run_emu422(emu, p, w, h, n, pad=2, first=0, force_general=0, frames=None, rng_pos=0):
+    out = []
+    pos = rng_pos
+    for k in range(first, first + n):
+        Y, U, V = (frames(k) if frames else yuv422_frame(w, h, k, pad))
+        nd = C.c_ulonglong(0)
+        rc = emu.emu422_process(C.byref(p), C.c_ulonglong(pos), _ptr(Y), C.c_int(Y.shape[1]), _ptr(U), C.c_int(U.shape[1]),
+                                _ptr(V), C.c_int(V.shape[1]), C.c_int(w), C.c_int(h), C.c_uint((k & 1) ^ 1),
+                                C.c_ulonglong(k), C.c_int(force_general), C.byref(nd))
+        assert rc == 0, rc
+        pos += nd.value
+        out.append((Y, U, V))
+    return out, pos
