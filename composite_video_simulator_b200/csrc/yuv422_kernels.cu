@@ -1,0 +1,39 @@
+// yuv422_kernels.cu -- instantiation and launchers of the 4:2:2 kernels (yuv422_kernels.cuh).
+#define CVS_YUV422_DEFINE_KERNELS
+#include "yuv422_kernels.cuh"
+
+namespace cvs422 {
+
+cudaError_t launch_yuv422(const Launch422 &a, const HsItem422 *d_items, int nitems, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(k_yuv422, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem422::total);
+    if (e != cudaSuccess) return e;
+    if (a.warps_per_field > 1) {
+        k_yuv422_halo<<<a.nfields * a.warps_per_field, 128, 0, st>>>(a);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    if (nitems > 0) {
+        k_yuv422_headswitch<<<(nitems + kHsNT - 1) / kHsNT, kHsNT, 0, st>>>(a, d_items, nitems);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    const int ctas = (a.total_warps + kWarps - 1) / kWarps;
+    k_yuv422<<<ctas, kNT, Smem422::total, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t occupancy_yuv422(int *ctas_per_sm) {
+    cudaError_t e = cudaFuncSetAttribute(k_yuv422, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem422::total);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_yuv422, kNT, Smem422::total);
+}
+
+cudaError_t launch_render_field(const RenderArgs &a, cudaStream_t st) {
+    int maxb = a.row_bytes[0];
+    for (int p = 1; p < 3; p++) maxb = a.row_bytes[p] > maxb ? a.row_bytes[p] : maxb;
+    const int rows = (a.dst_h > a.field) ? (a.dst_h - a.field + 1) / 2 : 0;
+    if (rows <= 0 || maxb <= 0) return cudaSuccess;
+    dim3 grid((unsigned)((maxb + 255) / 256), (unsigned)rows, 3);
+    k_render_field<<<grid, 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace cvs422

@@ -1,0 +1,377 @@
+// yuv422_kernels.cuh -- sm_100a kernels around yuv422_pipeline.cuh (the reference's 4:2:2 path,
+// ffmpeg_to_composite.cpp:629-952 and :1001-1129).
+//
+//   k_yuv422             one launch processes a batch of fields IN PLACE: a warp owns 31 consecutive
+//                        rows of one field (+ a halo lane), a lane streams its row through every stage
+//                        of composite_video_process(); stages talk through per-lane byte rings in
+//                        shared memory.  HBM traffic = one read + one write of the field's rows
+//                        (2 bytes per pixel each way).
+//   k_yuv422_halo        copies the one row per warp that a halo lane re-reads (the last row of the
+//                        warp above) before the in-place pass overwrites it.
+//   k_yuv422_headswitch  pre-pass for head-switch rotations that are not a short delay.
+//   k_render_field       render_field(): vertical 8.8 resampling of a source picture onto field rows.
+#ifndef CVS_YUV422_KERNELS_CUH
+#define CVS_YUV422_KERNELS_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "yuv422_pipeline.cuh"
+
+namespace cvs422 {
+
+constexpr int kNT = 128;                 // threads per CTA
+constexpr int kWarps = kNT / 32;
+constexpr int kRowsPerWarp = 31;         // lane 0 is the halo row
+constexpr int kStrideY = kRingY + 4;     // per-lane ring strides: +1 word so that equal offsets of the 32 lanes
+constexpr int kStrideC = kRingC + 4;     // fall into 32 different banks
+
+struct FieldDesc422 {
+    uint8_t *y, *u, *v;                  // picture planes (device), processed in place
+    const uint32_t *rowinfo;             // nl packed row records
+    const uint32_t *seek;                // nl * 62 jump-polynomial words of this geometry / parity
+    uint8_t *hs_scratch;                 // hs_count rotated composite rows of w bytes
+    const int32_t *hs_shift;
+    uint8_t *halo;                       // warps_per_field halo records (halo_pitch bytes each)
+    unsigned long long fieldno;
+    int32_t field, nl, hs_first, hs_count;
+    uint32_t window[64];
+};
+
+struct HsItem422 {
+    int32_t field_idx, slot;
+};
+
+struct Launch422 {
+    K422 K;
+    DivPair dv;
+    const FieldDesc422 *fields;
+    int32_t nfields, warps_per_field, total_warps;
+    int32_t ly, lu, lv;                  // linesizes
+    long long by, bu, bv;                // plane sizes in bytes (linesize * h): reads past them return 0
+    int32_t halo_pitch, halo_u, halo_v;  // halo record: [Y: w + 2 bytes][U at halo_u][V at halo_v]
+    int32_t vec;                         // planes, linesizes and picture strides allow 8 / 4 byte accesses
+    int32_t *status;
+};
+
+struct Smem422 {
+    static constexpr size_t rng = (size_t)2 * kRngSlots * kNT * sizeof(uint32_t);
+    static constexpr size_t wins = (size_t)kWarps * 64 * sizeof(uint32_t);
+    static constexpr size_t ry = (size_t)kNT * kStrideY, rya = ry;
+    static constexpr size_t rc = (size_t)kNT * kStrideC;
+    static constexpr size_t rcomb = (size_t)kNT * 3 * kMaxRecombine * sizeof(int32_t);
+    static constexpr size_t off_wins = rng, off_ry = off_wins + wins, off_rya = off_ry + ry, off_ru = off_rya + rya,
+                            off_rv = off_ru + rc, off_rcomb = off_rv + rc, total = off_rcomb + rcomb;
+};
+
+// what a lane reads its row from
+struct LaneSrc {
+    const uint8_t *y, *u, *v;
+    int y_avail;                         // readable luma bytes from y (<= w + 2; the rest reads as 0)
+};
+
+// ---- render_field (:1001-1129) ------------------------------------------------------------------------
+struct RenderArgs {
+    uint8_t *dst[3];
+    const uint8_t *src[3];
+    int32_t dst_ls[3], src_ls[3], row_bytes[3];
+    int32_t dst_h, src_h, is420, interlaced, tff, second, field;
+};
+
+// source rows and 8-bit fraction for output row y: luma (sy, sy2, syf) and chroma (csy, csy2, csyf)
+struct RowMap {
+    unsigned sy, sy2, syf, csy, csy2, csyf;
+};
+CVS_HD RowMap render_row_map(unsigned y, int dst_h, int src_h, int is420, int interlaced, int tff, int second) {
+    RowMap m;
+    const unsigned chroma_h = is420 ? (unsigned)src_h >> 1 : (unsigned)src_h;
+    unsigned sy = (y * 0x100u * (unsigned)src_h) / (unsigned)dst_h;
+    unsigned syf = sy & 0xFFu;
+    sy >>= 8;
+    unsigned csy = sy, csyf = syf;
+    if (is420) { if (!(csy & 1u)) csyf = 0; csy >>= 1; }
+    if (interlaced) {
+        unsigned which = tff ? 0u : 1u;
+        if (second) which ^= 1u;
+        if (which == 0) {
+            if (sy & 1u) { sy++; syf = 0; }
+            if (csy & 1u) { csy++; csyf = 0; }
+        } else {
+            if (!(sy & 1u)) { sy++; syf = 0; }
+            if (!(csy & 1u)) { csy++; csyf = 0; }
+        }
+        if (sy >= (unsigned)(src_h - 2)) { sy = (unsigned)(src_h - 2); syf = 0; }
+        m.sy2 = sy + 2;
+        if (csy >= chroma_h - 2) { csy = chroma_h - 2; csyf = 0; }
+        m.csy2 = csy + 1;
+    } else {
+        if (sy >= (unsigned)(src_h - 1)) { sy = (unsigned)(src_h - 1); syf = 0; }
+        m.sy2 = sy + 1;
+        if (csy >= chroma_h - 1) { csy = chroma_h - 1; csyf = 0; }
+        m.csy2 = csy + 1;
+    }
+    m.sy = sy; m.syf = syf; m.csy = csy; m.csyf = csyf;
+    return m;
+}
+
+#ifdef CVS_YUV422_DEFINE_KERNELS   // device code: compiled once, in yuv422_kernels.cu
+
+__device__ __forceinline__ void rebase422(const uint32_t *win_smem, const uint32_t *poly_g, uint32_t hist[31]) {
+    uint32_t poly[31];
+#pragma unroll
+    for (int i = 0; i < 31; i++) poly[i] = __ldg(poly_g + i);
+#pragma unroll 1
+    for (int k = 0; k < 31; k++) {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int i = 0; i < 31; i++) acc += poly[i] * win_smem[k + i];
+        hist[k] = acc;
+    }
+}
+
+__device__ __forceinline__ uint32_t gather4(const uint8_t *p, int n_valid) {
+    uint32_t w = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (k < n_valid) w |= (uint32_t)p[k] << (8 * k);
+    return w;
+}
+
+template <bool EDGE>
+__device__ __forceinline__ void load_block(const LaneSrc &src, const K422 &K, int s, bool vec, StepIO &io) {
+    const int x0 = s * kB, c0 = s * kBC;
+    if (EDGE) {
+        io.y0 = gather4(src.y + x0, src.y_avail - x0);
+        io.y1 = gather4(src.y + x0 + 4, src.y_avail - x0 - 4);
+        io.u = gather4(src.u + c0, K.cw - c0);
+        io.v = gather4(src.v + c0, K.cw - c0);
+    } else if (vec) {
+        const uint2 yy = *reinterpret_cast<const uint2 *>(src.y + x0);
+        io.y0 = yy.x; io.y1 = yy.y;
+        io.u = *reinterpret_cast<const uint32_t *>(src.u + c0);
+        io.v = *reinterpret_cast<const uint32_t *>(src.v + c0);
+    } else {
+        io.y0 = gather4(src.y + x0, 4);
+        io.y1 = gather4(src.y + x0 + 4, 4);
+        io.u = gather4(src.u + c0, 4);
+        io.v = gather4(src.v + c0, 4);
+    }
+}
+
+template <bool EDGE>
+__device__ __forceinline__ void store_block(uint8_t *y, uint8_t *u, uint8_t *v, const K422 &K, int bs, bool vec, const StepIO &o) {
+    const int x0 = bs * kB, c0 = bs * kBC;
+    if (vec && (!EDGE || x0 + kB <= K.w)) {
+        *reinterpret_cast<uint2 *>(y + x0) = make_uint2(o.y0, o.y1);
+        *reinterpret_cast<uint32_t *>(u + c0) = o.u;
+        *reinterpret_cast<uint32_t *>(v + c0) = o.v;
+    } else {
+#pragma unroll
+        for (int j = 0; j < kB; j++)
+            if (x0 + j < K.w) y[x0 + j] = (uint8_t)(((j < 4 ? o.y0 : o.y1) >> (8 * (j & 3))) & 0xFFu);
+#pragma unroll
+        for (int k = 0; k < kBC; k++)
+            if (c0 + k < K.cw) {
+                u[c0 + k] = (uint8_t)((o.u >> (8 * k)) & 0xFFu);
+                v[c0 + k] = (uint8_t)((o.v >> (8 * k)) & 0xFFu);
+            }
+    }
+}
+
+template <bool EDGE>
+__device__ __forceinline__ void one_step(const K422 &K, const DivPair &dv, const Row422 &rc, Lane422 &ln, int s,
+                                         const StepIO &in, bool warp_hs, const uint8_t *hsrow, bool valid,
+                                         uint8_t *dy, uint8_t *du, uint8_t *dvp, bool vec) {
+    uint32_t pu, pv;
+    step_front<EDGE>(K, dv, rc, ln, s, in, warp_hs, hsrow, pu, pv);
+    uint32_t au = 0, av = 0;
+    if (K.flags & G_VHS) {
+        au = __shfl_up_sync(0xffffffffu, pu, 1);
+        av = __shfl_up_sync(0xffffffffu, pv, 1);
+    }
+    StepIO out;
+    int bs;
+    const bool have = step_back<EDGE>(K, dv, rc, ln, s, pu, pv, au, av, out, bs);
+    if (have && valid) store_block<EDGE>(dy, du, dvp, K, bs, vec, out);
+}
+
+__global__ void __launch_bounds__(kNT, 2) k_yuv422(const __grid_constant__ Launch422 a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint32_t *rings = reinterpret_cast<uint32_t *>(smem);
+    uint32_t *wins = reinterpret_cast<uint32_t *>(smem + Smem422::off_wins);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gw = blockIdx.x * kWarps + warp;
+    if (gw >= a.total_warps) return;
+    const int fi = gw / a.warps_per_field, wp = gw - fi * a.warps_per_field;
+    const FieldDesc422 &fd = a.fields[fi];
+    const int nl = fd.nl;
+    if (kRowsPerWarp * wp >= nl) return;
+    const K422 &K = a.K;
+    const int w = K.w;
+
+    uint32_t *win = wins + warp * 64;
+    win[lane] = fd.window[lane];
+    win[lane + 32] = fd.window[lane + 32];
+    __syncwarp();
+
+    int row = kRowsPerWarp * wp + lane - 1;
+    const bool valid = (lane >= 1) && row < nl;
+    row = row < 0 ? 0 : (row > nl - 1 ? nl - 1 : row);
+    const long long y = (long long)fd.field + 2 * row;
+
+    Lane422 ln;
+    ln.reset();
+    ln.ry = smem + Smem422::off_ry + (size_t)tid * kStrideY;
+    ln.rya = smem + Smem422::off_rya + (size_t)tid * kStrideY;
+    ln.ru = smem + Smem422::off_ru + (size_t)tid * kStrideC;
+    ln.rv = smem + Smem422::off_rv + (size_t)tid * kStrideC;
+    ln.rcomb = reinterpret_cast<int32_t *>(smem + Smem422::off_rcomb) + (size_t)tid * 3 * kMaxRecombine;
+    for (int i = 0; i < 3 * kMaxRecombine; i++) ln.rcomb[i] = 16;
+
+    Row422 rc;
+    row_setup(K, (unsigned)fd.field, fd.fieldno, row, __ldg(fd.rowinfo + row), rc);
+
+    // rows: lanes 1..31 read the picture; the halo lane of warps 1.. reads the copy k_yuv422_halo took
+    LaneSrc src;
+    if (lane == 0 && wp > 0) {
+        const uint8_t *hr = fd.halo + (size_t)wp * (size_t)a.halo_pitch;
+        src.y = hr; src.u = hr + a.halo_u; src.v = hr + a.halo_v;
+        src.y_avail = w + 2;
+    } else {
+        src.y = fd.y + y * a.ly; src.u = fd.u + y * a.lu; src.v = fd.v + y * a.lv;
+        const long long left = a.by - y * a.ly;            // bytes of the plane from the row start
+        src.y_avail = (int)(left < (long long)(w + 2) ? left : (long long)(w + 2));
+    }
+    uint8_t *dy = fd.y + y * a.ly, *du = fd.u + y * a.lu, *dvp = fd.v + y * a.lv;
+    const uint8_t *hsrow = (rc.rflags & RG_HEADSW_PRE) ? fd.hs_scratch + (size_t)(row - fd.hs_first) * (size_t)w : nullptr;
+
+    {
+        bool ok = true;
+        uint32_t hist[31];
+        if (K.vnoise != 0) {
+            const long long pre = (long long)row * w;
+            const int nd = (int)(pre < kWarm ? pre : kWarm);
+            rebase422(win, fd.seek + (size_t)row * 62, hist);
+            ln.rngL.init(rings + tid, kNT, hist, kRngBase - (uint32_t)nd);
+            ok &= cvs::warm_luma((uint32_t)(2 * K.vnoise + 1), K.vmagic, K.vshift, K.vnoise, ln.rngL, nd, pre <= kWarm, ln.nY);
+        }
+        if (K.cnoise != 0) {
+            const long long pre = (long long)row * K.cw;
+            const int nd = (int)(pre < kWarm ? pre : kWarm);
+            rebase422(win, fd.seek + (size_t)row * 62 + 31, hist);
+            ln.rngC.init(rings + (size_t)kRngSlots * kNT + tid, kNT, hist, kRngBase - 2u * (uint32_t)nd);
+            ok &= cvs::warm_chroma((uint32_t)(2 * K.cnoise + 1), K.cmagic, K.cshift, K.cnoise, ln.rngC, nd, pre <= kWarm, ln.nU, ln.nV);
+        }
+        if (!ok) atomicOr(a.status, 1);
+    }
+
+    const int nsteps = line_steps(K);
+    int s_lo, s_hi;
+    interior_steps(K, s_lo, s_hi);
+    const bool warp_hs = __any_sync(0xffffffffu, rc.hs_delay > 0);
+    const bool vec = a.vec != 0;          // (halo records are 16-byte aligned, so the halo lane qualifies too)
+    const bool vec_ld = vec;
+
+    StepIO cur;
+    load_block<true>(src, K, 0, vec_ld, cur);
+    int s = 0;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+        const int s_end = (pass == 0) ? (s_lo < nsteps ? s_lo : nsteps) : nsteps;
+#pragma unroll 1
+        for (; s < s_end; s++) {
+            StepIO nxt;
+            load_block<true>(src, K, s + 1, vec_ld, nxt);
+            one_step<true>(K, a.dv, rc, ln, s, cur, warp_hs, hsrow, valid, dy, du, dvp, vec);
+            cur = nxt;
+        }
+        if (pass == 0) {
+#pragma unroll 1
+            for (; s < s_hi; s++) {
+                StepIO nxt;
+                if (s + 1 < s_hi) load_block<false>(src, K, s + 1, vec_ld, nxt);
+                else load_block<true>(src, K, s + 1, vec_ld, nxt);
+                one_step<false>(K, a.dv, rc, ln, s, cur, warp_hs, hsrow, valid, dy, du, dvp, vec);
+                cur = nxt;
+            }
+        }
+    }
+}
+
+// one CTA per (field, warp index >= 1): copy the row above the warp's first row
+__global__ void __launch_bounds__(128) k_yuv422_halo(const __grid_constant__ Launch422 a) {
+    const int fi = blockIdx.x / a.warps_per_field, wp = blockIdx.x - fi * a.warps_per_field;
+    const FieldDesc422 &fd = a.fields[fi];
+    if (wp == 0 || kRowsPerWarp * wp >= fd.nl) return;
+    const int row = kRowsPerWarp * wp - 1;
+    const long long y = (long long)fd.field + 2 * row;
+    uint8_t *hr = fd.halo + (size_t)wp * (size_t)a.halo_pitch;
+    const int w = a.K.w, cw = a.K.cw;
+    const long long left = a.by - y * a.ly;
+    for (int x = threadIdx.x; x < w + 2; x += blockDim.x) hr[x] = (x < left) ? fd.y[y * a.ly + x] : (uint8_t)0;
+    for (int c = threadIdx.x; c < cw; c += blockDim.x) {
+        hr[a.halo_u + c] = fd.u[y * a.lu + c];
+        hr[a.halo_v + c] = fd.v[y * a.lv + c];
+    }
+}
+
+constexpr int kHsNT = 32;
+
+__global__ void __launch_bounds__(kHsNT) k_yuv422_headswitch(const __grid_constant__ Launch422 a,
+                                                            const HsItem422 *__restrict__ items, int nitems) {
+    __shared__ uint32_t ring[kRngSlots * kHsNT];
+    __shared__ uint8_t rb[kHsNT * (2 * kStrideY + 2 * kStrideC)];
+    const int it = blockIdx.x * kHsNT + threadIdx.x;
+    if (it >= nitems) return;
+    const HsItem422 item = items[it];
+    const FieldDesc422 &fd = a.fields[item.field_idx];
+    const K422 &K = a.K;
+    const int w = K.w;
+    const int row = fd.hs_first + item.slot;
+    Lane422 ln;
+    ln.reset();
+    uint8_t *base = rb + (size_t)threadIdx.x * (2 * kStrideY + 2 * kStrideC);
+    ln.ry = base; ln.rya = base + kStrideY; ln.ru = base + 2 * kStrideY; ln.rv = base + 2 * kStrideY + kStrideC;
+    ln.rcomb = nullptr;
+    Row422 rc;
+    row_setup(K, (unsigned)fd.field, fd.fieldno, row, __ldg(fd.rowinfo + row), rc);
+    if (K.vnoise != 0) {
+        const long long pre = (long long)row * w;
+        const int nd = (int)(pre < kWarm ? pre : kWarm);
+        uint32_t hist[31];
+        cvs::rng_rebase(fd.window, fd.seek + (size_t)row * 62, hist);
+        ln.rngL.init(ring + threadIdx.x, kHsNT, hist, kRngBase - (uint32_t)nd);
+        if (!cvs::warm_luma((uint32_t)(2 * K.vnoise + 1), K.vmagic, K.vshift, K.vnoise, ln.rngL, nd, pre <= kWarm, ln.nY))
+            atomicOr(a.status, 1);
+    }
+    const long long y = (long long)fd.field + 2 * row;
+    headswitch_row(K, rc, ln, fd.y + y * a.ly, fd.u + y * a.lu, fd.v + y * a.lv,
+                   fd.hs_scratch + (size_t)item.slot * (size_t)w, __ldg(fd.hs_shift + item.slot));
+}
+
+// grid: (ceil(max row_bytes / 256), field rows, 3 planes); one byte per thread, coalesced along the row
+__global__ void __launch_bounds__(256) k_render_field(const __grid_constant__ RenderArgs a) {
+    const int p = blockIdx.z;
+    const unsigned y = (unsigned)a.field + 2u * blockIdx.y;
+    const int x = blockIdx.x * 256 + threadIdx.x;
+    if (y >= (unsigned)a.dst_h || x >= a.row_bytes[p]) return;
+    const RowMap m = render_row_map(y, a.dst_h, a.src_h, a.is420, a.interlaced, a.tff, a.second);
+    const bool chroma_map = a.is420 && p > 0;            // 4:2:2 sources use the luma mapping for all planes
+    const unsigned r1 = chroma_map ? m.csy : m.sy, r2 = chroma_map ? m.csy2 : m.sy2, fr = chroma_map ? m.csyf : m.syf;
+    const int s1 = a.src[p][(size_t)a.src_ls[p] * r1 + x];
+    int v = s1;
+    if (fr != 0) {
+        const int s2 = a.src[p][(size_t)a.src_ls[p] * r2 + x];
+        v = s1 + (int)(uint8_t)(((s2 - s1) * (int)fr) >> 8);
+    }
+    a.dst[p][(size_t)a.dst_ls[p] * y + x] = (uint8_t)v;
+}
+
+#endif  // CVS_YUV422_DEFINE_KERNELS
+
+cudaError_t launch_yuv422(const Launch422 &a, const HsItem422 *d_items, int nitems, cudaStream_t st);
+cudaError_t occupancy_yuv422(int *ctas_per_sm);
+cudaError_t launch_render_field(const RenderArgs &a, cudaStream_t st);
+
+}  // namespace cvs422
+#endif

@@ -124,3 +124,97 @@ def params_from_argv(argv):
     arr = (C.c_char_p * (len(argv) + 1))(b"ffmpeg_to_composite", *[a.encode() for a in argv])
     _check(_bind(["cvs422_params_apply_argv"]).cvs422_params_apply_argv(C.byref(p), len(argv) + 1, arr))
     return p
+
+
+def _np_ptr(a):
+    if not (isinstance(a, np.ndarray) and a.dtype == np.uint8 and a.ndim >= 2 and a.strides[-1] == 1):
+        raise TypeError("planes must be uint8 numpy arrays with contiguous rows")
+    return C.c_void_p(a.ctypes.data)
+
+
+class Yuv422Engine:
+    """One context of the 4:2:2 engine: parameters + rand() position + device resources.
+
+    ``Yuv422Engine(["-vhs", "-vhs-speed", "ep"])`` takes ffmpeg_to_composite's switches;
+    ``composite_video_process(Y, U, V, field, fieldno)`` is the reference's call
+    (ffmpeg_to_composite.cpp:1790) on numpy planes, in place."""
+
+    def __init__(self, argv_or_params=None, device=0, max_w=1920, max_h=1080, max_batch=1):
+        if isinstance(argv_or_params, Yuv422Params):
+            self.params = argv_or_params.copy()
+        else:
+            self.params = params_from_argv(list(argv_or_params or []))
+        self._lib = lib()
+        self._ctx = _vp()
+        _check(self._lib.cvs422_create(C.byref(self._ctx), C.byref(self.params), device, max_w, max_h, max_batch))
+        self.max_batch = max_batch
+
+    def close(self):
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            self._lib.cvs422_destroy(self._ctx)
+            self._ctx = _vp()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_params(self, p):
+        _check(self._lib.cvs422_set_params(self._ctx, C.byref(p)))
+        self.params = p.copy()
+
+    def composite_video_process(self, Y, U, V, w, field, fieldno):
+        h = Y.shape[0]
+        _check(self._lib.cvs422_composite_video_process(self._ctx, _np_ptr(Y), Y.strides[0], _np_ptr(U), U.strides[0],
+                                                        _np_ptr(V), V.strides[0], w, h, field, fieldno))
+
+    def process_fields_host(self, Y, U, V, w, first_fieldno):
+        """Y: [n, h, linesize_y], U, V: [n, h, linesize_c] uint8, processed in place."""
+        n, h = Y.shape[0], Y.shape[1]
+        _check(self._lib.cvs422_process_fields_host(self._ctx, _np_ptr(Y), _np_ptr(U), _np_ptr(V),
+                                                    Y.strides[0], U.strides[0], V.strides[0],
+                                                    Y.strides[1], U.strides[1], V.strides[1], w, h, n, first_fieldno))
+
+    def process_fields_device(self, Y, U, V, w, first_fieldno):
+        """The same on CUDA tensors (torch.uint8, [n, h, linesize]); asynchronous on the context's stream."""
+        n, h = Y.shape[0], Y.shape[1]
+        _check(self._lib.cvs422_process_fields_device(self._ctx, Y.data_ptr(), U.data_ptr(), V.data_ptr(),
+                                                      Y.stride(0), U.stride(0), V.stride(0),
+                                                      Y.stride(1), U.stride(1), V.stride(1), w, h, n, first_fieldno))
+
+    def render_field_device(self, dst, src, row_bytes, src_is_420, interlaced, tff, second_field, field):
+        """dst, src: three CUDA uint8 tensors [rows, linesize] each."""
+        _check(self._lib.cvs422_render_field_device(
+            self._ctx, _V3(*[t.data_ptr() for t in dst]), _I3(*[t.stride(0) for t in dst]), dst[0].shape[0],
+            _V3(*[t.data_ptr() for t in src]), _I3(*[t.stride(0) for t in src]), src[0].shape[0],
+            _I3(*row_bytes), int(src_is_420), int(interlaced), int(tff), int(second_field), field))
+
+    def synchronize(self):
+        _check(self._lib.cvs422_synchronize(self._ctx))
+
+    def set_stream(self, cuda_stream):
+        _check(self._lib.cvs422_set_stream(self._ctx, C.c_void_p(cuda_stream)))
+
+    def rng_seek(self, draws):
+        _check(self._lib.cvs422_rng_seek(self._ctx, draws))
+
+    def rng_tell(self):
+        return int(self._lib.cvs422_rng_tell(self._ctx))
+
+    def kernel_launches(self):
+        return int(self._lib.cvs422_kernel_launches(self._ctx))
+
+    def kernel_time_reset(self):
+        _check(self._lib.cvs422_kernel_time_reset(self._ctx))
+
+    def kernel_time_query(self):
+        ms, n = C.c_double(0), C.c_int(0)
+        _check(self._lib.cvs422_kernel_time_query(self._ctx, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
