@@ -20,11 +20,20 @@
 
 namespace cvs422 {
 
-constexpr int kNT = 128;                 // threads per CTA
+#ifndef CVS422_NT
+#define CVS422_NT 128
+#endif
+#ifndef CVS422_MIN_CTAS
+#define CVS422_MIN_CTAS 2
+#endif
+// Measured on B200 (1080p VHS-SP, 296 fields): 128 threads x 2 CTAs/SM (208 registers) 4.32 ms; 64 x 4 4.48 ms;
+// 64 x 5 (168 registers, spills) 5.30 ms: the third warp per scheduler does not pay for the register squeeze.
+constexpr int kNT = CVS422_NT;           // threads per CTA
 constexpr int kWarps = kNT / 32;
 constexpr int kRowsPerWarp = 31;         // lane 0 is the halo row
 constexpr int kStrideY = kRingY + 4;     // per-lane ring strides: +1 word so that equal offsets of the 32 lanes
 constexpr int kStrideC = kRingC + 4;     // fall into 32 different banks
+constexpr int kStrideA = kRingA + 4;
 
 struct FieldDesc422 {
     uint8_t *y, *u, *v;                  // picture planes (device), processed in place
@@ -57,7 +66,7 @@ struct Launch422 {
 struct Smem422 {
     static constexpr size_t rng = (size_t)2 * kRngSlots * kNT * sizeof(uint32_t);
     static constexpr size_t wins = (size_t)kWarps * 64 * sizeof(uint32_t);
-    static constexpr size_t ry = (size_t)kNT * kStrideY, rya = ry;
+    static constexpr size_t ry = (size_t)kNT * kStrideY, rya = (size_t)kNT * kStrideA;
     static constexpr size_t rc = (size_t)kNT * kStrideC;
     static constexpr size_t rcomb = (size_t)kNT * 3 * kMaxRecombine * sizeof(int32_t);
     static constexpr size_t off_wins = rng, off_ry = off_wins + wins, off_rya = off_ry + ry, off_ru = off_rya + rya,
@@ -179,11 +188,11 @@ __device__ __forceinline__ void store_block(uint8_t *y, uint8_t *u, uint8_t *v, 
 }
 
 template <bool EDGE>
-__device__ __forceinline__ void one_step(const K422 &K, const DivPair &dv, const Row422 &rc, Lane422 &ln, int s,
+__device__ __forceinline__ void one_step(const K422 &K, const Lags &L, const Geo &G, const DivPair &dv, const Row422 &rc, Lane422 &ln, int s,
                                          const StepIO &in, bool warp_hs, const uint8_t *hsrow, bool valid,
                                          uint8_t *dy, uint8_t *du, uint8_t *dvp, bool vec) {
     uint32_t pu, pv;
-    step_front<EDGE>(K, dv, rc, ln, s, in, warp_hs, hsrow, pu, pv);
+    step_front<EDGE>(K, L, G, dv, rc, ln, s, in, warp_hs, hsrow, pu, pv);
     uint32_t au = 0, av = 0;
     if (K.flags & G_VHS) {
         au = __shfl_up_sync(0xffffffffu, pu, 1);
@@ -191,11 +200,11 @@ __device__ __forceinline__ void one_step(const K422 &K, const DivPair &dv, const
     }
     StepIO out;
     int bs;
-    const bool have = step_back<EDGE>(K, dv, rc, ln, s, pu, pv, au, av, out, bs);
+    const bool have = step_back<EDGE>(K, L, G, dv, rc, ln, s, pu, pv, au, av, out, bs);
     if (have && valid) store_block<EDGE>(dy, du, dvp, K, bs, vec, out);
 }
 
-__global__ void __launch_bounds__(kNT, 2) k_yuv422(const __grid_constant__ Launch422 a) {
+__global__ void __launch_bounds__(kNT, CVS422_MIN_CTAS) k_yuv422(const __grid_constant__ Launch422 a) {
     extern __shared__ __align__(16) unsigned char smem[];
     uint32_t *rings = reinterpret_cast<uint32_t *>(smem);
     uint32_t *wins = reinterpret_cast<uint32_t *>(smem + Smem422::off_wins);
@@ -222,7 +231,7 @@ __global__ void __launch_bounds__(kNT, 2) k_yuv422(const __grid_constant__ Launc
     Lane422 ln;
     ln.reset();
     ln.ry = smem + Smem422::off_ry + (size_t)tid * kStrideY;
-    ln.rya = smem + Smem422::off_rya + (size_t)tid * kStrideY;
+    ln.rya = smem + Smem422::off_rya + (size_t)tid * kStrideA;
     ln.ru = smem + Smem422::off_ru + (size_t)tid * kStrideC;
     ln.rv = smem + Smem422::off_rv + (size_t)tid * kStrideC;
     ln.rcomb = reinterpret_cast<int32_t *>(smem + Smem422::off_rcomb) + (size_t)tid * 3 * kMaxRecombine;
@@ -266,9 +275,12 @@ __global__ void __launch_bounds__(kNT, 2) k_yuv422(const __grid_constant__ Launc
     }
 
     const int nsteps = line_steps(K);
+    const Lags LG = lags_of(K);
+    const Geo GE = geo_of(K);
     int s_lo, s_hi;
     interior_steps(K, s_lo, s_hi);
     const bool warp_hs = __any_sync(0xffffffffu, rc.hs_delay > 0);
+    if (__any_sync(0xffffffffu, hsrow != nullptr)) s_hi = s_lo;      // pre-pass rows only exist in the general variant
     const bool vec = a.vec != 0;          // (halo records are 16-byte aligned, so the halo lane qualifies too)
     const bool vec_ld = vec;
 
@@ -282,7 +294,7 @@ __global__ void __launch_bounds__(kNT, 2) k_yuv422(const __grid_constant__ Launc
         for (; s < s_end; s++) {
             StepIO nxt;
             load_block<true>(src, K, s + 1, vec_ld, nxt);
-            one_step<true>(K, a.dv, rc, ln, s, cur, warp_hs, hsrow, valid, dy, du, dvp, vec);
+            one_step<true>(K, LG, GE, a.dv, rc, ln, s, cur, warp_hs, hsrow, valid, dy, du, dvp, vec);
             cur = nxt;
         }
         if (pass == 0) {
@@ -291,7 +303,7 @@ __global__ void __launch_bounds__(kNT, 2) k_yuv422(const __grid_constant__ Launc
                 StepIO nxt;
                 if (s + 1 < s_hi) load_block<false>(src, K, s + 1, vec_ld, nxt);
                 else load_block<true>(src, K, s + 1, vec_ld, nxt);
-                one_step<false>(K, a.dv, rc, ln, s, cur, warp_hs, hsrow, valid, dy, du, dvp, vec);
+                one_step<false>(K, LG, GE, a.dv, rc, ln, s, cur, warp_hs, hsrow, valid, dy, du, dvp, vec);
                 cur = nxt;
             }
         }
@@ -320,7 +332,7 @@ constexpr int kHsNT = 32;
 __global__ void __launch_bounds__(kHsNT) k_yuv422_headswitch(const __grid_constant__ Launch422 a,
                                                             const HsItem422 *__restrict__ items, int nitems) {
     __shared__ uint32_t ring[kRngSlots * kHsNT];
-    __shared__ uint8_t rb[kHsNT * (2 * kStrideY + 2 * kStrideC)];
+    __shared__ __align__(4) uint8_t rb[kHsNT * (kStrideY + kStrideA + 2 * kStrideC)];
     const int it = blockIdx.x * kHsNT + threadIdx.x;
     if (it >= nitems) return;
     const HsItem422 item = items[it];
@@ -330,8 +342,8 @@ __global__ void __launch_bounds__(kHsNT) k_yuv422_headswitch(const __grid_consta
     const int row = fd.hs_first + item.slot;
     Lane422 ln;
     ln.reset();
-    uint8_t *base = rb + (size_t)threadIdx.x * (2 * kStrideY + 2 * kStrideC);
-    ln.ry = base; ln.rya = base + kStrideY; ln.ru = base + 2 * kStrideY; ln.rv = base + 2 * kStrideY + kStrideC;
+    uint8_t *base = rb + (size_t)threadIdx.x * (kStrideY + kStrideA + 2 * kStrideC);
+    ln.ry = base; ln.rya = base + kStrideY; ln.ru = base + kStrideY + kStrideA; ln.rv = base + kStrideY + kStrideA + kStrideC;
     ln.rcomb = nullptr;
     Row422 rc;
     row_setup(K, (unsigned)fd.field, fd.fieldno, row, __ldg(fd.rowinfo + row), rc);

@@ -49,7 +49,8 @@ constexpr int kBC = 4;                   // chroma samples per block
 constexpr int kRingY = 128;              // per-lane luma ring (bytes, power of two)
 constexpr int kRingC = 64;               // per-lane chroma rings
 constexpr int kMaxRecombine = 4;         // -yc-recomb rounds the rings have room for
-constexpr int kHsMaxDelay = kRingY - 2 * kB;   // largest head-switch delay the composite ring can express
+constexpr int kRingA = 64;               // per-lane ring of the composite signal for the in-ring head-switch delay
+constexpr int kHsMaxDelay = kRingA - 2 * kB;   // largest head-switch delay that ring can express
 constexpr int kWarm = 64;                // noise warm-up length (samples), see cvs::warm_luma
 
 enum : uint32_t {
@@ -63,6 +64,7 @@ enum : uint32_t {
     G_VBLEND = 1u << 7,       // vhs_chroma_vert_blend && output_ntsc
     G_SVIDEO = 1u << 8,
     G_PHASE = 1u << 9,        // video_chroma_phase_noise != 0
+    G_GENERAL = 1u << 10,     // a rarely used switch is on: every step takes the general (edge) variant
 };
 
 // per-row flags in the host side table (same packing as cvs::rowinfo_pack)
@@ -186,6 +188,8 @@ struct Row422 {
     int row;               // field row index
     uint32_t rflags;
     int hs_delay;          // RG_HEADSW: Y[x] = Y[x - hs_delay], 16 for x < hs_delay
+    int mU[4], mV[4];      // carrier taps for (x & 3): Umult / Vmult rotated by xi (:438-439)
+    int fl[4];             // 0xFF where the demodulator flips the sign of the chroma sample (x & 3), else 0 (:527-530)
     double cosp, sinp;     // phase noise rotation of this row
 };
 
@@ -202,6 +206,13 @@ CVS_HD void row_setup(const K422 &K, unsigned field, unsigned long long fieldno,
     rc.rflags = (rowinfo >> 16) & 0xFFu;
     rc.hs_delay = (rc.rflags & RG_HEADSW) ? (int)(rowinfo >> 24) : 0;
     rc.xi = line_phase(K, fieldno, field + 2u * (unsigned)row);
+    CVS_UNROLL
+    for (int j = 0; j < 4; j++) {
+        const int ph = (rc.xi + j) & 3;
+        rc.mU[j] = (ph == 0) ? 1 : ((ph == 2) ? -1 : 0);
+        rc.mV[j] = (ph == 1) ? 1 : ((ph == 3) ? -1 : 0);
+        rc.fl[j] = (((j + rc.xi + 2) & 3) < 2) ? 0xFF : 0;
+    }
     if (K.flags & G_PHASE) {
         const int st = (int)(int16_t)(rowinfo & 0xFFFFu);
         rc.cosp = K.phase_lut[2 * (st + K.pnoise)];
@@ -229,7 +240,7 @@ struct Lane422 {
     Demod dm1, dm2;
     int nY, nU, nV;
     LaneRng rngL, rngC;
-    uint8_t *ry, *ru, *rv, *rya;     // lane-private rings (kRingY / kRingC / kRingC / kRingY bytes)
+    uint8_t *ry, *ru, *rv, *rya;     // lane-private rings (kRingY / kRingC / kRingC / kRingA bytes), 4-byte aligned
     int32_t *rcomb;                  // 3 ints per -yc-recomb round (lane-private, 3 * kMaxRecombine ints)
 
     CVS_HD void reset() {
@@ -242,152 +253,226 @@ struct Lane422 {
     }
 };
 
-CVS_HD uint32_t pack4(int a, int b, int c, int d) {
+CVS_HD uint32_t pack4(int a, int b, int c, int d) {           // four values 0..255 -> one word
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(__byte_perm((uint32_t)a, (uint32_t)b, 0x0040), __byte_perm((uint32_t)c, (uint32_t)d, 0x0040), 0x5410);
+#else
     return (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)c << 16) | ((uint32_t)d << 24);
+#endif
 }
-CVS_HD int byte_of(uint32_t w, int k) { return (int)((w >> (8 * k)) & 0xFFu); }
+CVS_HD int byte_of(uint32_t w, int k) {                       // k is a compile-time constant at every call site
+#if defined(__CUDA_ARCH__)
+    return (int)__byte_perm(w, 0u, 0x4440u + (uint32_t)k);
+#else
+    return (int)((w >> (8 * k)) & 0xFFu);
+#endif
+}
+
+// Ring access.  Blocks are 8 luma bytes / 4 chroma bytes and the rings hold 16 of them, so a block never
+// wraps: whole blocks move as 32-bit words (the rings are 4-byte aligned), only delayed writes are bytes.
+CVS_HD uint8_t *yblk(uint8_t *ring, int b) { return ring + ((b & (kRingY / kB - 1)) * kB); }
+CVS_HD uint8_t *cblk(uint8_t *ring, int b) { return ring + ((b & (kRingC / kBC - 1)) * kBC); }
+CVS_HD uint32_t ldw(const uint8_t *p) {
+#if defined(__CUDA_ARCH__)
+    return *reinterpret_cast<const uint32_t *>(p);
+#else
+    uint32_t v;
+    __builtin_memcpy(&v, p, 4);
+    return v;
+#endif
+}
+CVS_HD void stw(uint8_t *p, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    *reinterpret_cast<uint32_t *>(p) = v;
+#else
+    __builtin_memcpy(p, &v, 4);
+#endif
+}
+
+// block counts of a row
+struct Geo {
+    int nb;      // blocks with pixels
+    int nbl;     // blocks the ring must take in (the two bytes past the row included)
+};
+CVS_HD Geo geo_of(const K422 &K) {
+    Geo g;
+    g.nb = (K.w + kB - 1) / kB;
+    g.nbl = (K.w + 2 + kB - 1) / kB;
+    return g;
+}
+
+// the division constants of the two demodulator gains (amp_back for the first, amp for the others)
+struct DivPair {
+    uint32_t back_magic, back_shift, amp_magic, amp_shift;
+};
+
+// What one step exchanges with its caller: block s of the source row comes in, the pre-blend chroma of
+// block bV goes to the lane below between front() and back(), block bS comes out.
+struct StepIO {
+    uint32_t y0, y1, u, v;        // in: block s (bytes beyond the data are don't-care); out: block bS
+};
 
 template <bool EDGE>
 struct Pipe422 {
     static CVS_HD bool in(int x, int lim) { return !EDGE || x < lim; }
 
-    // composite_video_chroma_lowpass / _lite on one block of one plane: reads P[c], writes P[c - d]
-    static CVS_HD void chroma_lp_block(const K422 &K, uint8_t *ring, int b, double st[4], double a_lp, double a_hp,
-                                       bool boost, int d) {
-        const int c0 = b * kBC;
+    // a delayed three-pole chroma lowpass on the four samples of block b (packed in wv): P[c - d] = lp(P[c]),
+    // optionally preceded by the boost s += highpass(s)                                    (:353-431, :830-851)
+    static CVS_HD void chroma_lp4(const K422 &K, uint8_t *ring, int b, uint32_t wv, double *hp, double lp[3],
+                                  double a_lp, double a_hp, int d) {
+        const int c0 = b * kBC, t = c0 - d;
         CVS_UNROLL
         for (int k = 0; k < kBC; k++) {
             const int c = c0 + k;
             if (in(c, K.cw)) {
-                double s = u2d(ring[c & (kRingC - 1)]);
-                if (boost) {
-                    const double lpv = pole(st[0], s, a_hp);         // s += hp.highpass(s)
+                double s = u2d((uint32_t)byte_of(wv, k));
+                if (hp) {
+                    const double lpv = pole(*hp, s, a_hp);
                     s = dadd(s, dsub(s, lpv));
                 }
-                s = pole(st[1], s, a_lp);
-                s = pole(st[2], s, a_lp);
-                s = pole(st[3], s, a_lp);
-                if (!EDGE || c >= d) ring[(c - d) & (kRingC - 1)] = (uint8_t)q8(s);
+                s = pole(lp[0], s, a_lp);
+                s = pole(lp[1], s, a_lp);
+                s = pole(lp[2], s, a_lp);
+                if (!EDGE || c >= d) ring[(t + k) & (kRingC - 1)] = (uint8_t)q8(s);
             }
         }
     }
 
-    // composite_video_yuv_to_ntsc on one block: Y += chroma / 50                     (:434-477)
-    static CVS_HD void modulate_px(const K422 &K, int xi, int j, int u, int v, int &y) {
-        const int ph = (xi + j) & 3;
-        int t = (ph & 1) ? (v - 128) : (u - 128);
-        int q;
-        if (K.amp == 50) q = t;
-        else q = div50(t * K.amp);
-        if (ph & 2) q = -q;
-        y = clamp8(y + q);
+    // composite_video_yuv_to_ntsc for one pixel: y += chroma / 50                        (:434-477)
+    static CVS_HD int modulate_px(const K422 &K, const Row422 &rc, int j, int u, int v, int y) {
+        int q = (u - 128) * rc.mU[j & 3] + (v - 128) * rc.mV[j & 3];
+        if (EDGE && K.amp != 50) q = div50(q * K.amp);
+        return clamp8(y + q);
     }
 
-    // G2: block b of the composite signal
-    static CVS_HD void stage_compose(const K422 &K, const Row422 &rc, Lane422 &ln, int b, bool warp_hs,
-                                     const uint8_t *hsrow) {
-        const int x0 = b * kB, c0 = b * kBC;
+    // G0 + G1: block s enters the rings; input chroma lowpass
+    static CVS_HD void stage_load(const K422 &K, const Geo &G, Lane422 &ln, int s, const StepIO &io) {
+        if (!EDGE || s < G.nbl) {
+            uint8_t *yb = yblk(ln.ry, s);
+            stw(yb, io.y0);
+            stw(yb + 4, io.y1);
+            stw(cblk(ln.ru, s), io.u);
+            stw(cblk(ln.rv, s), io.v);
+        }
+        if ((K.flags & G_IN_LP) && (!EDGE || s < G.nb)) {
+            chroma_lp4(K, ln.ru, s, io.u, &ln.inU[0], &ln.inU[1], K.a_in[0], K.a_inhp[0], K.d_in[0]);
+            chroma_lp4(K, ln.rv, s, io.v, &ln.inV[0], &ln.inV[1], K.a_in[1], K.a_inhp[1], K.d_in[1]);
+        }
+    }
+
+    // G2: block b of the composite signal.  FIRST: the full chain (pre-emphasis, noise, head switch);
+    // !FIRST: plain re-modulation of a block whose luma is final (VHS recombine, -yc-recomb).
+    template <bool FIRST>
+    static CVS_HD void stage_modulate(const K422 &K, const Row422 &rc, Lane422 &ln, int b, bool warp_hs,
+                                      const uint8_t *hsrow) {
+        const int x0 = b * kB;
+        uint8_t *yb = yblk(ln.ry, b), *ub = cblk(ln.ru, b), *vb = cblk(ln.rv, b);
+        const uint32_t y0 = ldw(yb), y1 = ldw(yb + 4), uw = ldw(ub), vw = ldw(vb);
         uint32_t *grp = nullptr, *grp_next = nullptr;
-        if (K.vnoise != 0) {
+        if (FIRST && K.vnoise != 0) {
             grp = ln.rngL.group_ptr(kRngBase + (uint32_t)x0);
             grp_next = ln.rngL.group_ptr(kRngBase + (uint32_t)x0 + kB);
         }
+        int yo[kB];
         CVS_UNROLL
         for (int j = 0; j < kB; j++) {
-            const int x = x0 + j, c = c0 + (j >> 1);
+            const int x = x0 + j;
+            int y = byte_of(j < 4 ? y0 : y1, j & 3);
             if (in(x, K.w)) {
-                const int u = ln.ru[c & (kRingC - 1)], v = ln.rv[c & (kRingC - 1)];
-                int y = ln.ry[x & (kRingY - 1)];
-                modulate_px(K, rc.xi, j, u, v, y);
-                if ((j & 1) && (K.flags & G_NOCOLOR)) ln.ru[c & (kRingC - 1)] = ln.rv[c & (kRingC - 1)] = 128;
-                if (K.flags & G_PREEMPH) {                                     // (:636-650)
-                    double s = u2d((uint32_t)y);
-                    const double lpv = pole(ln.pre, s, K.a_pre);
-                    s = dadd(s, dmul(dsub(s, lpv), K.preemph));
-                    y = q8(s);
+                y = modulate_px(K, rc, j, byte_of(uw, j >> 1), byte_of(vw, j >> 1), y);
+                if (FIRST) {
+                    if (EDGE && (K.flags & G_PREEMPH)) {                       // (:636-650)
+                        double sv = u2d((uint32_t)y);
+                        const double lpv = pole(ln.pre, sv, K.a_pre);
+                        sv = dadd(sv, dmul(dsub(sv, lpv), K.preemph));
+                        y = q8(sv);
+                    }
+                    if (K.vnoise != 0) {                                       // (:653-665)
+                        y = clamp8(y + ln.nY);
+                        const int d = draw_mod(ln.rngL.next_in_group(grp, grp_next, j, kB), (uint32_t)(2 * K.vnoise + 1), K.vmagic, K.vshift);
+                        ln.nY = noise_step(ln.nY, d, K.vnoise);
+                    }
+                    if (warp_hs) {                                             // (:697-731) as a delay line
+                        ln.rya[x & (kRingA - 1)] = (uint8_t)y;
+                        if (rc.hs_delay > 0) y = (x >= rc.hs_delay) ? ln.rya[(x - rc.hs_delay) & (kRingA - 1)] : 16;
+                    }
+                    if (EDGE && hsrow) y = hsrow[x];                           // rotated row from the pre-pass
                 }
-                if (K.vnoise != 0) {                                           // (:653-665)
-                    y = clamp8(y + ln.nY);
-                    const int d = draw_mod(ln.rngL.next_in_group(grp, grp_next, j, kB), (uint32_t)(2 * K.vnoise + 1), K.vmagic, K.vshift);
-                    ln.nY = noise_step(ln.nY, d, K.vnoise);
-                }
-                if (warp_hs) {                                                 // (:697-731) as a delay line
-                    ln.rya[x & (kRingY - 1)] = (uint8_t)y;
-                    if (rc.hs_delay > 0) y = (x >= rc.hs_delay) ? ln.rya[(x - rc.hs_delay) & (kRingY - 1)] : 16;
-                }
-                if (hsrow) y = hsrow[x];                                       // rotated row from the pre-pass
-                ln.ry[x & (kRingY - 1)] = (uint8_t)y;
             }
+            yo[j] = y;                                                         // bytes past the row stay (demod reads two)
+        }
+        stw(yb, pack4(yo[0], yo[1], yo[2], yo[3]));
+        stw(yb + 4, pack4(yo[4], yo[5], yo[6], yo[7]));
+        if (EDGE && (K.flags & G_NOCOLOR)) {                                   // (:473-474); chroma past the row is never read
+            stw(ub, 0x80808080u);
+            stw(vb, 0x80808080u);
         }
     }
 
-    // re-modulation of a block whose luma is already final in the ring (VHS recombine, -yc-recomb)
-    static CVS_HD void stage_remodulate(const K422 &K, const Row422 &rc, Lane422 &ln, int b) {
-        const int x0 = b * kB, c0 = b * kBC;
-        CVS_UNROLL
-        for (int j = 0; j < kB; j++) {
-            const int x = x0 + j, c = c0 + (j >> 1);
-            if (in(x, K.w)) {
-                const int u = ln.ru[c & (kRingC - 1)], v = ln.rv[c & (kRingC - 1)];
-                int y = ln.ry[x & (kRingY - 1)];
-                modulate_px(K, rc.xi, j, u, v, y);
-                if ((j & 1) && (K.flags & G_NOCOLOR)) ln.ru[c & (kRingC - 1)] = ln.rv[c & (kRingC - 1)] = 128;
-                ln.ry[x & (kRingY - 1)] = (uint8_t)y;
-            }
-        }
-    }
-
-    // composite_ntsc_to_yuv on one block (:480-553): box-filtered luma back into the ring, demodulated
-    // chroma returned in U[], V[] (the caller continues with them)
-    static CVS_HD void demod_block(const K422 &K, const Row422 &rc, Lane422 &ln, Demod &dm, int b, int divisor,
-                                   uint32_t dmagic, uint32_t dshift, int U[kBC], int V[kBC]) {
+    // composite_ntsc_to_yuv on one block (:480-553).  y0,y1 = the block, y2 = the next block (two bytes used).
+    static CVS_HD void demod8(const K422 &K, const Row422 &rc, Demod &dm, int b, uint32_t y0, uint32_t y1, uint32_t y2,
+                              int divisor, uint32_t dmagic, uint32_t dshift, int Yn[kB], int U[kBC], int V[kBC]) {
         const int x0 = b * kB;
         int ch[kB];
-        if (EDGE && b == 0) dm.reset(ln.ry[0], ln.ry[1]);
+        if (EDGE && b == 0) dm.reset(byte_of(y0, 0), byte_of(y0, 1));
         const int xflip0 = ((4 - rc.xi) & 3) + 2;          // first flipped index (:527)
         CVS_UNROLL
         for (int j = 0; j < kB; j++) {
             const int x = x0 + j;
+            const int c = (j < 2) ? byte_of(y0, j + 2) : ((j < 6) ? byte_of(y1, j - 2) : byte_of(y2, j - 6));
             ch[j] = 128;
+            Yn[j] = byte_of(j < 4 ? y0 : y1, j & 3);
             if (in(x, K.w)) {
-                const int c = ln.ry[(x + 2) & (kRingY - 1)];
                 const int sum = dm.o1 + dm.o2 + dm.o3 + c;
                 dm.o1 = dm.o2; dm.o2 = dm.o3; dm.o3 = c;
                 const int yn = sum >> 2;
                 int cv = clamp8(c + 128 - yn);
-                if (K.flags & G_NOCOLOR_YC) {
-                    ln.ry[x & (kRingY - 1)] = (uint8_t)cv;
+                if (EDGE && (K.flags & G_NOCOLOR_YC)) {
+                    Yn[j] = cv;                                                // (:504-508)
                 } else {
-                    ln.ry[x & (kRingY - 1)] = (uint8_t)yn;
-                    const bool flip = (((j + rc.xi + 2) & 3) < 2) && (!EDGE || x >= xflip0);
-                    if (flip) cv = 255 - cv;
-                    if (divisor != 50) cv = clamp8(div_trunc((cv - 128) * 50, divisor, dmagic, dshift) + 128);
+                    Yn[j] = yn;
+                    if (!EDGE || x >= xflip0) cv ^= rc.fl[j & 3];
+                    if (EDGE && divisor != 50) cv = clamp8(div_trunc((cv - 128) * 50, divisor, dmagic, dshift) + 128);
                 }
-                ch[j] = cv;
+                ch[j] = cv ^ 0xFF;                                             // 255 - chroma (:539-548)
             }
         }
-        const int odd = rc.xi & 1;
+        const bool odd = (rc.xi & 1) != 0;
         CVS_UNROLL
         for (int k = 0; k < kBC; k++) {
-            if (K.flags & G_NOCOLOR_YC) { U[k] = 128; V[k] = 128; }
+            if (EDGE && (K.flags & G_NOCOLOR_YC)) { U[k] = 128; V[k] = 128; }
             else {
-                const int a = 255 - ch[2 * k], bq = 255 - ch[2 * k + 1];
-                U[k] = odd ? bq : a;
-                V[k] = odd ? a : bq;
+                U[k] = odd ? ch[2 * k + 1] : ch[2 * k];
+                V[k] = odd ? ch[2 * k] : ch[2 * k + 1];
             }
         }
+    }
+
+    // luma bytes of a block back into the ring; in the last block the bytes past the row keep their value
+    static CVS_HD void store_luma(const K422 &K, uint8_t *yb, int x0, const int Y[kB], uint32_t y0, uint32_t y1) {
+        int o[kB];
+        CVS_UNROLL
+        for (int j = 0; j < kB; j++) o[j] = in(x0 + j, K.w) ? Y[j] : byte_of(j < 4 ? y0 : y1, j & 3);
+        stw(yb, pack4(o[0], o[1], o[2], o[3]));
+        stw(yb + 4, pack4(o[4], o[5], o[6], o[7]));
     }
 
     // G3: first demodulation of block b and everything pointwise after it
     static CVS_HD void stage_separate(const K422 &K, const Row422 &rc, Lane422 &ln, int b,
                                       uint32_t amag, uint32_t ashift) {
         const int x0 = b * kB, c0 = b * kBC;
-        int U[kBC], V[kBC];
-        if (!(K.flags & G_NOCOLOR)) {
-            demod_block(K, rc, ln, ln.dm1, b, K.amp_back, amag, ashift, U, V);
+        uint8_t *yb = yblk(ln.ry, b), *ub = cblk(ln.ru, b), *vb = cblk(ln.rv, b);
+        const uint32_t y0 = ldw(yb), y1 = ldw(yb + 4);
+        int Yn[kB], U[kBC], V[kBC];
+        if (!EDGE || !(K.flags & G_NOCOLOR)) {
+            const uint32_t y2 = ldw(yblk(ln.ry, b + 1));
+            demod8(K, rc, ln.dm1, b, y0, y1, y2, K.amp_back, amag, ashift, Yn, U, V);
         } else {
+            const uint32_t uw = ldw(ub), vw = ldw(vb);
             CVS_UNROLL
-            for (int k = 0; k < kBC; k++) { U[k] = ln.ru[(c0 + k) & (kRingC - 1)]; V[k] = ln.rv[(c0 + k) & (kRingC - 1)]; }
+            for (int j = 0; j < kB; j++) Yn[j] = byte_of(j < 4 ? y0 : y1, j & 3);
+            CVS_UNROLL
+            for (int k = 0; k < kBC; k++) { U[k] = byte_of(uw, k); V[k] = byte_of(vw, k); }
         }
         if (K.cnoise != 0) {                                                   // (:738-754)
             uint32_t *grp = ln.rngC.group_ptr(kRngBase + (uint32_t)(2 * c0));
@@ -414,62 +499,51 @@ struct Pipe422 {
                 V[k] = q8(dadd(v_, 128.0));
             }
         }
-        // the unfiltered values stay in the ring: a delayed filter never overwrites the last `delay` samples
-        CVS_UNROLL
-        for (int k = 0; k < kBC; k++) {
-            if (in(c0 + k, K.cw)) {
-                ln.ru[(c0 + k) & (kRingC - 1)] = (uint8_t)U[k];
-                ln.rv[(c0 + k) & (kRingC - 1)] = (uint8_t)V[k];
-            }
-        }
+        // the unfiltered values go into the ring: a delayed filter never overwrites the last `delay` samples
+        const uint32_t uw = pack4(U[0], U[1], U[2], U[3]), vw = pack4(V[0], V[1], V[2], V[3]);
+        stw(ub, uw);
+        stw(vb, vw);
         if (K.flags & G_VHS) {
             CVS_UNROLL
             for (int j = 0; j < kB; j++) {                                     // luma lowpass + boost, then sharpen
-                const int x = x0 + j;
-                if (in(x, K.w)) {
-                    double s = u2d(ln.ry[x & (kRingY - 1)]);
+                if (in(x0 + j, K.w)) {
+                    double s = u2d((uint32_t)Yn[j]);
                     s = pole(ln.lum[0], s, K.a_luma);
                     s = pole(ln.lum[1], s, K.a_luma);
                     s = pole(ln.lum[2], s, K.a_luma);
                     const double lpv = pole(ln.lum[3], s, K.a_luma);
                     s = dadd(s, dmul(dsub(s, lpv), 1.6));
-                    const double y1 = u2d((uint32_t)q8(s));
-                    double ts = pole(ln.lsh[0], y1, K.a_lsharp);
+                    const double y1d = u2d((uint32_t)q8(s));
+                    double ts = pole(ln.lsh[0], y1d, K.a_lsharp);
                     ts = pole(ln.lsh[1], ts, K.a_lsharp);
                     ts = pole(ln.lsh[2], ts, K.a_lsharp);
-                    ln.ry[x & (kRingY - 1)] = (uint8_t)q8(dadd(y1, dmul(dsub(y1, ts), K.sharpen)));
+                    Yn[j] = q8(dadd(y1d, dmul(dsub(y1d, ts), K.sharpen)));
                 }
             }
-            CVS_UNROLL
-            for (int k = 0; k < kBC; k++) {                                    // chroma lowpass, written cd samples back
-                const int c = c0 + k;
-                if (in(c, K.cw)) {
-                    double s = u2d((uint32_t)U[k]);
-                    s = pole(ln.chU[0], s, K.a_ch); s = pole(ln.chU[1], s, K.a_ch); s = pole(ln.chU[2], s, K.a_ch);
-                    if (!EDGE || c >= K.cd) ln.ru[(c - K.cd) & (kRingC - 1)] = (uint8_t)q8(s);
-                    s = u2d((uint32_t)V[k]);
-                    s = pole(ln.chV[0], s, K.a_ch); s = pole(ln.chV[1], s, K.a_ch); s = pole(ln.chV[2], s, K.a_ch);
-                    if (!EDGE || c >= K.cd) ln.rv[(c - K.cd) & (kRingC - 1)] = (uint8_t)q8(s);
-                }
-            }
+            store_luma(K, yb, x0, Yn, y0, y1);
+            chroma_lp4(K, ln.ru, b, uw, nullptr, ln.chU, K.a_ch, 0.0, K.cd);   // written cd samples back
+            chroma_lp4(K, ln.rv, b, vw, nullptr, ln.chV, K.a_ch, 0.0, K.cd);
+        } else {
+            store_luma(K, yb, x0, Yn, y0, y1);
         }
     }
 
     // G4 part 1: the lane's own chroma of block b before the vertical blend (what the lane below needs)
     static CVS_HD void blend_fetch(const Lane422 &ln, int b, uint32_t &pu, uint32_t &pv) {
-        const int c0 = b * kBC;
-        pu = pack4(ln.ru[c0 & (kRingC - 1)], ln.ru[(c0 + 1) & (kRingC - 1)], ln.ru[(c0 + 2) & (kRingC - 1)], ln.ru[(c0 + 3) & (kRingC - 1)]);
-        pv = pack4(ln.rv[c0 & (kRingC - 1)], ln.rv[(c0 + 1) & (kRingC - 1)], ln.rv[(c0 + 2) & (kRingC - 1)], ln.rv[(c0 + 3) & (kRingC - 1)]);
+        pu = ldw(cblk(ln.ru, b));
+        pv = ldw(cblk(ln.rv, b));
     }
     // G4 part 2: blend with the row above (:858-883), chroma sharpen (:904-925), re-modulate (:927-930)
     static CVS_HD void stage_vhs_chroma(const K422 &K, const Row422 &rc, Lane422 &ln, int b, uint32_t pu, uint32_t pv,
                                         uint32_t au, uint32_t av) {
         const int c0 = b * kBC;
+        int U[kBC], V[kBC];
         CVS_UNROLL
         for (int k = 0; k < kBC; k++) {
-            const int c = c0 + k;
-            if (in(c, K.cw)) {
-                int u = byte_of(pu, k), v = byte_of(pv, k);
+            U[k] = byte_of(pu, k);
+            V[k] = byte_of(pv, k);
+            if (in(c0 + k, K.cw)) {
+                int u = U[k], v = V[k];
                 if ((K.flags & G_VBLEND) && rc.row >= 1) {
                     // the delay line starts at 128 and row 0 never enters it
                     const int ua = (rc.row == 1) ? 128 : byte_of(au, k), va = (rc.row == 1) ? 128 : byte_of(av, k);
@@ -478,89 +552,58 @@ struct Pipe422 {
                 }
                 double s = u2d((uint32_t)u), ts;
                 ts = pole(ln.csU[0], s, K.a_csharp); ts = pole(ln.csU[1], ts, K.a_csharp); ts = pole(ln.csU[2], ts, K.a_csharp);
-                ln.ru[c & (kRingC - 1)] = (uint8_t)q8(dadd(s, dmul(dsub(s, ts), K.sharpen_c)));
+                U[k] = q8(dadd(s, dmul(dsub(s, ts), K.sharpen_c)));
                 s = u2d((uint32_t)v);
                 ts = pole(ln.csV[0], s, K.a_csharp); ts = pole(ln.csV[1], ts, K.a_csharp); ts = pole(ln.csV[2], ts, K.a_csharp);
-                ln.rv[c & (kRingC - 1)] = (uint8_t)q8(dadd(s, dmul(dsub(s, ts), K.sharpen_c)));
+                V[k] = q8(dadd(s, dmul(dsub(s, ts), K.sharpen_c)));
             }
         }
-        if (!(K.flags & G_SVIDEO)) stage_remodulate(K, rc, ln, b);
+        stw(cblk(ln.ru, b), pack4(U[0], U[1], U[2], U[3]));
+        stw(cblk(ln.rv, b), pack4(V[0], V[1], V[2], V[3]));
+        if (!(K.flags & G_SVIDEO)) stage_modulate<false>(K, rc, ln, b, false, nullptr);
     }
 
     // a demodulation whose result goes straight back into the rings (VHS recombine, -yc-recomb)
     static CVS_HD void stage_redemod(const K422 &K, const Row422 &rc, Lane422 &ln, Demod &dm, int b,
                                      uint32_t amag, uint32_t ashift) {
-        const int c0 = b * kBC;
-        int U[kBC], V[kBC];
-        demod_block(K, rc, ln, dm, b, K.amp, amag, ashift, U, V);
-        CVS_UNROLL
-        for (int k = 0; k < kBC; k++) {
-            if (in(c0 + k, K.cw)) {
-                ln.ru[(c0 + k) & (kRingC - 1)] = (uint8_t)U[k];
-                ln.rv[(c0 + k) & (kRingC - 1)] = (uint8_t)V[k];
-            }
-        }
+        uint8_t *yb = yblk(ln.ry, b);
+        const uint32_t y0 = ldw(yb), y1 = ldw(yb + 4), y2 = ldw(yblk(ln.ry, b + 1));
+        int Yn[kB], U[kBC], V[kBC];
+        demod8(K, rc, dm, b, y0, y1, y2, K.amp, amag, ashift, Yn, U, V);
+        store_luma(K, yb, b * kB, Yn, y0, y1);
+        stw(cblk(ln.ru, b), pack4(U[0], U[1], U[2], U[3]));
+        stw(cblk(ln.rv, b), pack4(V[0], V[1], V[2], V[3]));
     }
 
-    static CVS_HD void stage_dropout(const K422 &K, Lane422 &ln, int b) {       // (:932-941)
-        const int c0 = b * kBC;
-        CVS_UNROLL
-        for (int k = 0; k < kBC; k++)
-            if (in(c0 + k, K.cw)) ln.ru[(c0 + k) & (kRingC - 1)] = ln.rv[(c0 + k) & (kRingC - 1)] = 128;
+    static CVS_HD void stage_dropout(Lane422 &ln, int b) {                      // (:932-941)
+        stw(cblk(ln.ru, b), 0x80808080u);
+        stw(cblk(ln.rv, b), 0x80808080u);
     }
 };
 
-// the division constants of the two demodulator gains (amp_back for the first, amp for the others)
-struct DivPair {
-    uint32_t back_magic, back_shift, amp_magic, amp_shift;
-};
-
-// What one step exchanges with its caller: block s of the source row comes in, the pre-blend chroma of
-// block bV goes to the lane below between front() and back(), block bS comes out.
-struct StepIO {
-    uint32_t y0, y1, u, v;        // in: block s (bytes beyond the data are don't-care); out: block bS
-};
-
-// G0..G3 (+ the fetch of G4).  `load` = block s carries data for this row.
+// G0..G3 (+ the fetch of G4)
 template <bool EDGE>
-CVS_HD void step_front(const K422 &K, const DivPair &dv, const Row422 &rc, Lane422 &ln, int s, const StepIO &in,
-                       bool warp_hs, const uint8_t *hsrow, uint32_t &pu, uint32_t &pv) {
+CVS_HD void step_front(const K422 &K, const Lags &L, const Geo &G, const DivPair &dv, const Row422 &rc, Lane422 &ln, int s,
+                       const StepIO &in, bool warp_hs, const uint8_t *hsrow, uint32_t &pu, uint32_t &pv) {
     typedef Pipe422<EDGE> P;
-    const Lags L = lags_of(K);
-    const int nb = (K.w + kB - 1) / kB;               // blocks with pixels
-    const int nbl = (K.w + 2 + kB - 1) / kB;          // blocks the ring must hold (two bytes past the row)
-    if (!EDGE || s < nbl) {
-        const int x0 = s * kB, c0 = s * kBC;
-        CVS_UNROLL
-        for (int j = 0; j < 4; j++) {
-            ln.ry[(x0 + j) & (kRingY - 1)] = (uint8_t)byte_of(in.y0, j);
-            ln.ry[(x0 + 4 + j) & (kRingY - 1)] = (uint8_t)byte_of(in.y1, j);
-            ln.ru[(c0 + j) & (kRingC - 1)] = (uint8_t)byte_of(in.u, j);
-            ln.rv[(c0 + j) & (kRingC - 1)] = (uint8_t)byte_of(in.v, j);
-        }
-    }
-    if ((K.flags & G_IN_LP) && (!EDGE || s < nb)) {
-        P::chroma_lp_block(K, ln.ru, s, ln.inU, K.a_in[0], K.a_inhp[0], true, K.d_in[0]);
-        P::chroma_lp_block(K, ln.rv, s, ln.inV, K.a_in[1], K.a_inhp[1], true, K.d_in[1]);
-    }
+    P::stage_load(K, G, ln, s, in);
     const int bM = s - L.bM;
-    if (!EDGE || (bM >= 0 && bM < nb)) P::stage_compose(K, rc, ln, bM, warp_hs, hsrow);
+    if (!EDGE || (bM >= 0 && bM < G.nb)) P::template stage_modulate<true>(K, rc, ln, bM, warp_hs, hsrow);
     const int bD = s - L.bD;
-    if (!EDGE || (bD >= 0 && bD < nb)) P::stage_separate(K, rc, ln, bD, dv.back_magic, dv.back_shift);
+    if (!EDGE || (bD >= 0 && bD < G.nb)) P::stage_separate(K, rc, ln, bD, dv.back_magic, dv.back_shift);
     pu = pv = 0;
     if (K.flags & G_VHS) {
         const int bV = s - L.bV;
-        if (!EDGE || (bV >= 0 && bV < nb)) P::blend_fetch(ln, bV, pu, pv);
+        if (!EDGE || (bV >= 0 && bV < G.nb)) P::blend_fetch(ln, bV, pu, pv);
     }
 }
 
-// G4..store.  Returns true when `out` holds block *bs of the finished row.
+// G4..store.  Returns true when `out` holds block bs of the finished row.
 template <bool EDGE>
-CVS_HD bool step_back(const K422 &K, const DivPair &dv, const Row422 &rc, Lane422 &ln, int s,
+CVS_HD bool step_back(const K422 &K, const Lags &L, const Geo &G, const DivPair &dv, const Row422 &rc, Lane422 &ln, int s,
                       uint32_t pu, uint32_t pv, uint32_t au, uint32_t av, StepIO &out, int &bs) {
     typedef Pipe422<EDGE> P;
-    const Lags L = lags_of(K);
-    const int nb = (K.w + kB - 1) / kB;
+    const int nb = G.nb;
     if (K.flags & G_VHS) {
         const int bV = s - L.bV;
         if (!EDGE || (bV >= 0 && bV < nb)) P::stage_vhs_chroma(K, rc, ln, bV, pu, pv, au, av);
@@ -570,10 +613,10 @@ CVS_HD bool step_back(const K422 &K, const DivPair &dv, const Row422 &rc, Lane42
         }
     }
     const int bE = s - L.bE;
-    if ((rc.rflags & RG_DROPOUT) && (!EDGE || (bE >= 0 && bE < nb))) P::stage_dropout(K, ln, bE);
-    for (int i = 0; i < K.recombine; i++) {            // -yc-recomb: rare, state lives in shared memory
+    if ((rc.rflags & RG_DROPOUT) && (!EDGE || (bE >= 0 && bE < nb))) P::stage_dropout(ln, bE);
+    for (int i = 0; EDGE && i < K.recombine; i++) {    // -yc-recomb: rare, state lives in shared memory
         const int bm = bE - i, bd = bE - i - 1;
-        if (bm >= 0 && bm < nb) Pipe422<true>::stage_remodulate(K, rc, ln, bm);
+        if (bm >= 0 && bm < nb) Pipe422<true>::template stage_modulate<false>(K, rc, ln, bm, false, nullptr);
         if (bd >= 0 && bd < nb) {
             Demod dm;
             dm.o1 = ln.rcomb[3 * i]; dm.o2 = ln.rcomb[3 * i + 1]; dm.o3 = ln.rcomb[3 * i + 2];
@@ -583,21 +626,24 @@ CVS_HD bool step_back(const K422 &K, const DivPair &dv, const Row422 &rc, Lane42
     }
     const int bF = s - L.bF;
     if (!EDGE || (bF >= 0 && bF < nb)) {
-        if (K.flags & G_OUT_FULL) {
-            P::chroma_lp_block(K, ln.ru, bF, ln.outU, K.a_out[0], K.a_outhp[0], true, K.d_out[0]);
-            P::chroma_lp_block(K, ln.rv, bF, ln.outV, K.a_out[1], K.a_outhp[1], true, K.d_out[1]);
-        } else if (K.flags & G_OUT_LITE) {
-            P::chroma_lp_block(K, ln.ru, bF, ln.outU, K.a_out[0], 0.0, false, K.d_out[0]);
-            P::chroma_lp_block(K, ln.rv, bF, ln.outV, K.a_out[1], 0.0, false, K.d_out[1]);
+        if (K.flags & (G_OUT_FULL | G_OUT_LITE)) {
+            const uint32_t uw = ldw(cblk(ln.ru, bF)), vw = ldw(cblk(ln.rv, bF));
+            if (K.flags & G_OUT_FULL) {
+                P::chroma_lp4(K, ln.ru, bF, uw, &ln.outU[0], &ln.outU[1], K.a_out[0], K.a_outhp[0], K.d_out[0]);
+                P::chroma_lp4(K, ln.rv, bF, vw, &ln.outV[0], &ln.outV[1], K.a_out[1], K.a_outhp[1], K.d_out[1]);
+            } else {
+                P::chroma_lp4(K, ln.ru, bF, uw, nullptr, &ln.outU[1], K.a_out[0], 0.0, K.d_out[0]);
+                P::chroma_lp4(K, ln.rv, bF, vw, nullptr, &ln.outV[1], K.a_out[1], 0.0, K.d_out[1]);
+            }
         }
     }
     bs = s - L.bS;
     if (EDGE && (bs < 0 || bs >= nb)) return false;
-    const int x0 = bs * kB, c0 = bs * kBC;
-    out.y0 = pack4(ln.ry[x0 & (kRingY - 1)], ln.ry[(x0 + 1) & (kRingY - 1)], ln.ry[(x0 + 2) & (kRingY - 1)], ln.ry[(x0 + 3) & (kRingY - 1)]);
-    out.y1 = pack4(ln.ry[(x0 + 4) & (kRingY - 1)], ln.ry[(x0 + 5) & (kRingY - 1)], ln.ry[(x0 + 6) & (kRingY - 1)], ln.ry[(x0 + 7) & (kRingY - 1)]);
-    out.u = pack4(ln.ru[c0 & (kRingC - 1)], ln.ru[(c0 + 1) & (kRingC - 1)], ln.ru[(c0 + 2) & (kRingC - 1)], ln.ru[(c0 + 3) & (kRingC - 1)]);
-    out.v = pack4(ln.rv[c0 & (kRingC - 1)], ln.rv[(c0 + 1) & (kRingC - 1)], ln.rv[(c0 + 2) & (kRingC - 1)], ln.rv[(c0 + 3) & (kRingC - 1)]);
+    const uint8_t *yb = yblk(ln.ry, bs);
+    out.y0 = ldw(yb);
+    out.y1 = ldw(yb + 4);
+    out.u = ldw(cblk(ln.ru, bs));
+    out.v = ldw(cblk(ln.rv, bs));
     return true;
 }
 
@@ -611,31 +657,34 @@ CVS_HD void headswitch_row(const K422 &K, const Row422 &rc_in, Lane422 &ln, cons
     Row422 rc = rc_in;
     rc.rflags &= ~(uint32_t)(RG_HEADSW | RG_HEADSW_PRE);
     rc.hs_delay = 0;
-    const int w = K.w, tw = w + w / 10, nb = (w + kB - 1) / kB;
+    const Geo G = geo_of(K);
+    const int w = K.w, tw = w + w / 10, nb = G.nb;
     for (int x = 0; x < w; x++) scratch[x] = 16;
     for (int s = 0; s <= nb; s++) {
         if (s < nb) {
+            StepIO io;
+            io.y0 = io.y1 = io.u = io.v = 0;
             for (int j = 0; j < kB; j++)
-                if (s * kB + j < w) ln.ry[(s * kB + j) & (kRingY - 1)] = yrow[s * kB + j];
+                if (s * kB + j < w) {
+                    if (j < 4) io.y0 |= (uint32_t)yrow[s * kB + j] << (8 * j);
+                    else io.y1 |= (uint32_t)yrow[s * kB + j] << (8 * (j - 4));
+                }
             for (int k = 0; k < kBC; k++)
                 if (s * kBC + k < K.cw) {
-                    ln.ru[(s * kBC + k) & (kRingC - 1)] = urow[s * kBC + k];
-                    ln.rv[(s * kBC + k) & (kRingC - 1)] = vrow[s * kBC + k];
+                    io.u |= (uint32_t)urow[s * kBC + k] << (8 * k);
+                    io.v |= (uint32_t)vrow[s * kBC + k] << (8 * k);
                 }
-            if (K.flags & G_IN_LP) {
-                P::chroma_lp_block(K, ln.ru, s, ln.inU, K.a_in[0], K.a_inhp[0], true, K.d_in[0]);
-                P::chroma_lp_block(K, ln.rv, s, ln.inV, K.a_in[1], K.a_inhp[1], true, K.d_in[1]);
-            }
+            P::stage_load(K, G, ln, s, io);
         }
         const int bM = s - 1;
         if (bM >= 0 && bM < nb) {
-            P::stage_compose(K, rc, ln, bM, false, nullptr);
+            P::template stage_modulate<true>(K, rc, ln, bM, false, nullptr);
             for (int j = 0; j < kB; j++) {
                 const int x = bM * kB + j;
                 if (x < w) {
                     int xd = (x - shif) % tw;
                     if (xd < 0) xd += tw;
-                    if (xd < w) scratch[xd] = ln.ry[x & (kRingY - 1)];
+                    if (xd < w) scratch[xd] = yblk(ln.ry, bM)[j];
                 }
             }
         }
@@ -649,7 +698,7 @@ CVS_HD void interior_steps(const K422 &K, int &s_lo, int &s_hi) {
     s_lo = L.bS + 2;                                  // the oldest stage is past block 1 (c >= max delay, x >= first flip)
     s_hi = nb_full;                                   // the load front is a complete block inside the row
     if (s_hi < s_lo) s_hi = s_lo;
-    if (K.recombine != 0) s_hi = s_lo;                // -yc-recomb runs the general path
+    if (K.flags & G_GENERAL) s_hi = s_lo;             // rare switches only exist in the general variant
 }
 
 }  // namespace cvs422

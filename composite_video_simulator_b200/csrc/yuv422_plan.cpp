@@ -65,10 +65,12 @@ int make_k422(const cvs422_params &p, int w, int h, K422 &K, DivPair &dv, std::v
     if (p.vhs_chroma_vert_blend && ntsc) f |= G_VBLEND;               // (:858)
     if (p.vhs_svideo_out) f |= G_SVIDEO;
     if (p.video_chroma_phase_noise != 0) f |= G_PHASE;
-    K.flags = f;
     K.amp = p.subcarrier_amplitude;
     K.amp_back = p.subcarrier_amplitude_back;
     K.recombine = p.video_yc_recombine > 0 ? p.video_yc_recombine : 0;
+    // the interior (fast) variant of the kernel only knows the common switches
+    if ((f & (G_PREEMPH | G_NOCOLOR | G_NOCOLOR_YC)) || K.amp != 50 || K.amp_back != 50 || K.recombine != 0) f |= G_GENERAL;
+    K.flags = f;
     if (K.recombine > kMaxRecombine) return CVS_ERR_UNSUPPORTED;
     // divisors of the demodulators (:533): amp_back for the first, amp for the VHS / -yc-recomb ones
     const bool first_demod = !p.nocolor_subcarrier, later_demod = (p.emulating_vhs && !p.vhs_svideo_out) || K.recombine > 0;

@@ -13,7 +13,7 @@ using namespace cvs422;
 namespace {
 
 struct LaneMem {
-    uint8_t ry[kRingY], ru[kRingC], rv[kRingC], rya[kRingY];
+    alignas(4) uint8_t ry[kRingY], ru[kRingC], rv[kRingC], rya[kRingA];
     uint32_t ringL[cvs::kRngSlots], ringC[cvs::kRngSlots];
     int32_t rcomb[3 * kMaxRecombine];
 };
@@ -80,9 +80,11 @@ int emu422_process(const cvs422_params *p, unsigned long long rng_pos,
     }
 
     const int nl = g.nl, nsteps = line_steps(K);
+    const Lags LG = lags_of(K);
+    const Geo GE = geo_of(K);
     int s_lo, s_hi;
     interior_steps(K, s_lo, s_hi);
-    if (force_general) s_hi = s_lo;
+    if (force_general || fs.hs_count > 0) s_hi = s_lo;     // (pre-pass rows only exist in the general variant)
     int status = CVS_OK;
     for (int wp = 0; wp * 31 < nl; wp++) {
         std::vector<LaneMem> mem(32);
@@ -136,8 +138,8 @@ int emu422_process(const cvs422_params *p, unsigned long long rng_pos,
                 in.y1 = load_word(sy.data(), by, y * ly + x0 + 4, w + 2 - x0 - 4);
                 in.u = load_word(su.data(), bu, y * lu + c0, K.cw - c0);
                 in.v = load_word(sv.data(), bv, y * lv + c0, K.cw - c0);
-                if (fast) step_front<false>(K, dv, rc[lane], ln[lane], s, in, warp_hs, hsrow[lane], pu[lane], pv[lane]);
-                else step_front<true>(K, dv, rc[lane], ln[lane], s, in, warp_hs, hsrow[lane], pu[lane], pv[lane]);
+                if (fast) step_front<false>(K, LG, GE, dv, rc[lane], ln[lane], s, in, warp_hs, hsrow[lane], pu[lane], pv[lane]);
+                else step_front<true>(K, LG, GE, dv, rc[lane], ln[lane], s, in, warp_hs, hsrow[lane], pu[lane], pv[lane]);
                 // first demodulation of a -yc-recomb round: its box starts from the row's first two luma samples
                 // as they are when that stage reaches block 0 (handled inside demod_block via b == 0)
             }
@@ -146,8 +148,8 @@ int emu422_process(const cvs422_params *p, unsigned long long rng_pos,
                 StepIO out;
                 int bs;
                 bool have;
-                if (fast) have = step_back<false>(K, dv, rc[lane], ln[lane], s, pu[lane], pv[lane], au, av, out, bs);
-                else have = step_back<true>(K, dv, rc[lane], ln[lane], s, pu[lane], pv[lane], au, av, out, bs);
+                if (fast) have = step_back<false>(K, LG, GE, dv, rc[lane], ln[lane], s, pu[lane], pv[lane], au, av, out, bs);
+                else have = step_back<true>(K, LG, GE, dv, rc[lane], ln[lane], s, pu[lane], pv[lane], au, av, out, bs);
                 if (have && valid[lane]) {
                     const long long y = (long long)field + 2 * rows[lane];
                     for (int j = 0; j < kB; j++) {
