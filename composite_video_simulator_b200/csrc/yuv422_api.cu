@@ -47,7 +47,8 @@ struct Slot {
     uint32_t *h_rowinfo = nullptr, *d_rowinfo = nullptr;
     int32_t *h_hsshift = nullptr, *d_hsshift = nullptr;
     HsItem422 *h_items = nullptr, *d_items = nullptr;
-    cudaEvent_t uploaded = nullptr;
+    cudaEvent_t uploaded = nullptr;        // the table copies out of this slot's pinned buffers have finished
+    cudaEvent_t kernel_done = nullptr;     // the kernels reading this slot's device tables have finished
     bool in_flight = false;
 };
 
@@ -67,6 +68,7 @@ struct cvs422_ctx {
     int max_w = 0, max_h = 0, max_batch = 0, nl_max = 0, wpf_max = 0, hs_max = 0, halo_pitch_max = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = true;
+    cudaStream_t s_tab = nullptr;                 // uploads the per-batch side tables while the previous batch computes
     RandCursor cur;
     std::vector<std::unique_ptr<DevPlan422>> plans;
     Slot slots[kSlots];
@@ -98,12 +100,14 @@ void free_all(cvs422_ctx *c) {
         if (s.h_items) cudaFreeHost(s.h_items);
         cudaFree(s.d_fields); cudaFree(s.d_rowinfo); cudaFree(s.d_hsshift); cudaFree(s.d_items);
         if (s.uploaded) cudaEventDestroy(s.uploaded);
+        if (s.kernel_done) cudaEventDestroy(s.kernel_done);
         s = Slot();
     }
     cudaFree(c->d_scratch); cudaFree(c->d_halo); cudaFree(c->d_status); cudaFree(c->d_lut); cudaFree(c->d_planes);
     if (c->h_status) cudaFreeHost(c->h_status);
     for (auto &pr : c->ev_pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     c->ev_pool.clear();
+    if (c->s_tab) cudaStreamDestroy(c->s_tab);
     if (c->stream && c->own_stream) cudaStreamDestroy(c->stream);
 }
 
@@ -161,7 +165,11 @@ int run_device(cvs422_ctx *c, uint8_t *y, uint8_t *u, uint8_t *v, long long psy,
     DevPlan422 *plan[2] = {nullptr, nullptr};
     Slot &sl = c->slots[c->next_slot];
     c->next_slot = (c->next_slot + 1) % kSlots;
-    if (sl.in_flight) { CVS_CUDA(cudaEventSynchronize(sl.uploaded)); sl.in_flight = false; }
+    if (sl.in_flight) {
+        CVS_CUDA(cudaEventSynchronize(sl.uploaded));            // pinned buffers free again
+        CVS_CUDA(cudaStreamWaitEvent(c->s_tab, sl.kernel_done, 0));   // device tables free again
+        sl.in_flight = false;
+    }
 
     const int nl_max = (h + 1) / 2;
     const int wpf = (nl_max + kRowsPerWarp - 1) / kRowsPerWarp;
@@ -195,14 +203,15 @@ int run_device(cvs422_ctx *c, uint8_t *y, uint8_t *u, uint8_t *v, long long psy,
             nitems++;
         }
     }
-    CVS_CUDA(cudaMemcpyAsync(sl.d_fields, sl.h_fields, (size_t)n * sizeof(FieldDesc422), cudaMemcpyHostToDevice, c->stream));
-    CVS_CUDA(cudaMemcpyAsync(sl.d_rowinfo, sl.h_rowinfo, (size_t)n * (size_t)c->nl_max * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    CVS_CUDA(cudaMemcpyAsync(sl.d_fields, sl.h_fields, (size_t)n * sizeof(FieldDesc422), cudaMemcpyHostToDevice, c->s_tab));
+    CVS_CUDA(cudaMemcpyAsync(sl.d_rowinfo, sl.h_rowinfo, (size_t)n * (size_t)c->nl_max * sizeof(uint32_t), cudaMemcpyHostToDevice, c->s_tab));
     if (nitems > 0) {
-        CVS_CUDA(cudaMemcpyAsync(sl.d_hsshift, sl.h_hsshift, (size_t)n * (size_t)c->hs_max * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-        CVS_CUDA(cudaMemcpyAsync(sl.d_items, sl.h_items, (size_t)nitems * sizeof(HsItem422), cudaMemcpyHostToDevice, c->stream));
+        CVS_CUDA(cudaMemcpyAsync(sl.d_hsshift, sl.h_hsshift, (size_t)n * (size_t)c->hs_max * sizeof(int32_t), cudaMemcpyHostToDevice, c->s_tab));
+        CVS_CUDA(cudaMemcpyAsync(sl.d_items, sl.h_items, (size_t)nitems * sizeof(HsItem422), cudaMemcpyHostToDevice, c->s_tab));
     }
-    CVS_CUDA(cudaEventRecord(sl.uploaded, c->stream));
+    CVS_CUDA(cudaEventRecord(sl.uploaded, c->s_tab));
     sl.in_flight = true;
+    CVS_CUDA(cudaStreamWaitEvent(c->stream, sl.uploaded, 0));
 
     a.fields = sl.d_fields;
     a.nfields = n;
@@ -233,6 +242,7 @@ int run_device(cvs422_ctx *c, uint8_t *y, uint8_t *u, uint8_t *v, long long psy,
     }
     CVS_CUDA(launch_yuv422(a, sl.d_items, nitems, c->stream));
     if (e1) CVS_CUDA(cudaEventRecord(e1, c->stream));
+    CVS_CUDA(cudaEventRecord(sl.kernel_done, c->stream));
     c->launches += 1 + (wpf > 1 ? 1 : 0) + (nitems > 0 ? 1 : 0);
     return CVS_OK;
 }
@@ -268,6 +278,7 @@ int cvs422_create(cvs422_ctx **out, const cvs422_params *p, int device, int max_
     c->halo_pitch_max = round_up(max_w + 2, 16) + 2 * round_up(max_w / 2, 16);
     c->cur.seed(1);
     bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&c->s_tab, cudaStreamNonBlocking) == cudaSuccess;
     for (auto &s : c->slots) {
         if (!ok) break;
         const size_t nb = (size_t)max_batch;
@@ -280,6 +291,7 @@ int cvs422_create(cvs422_ctx **out, const cvs422_params *p, int device, int max_
         ok = ok && cudaMalloc((void **)&s.d_hsshift, nb * (size_t)c->hs_max * sizeof(int32_t)) == cudaSuccess;
         ok = ok && cudaMalloc((void **)&s.d_items, nb * (size_t)c->hs_max * sizeof(HsItem422)) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&s.uploaded, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&s.kernel_done, cudaEventDisableTiming) == cudaSuccess;
         if (ok) std::memset(s.h_hsshift, 0, nb * (size_t)c->hs_max * sizeof(int32_t));
     }
     ok = ok && cudaMalloc((void **)&c->d_scratch, (size_t)max_batch * (size_t)c->hs_max * (size_t)max_w) == cudaSuccess;
