@@ -27,3 +27,14 @@ def stream_position(params, w, h, g):
 def chunk(step, rank, world, batch):
     """(first global field index, count) of rank's share of one step."""
     return (step * world + rank) * batch, batch
+
+
+def stream_position_yuv422(params, w, h, g):
+    """The same closed form for the 4:2:2 path (include/cvs_yuv422.h): its draw layout differs
+    (ffmpeg_to_composite.cpp:653-941) but it also depends on the field parity only."""
+    import ctypes as C
+    from . import yuv422
+    L = yuv422._bind(["cvs422_draws_per_field"])
+    d_even = L.cvs422_draws_per_field(C.byref(params), w, h, field_parity(0))
+    d_odd = L.cvs422_draws_per_field(C.byref(params), w, h, field_parity(1))
+    return ((g + 1) // 2) * d_even + (g // 2) * d_odd

@@ -75,3 +75,56 @@ def test_two_ranks_equal_serial(oracle, tmp_path):
                                       src.ctypes.data_as(C.c_void_p), 4 * W, W, H, 0, 0, sharding.field_parity(k),
                                       C.c_ulonglong(k))
         assert np.array_equal(dst, got[k]), k
+
+
+# ---- the 4:2:2 path -------------------------------------------------------------------------------
+
+W2, H2 = 98, 65
+ARGV2 = ["-vhs", "-vhs-speed", "lp"]
+
+
+def _rank_main_yuv422(rank, world, port, out_dir):
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from composite_video_simulator_b200 import yuv422
+    emu = helpers.load_emu422()
+    buf = torch.zeros(C.sizeof(yuv422.Yuv422Params), dtype=torch.uint8)
+    if rank == 0:
+        buf.copy_(torch.frombuffer(bytearray(bytes(helpers.params422(*ARGV2))), dtype=torch.uint8))
+    dist.broadcast(buf, src=0)
+    p = yuv422.Yuv422Params.from_buffer_copy(buf.numpy().tobytes())
+    ks, pics = [], []
+    for step in range(STEPS):
+        first, count = sharding.chunk(step, rank, world, B)
+        out, _ = helpers.run_emu422(emu, p, W2, H2, count, first=first,
+                                    rng_pos=sharding.stream_position_yuv422(p, W2, H2, first))
+        for i, (Y, U, V) in enumerate(out):
+            ks.append(first + i)
+            pics.append(np.concatenate([Y.ravel(), U.ravel(), V.ravel()]))
+    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), ks=np.array(ks), pics=np.stack(pics))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_equal_serial_yuv422(tmp_path):
+    import torch.multiprocessing as mp
+    world = 2
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_rank_main_yuv422, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    got = {}
+    for r in range(world):
+        z = np.load(os.path.join(str(tmp_path), "rank%d.npz" % r))
+        for k, pic in zip(z["ks"], z["pics"]):
+            got[int(k)] = pic
+    n = world * B * STEPS
+    assert sorted(got) == list(range(n))
+    p = helpers.params422(*ARGV2)
+    want, g = helpers.run_oracle422(helpers.load_oracle422(), p, W2, H2, n)
+    assert g.pos == sharding.stream_position_yuv422(p, W2, H2, n)
+    for k in range(n):
+        Y, U, V = want[k]
+        assert np.array_equal(np.concatenate([Y.ravel(), U.ravel(), V.ravel()]), got[k]), k
