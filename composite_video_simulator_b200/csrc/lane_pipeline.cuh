@@ -479,11 +479,20 @@ CVS_HD int noise_step(int noise, int d, int v) {
     t += (int)((uint32_t)t >> 31);                     // C '/ 2' truncates toward zero
     return t >> 1;
 }
+// draw + update in one expression: noise + n - (q m + v) is one IADD3 fed by one IMAD on the device
+CVS_HD int noise_draw(int noise, uint32_t raw, uint32_t m, uint32_t magic, uint32_t shift, int v) {
+    const uint32_t n = raw >> 1;                       // rand() = q >> 1
+    const uint32_t q = umulhi32(n, magic) >> shift;
+    int t = noise + (int)n - (int)(q * m + (uint32_t)v);
+    t += (int)((uint32_t)t >> 31);
+    return t >> 1;
+}
 
 // ---- per-row constants --------------------------------------------------------------------------
 template <typename R>
 struct RowConst {
-    R mI[4], mQ[4];      // QAM carrier taps for (x & 3): Umult/Vmult rotated by the line phase xi (:1465-1466)
+    R sM;                // QAM carrier sign of x = 0 (mod 4): +1 when (xi & 2) == 0 (Umult/Vmult = {1,0,-1,0}/{0,1,0,-1}
+                         // rotated by the line phase xi, :1465-1466); the taps of x & 3 = j follow from xi and sM
     R sgA;               // demod sign for even x with (x & 2) == 0; the (x & 2) != 0 sign is -sgA
     R sinp, cosp, nsinp; // chroma phase noise rotation of this row (:1748-1749); nsinp = -sinp
     int xi;              // subcarrier phase index (:1473-1480)
@@ -496,12 +505,7 @@ struct RowConst {
 template <typename R>
 CVS_HD void rowconst_set_phase(RowConst<R> &rc, int xi) {
     rc.xi = xi;
-    CVS_UNROLL
-    for (int j = 0; j < 4; j++) {
-        const int ph = (xi + j) & 3;
-        rc.mI[j] = (R)((ph == 0) ? 1 : (ph == 2) ? -1 : 0);
-        rc.mQ[j] = (R)((ph == 1) ? 1 : (ph == 3) ? -1 : 0);
-    }
+    rc.sM = (R)((xi & 2) ? -1 : 1);
     // I[x] = -flip(x+xi) * chroma[x+xi]; for even x with (x&3)==0 the carrier is flipped iff xi is odd
     rc.sgA = (R)((xi & 1) ? 1 : -1);
 }
@@ -568,16 +572,23 @@ struct Lane {
     }
 };
 
-// QAM modulation of one sample (chroma_into_luma, :1486-1490).  amp == 50 makes (v*50)/50 == v.
+// QAM modulation of one sample (chroma_into_luma, :1486-1490): Y += (I amp Umult[ph] + Q amp Vmult[ph]) / 50 with
+// ph = (xi + x) & 3, Umult = {1,0,-1,0}, Vmult = {0,1,0,-1}: exactly one of the two taps is +-1, so the sample is
+// Y + sg * (ph odd ? Q : I) with sg = -1 for ph >= 2 (exact; amp == 50 makes (v*50)/50 == v).
+// MODE_FAST_EVEN: the whole warp has an even line phase (the default 180-degree phase), so the I/Q choice is
+// the compile-time parity of j and the sign is the lane's rc.sM: one FFMA per sample, no per-row tap table.
 template <typename R, int MODE>
-CVS_HD R modulate(R Yv, R Iv, R Qv, R mI, R mQ, int amp) {
-    if (MODE != 2 || amp == 50) {
-        // exactly one of mI, mQ is +-1, the other 0: the sum is exact
-        return Num<R>::fma_(Iv, mI, Num<R>::fma_(Qv, mQ, Yv));
-    } else {
-        const int chroma = (int)Iv * amp * (int)mI + (int)Qv * amp * (int)mQ;
-        return Num<R>::add(Yv, (R)(chroma / 50));
+CVS_HD R modulate(const RowConst<R> &rc, int j, R Yv, R Iv, R Qv, int amp) {
+    if (MODE < 0) {                                   // MODE_FAST_EVEN
+        const R v = (j & 1) ? Qv : Iv;
+        return Num<R>::fma_(v, (j & 2) ? -rc.sM : rc.sM, Yv);
     }
+    const int ph = (rc.xi + j) & 3;
+    const R v = (ph & 1) ? Qv : Iv;
+    const R sg = (ph & 2) ? (R)-1 : (R)1;
+    if (MODE != 2 || amp == 50) return Num<R>::fma_(v, sg, Yv);
+    const int chroma = (int)v * amp * (int)sg;
+    return Num<R>::add(Yv, (R)(chroma / 50));
 }
 
 // Y/C separation + QAM demodulation of block B(k) (chroma_from_luma, :1497-1567).
@@ -619,10 +630,10 @@ CVS_HD void demod_block(const RowConst<R> &rc, int k, int w, int amp, R cm1, con
     // the block plus the first of the next block (needed by the odd-pixel interpolation)
     const bool x1 = (rc.xi & 1) != 0, x2 = (rc.xi & 2) != 0;
     // With the default 180-degree line phase every row has xi in {0, 2}: the first level of the 4-way
-    // selection is then the identity for the whole warp and is skipped under a warp-uniform branch.
+    // selection is then the identity for the whole warp (MODE_FAST_EVEN).
     constexpr int NE = kT / 2 + 1;    // even positions: kT/2 in the block plus the first of the next block
     R s01[2 * NE], s23[2 * NE];      // [2e] = I candidate, [2e+1] = Q candidate
-    if (MODE == 0 && !rc.odd_any) {     // MODE_FAST
+    if (MODE < 0) {                     // MODE_FAST_EVEN
         CVS_UNROLL
         for (int e = 0; e < NE; e++) {
             s01[2 * e] = ch[2 * e]; s23[2 * e] = ch[2 * e + 2];
@@ -679,7 +690,10 @@ CVS_HD void demod_block(const RowConst<R> &rc, int k, int w, int amp, R cm1, con
 // Keeping MODE_EDGE free of the rarely used switches keeps the code that every line start/end pulls
 // through the instruction cache small (the first ncu capture showed 17% of the kernel time waiting on
 // instruction fetch in the then-combined edge+general body).
-enum { MODE_FAST = 0, MODE_EDGE = 1, MODE_GENERAL = 2 };
+// MODE_FAST_EVEN is MODE_FAST for warps whose rows all have an even subcarrier phase index (always, with the
+// default 180-degree line phase): the first level of the demodulator's 4-way selection and the I/Q choice of the
+// modulator are then compile-time.  The kernel picks the loop per warp (rc.odd_any).
+enum { MODE_FAST_EVEN = -1, MODE_FAST = 0, MODE_EDGE = 1, MODE_GENERAL = 2 };
 
 // ---- the step ------------------------------------------------------------------------------------
 // Exchange buffer for the vertical chroma blend: each lane publishes its pre-blend chroma block and
@@ -755,15 +769,14 @@ struct Pipeline {
                             if (rawQ) qv = q;
                         }
                     }
-                    c = modulate<R, MODE>(ln.Yprev[j], iv, qv, rc.mI[j & 3], rc.mQ[j & 3], K.amp);   // :1611
+                    c = modulate<R, MODE>(rc, j, ln.Yprev[j], iv, qv, K.amp);                        // :1611
                     if (GEN && (K.flags & F_PREEMPH)) {                                              // :1613-1629
                         const R lp = N::pole(ln.pPre, c, K.a_pre, K.b_pre);
                         c = N::preemph(c, N::sub(c, lp), K.preemph);
                     }
                     if (!GEN || K.vnoise != 0) {                                                     // :1631-1644
                         c = N::add(c, (R)ln.nY);
-                        const int d = draw_mod(ln.rngL.next_in_group(gL, gLn, j, kT), (uint32_t)(2 * K.vnoise + 1), K.vmagic, K.vshift);
-                        ln.nY = noise_step(ln.nY, d, K.vnoise);
+                        ln.nY = noise_draw(ln.nY, ln.rngL.next_in_group(gL, gLn, j, kT), (uint32_t)(2 * K.vnoise + 1), K.vmagic, K.vshift, K.vnoise);
                     }
                     if (EDGE && hs_row && (rc.rflags & RF_HEADSW)) c = (R)hs_row[x];                 // :1646-1713
                 }
@@ -821,10 +834,8 @@ struct Pipeline {
                 if (!EDGE || x0 + j < w) {
                     IQb[j] = N::add2(IQb[j], mk2((R)ln.nU, (R)ln.nV));
                     const uint32_t m = (uint32_t)(2 * K.cnoise + 1);
-                    const int dU = draw_mod(ln.rngC.next_in_group(gC, gCn, 2 * j, 2 * kT), m, K.cmagic, K.cshift);
-                    ln.nU = noise_step(ln.nU, dU, K.cnoise);
-                    const int dV = draw_mod(ln.rngC.next_in_group(gC, gCn, 2 * j + 1, 2 * kT), m, K.cmagic, K.cshift);
-                    ln.nV = noise_step(ln.nV, dV, K.cnoise);
+                    ln.nU = noise_draw(ln.nU, ln.rngC.next_in_group(gC, gCn, 2 * j, 2 * kT), m, K.cmagic, K.cshift, K.cnoise);
+                    ln.nV = noise_draw(ln.nV, ln.rngC.next_in_group(gC, gCn, 2 * j + 1, 2 * kT), m, K.cmagic, K.cshift, K.cnoise);
                 }
             }
         }
@@ -919,7 +930,7 @@ struct Pipeline {
                 const int x = kD * kT + j;
                 R cv = 0;
                 if (!EDGE || (x >= 0 && x < w))
-                    cv = modulate<R, MODE>(ln.Y3hist[0][j], UV[j].x, UV[j].y, rc.mI[j & 3], rc.mQ[j & 3], K.amp);
+                    cv = modulate<R, MODE>(rc, j, ln.Y3hist[0][j], UV[j].x, UV[j].y, K.amp);
                 c[kLB * kT + j] = cv;
                 c2new[j] = cv;
             }

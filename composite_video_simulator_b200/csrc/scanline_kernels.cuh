@@ -303,13 +303,24 @@ __global__ void __launch_bounds__(kNT, (sizeof(R) == 4 ? CVS_MIN_CTAS : 1)) k_fi
             for (int j = 0; j < kT; j++) px[j] = pxn[j];
         }
         if (pass == 0) {
+            if (!rc.odd_any) {                                       // every row of the warp has an even line phase
 #pragma unroll(kFastUnroll)
-            for (; s < s_hi; s++) {
-                uint32_t pxn[kT];
-                load_block_fast(srow, s + 1, vec_src, pxn);          // interior: always in range
-                St::template step<MODE_FAST>(K, rc, ln, s, px, srow, vec_src, hsrow, warp_hs, hsring, warp_inl, valid, drow, drow_bob, vec_dst);
+                for (; s < s_hi; s++) {
+                    uint32_t pxn[kT];
+                    load_block_fast(srow, s + 1, vec_src, pxn);      // interior: always in range
+                    St::template step<MODE_FAST_EVEN>(K, rc, ln, s, px, srow, vec_src, hsrow, warp_hs, hsring, warp_inl, valid, drow, drow_bob, vec_dst);
 #pragma unroll
-                for (int j = 0; j < kT; j++) px[j] = pxn[j];
+                    for (int j = 0; j < kT; j++) px[j] = pxn[j];
+                }
+            } else {
+#pragma unroll 1
+                for (; s < s_hi; s++) {
+                    uint32_t pxn[kT];
+                    load_block_fast(srow, s + 1, vec_src, pxn);
+                    St::template step<MODE_FAST>(K, rc, ln, s, px, srow, vec_src, hsrow, warp_hs, hsring, warp_inl, valid, drow, drow_bob, vec_dst);
+#pragma unroll
+                    for (int j = 0; j < kT; j++) px[j] = pxn[j];
+                }
             }
         }
     }

@@ -119,6 +119,8 @@ int run_field(const cvs_params &p, RandCursor &cur, uint8_t *dst, int dst_stride
             // 2 = edge variant everywhere, to exercise those variants on interior blocks as well)
             int mode = (K.flags & F_GENERAL) ? MODE_GENERAL : ((s >= s_lo && s < s_hi) ? MODE_FAST : MODE_EDGE);
             if (force_general == 2 && mode == MODE_FAST) mode = MODE_EDGE;
+            // MODE_FAST warps whose rows all have an even line phase run the MODE_FAST_EVEN loop (scanline_kernels.cuh)
+            if (mode == MODE_FAST && !odd_any) mode = MODE_FAST_EVEN;
             BlendXchg<R> xo[32];
             R Yb[32][kT];
             V2<R> IQb[32][kT];
@@ -129,20 +131,19 @@ int run_field(const cvs_params &p, RandCursor &cur, uint8_t *dst, int dst_stride
                 else for (int j = 0; j < kT; j++) pxprev[j] = 0;
                 R C[kT];
                 R *ring = &hsring[(size_t)l * kHsRing];
-                if (mode == MODE_FAST) {
-                    P::template stage_a<MODE_FAST>(K, rc[l], lane[l], s, px, pxprev, hsrow[l], C);
-                    headswitch_substitute<R>(rc[l], hsrow[l], s - 1, C);
-                    if (warp_inl) headswitch_delay_block<R>(ring, 1, s - 1, w, rc[l].hs_delay, C);
-                    P::template stage_b<MODE_FAST>(K, rc[l], lane[l], s, C, Yb[l], IQb[l], xo[l]);
-                } else if (mode == MODE_EDGE) {
-                    P::template stage_a<MODE_EDGE>(K, rc[l], lane[l], s, px, pxprev, hsrow[l], C);
-                    if (warp_inl && s >= 1) headswitch_delay_block<R>(ring, 1, s - 1, w, rc[l].hs_delay, C);
-                    P::template stage_b<MODE_EDGE>(K, rc[l], lane[l], s, C, Yb[l], IQb[l], xo[l]);
-                } else {
-                    P::template stage_a<MODE_GENERAL>(K, rc[l], lane[l], s, px, pxprev, hsrow[l], C);
-                    if (warp_inl && s >= 1) headswitch_delay_block<R>(ring, 1, s - 1, w, rc[l].hs_delay, C);
-                    P::template stage_b<MODE_GENERAL>(K, rc[l], lane[l], s, C, Yb[l], IQb[l], xo[l]);
-                }
+#define CVS_HEAD(M)                                                                                          \
+    {                                                                                                        \
+        constexpr bool FAST = (M) <= 0;                                                                      \
+        P::template stage_a<M>(K, rc[l], lane[l], s, px, pxprev, hsrow[l], C);                               \
+        if (FAST) headswitch_substitute<R>(rc[l], hsrow[l], s - 1, C);                                       \
+        if (warp_inl && (FAST || s >= 1)) headswitch_delay_block<R>(ring, 1, s - 1, w, rc[l].hs_delay, C);   \
+        P::template stage_b<M>(K, rc[l], lane[l], s, C, Yb[l], IQb[l], xo[l]);                               \
+    }
+                if (mode == MODE_FAST_EVEN) CVS_HEAD(MODE_FAST_EVEN)
+                else if (mode == MODE_FAST) CVS_HEAD(MODE_FAST)
+                else if (mode == MODE_EDGE) CVS_HEAD(MODE_EDGE)
+                else CVS_HEAD(MODE_GENERAL)
+#undef CVS_HEAD
             }
             for (int l = 0; l < 32; l++) {
                 R Yf[kT];
@@ -156,10 +157,11 @@ int run_field(const cvs_params &p, RandCursor &cur, uint8_t *dst, int dst_stride
         P::template stage_c<M>(K, rc[l], lane[l], s, Yb[l], xo[l], above, Yf, IQf, kf);                      \
         have = P::template stage_f<M>(K, rc[l], lane[l], kf, Yf, IQf, out);                                  \
     } else {                                                                                                 \
-        kf = s - 1 - kLB;                                                                                          \
+        kf = s - 1 - kLB;                                                                                    \
         have = P::template stage_f<M>(K, rc[l], lane[l], kf, Yb[l], IQb[l], out);                            \
     }
-                if (mode == MODE_FAST) { CVS_TAIL(MODE_FAST) }
+                if (mode == MODE_FAST_EVEN) { CVS_TAIL(MODE_FAST_EVEN) }
+                else if (mode == MODE_FAST) { CVS_TAIL(MODE_FAST) }
                 else if (mode == MODE_EDGE) { CVS_TAIL(MODE_EDGE) }
                 else { CVS_TAIL(MODE_GENERAL) }
 #undef CVS_TAIL
