@@ -32,9 +32,8 @@ constexpr int kWarpsPerCta = kNT / 32;
 #define CVS_MIN_CTAS 3              // CTAs per SM the register allocator must leave room for (168 registers)
 #endif
 #ifndef CVS_FAST_UNROLL
-#define CVS_FAST_UNROLL 1
+#define CVS_FAST_UNROLL 2       // steps per iteration of the interior loop (1 or 2)
 #endif
-constexpr int kFastUnroll = CVS_FAST_UNROLL;   // unroll factor of the interior loop (experiments)
 constexpr int kRowsPerWarp = 31;         // lane 0 is the halo row of the vertical chroma blend
 
 struct FieldDesc {
@@ -304,7 +303,20 @@ __global__ void __launch_bounds__(kNT, (sizeof(R) == 4 ? CVS_MIN_CTAS : 1)) k_fi
         }
         if (pass == 0) {
             if (!rc.odd_any) {                                       // every row of the warp has an even line phase
-#pragma unroll(kFastUnroll)
+#if CVS_FAST_UNROLL == 2
+                // two steps per iteration: the carried blocks (previous-block arrays, the prefetched pixels)
+                // change roles by renaming instead of being moved; a leftover odd step is taken by the edge
+                // loop below, which is valid on interior steps too
+#pragma unroll 1
+                for (; s + 1 < s_hi; s += 2) {
+                    uint32_t pxn[kT];
+                    load_block_fast(srow, s + 1, vec_src, pxn);      // interior: always in range
+                    St::template step<MODE_FAST_EVEN>(K, rc, ln, s, px, srow, vec_src, hsrow, warp_hs, hsring, warp_inl, valid, drow, drow_bob, vec_dst);
+                    load_block_fast(srow, s + 2, vec_src, px);
+                    St::template step<MODE_FAST_EVEN>(K, rc, ln, s + 1, pxn, srow, vec_src, hsrow, warp_hs, hsring, warp_inl, valid, drow, drow_bob, vec_dst);
+                }
+#else
+#pragma unroll 1
                 for (; s < s_hi; s++) {
                     uint32_t pxn[kT];
                     load_block_fast(srow, s + 1, vec_src, pxn);      // interior: always in range
@@ -312,6 +324,7 @@ __global__ void __launch_bounds__(kNT, (sizeof(R) == 4 ? CVS_MIN_CTAS : 1)) k_fi
 #pragma unroll
                     for (int j = 0; j < kT; j++) px[j] = pxn[j];
                 }
+#endif
             } else {
 #pragma unroll 1
                 for (; s < s_hi; s++) {
