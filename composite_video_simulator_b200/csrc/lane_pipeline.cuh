@@ -52,6 +52,9 @@ namespace cvs {
 #ifndef CVS_KT
 #define CVS_KT 4
 #endif
+#ifndef CVS_DEMOD_CARRY
+#define CVS_DEMOD_CARRY 1        // interior steps reuse the overlapping half of the previous demodulation's box filter
+#endif
 constexpr int kT = CVS_KT;       // pixels per step (8 or 4); every block lag below is derived from it
 static_assert(kT == 4 || kT == 8, "kT must be 4 or 8");
 constexpr int kLB = (7 + kT - 1) / kT;        // a demodulation of B(k) reads C up to x+7: kLB blocks of look-ahead
@@ -169,6 +172,7 @@ template <> struct Num<double> {
     }
     static CVS_HD P add2(P a, P b) { return mk2(add(a.x, b.x), add(a.y, b.y)); }
     static CVS_HD P scale2(P a, double k) { return mk2(mul(a.x, k), mul(a.y, k)); }
+    static CVS_HD P axpy2(P a, double k, P c) { return mk2(add(mul(a.x, k), c.x), add(mul(a.y, k), c.y)); }   // a k + c
     static CVS_HD P floor_half2(P s) { return mk2(floor_half(s.x), floor_half(s.y)); }
     static CVS_HD P rot2(P uv, double c, double s, double /*ns*/) { return mk2(rot_a(uv.x, c, uv.y, s), rot_b(uv.x, s, uv.y, c)); }
     static CVS_HD void rgb2yiq2(uint32_t px, double &Y, P &IQ) { rgb2yiq(px, Y, IQ.x, IQ.y); }
@@ -333,6 +337,13 @@ template <> struct Num<float> {
         return mk2(a.x * k, a.y * k);
 #endif
     }
+    static CVS_HD P axpy2(P a, float k, P c) {                      // a k + c per component (one rounding)
+#if defined(__CUDA_ARCH__)
+        return pp(__ffma2_rn(f2(a), make_float2(k, k), f2(c)));
+#else
+        return mk2(::fmaf(a.x, k, c.x), ::fmaf(a.y, k, c.y));
+#endif
+    }
     static CVS_HD P floor_half2(P s) {
 #if defined(__CUDA_ARCH__)
         const float2 m = make_float2(kMagic, kMagic);
@@ -385,23 +396,25 @@ template <> struct Num<float> {
         Q = trunc_mul_pos(fma_(0.48f, rd, mul(0.41f, bd)), 256.0f);
     }
     // one colour channel of YIQ_to_RGB (:1387-1395): trunc((Y + ci I + cq Q) / 256) clamped to 0..255.
-    // The /256 is folded into the operands (exact: power of two), the truncation is the RZ add against
-    // M = 1.5*2^23 and the clamp is done on the resulting bit pattern, whose low byte is the value.
+    // Device: the operands carry an extra 2^-16 (exact: powers of two), so the last FFMA can saturate to
+    // [0, 1] for free (.SAT) = the value clamped to [0, 256]; the truncation is one FFMA.RZ against
+    // M = 1.5*2^23, whose low bits are then the integer 0..256, and one integer min finishes the clamp.
     static CVS_HD uint32_t chan_(float Yp, float ci, float I, float cq, float Q) {
-        const float v = fma_(cq, Q, fma_(ci, I, Yp));
 #if defined(__CUDA_ARCH__)
-        const uint32_t bits = __float_as_uint(__fadd_rz(v, kMagic));
-        return min(max(bits, 0x4B400000u), 0x4B4000FFu);
+        const float u = __saturatef(__fmaf_rn(cq, Q, __fmaf_rn(ci, I, Yp)));
+        return min(__float_as_uint(__fmaf_rz(u, 256.0f, kMagic)), 0x4B4000FFu);
 #else
+        const float v = fma_(cq, Q, fma_(ci, I, Yp)) * 256.0f;   // (exact rescale of the device's 2^-16 operands)
         const int k = (v < 0.0f) ? 0 : (v > 255.0f ? 255 : (int)v);
         return 0x4B400000u + (uint32_t)k;
 #endif
     }
     static CVS_HD uint32_t yiq2bgra(float Y, float I, float Q) {
-        const float Yp = mul(Y, 0.00390625f);
-        const uint32_t r = chan_(Yp, 0.956f * 0.00390625f, I, 0.621f * 0.00390625f, Q);
-        const uint32_t g = chan_(Yp, -0.272f * 0.00390625f, I, -0.647f * 0.00390625f, Q);
-        const uint32_t b = chan_(Yp, -1.106f * 0.00390625f, I, 1.703f * 0.00390625f, Q);
+        constexpr float k = 1.0f / 65536.0f;
+        const float Yp = mul(Y, k);
+        const uint32_t r = chan_(Yp, 0.956f * k, I, 0.621f * k, Q);
+        const uint32_t g = chan_(Yp, -0.272f * k, I, -0.647f * k, Q);
+        const uint32_t b = chan_(Yp, -1.106f * k, I, 1.703f * k, Q);
 #if defined(__CUDA_ARCH__)
         return __byte_perm(__byte_perm(b, g, 0x7740), r, 0x5410);   // r byte 1 is 0x00: alpha = 0
 #else
@@ -499,6 +512,9 @@ struct RowConst {
     uint32_t rflags;
     int row;             // field row index (y = field + 2*row)
     int hs_delay;        // RF_HEADSW_INLINE: C'[x] = C[x - hs_delay], 0 for x < hs_delay
+    R bl_above, bl_own;  // vertical chroma blend as (above * bl_above + own * bl_own + 1) >> 1 (:1843-1863): (1, 1) for
+                         // rows >= field+4, (0, 1) for row field+2 (blends with the zeroed delay line), and (0, 2) where
+                         // nothing is blended (row `field`, or the blend is off): (2 own + 1) >> 1 == own
     bool odd_any;        // warp-uniform: some row of this warp has an odd phase index (set by the caller; default true)
 };
 
@@ -530,6 +546,7 @@ struct Lane {
     // B
     R Cm1;                           // C[kT*kB - 1], kB = s-1-kLB
     R Cwin[kLB][kT];                 // C of B(kB) .. B(s-2)
+    R chc1[5], chc2[5];              // chroma residues carried between consecutive demodulations (demod_block)
     int nU, nV;                      // chroma noise accumulators (:1720)
     R pL[3], pLpre;                  // VHS luma poles (:1800-1805)
     R pS[3];                         // sharpen poles (:1873-1876)
@@ -566,6 +583,7 @@ struct Lane {
         pLpre = 16;                         // :1805
         pPre = 16;                          // :1622
         Cm1 = 0; C2m1 = 0;
+        for (int m = 0; m < 5; m++) { chc1[m] = 0; chc2[m] = 0; }
         for (int j = 0; j < (kT - OD > 0 ? kT - OD : 1); j++) outprev[j] = 0;
         CVS_UNROLL
         for (int k = 0; k < OD; k++) { Ytail[k] = 0; IQtail[k] = mk2((R)0, (R)0); oOIQtail[k] = mk2((R)0, (R)0); }
@@ -595,23 +613,43 @@ CVS_HD R modulate(const RowConst<R> &rc, int j, R Yv, R Iv, R Qv, int amp) {
 //   cm1      = C[8k-1]
 //   c[i]     = C[kT k + i], i < (kLB+1) kT   (read up to kT+6; zero beyond the line end)
 // outputs Yb (box-filtered luma), Ib, Qb for the 8 pixels of the block.
+// chc[] carries the chroma residues ch[kT .. kT+4] of this block = ch[0..4] of the next one, so that an interior
+// step only filters the kT new positions (the other box values are recovered exactly: box[m] = C[m+2] - ch[m],
+// all integers); the edge variants recompute the whole window and only refresh the carry.
 template <typename R, int MODE>
 CVS_HD void demod_block(const RowConst<R> &rc, int k, int w, int amp, R cm1, const R c[(kLB + 1) * kT],
-                        R Yb[kT], V2<R> IQb[kT]) {
+                        R Yb[kT], V2<R> IQb[kT], R chc[5]) {
     constexpr bool EDGE = MODE >= 1, GEN = MODE == 2;
     const int x0 = k * kT;
     // box[m] = (C[m-1] + C[m] + C[m+1] + C[m+2]) / 4 ; chroma[m] = C[m+2] - box[m], m = 0..12
     // (all values are integers < 2^24, so the running sum is exact in any order)
     constexpr int NCH = kT + 5;       // chroma samples needed: up to (first even pixel of the next block) + xi + 1
     R ch[NCH];
-    R sum = Num<R>::add(Num<R>::add(cm1, c[0]), Num<R>::add(c[1], c[2]));
-    CVS_UNROLL
-    for (int m = 0; m < NCH; m++) {
-        if (m > 0) sum = Num<R>::add(Num<R>::sub(sum, (m == 1) ? cm1 : c[m - 2]), c[m + 2]);
-        const R box = div4_trunc<R>(sum);
-        if (m < kT) Yb[m] = box;
-        ch[m] = Num<R>::sub(c[m + 2], box);
+    if (!EDGE && CVS_DEMOD_CARRY) {
+        CVS_UNROLL
+        for (int m = 0; m < 5; m++) ch[m] = chc[m];
+        CVS_UNROLL
+        for (int m = 0; m < kT && m < 5; m++) Yb[m] = Num<R>::sub(c[m + 2], ch[m]);
+        R sum = Num<R>::add(Num<R>::add(c[4], c[5]), Num<R>::add(c[6], c[7]));
+        CVS_UNROLL
+        for (int m = 5; m < NCH; m++) {
+            if (m > 5) sum = Num<R>::add(Num<R>::sub(sum, c[m - 2]), c[m + 2]);
+            const R box = div4_trunc<R>(sum);
+            if (m < kT) Yb[m] = box;
+            ch[m] = Num<R>::sub(c[m + 2], box);
+        }
+    } else {
+        R sum = Num<R>::add(Num<R>::add(cm1, c[0]), Num<R>::add(c[1], c[2]));
+        CVS_UNROLL
+        for (int m = 0; m < NCH; m++) {
+            if (m > 0) sum = Num<R>::add(Num<R>::sub(sum, (m == 1) ? cm1 : c[m - 2]), c[m + 2]);
+            const R box = div4_trunc<R>(sum);
+            if (m < kT) Yb[m] = box;
+            ch[m] = Num<R>::sub(c[m + 2], box);
+        }
     }
+    CVS_UNROLL
+    for (int m = 0; m < 5; m++) chc[m] = ch[kT + m];
     if (EDGE) {
         // carrier sign flips with their line-end / line-start conditions (:1539-1542), then the
         // amplitude rescale (:1544-1546).  In the interior the flip folds into sgA below.
@@ -821,7 +859,7 @@ struct Pipeline {
             CVS_UNROLL
             for (int j = 0; j < kT; j++) { Yb[j] = c[j]; IQb[j] = mk2((R)0, (R)0); }
         } else {
-            demod_block<R, MODE>(rc, k, w, K.amp_back, ln.Cm1, c, Yb, IQb);   // :1716
+            demod_block<R, MODE>(rc, k, w, K.amp_back, ln.Cm1, c, Yb, IQb, ln.chc1);   // :1716
         }
         window_push<R>(ln.Cm1, ln.Cwin, Cnew);
 
@@ -900,17 +938,9 @@ struct Pipeline {
         const int w = K.w;
         const int kD = s - 1 - kLB - LD;                              // delayed chroma / C2 block
         V2<R> UV[kT];
-        const bool blend = (K.flags & F_VBLEND) && rc.row >= 1;       // loop starts at field+2, :1849
-        const bool have_above = rc.row >= 2;                          // row field+2 blends with zero
         CVS_UNROLL
-        for (int j = 0; j < kT; j++) {
-            V2<R> uv = own.uv[j];
-            if (blend) {                                              // (delay + cur + 1) >> 1, :1857-1858
-                const V2<R> a = have_above ? above.uv[j] : mk2((R)0, (R)0);
-                uv = N::floor_half2(N::add2(N::add2(a, uv), mk2((R)1, (R)1)));
-            }
-            UV[j] = uv;
-        }
+        for (int j = 0; j < kT; j++)                                  // (delay + cur + 1) >> 1, :1857-1858 (all integers: exact)
+            UV[j] = N::floor_half2(N::axpy2(above.uv[j], rc.bl_above, N::axpy2(own.uv[j], rc.bl_own, mk2((R)1, (R)1))));
         const bool svideo = GEN && (K.flags & F_SVIDEO);
         if (svideo) {                                                 // :1885: no recombine
             kf = kD;
@@ -935,7 +965,7 @@ struct Pipeline {
                 c2new[j] = cv;
             }
             if (!EDGE || kf >= 0) {
-                demod_block<R, MODE>(rc, kf, w, K.amp, ln.C2m1, c, Yf, IQf);      // :1887
+                demod_block<R, MODE>(rc, kf, w, K.amp, ln.C2m1, c, Yf, IQf, ln.chc2);      // :1887
             } else {
                 CVS_UNROLL
                 for (int j = 0; j < kT; j++) { Yf[j] = 0; IQf[j] = mk2((R)0, (R)0); }
@@ -1088,6 +1118,9 @@ CVS_HD void row_setup(const KConst<R> &K, unsigned field, unsigned long long fie
     rc.rflags = (rowinfo >> 16) & 0xFFu;
     rc.hs_delay = (rc.rflags & RF_HEADSW_INLINE) ? (int)(rowinfo >> 24) : 0;
     rc.odd_any = true;
+    const bool blend = (K.flags & F_VBLEND) && row >= 1;     // the loop starts at field+2 (:1849) ...
+    rc.bl_above = (R)((blend && row >= 2) ? 1 : 0);           // ... where the delay line is still zero (:1847-1848)
+    rc.bl_own = (R)(blend ? 1 : 2);
     rowconst_set_phase<R>(rc, line_phase(K.phase_shift, K.phase_offset, fieldno, field + 2u * (unsigned)row));
     if (K.flags & F_PHASE) {
         const int st = (int)(int16_t)(rowinfo & 0xFFFFu);
