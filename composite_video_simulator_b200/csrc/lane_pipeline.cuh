@@ -52,8 +52,16 @@ namespace cvs {
 #ifndef CVS_KT
 #define CVS_KT 4
 #endif
-#ifndef CVS_DEMOD_CARRY
-#define CVS_DEMOD_CARRY 1        // interior steps reuse the overlapping half of the previous demodulation's box filter
+// The conversion (XU) pipe runs at 1/8 of the FP32 rate, so the hot loop keeps clear of it (PRMT / directed-rounding
+// tricks instead of I2F / F2I / FRND) -- except for a few conversions that take work off the FMA pipe, which is the
+// busiest unit of this kernel.  Measured on B200, 1080p VHS-SP, fields/s (profiles/ab_variants_r1.txt):
+//   unpack by PRMT+FADD 121.4 k; unpack by I2F.U8 120.8 k; + CVS_XU_TRUNC=1 126.2 k; CVS_XU_TRUNC=2 125.0 k
+#ifndef CVS_XU_UNPACK
+#define CVS_XU_UNPACK 1          // BGRA bytes -> float by I2F.U8 (3 per pixel) instead of PRMT + FADD
+#endif
+#ifndef CVS_XU_TRUNC
+#define CVS_XU_TRUNC 1           // 1: trunc() of a ready fp32 value by F2I.TRUNC + I2FP instead of LOP3 + FADD.RZ + FADD;
+                                 // 2: also trunc(x * 2^k) (box filter / 4, Y * 256) by FMUL + F2I.TRUNC + I2FP
 #endif
 constexpr int kT = CVS_KT;       // pixels per step (8 or 4); every block lag below is derived from it
 static_assert(kT == 4 || kT == 8, "kT must be 4 or 8");
@@ -244,7 +252,9 @@ template <> struct Num<float> {
     }
     // trunc(x) for an fp32 value
     static CVS_HD float trunc_(float a) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && CVS_XU_TRUNC
+        return (float)__float2int_rz(a);                 // F2I.TRUNC (conversion pipe) + I2FP (ALU): |a| < 2^24
+#elif defined(__CUDA_ARCH__)
         const float ms = __uint_as_float((__float_as_uint(a) & 0x80000000u) | 0x4B400000u);
         return __fadd_rn(__fadd_rz(a, ms), -ms);
 #else
@@ -274,7 +284,15 @@ template <> struct Num<float> {
         return ::floorf(s * 0.5f);
 #endif
     }
-    static CVS_HD float trunc_quarter(float s) { return trunc_mul_pos(s, 0.25f); }   // C int '/ 4'
+    // trunc(a * b) for b a power of two (the product is exact in fp32)
+    static CVS_HD float trunc_pow2(float a, float b) {
+#if defined(__CUDA_ARCH__) && CVS_XU_TRUNC >= 2
+        return (float)__float2int_rz(__fmul_rn(a, b));    // FMUL + F2I.TRUNC + I2FP: one FMA-pipe slot instead of two
+#else
+        return trunc_mul_pos(a, b);
+#endif
+    }
+    static CVS_HD float trunc_quarter(float s) { return trunc_pow2(s, 0.25f); }   // C int '/ 4'
 
     static CVS_HD float pole(float &prev, float s, float alpha, float beta) {
         prev = fma_(beta, prev, mul(alpha, s));
@@ -366,12 +384,17 @@ template <> struct Num<float> {
     }
     static CVS_HD void rgb2yiq2(uint32_t px, float &Y, P &IQ) {
 #if defined(__CUDA_ARCH__)
+#if CVS_XU_UNPACK
+        // I2F.U8 with a byte selector: one instruction per channel on the (otherwise idle) conversion pipe
+        const float rf = (float)((px >> 16) & 0xFFu), gf = (float)((px >> 8) & 0xFFu), bf = (float)(px & 0xFFu);
+#else
         const float rf = __fadd_rn(__uint_as_float(__byte_perm(px, 0x4B000000u, 0x7442)), -8388608.0f);
         const float gf = __fadd_rn(__uint_as_float(__byte_perm(px, 0x4B000000u, 0x7441)), -8388608.0f);
         const float bf = __fadd_rn(__uint_as_float(__byte_perm(px, 0x4B000000u, 0x7440)), -8388608.0f);
+#endif
         const float dY = fma_(0.11f, bf, fma_(0.59f, gf, mul(0.30f, rf)));
         const float bd = sub(bf, dY), rd = sub(rf, dY);
-        Y = trunc_mul_pos(dY, 256.0f);
+        Y = trunc_pow2(dY, 256.0f);
         const float2 t = __fmul2_rn(make_float2(-0.27f, 0.41f), make_float2(bd, bd));
         const float2 iq = __ffma2_rn(make_float2(0.74f, 0.48f), make_float2(rd, rd), t);
         const float2 ms = msign2(iq);
