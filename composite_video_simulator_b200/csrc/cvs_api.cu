@@ -68,6 +68,7 @@ struct cvs_ctx {
     int host_chunk = kHostChunkDefault;
     int bob = 0;                               // fused line doubling (cvs_set_bob)
     int plan_threads = 4;                      // host threads that build the per-row side tables of a batch
+    int packed_rows = 1;                       // cut the batch's rows into warps across field boundaries (CVS_PACKED_ROWS=0: per field)
     cudaStream_t stream = nullptr;
     bool own_stream = true;
     cudaStream_t s_in = nullptr, s_out = nullptr;      // upload / download streams of the host-pointer path
@@ -191,8 +192,8 @@ template <> float *&lut_ptr<float>(cvs_ctx *c) { return c->d_lut_f; }
 template <> double *&lut_ptr<double>(cvs_ctx *c) { return c->d_lut_d; }
 
 template <typename R>
-int launch_batch(cvs_ctx *c, const Staging &sl, const Variant &v, int w, int h, int nfields, int max_nl, int nitems,
-                 int src_stride, int dst_stride, int opposite, bool vec_src, bool vec_dst) {
+int launch_batch(cvs_ctx *c, const Staging &sl, const Variant &v, int w, int h, int nfields, int max_nl, int total_rows,
+                 bool packed, int nitems, int src_stride, int dst_stride, int opposite, bool vec_src, bool vec_dst) {
     LaunchArgs<R> a;
     std::vector<R> lut;
     make_kconst<R>(c->p, w, h, v.outfull, a.K, lut);
@@ -212,6 +213,10 @@ int launch_batch(cvs_ctx *c, const Staging &sl, const Variant &v, int w, int h, 
     a.nfields = nfields;
     a.warps_per_field = (max_nl + kRowsPerWarp - 1) / kRowsPerWarp;
     a.total_warps = a.warps_per_field * nfields;
+    a.max_nl = max_nl;
+    a.total_rows = total_rows;
+    a.packed = packed ? 1 : 0;
+    if (packed) a.total_warps = (total_rows + kRowsPerWarp - 1) / kRowsPerWarp;
     a.src_stride = src_stride;
     a.dst_stride = dst_stride;
     a.opposite = opposite;
@@ -260,7 +265,7 @@ int run_device(cvs_ctx *c, uint8_t *dst, size_t dst_pic_stride, int dst_stride, 
     // draw (one 31x31 jump per field).  Pass 2 (a few host threads): the per-row side tables, which is
     // where the time goes (5.8 us per 1080p field on one thread).  Pass 3 (serial): the head-switch
     // pre-pass work list.
-    int nitems = 0, max_nl = 0;
+    int nitems = 0, max_nl = 0, min_nl = 1 << 30, total_rows = 0;
     struct Job { DevPlan *pl; RandCursor at; int hs_count; };
     std::vector<Job> jobs((size_t)n);
     for (int k = 0; k < n; k++) {
@@ -274,6 +279,7 @@ int run_device(cvs_ctx *c, uint8_t *dst, size_t dst_pic_stride, int dst_stride, 
         fd.field = (int32_t)field;
         jobs[(size_t)k].pl = nullptr;
         jobs[(size_t)k].hs_count = 0;
+        fd.row_start = total_rows;
         if ((int)field >= h) { fd.nl = 0; continue; }      // no rows of this parity: nothing drawn, nothing written
         DevPlan *pl = nullptr;
         int rc = get_plan(c, w, h, field, &pl);
@@ -282,7 +288,10 @@ int run_device(cvs_ctx *c, uint8_t *dst, size_t dst_pic_stride, int dst_stride, 
         jobs[(size_t)k].at = c->cur;
         c->cur.jump(pl->g.jumpN, pl->g.ndraws);
         fd.nl = pl->g.nl;
+        fd.row_start = total_rows;
+        total_rows += fd.nl;
         if (fd.nl > max_nl) max_nl = fd.nl;
+        if (fd.nl < min_nl) min_nl = fd.nl;
         fd.seek = pl->d_seek;
         fd.rowinfo = sl.d_rowinfo + (size_t)k * c->nl_max;
         fd.hs_scratch = c->d_scratch + (size_t)k * c->hs_max * (size_t)c->max_w;
@@ -338,11 +347,13 @@ int run_device(cvs_ctx *c, uint8_t *dst, size_t dst_pic_stride, int dst_stride, 
     sl.in_flight = true;
     CVS_CUDA(cudaStreamWaitEvent(c->stream, sl.consumed, 0));
 
+    // packed mapping (scanline_kernels.cuh): a warp of 31 consecutive rows then meets at most two fields
+    const bool packed = c->packed_rows && n > 1 && min_nl > kRowsPerWarp;
     const bool vec_src = ((uintptr_t)src % 16 == 0) && (src_stride % 16 == 0) && (src_pic_stride % 16 == 0);
     const bool vec_dst = ((uintptr_t)dst % 16 == 0) && (dst_stride % 16 == 0) && (dst_pic_stride % 16 == 0);
     const int rc = c->precision
-        ? launch_batch<double>(c, sl, v, w, h, n, max_nl, nitems, src_stride, dst_stride, opposite, vec_src, vec_dst)
-        : launch_batch<float>(c, sl, v, w, h, n, max_nl, nitems, src_stride, dst_stride, opposite, vec_src, vec_dst);
+        ? launch_batch<double>(c, sl, v, w, h, n, max_nl, total_rows, packed, nitems, src_stride, dst_stride, opposite, vec_src, vec_dst)
+        : launch_batch<float>(c, sl, v, w, h, n, max_nl, total_rows, packed, nitems, src_stride, dst_stride, opposite, vec_src, vec_dst);
     if (rc != CVS_OK) return rc;
     CVS_CUDA(cudaEventRecord(sl.kernel_done, c->stream));
     return CVS_OK;
@@ -497,6 +508,7 @@ int cvs_create(cvs_ctx **out, const cvs_params *p, int device, int max_w, int ma
             if (v >= 1 && v <= 64) c->plan_threads = v;
         }
     }
+    if (const char *e = std::getenv("CVS_PACKED_ROWS")) c->packed_rows = std::atoi(e) != 0;   // experiments / tests
     c->hs_max = head_switch_rows_bound(max_w);
     if (c->hs_max > c->nl_max) c->hs_max = c->nl_max;
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
@@ -558,8 +570,18 @@ int cvs_preferred_batch(cvs_ctx *ctx, int w, int h, int max_batch) {
     else CVS_CUDA(occupancy_variant<float>(v, &ctas));
     if (max_batch > ctx->max_batch) max_batch = ctx->max_batch;
     const long long slots = (long long)sms * ctas * kWarpsPerCta;
-    const long long tasks_per_field = ((h + 1) / 2 + kRowsPerWarp - 1) / kRowsPerWarp;
     if (slots <= 0) return max_batch;
+    if (ctx->packed_rows && h / 2 > kRowsPerWarp) {
+        // packed mapping: b consecutive fields are ceil(rows(b) / 31) tasks, rows(b) = nl(0) + nl(1) + ... with
+        // the parities alternating (odd heights: (h+1)/2 and h/2 rows)
+        auto tasks = [&](long long b) { return (((b + 1) / 2) * ((h + 1) / 2) + (b / 2) * (h / 2) + kRowsPerWarp - 1) / kRowsPerWarp; };
+        const long long waves = tasks(max_batch) / slots;
+        if (waves < 1) return max_batch;
+        long long b = max_batch;
+        while (b > 1 && tasks(b) > waves * slots) b--;
+        return (int)b;
+    }
+    const long long tasks_per_field = ((h + 1) / 2 + kRowsPerWarp - 1) / kRowsPerWarp;
     // largest batch <= max_batch whose task count is at most a whole number of waves
     const long long waves = ((long long)max_batch * tasks_per_field) / slots;
     if (waves < 1) return max_batch;

@@ -52,6 +52,9 @@ namespace cvs {
 #ifndef CVS_KT
 #define CVS_KT 4
 #endif
+#ifndef CVS_DEMOD_CARRY
+#define CVS_DEMOD_CARRY 1        // interior steps reuse the overlapping half of the previous demodulation's box filter
+#endif
 // The conversion (XU) pipe runs at 1/8 of the FP32 rate, so the hot loop keeps clear of it (PRMT / directed-rounding
 // tricks instead of I2F / F2I / FRND) -- except for a few conversions that take work off the FMA pipe, which is the
 // busiest unit of this kernel.  Measured on B200, 1080p VHS-SP, fields/s (profiles/ab_variants_r1.txt):

@@ -48,6 +48,7 @@ struct FieldDesc {
     const int32_t *hs_shift;             // hs_count shifts
     unsigned long long fieldno;
     int32_t field, nl, hs_first, hs_count;
+    int32_t row_start, pad_;             // rows of the preceding fields of the batch (packed mapping)
     uint32_t window[64];                 // q[base-31 .. base+29] (61 used)
 };
 
@@ -60,6 +61,9 @@ struct LaunchArgs {
     KConst<R> K;
     const FieldDesc *fields;
     int32_t nfields, warps_per_field, total_warps;
+    // packed mapping: the rows of all fields of the batch form one sequence that is cut into warps of 31
+    // rows, so that only the last warp of the launch has idle lanes (a field of 540 rows is 17.4 warps, not 18)
+    int32_t packed, total_rows, max_nl;
     int32_t src_stride, dst_stride, opposite;
     int32_t vec_src, vec_dst;            // rows are 16-byte aligned: use 128-bit loads / stores
     int32_t bob;                         // also write every processed row y >= 1 into row y-1 (ffmpeg_ntsc.cpp:2232-2257)
@@ -72,7 +76,7 @@ struct LaunchArgs {
 template <typename R, bool VHS>
 struct SmemLayout {
     static constexpr size_t rings = (size_t)2 * kRngSlots * kNT * sizeof(uint32_t);
-    static constexpr size_t wins = (size_t)kWarpsPerCta * 64 * sizeof(uint32_t);
+    static constexpr size_t wins = (size_t)kWarpsPerCta * 128 * sizeof(uint32_t);   // two fields can meet in a warp
     static constexpr size_t tails = VHS ? (size_t)2 * kTailSlots * kNT * sizeof(R) : 0;
     static constexpr size_t hsring = VHS ? (size_t)kHsRing * kNT * sizeof(R) : 0;
     static constexpr size_t off_wins = rings, off_tails = rings + wins, off_hsring = rings + wins + tails;
@@ -219,21 +223,44 @@ __global__ void __launch_bounds__(kNT, (sizeof(R) == 4 ? CVS_MIN_CTAS : 1)) k_fi
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gw = blockIdx.x * kWarpsPerCta + warp;
     if (gw >= a.total_warps) return;
-    const int fi = gw / a.warps_per_field, wp = gw - fi * a.warps_per_field;
-    const FieldDesc &fd = a.fields[fi];
-    const int nl = fd.nl;
-    if (kRowsPerWarp * wp >= nl) return;                 // (odd heights: the short parity has fewer rows)
     const KConst<R> &K = a.K;
     const int w = K.w, h = K.h;
+    // which field row this lane computes.  Lane 0 is the halo row: the row above lane 1's.
+    int fi, row;
+    bool valid;
+    if (a.packed) {
+        int g = kRowsPerWarp * gw + lane - 1;                 // position in the batch's sequence of rows
+        valid = (lane >= 1) && g < a.total_rows;
+        g = g < 0 ? 0 : (g > a.total_rows - 1 ? a.total_rows - 1 : g);
+        fi = g / a.max_nl;                                    // never beyond the row's field: row_start <= fi * max_nl
+        while (g >= a.fields[fi].row_start + a.fields[fi].nl) fi++;
+        row = g - a.fields[fi].row_start;
+        // a halo row in the previous field is not needed (lane 1 is then row 0, which is not blended): park it
+        const int fi1 = __shfl_sync(0xffffffffu, fi, 1);
+        if (lane == 0 && fi != fi1) { fi = fi1; row = 0; }
+    } else {
+        fi = gw / a.warps_per_field;
+        const int wp = gw - fi * a.warps_per_field, nlw = a.fields[fi].nl;
+        if (kRowsPerWarp * wp >= nlw) return;                 // (odd heights: the short parity has fewer rows)
+        row = kRowsPerWarp * wp + lane - 1;
+        valid = (lane >= 1) && row < nlw;
+        row = row < 0 ? 0 : (row > nlw - 1 ? nlw - 1 : row);
+    }
+    const FieldDesc &fd = a.fields[fi];
+    const int nl = fd.nl;
+    (void)nl;
 
-    uint32_t *win = wins + warp * 64;
-    win[lane] = fd.window[lane];
-    win[lane + 32] = fd.window[lane + 32];
-    __syncwarp();
-
-    int row = kRowsPerWarp * wp + lane - 1;
-    const bool valid = (lane >= 1) && row < nl;
-    row = row < 0 ? 0 : (row > nl - 1 ? nl - 1 : row);
+    // generator windows of the (at most two) fields of this warp: [0,64) the field of lane 1, [64,128) that of lane 31
+    uint32_t *win = wins + warp * 128;
+    {
+        const int fiA = __shfl_sync(0xffffffffu, fi, 1), fiB = __shfl_sync(0xffffffffu, fi, 31);
+        win[lane] = a.fields[fiA].window[lane];
+        win[lane + 32] = a.fields[fiA].window[lane + 32];
+        win[lane + 64] = a.fields[fiB].window[lane];
+        win[lane + 96] = a.fields[fiB].window[lane + 32];
+        __syncwarp();
+        if (fi != fiA) win += 64;
+    }
 
     L ln;
     ln.reset(K);

@@ -3,6 +3,8 @@
 fp32 (production): max |delta| <= 1 LSB per 8-bit channel (north_star's bar).
 fp64 (validation mode): bit-exact with the reference arithmetic.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -61,6 +63,44 @@ def test_batch_equals_sequential(oracle):
         eng.composite_fields_host(bat, src, 0)
         assert eng.rng_tell() == pos
     assert np.array_equal(seq, bat)
+
+
+@pytest.mark.parametrize("w,h,n,argv", [(100, 67, 7, ["-vhs"]),                 # 34 / 33 rows per parity: packed, two fields meet in a warp
+                                        (64, 65, 5, ["-vhs", "-vhs-speed", "ep"]),  # 33 / 32 rows
+                                        (64, 61, 5, ["-vhs"]),                   # 31 / 30 rows: too short to pack (per-field warps)
+                                        (720, 480, 9, [])])
+def test_packed_rows_batch_matches_oracle(oracle, w, h, n, argv):
+    """A batch is cut into warps of 31 rows across field boundaries (scanline_kernels.cuh, `packed`): fp64 must
+    stay bit-exact, whichever rows and fields meet in a warp, and equal to the per-field mapping."""
+    p = helpers.params(*argv)
+    frames = lambda k: helpers.noise_frame(w, h, 40 + k)
+    src = np.stack([frames(k) for k in range(n)])
+    got = {}
+    for packed in ("1", "0"):
+        os.environ["CVS_PACKED_ROWS"] = packed
+        try:
+            out = np.zeros((n, h, w), dtype=np.uint32)
+            with cvs.Engine(params=p, max_w=w, max_h=h, max_batch=n) as eng:
+                eng.set_precision(True)
+                eng.composite_fields_host(out, src, 0)
+            got[packed] = out
+        finally:
+            os.environ.pop("CVS_PACKED_ROWS", None)
+    assert np.array_equal(got["1"], got["0"])
+    seq = np.zeros((n, h, w), dtype=np.uint32)
+    with cvs.Engine(params=p, max_w=w, max_h=h, max_batch=1) as eng:
+        eng.set_precision(True)
+        for k in range(n):
+            eng.composite_layer(seq[k], src[k], (k & 1) ^ 1, k)
+    assert np.array_equal(got["1"], seq)
+    # and the sequential calls against the oracle (one destination picture, as the reference's loop uses it)
+    acc = np.zeros((h, w), dtype=np.uint32)
+    want, _ = helpers.run_oracle(oracle, p, frames, n, w, h)
+    with cvs.Engine(params=p, max_w=w, max_h=h, max_batch=1) as eng:
+        eng.set_precision(True)
+        for k in range(n):
+            eng.composite_layer(acc, frames(k), (k & 1) ^ 1, k)
+    assert np.array_equal(want, acc)
 
 
 @pytest.mark.parametrize("name", sorted(helpers.load_golden().keys()))
@@ -247,19 +287,20 @@ def test_async_host_calls_overlap_correctly():
 
 
 def test_preferred_batch_is_wave_aligned():
-    """cvs_preferred_batch: the largest batch <= max whose warp tasks fill whole waves of the GPU."""
+    """cvs_preferred_batch: the largest batch <= max whose warp tasks fill whole waves of the GPU (packed mapping:
+    b fields of 540 rows are ceil(540 b / 31) tasks)."""
     import torch
     sms = torch.cuda.get_device_properties(0).multi_processor_count
     with cvs.Engine(["-vhs"], max_w=1920, max_h=1080, max_batch=320) as eng:
         b = eng.preferred_batch(1920, 1080, 320)
         assert 1 <= b <= 320
-        tasks = 18                                   # ceil(540 rows / 31 rows per warp)
+        tasks = lambda n: (540 * n + 30) // 31
         # some residency of 1..4 CTAs x 4 warps per SM makes b the wave-aligned batch
         ok = False
         for ctas in (1, 2, 3, 4):
             slots = sms * ctas * 4
-            waves = (320 * tasks) // slots
-            ok |= waves >= 1 and b == (waves * slots) // tasks
+            waves = tasks(320) // slots
+            ok |= waves >= 1 and tasks(b) <= waves * slots < tasks(b + 1)
         assert ok, b
         assert eng.preferred_batch(1920, 1080, 1) == 1      # less than one wave: unchanged
         assert eng.preferred_batch(1920, 1080, 10**6) <= 320  # clamped to the context's capacity
