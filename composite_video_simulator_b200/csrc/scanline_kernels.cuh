@@ -31,9 +31,6 @@ constexpr int kWarpsPerCta = kNT / 32;
 #ifndef CVS_MIN_CTAS
 #define CVS_MIN_CTAS 3              // CTAs per SM the register allocator must leave room for (168 registers)
 #endif
-#ifndef CVS_L2_PREFETCH
-#define CVS_L2_PREFETCH 0           // bytes ahead of the interior loop's row load to prefetch into L2 (0 = off)
-#endif
 #ifndef CVS_FAST_UNROLL
 #define CVS_FAST_UNROLL 1       // steps per iteration of the interior loop (1 or 2).  Measured on B200 (1080p VHS-SP):
                                 // 2 executes 9 % fewer instructions (771 vs 853 per step, carried blocks rename instead of
@@ -131,16 +128,10 @@ __device__ __forceinline__ void load_block_dev(const uint32_t *srow, int k, int 
 }
 
 // interior blocks: the whole block is inside the line
-__device__ __forceinline__ void load_block_fast(const uint32_t *srow, int k, int w, bool vec, uint32_t px[kT]) {
+__device__ __forceinline__ void load_block_fast(const uint32_t *srow, int k, bool vec, uint32_t px[kT]) {
     const int x0 = k * kT;
     if (vec) {
         const uint4 *p = reinterpret_cast<const uint4 *>(srow + x0);
-#if CVS_L2_PREFETCH
-        // pull the line CVS_L2_PREFETCH bytes ahead into L2 (same base register, immediate offset: one instruction),
-        // as long as it is still inside the row
-        if (k < (w * 4 - CVS_L2_PREFETCH) / (4 * kT))
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(p) + CVS_L2_PREFETCH));
-#endif
 #pragma unroll
         for (int v = 0; v < kT / 4; v++) {
             const uint4 a = ld_row16(p + v);
@@ -349,16 +340,16 @@ __global__ void __launch_bounds__(kNT, (sizeof(R) == 4 ? CVS_MIN_CTAS : 1)) k_fi
 #pragma unroll 1
                 for (; s + 1 < s_hi; s += 2) {
                     uint32_t pxn[kT];
-                    load_block_fast(srow, s + 1, w, vec_src, pxn);      // interior: always in range
+                    load_block_fast(srow, s + 1, vec_src, pxn);      // interior: always in range
                     St::template step<MODE_FAST_EVEN>(K, rc, ln, s, px, srow, vec_src, hsrow, warp_hs, hsring, warp_inl, valid, drow, drow_bob, vec_dst);
-                    load_block_fast(srow, s + 2, w, vec_src, px);
+                    load_block_fast(srow, s + 2, vec_src, px);
                     St::template step<MODE_FAST_EVEN>(K, rc, ln, s + 1, pxn, srow, vec_src, hsrow, warp_hs, hsring, warp_inl, valid, drow, drow_bob, vec_dst);
                 }
 #else
 #pragma unroll 1
                 for (; s < s_hi; s++) {
                     uint32_t pxn[kT];
-                    load_block_fast(srow, s + 1, w, vec_src, pxn);      // interior: always in range
+                    load_block_fast(srow, s + 1, vec_src, pxn);      // interior: always in range
                     St::template step<MODE_FAST_EVEN>(K, rc, ln, s, px, srow, vec_src, hsrow, warp_hs, hsring, warp_inl, valid, drow, drow_bob, vec_dst);
 #pragma unroll
                     for (int j = 0; j < kT; j++) px[j] = pxn[j];
@@ -368,7 +359,7 @@ __global__ void __launch_bounds__(kNT, (sizeof(R) == 4 ? CVS_MIN_CTAS : 1)) k_fi
 #pragma unroll 1
                 for (; s < s_hi; s++) {
                     uint32_t pxn[kT];
-                    load_block_fast(srow, s + 1, w, vec_src, pxn);
+                    load_block_fast(srow, s + 1, vec_src, pxn);
                     St::template step<MODE_FAST>(K, rc, ln, s, px, srow, vec_src, hsrow, warp_hs, hsring, warp_inl, valid, drow, drow_bob, vec_dst);
 #pragma unroll
                     for (int j = 0; j < kT; j++) px[j] = pxn[j];
