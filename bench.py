@@ -248,6 +248,7 @@ def run_own_arm(args):
 
     nl = (H + 1) // 2
     eng = cvs.Engine(params=params, device=local_rank, max_w=W, max_h=H, max_batch=max(args.batch, args.e2e_batch))
+    eng.set_noise_mode(args.noise == "fast")
     # fields per step: the largest batch <= --batch that fills whole waves of the GPU (a lane = a scanline,
     # all tasks equally long: a partial last wave is pure loss); identical on every rank
     B = eng.preferred_batch(W, H, args.batch) if args.wave_align else args.batch
@@ -295,6 +296,32 @@ def run_own_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max, kernel_ms = float(t[0]), float(t[1])
     value = world * B * args.steps / (ms_max / 1e3)
+
+    # ---- side measurement (not the headline): the other per-pixel noise mode, same steps, same timing ----
+    # (cvs_set_noise_mode: CVS_NOISE_FAST draws the per-pixel noise from counter generators, within +-1 LSB)
+    other = None
+    if args.noise_side:
+        eng.set_noise_mode(args.noise != "fast")
+        for i in range(args.warmup):
+            step(i)
+        eng.synchronize()
+        barrier()
+        eng.kernel_time_reset()
+        e0.record(stream)
+        for i in range(args.steps):
+            step(args.warmup + i)
+        e1.record(stream)
+        e1.synchronize()
+        eng.synchronize()
+        barrier()
+        kms2, kn2 = eng.kernel_time_query()
+        t = torch.tensor([e0.elapsed_time(e1), kms2 / max(kn2, 1)], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        other = {"noise": "exact" if args.noise == "fast" else "fast (counter generators, +-1 LSB)",
+                 "value": world * B * args.steps / (float(t[0]) / 1e3), "unit": "fields/s", "kernel_ms_per_launch": float(t[1])}
+        eng.set_noise_mode(args.noise == "fast")
+        eng.kernel_time_reset()
 
     # ---- e2e: host buffers through the C ABI (H2D + kernels + D2H inside the timed region) ----
     Be = args.e2e_batch
@@ -376,7 +403,9 @@ def run_own_arm(args):
                                                         " ".join(ARGV) or "no switches", B),
                    "fields_per_step_per_gpu": B, "full_frames_per_s": value / 2,
                    "l2": "inputs larger than L2 (%.0f MB read + %.0f MB written per step)" % (alg_bytes / 2e6, alg_bytes / 2e6),
-                   "noise": "exact glibc rand() replay", "parallelism": "fields sharded by contiguous chunk, no data-path collective"},
+                   "noise": ("exact glibc rand() replay" if args.noise == "exact" else
+                             "fast mode: per-pixel noise from counter generators (+-1 LSB), per-line draws exact"),
+                   "other_noise_mode": other, "parallelism": "fields sharded by contiguous chunk, no data-path collective"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "fields/s", "h2d_bytes_per_step": Be * nl * 4 * W,
                 "d2h_bytes_per_step": Be * nl * 4 * W, "fields_per_step_per_gpu": Be, "result_checksum": e2e_checksum},
@@ -425,6 +454,10 @@ def main():
     ap.add_argument("--e2e-batch", type=int, default=128, help="fields per GPU per step (host buffers; 4 pinned buffers of this many pictures per rank)")
     ap.add_argument("--cpu-fields", type=int, default=64, help="fields of the single-thread CPU baseline sample")
     ap.add_argument("--ref-fields-per-proc", type=int, default=4)
+    ap.add_argument("--noise", default="exact", choices=["exact", "fast"],
+                    help="per-pixel noise source of the measured runs (cvs_set_noise_mode); the headline is exact")
+    ap.add_argument("--no-noise-side", dest="noise_side", action="store_false",
+                    help="skip the side measurement of the other noise mode")
     ap.add_argument("--width", type=int, default=1920, help="experiments only: the headline metric is 1920x1080")
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--preset", default="sp", choices=["sp", "ep", "lp", "comp"],

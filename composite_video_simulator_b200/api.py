@@ -100,6 +100,10 @@ class Engine:
         """Fuse the reference's line doubling (ffmpeg_ntsc.cpp:2232-2257) into the field call."""
         _check(self.lib.cvs_set_bob(self._ctx, 1 if enable else 0), "cvs_set_bob")
 
+    def set_noise_mode(self, fast):
+        """CVS_NOISE_FAST: per-pixel noise from counter generators (+-1 LSB); default exact rand() replay."""
+        _check(self.lib.cvs_set_noise_mode(self._ctx, 1 if fast else 0), "cvs_set_noise_mode")
+
     def preferred_batch(self, w, h, max_batch):
         """Largest batch <= max_batch that fills whole waves of the device (see cvs_preferred_batch)."""
         n = self.lib.cvs_preferred_batch(self._ctx, w, h, max_batch)

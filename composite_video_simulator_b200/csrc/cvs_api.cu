@@ -65,6 +65,7 @@ struct cvs_ctx {
     int device = 0;
     int max_w = 0, max_h = 0, max_batch = 0, nl_max = 0, hs_max = 0;
     int precision = 0;                         // 0 = float (production), 1 = double (reference arithmetic)
+    int noise_fast = 0;                        // CVS_NOISE_FAST requested (fp32 only, small amplitudes only)
     int host_chunk = kHostChunkDefault;
     int bob = 0;                               // fused line doubling (cvs_set_bob)
     int plan_threads = 4;                      // host threads that build the per-row side tables of a batch
@@ -164,8 +165,17 @@ int get_plan(cvs_ctx *c, int w, int h, unsigned field, DevPlan **out) {
 template <typename R>
 cudaError_t launch_variant(const Variant &v, const LaunchArgs<R> &a, cudaStream_t st);
 
+// the fast-noise instantiations (kern_n_*.cu)
+static cudaError_t launch_variant_fast_noise(const Variant &v, const LaunchArgs<float> &a, cudaStream_t st) {
+    if (!v.vhs) return v.outfull ? launch_fields<float, false, 9, true, true>(a, st) : launch_fields<float, false, 9, false, true>(a, st);
+    if (v.cd == 9) return v.outfull ? launch_fields<float, true, 9, true, true>(a, st) : launch_fields<float, true, 9, false, true>(a, st);
+    if (v.cd == 12) return v.outfull ? launch_fields<float, true, 12, true, true>(a, st) : launch_fields<float, true, 12, false, true>(a, st);
+    return v.outfull ? launch_fields<float, true, 14, true, true>(a, st) : launch_fields<float, true, 14, false, true>(a, st);
+}
+
 template <>
 cudaError_t launch_variant<float>(const Variant &v, const LaunchArgs<float> &a, cudaStream_t st) {
+    if (a.K.flags & F_NOISE_FAST) return launch_variant_fast_noise(v, a, st);
     if (!v.vhs) return v.outfull ? launch_fields<float, false, 9, true>(a, st) : launch_fields<float, false, 9, false>(a, st);
     if (v.cd == 9) return v.outfull ? launch_fields<float, true, 9, true>(a, st) : launch_fields<float, true, 9, false>(a, st);
     if (v.cd == 12) return v.outfull ? launch_fields<float, true, 12, true>(a, st) : launch_fields<float, true, 12, false>(a, st);
@@ -209,6 +219,8 @@ int launch_batch(cvs_ctx *c, const Staging &sl, const Variant &v, int w, int h, 
         c->lut_dirty = false;
     }
     a.K.phase_lut = lut_ptr<R>(c);
+    // fast per-pixel noise: production arithmetic only, and only while the noise is sub-LSB (include/cvs_ntsc.h)
+    if (c->noise_fast && sizeof(R) == 4 && a.K.vnoise + 2 * a.K.cnoise <= 96) a.K.flags |= F_NOISE_FAST;
     a.fields = sl.d_fields;
     a.nfields = nfields;
     a.warps_per_field = (max_nl + kRowsPerWarp - 1) / kRowsPerWarp;
@@ -594,6 +606,14 @@ int cvs_set_bob(cvs_ctx *ctx, int enable) {
     if (cudaSetDevice(ctx->device) != cudaSuccess) return CVS_ERR_CUDA;
     CVS_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->bob = enable ? 1 : 0;
+    return CVS_OK;
+}
+
+int cvs_set_noise_mode(cvs_ctx *ctx, int mode) {
+    if (!ctx || (mode != CVS_NOISE_EXACT && mode != CVS_NOISE_FAST)) return CVS_ERR_INVALID_ARG;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return CVS_ERR_CUDA;
+    CVS_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->noise_fast = mode == CVS_NOISE_FAST;
     return CVS_OK;
 }
 

@@ -1,0 +1,6 @@
+// kern_n_ep_full.cu -- one instantiation of the fused scanline kernel (see scanline_kernels.cuh), fast noise mode.
+// R = float; <VHS, chroma delay, full output lowpass, fast noise> = <true, 14, true, true>.
+#include "scanline_kernels.cuh"
+namespace cvs {
+CVS_DEFINE_LAUNCH_FIELDS_NF(float, true, 14, true, true)
+}

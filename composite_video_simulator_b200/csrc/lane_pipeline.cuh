@@ -87,6 +87,8 @@ enum : uint32_t {
     F_SVIDEO = 1u << 5,       // vhs_svideo_out
     F_PHASE = 1u << 6,        // video_chroma_phase_noise != 0
     F_GENERAL = 1u << 7,      // any non-default switch: run the general (edge) variant everywhere
+    F_NOISE_FAST = 1u << 8,   // per-pixel luma/chroma noise from a per-row counter generator instead of the exact
+                              // rand() replay (cvs_set_noise_mode; the per-line draws stay exact)
 };
 
 // per-row flags (host side table)
@@ -527,6 +529,22 @@ CVS_HD int noise_draw(int noise, uint32_t raw, uint32_t m, uint32_t magic, uint3
     return t >> 1;
 }
 
+// "Fast" per-pixel noise (the per-pixel noise amplitudes are sub-LSB in the x256 domain, so any
+// generator stays within +-1 LSB of the reference; the per-LINE draws are never substituted).  One 32-bit LCG per
+// lane and stream, seeded per (field, row, stream); a draw is uniform in [0, m): umulhi(state, m).
+CVS_HD uint32_t lcg_seed(unsigned long long fieldno, unsigned field, int row, uint32_t stream) {
+    uint32_t h = (uint32_t)fieldno * 0x9E3779B1u + (uint32_t)(fieldno >> 32) * 0x7F4A7C15u;
+    h ^= ((uint32_t)row * 2u + field) * 0x85EBCA77u + stream * 0xC2B2AE3Du;
+    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
+    return h;
+}
+CVS_HD int noise_draw_fast(int noise, uint32_t &state, uint32_t m, int v) {
+    state = state * 1664525u + 1013904223u;
+    int t = noise + (int)umulhi32(state, m) - v;
+    t += (int)((uint32_t)t >> 31);
+    return t >> 1;
+}
+
 // ---- per-row constants --------------------------------------------------------------------------
 template <typename R>
 struct RowConst {
@@ -589,6 +607,7 @@ struct Lane {
     uint32_t outprev[kT - OD > 0 ? kT - OD : 1];   // packed pixels of positions [kT(k-1), kT k - OD)
 
     LaneRng rngL, rngC;
+    // (fast noise mode keeps its two generator states in rngL.l1 / rngC.l1: the exact generators are idle then)
     R *tailU, *tailV;                // per-lane stash (kTailSlots each), stride tail_stride
     int tail_stride;
 
@@ -788,10 +807,12 @@ struct Pipeline {
     // ---- A1 + A2 (+ head-switch substitution): returns C block B(s-1) in Cnew --------------------
     // pxprev = BGRA of B(s-1): read only on the tail path (raw chroma of the last `delay` pixels), so
     // the fast variant never carries it; the edge variants re-read it from memory (an L2 hit).
-    template <int MODE>
+    // NFT: "fast noise" (a kernel instantiation of its own, so that the exact kernels carry none of it)
+    template <int MODE, bool NFT = false>
     static CVS_HD void stage_a(const KConst<R> &K, const RowConst<R> &rc, L &ln, int s,
                                const uint32_t px[kT], const uint32_t pxprev[kT], const int32_t *hs_row, R Cnew[kT]) {
         constexpr bool EDGE = MODE >= 1, GEN = MODE == 2;
+        constexpr bool nfast = NFT;
         const int w = K.w;
         const int p = s * kT;
         R Ycur[kT];
@@ -840,7 +861,8 @@ struct Pipeline {
                     }
                     if (!GEN || K.vnoise != 0) {                                                     // :1631-1644
                         c = N::add(c, (R)ln.nY);
-                        ln.nY = noise_draw(ln.nY, ln.rngL.next_in_group(gL, gLn, j, kT), (uint32_t)(2 * K.vnoise + 1), K.vmagic, K.vshift, K.vnoise);
+                        if (nfast) ln.nY = noise_draw_fast(ln.nY, ln.rngL.l1, (uint32_t)(2 * K.vnoise + 1), K.vnoise);
+                        else ln.nY = noise_draw(ln.nY, ln.rngL.next_in_group(gL, gLn, j, kT), (uint32_t)(2 * K.vnoise + 1), K.vmagic, K.vshift, K.vnoise);
                     }
                     if (EDGE && hs_row && (rc.rflags & RF_HEADSW)) c = (R)hs_row[x];                 // :1646-1713
                 }
@@ -860,10 +882,11 @@ struct Pipeline {
     // ---- B: demod of B(s-2), noise, phase; VHS luma/chroma filters ---------------------------------
     // Outputs: Yb/Ib/Qb of B(s-2) for the non-VHS path; for VHS publishes the completed delayed chroma
     // block B(s-4) in xo (pre-blend) and leaves Y3 of B(s-2) in y3new.
-    template <int MODE>
+    template <int MODE, bool NFT = false>
     static CVS_HD void stage_b(const KConst<R> &K, const RowConst<R> &rc, L &ln, int s, const R Cnew[kT],
                                R Yb[kT], V2<R> IQb[kT], BlendXchg<R> &xo) {
         constexpr bool EDGE = MODE >= 1, GEN = MODE == 2;
+        constexpr bool nfast = NFT;
         const int w = K.w;
         constexpr int LD = L::LD;
         const int k = s - 1 - kLB;                                 // kB
@@ -898,8 +921,13 @@ struct Pipeline {
                 if (!EDGE || x0 + j < w) {
                     IQb[j] = N::add2(IQb[j], mk2((R)ln.nU, (R)ln.nV));
                     const uint32_t m = (uint32_t)(2 * K.cnoise + 1);
-                    ln.nU = noise_draw(ln.nU, ln.rngC.next_in_group(gC, gCn, 2 * j, 2 * kT), m, K.cmagic, K.cshift, K.cnoise);
-                    ln.nV = noise_draw(ln.nV, ln.rngC.next_in_group(gC, gCn, 2 * j + 1, 2 * kT), m, K.cmagic, K.cshift, K.cnoise);
+                    if (nfast) {
+                        ln.nU = noise_draw_fast(ln.nU, ln.rngC.l1, m, K.cnoise);
+                        ln.nV = noise_draw_fast(ln.nV, ln.rngC.l1, m, K.cnoise);
+                    } else {
+                        ln.nU = noise_draw(ln.nU, ln.rngC.next_in_group(gC, gCn, 2 * j, 2 * kT), m, K.cmagic, K.cshift, K.cnoise);
+                        ln.nV = noise_draw(ln.nV, ln.rngC.next_in_group(gC, gCn, 2 * j + 1, 2 * kT), m, K.cmagic, K.cshift, K.cnoise);
+                    }
                 }
             }
         }
@@ -1213,7 +1241,7 @@ CVS_HD void load_block_scalar(const uint32_t *srow, int k, int w, uint32_t px[kT
 // the exact luma noise) computed up front and written, already rotated, to a scratch row; the main
 // pass substitutes it for its own C.  dest[(k - shif) mod twidth] = C[k]; everything else is the
 // zero padding of the reference's tmp[] ring.
-template <typename R>
+template <typename R, bool NFT = false>
 CVS_HD void headswitch_row(const KConst<R> &K, const RowConst<R> &rc_in, Lane<R, false, 9, false> &ln,
                            const uint32_t *srow, int32_t *scratch, int shif) {
     typedef Pipeline<R, false, 9, false> P;
@@ -1230,7 +1258,7 @@ CVS_HD void headswitch_row(const KConst<R> &K, const RowConst<R> &rc_in, Lane<R,
         uint32_t px[kT];
         load_block_scalar(srow, s, w, px);
         R C[kT];
-        P::template stage_a<MODE_GENERAL>(K, rc, ln, s, px, pxprev, (const int32_t *)0, C);
+        P::template stage_a<MODE_GENERAL, NFT>(K, rc, ln, s, px, pxprev, (const int32_t *)0, C);
         CVS_UNROLL
         for (int j = 0; j < kT; j++) pxprev[j] = px[j];
         if (s >= 1) {

@@ -143,7 +143,7 @@ __device__ __forceinline__ void load_block_fast(const uint32_t *srow, int k, boo
     }
 }
 
-template <typename R, bool VHS, int CD, bool OUTFULL>
+template <typename R, bool VHS, int CD, bool OUTFULL, bool NF>
 struct Stepper {
     typedef Lane<R, VHS, CD, OUTFULL> L;
     typedef Pipeline<R, VHS, CD, OUTFULL> P;
@@ -167,10 +167,10 @@ struct Stepper {
                 for (int j = 0; j < kT; j++) pxprev[j] = 0;
             }
         }
-        P::template stage_a<MODE>(K, rc, ln, s, px, pxprev, hsrow, C);
+        P::template stage_a<MODE, NF>(K, rc, ln, s, px, pxprev, hsrow, C);
         if (!EDGE && warp_hs) headswitch_substitute<R>(rc, hsrow, s - 1, C);
         if (warp_inl && (!EDGE || s >= 1)) headswitch_delay_block<R>(hsring, kNT, s - 1, K.w, rc.hs_delay, C);
-        P::template stage_b<MODE>(K, rc, ln, s, C, Yb, IQb, xo);
+        P::template stage_b<MODE, NF>(K, rc, ln, s, C, Yb, IQb, xo);
         uint32_t out[kT];
         bool have;
         int kf;
@@ -212,7 +212,8 @@ struct Stepper {
     }
 };
 
-template <typename R, bool VHS, int CD, bool OUTFULL>
+// NF: fast noise mode (cvs_set_noise_mode): per-pixel noise from per-row counter generators; fp32 only
+template <typename R, bool VHS, int CD, bool OUTFULL, bool NF = false>
 __global__ void __launch_bounds__(kNT, (sizeof(R) == 4 ? CVS_MIN_CTAS : 1)) k_fields(const __grid_constant__ LaunchArgs<R> a) {
     typedef Lane<R, VHS, CD, OUTFULL> L;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -279,7 +280,11 @@ __global__ void __launch_bounds__(kNT, (sizeof(R) == 4 ? CVS_MIN_CTAS : 1)) k_fi
     ln.tailV = tails + (size_t)kTailSlots * kNT + tid;
     ln.tail_stride = kNT;
     ln.nY = ln.nU = ln.nV = 0;
-    {
+    constexpr bool nfast = NF;
+    if (nfast) {
+        ln.rngL.l1 = lcg_seed(fd.fieldno, (unsigned)fd.field, row, 0u);
+        ln.rngC.l1 = lcg_seed(fd.fieldno, (unsigned)fd.field, row, 1u);
+    } else {
         const long long full = (long long)row * w;
         const int nd = (int)(full < kWarmPx ? full : kWarmPx);
         const bool from_start = full <= kWarmPx;
@@ -313,7 +318,7 @@ __global__ void __launch_bounds__(kNT, (sizeof(R) == 4 ? CVS_MIN_CTAS : 1)) k_fi
     // one loop the compiler would have to bring ~85 carried registers back to a common allocation at
     // every iteration (the r1e ncu capture showed exactly those moves at the loop head, 10 per pixel).
     // The edge/general loop runs twice, for the steps before and after the interior.
-    typedef Stepper<R, VHS, CD, OUTFULL> St;
+    typedef Stepper<R, VHS, CD, OUTFULL, NF> St;
     uint32_t px[kT];
     load_block_dev(srow, 0, w, vec_src, px);
     int s = 0;
@@ -387,7 +392,8 @@ __global__ void __launch_bounds__(kHsNT) k_headswitch(const __grid_constant__ La
     RowConst<R> rc;
     row_setup<R>(K, (unsigned)fd.field, fd.fieldno, row, __ldg(fd.rowinfo + row), rc);
     ln.nY = 0;
-    if (K.vnoise != 0) {
+    ln.rngL.l1 = lcg_seed(fd.fieldno, (unsigned)fd.field, row, 0u);       // fast noise mode (else init() below)
+    if (K.vnoise != 0 && !(K.flags & F_NOISE_FAST)) {
         const long long full = (long long)row * w;
         const int nd = (int)(full < kWarmPx ? full : kWarmPx);
         uint32_t hist[31];
@@ -398,38 +404,44 @@ __global__ void __launch_bounds__(kHsNT) k_headswitch(const __grid_constant__ La
     }
     int sy = fd.field + 2 * row + a.opposite;
     sy = sy > h - 1 ? h - 1 : sy;
-    headswitch_row<R>(K, rc, ln, row_ptr(fd.src, a.src_stride, sy), fd.hs_scratch + (size_t)item.slot * (size_t)w,
-                      __ldg(fd.hs_shift + item.slot));
+    if (K.flags & F_NOISE_FAST)
+        headswitch_row<R, true>(K, rc, ln, row_ptr(fd.src, a.src_stride, sy), fd.hs_scratch + (size_t)item.slot * (size_t)w,
+                                __ldg(fd.hs_shift + item.slot));
+    else
+        headswitch_row<R, false>(K, rc, ln, row_ptr(fd.src, a.src_stride, sy), fd.hs_scratch + (size_t)item.slot * (size_t)w,
+                                 __ldg(fd.hs_shift + item.slot));
 }
 
 // host-callable launchers (one translation unit per instantiation, see kern_*.cu)
-template <typename R, bool VHS, int CD, bool OUTFULL>
+template <typename R, bool VHS, int CD, bool OUTFULL, bool NF = false>
 cudaError_t launch_fields(const LaunchArgs<R> &a, cudaStream_t st);
 // resident CTAs per SM of an instantiation (for wave-aligned batch sizes)
-template <typename R, bool VHS, int CD, bool OUTFULL>
+template <typename R, bool VHS, int CD, bool OUTFULL, bool NF = false>
 cudaError_t occupancy_fields(int *ctas_per_sm);
 template <typename R>
 cudaError_t launch_headswitch(const LaunchArgs<R> &a, const HsItem *items, int nitems, cudaStream_t st);
 
-#define CVS_DEFINE_LAUNCH_FIELDS(R, VHS, CD, OUTFULL)                                                          \
+#define CVS_DEFINE_LAUNCH_FIELDS_NF(R, VHS, CD, OUTFULL, NF)                                                          \
     template <>                                                                                                \
-    cudaError_t launch_fields<R, VHS, CD, OUTFULL>(const LaunchArgs<R> &a, cudaStream_t st) {                  \
+    cudaError_t launch_fields<R, VHS, CD, OUTFULL, NF>(const LaunchArgs<R> &a, cudaStream_t st) {                  \
         const size_t smem = SmemLayout<R, VHS>::total;                                                         \
-        cudaError_t e = cudaFuncSetAttribute(k_fields<R, VHS, CD, OUTFULL>,                                    \
+        cudaError_t e = cudaFuncSetAttribute(k_fields<R, VHS, CD, OUTFULL, NF>,                                    \
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
         if (e != cudaSuccess) return e;                                                                        \
         const int ctas = (a.total_warps + kWarpsPerCta - 1) / kWarpsPerCta;                                    \
-        k_fields<R, VHS, CD, OUTFULL><<<ctas, kNT, smem, st>>>(a);                                             \
+        k_fields<R, VHS, CD, OUTFULL, NF><<<ctas, kNT, smem, st>>>(a);                                             \
         return cudaGetLastError();                                                                             \
     }                                                                                                          \
     template <>                                                                                                \
-    cudaError_t occupancy_fields<R, VHS, CD, OUTFULL>(int *ctas_per_sm) {                                      \
+    cudaError_t occupancy_fields<R, VHS, CD, OUTFULL, NF>(int *ctas_per_sm) {                                      \
         const size_t smem = SmemLayout<R, VHS>::total;                                                         \
-        cudaError_t e = cudaFuncSetAttribute(k_fields<R, VHS, CD, OUTFULL>,                                    \
+        cudaError_t e = cudaFuncSetAttribute(k_fields<R, VHS, CD, OUTFULL, NF>,                                    \
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
         if (e != cudaSuccess) return e;                                                                        \
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_fields<R, VHS, CD, OUTFULL>, kNT, smem); \
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_fields<R, VHS, CD, OUTFULL, NF>, kNT, smem); \
     }
+
+#define CVS_DEFINE_LAUNCH_FIELDS(R, VHS, CD, OUTFULL) CVS_DEFINE_LAUNCH_FIELDS_NF(R, VHS, CD, OUTFULL, false)
 
 }  // namespace cvs
 #endif

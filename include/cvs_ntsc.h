@@ -135,6 +135,18 @@ int  cvs_set_precision(cvs_ctx *ctx, int use_double);
  * y <- y+1 for y = 1,3,.. with y+1 < h, so for even h the last row is left as it was).  Off by default.
  */
 int  cvs_set_bob(cvs_ctx *ctx, int enable);
+/*
+ * Per-pixel noise source (production fp32 arithmetic only; the fp64 validation mode always replays).
+ *   CVS_NOISE_EXACT (default): every rand() draw of the reference is replayed (ffmpeg_ntsc.cpp:1640, 1729-1731).
+ *   CVS_NOISE_FAST: the per-PIXEL luma / chroma noise draws (:1640, :1729, :1731) come from per-row counter
+ *     generators instead; their amplitudes are sub-LSB in the reference's x256 domain, so the pictures stay within
+ *     +-1 LSB of the reference (more values move by 1 than in exact mode).  The per-LINE draws (phase noise :1744,
+ *     dropout :1896, head-switch jitter :1655) and the rand() stream position are exactly as in exact mode.
+ *     Ignored (exact replay) when video_noise + 2 * video_chroma_noise > 96, where the noise is no longer sub-LSB.
+ */
+#define CVS_NOISE_EXACT 0
+#define CVS_NOISE_FAST  1
+int  cvs_set_noise_mode(cvs_ctx *ctx, int mode);
 
 /* ---- the seam: exact analogue of the call at ffmpeg_ntsc.cpp:2229 ------------------------- */
 

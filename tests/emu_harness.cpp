@@ -20,7 +20,8 @@ using namespace cvs;
 
 namespace {
 
-template <typename R, bool VHS, int CD, bool OUTFULL>
+// NF: fast noise mode (cvs_set_noise_mode): the kernels' NF instantiations
+template <typename R, bool VHS, int CD, bool OUTFULL, bool NF>
 int run_field(const cvs_params &p, RandCursor &cur, uint8_t *dst, int dst_stride, const uint8_t *src,
               int src_stride, int w, int h, int interlaced, int tff, unsigned field,
               unsigned long long fieldno, int force_general) {
@@ -34,6 +35,7 @@ int run_field(const cvs_params &p, RandCursor &cur, uint8_t *dst, int dst_stride
     std::vector<R> lut;
     make_kconst<R>(p, w, h, OUTFULL, K, lut);
     if (force_general == 1) K.flags |= F_GENERAL;
+    if (NF) K.flags |= F_NOISE_FAST;
     const int nl = g.nl;
     const int opposite = interlaced ? (tff ? 1 : 0) : 0;
     auto src_row = [&](int row) {
@@ -51,7 +53,9 @@ int run_field(const cvs_params &p, RandCursor &cur, uint8_t *dst, int dst_stride
         RowConst<R> rc;
         row_setup<R>(K, field, fieldno, row, fs.rowinfo[(size_t)row], rc);
         uint32_t ring[kRngSlots];
-        if (K.vnoise != 0) {
+        ln.nY = 0;
+        ln.rngL.l1 = lcg_seed(fieldno, field, row, 0u);
+        if (K.vnoise != 0 && !NF) {
             uint32_t hist[31];
             rng_rebase(fs.window, &g.seek[(size_t)row * 62], hist);
             const int nd = warm_draws_luma(row, w);
@@ -61,7 +65,7 @@ int run_field(const cvs_params &p, RandCursor &cur, uint8_t *dst, int dst_stride
                            (long long)row * w <= kWarmPx, ln.nY))
                 return CVS_ERR_NOISE_SYNC;
         }
-        headswitch_row<R>(K, rc, ln, src_row(row), &scratch[(size_t)i * w], fs.hs_shift[(size_t)i]);
+        headswitch_row<R, NF>(K, rc, ln, src_row(row), &scratch[(size_t)i * w], fs.hs_shift[(size_t)i]);
     }
 
     const int nwarps = (nl + 30) / 31;
@@ -96,13 +100,17 @@ int run_field(const cvs_params &p, RandCursor &cur, uint8_t *dst, int dst_stride
             const int nd = warm_draws_luma(row, w);
             const bool from_start = (long long)row * w <= kWarmPx;
             uint32_t hist[31];
-            if (K.vnoise != 0) {
+            if (NF) {                                  // fast noise: per-row counter generators, no replay
+                ln.rngL.l1 = lcg_seed(fieldno, field, row, 0u);
+                ln.rngC.l1 = lcg_seed(fieldno, field, row, 1u);
+            }
+            if (K.vnoise != 0 && !NF) {
                 rng_rebase(fs.window, &g.seek[(size_t)row * 62], hist);
                 ln.rngL.init(&rings[(size_t)l * 2 * kRngSlots], 1, hist, kRngBase - (uint32_t)nd);
                 if (!warm_luma((uint32_t)(2 * K.vnoise + 1), K.vmagic, K.vshift, K.vnoise, ln.rngL, nd, from_start, ln.nY))
                     return CVS_ERR_NOISE_SYNC;
             }
-            if (K.cnoise != 0) {
+            if (K.cnoise != 0 && !NF) {
                 rng_rebase(fs.window, &g.seek[(size_t)row * 62 + 31], hist);
                 ln.rngC.init(&rings[(size_t)l * 2 * kRngSlots + kRngSlots], 1, hist, kRngBase - 2u * (uint32_t)nd);
                 if (!warm_chroma((uint32_t)(2 * K.cnoise + 1), K.cmagic, K.cshift, K.cnoise, ln.rngC, nd, from_start, ln.nU, ln.nV))
@@ -134,10 +142,10 @@ int run_field(const cvs_params &p, RandCursor &cur, uint8_t *dst, int dst_stride
 #define CVS_HEAD(M)                                                                                          \
     {                                                                                                        \
         constexpr bool FAST = (M) <= 0;                                                                      \
-        P::template stage_a<M>(K, rc[l], lane[l], s, px, pxprev, hsrow[l], C);                               \
+        P::template stage_a<M, NF>(K, rc[l], lane[l], s, px, pxprev, hsrow[l], C);                           \
         if (FAST) headswitch_substitute<R>(rc[l], hsrow[l], s - 1, C);                                       \
         if (warp_inl && (FAST || s >= 1)) headswitch_delay_block<R>(ring, 1, s - 1, w, rc[l].hs_delay, C);   \
-        P::template stage_b<M>(K, rc[l], lane[l], s, C, Yb[l], IQb[l], xo[l]);                               \
+        P::template stage_b<M, NF>(K, rc[l], lane[l], s, C, Yb[l], IQb[l], xo[l]);                           \
     }
                 if (mode == MODE_FAST_EVEN) CVS_HEAD(MODE_FAST_EVEN)
                 else if (mode == MODE_FAST) CVS_HEAD(MODE_FAST)
@@ -176,13 +184,13 @@ int run_field(const cvs_params &p, RandCursor &cur, uint8_t *dst, int dst_stride
     return 0;
 }
 
-template <typename R>
+template <typename R, bool NF>
 int dispatch(const cvs_params &p, RandCursor &cur, uint8_t *dst, int dst_stride, const uint8_t *src,
              int src_stride, int w, int h, int interlaced, int tff, unsigned field,
              unsigned long long fieldno, int force_general) {
     const Variant v = pick_variant(p);
 #define CVS_RUN(VHS, CD, OF) \
-    return run_field<R, VHS, CD, OF>(p, cur, dst, dst_stride, src, src_stride, w, h, interlaced, tff, field, fieldno, force_general)
+    return run_field<R, VHS, CD, OF, NF>(p, cur, dst, dst_stride, src, src_stride, w, h, interlaced, tff, field, fieldno, force_general)
     if (!v.vhs) { if (v.outfull) CVS_RUN(false, 9, true); else CVS_RUN(false, 9, false); }
     if (v.cd == 9) { if (v.outfull) CVS_RUN(true, 9, true); else CVS_RUN(true, 9, false); }
     if (v.cd == 12) { if (v.outfull) CVS_RUN(true, 12, true); else CVS_RUN(true, 12, false); }
@@ -196,18 +204,28 @@ extern "C" {
 
 // precision: 0 = float (production arithmetic), 1 = double (reference arithmetic).
 // rng_pos in/out: absolute rand() position (draws since the default seed).
-int emu_composite_layer(const cvs_params *p, int precision, unsigned long long *rng_pos,
-                        uint8_t *dst, int dst_stride, const uint8_t *src, int src_stride,
-                        int w, int h, int interlaced, int tff, unsigned field, unsigned long long fieldno,
-                        int force_general) {
+// noise_fast: CVS_NOISE_FAST as the library applies it (float only, small amplitudes only).
+int emu_composite_layer_ex(const cvs_params *p, int precision, unsigned long long *rng_pos,
+                           uint8_t *dst, int dst_stride, const uint8_t *src, int src_stride,
+                           int w, int h, int interlaced, int tff, unsigned field, unsigned long long fieldno,
+                           int force_general, int noise_fast) {
     if (!p || !dst || !src || w <= 0 || h <= 0 || dst_stride < 4 * w || src_stride < 4 * w) return CVS_ERR_INVALID_ARG;
     static RandCursor cur;
     cur.seek(*rng_pos);
     int rc;
-    if (precision) rc = dispatch<double>(*p, cur, dst, dst_stride, src, src_stride, w, h, interlaced, tff, field, fieldno, force_general);
-    else rc = dispatch<float>(*p, cur, dst, dst_stride, src, src_stride, w, h, interlaced, tff, field, fieldno, force_general);
+    const bool nf = noise_fast && !precision && p->video_noise + 2 * p->video_chroma_noise <= 96;
+    if (precision) rc = dispatch<double, false>(*p, cur, dst, dst_stride, src, src_stride, w, h, interlaced, tff, field, fieldno, force_general);
+    else if (nf) rc = dispatch<float, true>(*p, cur, dst, dst_stride, src, src_stride, w, h, interlaced, tff, field, fieldno, force_general);
+    else rc = dispatch<float, false>(*p, cur, dst, dst_stride, src, src_stride, w, h, interlaced, tff, field, fieldno, force_general);
     *rng_pos = cur.pos();
     return rc;
+}
+int emu_composite_layer(const cvs_params *p, int precision, unsigned long long *rng_pos,
+                        uint8_t *dst, int dst_stride, const uint8_t *src, int src_stride,
+                        int w, int h, int interlaced, int tff, unsigned field, unsigned long long fieldno,
+                        int force_general) {
+    return emu_composite_layer_ex(p, precision, rng_pos, dst, dst_stride, src, src_stride, w, h, interlaced, tff, field,
+                                  fieldno, force_general, 0);
 }
 
 // ---- small probes of the product's host-side code (glibc_rand.cpp, field_plan.cpp) -------------------

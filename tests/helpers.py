@@ -133,14 +133,14 @@ def run_ref(lib, p, frames, n, w, h, interlaced=0, tff=0):
     return dst
 
 
-def run_emu(lib, p, frames, n, w, h, precision, general=0, interlaced=0, tff=0):
+def run_emu(lib, p, frames, n, w, h, precision, general=0, interlaced=0, tff=0, noise_fast=0):
     dst = np.zeros((h, w), dtype=np.uint32)
     pos = C.c_ulonglong(0)
     for k in range(n):
         src = frames(k)
-        rc = lib.emu_composite_layer(C.byref(p), precision, C.byref(pos), dst.ctypes.data_as(C.c_void_p), 4 * w,
-                                     src.ctypes.data_as(C.c_void_p), 4 * w, w, h, interlaced, tff, (k & 1) ^ 1,
-                                     C.c_ulonglong(k), general)
+        rc = lib.emu_composite_layer_ex(C.byref(p), precision, C.byref(pos), dst.ctypes.data_as(C.c_void_p), 4 * w,
+                                        src.ctypes.data_as(C.c_void_p), 4 * w, w, h, interlaced, tff, (k & 1) ^ 1,
+                                        C.c_ulonglong(k), general, noise_fast)
         assert rc == 0, rc
     return dst, pos.value
 

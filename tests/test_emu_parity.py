@@ -75,3 +75,40 @@ def test_lane_pipeline_matches_golden(emu, name):
     argv, w, h, n, want = helpers.load_golden()[name]
     got, _ = helpers.run_emu(emu, helpers.params(*argv), lambda k: helpers.stream_frame(w, h, k), n, w, h, precision=1)
     assert np.array_equal(want, got)
+
+
+@pytest.mark.parametrize("w,h,n,argv", [(720, 480, 3, ["-vhs", "-vhs-speed", "sp"]), (724, 482, 2, ["-vhs", "-vhs-speed", "ep"]),
+                                        (720, 480, 2, []), (101, 67, 2, ["-vhs", "-vhs-speed", "lp"]),
+                                        (720, 480, 2, ["-vhs", "-chroma-dropout", "30000"])])
+def test_fast_noise_mode_stays_within_one_lsb(oracle, emu, w, h, n, argv):
+    """CVS_NOISE_FAST (include/cvs_ntsc.h): the per-pixel noise draws come from counter generators, everything
+    else -- per-line phase noise, dropouts, head-switch jitter, the rand() position -- is as in exact mode, so
+    the pictures stay within +-1 LSB of the reference and the stream position is unchanged."""
+    p = helpers.params(*argv)
+    frames = lambda k: helpers.stream_frame(w, h, k)
+    want, g = helpers.run_oracle(oracle, p, frames, n, w, h)
+    for general in (0, 1, 2):
+        got, pos = helpers.run_emu(emu, p, frames, n, w, h, precision=0, general=general, noise_fast=1)
+        mx, nd, n2 = helpers.channel_diff(want, got)
+        assert mx <= 1 and n2 == 0, (general, mx, nd, n2)
+        assert nd <= 0.15 * want.size * 4, nd            # more values move by 1 than in exact mode (< 0.5 %)
+        assert pos == g.pos
+        if general == 0:
+            ref = got
+        else:
+            assert np.array_equal(ref, got)              # all code variants draw the same fast stream
+    exact, _ = helpers.run_emu(emu, p, frames, n, w, h, precision=0)
+    assert not np.array_equal(exact, ref)                # (it really is a different noise)
+
+
+def test_fast_noise_mode_is_ignored_for_large_amplitudes_and_fp64(oracle, emu):
+    w, h, n = 160, 120, 2
+    frames = lambda k: helpers.stream_frame(w, h, k)
+    p = helpers.params("-vhs", "-noise", "100")           # 100 + 2 * 16 > 96: no longer sub-LSB
+    a, _ = helpers.run_emu(emu, p, frames, n, w, h, precision=0, noise_fast=1)
+    b, _ = helpers.run_emu(emu, p, frames, n, w, h, precision=0, noise_fast=0)
+    assert np.array_equal(a, b)
+    p = helpers.params("-vhs")
+    a, _ = helpers.run_emu(emu, p, frames, n, w, h, precision=1, noise_fast=1)
+    want, _ = helpers.run_oracle(oracle, p, frames, n, w, h)
+    assert np.array_equal(a, want)

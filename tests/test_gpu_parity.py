@@ -233,6 +233,48 @@ def test_gpu_fp32_is_bit_identical_to_cpu_emulation(emu, w, h, n, argv):
     assert np.array_equal(want, got)
 
 
+@pytest.mark.parametrize("w,h,n,argv", [(720, 480, 4, ["-vhs"]), (724, 482, 3, ["-vhs", "-vhs-speed", "ep"]),
+                                        (720, 480, 2, []), (1920, 1080, 2, ["-vhs", "-vhs-speed", "sp"]),
+                                        (101, 67, 3, ["-vhs", "-comp-catv", "-vhs-svideo", "1"]),
+                                        (3840, 2160, 1, ["-vhs", "-vhs-speed", "lp"])])   # head-switch pre-pass rows
+def test_fast_noise_mode(oracle, emu, w, h, n, argv):
+    """cvs_set_noise_mode(CVS_NOISE_FAST): per-pixel noise from counter generators (the kern_n_* instantiations).
+    Within +-1 LSB of the reference, bit-identical to the CPU emulation of the same mode, the same pictures from a
+    batch as from sequential calls, and the rand() position advances exactly as in exact mode."""
+    p = helpers.params(*argv)
+    frames = lambda k: helpers.stream_frame(w, h, k)
+    want, g = helpers.run_oracle(oracle, p, frames, n, w, h)
+    got = np.zeros((h, w), dtype=np.uint32)
+    with cvs.Engine(params=p, max_w=w, max_h=h, max_batch=n) as eng:
+        eng.set_noise_mode(True)
+        for k in range(n):
+            eng.composite_layer(got, frames(k), (k & 1) ^ 1, k)
+        assert eng.rng_tell() == g.pos
+        mx, nd, n2 = helpers.channel_diff(want, got)
+        assert mx <= 1 and n2 == 0, (mx, nd, n2)
+        assert nd <= 0.03 * want.size * 4, nd
+        if w <= 1920:
+            emu_out, _ = helpers.run_emu(emu, p, frames, n, w, h, precision=0, noise_fast=1)
+            assert np.array_equal(emu_out, got)
+        # batch == sequential in this mode too (the generators are seeded per field and row)
+        src = np.stack([frames(k) for k in range(n)])
+        bat = np.zeros((n, h, w), dtype=np.uint32)
+        eng.rng_seek(0)
+        eng.composite_fields_host(bat, src, 0)
+        seq = np.zeros((n, h, w), dtype=np.uint32)
+        eng.rng_seek(0)
+        for k in range(n):
+            eng.composite_layer(seq[k], src[k], (k & 1) ^ 1, k)
+        assert np.array_equal(bat, seq)
+        # and the fp64 validation mode ignores it: bit-exact
+        eng.set_precision(True)
+        eng.rng_seek(0)
+        exact = np.zeros((h, w), dtype=np.uint32)
+        for k in range(n):
+            eng.composite_layer(exact, frames(k), (k & 1) ^ 1, k)
+        assert np.array_equal(exact, want)
+
+
 @pytest.mark.parametrize("w,h", [(160, 120), (164, 121)])
 def test_fused_bob_matches_reference_loop(oracle, w, h):
     """composite_layer + the line doubling of the main loop (ffmpeg_ntsc.cpp:2229-2257) over a reused
