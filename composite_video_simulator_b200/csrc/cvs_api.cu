@@ -273,12 +273,14 @@ int run_device(cvs_ctx *c, uint8_t *dst, size_t dst_pic_stride, int dst_stride, 
     if (sl.in_flight) { CVS_CUDA(cudaEventSynchronize(sl.consumed)); sl.in_flight = false; }
 
     const int opposite = interlaced ? (tff ? 1 : 0) : 0;                               // :1585-1588
-    // Planning.  Pass 1 (serial, cheap): per field, its plan and a copy of the rand() cursor at its first
-    // draw (one 31x31 jump per field).  Pass 2 (a few host threads): the per-row side tables, which is
-    // where the time goes (5.8 us per 1080p field on one thread).  Pass 3 (serial): the head-switch
-    // pre-pass work list.
+    // Planning.  Pass 1 (serial, cheap): per field, its plan and the rand() position of its first draw
+    // relative to the batch (a prefix sum: the draw count is a function of the geometry).  Pass 2 (a few
+    // host threads): every thread jumps a copy of the cursor to its first field (one x^d, d < 2^40) and then
+    // walks its fields (one 31x31 jump each) building the per-row side tables, which is where the time goes
+    // (5.8 us per 1080p field on one thread).  Pass 3 (serial): the head-switch pre-pass work list.
     int nitems = 0, max_nl = 0, min_nl = 1 << 30, total_rows = 0;
-    struct Job { DevPlan *pl; RandCursor at; int hs_count; };
+    struct Job { DevPlan *pl; unsigned long long rel; int hs_count; };   // rel: draws of the batch before this field
+    unsigned long long total_draws = 0;
     std::vector<Job> jobs((size_t)n);
     for (int k = 0; k < n; k++) {
         const unsigned long long fieldno = first_fieldno + (unsigned long long)k;
@@ -290,6 +292,7 @@ int run_device(cvs_ctx *c, uint8_t *dst, size_t dst_pic_stride, int dst_stride, 
         fd.fieldno = fieldno;
         fd.field = (int32_t)field;
         jobs[(size_t)k].pl = nullptr;
+        jobs[(size_t)k].rel = total_draws;
         jobs[(size_t)k].hs_count = 0;
         fd.row_start = total_rows;
         if ((int)field >= h) { fd.nl = 0; continue; }      // no rows of this parity: nothing drawn, nothing written
@@ -297,8 +300,7 @@ int run_device(cvs_ctx *c, uint8_t *dst, size_t dst_pic_stride, int dst_stride, 
         int rc = get_plan(c, w, h, field, &pl);
         if (rc != CVS_OK) return rc;
         jobs[(size_t)k].pl = pl;
-        jobs[(size_t)k].at = c->cur;
-        c->cur.jump(pl->g.jumpN, pl->g.ndraws);
+        total_draws += pl->g.ndraws;
         fd.nl = pl->g.nl;
         fd.row_start = total_rows;
         total_rows += fd.nl;
@@ -310,13 +312,18 @@ int run_device(cvs_ctx *c, uint8_t *dst, size_t dst_pic_stride, int dst_stride, 
         fd.hs_shift = sl.d_hsshift + (size_t)k * c->hs_max;
     }
     bool capacity_error = false;
+    const RandCursor batch_start = c->cur;
+    RandCursor batch_end = c->cur;
     auto plan_range = [&](int k0, int k1) {
         FieldSide fs;
+        RandCursor cur = batch_start;
+        if (jobs[(size_t)k0].rel) cur.advance(jobs[(size_t)k0].rel);
         for (int k = k0; k < k1; k++) {
             Job &jb = jobs[(size_t)k];
             if (!jb.pl) continue;
             FieldDesc &fd = sl.h_fields[k];
-            build_field_side_at(c->p, jb.pl->g, jb.at, fs);
+            build_field_side_at(c->p, jb.pl->g, cur, fs);
+            cur.jump(jb.pl->g.jumpN, jb.pl->g.ndraws);
             std::memcpy(sl.h_rowinfo + (size_t)k * c->nl_max, fs.rowinfo.data(), fs.rowinfo.size() * sizeof(uint32_t));
             std::memcpy(fd.window, fs.window, sizeof(fs.window));
             fd.hs_first = fs.hs_first;
@@ -325,6 +332,7 @@ int run_device(cvs_ctx *c, uint8_t *dst, size_t dst_pic_stride, int dst_stride, 
             for (int i = 0; i < fs.hs_count; i++) sl.h_hsshift[(size_t)k * c->hs_max + i] = fs.hs_shift[(size_t)i];
             jb.hs_count = fs.hs_count;
         }
+        if (k1 == n) batch_end = cur;                  // (exactly one range ends the batch)
     };
     const int nthreads = (n >= 64) ? c->plan_threads : 1;
     if (nthreads <= 1) {
@@ -337,6 +345,7 @@ int run_device(cvs_ctx *c, uint8_t *dst, size_t dst_pic_stride, int dst_stride, 
         plan_range(0, per < n ? per : n);
         for (auto &th : pool) th.join();
     }
+    c->cur = batch_end;                                // the stream position after the batch
     if (capacity_error) return CVS_ERR_CAPACITY;
     for (int k = 0; k < n; k++)
         for (int i = 0; i < jobs[(size_t)k].hs_count; i++) {
