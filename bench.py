@@ -219,6 +219,29 @@ def make_device_stream(torch, n, first, device):
     return out
 
 
+def bind_near_gpu(torch, local_rank):
+    """Run this rank (and the threads and pinned buffers it creates from here on: first touch) on the CPUs of the
+    GPU's NUMA node, as a host application feeding a GPU over PCIe would.  Returns a description, or None."""
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        dom, bus, devn = getattr(pr, "pci_domain_id", 0), pr.pci_bus_id, pr.pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/local_cpulist" % (dom, bus, devn)
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            if not part:
+                continue
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cur = os.sched_getaffinity(0)
+        near = cpus & cur
+        if not near or near == cur:
+            return None
+        os.sched_setaffinity(0, near)
+        return "%d CPUs of the GPU's NUMA node" % len(near)
+    except Exception:
+        return None
+
+
 def run_own_arm(args):
     import numpy as np
     import torch
@@ -232,6 +255,7 @@ def run_own_arm(args):
         raise RuntimeError("bench.py needs a CUDA device: the engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_near_gpu(torch, local_rank) if args.numa_bind else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -405,7 +429,7 @@ def run_own_arm(args):
                    "l2": "inputs larger than L2 (%.0f MB read + %.0f MB written per step)" % (alg_bytes / 2e6, alg_bytes / 2e6),
                    "noise": ("exact glibc rand() replay" if args.noise == "exact" else
                              "fast mode: per-pixel noise from counter generators (+-1 LSB), per-line draws exact"),
-                   "other_noise_mode": other, "parallelism": "fields sharded by contiguous chunk, no data-path collective"},
+                   "other_noise_mode": other, "host_affinity": numa or "unchanged", "parallelism": "fields sharded by contiguous chunk, no data-path collective"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "fields/s", "h2d_bytes_per_step": Be * nl * 4 * W,
                 "d2h_bytes_per_step": Be * nl * 4 * W, "fields_per_step_per_gpu": Be, "result_checksum": e2e_checksum},
@@ -454,6 +478,8 @@ def main():
     ap.add_argument("--e2e-batch", type=int, default=128, help="fields per GPU per step (host buffers; 4 pinned buffers of this many pictures per rank)")
     ap.add_argument("--cpu-fields", type=int, default=64, help="fields of the single-thread CPU baseline sample")
     ap.add_argument("--ref-fields-per-proc", type=int, default=4)
+    ap.add_argument("--no-numa-bind", dest="numa_bind", action="store_false",
+                    help="do not move the process to the CPUs of the GPU's NUMA node")
     ap.add_argument("--noise", default="exact", choices=["exact", "fast"],
                     help="per-pixel noise source of the measured runs (cvs_set_noise_mode); the headline is exact")
     ap.add_argument("--no-noise-side", dest="noise_side", action="store_false",
