@@ -70,6 +70,7 @@ struct cvs422_ctx {
     bool own_stream = true;
     cudaStream_t s_tab = nullptr;                 // uploads the per-batch side tables while the previous batch computes
     RandCursor cur;
+    int packed_rows = 1;                          // CVS_PACKED_ROWS=0: per-field warps (experiments / tests)
     std::vector<std::unique_ptr<DevPlan422>> plans;
     Slot slots[kSlots];
     int next_slot = 0;
@@ -175,7 +176,7 @@ int run_device(cvs422_ctx *c, uint8_t *y, uint8_t *u, uint8_t *v, long long psy,
     const int wpf = (nl_max + kRowsPerWarp - 1) / kRowsPerWarp;
     const int halo_y = round_up(w + 2, 16), halo_c = round_up(w / 2, 16);
     const int halo_pitch = halo_y + 2 * halo_c;
-    int nitems = 0;
+    int nitems = 0, total_rows = 0, max_nl = 0, min_nl = 1 << 30;
     FieldSide fs;
     for (int k = 0; k < n; k++) {
         const unsigned long long fieldno = first_fieldno + (unsigned long long)k;
@@ -193,6 +194,10 @@ int run_device(cvs422_ctx *c, uint8_t *y, uint8_t *u, uint8_t *v, long long psy,
         fd.halo = c->d_halo + (size_t)k * (size_t)c->wpf_max * (size_t)c->halo_pitch_max;
         fd.fieldno = fieldno;
         fd.field = (int32_t)field; fd.nl = g.nl; fd.hs_first = fs.hs_first; fd.hs_count = fs.hs_count;
+        fd.row_start = total_rows; fd.pad_ = 0;
+        total_rows += g.nl;
+        if (g.nl > max_nl) max_nl = g.nl;
+        if (g.nl < min_nl) min_nl = g.nl;
         std::memcpy(fd.window, fs.window, sizeof(fs.window));
         if (g.nl > 0) std::memcpy(sl.h_rowinfo + (size_t)k * (size_t)c->nl_max, fs.rowinfo.data(), (size_t)g.nl * sizeof(uint32_t));
         if (fs.hs_count > c->hs_max) return CVS_ERR_CAPACITY;
@@ -217,6 +222,12 @@ int run_device(cvs422_ctx *c, uint8_t *y, uint8_t *u, uint8_t *v, long long psy,
     a.nfields = n;
     a.warps_per_field = wpf;
     a.total_warps = n * wpf;
+    // packed mapping: a warp of 31 consecutive rows of the batch then meets at most two fields
+    a.packed = (c->packed_rows && n > 1 && min_nl > kRowsPerWarp) ? 1 : 0;
+    a.total_rows = total_rows;
+    a.max_nl = max_nl > 0 ? max_nl : 1;
+    a.halo_base = c->d_halo;
+    if (a.packed) a.total_warps = (total_rows + kRowsPerWarp - 1) / kRowsPerWarp;
     a.ly = ly; a.lu = lu; a.lv = lv;
     a.by = (long long)ly * h; a.bu = (long long)lu * h; a.bv = (long long)lv * h;
     a.halo_pitch = halo_pitch; a.halo_u = halo_y; a.halo_v = halo_y + halo_c;
@@ -243,7 +254,7 @@ int run_device(cvs422_ctx *c, uint8_t *y, uint8_t *u, uint8_t *v, long long psy,
     CVS_CUDA(launch_yuv422(a, sl.d_items, nitems, c->stream));
     if (e1) CVS_CUDA(cudaEventRecord(e1, c->stream));
     CVS_CUDA(cudaEventRecord(sl.kernel_done, c->stream));
-    c->launches += 1 + (wpf > 1 ? 1 : 0) + (nitems > 0 ? 1 : 0);
+    c->launches += 1 + ((a.packed ? a.total_warps > 1 : wpf > 1) ? 1 : 0) + (nitems > 0 ? 1 : 0);
     return CVS_OK;
 }
 
@@ -277,6 +288,7 @@ int cvs422_create(cvs422_ctx **out, const cvs422_params *p, int device, int max_
     c->hs_max = head_switch_rows_bound(max_w);
     c->halo_pitch_max = round_up(max_w + 2, 16) + 2 * round_up(max_w / 2, 16);
     c->cur.seed(1);
+    if (const char *e = std::getenv("CVS_PACKED_ROWS")) c->packed_rows = std::atoi(e) != 0;
     bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&c->s_tab, cudaStreamNonBlocking) == cudaSuccess;
     for (auto &s : c->slots) {

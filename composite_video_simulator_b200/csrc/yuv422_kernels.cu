@@ -7,8 +7,8 @@ namespace cvs422 {
 cudaError_t launch_yuv422(const Launch422 &a, const HsItem422 *d_items, int nitems, cudaStream_t st) {
     cudaError_t e = cudaFuncSetAttribute(k_yuv422, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem422::total);
     if (e != cudaSuccess) return e;
-    if (a.warps_per_field > 1) {
-        k_yuv422_halo<<<a.nfields * a.warps_per_field, 128, 0, st>>>(a);
+    if (a.packed ? a.total_warps > 1 : a.warps_per_field > 1) {
+        k_yuv422_halo<<<a.packed ? a.total_warps : a.nfields * a.warps_per_field, 128, 0, st>>>(a);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     if (nitems > 0) {

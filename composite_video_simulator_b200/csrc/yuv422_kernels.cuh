@@ -44,6 +44,7 @@ struct FieldDesc422 {
     uint8_t *halo;                       // warps_per_field halo records (halo_pitch bytes each)
     unsigned long long fieldno;
     int32_t field, nl, hs_first, hs_count;
+    int32_t row_start, pad_;             // rows of the preceding fields of the batch (packed mapping)
     uint32_t window[64];
 };
 
@@ -56,6 +57,10 @@ struct Launch422 {
     DivPair dv;
     const FieldDesc422 *fields;
     int32_t nfields, warps_per_field, total_warps;
+    // packed mapping (as in scanline_kernels.cuh): the rows of all fields of the batch form one sequence cut into
+    // warps of 31; halo records are then indexed by the global warp (halo_base), not by (field, warp of the field)
+    int32_t packed, total_rows, max_nl;
+    uint8_t *halo_base;
     int32_t ly, lu, lv;                  // linesizes
     long long by, bu, bv;                // plane sizes in bytes (linesize * h): reads past them return 0
     int32_t halo_pitch, halo_u, halo_v;  // halo record: [Y: w + 2 bytes][U at halo_u][V at halo_v]
@@ -65,7 +70,7 @@ struct Launch422 {
 
 struct Smem422 {
     static constexpr size_t rng = (size_t)2 * kRngSlots * kNT * sizeof(uint32_t);
-    static constexpr size_t wins = (size_t)kWarps * 64 * sizeof(uint32_t);
+    static constexpr size_t wins = (size_t)kWarps * 128 * sizeof(uint32_t);   // two fields can meet in a warp
     static constexpr size_t ry = (size_t)kNT * kStrideY, rya = (size_t)kNT * kStrideA;
     static constexpr size_t rc = (size_t)kNT * kStrideC;
     static constexpr size_t rcomb = (size_t)kNT * 3 * kMaxRecombine * sizeof(int32_t);
@@ -211,21 +216,46 @@ __global__ void __launch_bounds__(kNT, CVS422_MIN_CTAS) k_yuv422(const __grid_co
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gw = blockIdx.x * kWarps + warp;
     if (gw >= a.total_warps) return;
-    const int fi = gw / a.warps_per_field, wp = gw - fi * a.warps_per_field;
-    const FieldDesc422 &fd = a.fields[fi];
-    const int nl = fd.nl;
-    if (kRowsPerWarp * wp >= nl) return;
     const K422 &K = a.K;
     const int w = K.w;
+    // which field row this lane computes (lane 0 = the halo row: the row above lane 1's)
+    int fi, row;
+    bool valid;
+    const uint8_t *halo_rec;             // this warp's halo record
+    if (a.packed) {
+        int g = kRowsPerWarp * gw + lane - 1;
+        valid = (lane >= 1) && g < a.total_rows;
+        g = g < 0 ? 0 : (g > a.total_rows - 1 ? a.total_rows - 1 : g);
+        fi = g / a.max_nl;                                    // never beyond the row's field
+        while (g >= a.fields[fi].row_start + a.fields[fi].nl) fi++;
+        row = g - a.fields[fi].row_start;
+        const int fi1 = __shfl_sync(0xffffffffu, fi, 1);
+        if (lane == 0 && fi != fi1) { fi = fi1; row = 0; }    // lane 1 is row 0 of its field: no halo needed
+        halo_rec = a.halo_base + (size_t)gw * (size_t)a.halo_pitch;
+    } else {
+        fi = gw / a.warps_per_field;
+        const int wp = gw - fi * a.warps_per_field, nlw = a.fields[fi].nl;
+        if (kRowsPerWarp * wp >= nlw) return;
+        row = kRowsPerWarp * wp + lane - 1;
+        valid = (lane >= 1) && row < nlw;
+        row = row < 0 ? 0 : (row > nlw - 1 ? nlw - 1 : row);
+        halo_rec = a.fields[fi].halo + (size_t)wp * (size_t)a.halo_pitch;
+    }
+    const FieldDesc422 &fd = a.fields[fi];
+    // lane 0 re-reads the row above lane 1's row from the copy k_yuv422_halo took, unless lane 1 is row 0
+    const bool halo_copy = __shfl_sync(0xffffffffu, row, 1) >= 1;
 
-    uint32_t *win = wins + warp * 64;
-    win[lane] = fd.window[lane];
-    win[lane + 32] = fd.window[lane + 32];
-    __syncwarp();
-
-    int row = kRowsPerWarp * wp + lane - 1;
-    const bool valid = (lane >= 1) && row < nl;
-    row = row < 0 ? 0 : (row > nl - 1 ? nl - 1 : row);
+    // generator windows of the (at most two) fields of this warp: [0,64) the field of lane 1, [64,128) that of lane 31
+    uint32_t *win = wins + warp * 128;
+    {
+        const int fiA = __shfl_sync(0xffffffffu, fi, 1), fiB = __shfl_sync(0xffffffffu, fi, 31);
+        win[lane] = a.fields[fiA].window[lane];
+        win[lane + 32] = a.fields[fiA].window[lane + 32];
+        win[lane + 64] = a.fields[fiB].window[lane];
+        win[lane + 96] = a.fields[fiB].window[lane + 32];
+        __syncwarp();
+        if (fi != fiA) win += 64;
+    }
     const long long y = (long long)fd.field + 2 * row;
 
     Lane422 ln;
@@ -242,8 +272,8 @@ __global__ void __launch_bounds__(kNT, CVS422_MIN_CTAS) k_yuv422(const __grid_co
 
     // rows: lanes 1..31 read the picture; the halo lane of warps 1.. reads the copy k_yuv422_halo took
     LaneSrc src;
-    if (lane == 0 && wp > 0) {
-        const uint8_t *hr = fd.halo + (size_t)wp * (size_t)a.halo_pitch;
+    if (lane == 0 && halo_copy) {
+        const uint8_t *hr = halo_rec;
         src.y = hr; src.u = hr + a.halo_u; src.v = hr + a.halo_v;
         src.y_avail = w + 2;
     } else {
@@ -310,14 +340,27 @@ __global__ void __launch_bounds__(kNT, CVS422_MIN_CTAS) k_yuv422(const __grid_co
     }
 }
 
-// one CTA per (field, warp index >= 1): copy the row above the warp's first row
+// one CTA per warp of the main pass: copy the row above the warp's first row (unless that is row 0 of a field)
 __global__ void __launch_bounds__(128) k_yuv422_halo(const __grid_constant__ Launch422 a) {
-    const int fi = blockIdx.x / a.warps_per_field, wp = blockIdx.x - fi * a.warps_per_field;
+    int fi, row;
+    uint8_t *hr;
+    if (a.packed) {
+        const int gw = blockIdx.x, g1 = kRowsPerWarp * gw;     // lane 1's position in the batch's sequence of rows
+        if (g1 >= a.total_rows) return;
+        fi = g1 / a.max_nl;
+        while (g1 >= a.fields[fi].row_start + a.fields[fi].nl) fi++;
+        row = g1 - a.fields[fi].row_start - 1;
+        if (row < 0) return;
+        hr = a.halo_base + (size_t)gw * (size_t)a.halo_pitch;
+    } else {
+        fi = blockIdx.x / a.warps_per_field;
+        const int wp = blockIdx.x - fi * a.warps_per_field;
+        if (wp == 0 || kRowsPerWarp * wp >= a.fields[fi].nl) return;
+        row = kRowsPerWarp * wp - 1;
+        hr = a.fields[fi].halo + (size_t)wp * (size_t)a.halo_pitch;
+    }
     const FieldDesc422 &fd = a.fields[fi];
-    if (wp == 0 || kRowsPerWarp * wp >= fd.nl) return;
-    const int row = kRowsPerWarp * wp - 1;
     const long long y = (long long)fd.field + 2 * row;
-    uint8_t *hr = fd.halo + (size_t)wp * (size_t)a.halo_pitch;
     const int w = a.K.w, cw = a.K.cw;
     const long long left = a.by - y * a.ly;
     for (int x = threadIdx.x; x < w + 2; x += blockDim.x) hr[x] = (x < left) ? fd.y[y * a.ly + x] : (uint8_t)0;

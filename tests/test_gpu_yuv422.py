@@ -94,6 +94,32 @@ def test_batch_equals_sequential_and_device_form(orc, y422):
                 assert np.array_equal(want[k][pl], got.cpu().numpy()), (k, pl)
 
 
+@pytest.mark.parametrize("w,h,n,argv", [(64, 67, 7, ["-vhs"]),                       # 34 / 33 rows per parity: two fields meet in a warp
+                                        (96, 65, 5, ["-vhs", "-vhs-speed", "ep"]),   # 33 / 32 rows
+                                        (64, 61, 5, ["-vhs"]),                       # 31 / 30 rows: not packed
+                                        (720, 480, 6, [])])
+def test_packed_rows_batch_equals_oracle(orc, y422, w, h, n, argv):
+    """The batch's rows are cut into warps of 31 across field boundaries (`packed`, halo records per warp of the
+    launch): bit-exact against the oracle, and the same bytes as the per-field mapping."""
+    import os
+    p = helpers.params422(*argv)
+    want, _ = helpers.run_oracle422(orc, p, w, h, n, pad=4)
+    got = {}
+    for packed in ("1", "0"):
+        os.environ["CVS_PACKED_ROWS"] = packed
+        try:
+            Y, U, V = stack([helpers.yuv422_frame(w, h, k, 4) for k in range(n)])
+            with y422.Yuv422Engine(argv, max_w=w, max_h=h, max_batch=n) as eng:
+                eng.process_fields_host(Y, U, V, w, 0)
+            got[packed] = (Y, U, V)
+        finally:
+            os.environ.pop("CVS_PACKED_ROWS", None)
+    for k in range(n):
+        for pl in range(3):
+            assert np.array_equal(want[k][pl], got["1"][pl][k]), (k, pl)
+            assert np.array_equal(got["0"][pl][k], got["1"][pl][k]), (k, pl)
+
+
 def test_tight_rows_and_unaligned_strides(orc, y422):
     """linesize == width (the two bytes past a row are the next row's) and odd linesizes (byte path)."""
     for w, h, pad in ((64, 32, 0), (102, 31, 3), (720, 64, 5)):
