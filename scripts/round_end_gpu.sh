@@ -13,6 +13,7 @@ for l in sys.stdin:
         d=json.loads(l); print('$1 $2x$3 B=%d value %.0f kernel_ms %.3f achieved %.1f GB/s frac %.4f'%(d['config']['fields_per_step_per_gpu'],d['value'],d['roofline']['kernel_ms_per_launch'],d['roofline']['achieved'],d['roofline']['frac']))
 "
 done | tee gpurun_out/bench_r1_presets.txt
+python scripts/bench_yuv422.py --steps 5 --warmup 3 > gpurun_out/bench_r1_yuv422.json 2> gpurun_out/bench_r1_yuv422.err
 # the dominant kernel, once (cold-cache, serialised: compare shares, not absolute times)
 ncu --set full --clock-control none --import-source on -k regex:k_fields -s 3 -c 1 -o gpurun_out/prof_r1i_kfields python bench.py --steps 1 --warmup 3 --e2e-batch 16 --cpu-fields 0 > /dev/null 2>&1
 # every launch of the step with its device time
