@@ -13,7 +13,8 @@
 // Switches: every switch of the reference's parse_argv() (ffmpeg_ntsc.cpp:972-1282; -i/-o name raw
 // files, "-" = stdin/stdout), plus  -height <n> (the reference derives it from -tvstd),
 // -fields-per-frame <n> (how many output fields each input frame is shown for; default 2 = 29.97p
-// material at the 59.94 field rate), -batch <n> (fields per GPU launch), -double (fp64 validation mode).
+// material at the 59.94 field rate), -batch <n> (fields per GPU launch), -double (fp64 validation mode), -fast-noise (per-pixel noise from counter
+// generators instead of the exact rand() replay: within +-1 LSB, per-line effects unchanged; cvs_set_noise_mode).
 //
 // Example (ffmpeg on either side does the decode/encode the reference does in-process):
 //   ffmpeg -i in.mp4 -vf scale=720:480 -pix_fmt bgra -f rawvideo - |
@@ -40,7 +41,7 @@ static size_t read_full(FILE *f, uint8_t *buf, size_t n) {
 
 int main(int argc, char **argv) {
     std::string in_path, out_path;
-    int height = 0, fields_per_frame = 2, batch = 32, use_double = 0;
+    int height = 0, fields_per_frame = 2, batch = 32, use_double = 0, fast_noise = 0;
     std::vector<const char *> ref_argv;
     ref_argv.push_back(argv[0]);
     for (int i = 1; i < argc; i++) {
@@ -57,6 +58,7 @@ int main(int argc, char **argv) {
         else if (a[0] == '-' && !strcmp(n, "fields-per-frame")) fields_per_frame = atoi(need("-fields-per-frame"));
         else if (a[0] == '-' && !strcmp(n, "batch")) batch = atoi(need("-batch"));
         else if (a[0] == '-' && !strcmp(n, "double")) use_double = 1;
+        else if (a[0] == '-' && !strcmp(n, "fast-noise")) fast_noise = 1;
         else ref_argv.push_back(a);
     }
     cvs_params p;
@@ -81,6 +83,7 @@ int main(int argc, char **argv) {
     if (rc != CVS_OK) { fprintf(stderr, "cvs_create: %s\n", cvs_strerror(rc)); return 1; }
     cvs_set_bob(ctx, 1);
     cvs_set_precision(ctx, use_double);
+    cvs_set_noise_mode(ctx, fast_noise ? CVS_NOISE_FAST : CVS_NOISE_EXACT);
 
     const size_t pic = (size_t)w * h * 4, row = (size_t)w * 4;
     std::vector<uint8_t> frame(pic), src((size_t)batch * pic), dst((size_t)batch * pic);
