@@ -38,6 +38,10 @@ def load():
         "cvs_set_precision": (C.c_int, [vp, C.c_int]),
         "cvs_set_bob": (C.c_int, [vp, C.c_int]),
         "cvs_set_noise_mode": (C.c_int, [vp, C.c_int]),
+        "cvs_audio_channels": (C.c_int, [P]),
+        "cvs_audio_create": (C.c_int, [C.POINTER(vp), P]),
+        "cvs_audio_process": (C.c_int, [vp, C.c_void_p, C.c_uint, C.POINTER(C.c_ulonglong)]),
+        "cvs_audio_destroy": (None, [vp]),
         "cvs_preferred_batch": (C.c_int, [vp, C.c_int, C.c_int, C.c_int]),
         "cvs_composite_layer": (C.c_int, [vp, u8p, C.c_int, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                           C.c_uint, C.c_ulonglong]),
@@ -66,7 +70,8 @@ def load():
 EXPORTED_SYMBOLS = [
     "cvs_abi_version", "cvs_strerror", "cvs_params_default_ntsc", "cvs_params_preset_pal",
     "cvs_params_apply_argv", "cvs_draws_per_field", "cvs_create", "cvs_destroy", "cvs_set_params",
-    "cvs_set_precision", "cvs_set_bob", "cvs_set_noise_mode", "cvs_preferred_batch", "cvs_composite_layer", "cvs_composite_fields_device", "cvs_composite_fields_host",
+    "cvs_set_precision", "cvs_set_bob", "cvs_set_noise_mode", "cvs_audio_channels", "cvs_audio_create", "cvs_audio_process",
+    "cvs_audio_destroy", "cvs_preferred_batch", "cvs_composite_layer", "cvs_composite_fields_device", "cvs_composite_fields_host",
     "cvs_composite_fields_host_async",
     "cvs_synchronize", "cvs_rng_seek", "cvs_rng_tell", "cvs_kernel_launches", "cvs_kernel_time_reset",
     "cvs_kernel_time_query", "cvs_set_stream",

@@ -60,6 +60,44 @@ def _ptr(a):
     raise TypeError("expected a numpy array, a torch tensor or an address")
 
 
+class Audio:
+    """composite_audio_process() of ffmpeg_ntsc (ffmpeg_ntsc.cpp:901-970) on the CPU: cvs_audio_* of the C ABI.
+    `process(pcm, rng_pos)` filters interleaved int16 samples [n, channels] in place and returns the rand() stream
+    position after the tape-hiss draws, to be handed back to the video engine (Engine.rng_seek)."""
+
+    def __init__(self, argv=(), params=None):
+        self.lib = _lib.load()
+        self.params = params.copy() if params is not None else params_from_argv(list(argv))
+        self._a = C.c_void_p()
+        _check(self.lib.cvs_audio_create(C.byref(self._a), C.byref(self.params)), "cvs_audio_create")
+        self.channels = self.lib.cvs_audio_channels(C.byref(self.params))
+
+    def process(self, pcm, rng_pos=0):
+        import numpy as np
+        assert pcm.dtype == np.int16 and pcm.flags["C_CONTIGUOUS"] and pcm.size % self.channels == 0
+        pos = C.c_ulonglong(rng_pos)
+        _check(self.lib.cvs_audio_process(self._a, pcm.ctypes.data_as(C.c_void_p), pcm.size // self.channels,
+                                          C.byref(pos)), "cvs_audio_process")
+        return pos.value
+
+    def close(self):
+        if getattr(self, "_a", None) is not None and self._a:
+            self.lib.cvs_audio_destroy(self._a)
+            self._a = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
 class Engine:
     """One CUDA scanline engine (context of the C ABI) bound to one device."""
 

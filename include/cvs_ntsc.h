@@ -148,6 +148,22 @@ int  cvs_set_bob(cvs_ctx *ctx, int enable);
 #define CVS_NOISE_FAST  1
 int  cvs_set_noise_mode(cvs_ctx *ctx, int mode);
 
+/* ---- the audio step of the same program (CPU) ----------------------------------
+ * composite_audio_process(int16_t *audio, unsigned samples) (ffmpeg_ntsc.cpp:901-970; called per decoded audio
+ * packet from process_audio(), :1284-1290): band limiting, pre/de-emphasis, sync-pulse buzz of linear tracks, tape
+ * hiss, high boost -- in place on interleaved signed 16-bit samples at 44.1 kHz (output_audio_rate, :212) with
+ * cvs_audio_channels(p) channels (output_audio_channels after parse_argv(), :1227-1262).  It needs no GPU.
+ * The hiss draws rand() once per sample and channel (:952) from the SAME stream as the video noise, so a host
+ * that interleaves audio packets and fields like the reference's main loop passes the stream position through:
+ *     cvs_rng_tell(ctx, &pos); cvs_audio_process(a, pcm, n, &pos); cvs_rng_seek(ctx, pos);
+ * Filter state and the sample counter (audio_proc_count, :889) persist in the cvs_audio object.
+ */
+typedef struct cvs_audio cvs_audio;
+int  cvs_audio_channels(const cvs_params *p);
+int  cvs_audio_create(cvs_audio **out, const cvs_params *p);          /* == "prepare audio filtering", :2031-2066 */
+int  cvs_audio_process(cvs_audio *a, int16_t *audio, unsigned samples, unsigned long long *rng_pos /* in/out */);
+void cvs_audio_destroy(cvs_audio *a);
+
 /* ---- the seam: exact analogue of the call at ffmpeg_ntsc.cpp:2229 ------------------------- */
 
 /*

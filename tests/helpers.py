@@ -50,6 +50,46 @@ def load_ref():
     return lib
 
 
+def load_refaudio():
+    """The reference's own composite_audio_process(), extracted at build time (never committed)."""
+    path = os.path.join(ORACLE_DIR, "_ref", "librefaudio.so")
+    if not os.path.exists(path):
+        if os.path.exists("/root/reference/ffmpeg_ntsc.cpp"):
+            subprocess.check_call(["make", "ref"], cwd=ORACLE_DIR, stdout=subprocess.DEVNULL)
+        else:
+            return None
+    return C.CDLL(path)
+
+
+def audio_signal(n, channels, seed):
+    """Deterministic test PCM [n, channels] int16: a sweep, a loud low tone (drives the limiter) and LCG noise."""
+    t = np.arange(n, dtype=np.float64) / 44100.0
+    x = 0.45 * np.sin(2 * np.pi * (200.0 + 6000.0 * t) * t) + 0.7 * np.sin(2 * np.pi * 55.0 * t)
+    s = np.uint64(seed * 2654435761 + 12345)
+    noise = np.empty(n * channels, dtype=np.float64)
+    v = int(s) & 0xFFFFFFFF
+    for i in range(n * channels):
+        v = (v * 1664525 + 1013904223) & 0xFFFFFFFF
+        noise[i] = ((v >> 8) / float(1 << 24) - 0.5) * 0.3
+    out = np.empty((n, channels), dtype=np.float64)
+    for c in range(channels):
+        out[:, c] = x * (1.0 if c == 0 else 0.8) + noise[c::channels]
+    return np.clip(np.round(out * 32768.0), -32768, 32767).astype(np.int16)
+
+
+def run_refaudio(lib, p, pcm_packets):
+    """The reference on a list of int16 packets [n, ch] (fresh filters, default-seeded rand()); returns the
+    processed packets and the number of rand() draws it made."""
+    lib.refaudio_setup(C.byref(p))
+    lib.refaudio_srand(1)
+    out = []
+    for pk in pcm_packets:
+        a = np.ascontiguousarray(pk.copy())
+        lib.refaudio_process(a.ctypes.data_as(C.c_void_p), C.c_uint(a.shape[0]))
+        out.append(a)
+    return out, int(lib.refaudio_rand())
+
+
 def load_emu():
     """CPU emulation of the lane pipeline.  CVS_EMU_KT=4 builds it with the 4-pixel step (experiments)."""
     kt = os.environ.get("CVS_EMU_KT")
