@@ -195,6 +195,15 @@ class Engine:
                                                     int(src_top_field_first), n, first_fieldno),
                "cvs_composite_fields_device")
 
+    def bgra_to_yuv_device(self, y, u, v, bgra, w, h, n=1, fmt420=True, ly=None, lu=None, lv=None, stride=None):
+        """BGRA -> planar YUV 4:2:0 / 4:2:2 (BT.601 limited range) for n packed pictures on the device; asynchronous.
+        Planes are tightly packed per picture unless strides are given (cvs_bgra_to_yuv_device)."""
+        cw, ch = (w + 1) // 2, ((h + 1) // 2 if fmt420 else h)
+        ly, lu, lv, stride = ly or w, lu or cw, lv or cw, stride or 4 * w
+        _check(self.lib.cvs_bgra_to_yuv_device(self._ctx, _ptr(y), ly, ly * h, _ptr(u), lu, lu * ch, _ptr(v), lv, lv * ch,
+                                               _ptr(bgra), stride, stride * h, w, h, n, 0 if fmt420 else 1),
+               "cvs_bgra_to_yuv_device")
+
     def synchronize(self):
         _check(self.lib.cvs_synchronize(self._ctx), "cvs_synchronize")
 

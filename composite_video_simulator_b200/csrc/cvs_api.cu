@@ -19,6 +19,7 @@
 #include "field_plan.h"
 #include "glibc_rand.h"
 #include "scanline_kernels.cuh"
+#include "yuv_convert.cuh"
 
 using namespace cvs;
 
@@ -699,6 +700,31 @@ int cvs_set_stream(cvs_ctx *ctx, void *cuda_stream) {
     ctx->own_stream = false;
     for (auto &s : ctx->slots) s.in_flight = false;
     ctx->ev_used = 0;
+    return CVS_OK;
+}
+
+int cvs_bgra_to_yuv_device(cvs_ctx *ctx, void *y, int ly, long long y_pic_stride, void *u, int lu, long long u_pic_stride,
+                           void *v, int lv, long long v_pic_stride, const void *bgra, int stride,
+                           long long bgra_pic_stride, int w, int h, int n, int format) {
+    if (!ctx || !y || !u || !v || !bgra || w <= 0 || h <= 0 || n < 0) return CVS_ERR_INVALID_ARG;
+    if (format != CVS_YUV420P && format != CVS_YUV422P) return CVS_ERR_INVALID_ARG;
+    const int cw = (w + 1) / 2;
+    if (stride < 4 * w || (stride & 3) || ((uintptr_t)bgra & 3) || ly < w || lu < cw || lv < cw) return CVS_ERR_INVALID_ARG;
+    if (n == 0) return CVS_OK;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return CVS_ERR_CUDA;
+    YuvArgs a;
+    a.bgra = (const uint8_t *)bgra; a.y = (uint8_t *)y; a.u = (uint8_t *)u; a.v = (uint8_t *)v;
+    a.sp_bgra = bgra_pic_stride; a.sp_y = y_pic_stride; a.sp_u = u_pic_stride; a.sp_v = v_pic_stride;
+    a.stride = stride; a.ly = ly; a.lu = lu; a.lv = lv;
+    a.w = w; a.h = h; a.n = n; a.v420 = format == CVS_YUV420P;
+    a.c = yuv_coef_bt601();
+    const int groups = (w + 7) / 8, crows = a.v420 ? (h + 1) / 2 : h;
+    const dim3 block(groups < 256 ? ((groups + 31) / 32) * 32 : 256);
+    const dim3 grid((groups + block.x - 1) / block.x, crows, n);
+    if (crows > 65535 || n > 65535) return CVS_ERR_CAPACITY;
+    k_bgra_to_yuv<<<grid, block, 0, ctx->stream>>>(a);
+    CVS_CUDA(cudaGetLastError());
+    ctx->launches++;
     return CVS_OK;
 }
 

@@ -148,6 +148,19 @@ int  cvs_set_bob(cvs_ctx *ctx, int enable);
 #define CVS_NOISE_FAST  1
 int  cvs_set_noise_mode(cvs_ctx *ctx, int mode);
 
+/* ---- the step after the field loop: BGRA -> the encoder's planar YUV ----------
+ * ffmpeg_ntsc hands every finished BGRA picture to sws_scale() (ffmpeg_ntsc.cpp:2266-2274; BT.601 / SMPTE170M,
+ * MPEG range, :2100-2101) before encoding.  This entry point does that conversion on the device, for n pictures,
+ * asynchronously on the context's stream: y is w x h, u and v are ceil(w/2) x ceil(h/2) (CVS_YUV420P) or
+ * ceil(w/2) x h (CVS_YUV422P); *_pic_stride are the byte distances between consecutive pictures of a plane.
+ * NOT pinned against libswscale (absent here): the arithmetic is the published 15-bit fixed-point BT.601
+ * limited-range matrix, chroma = rounded mean of the covered pixels (csrc/yuv_convert.cuh says exactly what).
+ */
+enum { CVS_YUV420P = 0, CVS_YUV422P = 1 };
+int  cvs_bgra_to_yuv_device(cvs_ctx *ctx, void *y, int ly, long long y_pic_stride, void *u, int lu, long long u_pic_stride,
+                            void *v, int lv, long long v_pic_stride, const void *bgra, int stride,
+                            long long bgra_pic_stride, int w, int h, int n, int format);
+
 /* ---- the audio step of the same program (CPU) ----------------------------------
  * composite_audio_process(int16_t *audio, unsigned samples) (ffmpeg_ntsc.cpp:901-970; called per decoded audio
  * packet from process_audio(), :1284-1290): band limiting, pre/de-emphasis, sync-pulse buzz of linear tracks, tape

@@ -1,0 +1,95 @@
+"""cvs_bgra_to_yuv_device: BGRA -> planar YUV 4:2:0 / 4:2:2, BT.601 limited range.
+NOT pinned against libswscale (absent here; include/cvs_ntsc.h says so): checked bit for bit against the same
+published fixed-point formula in numpy, and within +-1 of the real-valued BT.601 conversion."""
+import numpy as np
+import pytest
+
+import composite_video_simulator_b200 as cvs
+
+pytestmark = pytest.mark.gpu
+
+S = 15
+RY, GY, BY = int(0.299 * 219 / 255 * 2 ** S + 0.5), int(0.587 * 219 / 255 * 2 ** S + 0.5), int(0.114 * 219 / 255 * 2 ** S + 0.5)
+RU, GU, BU = int(-0.169 * 224 / 255 * 2 ** S + 0.5), int(-0.331 * 224 / 255 * 2 ** S + 0.5), int(0.500 * 224 / 255 * 2 ** S + 0.5)
+RV, GV, BV = int(0.500 * 224 / 255 * 2 ** S + 0.5), int(-0.419 * 224 / 255 * 2 ** S + 0.5), int(-0.081 * 224 / 255 * 2 ** S + 0.5)
+
+
+def formula(bgra, v420):
+    """The kernel's arithmetic restated with numpy integers (csrc/yuv_convert.cuh)."""
+    h, w = bgra.shape
+    b, g, r = [((bgra >> s) & 0xFF).astype(np.int64) for s in (0, 8, 16)]
+    y = (RY * r + GY * g + BY * b + (16 << S) + (1 << (S - 1))) >> S
+    wp, hp = w + (w & 1), h + ((h & 1) if v420 else 0)
+    pad = lambda a: np.pad(a, ((0, hp - h), (0, wp - w)), mode="edge")
+    r, g, b = pad(r), pad(g), pad(b)
+    if v420:
+        sm = lambda a: a[0::2, 0::2] + a[0::2, 1::2] + a[1::2, 0::2] + a[1::2, 1::2]
+        n, sh = 4, S + 2
+    else:
+        sm = lambda a: a[:, 0::2] + a[:, 1::2]
+        n, sh = 2, S + 1
+    sr, sg, sb = sm(r), sm(g), sm(b)
+    u = (RU * sr + GU * sg + BU * sb + ((128 * n) << S) + (1 << (sh - 1))) >> sh
+    v = (RV * sr + GV * sg + BV * sb + ((128 * n) << S) + (1 << (sh - 1))) >> sh
+    return y.astype(np.uint8), u.astype(np.uint8), v.astype(np.uint8)
+
+
+def real_bt601(bgra, v420):
+    h, w = bgra.shape
+    b, g, r = [((bgra >> s) & 0xFF).astype(np.float64) for s in (0, 8, 16)]
+    y = 16 + (0.299 * r + 0.587 * g + 0.114 * b) * 219 / 255
+    cb = 128 + (-0.168736 * r - 0.331264 * g + 0.5 * b) * 224 / 255
+    cr = 128 + (0.5 * r - 0.418688 * g - 0.081312 * b) * 224 / 255
+    wp, hp = w + (w & 1), h + ((h & 1) if v420 else 0)
+    pad = lambda a: np.pad(a, ((0, hp - h), (0, wp - w)), mode="edge")
+    if v420:
+        mean = lambda a: (lambda q: (q[0::2, 0::2] + q[0::2, 1::2] + q[1::2, 0::2] + q[1::2, 1::2]) / 4)(pad(a))
+    else:
+        mean = lambda a: (lambda q: (q[:, 0::2] + q[:, 1::2]) / 2)(pad(a))
+    return y, mean(cb), mean(cr)
+
+
+@pytest.mark.parametrize("w,h,n", [(64, 32, 1), (720, 480, 3), (1920, 1080, 2), (101, 67, 2), (8, 2, 1), (1366, 768, 1)])
+@pytest.mark.parametrize("v420", [True, False])
+def test_bgra_to_yuv_matches_the_formula(w, h, n, v420):
+    import torch
+    rng = np.random.default_rng(w * 31 + h)
+    src = rng.integers(0, 1 << 24, size=(n, h, w), dtype=np.uint32)
+    src[0, : min(h, 4)] = np.array([0x000000, 0xFFFFFF, 0xFF0000, 0x00FF00, 0x0000FF, 0x808080, 0xC0C000, 0x00C0C0],
+                                   dtype=np.uint32)[np.arange(w) % 8]
+    cw, ch = (w + 1) // 2, ((h + 1) // 2 if v420 else h)
+    d = torch.from_numpy(src.view(np.int32)).cuda()
+    y = torch.zeros((n, h, w), dtype=torch.uint8, device="cuda")
+    u = torch.zeros((n, ch, cw), dtype=torch.uint8, device="cuda")
+    v = torch.zeros((n, ch, cw), dtype=torch.uint8, device="cuda")
+    with cvs.Engine([], max_w=w, max_h=h, max_batch=1) as eng:
+        eng.bgra_to_yuv_device(y, u, v, d, w, h, n, fmt420=v420)
+        eng.synchronize()
+    for k in range(n):
+        wy, wu, wv = formula(src[k], v420)
+        assert np.array_equal(y[k].cpu().numpy(), wy), (k, "y")
+        assert np.array_equal(u[k].cpu().numpy(), wu), (k, "u")
+        assert np.array_equal(v[k].cpu().numpy(), wv), (k, "v")
+        fy, fu, fv = real_bt601(src[k], v420)
+        assert np.abs(wy - fy).max() <= 1.0 and np.abs(wu - fu).max() <= 1.0 and np.abs(wv - fv).max() <= 1.0
+    # limited range: black -> (16, 128, 128), white -> (235, 128, 128)
+    assert int(y[0, 0, 0]) == 16 and int(y[0, 0, 1]) == 235
+
+
+def test_bgra_to_yuv_padded_strides_and_errors():
+    import torch
+    w, h = 100, 50
+    src = np.random.default_rng(5).integers(0, 1 << 24, size=(h, w + 12), dtype=np.uint32)
+    d = torch.from_numpy(src.view(np.int32)).cuda()
+    y = torch.full((h, w + 7), 7, dtype=torch.uint8, device="cuda")
+    u = torch.full((h // 2, w // 2 + 3), 7, dtype=torch.uint8, device="cuda")
+    v = torch.full((h // 2, w // 2 + 5), 7, dtype=torch.uint8, device="cuda")
+    with cvs.Engine([], max_w=w, max_h=h, max_batch=1) as eng:
+        eng.bgra_to_yuv_device(y, u, v, d, w, h, 1, fmt420=True, ly=w + 7, lu=w // 2 + 3, lv=w // 2 + 5, stride=4 * (w + 12))
+        eng.synchronize()
+        wy, wu, wv = formula(src[:, :w], True)
+        assert np.array_equal(y.cpu().numpy()[:, :w], wy) and (y.cpu().numpy()[:, w:] == 7).all()
+        assert np.array_equal(u.cpu().numpy()[:, : w // 2], wu) and (u.cpu().numpy()[:, w // 2:] == 7).all()
+        assert np.array_equal(v.cpu().numpy()[:, : w // 2], wv) and (v.cpu().numpy()[:, w // 2:] == 7).all()
+        with pytest.raises(cvs.CvsError):
+            eng.bgra_to_yuv_device(y, u, v, d, w, h, 1, fmt420=True, ly=w - 1)      # luma rows shorter than w
