@@ -718,12 +718,11 @@ int cvs_bgra_to_yuv_device(cvs_ctx *ctx, void *y, int ly, long long y_pic_stride
     a.stride = stride; a.ly = ly; a.lu = lu; a.lv = lv;
     a.w = w; a.h = h; a.n = n; a.v420 = format == CVS_YUV420P;
     a.c = yuv_coef_bt601();
-    a.groups = (w + 7) / 8;
-    a.crows = a.v420 ? (h + 1) / 2 : h;
-    a.total = (long long)a.groups * a.crows * n;
-    const long long blocks = (a.total + 255) / 256;
-    if (blocks > 0x7FFFFFFFLL) return CVS_ERR_CAPACITY;
-    k_bgra_to_yuv<<<(unsigned)blocks, 256, 0, ctx->stream>>>(a);
+    const int groups = (w + 7) / 8, crows = a.v420 ? (h + 1) / 2 : h;
+    const dim3 block(groups < 256 ? ((groups + 31) / 32) * 32 : 256);
+    const dim3 grid((groups + block.x - 1) / block.x, crows, n);
+    if (crows > 65535 || n > 65535) return CVS_ERR_CAPACITY;
+    k_bgra_to_yuv<<<grid, block, 0, ctx->stream>>>(a);
     CVS_CUDA(cudaGetLastError());
     ctx->launches++;
     return CVS_OK;

@@ -33,21 +33,16 @@ struct YuvArgs {
     long long sp_bgra, sp_y, sp_u, sp_v;     // picture strides (bytes) of a batch
     int stride, ly, lu, lv;                  // row strides (bytes)
     int w, h, n, v420;                       // v420: chroma is subsampled vertically too
-    int groups, crows;                       // 8-pixel groups per row, chroma rows per picture
-    long long total;                         // groups * crows * n work items
     YuvCoef c;
 };
 
 // one thread = 8 pixels x (2 rows for 4:2:0 / 1 row for 4:2:2): 32-byte loads, 8-byte luma stores, 4-byte chroma stores
 __global__ void __launch_bounds__(256) k_bgra_to_yuv(const __grid_constant__ YuvArgs a) {
-    // work items are numbered (picture, chroma row, group) so that no thread of a block idles at a row end
-    const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (item >= a.total) return;
-    const int gx = (int)(item % a.groups);                         // group of 8 pixels
-    const long long rest = item / a.groups;
-    const int ry = (int)(rest % a.crows);                          // chroma row
-    const int k = (int)(rest / a.crows);
+    const int gx = blockIdx.x * blockDim.x + threadIdx.x;          // group of 8 pixels
+    const int ry = blockIdx.y;                                     // chroma row
+    const int k = blockIdx.z;
     const int x0 = gx * 8;
+    if (x0 >= a.w) return;
     const int rows = a.v420 ? 2 : 1;
     const int y0 = ry * rows;
     const uint8_t *src = a.bgra + (long long)k * a.sp_bgra;
@@ -58,7 +53,7 @@ __global__ void __launch_bounds__(256) k_bgra_to_yuv(const __grid_constant__ Yuv
         const uint32_t *row = reinterpret_cast<const uint32_t *>(src + (long long)yy * a.stride);
         uint32_t px[8];
         if (full && ((reinterpret_cast<uintptr_t>(row + x0) & 15) == 0)) {
-            const uint4 p0 = __ldg(reinterpret_cast<const uint4 *>(row + x0)), p1 = __ldg(reinterpret_cast<const uint4 *>(row + x0 + 4));
+            const uint4 p0 = *reinterpret_cast<const uint4 *>(row + x0), p1 = *reinterpret_cast<const uint4 *>(row + x0 + 4);
             px[0] = p0.x; px[1] = p0.y; px[2] = p0.z; px[3] = p0.w; px[4] = p1.x; px[5] = p1.y; px[6] = p1.z; px[7] = p1.w;
         } else {
 #pragma unroll
