@@ -60,6 +60,24 @@ def _ptr(a):
     raise TypeError("expected a numpy array, a torch tensor or an address")
 
 
+def _host_pictures(dst, src, ndim, dst_stride=None, src_stride=None):
+    """Validate a pair of HOST picture arrays before their addresses cross the C ABI: the library trusts the
+    geometry it is given, so a short, narrow or non-contiguous array would let its copies run outside the buffer."""
+    for name, a in (("dst", dst), ("src", src)):
+        if not isinstance(a, np.ndarray):
+            raise TypeError("%s must be a numpy array in host memory (use composite_fields_device for device "
+                            "pictures), got %s" % (name, type(a).__name__))
+        if a.ndim != ndim or a.dtype.itemsize != 4 or a.dtype.kind not in "ui":
+            raise ValueError("%s must be a %d-dimensional array of 32-bit BGRA pixels, got %s %s"
+                             % (name, ndim, a.dtype, a.shape))
+        if a.strides[-1] != 4 or any(st <= 0 for st in a.strides):
+            raise ValueError("%s rows must be contiguous (pixel stride 4 bytes), got strides %s" % (name, a.strides))
+    if not dst.flags.writeable:
+        raise ValueError("dst is read-only")
+    if dst_stride is None and src_stride is None and dst.shape != src.shape:
+        raise ValueError("dst %s and src %s must have the same shape" % (dst.shape, src.shape))
+
+
 class Audio:
     """composite_audio_process() of ffmpeg_ntsc (ffmpeg_ntsc.cpp:901-970) on the CPU: cvs_audio_* of the C ABI.
     `process(pcm, rng_pos)` filters interleaved int16 samples [n, channels] in place and returns the rand() stream
@@ -161,6 +179,7 @@ class Engine:
     def composite_layer(self, dst, src, field, fieldno, src_interlaced=False, src_top_field_first=False,
                         dst_stride=None, src_stride=None):
         """ffmpeg_ntsc.cpp:2229: dst/src are uint32[h, w] BGRA host pictures; writes rows y = field (mod 2)."""
+        _host_pictures(dst, src, 2, dst_stride, src_stride)
         h, w = src.shape[:2]
         _check(self.lib.cvs_composite_layer(self._ctx, _ptr(dst), dst_stride or dst.strides[0], _ptr(src),
                                             src_stride or src.strides[0], w, h, int(src_interlaced),
@@ -169,6 +188,7 @@ class Engine:
     # -- throughput forms -----------------------------------------------------------------------------
     def composite_fields_host(self, dst, src, first_fieldno, src_interlaced=False, src_top_field_first=False):
         """dst/src: uint32[n, h, w] host arrays (pinned for full PCIe speed)."""
+        _host_pictures(dst, src, 3)
         n, h, w = src.shape
         _check(self.lib.cvs_composite_fields_host(self._ctx, _ptr(dst), dst.strides[0], dst.strides[1], _ptr(src),
                                                   src.strides[0], src.strides[1], w, h, int(src_interlaced),
@@ -178,6 +198,7 @@ class Engine:
     def composite_fields_host_async(self, dst, src, first_fieldno, src_interlaced=False, src_top_field_first=False):
         """As composite_fields_host but only queues the work; dst is complete after synchronize().
         Consecutive calls overlap; do not reuse dst/src before the synchronize (use two buffer sets)."""
+        _host_pictures(dst, src, 3)
         n, h, w = src.shape
         _check(self.lib.cvs_composite_fields_host_async(self._ctx, _ptr(dst), dst.strides[0], dst.strides[1], _ptr(src),
                                                         src.strides[0], src.strides[1], w, h, int(src_interlaced),

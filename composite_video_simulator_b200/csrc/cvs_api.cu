@@ -7,6 +7,7 @@
 // usable every compute entry point fails with CVS_ERR_CUDA.
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -88,7 +89,7 @@ struct cvs_ctx {
     int32_t *h_status = nullptr;               // pinned
     float *d_lut_f = nullptr;
     double *d_lut_d = nullptr;
-    size_t lut_cap = 0;
+    size_t lut_cap_f = 0, lut_cap_d = 0;       // one capacity per table: they are separate allocations
     bool lut_dirty = true;
     // device pictures for the host-pointer entry points
     // two sets, alternating per call, so an asynchronous call can upload while the previous one drains
@@ -201,6 +202,9 @@ cudaError_t occupancy_variant(const Variant &v, int *n) {
 template <typename R> R *&lut_ptr(cvs_ctx *c);
 template <> float *&lut_ptr<float>(cvs_ctx *c) { return c->d_lut_f; }
 template <> double *&lut_ptr<double>(cvs_ctx *c) { return c->d_lut_d; }
+template <typename R> size_t &lut_cap(cvs_ctx *c);
+template <> size_t &lut_cap<float>(cvs_ctx *c) { return c->lut_cap_f; }
+template <> size_t &lut_cap<double>(cvs_ctx *c) { return c->lut_cap_d; }
 
 template <typename R>
 int launch_batch(cvs_ctx *c, const Staging &sl, const Variant &v, int w, int h, int nfields, int max_nl, int total_rows,
@@ -208,10 +212,10 @@ int launch_batch(cvs_ctx *c, const Staging &sl, const Variant &v, int w, int h, 
     LaunchArgs<R> a;
     std::vector<R> lut;
     make_kconst<R>(c->p, w, h, v.outfull, a.K, lut);
-    if (lut.size() > c->lut_cap || !lut_ptr<R>(c)) {
-        if (lut_ptr<R>(c)) { CVS_CUDA(cudaStreamSynchronize(c->stream)); cudaFree(lut_ptr<R>(c)); lut_ptr<R>(c) = nullptr; }
+    if (lut.size() > lut_cap<R>(c) || !lut_ptr<R>(c)) {
+        if (lut_ptr<R>(c)) { CVS_CUDA(cudaStreamSynchronize(c->stream)); cudaFree(lut_ptr<R>(c)); lut_ptr<R>(c) = nullptr; lut_cap<R>(c) = 0; }
         CVS_CUDA(dev_alloc(&lut_ptr<R>(c), lut.size() + 2));
-        c->lut_cap = lut.size() + 2;
+        lut_cap<R>(c) = lut.size() + 2;
         c->lut_dirty = true;
     }
     if (c->lut_dirty) {
@@ -312,7 +316,7 @@ int run_device(cvs_ctx *c, uint8_t *dst, size_t dst_pic_stride, int dst_stride, 
         fd.hs_scratch = c->d_scratch + (size_t)k * c->hs_max * (size_t)c->max_w;
         fd.hs_shift = sl.d_hsshift + (size_t)k * c->hs_max;
     }
-    bool capacity_error = false;
+    std::atomic<bool> capacity_error(false);
     const RandCursor batch_start = c->cur;
     RandCursor batch_end = c->cur;
     auto plan_range = [&](int k0, int k1) {
@@ -339,22 +343,40 @@ int run_device(cvs_ctx *c, uint8_t *dst, size_t dst_pic_stride, int dst_stride, 
     if (nthreads <= 1) {
         plan_range(0, n);
     } else {
+        // a thread that cannot be started (std::system_error must not cross the C ABI) leaves its range, and
+        // every later one, to this thread
         std::vector<std::thread> pool;
         const int per = (n + nthreads - 1) / nthreads;
-        for (int t = 1; t < nthreads; t++)
-            if (t * per < n) pool.emplace_back(plan_range, t * per, (t + 1) * per < n ? (t + 1) * per : n);
+        int done_to = per < n ? per : n;               // ranges [done_to, n) still need a planner
+        try {
+            pool.reserve((size_t)nthreads);
+            for (int t = 1; t < nthreads && t * per < n; t++) {
+                const int k1 = (t + 1) * per < n ? (t + 1) * per : n;
+                pool.emplace_back(plan_range, t * per, k1);
+                done_to = k1;
+            }
+        } catch (...) {
+        }
         plan_range(0, per < n ? per : n);
         for (auto &th : pool) th.join();
+        const int started_to = done_to;
+        for (int k0 = started_to; k0 < n; k0 += per) plan_range(k0, k0 + per < n ? k0 + per : n);
     }
+    // From here on the call either completes or leaves the rand() position where it was (the header's
+    // contract: an invalid or failed call does not consume draws).
+    struct CursorGuard {
+        cvs_ctx *c; const RandCursor &start; bool armed;
+        ~CursorGuard() { if (armed) c->cur = start; }
+    } guard{c, batch_start, true};
     c->cur = batch_end;                                // the stream position after the batch
-    if (capacity_error) return CVS_ERR_CAPACITY;
+    if (capacity_error.load()) return CVS_ERR_CAPACITY;
     for (int k = 0; k < n; k++)
         for (int i = 0; i < jobs[(size_t)k].hs_count; i++) {
             sl.h_items[nitems].field_idx = k;
             sl.h_items[nitems].slot = i;
             nitems++;
         }
-    if (max_nl == 0) return CVS_OK;
+    if (max_nl == 0) { guard.armed = false; return CVS_OK; }
 
     // tables go up on their own stream, behind the kernels that last read this slot's device copies,
     // and the compute stream picks them up through an event: the upload overlaps the previous batch
@@ -378,6 +400,7 @@ int run_device(cvs_ctx *c, uint8_t *dst, size_t dst_pic_stride, int dst_stride, 
         : launch_batch<float>(c, sl, v, w, h, n, max_nl, total_rows, packed, nitems, src_stride, dst_stride, opposite, vec_src, vec_dst);
     if (rc != CVS_OK) return rc;
     CVS_CUDA(cudaEventRecord(sl.kernel_done, c->stream));
+    guard.armed = false;
     return CVS_OK;
 }
 
@@ -447,6 +470,7 @@ int run_host(cvs_ctx *c, uint8_t *dst, size_t dst_pic_stride, int dst_stride, co
         c->ev_k.push_back(b);
     }
     const int opposite = interlaced ? (tff ? 1 : 0) : 0;
+    const RandCursor call_start = c->cur;
     auto field_of = [&](int k) {
         const unsigned long long fieldno = first_fieldno + (unsigned long long)k;
         return explicit_field >= 0 ? explicit_field : (int)((fieldno & 1) ^ 1);
@@ -473,7 +497,11 @@ int run_host(cvs_ctx *c, uint8_t *dst, size_t dst_pic_stride, int dst_stride, co
         CVS_CUDA(cudaStreamWaitEvent(c->stream, c->ev_in[ci], 0));
         int rc = run_device(c, d_dst + (size_t)k0 * dpic, dpic, dstride, d_src + (size_t)k0 * dpic, dpic, dstride, w, h,
                             interlaced, tff, k1 - k0, first_fieldno + (unsigned long long)k0, explicit_field);
-        if (rc != CVS_OK) { cudaStreamSynchronize(c->s_in); cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->s_out); return rc; }
+        if (rc != CVS_OK) {        // a failed call consumes no draws, whichever chunk failed
+            cudaStreamSynchronize(c->s_in); cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->s_out);
+            c->cur = call_start;
+            return rc;
+        }
         CVS_CUDA(cudaEventRecord(c->ev_k[ci], c->stream));
         CVS_CUDA(cudaStreamWaitEvent(c->s_out, c->ev_k[ci], 0));
         for (int k = k0; k < k1; k++) {                       // download, stream s_out

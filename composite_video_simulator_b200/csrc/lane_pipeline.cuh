@@ -1131,14 +1131,16 @@ CVS_HD int line_steps(int w) { return (w + kT - 1) / kT + (VHS ? 2 + 2 * kLB + l
 // Block indices at step s: kB = s-1-kLB (first demod, VHS filters), kD = kB-LD (delayed chroma, C2),
 // kC = kD-kLB (second demod).  Line start: the first block of each demodulation (index 0) has the
 // carrier-period condition g >= 0, so kB >= 1 and, with VHS, kC >= 1.  Line end, for step s: A1 reads
-// B(s) whole: kT(s+1) <= w;  A2 builds B(s-1) and must stay clear of the raw-chroma tail (x+4 >= w):
+// B(s) whole and the loop prefetches B(s+1): kT(s+2) <= w;  A2 builds B(s-1) and must stay clear of the raw-chroma tail (x+4 >= w):
 // kT s + 3 < w;  the VHS chroma stash starts at x >= w-CD for x in B(kB): kT(s-kLB) - 1 < w - CD.
 // Everything downstream is older and weaker.
 template <bool VHS, int CD>
 CVS_HD void interior_steps(int w, int &s_lo, int &s_hi) {
     constexpr int LD = lag_blocks(CD);
     s_lo = VHS ? 2 + 2 * kLB + LD : 2 + kLB;
-    int hi = (w - kT) / kT + 1;                          // kT(s+1) <= w
+    // the interior loop prefetches B(s+1) with an unguarded load, so B(s+1) must lie inside the row as
+    // well: kT(s+2) <= w (a row that ends the picture ends the caller's buffer)
+    int hi = w / kT - 1;
     const int a2 = (w - 3 + kT - 1) / kT;                // kT s < w - 3
     if (a2 < hi) hi = a2;
     if (VHS) {

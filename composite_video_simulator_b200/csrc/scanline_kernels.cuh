@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(kNT, (sizeof(R) == 4 ? CVS_MIN_CTAS : 1)) k_fi
 #pragma unroll 1
                 for (; s + 1 < s_hi; s += 2) {
                     uint32_t pxn[kT];
-                    load_block_fast(srow, s + 1, vec_src, pxn);      // interior: always in range
+                    load_block_fast(srow, s + 1, vec_src, pxn);      // in range: interior_steps() keeps kT(s+2) <= w
                     St::template step<MODE_FAST_EVEN>(K, rc, ln, s, px, srow, vec_src, hsrow, warp_hs, hsring, warp_inl, valid, drow, drow_bob, vec_dst);
                     load_block_fast(srow, s + 2, vec_src, px);
                     St::template step<MODE_FAST_EVEN>(K, rc, ln, s + 1, pxn, srow, vec_src, hsrow, warp_hs, hsring, warp_inl, valid, drow, drow_bob, vec_dst);
@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(kNT, (sizeof(R) == 4 ? CVS_MIN_CTAS : 1)) k_fi
 #pragma unroll 1
                 for (; s < s_hi; s++) {
                     uint32_t pxn[kT];
-                    load_block_fast(srow, s + 1, vec_src, pxn);      // interior: always in range
+                    load_block_fast(srow, s + 1, vec_src, pxn);      // in range: interior_steps() keeps kT(s+2) <= w
                     St::template step<MODE_FAST_EVEN>(K, rc, ln, s, px, srow, vec_src, hsrow, warp_hs, hsring, warp_inl, valid, drow, drow_bob, vec_dst);
 #pragma unroll
                     for (int j = 0; j < kT; j++) px[j] = pxn[j];

@@ -146,6 +146,11 @@ int run_device(cvs422_ctx *c, uint8_t *y, uint8_t *u, uint8_t *v, long long psy,
     if (!c->p.enable_composite_emulation) {                   // the reference skips the call (:1789)
         return CVS_OK;
     }
+    // a call that fails leaves the rand() position where it was (include/cvs_yuv422.h)
+    struct CursorGuard {
+        cvs422_ctx *c; RandCursor start; bool armed;
+        ~CursorGuard() { if (armed) c->cur = start; }
+    } guard{c, c->cur, true};
     Launch422 a;
     std::vector<double> lut;
     int rc = make_k422(c->p, w, h, a.K, a.dv, lut);
@@ -255,6 +260,7 @@ int run_device(cvs422_ctx *c, uint8_t *y, uint8_t *u, uint8_t *v, long long psy,
     if (e1) CVS_CUDA(cudaEventRecord(e1, c->stream));
     CVS_CUDA(cudaEventRecord(sl.kernel_done, c->stream));
     c->launches += 1 + ((a.packed ? a.total_warps > 1 : wpf > 1) ? 1 : 0) + (nitems > 0 ? 1 : 0);
+    guard.armed = false;
     return CVS_OK;
 }
 

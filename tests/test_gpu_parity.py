@@ -26,6 +26,19 @@ CASES = [
     (1920, 1080, 2, ["-vhs", "-vhs-speed", "ep"]),          # BASELINE config 3
     (3840, 2160, 2, []),                                    # BASELINE config 4: composite only, 4K
     (3840, 2160, 1, ["-vhs", "-vhs-speed", "lp"]),          # head-switch shift beyond the in-kernel ring: pre-pass
+    # every switch the oracle sweep (tests/test_oracle_vs_ref.py) pins against the reference's code, on the GPU:
+    (720, 480, 3, ["-vhs", "-chroma-dropout", "30000"]),                       # a16: ~30 % of the rows lose chroma (:1891-1901)
+    (720, 480, 4, ["-vhs", "-comp-phase", "270", "-comp-phase-offset", "1"]),  # line phase -(y>>1) (:1473-1480)
+    (720, 480, 3, ["-vhs", "-comp-phase", "0"]),
+    (720, 480, 3, ["-comp-phase", "90", "-comp-phase-offset", "3"]),
+    (720, 480, 2, ["-vhs", "-nocolor-subcarrier"]),                            # :1715
+    (720, 480, 2, ["-vhs", "-in-composite-lowpass", "0", "-out-composite-lowpass", "0"]),
+    (720, 480, 3, ["-vhs", "-vhs-chroma-vblend", "0"]),                        # :1843
+    (720, 480, 2, ["-vhs", "-vhs-svideo", "1", "-vhs-chroma-vblend", "0"]),
+    (720, 480, 2, ["-comp-catv3", "-chroma-noise", "5"]),                      # chroma noise without VHS (:1718)
+    (720, 576, 2, ["-tvstd", "pal", "-vhs"]),                                  # PAL: no vertical blend, 312.5-line head switch
+    (33, 21, 3, ["-vhs", "-vhs-speed", "ep"]),                                 # a row shorter than the pipeline depth
+    (1024, 512, 2, ["-vhs"]),                                                  # 2 MiB pictures: last row ends the mapping
 ]
 
 
@@ -346,3 +359,112 @@ def test_preferred_batch_is_wave_aligned():
         assert ok, b
         assert eng.preferred_batch(1920, 1080, 1) == 1      # less than one wave: unchanged
         assert eng.preferred_batch(1920, 1080, 10**6) <= 320  # clamped to the context's capacity
+
+
+# SURVEY.md App. D known answers (FNV-1a-64 of the reused dst picture after n fields of 75 % colour bars, default
+# seed), reproduced by the CUDA path in the fp64 validation mode: the same hashes the reference's own code gives.
+KAT = [
+    (720, 480, "sp", 4, 0xadc46d5e6368519b),
+    (720, 480, "sp", 60, 0x6efec46688da8257),        # BASELINE config 1
+    (720, 480, "comp", 60, 0xdddc5e14c4d9b4a9),
+    (1920, 1080, "sp", 32, 0x69cd6d98c07172ab),
+    (1920, 1080, "ep", 16, 0x34b7815ed20c013d),
+    (3840, 2160, "comp", 8, 0x950d9b8328d39f81),
+]
+KAT_MODES = {"sp": ["-vhs", "-vhs-speed", "sp"], "ep": ["-vhs", "-vhs-speed", "ep"], "comp": []}
+
+
+@pytest.mark.parametrize("w,h,mode,n,want", KAT)
+def test_known_answer_hashes_fp64(w, h, mode, n, want):
+    bars = helpers.bars_frame(w, h)
+    dst = np.zeros((h, w), dtype=np.uint32)
+    with cvs.Engine(KAT_MODES[mode], max_w=w, max_h=h, max_batch=1) as eng:
+        eng.set_precision(True)
+        for k in range(n):
+            eng.composite_layer(dst, bars, (k & 1) ^ 1, k)
+        assert eng.rng_tell() == sum(cvs.draws_per_field(eng.params, w, h, (k & 1) ^ 1) for k in range(n))
+    assert helpers.fnv1a64(dst) == want
+
+
+def test_config1_480p_vhs_60_colour_bar_fields_fp32(oracle):
+    """BASELINE config 1 in production arithmetic: 60 colour-bar fields at 720x480 `-vhs`, within +-1 LSB of the
+    CPU path, as one batch and with the fields in a reused picture as the reference's loop has them."""
+    w, h, n = 720, 480, 60
+    p = helpers.params("-vhs")
+    bars = helpers.bars_frame(w, h)
+    want, g = helpers.run_oracle(oracle, p, lambda k: bars, n, w, h)
+    assert helpers.fnv1a64(want) == 0x6efec46688da8257
+    src = np.ascontiguousarray(np.broadcast_to(bars, (n, h, w)))
+    got = np.zeros((n, h, w), dtype=np.uint32)
+    with cvs.Engine(params=p, max_w=w, max_h=h, max_batch=n) as eng:
+        eng.composite_fields_host(got, src, 0)
+        assert eng.rng_tell() == g.pos
+    # the reused picture after 60 calls = odd rows of field 58 (field parity 1) and even rows of field 59
+    last = np.zeros((h, w), dtype=np.uint32)
+    last[1::2] = got[58][1::2]
+    last[0::2] = got[59][0::2]
+    mx, nd, n2 = helpers.channel_diff(want, last)
+    assert mx <= 1 and n2 == 0 and nd <= 0.005 * want.size * 4, (mx, nd, n2)
+
+
+def test_failed_call_consumes_no_draws():
+    """include/cvs_ntsc.h: a call that fails leaves the rand() position untouched (the reference returns before its
+    first draw, ffmpeg_ntsc.cpp:1578-1583)."""
+    w, h = 64, 480
+    with cvs.Engine(["-vhs"], max_w=w, max_h=h, max_batch=2) as eng:
+        eng.rng_seek(12345)
+        src = np.stack([helpers.stream_frame(w, h, k) for k in range(2)])
+        dst = np.zeros_like(src)
+        with pytest.raises(ValueError):
+            eng.composite_fields_host(dst[:, :, : w - 1], src, 0)              # shapes differ: rejected before the ABI
+        assert eng.rng_tell() == 12345
+        with pytest.raises(cvs.CvsError) as e:
+            eng.composite_layer(dst[0], src[0], 2, 0)                          # field > 1
+        assert e.value.status == -1 and eng.rng_tell() == 12345
+        eng.composite_fields_host(dst, src, 0)
+        assert eng.rng_tell() == 12345 + sum(cvs.draws_per_field(eng.params, w, h, f) for f in (1, 0))
+
+
+def test_phase_table_survives_precision_switches(oracle):
+    """The {sin, cos} table of the chroma phase noise has one device copy per precision; growing one must not let
+    the other be overrun (a larger -chroma-phase-noise after a precision round trip)."""
+    w, h = 160, 120
+    frames = lambda k: helpers.stream_frame(w, h, k)
+    with cvs.Engine(["-vhs", "-chroma-phase-noise", "2"], max_w=w, max_h=h, max_batch=1) as eng:
+        got = np.zeros((h, w), dtype=np.uint32)
+        eng.composite_layer(got, frames(0), 1, 0)                 # float table, 5 states
+        p = helpers.params("-vhs", "-chroma-phase-noise", "40")
+        eng.set_params(p)
+        eng.set_precision(True)
+        eng.rng_seek(0)
+        eng.composite_layer(got, frames(0), 1, 0)                 # double table, 81 states
+        eng.set_precision(False)
+        eng.rng_seek(0)
+        got = np.zeros((h, w), dtype=np.uint32)
+        for k in range(3):
+            eng.composite_layer(got, frames(k), (k & 1) ^ 1, k)   # float again, 81 states
+    want, _ = helpers.run_oracle(oracle, p, frames, 3, w, h)
+    mx, nd, n2 = helpers.channel_diff(want, got)
+    assert mx <= 1 and n2 == 0, (mx, nd, n2)
+
+
+def test_last_row_of_an_exactly_sized_device_buffer():
+    """A field whose last row is the last row of the allocation (field 1, even height): the kernel must not read
+    past the end of the row (run under compute-sanitizer by scripts/sanitizer_probe.py; here: it runs and equals
+    the same picture processed inside a larger allocation)."""
+    import torch
+    w, h = 1024, 512                                  # 2 MiB per picture
+    p = helpers.params("-vhs")
+    pic = torch.from_numpy(helpers.stream_frame(w, h, 3).view(np.int32))
+    exact = pic.cuda()
+    big = torch.zeros((2, h, w), dtype=torch.int32, device="cuda")
+    big[0] = exact
+    outs = []
+    with cvs.Engine(params=p, max_w=w, max_h=h, max_batch=1) as eng:
+        for src in (exact, big):
+            dst = torch.zeros((h, w), dtype=torch.int32, device="cuda")
+            eng.rng_seek(0)
+            eng.composite_fields_device(dst, src, 1, h, w, 0)     # fieldno 0 -> field 1: rows 1, 3, .. h-1
+            eng.synchronize()
+            outs.append(dst.cpu())
+    assert torch.equal(outs[0], outs[1])

@@ -11,9 +11,12 @@ KAT = [
     (720, 480, "sp", 4, 0xadc46d5e6368519b),
     (720, 480, "sp", 8, 0x1f6f1de0e08b3970),
     (720, 480, "sp", 60, 0x6efec46688da8257),
+    (720, 480, "sp", 120, 0x8ff744cad3018bd9),
     (720, 480, "comp", 60, 0xdddc5e14c4d9b4a9),
     (1920, 1080, "sp", 16, 0x6dbd7301d1debb9f),
+    (1920, 1080, "sp", 32, 0x69cd6d98c07172ab),
     (1920, 1080, "ep", 16, 0x34b7815ed20c013d),
+    (3840, 2160, "comp", 8, 0x950d9b8328d39f81),
 ]
 MODES = {"sp": ["-vhs", "-vhs-speed", "sp"], "ep": ["-vhs", "-vhs-speed", "ep"], "comp": []}
 
