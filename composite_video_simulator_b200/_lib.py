@@ -54,6 +54,8 @@ def load():
         "cvs_composite_fields_host_async": (C.c_int, [vp, vp, C.c_size_t, C.c_int, vp, C.c_size_t, C.c_int, C.c_int,
                                                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_ulonglong]),
         "cvs_synchronize": (C.c_int, [vp]),
+        "cvs_alloc_host": (C.c_int, [vp, C.POINTER(vp), C.c_size_t]),
+        "cvs_free_host": (C.c_int, [vp, vp]),
         "cvs_rng_seek": (C.c_int, [vp, C.c_ulonglong]),
         "cvs_rng_tell": (C.c_int, [vp, C.POINTER(C.c_ulonglong)]),
         "cvs_kernel_launches": (C.c_ulonglong, [vp]),
@@ -75,6 +77,6 @@ EXPORTED_SYMBOLS = [
     "cvs_set_precision", "cvs_set_bob", "cvs_set_noise_mode", "cvs_audio_channels", "cvs_audio_create", "cvs_audio_process",
     "cvs_audio_destroy", "cvs_bgra_to_yuv_device", "cvs_preferred_batch", "cvs_composite_layer", "cvs_composite_fields_device", "cvs_composite_fields_host",
     "cvs_composite_fields_host_async",
-    "cvs_synchronize", "cvs_rng_seek", "cvs_rng_tell", "cvs_kernel_launches", "cvs_kernel_time_reset",
+    "cvs_synchronize", "cvs_alloc_host", "cvs_free_host", "cvs_rng_seek", "cvs_rng_tell", "cvs_kernel_launches", "cvs_kernel_time_reset",
     "cvs_kernel_time_query", "cvs_set_stream",
 ]

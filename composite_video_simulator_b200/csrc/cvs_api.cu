@@ -71,6 +71,7 @@ struct cvs_ctx {
     int host_chunk = kHostChunkDefault;
     int bob = 0;                               // fused line doubling (cvs_set_bob)
     int plan_threads = 4;                      // host threads that build the per-row side tables of a batch
+    int warm_px = kWarmPx;                     // noise warm-up length (CVS_WARM_PX: tests force the second-chance path)
     int packed_rows = 1;                       // cut the batch's rows into warps across field boundaries (CVS_PACKED_ROWS=0: per field)
     cudaStream_t stream = nullptr;
     bool own_stream = true;
@@ -152,7 +153,7 @@ int get_plan(cvs_ctx *c, int w, int h, unsigned field, DevPlan **out) {
     std::unique_ptr<DevPlan> pl(new (std::nothrow) DevPlan());
     if (!pl) return CVS_ERR_NOMEM;
     pl->w = w; pl->h = h; pl->field = field;
-    build_geom_plan(c->p, w, h, field, pl->g);
+    build_geom_plan(c->p, w, h, field, pl->g, c->warm_px);
     const size_t words = pl->g.seek.size() > 0 ? pl->g.seek.size() : 1;
     CVS_CUDA(dev_alloc(&pl->d_seek, words));
     if (!pl->g.seek.empty())
@@ -240,6 +241,7 @@ int launch_batch(cvs_ctx *c, const Staging &sl, const Variant &v, int w, int h, 
     a.vec_src = vec_src;
     a.vec_dst = vec_dst;
     a.bob = c->bob;
+    a.warm_px = c->warm_px;
     a.status = c->d_status;
     if (nitems > 0) {
         CVS_CUDA(launch_headswitch<R>(a, sl.d_items, nitems, c->stream));
@@ -559,6 +561,10 @@ int cvs_create(cvs_ctx **out, const cvs_params *p, int device, int max_w, int ma
         }
     }
     if (const char *e = std::getenv("CVS_PACKED_ROWS")) c->packed_rows = std::atoi(e) != 0;   // experiments / tests
+    if (const char *e = std::getenv("CVS_WARM_PX")) {           // tests: a short warm-up makes the first attempt fail
+        const int v = std::atoi(e);
+        if (v >= 0 && v <= kWarmPx) c->warm_px = v;
+    }
     c->hs_max = head_switch_rows_bound(max_w);
     if (c->hs_max > c->nl_max) c->hs_max = c->nl_max;
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
@@ -703,6 +709,23 @@ int cvs_synchronize(cvs_ctx *ctx) {
     const int rc = check_status(ctx);          // synchronises the compute stream
     CVS_CUDA(cudaStreamSynchronize(ctx->s_out));
     return rc;
+}
+
+int cvs_alloc_host(cvs_ctx *ctx, void **out, size_t bytes) {
+    if (!ctx || !out || bytes == 0) return CVS_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return CVS_ERR_CUDA;
+    const cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) { *out = nullptr; return e == cudaErrorMemoryAllocation ? CVS_ERR_NOMEM : CVS_ERR_CUDA; }
+    return CVS_OK;
+}
+
+int cvs_free_host(cvs_ctx *ctx, void *p) {
+    if (!ctx) return CVS_ERR_INVALID_ARG;
+    if (!p) return CVS_OK;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return CVS_ERR_CUDA;
+    CVS_CUDA(cudaFreeHost(p));
+    return CVS_OK;
 }
 
 int cvs_rng_seek(cvs_ctx *ctx, unsigned long long draws_consumed) {

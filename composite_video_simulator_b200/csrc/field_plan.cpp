@@ -58,6 +58,19 @@ void make_kconst(const cvs_params &p, int w, int h, bool outfull, KConst<R> &K, 
     K.a_ch.y = K.a_ch.x; K.b_ch.y = K.b_ch.x; K.c_ch.y = K.c_ch.x;
     set(K.a_sharp, K.b_sharp, K.c_sharp, pole_alpha(luma_cut * 4));    // :1874
     K.sharpen = (R)p.vhs_out_sharpen;
+    {   // merged fp32 forms (lane_pipeline.cuh, Num<float>::vhs_luma / rgb2yiq2); products formed in double
+        const double al = pole_alpha(luma_cut), as = pole_alpha(luma_cut * 4), g = p.vhs_out_sharpen;
+        K.k_boost_r = (R)(2.6 * al * al * al);
+        K.k_boost_p = (R)(-1.6 * al * al * al * al);
+        K.k_sharp_y = (R)(1.0 + 2.0 * g);
+        K.k_sharp_t = (R)(-2.0 * g * as * as * as);
+        // I = -.27 (b - dY) + .74 (r - dY), Q = .41 (b - dY) + .48 (r - dY), dY = .30 r + .59 g + .11 b   (:1377-1382)
+        const double ky[3] = {0.30, 0.59, 0.11};
+        const double ci[3] = {0.74 - 0.47 * ky[0], -0.47 * ky[1], -0.27 - 0.47 * ky[2]};
+        const double cq[3] = {0.48 - 0.89 * ky[0], -0.89 * ky[1], 0.41 - 0.89 * ky[2]};
+        K.k_iq_r.x = (R)(256 * ci[0]); K.k_iq_g.x = (R)(256 * ci[1]); K.k_iq_b.x = (R)(256 * ci[2]);
+        K.k_iq_r.y = (R)(256 * cq[0]); K.k_iq_g.y = (R)(256 * cq[1]); K.k_iq_b.y = (R)(256 * cq[2]);
+    }
     if (outfull) {                                          // composite_lowpass, :1442
         set(K.a_out.x, K.b_out.x, K.c_out.x, pole_alpha(1300000));
         set(K.a_out.y, K.b_out.y, K.c_out.y, pole_alpha(600000));
@@ -106,7 +119,7 @@ void make_kconst(const cvs_params &p, int w, int h, bool outfull, KConst<R> &K, 
 template void make_kconst<float>(const cvs_params &, int, int, bool, KConst<float> &, std::vector<float> &);
 template void make_kconst<double>(const cvs_params &, int, int, bool, KConst<double> &, std::vector<double> &);
 
-void build_geom_plan(const cvs_params &p, int w, int h, unsigned field, GeomPlan &g) {
+void build_geom_plan(const cvs_params &p, int w, int h, unsigned field, GeomPlan &g, int warm_px) {
     g.w = w;
     g.h = h;
     g.field = field;
@@ -133,14 +146,14 @@ void build_geom_plan(const cvs_params &p, int w, int h, unsigned field, GeomPlan
     RandPoly curL = rand_poly_one(), curC = rand_poly_one();
     bool steadyL = false, steadyC = false;
     for (int r = 0; r < g.nl; r++) {
-        const uint64_t warm = (uint64_t)warm_draws_luma(r, w);
+        const uint64_t warm = (uint64_t)warm_draws_luma(r, w, warm_px);
         const uint64_t posL = g.offL + (uint64_t)r * w - warm;
         const uint64_t posC = g.offC + 2ull * (uint64_t)r * w - 2 * warm;
         // once the warm-up is at full length consecutive rows are a constant jump apart
-        if (warm == (uint64_t)kWarmPx && steadyL) curL = rand_poly_mul(curL, stepL);
-        else { curL = rand_poly_xpow(posL); steadyL = (warm == (uint64_t)kWarmPx); }
-        if (warm == (uint64_t)kWarmPx && steadyC) curC = rand_poly_mul(curC, stepC);
-        else { curC = rand_poly_xpow(posC); steadyC = (warm == (uint64_t)kWarmPx); }
+        if (warm == (uint64_t)warm_px && steadyL) curL = rand_poly_mul(curL, stepL);
+        else { curL = rand_poly_xpow(posL); steadyL = (warm == (uint64_t)warm_px); }
+        if (warm == (uint64_t)warm_px && steadyC) curC = rand_poly_mul(curC, stepC);
+        else { curC = rand_poly_xpow(posC); steadyC = (warm == (uint64_t)warm_px); }
         std::memcpy(&g.seek[(size_t)r * 62], curL.c, sizeof(curL.c));
         std::memcpy(&g.seek[(size_t)r * 62 + 31], curC.c, sizeof(curC.c));
     }

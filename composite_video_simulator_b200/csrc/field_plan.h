@@ -38,12 +38,13 @@ struct FieldSide {
     std::vector<int32_t> hs_shift;     // hs_count shifts (all non-zero)
 };
 
-inline int warm_draws_luma(int row, int w) {
+// warm_px: noise warm-up length in pixels (kWarmPx; shorter only to exercise the kernels' second-chance path in tests)
+inline int warm_draws_luma(int row, int w, int warm_px = kWarmPx) {
     const long long full = (long long)row * w;
-    return (int)(full < kWarmPx ? full : kWarmPx);
+    return (int)(full < warm_px ? full : warm_px);
 }
 
-void build_geom_plan(const cvs_params &p, int w, int h, unsigned field, GeomPlan &g);
+void build_geom_plan(const cvs_params &p, int w, int h, unsigned field, GeomPlan &g, int warm_px = kWarmPx);
 
 // `cur` must sit at the field's first draw; on return it sits at the next field's first draw.
 void build_field_side(const cvs_params &p, const GeomPlan &g, RandCursor &cur, FieldSide &fs);

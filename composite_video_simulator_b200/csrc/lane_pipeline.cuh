@@ -66,6 +66,12 @@ namespace cvs {
 #define CVS_XU_TRUNC 1           // 1: trunc() of a ready fp32 value by F2I.TRUNC + I2FP instead of LOP3 + FADD.RZ + FADD;
                                  // 2: also trunc(x * 2^k) (box filter / 4, Y * 256) by FMUL + F2I.TRUNC + I2FP
 #endif
+#ifndef CVS_MERGED_LUMA
+#define CVS_MERGED_LUMA 1        // fp32 VHS luma chain on scaled states with merged boost / sharpen (Num<float>::vhs_luma)
+#endif
+#ifndef CVS_DIRECT_IQ
+#define CVS_DIRECT_IQ 1          // fp32 RGB -> I, Q straight from the channels (three packed operations)
+#endif
 constexpr int kT = CVS_KT;       // pixels per step (8 or 4); every block lag below is derived from it
 static_assert(kT == 4 || kT == 8, "kT must be 4 or 8");
 constexpr int kLB = (7 + kT - 1) / kT;        // a demodulation of B(k) reads C up to x+7: kLB blocks of look-ahead
@@ -97,7 +103,10 @@ enum : uint32_t {
     RF_HEADSW = 1u << 1,      // row is rotated by the head switch; C comes from the scratch row (pre-pass)
     RF_HEADSW_INLINE = 1u << 2,   // row is rotated by a small right shift with zero fill: delayed in-kernel
 };
-constexpr int kHsRing = 48;               // per-lane delay ring of the in-kernel head switch (a multiple of kT; not a
+#ifndef CVS_HS_RING
+#define CVS_HS_RING 48
+#endif
+constexpr int kHsRing = CVS_HS_RING;               // per-lane delay ring of the in-kernel head switch (a multiple of kT; not a
                                           // power of two on purpose: 3 CTAs/SM must fit in shared memory; the default
                                           // 1080p shift is -22 +-4 px of jitter; bigger shifts take the pre-pass)
 constexpr int kHsMaxDelay = kHsRing - kT; // largest shift the ring can express
@@ -120,6 +129,11 @@ struct KConst {
     R a_luma, b_luma, c_luma;                     // VHS luma lowpass                          (:1800)
     V2<R> a_ch, b_ch, c_ch;                       // VHS chroma lowpass (U and V alike)         (:1821)
     R a_sharp, b_sharp, c_sharp, sharpen;         // VHS sharpen lowpass (4x luma cut), gain   (:1874,:1880)
+    // merged forms of the fp32 luma chain (Num<float>::vhs_luma): boost = 2.6 sv - 1.6 lp on the scaled states,
+    // sharpen = (1 + 2g) y2 - 2g ts
+    R k_boost_r, k_boost_p, k_sharp_y, k_sharp_t;
+    // RGB -> I, Q straight from the channels (x 256): {r, g, b} coefficients of I (.x) and Q (.y), :1381-1382
+    V2<R> k_iq_r, k_iq_g, k_iq_b;
     V2<R> a_out, b_out, c_out;                    // output chroma lowpass: x = I, y = Q        (:1411 / :1442)
     const R *phase_lut;                   // [2*pnoise+1][2] = {sin, cos} of state*pi/100, state = -p..p (:1746-1749)
     uint32_t flags;
@@ -188,7 +202,8 @@ template <> struct Num<double> {
     static CVS_HD P axpy2(P a, double k, P c) { return mk2(add(mul(a.x, k), c.x), add(mul(a.y, k), c.y)); }   // a k + c
     static CVS_HD P floor_half2(P s) { return mk2(floor_half(s.x), floor_half(s.y)); }
     static CVS_HD P rot2(P uv, double c, double s, double /*ns*/) { return mk2(rot_a(uv.x, c, uv.y, s), rot_b(uv.x, s, uv.y, c)); }
-    static CVS_HD void rgb2yiq2(uint32_t px, double &Y, P &IQ) { rgb2yiq(px, Y, IQ.x, IQ.y); }
+    static CVS_HD void rgb2yiq2(uint32_t px, double &Y, P &IQ, const KConst<double> &) { rgb2yiq(px, Y, IQ.x, IQ.y); }
+    static CVS_HD void rgb2yiq(uint32_t px, double &Y, double &I, double &Q, const KConst<double> &) { rgb2yiq(px, Y, I, Q); }
     static CVS_HD double floor_half(double s) { return ::floor(mul(s, 0.5)); }          // C int '>> 1'
     static CVS_HD double trunc_quarter(double s) { return ::trunc(mul(s, 0.25)); }     // C int '/ 4'
     static CVS_HD void unpack_rgb(uint32_t px, int &r, int &g, int &b) {
@@ -220,6 +235,15 @@ template <> struct Num<double> {
     static CVS_HD double boost(double s, double hp, double g) { return trunc_(add(s, mul(hp, g))); }                  // :1808-1810
     static CVS_HD double sharpen(double s, double ts, double g) { return trunc_(add(s, mul(mul(sub(s, ts), g), 2))); } // :1880
     static CVS_HD double preemph(double s, double hp, double g) { return trunc_(add(s, mul(hp, g))); }                // :1626-1627
+    // VHS luma of one sample: three poles, + 1.6 x its own highpass (:1793-1812), then the sharpener (:1865-1883)
+    static CVS_HD double pre_reset(double v, const KConst<double> &) { return v; }
+    static CVS_HD double vhs_luma(double pL[3], double &pLpre, double pS[3], double y, const KConst<double> &K) {
+        const double sv = cascade3(pL, y, K.a_luma, K.b_luma, K.c_luma);
+        const double lp = pole(pLpre, sv, K.a_luma, K.b_luma);
+        const double y2 = boost(sv, sub(sv, lp), 1.6);
+        const double ts = cascade3(pS, y2, K.a_sharp, K.b_sharp, K.c_sharp);
+        return sharpen(y2, ts, K.sharpen);
+    }
 };
 
 // fp32 notes.
@@ -280,6 +304,14 @@ template <> struct Num<float> {
         return __fadd_rn(__fadd_rd(a, kMagic), -kMagic);
 #else
         return ::floorf(a);
+#endif
+    }
+    // trunc(a * b) of the exact product for a, b >= 0: truncation is floor, no sign to look at
+    static CVS_HD float trunc_mul_nonneg(float a, float b) {
+#if defined(__CUDA_ARCH__)
+        return __fadd_rn(__fmaf_rd(a, b, kMagic), -kMagic);
+#else
+        return (float)::trunc((double)a * (double)b);
 #endif
     }
     static CVS_HD float floor_half(float s) {            // floor(s / 2), C int '>> 1'
@@ -387,7 +419,10 @@ template <> struct Num<float> {
         return mk2(rot_a(uv.x, c, uv.y, s), rot_b(uv.x, s, uv.y, c));
 #endif
     }
-    static CVS_HD void rgb2yiq2(uint32_t px, float &Y, P &IQ) {
+    // RGB_to_YIQ (:1375-1383).  Y = trunc(256 dY) with dY >= 0; I and Q are linear in (r, g, b), so they come
+    // straight from the channels with the x256 folded into the coefficients (K.k_iq_*: three packed operations
+    // for both planes instead of forming b - dY and r - dY first).
+    static CVS_HD void rgb2yiq2(uint32_t px, float &Y, P &IQ, const KConst<float> &K) {
 #if defined(__CUDA_ARCH__)
 #if CVS_XU_UNPACK
         // I2F.U8 with a byte selector: one instruction per channel on the (otherwise idle) conversion pipe
@@ -398,17 +433,25 @@ template <> struct Num<float> {
         const float bf = __fadd_rn(__uint_as_float(__byte_perm(px, 0x4B000000u, 0x7440)), -8388608.0f);
 #endif
         const float dY = fma_(0.11f, bf, fma_(0.59f, gf, mul(0.30f, rf)));
+        Y = trunc_mul_nonneg(dY, 256.0f);
+#if CVS_DIRECT_IQ
+        float2 iq = __fmul2_rn(f2(K.k_iq_r), make_float2(rf, rf));
+        iq = __ffma2_rn(f2(K.k_iq_g), make_float2(gf, gf), iq);
+        iq = __ffma2_rn(f2(K.k_iq_b), make_float2(bf, bf), iq);
+        const float2 ms = msign2(iq);
+        IQ = pp(__fadd2_rn(__fadd2_rz(iq, ms), make_float2(-ms.x, -ms.y)));
+#else
         const float bd = sub(bf, dY), rd = sub(rf, dY);
-        Y = trunc_pow2(dY, 256.0f);
         const float2 t = __fmul2_rn(make_float2(-0.27f, 0.41f), make_float2(bd, bd));
         const float2 iq = __ffma2_rn(make_float2(0.74f, 0.48f), make_float2(rd, rd), t);
         const float2 ms = msign2(iq);
         IQ = pp(__fadd2_rn(__ffma2_rz(iq, make_float2(256.0f, 256.0f), ms), make_float2(-ms.x, -ms.y)));
+#endif
 #else
-        rgb2yiq(px, Y, IQ.x, IQ.y);
+        rgb2yiq(px, Y, IQ.x, IQ.y, K);
 #endif
     }
-    static CVS_HD void rgb2yiq(uint32_t px, float &Y, float &I, float &Q) {
+    static CVS_HD void rgb2yiq(uint32_t px, float &Y, float &I, float &Q, const KConst<float> &K) {
 #if defined(__CUDA_ARCH__)
         // 0x4B0000bb is the float 2^23 + bb: one PRMT + one FADD per channel instead of an I2F
         const float rf = __fadd_rn(__uint_as_float(__byte_perm(px, 0x4B000000u, 0x7442)), -8388608.0f);
@@ -418,10 +461,15 @@ template <> struct Num<float> {
         const float rf = (float)((px >> 16) & 0xFF), gf = (float)((px >> 8) & 0xFF), bf = (float)(px & 0xFF);
 #endif
         const float dY = fma_(0.11f, bf, fma_(0.59f, gf, mul(0.30f, rf)));
+        Y = trunc_mul_nonneg(dY, 256.0f);
+#if CVS_DIRECT_IQ
+        I = trunc_(fma_(K.k_iq_b.x, bf, fma_(K.k_iq_g.x, gf, mul(K.k_iq_r.x, rf))));
+        Q = trunc_(fma_(K.k_iq_b.y, bf, fma_(K.k_iq_g.y, gf, mul(K.k_iq_r.y, rf))));
+#else
         const float bd = sub(bf, dY), rd = sub(rf, dY);
-        Y = trunc_mul_pos(dY, 256.0f);
         I = trunc_mul_pos(fma_(0.74f, rd, mul(-0.27f, bd)), 256.0f);
         Q = trunc_mul_pos(fma_(0.48f, rd, mul(0.41f, bd)), 256.0f);
+#endif
     }
     // one colour channel of YIQ_to_RGB (:1387-1395): trunc((Y + ci I + cq Q) / 256) clamped to 0..255.
     // Device: the operands carry an extra 2^-16 (exact: powers of two), so the last FFMA can saturate to
@@ -454,6 +502,28 @@ template <> struct Num<float> {
     static CVS_HD float boost(float s, float hp, float g) { return trunc_(fma_(hp, g, s)); }
     static CVS_HD float sharpen(float s, float ts, float g) { return trunc_(fma_(mul(sub(s, ts), g), 2.0f, s)); }
     static CVS_HD float preemph(float s, float hp, float g) { return trunc_(fma_(hp, g, s)); }
+    // VHS luma of one sample on scaled states (see the fp32 notes): r = lowpassed luma / alpha^3; the pre-emphasis
+    // pole keeps lp / alpha^4, so its update is one FFMA on r; the boost sv + 1.6 (sv - lp) and the sharpener
+    // y2 + 2g (y2 - ts) are each one FMUL + one FFMA on those states (8 + 7 instructions instead of 10 + 9).
+#if !CVS_MERGED_LUMA
+    static CVS_HD float pre_reset(float v, const KConst<float> &) { return v; }
+    static CVS_HD float vhs_luma(float pL[3], float &pLpre, float pS[3], float y, const KConst<float> &K) {
+        const float sv = cascade3(pL, y, K.a_luma, K.b_luma, K.c_luma);
+        const float lp = pole(pLpre, sv, K.a_luma, K.b_luma);
+        const float y2 = boost(sv, sub(sv, lp), 1.6f);
+        const float ts = cascade3(pS, y2, K.a_sharp, K.b_sharp, K.c_sharp);
+        return sharpen(y2, ts, K.sharpen);
+    }
+#else
+    static CVS_HD float pre_reset(float v, const KConst<float> &K) { return v / (K.a_luma * K.c_luma); }
+    static CVS_HD float vhs_luma(float pL[3], float &pLpre, float pS[3], float y, const KConst<float> &K) {
+        const float r = cascade3_raw(pL, y, K.b_luma);
+        pLpre = fma_(K.b_luma, pLpre, r);
+        const float y2 = trunc_(fma_(pLpre, K.k_boost_p, mul(r, K.k_boost_r)));
+        const float t = cascade3_raw(pS, y2, K.b_sharp);
+        return trunc_(fma_(t, K.k_sharp_t, mul(y2, K.k_sharp_y)));
+    }
+#endif
 };
 
 // integer helpers on integer-valued reals (all plane values are integers, |v| < 2^24)
@@ -625,7 +695,7 @@ struct Lane {
         Num<R>::cascade_reset2(pUV, (R)0);        // :1823,:1825
         Num<R>::cascade_reset2(pOIQ, (R)0);       // :1416
         Num<R>::cascade_reset(pL, (R)16, K.a_luma);   // resetFilter(16), :1802
-        pLpre = 16;                         // :1805
+        pLpre = Num<R>::pre_reset((R)16, K);    // :1805
         pPre = 16;                          // :1622
         Cm1 = 0; C2m1 = 0;
         for (int m = 0; m < 5; m++) { chc1[m] = 0; chc2[m] = 0; }
@@ -824,7 +894,7 @@ struct Pipeline {
             if (!EDGE || t < w) {
                 R y;
                 V2<R> iq;
-                N::rgb2yiq2(px[j], y, iq);
+                N::rgb2yiq2(px[j], y, iq, K);
                 Ycur[j] = y;
                 oIQcur[j] = N::cascade3_trunc2(ln.pIQ, iq, K.a_in, K.b_in, K.c_in);   // P[x-delay] = s, :1453
             } else {
@@ -849,7 +919,7 @@ struct Pipeline {
                         const bool rawI = !in_lp || (x + 2 >= w), rawQ = !in_lp || (x + 4 >= w);
                         if (rawI || rawQ) {
                             R y, i, q;
-                            N::rgb2yiq(pxprev[j], y, i, q);
+                            N::rgb2yiq(pxprev[j], y, i, q, K);
                             if (rawI) iv = i;
                             if (rawQ) qv = q;
                         }
@@ -945,11 +1015,7 @@ struct Pipeline {
         CVS_UNROLL
         for (int j = 0; j < kT; j++) {
             if (!EDGE || x0 + j < w) {
-                R sv = N::cascade3(ln.pL, Yb[j], K.a_luma, K.b_luma, K.c_luma);
-                const R lp = N::pole(ln.pLpre, sv, K.a_luma, K.b_luma);
-                const R y2 = N::boost(sv, N::sub(sv, lp), (R)1.6);
-                const R ts = N::cascade3(ln.pS, y2, K.a_sharp, K.b_sharp, K.c_sharp);
-                Yb[j] = N::sharpen(y2, ts, K.sharpen);
+                Yb[j] = N::vhs_luma(ln.pL, ln.pLpre, ln.pS, Yb[j], K);
                 oUVcur[j] = N::cascade3_trunc2(ln.pUV, IQb[j], K.a_ch, K.b_ch, K.c_ch);
                 if (EDGE && (x0 + j >= w - CD) && (x0 + j - (w - CD)) < kTailSlots) {
                     // the last CD samples keep their pre-filter values (:1830,:1834): stash them
@@ -1037,7 +1103,8 @@ struct Pipeline {
 
     // ---- F: dropout, output chroma lowpass, YIQ -> RGB; completes output block B(kf-1) ----------------
     // Returns true when `out` holds a complete block B(kf-1) (kf >= 1).
-    template <int MODE>
+    // NODROP: the caller knows that no row of the warp lost its chroma (the lean interior loop)
+    template <int MODE, bool NODROP = false>
     static CVS_HD bool stage_f(const KConst<R> &K, const RowConst<R> &rc, L &ln, int kf,
                                R Yf[kT], V2<R> IQf[kT], uint32_t out[kT]) {
         constexpr bool EDGE = MODE >= 1, GEN = MODE == 2;
@@ -1045,9 +1112,11 @@ struct Pipeline {
         const int w = K.w;
         if (EDGE && kf < 0) return false;
         const int x0 = kf * kT;
-        const R keep = (rc.rflags & RF_DROPOUT) ? (R)0 : (R)1;       // :1891-1901: the row loses its chroma
-        CVS_UNROLL
-        for (int j = 0; j < kT; j++) IQf[j] = N::scale2(IQf[j], keep);
+        if (!NODROP) {
+            const R keep = (rc.rflags & RF_DROPOUT) ? (R)0 : (R)1;   // :1891-1901: the row loses its chroma
+            CVS_UNROLL
+            for (int j = 0; j < kT; j++) IQf[j] = N::scale2(IQf[j], keep);
+        }
         V2<R> oIQ[kT];
         CVS_UNROLL
         for (int j = 0; j < kT; j++) {
@@ -1204,9 +1273,11 @@ CVS_HD void rng_rebase(const uint32_t *window, const uint32_t *poly, uint32_t hi
 // [-v, v] over the draws preceding the row brackets the true state; after a few dozen draws the two
 // runs coincide (they merge with probability 1/2 per draw once adjacent) and the state is exact.
 // Returns false if they did not merge (the host then retries from further back).
+// `bracket` (optional): a [lo, hi] pair narrower than [-v, v], from rewarm_bracket().
 CVS_HD bool warm_luma(const uint32_t mod, uint32_t magic, uint32_t shift, int v, LaneRng &g, int ndraws,
-                      bool from_field_start, int &state) {
+                      bool from_field_start, int &state, const int *bracket = nullptr) {
     int lo = from_field_start ? 0 : -v, hi = from_field_start ? 0 : v;
+    if (bracket) { lo = bracket[0]; hi = bracket[1]; }
     for (int i = 0; i < ndraws; i++) {
         const int d = draw_mod(g.next_raw(kRngBase - (uint32_t)ndraws + (uint32_t)i), mod, magic, shift);
         lo = noise_step(lo, d, v);
@@ -1216,8 +1287,9 @@ CVS_HD bool warm_luma(const uint32_t mod, uint32_t magic, uint32_t shift, int v,
     return lo == hi;
 }
 CVS_HD bool warm_chroma(const uint32_t mod, uint32_t magic, uint32_t shift, int v, LaneRng &g, int npx,
-                        bool from_field_start, int &su, int &sv) {
+                        bool from_field_start, int &su, int &sv, const int *bracket = nullptr) {
     int lou = from_field_start ? 0 : -v, hiu = from_field_start ? 0 : v, lov = lou, hiv = hiu;
+    if (bracket) { lou = bracket[0]; hiu = bracket[1]; lov = bracket[2]; hiv = bracket[3]; }
     for (int i = 0; i < npx; i++) {
         const uint32_t n = kRngBase - 2u * (uint32_t)npx + 2u * (uint32_t)i;
         const int du = draw_mod(g.next_raw(n), mod, magic, shift);
@@ -1227,6 +1299,37 @@ CVS_HD bool warm_chroma(const uint32_t mod, uint32_t magic, uint32_t shift, int 
     }
     su = lou; sv = lov;
     return lou == hiu && lov == hiv;
+}
+
+// Second chance of the warm-up (cold path; the first attempt fails with p < 2^-58 per row): the generator is
+// invertible, q[n-31] = q[n] - q[n-3], so from the 31 words `hist` preceding the warm-up the lane steps BACKWARD by
+// streams * extra_px draws, then forward again over them with the two bracketing runs.  The returned bracket(s)
+// [lo, hi] per stream (1 = luma, 2 = chroma U, V interleaved) then seed the regular warm-up, which leaves the ring
+// exactly as the first attempt did.  extra_px must not reach before the field's first draw of the stream; when it
+// reaches it exactly (at_field_start) the state there is the known 0.
+constexpr int kRewarmPx = 2048;
+CVS_HD void rewarm_bracket(const uint32_t hist[31], int streams, int extra_px, bool at_field_start, uint32_t mod,
+                           uint32_t magic, uint32_t shift, int v, int bracket[4]) {
+    uint32_t b[31];                       // slot k holds q[t0 - 31 + k + 31 j] for the j that is current
+    for (int k = 0; k < 31; k++) b[k] = hist[k];
+    const int n = streams * extra_px;
+    int slot = 0;                         // slot of q[t0 - i], i = 1..n, walking down: (31 - i) mod 31
+    for (int i = 1; i <= n; i++) {
+        slot = slot == 0 ? 30 : slot - 1;
+        const int s3 = slot >= 3 ? slot - 3 : slot + 28;
+        b[slot] = b[slot] - b[s3];        // q[t0 - i - 31] = q[t0 - i] - q[t0 - i - 3], stored where q[t0 - i] was
+    }
+    for (int k = 0; k < 4; k++) bracket[k] = (k & 1) ? (at_field_start ? 0 : v) : (at_field_start ? 0 : -v);
+    for (int i = 0; i < n; i++) {         // forward again: position t0 - n + i lives in the slot the walk is at
+        const int s3 = slot >= 3 ? slot - 3 : slot + 28;
+        const uint32_t qv = b[slot] + b[s3];
+        b[slot] = qv;
+        slot = slot == 30 ? 0 : slot + 1;
+        const int d = draw_mod(qv, mod, magic, shift);
+        const int st = (streams == 2) ? (i & 1) : 0;
+        bracket[2 * st] = noise_step(bracket[2 * st], d, v);
+        bracket[2 * st + 1] = noise_step(bracket[2 * st + 1], d, v);
+    }
 }
 
 // 8 BGRA pixels of B(k) of a source row; zero beyond the line end

@@ -28,14 +28,15 @@ namespace cvs {
 #endif
 constexpr int kNT = CVS_NT;              // threads per CTA
 constexpr int kWarpsPerCta = kNT / 32;
-#ifndef CVS_MIN_CTAS
-#define CVS_MIN_CTAS 3              // CTAs per SM the register allocator must leave room for (168 registers)
+#ifndef CVS_MIN_WARPS
+#define CVS_MIN_WARPS 12            // warps per SM the register allocator must leave room for (168 registers)
 #endif
-#ifndef CVS_FAST_UNROLL
-#define CVS_FAST_UNROLL 1       // steps per iteration of the interior loop (1 or 2).  Measured on B200 (1080p VHS-SP):
-                                // 2 executes 9 % fewer instructions (771 vs 853 per step, carried blocks rename instead of
-                                // moving) but its 25 KB body misses the instruction cache more (no_instruction stalls 0.18
-                                // -> 0.47 per issue): 118.4 k fields/s against 121.4 k with one step per iteration
+#define CVS_MIN_CTAS (CVS_MIN_WARPS / (CVS_NT / 32))
+#ifndef CVS_LEAN_LOOP
+#define CVS_LEAN_LOOP 1         // a lean interior loop for warps without head-switch / dropout rows
+#endif
+#ifndef CVS_EVEN_LOOP
+#define CVS_EVEN_LOOP 0         // an even-phase interior loop of their own for the warps that are not lean (else: the generic one)
 #endif
 constexpr int kRowsPerWarp = 31;         // lane 0 is the halo row of the vertical chroma blend
 
@@ -67,6 +68,7 @@ struct LaunchArgs {
     int32_t src_stride, dst_stride, opposite;
     int32_t vec_src, vec_dst;            // rows are 16-byte aligned: use 128-bit loads / stores
     int32_t bob;                         // also write every processed row y >= 1 into row y-1 (ffmpeg_ntsc.cpp:2232-2257)
+    int32_t warm_px;                     // noise warm-up length in pixels (kWarmPx)
     int32_t *status;                     // sticky error word (CVS_ERR_NOISE_SYNC)
 };
 
@@ -100,6 +102,12 @@ __device__ __forceinline__ void rebase_dev(const uint32_t *win_smem, const uint3
         for (int i = 0; i < 31; i++) acc += poly[i] * win_smem[k + i];
         hist[k] = acc;
     }
+}
+
+// The warm-up's second chance (lane_pipeline.cuh, rewarm_bracket), out of line: it runs for one row in 2^58.
+static __device__ __noinline__ void rewarm_dev(const uint32_t *hist, int streams, int extra_px, bool at_field_start, uint32_t mod,
+                                        uint32_t magic, uint32_t shift, int v, int *bracket) {
+    rewarm_bracket(hist, streams, extra_px, at_field_start, mod, magic, shift, v, bracket);
 }
 
 // Each lane reads its own row, 32 bytes (one sector) per step; four consecutive steps share one
@@ -148,12 +156,19 @@ struct Stepper {
     typedef Lane<R, VHS, CD, OUTFULL> L;
     typedef Pipeline<R, VHS, CD, OUTFULL> P;
 
-    template <int MODE>
+    // LEAN (interior steps only): the warp has no pre-pass head-switch row and no dropout row, and the pictures are
+    // 16-byte aligned, so none of that is compiled into the loop.  The instructions this removes were branched over,
+    // not executed; what it buys is instruction-cache footprint (profiles/ab_variants_r2.txt): the interior loop
+    // and the line-end body compete for the same cache, and a SECOND interior loop live on the SM costs more than
+    // the dead code did -- so the rows delayed by the default head switch stay in this loop behind one branch.
+    template <int MODE, bool LEAN = false>
     static __device__ __forceinline__ void step(const KConst<R> &K, const RowConst<R> &rc, L &ln, int s,
                                                 const uint32_t px[kT], const uint32_t *srow, bool vec_src,
                                                 const int32_t *hsrow, bool warp_hs,
                                                 R *hsring, bool warp_inl, bool valid, uint32_t *drow, uint32_t *drow_bob, bool vec_dst) {
         constexpr bool EDGE = MODE >= 1;
+        static_assert(!(LEAN && EDGE), "the lean step is an interior step");
+        if (LEAN) { warp_hs = false; vec_dst = true; }     // (the in-kernel head-switch delay stays: a warp-uniform branch)
         R C[kT], Yb[kT];
         V2<R> IQb[kT];
         BlendXchg<R> xo;
@@ -184,11 +199,12 @@ struct Stepper {
             R Yf[kT];
             V2<R> IQf[kT];
             P::template stage_c<MODE>(K, rc, ln, s, Yb, xo, above, Yf, IQf, kf);
-            have = P::template stage_f<MODE>(K, rc, ln, kf, Yf, IQf, out);
+            have = P::template stage_f<MODE, LEAN>(K, rc, ln, kf, Yf, IQf, out);
         } else {
             kf = s - 1 - kLB;
-            have = P::template stage_f<MODE>(K, rc, ln, kf, Yb, IQb, out);
+            have = P::template stage_f<MODE, LEAN>(K, rc, ln, kf, Yb, IQb, out);
         }
+        if (LEAN) have = true;                             // interior: s >= LAG, so block kf - 1 >= 0 is complete
         if (have && valid) {
             const int x0 = (kf - 1) * kT;
             if (vec_dst && (!EDGE || x0 + kT <= K.w)) {
@@ -285,22 +301,36 @@ __global__ void __launch_bounds__(kNT, (sizeof(R) == 4 ? CVS_MIN_CTAS : 1)) k_fi
         ln.rngL.l1 = lcg_seed(fd.fieldno, (unsigned)fd.field, row, 0u);
         ln.rngC.l1 = lcg_seed(fd.fieldno, (unsigned)fd.field, row, 1u);
     } else {
-        const long long full = (long long)row * w;
-        const int nd = (int)(full < kWarmPx ? full : kWarmPx);
-        const bool from_start = full <= kWarmPx;
+        const long long full = (long long)row * w;          // pixels of this field's noise segments before the row
+        const int nd = (int)(full < a.warm_px ? full : a.warm_px);
+        const bool from_start = full <= a.warm_px;
+        // when the bracketing runs of a warm-up do not merge, the lane walks the generator further back and tries again
+        const long long avail = full - nd;
+        const int extra = (int)(avail < kRewarmPx ? avail : kRewarmPx);
         bool ok = true;
         uint32_t hist[31];
+        int br[4];
         if (K.vnoise != 0) {
+            const uint32_t m = (uint32_t)(2 * K.vnoise + 1);
             rebase_dev(win, fd.seek + (size_t)row * 62, hist);
             ln.rngL.init(rings + tid, kNT, hist, kRngBase - (uint32_t)nd);
-            ok &= warm_luma((uint32_t)(2 * K.vnoise + 1), K.vmagic, K.vshift, K.vnoise, ln.rngL, nd, from_start, ln.nY);
+            if (!warm_luma(m, K.vmagic, K.vshift, K.vnoise, ln.rngL, nd, from_start, ln.nY)) {
+                rewarm_dev(hist, 1, extra, extra == avail, m, K.vmagic, K.vshift, K.vnoise, br);
+                ln.rngL.init(rings + tid, kNT, hist, kRngBase - (uint32_t)nd);
+                ok &= warm_luma(m, K.vmagic, K.vshift, K.vnoise, ln.rngL, nd, from_start, ln.nY, br);
+            }
         }
         if (K.cnoise != 0) {
+            const uint32_t m = (uint32_t)(2 * K.cnoise + 1);
             rebase_dev(win, fd.seek + (size_t)row * 62 + 31, hist);
             ln.rngC.init(rings + (size_t)kRngSlots * kNT + tid, kNT, hist, kRngBase - 2u * (uint32_t)nd);
-            ok &= warm_chroma((uint32_t)(2 * K.cnoise + 1), K.cmagic, K.cshift, K.cnoise, ln.rngC, nd, from_start, ln.nU, ln.nV);
+            if (!warm_chroma(m, K.cmagic, K.cshift, K.cnoise, ln.rngC, nd, from_start, ln.nU, ln.nV)) {
+                rewarm_dev(hist, 2, extra, extra == avail, m, K.cmagic, K.cshift, K.cnoise, br);
+                ln.rngC.init(rings + (size_t)kRngSlots * kNT + tid, kNT, hist, kRngBase - 2u * (uint32_t)nd);
+                ok &= warm_chroma(m, K.cmagic, K.cshift, K.cnoise, ln.rngC, nd, from_start, ln.nU, ln.nV, br);
+            }
         }
-        if (!ok) atomicOr(a.status, 1);
+        if (!ok) atomicOr(a.status, 1);                     // (both attempts failed: p < 2^-2000)
     }
 
     const int nsteps = line_steps<VHS, CD>(w);
@@ -313,6 +343,9 @@ __global__ void __launch_bounds__(kNT, (sizeof(R) == 4 ? CVS_MIN_CTAS : 1)) k_fi
     const bool warp_hs = __any_sync(0xffffffffu, hsrow != nullptr);
     const bool warp_inl = VHS && __any_sync(0xffffffffu, rc.hs_delay > 0);   // (the host only plans it for VHS kernels)
     R *hsring = reinterpret_cast<R *>(smem_raw + SL::off_hsring) + tid;   // VHS only (head switching needs -vhs)
+    // the lean interior loop: aligned pictures and no row of the warp that needs a head-switch or dropout special case
+    const bool lean = vec_src && vec_dst && !warp_hs && !__any_sync(0xffffffffu, (rc.rflags & RF_DROPOUT) != 0);
+    (void)lean;
 
     // Step loop.  The interior (fast) steps get a loop of their own: if the three code variants shared
     // one loop the compiler would have to bring ~85 carried registers back to a common allocation at
@@ -337,29 +370,28 @@ __global__ void __launch_bounds__(kNT, (sizeof(R) == 4 ? CVS_MIN_CTAS : 1)) k_fi
             for (int j = 0; j < kT; j++) px[j] = pxn[j];
         }
         if (pass == 0) {
-            if (!rc.odd_any) {                                       // every row of the warp has an even line phase
-#if CVS_FAST_UNROLL == 2
-                // two steps per iteration: the carried blocks (previous-block arrays, the prefetched pixels)
-                // change roles by renaming instead of being moved; a leftover odd step is taken by the edge
-                // loop below, which is valid on interior steps too
-#pragma unroll 1
-                for (; s + 1 < s_hi; s += 2) {
-                    uint32_t pxn[kT];
-                    load_block_fast(srow, s + 1, vec_src, pxn);      // in range: interior_steps() keeps kT(s+2) <= w
-                    St::template step<MODE_FAST_EVEN>(K, rc, ln, s, px, srow, vec_src, hsrow, warp_hs, hsring, warp_inl, valid, drow, drow_bob, vec_dst);
-                    load_block_fast(srow, s + 2, vec_src, px);
-                    St::template step<MODE_FAST_EVEN>(K, rc, ln, s + 1, pxn, srow, vec_src, hsrow, warp_hs, hsring, warp_inl, valid, drow, drow_bob, vec_dst);
-                }
-#else
+            // Interior steps: three loops, picked per warp.  (One step per iteration: two steps per iteration
+            // execute 9 % fewer instructions but measured slower twice, profiles/ab_variants_r1.txt and _r2.txt.)
+            if (!rc.odd_any && lean && CVS_LEAN_LOOP) {
+                // every row has an even line phase and none needs a pre-pass or dropout special case
 #pragma unroll 1
                 for (; s < s_hi; s++) {
                     uint32_t pxn[kT];
-                    load_block_fast(srow, s + 1, vec_src, pxn);      // in range: interior_steps() keeps kT(s+2) <= w
-                    St::template step<MODE_FAST_EVEN>(K, rc, ln, s, px, srow, vec_src, hsrow, warp_hs, hsring, warp_inl, valid, drow, drow_bob, vec_dst);
+                    load_block_fast(srow, s + 1, true, pxn);         // in range: interior_steps() keeps kT(s+2) <= w
+                    St::template step<MODE_FAST_EVEN, true>(K, rc, ln, s, px, srow, true, hsrow, false, hsring, warp_inl, valid, drow, drow_bob, true);
 #pragma unroll
                     for (int j = 0; j < kT; j++) px[j] = pxn[j];
                 }
-#endif
+            } else if (!rc.odd_any && CVS_EVEN_LOOP) {
+                // even line phase, but some row is rotated by the head switch, lost its chroma or is unaligned
+#pragma unroll 1
+                for (; s < s_hi; s++) {
+                    uint32_t pxn[kT];
+                    load_block_fast(srow, s + 1, vec_src, pxn);
+                    St::template step<MODE_FAST_EVEN, false>(K, rc, ln, s, px, srow, vec_src, hsrow, warp_hs, hsring, warp_inl, valid, drow, drow_bob, vec_dst);
+#pragma unroll
+                    for (int j = 0; j < kT; j++) px[j] = pxn[j];
+                }
             } else {
 #pragma unroll 1
                 for (; s < s_hi; s++) {
@@ -395,12 +427,19 @@ __global__ void __launch_bounds__(kHsNT) k_headswitch(const __grid_constant__ La
     ln.rngL.l1 = lcg_seed(fd.fieldno, (unsigned)fd.field, row, 0u);       // fast noise mode (else init() below)
     if (K.vnoise != 0 && !(K.flags & F_NOISE_FAST)) {
         const long long full = (long long)row * w;
-        const int nd = (int)(full < kWarmPx ? full : kWarmPx);
+        const int nd = (int)(full < a.warm_px ? full : a.warm_px);
+        const uint32_t m = (uint32_t)(2 * K.vnoise + 1);
         uint32_t hist[31];
         rng_rebase(fd.window, fd.seek + (size_t)row * 62, hist);
         ln.rngL.init(ring + threadIdx.x, kHsNT, hist, kRngBase - (uint32_t)nd);
-        if (!warm_luma((uint32_t)(2 * K.vnoise + 1), K.vmagic, K.vshift, K.vnoise, ln.rngL, nd, full <= kWarmPx, ln.nY))
-            atomicOr(a.status, 1);
+        if (!warm_luma(m, K.vmagic, K.vshift, K.vnoise, ln.rngL, nd, full <= a.warm_px, ln.nY)) {
+            const long long avail = full - nd;
+            const int extra = (int)(avail < kRewarmPx ? avail : kRewarmPx);
+            int br[4];
+            rewarm_dev(hist, 1, extra, extra == avail, m, K.vmagic, K.vshift, K.vnoise, br);
+            ln.rngL.init(ring + threadIdx.x, kHsNT, hist, kRngBase - (uint32_t)nd);
+            if (!warm_luma(m, K.vmagic, K.vshift, K.vnoise, ln.rngL, nd, full <= a.warm_px, ln.nY, br)) atomicOr(a.status, 1);
+        }
     }
     int sy = fd.field + 2 * row + a.opposite;
     sy = sy > h - 1 ? h - 1 : sy;

@@ -38,7 +38,9 @@ typedef enum cvs_status {
     CVS_ERR_NOMEM = -4,
     CVS_ERR_CAPACITY = -5,      /* w/h/batch larger than the context was created for                    */
     CVS_ERR_HELP = -6,          /* -h/-help seen (reference prints help and exits 1, :981-984)          */
-    CVS_ERR_NOISE_SYNC = -7,    /* internal: noise warm-up did not converge (retried by the host)       */
+    CVS_ERR_NOISE_SYNC = -7,    /* internal: a row's noise warm-up did not converge even after the kernel's
+                                   second, 2048-pixel attempt (p < 2^-2000 per row); the batch's pictures are
+                                   not the reference's.  Reported by the next synchronising call.          */
     CVS_ERR_UNSUPPORTED = -8
 } cvs_status;
 
@@ -229,6 +231,13 @@ int cvs_composite_fields_host_async(cvs_ctx *ctx,
                                     int w, int h, int src_interlaced, int src_top_field_first,
                                     int n, unsigned long long first_fieldno);
 int cvs_synchronize(cvs_ctx *ctx);
+/*
+ * Page-locked host memory for the pictures handed to the _host entry points (what the reference keeps in its
+ * AVFrame buffers, ffmpeg_ntsc.cpp:2069-2092): pageable memory halves the transfer rate.  Plain
+ * cudaHostAlloc / cudaFreeHost on the context's device.
+ */
+int cvs_alloc_host(cvs_ctx *ctx, void **out, size_t bytes);
+int cvs_free_host(cvs_ctx *ctx, void *p);
 
 /* ---- RNG stream (hidden state of the reference: the libc rand() position) ------------------ */
 

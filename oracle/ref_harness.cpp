@@ -55,6 +55,33 @@ void ref_set_params(const cvs_params *p) {
     vhs_head_switching_phase_noise = p->vhs_head_switching_phase_noise;
 }
 
+// The BASELINE presets applied to the reference's own globals, for callers that must not load the product
+// library (bench.py --impl reference).  What each switch sets is ffmpeg_ntsc.cpp:1141-1151 (-vhs) and :1160-1189
+// (-vhs-speed); "comp" leaves the global initialisers (:756-809) as compiled.  Returns 0, or -1 for an unknown name.
+int ref_set_preset(const char *name) {
+    static bool saved = false;
+    static int d_pn, d_cn, d_cl, d_vn, d_speed;
+    static bool d_vhs, d_hs;
+    if (!saved) {          // remember the initialisers so that presets do not accumulate
+        d_pn = video_chroma_phase_noise; d_cn = video_chroma_noise; d_cl = video_chroma_loss; d_vn = video_noise;
+        d_speed = output_vhs_tape_speed; d_vhs = emulating_vhs; d_hs = vhs_head_switching;
+        saved = true;
+    }
+    video_chroma_phase_noise = d_pn; video_chroma_noise = d_cn; video_chroma_loss = d_cl; video_noise = d_vn;
+    output_vhs_tape_speed = d_speed; emulating_vhs = d_vhs; vhs_head_switching = d_hs;
+    if (!strcmp(name, "comp")) return 0;
+    int pn, cn, cl, vn, speed;
+    if (!strcmp(name, "sp")) { speed = VHS_SP; pn = 4; cn = 16; cl = 4; vn = 4; }
+    else if (!strcmp(name, "lp")) { speed = VHS_LP; pn = 5; cn = 19; cl = 6; vn = 5; }
+    else if (!strcmp(name, "ep")) { speed = VHS_EP; pn = 6; cn = 22; cl = 8; vn = 6; }
+    else return -1;
+    emulating_vhs = true;              // -vhs
+    vhs_head_switching = true;
+    output_vhs_tape_speed = speed;     // -vhs-speed <name>
+    video_chroma_phase_noise = pn; video_chroma_noise = cn; video_chroma_loss = cl; video_noise = vn;
+    return 0;
+}
+
 void ref_srand(unsigned seed) { srand(seed); }
 int  ref_rand(void) { return rand(); }
 

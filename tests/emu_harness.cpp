@@ -20,6 +20,29 @@ using namespace cvs;
 
 namespace {
 
+int g_warm_px = kWarmPx;      // emu_set_warm_px(): a short warm-up exercises the second-chance path (rewarm_bracket)
+
+// the kernels' warm-up with its second chance (scanline_kernels.cuh)
+template <typename R>
+bool warm_up(const KConst<R> &K, bool chroma, LaneRng &g, uint32_t *ring, int stride, const uint32_t hist[31], int row, int w,
+             int &s0, int &s1) {
+    const long long full = (long long)row * w;
+    const int nd = (int)(full < g_warm_px ? full : g_warm_px);
+    const bool from_start = full <= g_warm_px;
+    const int v = chroma ? K.cnoise : K.vnoise;
+    const uint32_t m = (uint32_t)(2 * v + 1), magic = chroma ? K.cmagic : K.vmagic, shift = chroma ? K.cshift : K.vshift;
+    const uint32_t n0 = kRngBase - (chroma ? 2u : 1u) * (uint32_t)nd;
+    g.init(ring, stride, hist, n0);
+    bool ok = chroma ? warm_chroma(m, magic, shift, v, g, nd, from_start, s0, s1) : warm_luma(m, magic, shift, v, g, nd, from_start, s0);
+    if (ok) return true;
+    const long long avail = full - nd;
+    const int extra = (int)(avail < kRewarmPx ? avail : kRewarmPx);
+    int br[4];
+    rewarm_bracket(hist, chroma ? 2 : 1, extra, extra == avail, m, magic, shift, v, br);
+    g.init(ring, stride, hist, n0);
+    return chroma ? warm_chroma(m, magic, shift, v, g, nd, from_start, s0, s1, br) : warm_luma(m, magic, shift, v, g, nd, from_start, s0, br);
+}
+
 // NF: fast noise mode (cvs_set_noise_mode): the kernels' NF instantiations
 template <typename R, bool VHS, int CD, bool OUTFULL, bool NF>
 int run_field(const cvs_params &p, RandCursor &cur, uint8_t *dst, int dst_stride, const uint8_t *src,
@@ -28,7 +51,7 @@ int run_field(const cvs_params &p, RandCursor &cur, uint8_t *dst, int dst_stride
     typedef Lane<R, VHS, CD, OUTFULL> L;
     typedef Pipeline<R, VHS, CD, OUTFULL> P;
     GeomPlan g;
-    build_geom_plan(p, w, h, field, g);
+    build_geom_plan(p, w, h, field, g, g_warm_px);
     FieldSide fs;
     build_field_side(p, g, cur, fs);
     KConst<R> K;
@@ -58,12 +81,9 @@ int run_field(const cvs_params &p, RandCursor &cur, uint8_t *dst, int dst_stride
         if (K.vnoise != 0 && !NF) {
             uint32_t hist[31];
             rng_rebase(fs.window, &g.seek[(size_t)row * 62], hist);
-            const int nd = warm_draws_luma(row, w);
-            ln.rngL.init(ring, 1, hist, kRngBase - (uint32_t)nd);
             ln.nY = 0;
-            if (!warm_luma((uint32_t)(2 * K.vnoise + 1), K.vmagic, K.vshift, K.vnoise, ln.rngL, nd,
-                           (long long)row * w <= kWarmPx, ln.nY))
-                return CVS_ERR_NOISE_SYNC;
+            int unused = 0;
+            if (!warm_up<R>(K, false, ln.rngL, ring, 1, hist, row, w, ln.nY, unused)) return CVS_ERR_NOISE_SYNC;
         }
         headswitch_row<R, NF>(K, rc, ln, src_row(row), &scratch[(size_t)i * w], fs.hs_shift[(size_t)i]);
     }
@@ -97,8 +117,6 @@ int run_field(const cvs_params &p, RandCursor &cur, uint8_t *dst, int dst_stride
             ln.tailV = ln.tailU + kTailSlots;
             ln.tail_stride = 1;
             ln.nY = ln.nU = ln.nV = 0;
-            const int nd = warm_draws_luma(row, w);
-            const bool from_start = (long long)row * w <= kWarmPx;
             uint32_t hist[31];
             if (NF) {                                  // fast noise: per-row counter generators, no replay
                 ln.rngL.l1 = lcg_seed(fieldno, field, row, 0u);
@@ -106,14 +124,13 @@ int run_field(const cvs_params &p, RandCursor &cur, uint8_t *dst, int dst_stride
             }
             if (K.vnoise != 0 && !NF) {
                 rng_rebase(fs.window, &g.seek[(size_t)row * 62], hist);
-                ln.rngL.init(&rings[(size_t)l * 2 * kRngSlots], 1, hist, kRngBase - (uint32_t)nd);
-                if (!warm_luma((uint32_t)(2 * K.vnoise + 1), K.vmagic, K.vshift, K.vnoise, ln.rngL, nd, from_start, ln.nY))
+                int unused = 0;
+                if (!warm_up<R>(K, false, ln.rngL, &rings[(size_t)l * 2 * kRngSlots], 1, hist, row, w, ln.nY, unused))
                     return CVS_ERR_NOISE_SYNC;
             }
             if (K.cnoise != 0 && !NF) {
                 rng_rebase(fs.window, &g.seek[(size_t)row * 62 + 31], hist);
-                ln.rngC.init(&rings[(size_t)l * 2 * kRngSlots + kRngSlots], 1, hist, kRngBase - 2u * (uint32_t)nd);
-                if (!warm_chroma((uint32_t)(2 * K.cnoise + 1), K.cmagic, K.cshift, K.cnoise, ln.rngC, nd, from_start, ln.nU, ln.nV))
+                if (!warm_up<R>(K, true, ln.rngC, &rings[(size_t)l * 2 * kRngSlots + kRngSlots], 1, hist, row, w, ln.nU, ln.nV))
                     return CVS_ERR_NOISE_SYNC;
             }
         }
@@ -122,13 +139,16 @@ int run_field(const cvs_params &p, RandCursor &cur, uint8_t *dst, int dst_stride
         bool odd_any = false;
         for (int l = 0; l < 32; l++) odd_any |= (rc[l].xi & 1) != 0;
         for (int l = 0; l < 32; l++) rc[l].odd_any = odd_any;
+        // the kernel's lean interior loop (scanline_kernels.cuh): no pre-pass head-switch row, no dropout row
+        bool lean = true;
+        for (int l = 0; l < 32; l++) lean &= hsrow[l] == nullptr && !(rc[l].rflags & RF_DROPOUT);
         for (int s = 0; s < nsteps; s++) {
             // the kernel's choice of code variant for this step (force_general: 1 = general everywhere,
             // 2 = edge variant everywhere, to exercise those variants on interior blocks as well)
             int mode = (K.flags & F_GENERAL) ? MODE_GENERAL : ((s >= s_lo && s < s_hi) ? MODE_FAST : MODE_EDGE);
             if (force_general == 2 && mode == MODE_FAST) mode = MODE_EDGE;
             // MODE_FAST warps whose rows all have an even line phase run the MODE_FAST_EVEN loop (scanline_kernels.cuh)
-            if (mode == MODE_FAST && !odd_any) mode = MODE_FAST_EVEN;
+            if (mode == MODE_FAST && !odd_any && lean) mode = MODE_FAST_EVEN;
             BlendXchg<R> xo[32];
             R Yb[32][kT];
             V2<R> IQb[32][kT];
@@ -163,10 +183,10 @@ int run_field(const cvs_params &p, RandCursor &cur, uint8_t *dst, int dst_stride
 #define CVS_TAIL(M)                                                                                          \
     if (VHS) {                                                                                               \
         P::template stage_c<M>(K, rc[l], lane[l], s, Yb[l], xo[l], above, Yf, IQf, kf);                      \
-        have = P::template stage_f<M>(K, rc[l], lane[l], kf, Yf, IQf, out);                                  \
+        have = P::template stage_f<M, (M) == MODE_FAST_EVEN>(K, rc[l], lane[l], kf, Yf, IQf, out);           \
     } else {                                                                                                 \
         kf = s - 1 - kLB;                                                                                    \
-        have = P::template stage_f<M>(K, rc[l], lane[l], kf, Yb[l], IQb[l], out);                            \
+        have = P::template stage_f<M, (M) == MODE_FAST_EVEN>(K, rc[l], lane[l], kf, Yb[l], IQb[l], out);     \
     }
                 if (mode == MODE_FAST_EVEN) { CVS_TAIL(MODE_FAST_EVEN) }
                 else if (mode == MODE_FAST) { CVS_TAIL(MODE_FAST) }
@@ -201,6 +221,9 @@ int dispatch(const cvs_params &p, RandCursor &cur, uint8_t *dst, int dst_stride,
 }  // namespace
 
 extern "C" {
+
+// tests: a warm-up shorter than kWarmPx makes the first attempt fail on most rows (second-chance path)
+void emu_set_warm_px(int px) { g_warm_px = (px >= 0 && px <= kWarmPx) ? px : kWarmPx; }
 
 // precision: 0 = float (production arithmetic), 1 = double (reference arithmetic).
 // rng_pos in/out: absolute rand() position (draws since the default seed).

@@ -112,3 +112,22 @@ def test_fast_noise_mode_is_ignored_for_large_amplitudes_and_fp64(oracle, emu):
     a, _ = helpers.run_emu(emu, p, frames, n, w, h, precision=1, noise_fast=1)
     want, _ = helpers.run_oracle(oracle, p, frames, n, w, h)
     assert np.array_equal(a, want)
+
+
+@pytest.mark.parametrize("warm_px", [0, 3])
+@pytest.mark.parametrize("w,h,n,argv", [(160, 120, 3, ["-vhs"]), (101, 67, 2, ["-vhs", "-vhs-speed", "ep"]), (64, 300, 2, [])])
+def test_short_warmup_takes_the_second_chance_and_stays_exact(oracle, emu, warm_px, w, h, n, argv):
+    """The noise state of a row is recovered by running the recurrence from both ends of its range over the draws
+    before the row; when the two runs do not merge (p < 2^-58 per row at the production length of 64 pixels) the lane
+    walks the generator BACKWARD (rewarm_bracket, lane_pipeline.cuh) and tries again.  A warm-up of 0 or 3 pixels
+    makes the first attempt fail on nearly every row: the pictures must still be the reference's, bit for bit."""
+    p = helpers.params(*argv)
+    frames = lambda k: helpers.noise_frame(w, h, 7 + k)
+    want, g = helpers.run_oracle(oracle, p, frames, n, w, h)
+    emu.emu_set_warm_px(warm_px)
+    try:
+        got, pos = helpers.run_emu(emu, p, frames, n, w, h, precision=1)
+    finally:
+        emu.emu_set_warm_px(64)
+    assert pos == g.pos
+    assert np.array_equal(want, got)

@@ -468,3 +468,26 @@ def test_last_row_of_an_exactly_sized_device_buffer():
             eng.synchronize()
             outs.append(dst.cpu())
     assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("warm_px", ["0", "5"])
+@pytest.mark.parametrize("w,h,n,argv", [(720, 480, 3, ["-vhs"]), (101, 67, 2, ["-vhs", "-vhs-speed", "ep"]),
+                                        (3840, 2160, 1, ["-vhs", "-vhs-speed", "lp"])])    # (pre-pass rows warm up too)
+def test_noise_warmup_second_chance(oracle, w, h, n, argv, warm_px):
+    """CVS_ERR_NOISE_SYNC is not something a caller has to handle: a lane whose noise warm-up does not converge walks
+    the generator backward and tries again in the kernel (scanline_kernels.cuh).  CVS_WARM_PX shortens the first
+    attempt so that nearly every row takes that path; fp64 must still be the reference bit for bit."""
+    p = helpers.params(*argv)
+    frames = lambda k: helpers.noise_frame(w, h, 11 + k)
+    want, g = helpers.run_oracle(oracle, p, frames, n, w, h)
+    got = np.zeros((h, w), dtype=np.uint32)
+    os.environ["CVS_WARM_PX"] = warm_px
+    try:
+        with cvs.Engine(params=p, max_w=w, max_h=h, max_batch=2) as eng:
+            eng.set_precision(True)
+            for k in range(n):
+                eng.composite_layer(got, frames(k), (k & 1) ^ 1, k)
+            assert eng.rng_tell() == g.pos
+    finally:
+        os.environ.pop("CVS_WARM_PX", None)
+    assert np.array_equal(want, got)
