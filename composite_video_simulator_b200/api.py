@@ -225,6 +225,21 @@ class Engine:
                                                _ptr(bgra), stride, stride * h, w, h, n, 0 if fmt420 else 1),
                "cvs_bgra_to_yuv_device")
 
+    def scale_to_bgra_device(self, dst, dw, dh, planes, linesizes, sw, sh, fmt, n=1, dst_stride=None, dst_pic_stride=None,
+                             pic_strides=None):
+        """Decoder pictures -> BGRA at dw x dh on the device (frame_copy_scale, ffmpeg_ntsc.cpp:544-613); asynchronous.
+        planes: device addresses / CUDA tensors of the source planes (1 for BGRA, 2 for NV12, 3 for planar YUV);
+        fmt: 0 BGRA, 1 YUV420P, 2 YUV422P, 3 NV12 (CVS_PIX_*)."""
+        ch = sh if fmt == 2 else (sh + 1) // 2
+        rows = [sh, ch, ch]
+        ptrs = (C.c_void_p * 3)(*([_ptr(p) for p in planes] + [None] * (3 - len(planes))))
+        ls = (C.c_int * 3)(*(list(linesizes) + [0] * (3 - len(linesizes))))
+        ps = pic_strides or [linesizes[i] * rows[i] for i in range(len(planes))]
+        pst = (C.c_longlong * 3)(*(list(ps) + [0] * (3 - len(ps))))
+        ds = dst_stride or 4 * dw
+        _check(self.lib.cvs_scale_to_bgra_device(self._ctx, _ptr(dst), ds, dst_pic_stride or ds * dh, dw, dh, ptrs, ls, pst,
+                                                 sw, sh, fmt, n), "cvs_scale_to_bgra_device")
+
     def synchronize(self):
         _check(self.lib.cvs_synchronize(self._ctx), "cvs_synchronize")
 

@@ -20,6 +20,7 @@
 #include "field_plan.h"
 #include "glibc_rand.h"
 #include "scanline_kernels.cuh"
+#include "scale_convert.cuh"
 #include "yuv_convert.cuh"
 
 using namespace cvs;
@@ -30,6 +31,15 @@ constexpr int kStagingSlots = 3;
 constexpr size_t kMaxEventPairs = 4096;
 constexpr int kHostChunkDefault = 32;       // fields per pipeline stage of the host-pointer entry points
                                             // (measured: 16 -> 8.6k, 32 -> 9.5k, 64 -> 9.6k fields/s at 1080p)
+
+// device copy of the tap tables of one scaling geometry (scale_convert.cuh)
+struct ScalePlan {
+    int dw = 0, dh = 0, sw = 0, sh = 0, format = 0;
+    int32_t *d_first = nullptr;      // fx | fy | cfx | cfy
+    int16_t *d_w = nullptr;          // wx | wy | cwx | cwy
+    size_t off_first[4] = {0, 0, 0, 0}, off_w[4] = {0, 0, 0, 0};
+    int taps[4] = {0, 0, 0, 0};
+};
 
 struct DevPlan {
     int w = 0, h = 0;
@@ -82,6 +92,7 @@ struct cvs_ctx {
     size_t ev_used = 0;
     RandCursor cur;
     std::vector<std::unique_ptr<DevPlan>> plans;
+    std::vector<std::unique_ptr<ScalePlan>> scale_plans;
     Staging slots[kStagingSlots];
     int next_slot = 0;
     cudaStream_t s_tab = nullptr;              // uploads the per-batch side tables
@@ -123,6 +134,8 @@ void free_all(cvs_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto &pl : c->plans) if (pl && pl->d_seek) cudaFree(pl->d_seek);
     c->plans.clear();
+    for (auto &sp : c->scale_plans) if (sp) { cudaFree(sp->d_first); cudaFree(sp->d_w); }
+    c->scale_plans.clear();
     for (auto &s : c->slots) {
         if (s.h_fields) cudaFreeHost(s.h_fields);
         if (s.h_rowinfo) cudaFreeHost(s.h_rowinfo);
@@ -774,6 +787,75 @@ int cvs_bgra_to_yuv_device(cvs_ctx *ctx, void *y, int ly, long long y_pic_stride
     const dim3 grid((groups + block.x - 1) / block.x, crows, n);
     if (crows > 65535 || n > 65535) return CVS_ERR_CAPACITY;
     k_bgra_to_yuv<<<grid, block, 0, ctx->stream>>>(a);
+    CVS_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return CVS_OK;
+}
+
+int cvs_scale_to_bgra_device(cvs_ctx *ctx, void *dst, int dst_stride, long long dst_pic_stride, int dw, int dh,
+                             const void *const src[3], const int src_linesize[3], const long long src_pic_stride[3],
+                             int sw, int sh, int format, int n) {
+    if (!ctx || !dst || !src || !src_linesize || !src_pic_stride || !src[0]) return CVS_ERR_INVALID_ARG;
+    if (dw <= 0 || dh <= 0 || sw <= 0 || sh <= 0 || n < 0) return CVS_ERR_INVALID_ARG;
+    if (format < CVS_PIX_BGRA || format > CVS_PIX_NV12) return CVS_ERR_INVALID_ARG;
+    if (dst_stride < 4 * dw || (dst_stride & 3) || ((uintptr_t)dst & 3) || (dst_pic_stride & 3)) return CVS_ERR_INVALID_ARG;
+    const int cw = (sw + 1) / 2, ch = format == CVS_PIX_YUV422P ? sh : (sh + 1) / 2;
+    if (format == CVS_PIX_BGRA) {
+        if (src_linesize[0] < 4 * sw) return CVS_ERR_INVALID_ARG;
+    } else {
+        if (src_linesize[0] < sw || !src[1]) return CVS_ERR_INVALID_ARG;
+        if (format == CVS_PIX_NV12 ? src_linesize[1] < 2 * cw : (src_linesize[1] < cw || !src[2] || src_linesize[2] < cw))
+            return CVS_ERR_INVALID_ARG;
+    }
+    if (sw > 16 * dw || sh > 16 * dh || dh > 65535 || n > 65535) return CVS_ERR_CAPACITY;
+    if (n == 0) return CVS_OK;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return CVS_ERR_CUDA;
+    ScalePlan *sp = nullptr;
+    for (auto &q : ctx->scale_plans)
+        if (q->dw == dw && q->dh == dh && q->sw == sw && q->sh == sh && q->format == format) sp = q.get();
+    if (!sp) {
+        std::unique_ptr<ScalePlan> q(new (std::nothrow) ScalePlan());
+        if (!q) return CVS_ERR_NOMEM;
+        q->dw = dw; q->dh = dh; q->sw = sw; q->sh = sh; q->format = format;
+        ScaleAxis ax[4];
+        const int suby = format == CVS_PIX_YUV422P ? 1 : 2;
+        scale_build_axis(dw, sw, 1, 0, ax[0]);
+        scale_build_axis(dh, sh, 1, 0, ax[1]);
+        scale_build_axis(dw, sw, 2, 0, ax[2]);                       // chroma: co-sited with the even luma columns
+        scale_build_axis(dh, sh, suby, suby == 2 ? 1 : 0, ax[3]);    // 4:2:0 chroma rows sit between two luma rows
+        std::vector<int32_t> first;
+        std::vector<int16_t> wts;
+        for (int i = 0; i < 4; i++) {
+            q->off_first[i] = first.size();
+            q->off_w[i] = wts.size();
+            q->taps[i] = ax[i].taps;
+            first.insert(first.end(), ax[i].first.begin(), ax[i].first.end());
+            wts.insert(wts.end(), ax[i].w.begin(), ax[i].w.end());
+        }
+        CVS_CUDA(dev_alloc(&q->d_first, first.size()));
+        CVS_CUDA(dev_alloc(&q->d_w, wts.size()));
+        CVS_CUDA(cudaMemcpyAsync(q->d_first, first.data(), first.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        CVS_CUDA(cudaMemcpyAsync(q->d_w, wts.data(), wts.size() * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
+        CVS_CUDA(cudaStreamSynchronize(ctx->stream));                // the tables are pageable temporaries
+        sp = q.get();
+        ctx->scale_plans.push_back(std::move(q));
+    }
+    ScaleArgs a;
+    a.dst = (uint8_t *)dst; a.dst_pic_stride = dst_pic_stride; a.dst_stride = dst_stride; a.dw = dw; a.dh = dh;
+    for (int i = 0; i < 3; i++) {
+        const bool used = i == 0 || (format != CVS_PIX_BGRA && (i == 1 || format != CVS_PIX_NV12));
+        a.src[i] = used ? (const uint8_t *)src[i] : nullptr;
+        a.src_pic_stride[i] = used ? src_pic_stride[i] : 0;
+        a.src_linesize[i] = used ? src_linesize[i] : 0;
+    }
+    a.sw = sw; a.sh = sh; a.cw = cw; a.ch = ch; a.format = format; a.n = n;
+    a.fx = sp->d_first + sp->off_first[0]; a.fy = sp->d_first + sp->off_first[1];
+    a.cfx = sp->d_first + sp->off_first[2]; a.cfy = sp->d_first + sp->off_first[3];
+    a.wx = sp->d_w + sp->off_w[0]; a.wy = sp->d_w + sp->off_w[1]; a.cwx = sp->d_w + sp->off_w[2]; a.cwy = sp->d_w + sp->off_w[3];
+    a.tx = sp->taps[0]; a.ty = sp->taps[1]; a.ctx_ = sp->taps[2]; a.cty = sp->taps[3];
+    const dim3 block(dw < 256 ? ((dw + 31) / 32) * 32 : 256);
+    const dim3 grid((dw + block.x - 1) / block.x, dh, n);
+    k_scale_to_bgra<<<grid, block, 0, ctx->stream>>>(a);
     CVS_CUDA(cudaGetLastError());
     ctx->launches++;
     return CVS_OK;

@@ -5,10 +5,11 @@
 // MPEG range at :2100-2101).  SURVEY section 8f-1.  libswscale is a third-party dependency that is absent here (no
 // FFmpeg in this environment), so this is NOT pinned against the reference: the arithmetic below is the
 // published 15-bit fixed-point form of the BT.601 limited-range matrix that swscale's C path uses for RGB input
-// (coefficients (int)(c * 219/255 * 2^15 + 0.5) for luma and (int)(c * 224/255 * 2^15 + 0.5) for chroma), with
+// (coefficients c * 219/255 * 2^15 for luma and c * 224/255 * 2^15 for chroma, rounded to nearest), with
 // the chroma sample taken from the mean of the 2x1 (4:2:2) or 2x2 (4:2:0) pixels it covers, rounded to nearest.
-// swscale's bilinear chroma scaler and its chroma siting are not reproduced; tests/test_gpu_yuv_convert.py checks
-// this kernel bit for bit against the same formula in numpy and within +-1 of the real-valued BT.601 conversion.
+// swscale's bilinear chroma scaler and its chroma siting are not reproduced.  oracle/convert_oracle.c restates the
+// conversion independently of this file; tests/test_gpu_yuv_convert.py compares the two bit for bit and checks
+// both within +-1 of the real-valued BT.601 conversion.
 #ifndef CVS_YUV_CONVERT_CUH
 #define CVS_YUV_CONVERT_CUH
 
@@ -21,10 +22,12 @@ constexpr int kYuvShift = 15;
 struct YuvCoef { int ry, gy, by, ru, gu, bu, rv, gv, bv; };
 inline YuvCoef yuv_coef_bt601() {
     YuvCoef c;
-    const double s = (double)(1 << kYuvShift);
-    c.ry = (int)(0.299 * 219 / 255 * s + 0.5); c.gy = (int)(0.587 * 219 / 255 * s + 0.5); c.by = (int)(0.114 * 219 / 255 * s + 0.5);
-    c.ru = (int)(-0.169 * 224 / 255 * s + 0.5); c.gu = (int)(-0.331 * 224 / 255 * s + 0.5); c.bu = (int)(0.500 * 224 / 255 * s + 0.5);
-    c.rv = (int)(0.500 * 224 / 255 * s + 0.5); c.gv = (int)(-0.419 * 224 / 255 * s + 0.5); c.bv = (int)(-0.081 * 224 / 255 * s + 0.5);
+    // rounded to NEAREST, also the negative ones (so that the U and V rows each sum to zero: grey stays 128)
+    auto q = [](double v) { const double t = v * (double)(1 << kYuvShift); return (int)(t < 0 ? -(long long)(-t + 0.5) : (long long)(t + 0.5)); };
+    const double ys = 219.0 / 255.0, cs = 224.0 / 255.0;
+    c.ry = q(0.299 * ys); c.gy = q(0.587 * ys); c.by = q(0.114 * ys);
+    c.ru = q(-0.169 * cs); c.gu = q(-0.331 * cs); c.bu = q(0.500 * cs);
+    c.rv = q(0.500 * cs); c.gv = q(-0.419 * cs); c.bv = q(-0.081 * cs);
     return c;
 }
 

@@ -179,6 +179,24 @@ int  cvs_audio_create(cvs_audio **out, const cvs_params *p);          /* == "pre
 int  cvs_audio_process(cvs_audio *a, int16_t *audio, unsigned samples, unsigned long long *rng_pos /* in/out */);
 void cvs_audio_destroy(cvs_audio *a);
 
+/* ---- the step before the field loop: decoder picture -> BGRA at the output size ----------
+ * InputFile::frame_copy_scale() (ffmpeg_ntsc.cpp:544-613) runs every decoded picture through sws_scale() to BGRA at
+ * output_width x output_height (SWS_BILINEAR, :574-585) before composite_layer() reads it.  This entry point does
+ * that on the device for n pictures, asynchronously on the context's stream, so a decoder that leaves its pictures in
+ * device memory (NV12 from NVDEC, planar YUV) feeds the field loop without a CPU pass.
+ *   format     CVS_PIX_BGRA (src[0]), CVS_PIX_YUV420P / CVS_PIX_YUV422P (src[0..2] = Y, U, V; chroma planes are
+ *              ceil(sw/2) wide and ceil(sh/2) / sh high), CVS_PIX_NV12 (src[0] = Y, src[1] = interleaved UV)
+ *   dst        n BGRA pictures, dw x dh, rows dst_stride bytes (multiple of 4), pictures dst_pic_stride bytes apart
+ * NOT pinned against libswscale (absent here).  The resampler is specified in csrc/scale_convert.cuh (triangle kernel
+ * with 14-bit weights, centre-aligned, chroma co-sited horizontally and centred vertically for 4:2:0, 15-bit
+ * intermediate; BT.601 limited range -> full-range RGB, alpha 255) and restated independently in
+ * oracle/convert_oracle.c.  Shrinking by more than 16x per axis returns CVS_ERR_CAPACITY.
+ */
+enum { CVS_PIX_BGRA = 0, CVS_PIX_YUV420P = 1, CVS_PIX_YUV422P = 2, CVS_PIX_NV12 = 3 };
+int  cvs_scale_to_bgra_device(cvs_ctx *ctx, void *dst, int dst_stride, long long dst_pic_stride, int dw, int dh,
+                              const void *const src[3], const int src_linesize[3], const long long src_pic_stride[3],
+                              int sw, int sh, int format, int n);
+
 /* ---- the seam: exact analogue of the call at ffmpeg_ntsc.cpp:2229 ------------------------- */
 
 /*

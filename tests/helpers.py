@@ -296,3 +296,86 @@ def run_emu422(emu, p, w, h, n, pad=2, first=0, force_general=0, frames=None, rn
         pos += nd.value
         out.append((Y, U, V))
     return out, pos
+
+
+# ---- the reference's field loop with its audio step: one libc rand() stream for both ----------------
+
+def audio_due(frames_done, current, ntsc=True):
+    """tools/cvs_ntsc_raw.cpp's schedule: an audio packet that starts at or before field `current` is shown
+    (current * 1001 / 60000 s, PAL current / 50 s) runs before that field."""
+    num, den = (1001, 60000) if ntsc else (1, 50)
+    return frames_done * den <= current * num * 44100
+
+
+def reference_av_loop(ref, refaudio, oracle, p, frames, pcm, w, h, fields_per_frame, delay, packet, bob=True):
+    """The reference's main loop (ffmpeg_ntsc.cpp:2140-2284) on its OWN code: libref.so's composite_layer() and
+    librefaudio.so's composite_audio_process() both call libc rand(), i.e. they share one stream exactly as inside the
+    reference program.  Returns (pictures [nfields, h, w], processed pcm)."""
+    ref.ref_set_params(C.byref(p))
+    refaudio.refaudio_setup(C.byref(p))
+    ref.ref_srand(1)
+    ch = refaudio.refaudio_channels()
+    pcm = np.ascontiguousarray(pcm.copy())
+    done, total = 0, pcm.shape[0]
+    ring = [np.zeros((h, w), dtype=np.uint32) for _ in range(delay)]
+    out, idx = [], 0
+
+    def audio_packet():
+        nonlocal done
+        n = min(packet, total - done)
+        blk = np.ascontiguousarray(pcm[done:done + n])
+        refaudio.refaudio_process(blk.ctypes.data_as(C.c_void_p), C.c_uint(n))
+        pcm[done:done + n] = blk
+        done += n
+
+    for current in range(len(frames) * fields_per_frame):
+        while done < total and audio_due(done, current, bool(p.output_ntsc)):
+            audio_packet()
+        src = frames[current // fields_per_frame]
+        f = (current & 1) ^ 1
+        pic = ring[idx]
+        ref.ref_composite_layer(pic.ctypes.data_as(C.c_void_p), 4 * w, src.ctypes.data_as(C.c_void_p), 4 * w,
+                                w, h, 0, 0, f, C.c_ulonglong(current))
+        if bob:
+            oracle.oracle_bob(pic.ctypes.data_as(C.c_void_p), 4 * w, w, h, f)
+        out.append(pic.copy())
+        idx = (idx + 1) % delay
+    while done < total:
+        audio_packet()
+    assert ch == pcm.shape[1]
+    return np.stack(out), pcm
+
+
+# ---- the picture conversions either side of the path (oracle/convert_oracle.c; unpinned: libswscale is absent) ----
+
+def load_convert_oracle():
+    path = os.path.join(ORACLE_DIR, "libconvertoracle.so")
+    src = os.path.join(ORACLE_DIR, "convert_oracle.c")
+    if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+        subprocess.check_call(["make", "libconvertoracle.so"], cwd=ORACLE_DIR, stdout=subprocess.DEVNULL)
+    return C.CDLL(path)
+
+
+def oracle_bgra_to_yuv(bgra, v420):
+    """bgra: uint32[h, w] -> (y, u, v) uint8 planes."""
+    lib = load_convert_oracle()
+    h, w = bgra.shape
+    cw, ch = (w + 1) // 2, ((h + 1) // 2 if v420 else h)
+    src = np.ascontiguousarray(bgra)
+    y = np.zeros((h, w), np.uint8)
+    u = np.zeros((ch, cw), np.uint8)
+    v = np.zeros((ch, cw), np.uint8)
+    rc = lib.oracle_bgra_to_yuv(_ptr(y), w, _ptr(u), cw, _ptr(v), cw, _ptr(src), src.strides[0], w, h, 1 if v420 else 0)
+    assert rc == 0
+    return y, u, v
+
+
+def oracle_scale_to_bgra(planes, sw, sh, fmt, dw, dh):
+    """planes: list of uint8 arrays (BGRA: one [sh, sw*4]); -> uint32[dh, dw]."""
+    lib = load_convert_oracle()
+    ps = [np.ascontiguousarray(p) for p in planes] + [None] * (3 - len(planes))
+    dst = np.zeros((dh, dw), np.uint32)
+    rc = lib.oracle_scale_to_bgra(_ptr(dst), 4 * dw, dw, dh, *[(_ptr(p) if p is not None else None) for p in ps],
+                                  *[(p.strides[0] if p is not None else 0) for p in ps], sw, sh, fmt)
+    assert rc == 0, rc
+    return dst

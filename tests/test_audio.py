@@ -96,3 +96,45 @@ def test_audio_disabled_and_errors():
         assert np.array_equal(buf, keep)
     lib = cvs._lib.load()
     assert lib.cvs_audio_process(None, None, 0, None) == -1
+
+
+@pytest.mark.parametrize("argv", [["-vhs", "-vhs-hifi", "0"], ["-vhs", "-vhs-speed", "ep"], ["-audio-hiss", "-30"]])
+def test_interleaved_audio_and_video_share_one_stream(emu, oracle, ref, argv):
+    """The reference's loop alternates audio packets and fields on ONE libc rand() stream (ffmpeg_ntsc.cpp:2157-2163,
+    :2229).  Here the two engines are separate objects and the stream position is handed back and forth
+    (cvs_rng_tell -> cvs_audio_process(..., &pos) -> cvs_rng_seek): the result must be what the reference's own two
+    functions produce when they share libc's generator in one process."""
+    refaudio = helpers.load_refaudio()
+    if refaudio is None:
+        pytest.skip("oracle/_ref/librefaudio.so not built (needs /root/reference)")
+    w, h, nframes, fpf, packet = 96, 64, 3, 2, 300
+    p = helpers.params(*(["-width", str(w)] + argv))
+    frames = [helpers.stream_frame(w, h, k) for k in range(nframes)]
+    with Audio(params=p) as a:
+        ch = a.channels
+        pcm = helpers.audio_signal(5000, ch, 9)
+        want_pics, want_pcm = helpers.reference_av_loop(ref, refaudio, oracle, p, frames, pcm, w, h, fpf, 1, packet, bob=False)
+        got_pcm = np.ascontiguousarray(pcm.copy())
+        pos = helpers.C.c_ulonglong(0)
+        done = 0
+        dst = np.zeros((h, w), dtype=np.uint32)
+        for current in range(nframes * fpf):
+            while done < len(got_pcm) and helpers.audio_due(done, current):
+                n = min(packet, len(got_pcm) - done)
+                blk = np.ascontiguousarray(got_pcm[done:done + n])
+                pos.value = a.process(blk, pos.value)
+                got_pcm[done:done + n] = blk
+                done += n
+            src = frames[current // fpf]
+            rc = emu.emu_composite_layer_ex(helpers.C.byref(p), 1, helpers.C.byref(pos), dst.ctypes.data_as(helpers.C.c_void_p),
+                                            4 * w, src.ctypes.data_as(helpers.C.c_void_p), 4 * w, w, h, 0, 0, (current & 1) ^ 1,
+                                            helpers.C.c_ulonglong(current), 0, 0)
+            assert rc == 0
+            assert np.array_equal(dst, want_pics[current]), current
+        while done < len(got_pcm):
+            n = min(packet, len(got_pcm) - done)
+            blk = np.ascontiguousarray(got_pcm[done:done + n])
+            pos.value = a.process(blk, pos.value)
+            got_pcm[done:done + n] = blk
+            done += n
+    assert np.array_equal(got_pcm, want_pcm)

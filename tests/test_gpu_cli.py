@@ -57,3 +57,37 @@ def test_cli_rejects_what_the_reference_rejects():
     assert r.returncode == 1
     r = subprocess.run([TOOL, "-vhs"], capture_output=True)
     assert r.returncode == 1 and b"No input files specified" in r.stderr
+
+
+@pytest.mark.parametrize("w,h,delay,batch,argv", [
+    (160, 120, 1, 4, ["-vhs", "-vhs-hifi", "0"]),
+    (96, 64, 2, 3, ["-vhs", "-vhs-speed", "ep"]),
+])
+def test_cli_audio_and_video_share_the_rand_stream(oracle, ref, tmp_path, w, h, delay, batch, argv):
+    """`-audio-in/-audio-out`: the host alternates audio packets and fields like the reference's loop
+    (ffmpeg_ntsc.cpp:2157-2163, :2229) and hands the rand() position between the two engines; against the reference's
+    own composite_layer() and composite_audio_process() sharing libc's generator in one process.  Small audio packets
+    force batches to be cut where a packet is due."""
+    refaudio = helpers.load_refaudio()
+    if refaudio is None:
+        pytest.skip("oracle/_ref/librefaudio.so not built (needs /root/reference)")
+    nframes, fpf, packet = 5, 2, 500
+    p = helpers.params(*(["-width", str(w)] + argv))
+    import composite_video_simulator_b200 as cvs
+    ch = cvs._lib.load().cvs_audio_channels(C.byref(p))
+    frames = [helpers.stream_frame(w, h, k) for k in range(nframes)]
+    pcm = helpers.audio_signal(9000, ch, 4)
+    want_pics, want_pcm = helpers.reference_av_loop(ref, refaudio, oracle, p, frames, pcm, w, h, fpf, delay, packet)
+    inp, outp = str(tmp_path / "in.bgra"), str(tmp_path / "out.bgra")
+    ain, aout = str(tmp_path / "in.s16"), str(tmp_path / "out.s16")
+    np.stack(frames).tofile(inp)
+    pcm.tofile(ain)
+    cmd = [TOOL, "-i", inp, "-o", outp, "-width", str(w), "-height", str(h), "-d", str(delay), "-batch", str(batch),
+           "-fields-per-frame", str(fpf), "-double", "-audio-in", ain, "-audio-out", aout, "-audio-packet", str(packet)] + argv
+    subprocess.run(cmd, check=True, stderr=subprocess.DEVNULL)
+    got = np.fromfile(outp, dtype=np.uint32).reshape(-1, h, w)
+    got_pcm = np.fromfile(aout, dtype=np.int16).reshape(-1, ch)
+    assert got.shape == want_pics.shape
+    for k in range(len(want_pics)):
+        assert np.array_equal(got[k], want_pics[k]), k
+    assert np.array_equal(got_pcm, want_pcm)

@@ -1,0 +1,92 @@
+"""cvs_scale_to_bgra_device (the input side: InputFile::frame_copy_scale(), ffmpeg_ntsc.cpp:544-613):
+decoder picture -> BGRA at the output size on the device.  NOT pinned against libswscale (absent here); the kernel
+is compared bit for bit with oracle/convert_oracle.c, which restates the resampler from its specification
+(csrc/scale_convert.cuh header) independently of the kernel; tests/test_convert_oracle.py checks the oracle itself."""
+import numpy as np
+import pytest
+
+import helpers
+import composite_video_simulator_b200 as cvs
+
+pytestmark = pytest.mark.gpu
+
+BGRA, YUV420P, YUV422P, NV12 = 0, 1, 2, 3
+
+
+def source(w, h, fmt, seed):
+    rng = np.random.default_rng(seed)
+    if fmt == BGRA:
+        return [rng.integers(0, 256, size=(h, 4 * w), dtype=np.uint8)]
+    cw, ch = (w + 1) // 2, (h if fmt == YUV422P else (h + 1) // 2)
+    Y = rng.integers(0, 256, size=(h, w), dtype=np.uint8)
+    U = rng.integers(0, 256, size=(ch, cw), dtype=np.uint8)
+    V = rng.integers(0, 256, size=(ch, cw), dtype=np.uint8)
+    if fmt == NV12:
+        return [Y, np.ascontiguousarray(np.stack([U, V], axis=2).reshape(ch, 2 * cw))]
+    return [Y, U, V]
+
+
+@pytest.mark.parametrize("sw,sh,dw,dh", [(64, 48, 64, 48), (64, 48, 160, 120), (720, 480, 1920, 1080), (1920, 1080, 720, 480),
+                                         (101, 67, 33, 200), (352, 288, 720, 576), (33, 21, 7, 5)])
+@pytest.mark.parametrize("fmt", [BGRA, YUV420P, YUV422P, NV12])
+def test_scaler_matches_the_oracle(sw, sh, dw, dh, fmt):
+    import torch
+    planes = source(sw, sh, fmt, sw * 7 + dw + fmt)
+    want = helpers.oracle_scale_to_bgra(planes, sw, sh, fmt, dw, dh)
+    dev = [torch.from_numpy(p).cuda() for p in planes]
+    dst = torch.zeros((dh, dw), dtype=torch.int32, device="cuda")
+    with cvs.Engine([], max_w=dw, max_h=dh, max_batch=1) as eng:
+        eng.scale_to_bgra_device(dst, dw, dh, dev, [p.shape[1] for p in planes], sw, sh, fmt)
+        eng.synchronize()
+    assert np.array_equal(dst.cpu().numpy().view(np.uint32), want)
+
+
+def test_scaler_batches_strides_and_errors():
+    import torch
+    sw, sh, dw, dh, n = 90, 50, 120, 80, 3
+    pics = [source(sw, sh, YUV420P, 40 + k) for k in range(n)]
+    pad = 6
+    dev = []
+    for i in range(3):
+        arr = np.stack([np.pad(p[i], ((0, 0), (0, pad))) for p in pics])           # padded rows, pictures back to back
+        dev.append(torch.from_numpy(arr).cuda())
+    dst = torch.full((n, dh, dw + 4), 0x55, dtype=torch.int32, device="cuda")
+    with cvs.Engine([], max_w=dw, max_h=dh, max_batch=1) as eng:
+        eng.scale_to_bgra_device(dst, dw, dh, dev, [d.shape[2] for d in dev], sw, sh, YUV420P, n=n, dst_stride=4 * (dw + 4),
+                                 dst_pic_stride=4 * (dw + 4) * dh, pic_strides=[d.shape[1] * d.shape[2] for d in dev])
+        eng.synchronize()
+        out = dst.cpu().numpy().view(np.uint32)
+        for k in range(n):
+            assert np.array_equal(out[k][:, :dw], helpers.oracle_scale_to_bgra(pics[k], sw, sh, YUV420P, dw, dh)), k
+            assert (out[k][:, dw:] == 0x55).all()                                     # padding untouched
+        with pytest.raises(cvs.CvsError) as e:
+            eng.scale_to_bgra_device(dst, dw, dh, dev, [sw - 1, 45, 45], sw, sh, YUV420P)   # luma rows shorter than sw
+        assert e.value.status == -1
+        with pytest.raises(cvs.CvsError) as e:
+            eng.scale_to_bgra_device(dst, 4, 2, dev, [d.shape[2] for d in dev], sw, sh, YUV420P)   # > 16x reduction
+        assert e.value.status == -5
+
+
+def test_scaled_pictures_feed_the_field_loop(oracle):
+    """decode -> scale -> composite_layer, all on the device: the scaler's BGRA goes straight into
+    cvs_composite_fields_device and the result equals the oracle run on the oracle-scaled picture."""
+    import torch
+    sw, sh, w, h, n = 176, 144, 320, 240, 2
+    p = helpers.params("-vhs")
+    srcs = [source(sw, sh, NV12, 70 + k) for k in range(n)]
+    scaled = [helpers.oracle_scale_to_bgra(s, sw, sh, NV12, w, h) for s in srcs]
+    want, _ = helpers.run_oracle(oracle, p, lambda k: scaled[k], n, w, h)
+    Y = torch.from_numpy(np.stack([s[0] for s in srcs])).cuda()
+    UV = torch.from_numpy(np.stack([s[1] for s in srcs])).cuda()
+    bgra = torch.zeros((n, h, w), dtype=torch.int32, device="cuda")
+    out = torch.zeros((n, h, w), dtype=torch.int32, device="cuda")
+    with cvs.Engine(params=p, max_w=w, max_h=h, max_batch=n) as eng:
+        eng.set_precision(True)
+        eng.scale_to_bgra_device(bgra, w, h, [Y, UV], [Y.shape[2], UV.shape[2]], sw, sh, NV12, n=n)
+        eng.composite_fields_device(out, bgra, n, h, w, 0)
+        eng.synchronize()
+    got = np.zeros((h, w), dtype=np.uint32)
+    o = out.cpu().numpy().view(np.uint32)
+    got[1::2] = o[0][1::2]
+    got[0::2] = o[1][0::2]
+    assert np.array_equal(got, want)

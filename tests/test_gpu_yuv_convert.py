@@ -1,6 +1,7 @@
 """cvs_bgra_to_yuv_device: BGRA -> planar YUV 4:2:0 / 4:2:2, BT.601 limited range.
-NOT pinned against libswscale (absent here; include/cvs_ntsc.h says so): checked bit for bit against the same
-published fixed-point formula in numpy, and within +-1 of the real-valued BT.601 conversion."""
+NOT pinned against libswscale (absent here; include/cvs_ntsc.h says so): checked bit for bit against
+oracle/convert_oracle.c (written from the specification, not from the kernel), and both within +-1 of the real-valued
+BT.601 conversion; grey must stay exactly grey (the chroma rows of the matrix sum to zero)."""
 import numpy as np
 import pytest
 
@@ -8,30 +9,10 @@ import composite_video_simulator_b200 as cvs
 
 pytestmark = pytest.mark.gpu
 
-S = 15
-RY, GY, BY = int(0.299 * 219 / 255 * 2 ** S + 0.5), int(0.587 * 219 / 255 * 2 ** S + 0.5), int(0.114 * 219 / 255 * 2 ** S + 0.5)
-RU, GU, BU = int(-0.169 * 224 / 255 * 2 ** S + 0.5), int(-0.331 * 224 / 255 * 2 ** S + 0.5), int(0.500 * 224 / 255 * 2 ** S + 0.5)
-RV, GV, BV = int(0.500 * 224 / 255 * 2 ** S + 0.5), int(-0.419 * 224 / 255 * 2 ** S + 0.5), int(-0.081 * 224 / 255 * 2 ** S + 0.5)
-
-
 def formula(bgra, v420):
-    """The kernel's arithmetic restated with numpy integers (csrc/yuv_convert.cuh)."""
-    h, w = bgra.shape
-    b, g, r = [((bgra >> s) & 0xFF).astype(np.int64) for s in (0, 8, 16)]
-    y = (RY * r + GY * g + BY * b + (16 << S) + (1 << (S - 1))) >> S
-    wp, hp = w + (w & 1), h + ((h & 1) if v420 else 0)
-    pad = lambda a: np.pad(a, ((0, hp - h), (0, wp - w)), mode="edge")
-    r, g, b = pad(r), pad(g), pad(b)
-    if v420:
-        sm = lambda a: a[0::2, 0::2] + a[0::2, 1::2] + a[1::2, 0::2] + a[1::2, 1::2]
-        n, sh = 4, S + 2
-    else:
-        sm = lambda a: a[:, 0::2] + a[:, 1::2]
-        n, sh = 2, S + 1
-    sr, sg, sb = sm(r), sm(g), sm(b)
-    u = (RU * sr + GU * sg + BU * sb + ((128 * n) << S) + (1 << (sh - 1))) >> sh
-    v = (RV * sr + GV * sg + BV * sb + ((128 * n) << S) + (1 << (sh - 1))) >> sh
-    return y.astype(np.uint8), u.astype(np.uint8), v.astype(np.uint8)
+    """oracle/convert_oracle.c: the conversion restated from its specification, independently of the kernel."""
+    import helpers
+    return helpers.oracle_bgra_to_yuv(bgra, v420)
 
 
 def real_bt601(bgra, v420):
@@ -74,6 +55,22 @@ def test_bgra_to_yuv_matches_the_formula(w, h, n, v420):
         assert np.abs(wy - fy).max() <= 1.0 and np.abs(wu - fu).max() <= 1.0 and np.abs(wv - fv).max() <= 1.0
     # limited range: black -> (16, 128, 128), white -> (235, 128, 128)
     assert int(y[0, 0, 0]) == 16 and int(y[0, 0, 1]) == 235
+
+
+def test_grey_stays_grey():
+    """Every grey level maps to U = V = 128 exactly: the 15-bit chroma coefficients are rounded to nearest (also the
+    negative ones), so each chroma row of the matrix sums to zero."""
+    import torch
+    w, h = 256, 4
+    src = np.broadcast_to((np.arange(w, dtype=np.uint32) * 0x010101)[None, :], (h, w)).copy()
+    d = torch.from_numpy(src.view(np.int32)).cuda()
+    y = torch.zeros((h, w), dtype=torch.uint8, device="cuda")
+    u = torch.zeros((h // 2, w // 2), dtype=torch.uint8, device="cuda")
+    v = torch.zeros_like(u)
+    with cvs.Engine([], max_w=w, max_h=h, max_batch=1) as eng:
+        eng.bgra_to_yuv_device(y, u, v, d, w, h, 1, fmt420=True)
+        eng.synchronize()
+    assert (u.cpu().numpy() == 128).all() and (v.cpu().numpy() == 128).all()
 
 
 def test_bgra_to_yuv_padded_strides_and_errors():
