@@ -471,32 +471,28 @@ template <> struct Num<float> {
         Q = trunc_mul_pos(fma_(0.48f, rd, mul(0.41f, bd)), 256.0f);
 #endif
     }
-    // one colour channel of YIQ_to_RGB (:1387-1395): trunc((Y + ci I + cq Q) / 256) clamped to 0..255.
-    // Device: the operands carry an extra 2^-16 (exact: powers of two), so the last FFMA can saturate to
-    // [0, 1] for free (.SAT) = the value clamped to [0, 256]; the truncation is one FFMA.RZ against
-    // M = 1.5*2^23, whose low bits are then the integer 0..256, and one integer min finishes the clamp.
-    static CVS_HD uint32_t chan_(float Yp, float ci, float I, float cq, float Q) {
-#if defined(__CUDA_ARCH__)
-        const float u = __saturatef(__fmaf_rn(cq, Q, __fmaf_rn(ci, I, Yp)));
-        return min(__float_as_uint(__fmaf_rz(u, 256.0f, kMagic)), 0x4B4000FFu);
-#else
-        const float v = fma_(cq, Q, fma_(ci, I, Yp)) * 256.0f;   // (exact rescale of the device's 2^-16 operands)
-        const int k = (v < 0.0f) ? 0 : (v > 255.0f ? 255 : (int)v);
-        return 0x4B400000u + (uint32_t)k;
-#endif
-    }
+    // YIQ_to_RGB (:1385-1396) + the store's packing (:1914): trunc((Y + ci I + cq Q) / 256) clamped to 0..255 per
+    // channel, alpha 0.  The operands carry the 1/256 (exact: a power of two), so each channel is two FFMAs, and
+    // on sm_100 the truncation, the clamp AND the byte packing are the packed conversion F2IP.U8.F32.TRUNC
+    // (PTX cvt.rzi.u8.f32 / cvt.pack.sat.u8.s32.b32 on a float-to-int pair): two instructions per pixel where the
+    // round-1 kernel needed a saturating FFMA, an FFMA.RZ, an integer min per channel and two PRMTs.
     static CVS_HD uint32_t yiq2bgra(float Y, float I, float Q) {
-        constexpr float k = 1.0f / 65536.0f;
+        constexpr float k = 1.0f / 256.0f;
         const float Yp = mul(Y, k);
-        const uint32_t r = chan_(Yp, 0.956f * k, I, 0.621f * k, Q);
-        const uint32_t g = chan_(Yp, -0.272f * k, I, -0.647f * k, Q);
-        const uint32_t b = chan_(Yp, -1.106f * k, I, 1.703f * k, Q);
+        const float r = fma_(0.621f * k, Q, fma_(0.956f * k, I, Yp));
+        const float g = fma_(-0.647f * k, Q, fma_(-0.272f * k, I, Yp));
+        const float b = fma_(1.703f * k, Q, fma_(-1.106f * k, I, Yp));
 #if defined(__CUDA_ARCH__)
-        return __byte_perm(__byte_perm(b, g, 0x7740), r, 0x5410);   // r byte 1 is 0x00: alpha = 0
+        uint32_t hi, px;
+        asm("cvt.rzi.u8.f32 %0, %1;" : "=r"(hi) : "f"(r));                       // 0x000000RR
+        asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;"                             // (hi << 16) | G << 8 | B
+            : "=r"(px) : "r"(__float2int_rz(g)), "r"(__float2int_rz(b)), "r"(hi));
+        return px;
 #else
-        return ((r & 0xFF) << 16) | ((g & 0xFF) << 8) | (b & 0xFF);
+        return ((uint32_t)chan8(r) << 16) | ((uint32_t)chan8(g) << 8) | (uint32_t)chan8(b);
 #endif
     }
+    static CVS_HD int chan8(float v) { return (v < 0.0f) ? 0 : (v > 255.0f ? 255 : (int)v); }
     static CVS_HD float rot_a(float u, float c, float v, float s) { return trunc_(fma_(u, c, -mul(v, s))); }
     static CVS_HD float rot_b(float u, float s, float v, float c) { return trunc_(fma_(u, s, mul(v, c))); }
     static CVS_HD float boost(float s, float hp, float g) { return trunc_(fma_(hp, g, s)); }

@@ -40,3 +40,27 @@ with cvs.Engine([], max_w=w, max_h=h, max_batch=1) as eng:
         print(json.dumps({"kernel": "k_bgra_to_yuv", "format": "yuv420p" if v420 else "yuv422p", "frames_per_s": n / (ms / 1e3),
                           "ms_per_launch": ms, "pictures_per_launch": n, "algorithmic_GBps": gbs,
                           "frac_of_measured_hbm_peak": (gbs / peak) if peak else None}))
+
+# the input side: cvs_scale_to_bgra_device (frame_copy_scale), NV12 720x480 -> BGRA 1920x1080 and 1080p -> 1080p
+with cvs.Engine([], max_w=w, max_h=h, max_batch=1) as eng:
+    st = torch.cuda.Stream()
+    eng.set_stream(st.cuda_stream)
+    for sw, sh in ((720, 480), (1920, 1080), (3840, 2160)):
+        ns = 64
+        Y = torch.randint(0, 256, (ns, sh, sw), dtype=torch.uint8, device="cuda")
+        UV = torch.randint(0, 256, (ns, sh // 2, sw), dtype=torch.uint8, device="cuda")
+        dst = torch.empty((ns, h, w), dtype=torch.int32, device="cuda")
+        with torch.cuda.stream(st):
+            for _ in range(3):
+                eng.scale_to_bgra_device(dst, w, h, [Y, UV], [sw, sw], sw, sh, 3, n=ns)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            for _ in range(steps):
+                eng.scale_to_bgra_device(dst, w, h, [Y, UV], [sw, sw], sw, sh, 3, n=ns)
+            e1.record(st)
+            e1.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        bytes_ = ns * (sw * sh * 1.5 + w * h * 4.0)
+        gbs = bytes_ / (ms / 1e3) / 1e9
+        print(json.dumps({"kernel": "k_scale_to_bgra", "format": "nv12 %dx%d -> bgra %dx%d" % (sw, sh, w, h),
+                          "frames_per_s": ns / (ms / 1e3), "algorithmic_GBps": gbs, "frac_of_measured_hbm_peak": gbs / peak if peak else None}))
