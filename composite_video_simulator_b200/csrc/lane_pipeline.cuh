@@ -58,13 +58,24 @@ namespace cvs {
 // The conversion (XU) pipe runs at 1/8 of the FP32 rate, so the hot loop keeps clear of it (PRMT / directed-rounding
 // tricks instead of I2F / F2I / FRND) -- except for a few conversions that take work off the FMA pipe, which is the
 // busiest unit of this kernel.  Measured on B200, 1080p VHS-SP, fields/s (profiles/ab_variants_r1.txt):
-//   unpack by PRMT+FADD 121.4 k; unpack by I2F.U8 120.8 k; + CVS_XU_TRUNC=1 126.2 k; CVS_XU_TRUNC=2 125.0 k
+//   round 1: unpack by PRMT+FADD 121.4 k; unpack by I2F.U8 120.8 k; + CVS_XU_TRUNC=1 126.2 k; CVS_XU_TRUNC=2 125.0 k
+//   round 2 (profiles/ab_variants_r2.txt): TRUNC=1 141.1 k; TRUNC=3 145.0 k; + PAIR_TRUNC=1 148.7 k
 #ifndef CVS_XU_UNPACK
 #define CVS_XU_UNPACK 1          // BGRA bytes -> float by I2F.U8 (3 per pixel) instead of PRMT + FADD
 #endif
 #ifndef CVS_XU_TRUNC
-#define CVS_XU_TRUNC 1           // 1: trunc() of a ready fp32 value by F2I.TRUNC + I2FP instead of LOP3 + FADD.RZ + FADD;
-                                 // 2: also trunc(x * 2^k) (box filter / 4, Y * 256) by FMUL + F2I.TRUNC + I2FP
+#define CVS_XU_TRUNC 3           // 1: trunc() of a ready fp32 value by F2I.TRUNC + I2FP instead of LOP3 + FADD.RZ + FADD;
+                                 // 2: also trunc(x * 2^k) (box filter / 4) by FMUL + F2I.TRUNC + I2FP;
+                                 // 3: both by FRND.TRUNC, one conversion-pipe instruction (round 2: with ~20 % fewer
+                                 //    instructions per step than in round 1 the conversion pipe has the room)
+#endif
+#ifndef CVS_XU_PAIR_TRUNC
+#define CVS_XU_PAIR_TRUNC 1      // truncation of ready (I, Q) pairs by two FRND.TRUNC instead of the packed magic-number add
+#endif
+#ifndef CVS_RNG_PAIRED
+#define CVS_RNG_PAIRED 0         // generator ring as 64-bit pairs (LaneRngP): half the LDS / STS, but the raw words of a
+                                 // group are live together -- the register pressure costs more than the 12 instructions
+                                 // save (profiles/ab_variants_r2.txt: VHS-EP 123 k against 138 k fields/s)
 #endif
 #ifndef CVS_MERGED_LUMA
 #define CVS_MERGED_LUMA 1        // fp32 VHS luma chain on scaled states with merged boost / sharpen (Num<float>::vhs_luma)
@@ -104,11 +115,12 @@ enum : uint32_t {
     RF_HEADSW_INLINE = 1u << 2,   // row is rotated by a small right shift with zero fill: delayed in-kernel
 };
 #ifndef CVS_HS_RING
-#define CVS_HS_RING 48
+#define CVS_HS_RING 44
 #endif
-constexpr int kHsRing = CVS_HS_RING;               // per-lane delay ring of the in-kernel head switch (a multiple of kT; not a
-                                          // power of two on purpose: 3 CTAs/SM must fit in shared memory; the default
-                                          // 1080p shift is -22 +-4 px of jitter; bigger shifts take the pre-pass)
+constexpr int kHsRing = CVS_HS_RING;      // per-lane delay ring of the in-kernel head switch: a multiple of kT; not a power
+                                          // of two on purpose (3 CTAs/SM must fit in shared memory).  The default 1080p
+                                          // shift is -22 +-4 px of jitter; bigger shifts take the pre-pass.
+constexpr int kHsSlots = kHsRing + kT;    // + one block: block 0 is stored twice so that a read of kT samples never wraps
 constexpr int kHsMaxDelay = kHsRing - kT; // largest shift the ring can express
 
 // ---- pairs --------------------------------------------------------------------------------------
@@ -281,7 +293,9 @@ template <> struct Num<float> {
     }
     // trunc(x) for an fp32 value
     static CVS_HD float trunc_(float a) {
-#if defined(__CUDA_ARCH__) && CVS_XU_TRUNC
+#if defined(__CUDA_ARCH__) && CVS_XU_TRUNC == 3
+        return truncf(a);                                // FRND.TRUNC: one instruction on the conversion pipe
+#elif defined(__CUDA_ARCH__) && CVS_XU_TRUNC
         return (float)__float2int_rz(a);                 // F2I.TRUNC (conversion pipe) + I2FP (ALU): |a| < 2^24
 #elif defined(__CUDA_ARCH__)
         const float ms = __uint_as_float((__float_as_uint(a) & 0x80000000u) | 0x4B400000u);
@@ -323,7 +337,9 @@ template <> struct Num<float> {
     }
     // trunc(a * b) for b a power of two (the product is exact in fp32)
     static CVS_HD float trunc_pow2(float a, float b) {
-#if defined(__CUDA_ARCH__) && CVS_XU_TRUNC >= 2
+#if defined(__CUDA_ARCH__) && CVS_XU_TRUNC == 3
+        return truncf(__fmul_rn(a, b));                   // FMUL + FRND.TRUNC
+#elif defined(__CUDA_ARCH__) && CVS_XU_TRUNC >= 2
         return (float)__float2int_rz(__fmul_rn(a, b));    // FMUL + F2I.TRUNC + I2FP: one FMA-pipe slot instead of two
 #else
         return trunc_mul_pos(a, b);
@@ -360,6 +376,18 @@ template <> struct Num<float> {
                            __uint_as_float((__float_as_uint(a.y) & 0x80000000u) | 0x4B400000u));
     }
 #endif
+#if defined(__CUDA_ARCH__)
+    // trunc of both components of a ready pair: packed directed-rounding add (4 instructions, FMA + ALU pipes), or
+    // two FRND.TRUNC on the conversion pipe (CVS_XU_PAIR_TRUNC: A/B switch)
+    static __device__ __forceinline__ float2 trunc2_ready(float2 r) {
+#if CVS_XU_PAIR_TRUNC
+        return make_float2(truncf(r.x), truncf(r.y));
+#else
+        const float2 ms = msign2(r);
+        return __fadd2_rn(__fadd2_rz(r, ms), make_float2(-ms.x, -ms.y));
+#endif
+    }
+#endif
     static CVS_HD void cascade_reset2(P p[3], float v) { (void)v; p[0] = mk2(0.0f, 0.0f); p[1] = p[0]; p[2] = p[0]; }   // chroma resets to 0
     static CVS_HD P cascade3_trunc2(P p[3], P s, P /*a*/, P b, P c) {
 #if defined(__CUDA_ARCH__)
@@ -368,6 +396,7 @@ template <> struct Num<float> {
         float2 q1 = __ffma2_rn(bb, f2(p[1]), q0);
         float2 q2 = __ffma2_rn(bb, f2(p[2]), q1);
         p[0] = pp(q0); p[1] = pp(q1); p[2] = pp(q2);
+        // (FMUL2 + two FRND.TRUNC here as well measured slower: 145.6 k against 148.7 k fields/s, profiles/ab_variants_r2.txt)
         const float2 ms = msign2(q2);                               // sign(q2 * c) == sign(q2): c > 0
         return pp(__fadd2_rn(__ffma2_rz(q2, f2(c), ms), make_float2(-ms.x, -ms.y)));
 #else
@@ -412,8 +441,7 @@ template <> struct Num<float> {
 #if defined(__CUDA_ARCH__)
         const float2 t = __fmul2_rn(make_float2(uv.y, uv.y), make_float2(ns, c));
         const float2 r = __ffma2_rn(make_float2(uv.x, uv.x), make_float2(c, s), t);
-        const float2 ms = msign2(r);
-        return pp(__fadd2_rn(__fadd2_rz(r, ms), make_float2(-ms.x, -ms.y)));
+        return pp(trunc2_ready(r));
 #else
         (void)ns;
         return mk2(rot_a(uv.x, c, uv.y, s), rot_b(uv.x, s, uv.y, c));
@@ -438,8 +466,7 @@ template <> struct Num<float> {
         float2 iq = __fmul2_rn(f2(K.k_iq_r), make_float2(rf, rf));
         iq = __ffma2_rn(f2(K.k_iq_g), make_float2(gf, gf), iq);
         iq = __ffma2_rn(f2(K.k_iq_b), make_float2(bf, bf), iq);
-        const float2 ms = msign2(iq);
-        IQ = pp(__fadd2_rn(__fadd2_rz(iq, ms), make_float2(-ms.x, -ms.y)));
+        IQ = pp(trunc2_ready(iq));
 #else
         const float bd = sub(bf, dY), rd = sub(rf, dY);
         const float2 t = __fmul2_rn(make_float2(-0.27f, 0.41f), make_float2(bd, bd));
@@ -545,6 +572,7 @@ struct LaneRng {
         for (int i = 0; i < 31; i++) ring[((n0 - 31 + i) & (kRngSlots - 1)) * stride] = hist[i];
         l1 = hist[30]; l2 = hist[29]; l3 = hist[28];
     }
+    CVS_HD void init(uint32_t *base, int lane, int stride_, const uint32_t hist[31], uint32_t n0) { init(base + lane, stride_, hist, n0); }
     // q[n] = q[n-31] + q[n-3].  The caller supplies n (same for every lane of a warp, so the slot
     // arithmetic is warp-uniform); draws must be requested in increasing n without gaps.
     CVS_HD uint32_t next_raw(uint32_t n) {
@@ -564,6 +592,70 @@ struct LaneRng {
         grp[i * stride] = v;
         l3 = l2; l2 = l1; l1 = v;
         return v;
+    }
+};
+
+// The same generator with the ring stored as PAIRS of consecutive words (k_fields): pair p of a lane is the 64-bit
+// word at ((p * stride) + lane) * 2, so a warp's 64-bit access covers 256 contiguous bytes (conflict-free) and a
+// group of COUNT consecutive draws costs COUNT/2 loads and COUNT/2 stores instead of COUNT each.  The long-lag tap
+// of draw n is slot (n + 1) & 31, i.e. the taps of an aligned group straddle the pair grid by one word: the first
+// tap is the high word of the group's own first pair -- carried over from the previous group's last load -- and the
+// last tap is the low word of the NEXT group's first pair, whose high word becomes the new carry.
+struct LaneRngP {
+    uint32_t *ring;      // already offset by 2 * lane words
+    int stride;          // lanes sharing the buffer
+    uint32_t l1, l2, l3; // q[n-1], q[n-2], q[n-3]
+    uint32_t carry;      // the word at slot (n + 1) & 31 for the next group's first draw n
+
+    CVS_HD uint32_t &word(uint32_t slot) const { return ring[(size_t)((slot & (kRngSlots - 1)) >> 1) * 2 * stride + (slot & 1)]; }
+    CVS_HD void init(uint32_t *base, int lane, int stride_, const uint32_t hist[31], uint32_t n0) {
+        ring = base + 2 * lane;
+        stride = stride_;
+        for (int i = 0; i < 31; i++) word(n0 - 31 + (uint32_t)i) = hist[i];
+        l1 = hist[30]; l2 = hist[29]; l3 = hist[28];
+        carry = 0;
+    }
+    CVS_HD uint32_t next_raw(uint32_t n) {               // one draw, any n (warm-up)
+        const uint32_t v = word(n + 1) + l3;
+        word(n) = v;
+        l3 = l2; l2 = l1; l1 = v;
+        return v;
+    }
+    CVS_HD void begin_groups(uint32_t n_first) { carry = word(n_first + 1); }
+    // COUNT consecutive draws from n_first (a multiple of COUNT; groups must be drawn in order without gaps)
+    template <int COUNT>
+    CVS_HD void draw_group(uint32_t n_first, uint32_t out[COUNT]) {
+        static_assert(COUNT % 2 == 0 && kRngSlots % COUNT == 0, "aligned groups of pairs");
+        uint32_t *grp = ring + (size_t)((n_first & (kRngSlots - 1)) >> 1) * 2 * stride;
+        const uint32_t *nxt = ring + (size_t)(((n_first + COUNT) & (kRngSlots - 1)) >> 1) * 2 * stride;
+        uint32_t tap[COUNT];
+        tap[0] = carry;
+        CVS_UNROLL
+        for (int p = 1; p < COUNT / 2; p++) ld2(grp + (size_t)p * 2 * stride, tap[2 * p - 1], tap[2 * p]);
+        ld2(nxt, tap[COUNT - 1], carry);
+        CVS_UNROLL
+        for (int i = 0; i < COUNT; i++) {
+            const uint32_t v = tap[i] + l3;
+            l3 = l2; l2 = l1; l1 = v;
+            out[i] = v;
+        }
+        CVS_UNROLL
+        for (int p = 0; p < COUNT / 2; p++) st2(grp + (size_t)p * 2 * stride, out[2 * p], out[2 * p + 1]);
+    }
+    static CVS_HD void ld2(const uint32_t *p, uint32_t &a, uint32_t &b) {
+#if defined(__CUDA_ARCH__)
+        const uint2 t = *reinterpret_cast<const uint2 *>(p);
+        a = t.x; b = t.y;
+#else
+        a = p[0]; b = p[1];
+#endif
+    }
+    static CVS_HD void st2(uint32_t *p, uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+        *reinterpret_cast<uint2 *>(p) = make_uint2(a, b);
+#else
+        p[0] = a; p[1] = b;
+#endif
     }
 };
 
@@ -672,7 +764,12 @@ struct Lane {
     V2<R> IQtail[OD], oOIQtail[OD];  // ... of the raw (I4, Q4) and of the cascade outputs
     uint32_t outprev[kT - OD > 0 ? kT - OD : 1];   // packed pixels of positions [kT(k-1), kT k - OD)
 
-    LaneRng rngL, rngC;
+#if CVS_RNG_PAIRED
+    typedef LaneRngP Gen;
+#else
+    typedef LaneRng Gen;
+#endif
+    Gen rngL, rngC;
     // (fast noise mode keeps its two generator states in rngL.l1 / rngC.l1: the exact generators are idle then)
     R *tailU, *tailV;                // per-lane stash (kTailSlots each), stride tail_stride
     int tail_stride;
@@ -900,8 +997,15 @@ struct Pipeline {
         // A2: composite block B(s-1)
         if (!EDGE || s >= 1) {
             const bool in_lp = !GEN || (K.flags & F_IN_LP);
+#if CVS_RNG_PAIRED
+            uint32_t rawL[kT];                                                       // luma draws of B(s-1)
+            if (!nfast && (!GEN || K.vnoise != 0)) ln.rngL.template draw_group<kT>(kRngBase + (uint32_t)(p - kT), rawL);
+#define CVS_RAW_L(j) rawL[j]
+#else
             uint32_t *gL = ln.rngL.group_ptr(kRngBase + (uint32_t)(p - kT));          // luma draws of B(s-1)
             const uint32_t *gLn = ln.rngL.group_ptr(kRngBase + (uint32_t)p);
+#define CVS_RAW_L(j) ln.rngL.next_in_group(gL, gLn, j, kT)
+#endif
             CVS_UNROLL
             for (int j = 0; j < kT; j++) {
                 const int x = p - kT + j;
@@ -928,7 +1032,7 @@ struct Pipeline {
                     if (!GEN || K.vnoise != 0) {                                                     // :1631-1644
                         c = N::add(c, (R)ln.nY);
                         if (nfast) ln.nY = noise_draw_fast(ln.nY, ln.rngL.l1, (uint32_t)(2 * K.vnoise + 1), K.vnoise);
-                        else ln.nY = noise_draw(ln.nY, ln.rngL.next_in_group(gL, gLn, j, kT), (uint32_t)(2 * K.vnoise + 1), K.vmagic, K.vshift, K.vnoise);
+                        else ln.nY = noise_draw(ln.nY, CVS_RAW_L(j), (uint32_t)(2 * K.vnoise + 1), K.vmagic, K.vshift, K.vnoise);
                     }
                     if (EDGE && hs_row && (rc.rflags & RF_HEADSW)) c = (R)hs_row[x];                 // :1646-1713
                 }
@@ -980,8 +1084,15 @@ struct Pipeline {
 
         const int x0 = k * kT;
         if (GEN ? (K.cnoise != 0) : VHS) {                         // :1718-1735
-            uint32_t *gC = ln.rngC.group_ptr(kRngBase + 2u * (uint32_t)x0);           // 16 chroma draws of B(s-2)
+#if CVS_RNG_PAIRED
+            uint32_t rawC[2 * kT];                                                   // chroma draws of B(kB): U, V per pixel
+            if (!nfast) ln.rngC.template draw_group<2 * kT>(kRngBase + 2u * (uint32_t)x0, rawC);
+#define CVS_RAW_C(i) rawC[i]
+#else
+            uint32_t *gC = ln.rngC.group_ptr(kRngBase + 2u * (uint32_t)x0);           // chroma draws of B(kB): U, V per pixel
             const uint32_t *gCn = ln.rngC.group_ptr(kRngBase + 2u * (uint32_t)(x0 + kT));
+#define CVS_RAW_C(i) ln.rngC.next_in_group(gC, gCn, i, 2 * kT)
+#endif
             CVS_UNROLL
             for (int j = 0; j < kT; j++) {
                 if (!EDGE || x0 + j < w) {
@@ -991,8 +1102,8 @@ struct Pipeline {
                         ln.nU = noise_draw_fast(ln.nU, ln.rngC.l1, m, K.cnoise);
                         ln.nV = noise_draw_fast(ln.nV, ln.rngC.l1, m, K.cnoise);
                     } else {
-                        ln.nU = noise_draw(ln.nU, ln.rngC.next_in_group(gC, gCn, 2 * j, 2 * kT), m, K.cmagic, K.cshift, K.cnoise);
-                        ln.nV = noise_draw(ln.nV, ln.rngC.next_in_group(gC, gCn, 2 * j + 1, 2 * kT), m, K.cmagic, K.cshift, K.cnoise);
+                        ln.nU = noise_draw(ln.nU, CVS_RAW_C(2 * j), m, K.cmagic, K.cshift, K.cnoise);
+                        ln.nV = noise_draw(ln.nV, CVS_RAW_C(2 * j + 1), m, K.cmagic, K.cshift, K.cnoise);
                     }
                 }
             }
@@ -1171,20 +1282,29 @@ CVS_HD void headswitch_substitute(const RowConst<R> &rc, const int32_t *hs_row, 
 
 // In-kernel head switch for the common case (ffmpeg_ntsc.cpp:1683-1700 with a small negative shift
 // whose wrapped-in part is entirely zero padding): Y'[x] = Y[x - d] for x >= d, 0 below.  The finished
-// composite block B(k) goes through a per-lane ring (ring[(x & 63) * stride], already offset by the
-// lane) and comes back delayed by the lane's own d (0 for rows that are not rotated).
+// composite block B(k) goes through a per-lane ring (ring[slot * stride], already offset by the lane) and
+// comes back delayed by the lane's own d (0 for rows that are not rotated).  The ring holds kHsRing samples
+// plus a second copy of its first block behind the last one, so the kT samples a lane reads are always
+// contiguous: one wrap test per lane and step instead of one modulo per sample (the block index is
+// warp-uniform, so the write position is uniform arithmetic).
 template <typename R>
 CVS_HD void headswitch_delay_block(R *ring, int stride, int k, int w, int d, R C[kT]) {
     static_assert(kHsRing % kT == 0, "a block never wraps inside the ring");
+    constexpr int kBlocks = kHsRing / kT;
     const int x0 = k * kT;
-    const int b0 = x0 % kHsRing;
+    const int b0 = (k % kBlocks) * kT;                  // k >= 0 at every call site
     CVS_UNROLL
     for (int j = 0; j < kT; j++) ring[(b0 + j) * stride] = C[j];
+    if (b0 == 0) {
+        CVS_UNROLL
+        for (int j = 0; j < kT; j++) ring[(kHsRing + j) * stride] = C[j];
+    }
+    int r0 = b0 - d;                                    // 0 <= d <= kHsMaxDelay < kHsRing: one correction
+    r0 += (r0 < 0) ? kHsRing : 0;
     CVS_UNROLL
     for (int j = 0; j < kT; j++) {
-        const int xs = x0 + j - d;
-        const R v = ring[(((xs % kHsRing) + kHsRing) % kHsRing) * stride];
-        C[j] = (xs >= 0 && x0 + j < w) ? v : (R)0;          // the composite signal is zero beyond the line end
+        const R v = ring[(r0 + j) * stride];
+        C[j] = (x0 + j >= d && x0 + j < w) ? v : (R)0;   // the composite signal is zero before the line and beyond its end
     }
 }
 
@@ -1270,7 +1390,10 @@ CVS_HD void rng_rebase(const uint32_t *window, const uint32_t *poly, uint32_t hi
 // runs coincide (they merge with probability 1/2 per draw once adjacent) and the state is exact.
 // Returns false if they did not merge (the host then retries from further back).
 // `bracket` (optional): a [lo, hi] pair narrower than [-v, v], from rewarm_bracket().
-CVS_HD bool warm_luma(const uint32_t mod, uint32_t magic, uint32_t shift, int v, LaneRng &g, int ndraws,
+CVS_HD void rng_begin_groups(LaneRng &, uint32_t) {}
+CVS_HD void rng_begin_groups(LaneRngP &g, uint32_t n_first) { g.begin_groups(n_first); }
+template <typename G>
+CVS_HD bool warm_luma(const uint32_t mod, uint32_t magic, uint32_t shift, int v, G &g, int ndraws,
                       bool from_field_start, int &state, const int *bracket = nullptr) {
     int lo = from_field_start ? 0 : -v, hi = from_field_start ? 0 : v;
     if (bracket) { lo = bracket[0]; hi = bracket[1]; }
@@ -1280,9 +1403,11 @@ CVS_HD bool warm_luma(const uint32_t mod, uint32_t magic, uint32_t shift, int v,
         hi = noise_step(hi, d, v);
     }
     state = lo;
+    rng_begin_groups(g, kRngBase);
     return lo == hi;
 }
-CVS_HD bool warm_chroma(const uint32_t mod, uint32_t magic, uint32_t shift, int v, LaneRng &g, int npx,
+template <typename G>
+CVS_HD bool warm_chroma(const uint32_t mod, uint32_t magic, uint32_t shift, int v, G &g, int npx,
                         bool from_field_start, int &su, int &sv, const int *bracket = nullptr) {
     int lou = from_field_start ? 0 : -v, hiu = from_field_start ? 0 : v, lov = lou, hiv = hiu;
     if (bracket) { lou = bracket[0]; hiu = bracket[1]; lov = bracket[2]; hiv = bracket[3]; }
@@ -1294,6 +1419,7 @@ CVS_HD bool warm_chroma(const uint32_t mod, uint32_t magic, uint32_t shift, int 
         lov = noise_step(lov, dv, v); hiv = noise_step(hiv, dv, v);
     }
     su = lou; sv = lov;
+    rng_begin_groups(g, kRngBase);
     return lou == hiu && lov == hiv;
 }
 

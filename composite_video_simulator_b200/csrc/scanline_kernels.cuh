@@ -32,6 +32,9 @@ constexpr int kWarpsPerCta = kNT / 32;
 #define CVS_MIN_WARPS 12            // warps per SM the register allocator must leave room for (168 registers)
 #endif
 #define CVS_MIN_CTAS (CVS_MIN_WARPS / (CVS_NT / 32))
+#ifndef CVS_FAST_UNROLL
+#define CVS_FAST_UNROLL 0       // steps per iteration of the lean interior loop: 0 = per kernel (see there), 1, 2
+#endif
 #ifndef CVS_LEAN_LOOP
 #define CVS_LEAN_LOOP 1         // a lean interior loop for warps without head-switch / dropout rows
 #endif
@@ -80,7 +83,7 @@ struct SmemLayout {
     static constexpr size_t rings = (size_t)2 * kRngSlots * kNT * sizeof(uint32_t);
     static constexpr size_t wins = (size_t)kWarpsPerCta * 128 * sizeof(uint32_t);   // two fields can meet in a warp
     static constexpr size_t tails = VHS ? (size_t)2 * kTailSlots * kNT * sizeof(R) : 0;
-    static constexpr size_t hsring = VHS ? (size_t)kHsRing * kNT * sizeof(R) : 0;
+    static constexpr size_t hsring = VHS ? (size_t)kHsSlots * kNT * sizeof(R) : 0;
     static constexpr size_t off_wins = rings, off_tails = rings + wins, off_hsring = rings + wins + tails;
     static constexpr size_t total = rings + wins + tails + hsring;
 };
@@ -313,20 +316,20 @@ __global__ void __launch_bounds__(kNT, (sizeof(R) == 4 ? CVS_MIN_CTAS : 1)) k_fi
         if (K.vnoise != 0) {
             const uint32_t m = (uint32_t)(2 * K.vnoise + 1);
             rebase_dev(win, fd.seek + (size_t)row * 62, hist);
-            ln.rngL.init(rings + tid, kNT, hist, kRngBase - (uint32_t)nd);
+            ln.rngL.init(rings, tid, kNT, hist, kRngBase - (uint32_t)nd);
             if (!warm_luma(m, K.vmagic, K.vshift, K.vnoise, ln.rngL, nd, from_start, ln.nY)) {
                 rewarm_dev(hist, 1, extra, extra == avail, m, K.vmagic, K.vshift, K.vnoise, br);
-                ln.rngL.init(rings + tid, kNT, hist, kRngBase - (uint32_t)nd);
+                ln.rngL.init(rings, tid, kNT, hist, kRngBase - (uint32_t)nd);
                 ok &= warm_luma(m, K.vmagic, K.vshift, K.vnoise, ln.rngL, nd, from_start, ln.nY, br);
             }
         }
         if (K.cnoise != 0) {
             const uint32_t m = (uint32_t)(2 * K.cnoise + 1);
             rebase_dev(win, fd.seek + (size_t)row * 62 + 31, hist);
-            ln.rngC.init(rings + (size_t)kRngSlots * kNT + tid, kNT, hist, kRngBase - 2u * (uint32_t)nd);
+            ln.rngC.init(rings + (size_t)kRngSlots * kNT, tid, kNT, hist, kRngBase - 2u * (uint32_t)nd);
             if (!warm_chroma(m, K.cmagic, K.cshift, K.cnoise, ln.rngC, nd, from_start, ln.nU, ln.nV)) {
                 rewarm_dev(hist, 2, extra, extra == avail, m, K.cmagic, K.cshift, K.cnoise, br);
-                ln.rngC.init(rings + (size_t)kRngSlots * kNT + tid, kNT, hist, kRngBase - 2u * (uint32_t)nd);
+                ln.rngC.init(rings + (size_t)kRngSlots * kNT, tid, kNT, hist, kRngBase - 2u * (uint32_t)nd);
                 ok &= warm_chroma(m, K.cmagic, K.cshift, K.cnoise, ln.rngC, nd, from_start, ln.nU, ln.nV, br);
             }
         }
@@ -374,6 +377,19 @@ __global__ void __launch_bounds__(kNT, (sizeof(R) == 4 ? CVS_MIN_CTAS : 1)) k_fi
             // execute 9 % fewer instructions but measured slower twice, profiles/ab_variants_r1.txt and _r2.txt.)
             if (!rc.odd_any && lean && CVS_LEAN_LOOP) {
                 // every row has an even line phase and none needs a pre-pass or dropout special case
+                // Two steps per iteration where the doubled body still sits well in the instruction cache: the carried
+                // blocks rename instead of moving (-7.5 % instructions).  Measured (profiles/ab_variants_r2.txt):
+                // composite-only +13 % (9 KB body), VHS with fast noise +3.6 % (17 KB), VHS exact -2 % (19.5 KB).
+                // A leftover odd step is taken by the loop below.
+                if (CVS_FAST_UNROLL == 2 || (CVS_FAST_UNROLL == 0 && (!VHS || NF)))
+#pragma unroll 1
+                for (; s + 1 < s_hi; s += 2) {
+                    uint32_t pxn[kT];
+                    load_block_fast(srow, s + 1, true, pxn);
+                    St::template step<MODE_FAST_EVEN, true>(K, rc, ln, s, px, srow, true, hsrow, false, hsring, warp_inl, valid, drow, drow_bob, true);
+                    load_block_fast(srow, s + 2, true, px);
+                    St::template step<MODE_FAST_EVEN, true>(K, rc, ln, s + 1, pxn, srow, true, hsrow, false, hsring, warp_inl, valid, drow, drow_bob, true);
+                }
 #pragma unroll 1
                 for (; s < s_hi; s++) {
                     uint32_t pxn[kT];
@@ -431,13 +447,13 @@ __global__ void __launch_bounds__(kHsNT) k_headswitch(const __grid_constant__ La
         const uint32_t m = (uint32_t)(2 * K.vnoise + 1);
         uint32_t hist[31];
         rng_rebase(fd.window, fd.seek + (size_t)row * 62, hist);
-        ln.rngL.init(ring + threadIdx.x, kHsNT, hist, kRngBase - (uint32_t)nd);
+        ln.rngL.init(ring, (int)threadIdx.x, kHsNT, hist, kRngBase - (uint32_t)nd);
         if (!warm_luma(m, K.vmagic, K.vshift, K.vnoise, ln.rngL, nd, full <= a.warm_px, ln.nY)) {
             const long long avail = full - nd;
             const int extra = (int)(avail < kRewarmPx ? avail : kRewarmPx);
             int br[4];
             rewarm_dev(hist, 1, extra, extra == avail, m, K.vmagic, K.vshift, K.vnoise, br);
-            ln.rngL.init(ring + threadIdx.x, kHsNT, hist, kRngBase - (uint32_t)nd);
+            ln.rngL.init(ring, (int)threadIdx.x, kHsNT, hist, kRngBase - (uint32_t)nd);
             if (!warm_luma(m, K.vmagic, K.vshift, K.vnoise, ln.rngL, nd, full <= a.warm_px, ln.nY, br)) atomicOr(a.status, 1);
         }
     }

@@ -23,8 +23,8 @@ namespace {
 int g_warm_px = kWarmPx;      // emu_set_warm_px(): a short warm-up exercises the second-chance path (rewarm_bracket)
 
 // the kernels' warm-up with its second chance (scanline_kernels.cuh)
-template <typename R>
-bool warm_up(const KConst<R> &K, bool chroma, LaneRng &g, uint32_t *ring, int stride, const uint32_t hist[31], int row, int w,
+template <typename R, typename G>
+bool warm_up(const KConst<R> &K, bool chroma, G &g, uint32_t *ring, int stride, const uint32_t hist[31], int row, int w,
              int &s0, int &s1) {
     const long long full = (long long)row * w;
     const int nd = (int)(full < g_warm_px ? full : g_warm_px);
@@ -32,14 +32,14 @@ bool warm_up(const KConst<R> &K, bool chroma, LaneRng &g, uint32_t *ring, int st
     const int v = chroma ? K.cnoise : K.vnoise;
     const uint32_t m = (uint32_t)(2 * v + 1), magic = chroma ? K.cmagic : K.vmagic, shift = chroma ? K.cshift : K.vshift;
     const uint32_t n0 = kRngBase - (chroma ? 2u : 1u) * (uint32_t)nd;
-    g.init(ring, stride, hist, n0);
+    g.init(ring, 0, stride, hist, n0);
     bool ok = chroma ? warm_chroma(m, magic, shift, v, g, nd, from_start, s0, s1) : warm_luma(m, magic, shift, v, g, nd, from_start, s0);
     if (ok) return true;
     const long long avail = full - nd;
     const int extra = (int)(avail < kRewarmPx ? avail : kRewarmPx);
     int br[4];
     rewarm_bracket(hist, chroma ? 2 : 1, extra, extra == avail, m, magic, shift, v, br);
-    g.init(ring, stride, hist, n0);
+    g.init(ring, 0, stride, hist, n0);
     return chroma ? warm_chroma(m, magic, shift, v, g, nd, from_start, s0, s1, br) : warm_luma(m, magic, shift, v, g, nd, from_start, s0, br);
 }
 
@@ -94,7 +94,7 @@ int run_field(const cvs_params &p, RandCursor &cur, uint8_t *dst, int dst_stride
     interior_steps<VHS, CD>(w, s_lo, s_hi);
     std::vector<uint32_t> rings((size_t)32 * 2 * kRngSlots);
     std::vector<R> tails((size_t)32 * 2 * kTailSlots);
-    std::vector<R> hsring((size_t)32 * kHsRing);
+    std::vector<R> hsring((size_t)32 * kHsSlots);
     for (int wp = 0; wp < nwarps; wp++) {
         L lane[32];
         RowConst<R> rc[32];
@@ -158,7 +158,7 @@ int run_field(const cvs_params &p, RandCursor &cur, uint8_t *dst, int dst_stride
                 if (s >= 1) load_block_scalar(srow[l], s - 1, w, pxprev);
                 else for (int j = 0; j < kT; j++) pxprev[j] = 0;
                 R C[kT];
-                R *ring = &hsring[(size_t)l * kHsRing];
+                R *ring = &hsring[(size_t)l * kHsSlots];
 #define CVS_HEAD(M)                                                                                          \
     {                                                                                                        \
         constexpr bool FAST = (M) <= 0;                                                                      \
