@@ -399,6 +399,37 @@ def measure_yuv422(torch, timed, dev, local_rank, w, h, argv, max_batch, steps, 
                          "algorithmic_bytes_per_launch": alg}}
 
 
+def measure_field_loop(torch, cvs, local_rank, w, h, preset, n, calls):
+    """The whole field loop around the seam through cvs_field_loop_host: NV12 decoder pictures (one per two fields) in
+    pinned host memory -> scale -> composite_layer -> line doubling -> YUV 4:2:0 in pinned host memory.  Synchronous
+    calls, wall clock; H2D and D2H inside."""
+    import numpy as np
+    params = cvs.params_from_argv(PRESETS[preset])
+    nsrc = n // 2
+    cw, ch = w // 2, h // 2
+    Ys = torch.randint(16, 236, (nsrc, h, w), dtype=torch.uint8).pin_memory()
+    UVs = torch.randint(16, 241, (nsrc, ch, 2 * cw), dtype=torch.uint8).pin_memory()
+    y = torch.zeros((n, h, w), dtype=torch.uint8).pin_memory()
+    u = torch.zeros((n, ch, cw), dtype=torch.uint8).pin_memory()
+    v = torch.zeros((n, ch, cw), dtype=torch.uint8).pin_memory()
+    idx = [k // 2 for k in range(n)]
+    with cvs.Engine(params=params, device=local_rank, max_w=w, max_h=h, max_batch=n) as eng:
+        l0 = eng.kernel_launches()
+        eng.field_loop_host([Ys.numpy(), UVs.numpy()], w, h, 3, w, h, n, 0, y.numpy(), u.numpy(), v.numpy(), True, idx)
+        t0 = time.perf_counter()
+        for c in range(calls):
+            eng.field_loop_host([Ys.numpy(), UVs.numpy()], w, h, 3, w, h, n, (c + 1) * n, y.numpy(), u.numpy(), v.numpy(), True, idx)
+        dt = time.perf_counter() - t0
+        launches = eng.kernel_launches() - l0
+    h2d = nsrc * (w * h + ch * 2 * cw)
+    d2h = n * (w * h + 2 * ch * cw)
+    return {"workload": "%dx%d NV12 decoder pictures (1 per 2 fields) -> scale -> %s -> line doubling -> YUV 4:2:0, host to host, "
+                        "%d fields per call" % (w, h, workload_name(w, h, preset), n),
+            "value": calls * n / dt, "unit": "fields/s", "h2d_bytes_per_call": h2d, "d2h_bytes_per_call": d2h,
+            "pcie_bytes_per_field": (h2d + d2h) / n, "gpu_launches": launches,
+            "checksum": int(y.numpy()[-1].astype(np.uint32).sum() & 0xFFFFFFFF)}
+
+
 def copy_ceiling(torch, dist, dev, w, h, Be, steps, chunk, contiguous=False):
     """What the box moves with the e2e path's copies alone: per field the rows of one parity up (pitch 2 x stride ->
     the device picture) and down, in chunks on two streams, no kernel in between.  Same sizes, pitches and pinned
@@ -658,6 +689,7 @@ def run_own_arm(args):
                 continue
             others[name] = measure_other_bgra(torch, cvs, sharding, timed, dev, local_rank, name, w2, h2, pr2, mb, st2,
                                               args.warmup, peak)
+        others["field_loop_nv12_to_yuv420p_1080p"] = measure_field_loop(torch, cvs, local_rank, 1920, 1080, "sp", 128, 3)
         others["yuv422_sp_1080p"] = measure_yuv422(torch, timed, dev, local_rank, 1920, 1080, ["-vhs", "-vhs-speed", "sp"],
                                                    339, st2, args.warmup, peak)
 

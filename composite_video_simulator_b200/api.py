@@ -116,6 +116,17 @@ class Audio:
         self.close()
 
 
+class FieldLoopDesc(C.Structure):
+    """cvs_field_loop of include/cvs_ntsc.h."""
+    _fields_ = [("struct_size", C.c_int32), ("src_format", C.c_int32), ("src_w", C.c_int32), ("src_h", C.c_int32),
+                ("src", C.c_void_p * 3), ("src_linesize", C.c_int32 * 3), ("nsrc", C.c_int32),
+                ("src_pic_stride", C.c_longlong * 3), ("src_of_field", C.POINTER(C.c_int32)),
+                ("w", C.c_int32), ("h", C.c_int32), ("out_format", C.c_int32), ("pad_", C.c_int32),
+                ("y", C.c_void_p), ("u", C.c_void_p), ("v", C.c_void_p),
+                ("ly", C.c_int32), ("lu", C.c_int32), ("lv", C.c_int32), ("pad2_", C.c_int32),
+                ("y_pic_stride", C.c_longlong), ("u_pic_stride", C.c_longlong), ("v_pic_stride", C.c_longlong)]
+
+
 class Engine:
     """One CUDA scanline engine (context of the C ABI) bound to one device."""
 
@@ -239,6 +250,27 @@ class Engine:
         ds = dst_stride or 4 * dw
         _check(self.lib.cvs_scale_to_bgra_device(self._ctx, _ptr(dst), ds, dst_pic_stride or ds * dh, dw, dh, ptrs, ls, pst,
                                                  sw, sh, fmt, n), "cvs_scale_to_bgra_device")
+
+    def field_loop_host(self, planes, src_w, src_h, src_fmt, w, h, n, first_fieldno, y, u, v, fmt420=True, src_of_field=None):
+        """The reference's whole field loop on the device (cvs_field_loop_host): `planes` = host arrays [nsrc, rows,
+        linesize] of the decoder pictures (CVS_PIX_* src_fmt), y/u/v = host arrays [n, rows, linesize] that receive the
+        n line-doubled output pictures as planar YUV."""
+        d = FieldLoopDesc()
+        d.struct_size = C.sizeof(FieldLoopDesc)
+        d.src_format, d.src_w, d.src_h, d.nsrc = src_fmt, src_w, src_h, planes[0].shape[0]
+        for i, p in enumerate(planes):
+            d.src[i] = p.ctypes.data
+            d.src_linesize[i] = p.strides[1]
+            d.src_pic_stride[i] = p.strides[0]
+        idx = None
+        if src_of_field is not None:
+            idx = (C.c_int32 * n)(*[int(i) for i in src_of_field])
+            d.src_of_field = C.cast(idx, C.POINTER(C.c_int32))
+        d.w, d.h, d.out_format = w, h, (0 if fmt420 else 1)
+        d.y, d.u, d.v = y.ctypes.data, u.ctypes.data, v.ctypes.data
+        d.ly, d.lu, d.lv = y.strides[1], u.strides[1], v.strides[1]
+        d.y_pic_stride, d.u_pic_stride, d.v_pic_stride = y.strides[0], u.strides[0], v.strides[0]
+        _check(self.lib.cvs_field_loop_host(self._ctx, C.byref(d), n, first_fieldno), "cvs_field_loop_host")
 
     def synchronize(self):
         _check(self.lib.cvs_synchronize(self._ctx), "cvs_synchronize")

@@ -110,6 +110,9 @@ struct cvs_ctx {
     cudaEvent_t host_call_done[2] = {nullptr, nullptr};   // recorded on s_out when a call's last download is queued
     int host_call_parity = 0;
     unsigned long long launches = 0;
+    // cvs_field_loop_host: device buffers of the chain and the ring row that field-0 pictures inherit
+    uint8_t *fl_src = nullptr, *fl_scaled = nullptr, *fl_out = nullptr, *fl_yuv = nullptr, *fl_last_row = nullptr;
+    size_t fl_src_cap = 0, fl_scaled_cap = 0, fl_out_cap = 0, fl_yuv_cap = 0, fl_last_row_cap = 0;
 };
 
 namespace {
@@ -149,6 +152,7 @@ void free_all(cvs_ctx *c) {
     if (c->s_tab) cudaStreamDestroy(c->s_tab);
     cudaFree(c->d_scratch); cudaFree(c->d_status); cudaFree(c->d_lut_f); cudaFree(c->d_lut_d);
     for (int i = 0; i < 2; i++) { cudaFree(c->d_src[i]); cudaFree(c->d_dst[i]); if (c->host_call_done[i]) cudaEventDestroy(c->host_call_done[i]); }
+    cudaFree(c->fl_src); cudaFree(c->fl_scaled); cudaFree(c->fl_out); cudaFree(c->fl_yuv); cudaFree(c->fl_last_row);
     if (c->h_status) cudaFreeHost(c->h_status);
     for (auto &pr : c->ev_pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (auto e : c->ev_in) cudaEventDestroy(e);
@@ -276,9 +280,10 @@ int launch_batch(cvs_ctx *c, const Staging &sl, const Variant &v, int w, int h, 
 
 // Plan + launch n fields whose pictures are device-resident.  explicit_field < 0 => the
 // reference loop's schedule field = ((fieldno) & 1) ^ 1  (ffmpeg_ntsc.cpp:2229).
+// src_index (optional): source picture of field k is src + src_index[k] * src_pic_stride instead of src + k * ...
 int run_device(cvs_ctx *c, uint8_t *dst, size_t dst_pic_stride, int dst_stride, const uint8_t *src,
                size_t src_pic_stride, int src_stride, int w, int h, int interlaced, int tff, int n,
-               unsigned long long first_fieldno, int explicit_field) {
+               unsigned long long first_fieldno, int explicit_field, const int32_t *src_index = nullptr) {
     if (!c || !dst || !src) return CVS_ERR_INVALID_ARG;
     if (w <= 0 || h <= 0 || n < 0) return CVS_ERR_INVALID_ARG;
     if (dst_stride < 4 * w || src_stride < 4 * w) return CVS_ERR_INVALID_ARG;          // :1580-1581
@@ -307,7 +312,7 @@ int run_device(cvs_ctx *c, uint8_t *dst, size_t dst_pic_stride, int dst_stride, 
         const unsigned field = explicit_field >= 0 ? (unsigned)explicit_field : (unsigned)((fieldno & 1) ^ 1);
         FieldDesc &fd = sl.h_fields[k];
         std::memset(&fd, 0, sizeof(fd));
-        fd.src = src + (size_t)k * src_pic_stride;
+        fd.src = src + (size_t)(src_index ? src_index[k] : k) * src_pic_stride;
         fd.dst = dst + (size_t)k * dst_pic_stride;
         fd.fieldno = fieldno;
         fd.field = (int32_t)field;
@@ -859,6 +864,152 @@ int cvs_scale_to_bgra_device(cvs_ctx *ctx, void *dst, int dst_stride, long long 
     CVS_CUDA(cudaGetLastError());
     ctx->launches++;
     return CVS_OK;
+}
+
+namespace {
+
+// row h-1 of the pictures whose field does not own it keeps what the frame ring held (ffmpeg_ntsc.cpp:2247): with a
+// ring of one picture that is the previous output picture's last row (or the row saved by the previous call)
+__global__ void __launch_bounds__(256) k_inherit_last_row(uint8_t *out, size_t pic, int stride, int w, int h, int n,
+                                                          unsigned long long first_fieldno, const uint8_t *saved) {
+    const int k = blockIdx.y;
+    const unsigned field = (unsigned)(((first_fieldno + (unsigned long long)k) & 1ull) ^ 1ull);
+    if (k >= n || (unsigned)((h - 1) & 1) == field) return;              // the field wrote the row itself
+    const uint32_t *from = reinterpret_cast<const uint32_t *>(k == 0 ? saved : out + (size_t)(k - 1) * pic + (size_t)(h - 1) * stride);
+    uint32_t *to = reinterpret_cast<uint32_t *>(out + (size_t)k * pic + (size_t)(h - 1) * stride);
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < w; x += gridDim.x * blockDim.x) to[x] = from[x];
+}
+
+cudaError_t grow(uint8_t **p, size_t *cap, size_t need, bool zero = false) {
+    if (need <= *cap && *p) return cudaSuccess;
+    cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    cudaError_t e = cudaMalloc((void **)p, need);
+    if (e != cudaSuccess) return e;
+    *cap = need;
+    return zero ? cudaMemset(*p, 0, need) : cudaSuccess;
+}
+
+}  // namespace
+
+int cvs_field_loop_host(cvs_ctx *ctx, const cvs_field_loop *d, int n, unsigned long long first_fieldno) {
+    if (!ctx || !d || d->struct_size != (int32_t)sizeof(cvs_field_loop) || n < 0) return CVS_ERR_INVALID_ARG;
+    const int w = d->w, h = d->h, sw = d->src_w, sh = d->src_h, fmt = d->src_format;
+    if (w <= 0 || h <= 0 || sw <= 0 || sh <= 0 || d->nsrc <= 0 || !d->src[0] || !d->y || !d->u || !d->v) return CVS_ERR_INVALID_ARG;
+    if (fmt < CVS_PIX_BGRA || fmt > CVS_PIX_NV12) return CVS_ERR_INVALID_ARG;
+    if (d->out_format != CVS_YUV420P && d->out_format != CVS_YUV422P) return CVS_ERR_INVALID_ARG;
+    const int cw = (w + 1) / 2, chh = d->out_format == CVS_YUV420P ? (h + 1) / 2 : h;
+    if (d->ly < w || d->lu < cw || d->lv < cw) return CVS_ERR_INVALID_ARG;
+    if (w > ctx->max_w || h > ctx->max_h || n > ctx->max_batch) return CVS_ERR_CAPACITY;
+    if (d->src_of_field)
+        for (int k = 0; k < n; k++)
+            if (d->src_of_field[k] < 0 || d->src_of_field[k] >= d->nsrc) return CVS_ERR_INVALID_ARG;
+    if (n == 0) return CVS_OK;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return CVS_ERR_CUDA;
+    cvs_ctx *c = ctx;
+
+    // source planes: rows packed to their own width on the device
+    const int scw = (sw + 1) / 2, sch = fmt == CVS_PIX_YUV422P ? sh : (sh + 1) / 2;
+    const int nplanes = fmt == CVS_PIX_BGRA ? 1 : (fmt == CVS_PIX_NV12 ? 2 : 3);
+    int rowb[3] = {0, 0, 0}, rows[3] = {0, 0, 0};
+    rowb[0] = fmt == CVS_PIX_BGRA ? 4 * sw : sw; rows[0] = sh;
+    if (nplanes >= 2) { rowb[1] = fmt == CVS_PIX_NV12 ? 2 * scw : scw; rows[1] = sch; }
+    if (nplanes == 3) { rowb[2] = scw; rows[2] = sch; }
+    size_t plane_off[3] = {0, 0, 0}, src_pic = 0;
+    int dl[3] = {0, 0, 0};
+    for (int i = 0; i < nplanes; i++) {
+        if (!d->src[i] || d->src_linesize[i] < rowb[i]) return CVS_ERR_INVALID_ARG;
+        dl[i] = (rowb[i] + 15) / 16 * 16;
+        plane_off[i] = src_pic;
+        src_pic += (size_t)dl[i] * (size_t)rows[i];
+    }
+    const int dstride = ((4 * w + 15) / 16) * 16;
+    const size_t dpic = (size_t)dstride * (size_t)h;
+    const int yl = (w + 15) / 16 * 16, cl = (cw + 15) / 16 * 16;
+    const size_t ypl = (size_t)yl * h, cpl = (size_t)cl * chh, yuv_pic = ypl + 2 * cpl;
+    CVS_CUDA(cudaStreamSynchronize(c->stream));
+    CVS_CUDA(cudaStreamSynchronize(c->s_out));
+    CVS_CUDA(grow(&c->fl_src, &c->fl_src_cap, src_pic * (size_t)d->nsrc));
+    CVS_CUDA(grow(&c->fl_scaled, &c->fl_scaled_cap, dpic * (size_t)d->nsrc));
+    CVS_CUDA(grow(&c->fl_out, &c->fl_out_cap, dpic * (size_t)n));
+    CVS_CUDA(grow(&c->fl_yuv, &c->fl_yuv_cap, yuv_pic * (size_t)n));
+    CVS_CUDA(grow(&c->fl_last_row, &c->fl_last_row_cap, (size_t)dstride, true));     // the zeroed ring (:2069-2092)
+
+    // 1. decoder pictures up (s_in), 2. scaled to BGRA at the output size (frame_copy_scale)
+    for (int q = 0; q < d->nsrc; q++)
+        for (int i = 0; i < nplanes; i++)
+            CVS_CUDA(cudaMemcpy2DAsync(c->fl_src + (size_t)q * src_pic + plane_off[i], (size_t)dl[i],
+                                       (const uint8_t *)d->src[i] + (size_t)q * (size_t)d->src_pic_stride[i], (size_t)d->src_linesize[i],
+                                       (size_t)rowb[i], (size_t)rows[i], cudaMemcpyHostToDevice, c->s_in));
+    while (c->ev_in.empty()) {
+        cudaEvent_t a, b;
+        CVS_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        CVS_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        c->ev_in.push_back(a);
+        c->ev_k.push_back(b);
+    }
+    CVS_CUDA(cudaEventRecord(c->ev_in[0], c->s_in));
+    CVS_CUDA(cudaStreamWaitEvent(c->stream, c->ev_in[0], 0));
+    {
+        const void *sp[3] = {c->fl_src + plane_off[0], nplanes >= 2 ? c->fl_src + plane_off[1] : nullptr,
+                             nplanes == 3 ? c->fl_src + plane_off[2] : nullptr};
+        const long long sps[3] = {(long long)src_pic, (long long)src_pic, (long long)src_pic};
+        const int rc = cvs_scale_to_bgra_device(c, c->fl_scaled, dstride, (long long)dpic, w, h, sp, dl, sps, sw, sh, fmt, d->nsrc);
+        if (rc != CVS_OK) return rc;
+    }
+    // 3. per chunk: composite_layer() + line doubling, the inherited ring row, the encoder's YUV; 4. pictures down
+    std::vector<int32_t> index((size_t)n);
+    for (int k = 0; k < n; k++) index[(size_t)k] = d->src_of_field ? d->src_of_field[k] : (int32_t)(((long long)k * d->nsrc) / n);
+    const int saved_bob = c->bob;
+    const RandCursor call_start = c->cur;
+    c->bob = 1;
+    int rc = CVS_OK;
+    const int chunk = c->host_chunk;
+    int ci = 0;
+    for (int k0 = 0; k0 < n && rc == CVS_OK; k0 += chunk, ci++) {
+        const int m = n - k0 < chunk ? n - k0 : chunk;
+        uint8_t *out = c->fl_out + (size_t)k0 * dpic;
+        rc = run_device(c, out, dpic, dstride, c->fl_scaled, dpic, dstride, w, h, 0, 0, m, first_fieldno + (unsigned long long)k0, -1,
+                        index.data() + k0);
+        if (rc != CVS_OK) break;
+        {
+            const uint8_t *saved = k0 == 0 ? c->fl_last_row : out - dpic + (size_t)(h - 1) * dstride;
+            const dim3 grid((unsigned)((w + 255) / 256 < 8 ? (w + 255) / 256 : 8), (unsigned)m);
+            k_inherit_last_row<<<grid, 256, 0, c->stream>>>(out, dpic, dstride, w, h, m, first_fieldno + (unsigned long long)k0, saved);
+            if (cudaGetLastError() != cudaSuccess) { rc = CVS_ERR_CUDA; break; }
+            c->launches++;
+        }
+        uint8_t *yv = c->fl_yuv + (size_t)k0 * yuv_pic;
+        rc = cvs_bgra_to_yuv_device(c, yv, yl, (long long)yuv_pic, yv + ypl, cl, (long long)yuv_pic, yv + ypl + cpl, cl, (long long)yuv_pic,
+                                    out, dstride, (long long)dpic, w, h, m, d->out_format);
+        if (rc != CVS_OK) break;
+        while ((int)c->ev_k.size() <= ci) {
+            cudaEvent_t a, b;
+            if (cudaEventCreateWithFlags(&a, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&b, cudaEventDisableTiming) != cudaSuccess) { rc = CVS_ERR_CUDA; break; }
+            c->ev_in.push_back(a);
+            c->ev_k.push_back(b);
+        }
+        if (rc != CVS_OK) break;
+        if (cudaEventRecord(c->ev_k[ci], c->stream) != cudaSuccess || cudaStreamWaitEvent(c->s_out, c->ev_k[ci], 0) != cudaSuccess) { rc = CVS_ERR_CUDA; break; }
+        for (int k = k0; k < k0 + m && rc == CVS_OK; k++) {
+            const uint8_t *pk = c->fl_yuv + (size_t)k * yuv_pic;
+            cudaError_t e = cudaMemcpy2DAsync((uint8_t *)d->y + (size_t)k * (size_t)d->y_pic_stride, (size_t)d->ly, pk, (size_t)yl, (size_t)w, (size_t)h,
+                                              cudaMemcpyDeviceToHost, c->s_out);
+            if (e == cudaSuccess) e = cudaMemcpy2DAsync((uint8_t *)d->u + (size_t)k * (size_t)d->u_pic_stride, (size_t)d->lu, pk + ypl, (size_t)cl, (size_t)cw,
+                                                        (size_t)chh, cudaMemcpyDeviceToHost, c->s_out);
+            if (e == cudaSuccess) e = cudaMemcpy2DAsync((uint8_t *)d->v + (size_t)k * (size_t)d->v_pic_stride, (size_t)d->lv, pk + ypl + cpl, (size_t)cl, (size_t)cw,
+                                                        (size_t)chh, cudaMemcpyDeviceToHost, c->s_out);
+            if (e != cudaSuccess) rc = CVS_ERR_CUDA;
+        }
+    }
+    if (rc == CVS_OK && cudaMemcpyAsync(c->fl_last_row, c->fl_out + (size_t)(n - 1) * dpic + (size_t)(h - 1) * dstride, (size_t)dstride,
+                                        cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess) rc = CVS_ERR_CUDA;
+    c->bob = saved_bob;
+    cudaStreamSynchronize(c->s_in);
+    cudaStreamSynchronize(c->s_out);
+    if (rc != CVS_OK) { cudaStreamSynchronize(c->stream); c->cur = call_start; return rc; }
+    return check_status(c);
 }
 
 int cvs_kernel_time_reset(cvs_ctx *ctx) {

@@ -163,6 +163,40 @@ int  cvs_bgra_to_yuv_device(cvs_ctx *ctx, void *y, int ly, long long y_pic_strid
                             void *v, int lv, long long v_pic_stride, const void *bgra, int stride,
                             long long bgra_pic_stride, int w, int h, int n, int format);
 
+/* ---- the whole field loop around the seam, host pictures in, host pictures out ----------
+ * What ffmpeg_ntsc's main loop does per output field (ffmpeg_ntsc.cpp:2190-2282), with only the decoder's pictures
+ * going up and only the encoder's planar YUV coming down:
+ *     frame_copy_scale() (:544-613)  ->  composite_layer() (:2229)  ->  line doubling (:2232-2257)
+ *                                    ->  sws_scale() to the encoder's format (:2266-2274)
+ * for n consecutive output fields first_fieldno .. first_fieldno + n - 1.  A 1080p field then costs 3.1 MB of
+ * download (4:2:0) plus its share of a source picture instead of the 4.1 MB + 4.1 MB of field rows that
+ * cvs_composite_fields_host moves, and no CPU pass touches a pixel.
+ *   src*            nsrc decoder pictures in HOST memory (pinned recommended), format CVS_PIX_*, src_w x src_h
+ *   src_of_field    n entries: which source picture each output field shows (the reference shows a decoded frame for
+ *                   as many fields as its pts lasts); NULL = field k shows picture k * nsrc / n
+ *   y, u, v         n output pictures in HOST memory, w x h luma, chroma per out_format (CVS_YUV420P / CVS_YUV422P)
+ * The line doubling leaves row h-1 of an even-height picture of field 0 as the frame ring had it (:2247): the context
+ * keeps that row from call to call (the default ring of one picture, `-d 1`), starting from the zeroed ring (:2069-2092).
+ * Conversions as specified at cvs_scale_to_bgra_device / cvs_bgra_to_yuv_device (not pinned against libswscale); the
+ * composite_layer() step is the pinned hot path.  Synchronous; the rand() position advances as for n
+ * cvs_composite_layer() calls.
+ */
+typedef struct cvs_field_loop {
+    int32_t struct_size;                    /* sizeof(cvs_field_loop) */
+    int32_t src_format, src_w, src_h;
+    const void *src[3];
+    int32_t src_linesize[3];
+    int32_t nsrc;
+    long long src_pic_stride[3];
+    const int32_t *src_of_field;
+    int32_t w, h;                           /* output_width x output_height */
+    int32_t out_format, pad_;
+    void *y, *u, *v;
+    int32_t ly, lu, lv, pad2_;
+    long long y_pic_stride, u_pic_stride, v_pic_stride;
+} cvs_field_loop;
+int  cvs_field_loop_host(cvs_ctx *ctx, const cvs_field_loop *d, int n, unsigned long long first_fieldno);
+
 /* ---- the audio step of the same program (CPU) ----------------------------------
  * composite_audio_process(int16_t *audio, unsigned samples) (ffmpeg_ntsc.cpp:901-970; called per decoded audio
  * packet from process_audio(), :1284-1290): band limiting, pre/de-emphasis, sync-pulse buzz of linear tracks, tape

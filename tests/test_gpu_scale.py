@@ -90,3 +90,45 @@ def test_scaled_pictures_feed_the_field_loop(oracle):
     got[1::2] = o[0][1::2]
     got[0::2] = o[1][0::2]
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("w,h,v420", [(320, 240, True), (164, 121, True), (160, 120, False)])
+def test_field_loop_host_equals_the_reference_loop_with_the_oracle_conversions(oracle, w, h, v420):
+    """cvs_field_loop_host: decoder pictures (NV12, host) -> scale -> composite_layer -> line doubling -> encoder YUV
+    (host), in two calls (the ring row travels in the context), against the same chain made of the oracles: the
+    reference's field loop (one ring picture, ffmpeg_ntsc.cpp:2190-2282) with oracle/convert_oracle.c on both ends."""
+    import ctypes as C
+    sw, sh, nsrc, fpf = 176, 144, 4, 2
+    n = nsrc * fpf
+    p = helpers.params("-vhs")
+    srcs = [source(sw, sh, NV12, 90 + k) for k in range(nsrc)]
+    # the oracle chain
+    g = helpers.OracleRng()
+    oracle.oracle_rng_seed(C.byref(g), 1)
+    ring = np.zeros((h, w), dtype=np.uint32)
+    want = []
+    for cur in range(n):
+        bgra = helpers.oracle_scale_to_bgra(srcs[cur // fpf], sw, sh, NV12, w, h)
+        f = (cur & 1) ^ 1
+        oracle.oracle_composite_layer(C.byref(p), C.byref(g), ring.ctypes.data_as(C.c_void_p), 4 * w,
+                                      bgra.ctypes.data_as(C.c_void_p), 4 * w, w, h, 0, 0, f, C.c_ulonglong(cur))
+        oracle.oracle_bob(ring.ctypes.data_as(C.c_void_p), 4 * w, w, h, f)
+        want.append(helpers.oracle_bgra_to_yuv(ring, v420))
+    # the engine, two calls of n/2 fields
+    Ys = np.stack([s[0] for s in srcs])
+    UVs = np.stack([s[1] for s in srcs])
+    cw, ch = (w + 1) // 2, ((h + 1) // 2 if v420 else h)
+    y = np.zeros((n, h, w), np.uint8)
+    u = np.zeros((n, ch, cw), np.uint8)
+    v = np.zeros((n, ch, cw), np.uint8)
+    half = n // 2
+    with cvs.Engine(params=p, max_w=w, max_h=h, max_batch=n) as eng:
+        eng.set_precision(True)
+        for c0 in (0, half):
+            sel = slice(c0 // fpf, (c0 + half) // fpf)
+            eng.field_loop_host([Ys[sel], UVs[sel]], sw, sh, NV12, w, h, half, c0, y[c0:c0 + half], u[c0:c0 + half], v[c0:c0 + half],
+                                fmt420=v420, src_of_field=[k // fpf for k in range(half)])
+        assert eng.rng_tell() == g.pos
+    for k in range(n):
+        for name, got, wnt in (("y", y[k], want[k][0]), ("u", u[k], want[k][1]), ("v", v[k], want[k][2])):
+            assert np.array_equal(got, wnt), (k, name)
