@@ -113,6 +113,26 @@ static __device__ __noinline__ void rewarm_dev(const uint32_t *hist, int streams
     rewarm_bracket(hist, streams, extra_px, at_field_start, mod, magic, shift, v, bracket);
 }
 
+// Both streams at once: one pass over the window feeds two accumulators (half the shared-memory reads of two passes).
+__device__ __forceinline__ void rebase2_dev(const uint32_t *win_smem, const uint32_t *__restrict__ poly_g,
+                                            uint32_t histL[31], uint32_t histC[31]) {
+    uint32_t pl[31], pc[31];
+#pragma unroll
+    for (int i = 0; i < 31; i++) { pl[i] = __ldg(poly_g + i); pc[i] = __ldg(poly_g + 31 + i); }
+#pragma unroll 1
+    for (int k = 0; k < 31; k++) {
+        uint32_t al = 0, ac = 0;
+#pragma unroll
+        for (int i = 0; i < 31; i++) {
+            const uint32_t wv = win_smem[k + i];
+            al += pl[i] * wv;
+            ac += pc[i] * wv;
+        }
+        histL[k] = al;
+        histC[k] = ac;
+    }
+}
+
 // Each lane reads its own row, 32 bytes (one sector) per step; four consecutive steps share one
 // 128-byte line.  The L2::128B hint makes the first touch bring the whole line into L2, so DRAM sees
 // every line exactly once (the first ncu capture, taken with evict-first loads, showed 1.7x the
@@ -311,11 +331,13 @@ __global__ void __launch_bounds__(kNT, (sizeof(R) == 4 ? CVS_MIN_CTAS : 1)) k_fi
         const long long avail = full - nd;
         const int extra = (int)(avail < kRewarmPx ? avail : kRewarmPx);
         bool ok = true;
-        uint32_t hist[31];
+        uint32_t hist[31], histC[31];
         int br[4];
+        const bool both = K.vnoise != 0 && K.cnoise != 0;
+        if (both) rebase2_dev(win, fd.seek + (size_t)row * 62, hist, histC);
         if (K.vnoise != 0) {
             const uint32_t m = (uint32_t)(2 * K.vnoise + 1);
-            rebase_dev(win, fd.seek + (size_t)row * 62, hist);
+            if (!both) rebase_dev(win, fd.seek + (size_t)row * 62, hist);
             ln.rngL.init(rings, tid, kNT, hist, kRngBase - (uint32_t)nd);
             if (!warm_luma(m, K.vmagic, K.vshift, K.vnoise, ln.rngL, nd, from_start, ln.nY)) {
                 rewarm_dev(hist, 1, extra, extra == avail, m, K.vmagic, K.vshift, K.vnoise, br);
@@ -325,11 +347,11 @@ __global__ void __launch_bounds__(kNT, (sizeof(R) == 4 ? CVS_MIN_CTAS : 1)) k_fi
         }
         if (K.cnoise != 0) {
             const uint32_t m = (uint32_t)(2 * K.cnoise + 1);
-            rebase_dev(win, fd.seek + (size_t)row * 62 + 31, hist);
-            ln.rngC.init(rings + (size_t)kRngSlots * kNT, tid, kNT, hist, kRngBase - 2u * (uint32_t)nd);
+            if (!both) rebase_dev(win, fd.seek + (size_t)row * 62 + 31, histC);
+            ln.rngC.init(rings + (size_t)kRngSlots * kNT, tid, kNT, histC, kRngBase - 2u * (uint32_t)nd);
             if (!warm_chroma(m, K.cmagic, K.cshift, K.cnoise, ln.rngC, nd, from_start, ln.nU, ln.nV)) {
-                rewarm_dev(hist, 2, extra, extra == avail, m, K.cmagic, K.cshift, K.cnoise, br);
-                ln.rngC.init(rings + (size_t)kRngSlots * kNT, tid, kNT, hist, kRngBase - 2u * (uint32_t)nd);
+                rewarm_dev(histC, 2, extra, extra == avail, m, K.cmagic, K.cshift, K.cnoise, br);
+                ln.rngC.init(rings + (size_t)kRngSlots * kNT, tid, kNT, histC, kRngBase - 2u * (uint32_t)nd);
                 ok &= warm_chroma(m, K.cmagic, K.cshift, K.cnoise, ln.rngC, nd, from_start, ln.nU, ln.nV, br);
             }
         }
