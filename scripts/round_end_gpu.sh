@@ -36,7 +36,8 @@ for tag, key, fields_key in (("r2_sp", "sp_1920x1080", None), ("r2_ep", "ep_1920
         scale = lambda u: {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[u]
         total = rd * scale(unit["dram__bytes_read.sum"]) + wr * scale(unit["dram__bytes_write.sum"])
         w, h = (3840, 2160) if "comp" in tag else (1920, 1080)
-        fields = json.load(open("gpurun_out/prof_%s.bench.json" % tag))["config"]["fields_per_step_per_gpu"]
+        line = [l for l in open("gpurun_out/prof_%s.bench.json" % tag) if l.startswith("{")][-1]     # (ncu prints its banner there too)
+        fields = json.loads(line)["config"]["fields_per_step_per_gpu"]
         caps[key] = {"dram_bytes": total, "fields": fields, "grid": f(m["launch__grid_size"]),
                      "algorithmic_bytes": 8.0 * w * ((h + 1) // 2) * fields}
     except Exception as e:
