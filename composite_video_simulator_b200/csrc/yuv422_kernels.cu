@@ -5,7 +5,7 @@
 namespace cvs422 {
 
 cudaError_t launch_yuv422(const Launch422 &a, const HsItem422 *d_items, int nitems, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(k_yuv422, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem422::total);
+    cudaError_t e = cudaFuncSetAttribute(k_yuv422, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem422::total_max);
     if (e != cudaSuccess) return e;
     if (a.packed ? a.total_warps > 1 : a.warps_per_field > 1) {
         k_yuv422_halo<<<a.packed ? a.total_warps : a.nfields * a.warps_per_field, 128, 0, st>>>(a);
@@ -16,14 +16,14 @@ cudaError_t launch_yuv422(const Launch422 &a, const HsItem422 *d_items, int nite
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     const int ctas = (a.total_warps + kWarps - 1) / kWarps;
-    k_yuv422<<<ctas, kNT, Smem422::total, st>>>(a);
+    k_yuv422<<<ctas, kNT, Smem422::total(a.K), st>>>(a);
     return cudaGetLastError();
 }
 
-cudaError_t occupancy_yuv422(int *ctas_per_sm) {
-    cudaError_t e = cudaFuncSetAttribute(k_yuv422, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem422::total);
+cudaError_t occupancy_yuv422(const K422 &K, int *ctas_per_sm) {
+    cudaError_t e = cudaFuncSetAttribute(k_yuv422, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem422::total_max);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_yuv422, kNT, Smem422::total);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_yuv422, kNT, Smem422::total(K));
 }
 
 cudaError_t launch_render_field(const RenderArgs &a, cudaStream_t st) {

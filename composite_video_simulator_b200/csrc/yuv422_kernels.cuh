@@ -68,14 +68,19 @@ struct Launch422 {
     int32_t *status;
 };
 
+// Dynamic shared memory of k_yuv422: the per-lane rings, then one generator ring per noise stream that is ON
+// (16 KB each for 128 lanes: with the default -chroma-noise 0 a third CTA fits on an SM).
 struct Smem422 {
-    static constexpr size_t rng = (size_t)2 * kRngSlots * kNT * sizeof(uint32_t);
+    static constexpr size_t rng1 = (size_t)kRngSlots * kNT * sizeof(uint32_t);            // one stream
     static constexpr size_t wins = (size_t)kWarps * 128 * sizeof(uint32_t);   // two fields can meet in a warp
     static constexpr size_t ry = (size_t)kNT * kStrideY, rya = (size_t)kNT * kStrideA;
     static constexpr size_t rc = (size_t)kNT * kStrideC;
     static constexpr size_t rcomb = (size_t)kNT * 3 * kMaxRecombine * sizeof(int32_t);
-    static constexpr size_t off_wins = rng, off_ry = off_wins + wins, off_rya = off_ry + ry, off_ru = off_rya + rya,
-                            off_rv = off_ru + rc, off_rcomb = off_rv + rc, total = off_rcomb + rcomb;
+    static constexpr size_t off_wins = 0, off_ry = off_wins + wins, off_rya = off_ry + ry, off_ru = off_rya + rya,
+                            off_rv = off_ru + rc, off_rcomb = off_rv + rc, off_rng = off_rcomb + rcomb;
+    static constexpr size_t total_max = off_rng + 2 * rng1;
+    static CVS_HD size_t off_rng_chroma(const K422 &K) { return off_rng + (K.vnoise != 0 ? rng1 : 0); }
+    static CVS_HD size_t total(const K422 &K) { return off_rng_chroma(K) + (K.cnoise != 0 ? rng1 : 0); }
 };
 
 // what a lane reads its row from
@@ -209,9 +214,35 @@ __device__ __forceinline__ void one_step(const K422 &K, const Lags &L, const Geo
     if (have && valid) store_block<EDGE>(dy, du, dvp, K, bs, vec, out);
 }
 
+__device__ __forceinline__ void load_block_vec(const LaneSrc &src, int s, StepIO &io) {
+    const uint2 yy = *reinterpret_cast<const uint2 *>(src.y + s * kB);
+    io.y0 = yy.x; io.y1 = yy.y;
+    io.u = *reinterpret_cast<const uint32_t *>(src.u + s * kBC);
+    io.v = *reinterpret_cast<const uint32_t *>(src.v + s * kBC);
+}
+
+// one step of the interior variant (whole blocks, aligned rows): yuv422_pipeline.cuh, Fast422
+__device__ __forceinline__ void interior_step(const K422 &K, const Lags &L, const Row422 &rc, Lane422 &ln, int s, const StepIO &in,
+                                              bool warp_hs, bool valid, uint8_t *dy, uint8_t *du, uint8_t *dvp) {
+    uint32_t pu, pv;
+    fast_front(K, L, rc, ln, s, in, warp_hs, pu, pv);
+    uint32_t au = 0, av = 0;
+    if (K.flags & G_VHS) {
+        au = __shfl_up_sync(0xffffffffu, pu, 1);
+        av = __shfl_up_sync(0xffffffffu, pv, 1);
+    }
+    StepIO o;
+    int bs;
+    fast_back(K, L, rc, ln, s, pu, pv, au, av, o, bs);
+    if (valid) {
+        *reinterpret_cast<uint2 *>(dy + bs * kB) = make_uint2(o.y0, o.y1);
+        *reinterpret_cast<uint32_t *>(du + bs * kBC) = o.u;
+        *reinterpret_cast<uint32_t *>(dvp + bs * kBC) = o.v;
+    }
+}
+
 __global__ void __launch_bounds__(kNT, CVS422_MIN_CTAS) k_yuv422(const __grid_constant__ Launch422 a) {
     extern __shared__ __align__(16) unsigned char smem[];
-    uint32_t *rings = reinterpret_cast<uint32_t *>(smem);
     uint32_t *wins = reinterpret_cast<uint32_t *>(smem + Smem422::off_wins);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gw = blockIdx.x * kWarps + warp;
@@ -291,14 +322,14 @@ __global__ void __launch_bounds__(kNT, CVS422_MIN_CTAS) k_yuv422(const __grid_co
             const long long pre = (long long)row * w;
             const int nd = (int)(pre < kWarm ? pre : kWarm);
             rebase422(win, fd.seek + (size_t)row * 62, hist);
-            ln.rngL.init(rings + tid, kNT, hist, kRngBase - (uint32_t)nd);
+            ln.rngL.init(reinterpret_cast<uint32_t *>(smem + Smem422::off_rng) + tid, kNT, hist, kRngBase - (uint32_t)nd);
             ok &= cvs::warm_luma((uint32_t)(2 * K.vnoise + 1), K.vmagic, K.vshift, K.vnoise, ln.rngL, nd, pre <= kWarm, ln.nY);
         }
         if (K.cnoise != 0) {
             const long long pre = (long long)row * K.cw;
             const int nd = (int)(pre < kWarm ? pre : kWarm);
             rebase422(win, fd.seek + (size_t)row * 62 + 31, hist);
-            ln.rngC.init(rings + (size_t)kRngSlots * kNT + tid, kNT, hist, kRngBase - 2u * (uint32_t)nd);
+            ln.rngC.init(reinterpret_cast<uint32_t *>(smem + Smem422::off_rng_chroma(K)) + tid, kNT, hist, kRngBase - 2u * (uint32_t)nd);
             ok &= cvs::warm_chroma((uint32_t)(2 * K.cnoise + 1), K.cmagic, K.cshift, K.cnoise, ln.rngC, nd, pre <= kWarm, ln.nU, ln.nV);
         }
         if (!ok) atomicOr(a.status, 1);
@@ -313,6 +344,7 @@ __global__ void __launch_bounds__(kNT, CVS422_MIN_CTAS) k_yuv422(const __grid_co
     if (__any_sync(0xffffffffu, hsrow != nullptr)) s_hi = s_lo;      // pre-pass rows only exist in the general variant
     const bool vec = a.vec != 0;          // (halo records are 16-byte aligned, so the halo lane qualifies too)
     const bool vec_ld = vec;
+    if (!vec) s_hi = s_lo;                // the interior variant moves whole words; unaligned pictures take the general one
 
     StepIO cur;
     load_block<true>(src, K, 0, vec_ld, cur);
@@ -327,15 +359,23 @@ __global__ void __launch_bounds__(kNT, CVS422_MIN_CTAS) k_yuv422(const __grid_co
             one_step<true>(K, LG, GE, a.dv, rc, ln, s, cur, warp_hs, hsrow, valid, dy, du, dvp, vec);
             cur = nxt;
         }
-        if (pass == 0) {
+        if (pass == 0 && s < s_hi) {
+            interior_enter(K, LG, ln, s);
 #pragma unroll 1
-            for (; s < s_hi; s++) {
+            for (; s < s_hi - 1; s++) {
                 StepIO nxt;
-                if (s + 1 < s_hi) load_block<false>(src, K, s + 1, vec_ld, nxt);
-                else load_block<true>(src, K, s + 1, vec_ld, nxt);
-                one_step<false>(K, LG, GE, a.dv, rc, ln, s, cur, warp_hs, hsrow, valid, dy, du, dvp, vec);
+                load_block_vec(src, s + 1, nxt);
+                interior_step(K, LG, rc, ln, s, cur, warp_hs, valid, dy, du, dvp);
                 cur = nxt;
             }
+            {
+                StepIO nxt;
+                load_block<true>(src, K, s + 1, vec_ld, nxt);
+                interior_step(K, LG, rc, ln, s, cur, warp_hs, valid, dy, du, dvp);
+                cur = nxt;
+                s++;
+            }
+            interior_leave(K, LG, ln, s);
         }
     }
 }
@@ -425,7 +465,7 @@ __global__ void __launch_bounds__(256) k_render_field(const __grid_constant__ Re
 #endif  // CVS_YUV422_DEFINE_KERNELS
 
 cudaError_t launch_yuv422(const Launch422 &a, const HsItem422 *d_items, int nitems, cudaStream_t st);
-cudaError_t occupancy_yuv422(int *ctas_per_sm);
+cudaError_t occupancy_yuv422(const K422 &K, int *ctas_per_sm);
 cudaError_t launch_render_field(const RenderArgs &a, cudaStream_t st);
 
 }  // namespace cvs422

@@ -182,6 +182,69 @@ CVS_HD int div50(int v) {                // exact for every 32-bit magnitude
     return v < 0 ? -(int)q : (int)q;
 }
 
+// ---- interior-variant helpers (round 2) ------------------------------------------------------------------
+// The interior loop is bound by the FP64 pipe (one warp instruction per two cycles per scheduler) and by the
+// instruction cache (32 KB L1.5 per SM), so it (1) keeps the 8-bit <-> double conversions off the FP64 pipe,
+// on the otherwise idle conversion pipe (I2F.F64 / F2I.F64.TRUNC), (2) clamps and packs with the saturating
+// pack (I2IP.U8.S32.SAT: four values -> one word in two instructions), (3) runs its filters as ROLLED loops
+// of CVS422_CU chroma samples / CVS422_LU luma pixels per iteration, and (4) writes delayed filter outputs as
+// whole words (the bytes that belong to the next word wait in a carry register).
+#ifndef CVS422_XU_CONV
+#define CVS422_XU_CONV 1
+#endif
+#ifndef CVS422_CU
+#define CVS422_CU 2                      // chroma samples per iteration of a rolled filter loop: 1, 2 or 4
+#endif
+#ifndef CVS422_LU
+#define CVS422_LU 2                      // luma pixels per iteration: 1, 2, 4 or 8
+#endif
+#if defined(__CUDA_ARCH__)
+#define CVS_ROLLED _Pragma("unroll 1")
+#else
+#define CVS_ROLLED
+#endif
+
+CVS_HD double fu2d(uint32_t v) {         // exact (double)v
+#if defined(__CUDA_ARCH__) && CVS422_XU_CONV
+    return __uint2double_rn(v);
+#else
+    return u2d(v);
+#endif
+}
+// an integer whose clamp to 0..255 is clampu8((int)s): truncation or floor, they differ only below zero
+CVS_HD int fq(double s) {
+#if defined(__CUDA_ARCH__)
+#if CVS422_XU_CONV
+    return __double2int_rz(s);
+#else
+    return __double2loint(__dadd_rd(s, 6755399441055744.0));
+#endif
+#else
+    return (int)s;
+#endif
+}
+// (upper << 16) | clamp8(hi) << 8 | clamp8(lo)
+CVS_HD uint32_t sat_pack2(int hi, int lo, uint32_t upper) {
+#if defined(__CUDA_ARCH__)
+    uint32_t d;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(hi), "r"(lo), "r"(upper));
+    return d;
+#else
+    return (upper << 16) | ((uint32_t)clamp8(hi) << 8) | (uint32_t)clamp8(lo);
+#endif
+}
+CVS_HD uint32_t sat4(int a, int b, int c, int d) { return sat_pack2(b, a, sat_pack2(d, c, 0u)); }   // a = byte 0
+CVS_HD int sat1(int v) { return (int)sat_pack2(0, v, 0u); }                                        // clamp8 in one instruction
+CVS_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, int sh) {             // low word of (hi:lo) >> sh, 0 < sh < 32
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, (uint32_t)sh);
+#else
+    return (lo >> sh) | (hi << (32 - sh));
+#endif
+}
+// per-byte (a + b + 1) >> 1
+CVS_HD uint32_t avg4_up(uint32_t a, uint32_t b) { return (a | b) - (((a ^ b) & 0xFEFEFEFEu) >> 1); }
+
 // ---- per-row constants -------------------------------------------------------------------------------
 struct Row422 {
     int xi;                // subcarrier phase index of the line (:449-459)
@@ -240,6 +303,7 @@ struct Lane422 {
     Demod dm1, dm2;
     int nY, nU, nV;
     LaneRng rngL, rngC;
+    uint32_t cIn[2], cCh[2], cOut[2];  // interior variant: bytes of a delayed filter that wait for their word (U, V)
     uint8_t *ry, *ru, *rv, *rya;     // lane-private rings (kRingY / kRingC / kRingC / kRingA bytes), 4-byte aligned
     int32_t *rcomb;                  // 3 ints per -yc-recomb round (lane-private, 3 * kMaxRecombine ints)
 
@@ -580,6 +644,329 @@ struct Pipe422 {
         stw(cblk(ln.rv, b), 0x80808080u);
     }
 };
+
+// ---- the interior variant: whole blocks inside the row, common switches only --------------------------
+// Same arithmetic, same ring contents at every step boundary as Pipe422<false>; what differs is the shape of
+// the code (see "interior-variant helpers").  tests/test_yuv422_emu.py runs it on the CPU against the oracle.
+struct Fast422 {
+    // a delayed filter's block: positions 4b - d + k.  The word that is complete now is stored; with d % 4 != 0
+    // the bytes of the following word wait in `carry` (= the previous block's outputs)
+    static CVS_HD void put_delayed(uint8_t *ring, int b, int d, uint32_t nw, uint32_t &carry) {
+        const int r = d & 3, qd = d >> 2;
+        if (r == 0) {
+            stw(cblk(ring, b - qd), nw);
+        } else {
+            stw(cblk(ring, b - qd - 1), funnel_r(carry, nw, 8 * r));
+            carry = nw;
+        }
+    }
+    // entering the interior at block b: the low 4 - r bytes of the pending word were written by the edge variant
+    static CVS_HD void carry_enter(uint8_t *ring, int b, int d, uint32_t &carry) {
+        const int r = d & 3, qd = d >> 2;
+        carry = r ? (ldw(cblk(ring, b - qd - 1)) << (8 * r)) : 0u;
+    }
+    // leaving it after block b: the waiting bytes go where the edge variant expects them
+    static CVS_HD void carry_leave(uint8_t *ring, int b, int d, uint32_t carry) {
+        const int r = d & 3, qd = d >> 2;
+        if (r == 0) return;
+        for (int k = r; k < 4; k++) ring[(kBC * (b - qd) + k - r) & (kRingC - 1)] = (uint8_t)((carry >> (8 * k)) & 0xFFu);
+    }
+
+    // three-pole lowpass (BOOST: preceded by s += s - highpass(s)) on the four samples of wu and of wv
+    template <bool BOOST>
+    static CVS_HD void lp_pair(uint32_t wu, uint32_t wv, double *hpU, double *lpU, double *hpV, double *lpV, double aU, double ahU,
+                               double aV, double ahV, uint32_t &ou, uint32_t &ov) {
+        ou = ov = 0;
+        CVS_ROLLED
+        for (int it = 0; it < kBC / CVS422_CU; it++) {
+            int qu[CVS422_CU], qv[CVS422_CU];
+            CVS_UNROLL
+            for (int j = 0; j < CVS422_CU; j++) {
+                double s = fu2d((uint32_t)byte_of(wu, j)), t = fu2d((uint32_t)byte_of(wv, j));
+                if (BOOST) {
+                    const double lu = pole(*hpU, s, ahU), lv = pole(*hpV, t, ahV);
+                    s = dadd(s, dsub(s, lu));
+                    t = dadd(t, dsub(t, lv));
+                }
+                s = pole(lpU[0], s, aU); t = pole(lpV[0], t, aV);
+                s = pole(lpU[1], s, aU); t = pole(lpV[1], t, aV);
+                s = pole(lpU[2], s, aU); t = pole(lpV[2], t, aV);
+                qu[j] = fq(s);
+                qv[j] = fq(t);
+            }
+            push_c(ou, qu);
+            push_c(ov, qv);
+            if (CVS422_CU < 4) { wu >>= (8 * CVS422_CU) & 31; wv >>= (8 * CVS422_CU) & 31; }
+        }
+    }
+    // CVS422_CU clamped bytes enter a word from the top (after 4 / CU pushes the first one is byte 0)
+    static CVS_HD void push_c(uint32_t &acc, const int *q) {
+        if (CVS422_CU == 4) acc = sat4(q[0], q[1], q[2], q[3 % CVS422_CU]);
+        else if (CVS422_CU == 2) acc = funnel_r(acc, sat_pack2(q[1 % CVS422_CU], q[0], 0u), 16);
+        else acc = funnel_r(acc, (uint32_t)sat1(q[0]), 8);
+    }
+
+    // G0 + G1
+    static CVS_HD void stage_load(const K422 &K, Lane422 &ln, int s, const StepIO &io) {
+        uint8_t *yb = yblk(ln.ry, s);
+        stw(yb, io.y0);
+        stw(yb + 4, io.y1);
+        stw(cblk(ln.ru, s), io.u);
+        stw(cblk(ln.rv, s), io.v);
+        if (K.flags & G_IN_LP) {
+            uint32_t ou, ov;
+            lp_pair<true>(io.u, io.v, &ln.inU[0], &ln.inU[1], &ln.inV[0], &ln.inV[1], K.a_in[0], K.a_inhp[0], K.a_in[1], K.a_inhp[1], ou, ov);
+            put_delayed(ln.ru, s, K.d_in[0], ou, ln.cIn[0]);
+            put_delayed(ln.rv, s, K.d_in[1], ov, ln.cIn[1]);
+        }
+    }
+
+    // y + chroma on the carrier for the 8 pixels of a block (amp == 50), not yet clamped
+    static CVS_HD void modulate8(const Row422 &rc, uint32_t y0, uint32_t y1, uint32_t uw, uint32_t vw, int yo[kB]) {
+        CVS_UNROLL
+        for (int j = 0; j < kB; j++) {
+            const int u = byte_of(uw, j >> 1) - 128, v = byte_of(vw, j >> 1) - 128;
+            yo[j] = byte_of(j < 4 ? y0 : y1, j & 3) + u * rc.mU[j & 3] + v * rc.mV[j & 3];
+        }
+    }
+
+    // G2, first modulation: + luma noise, + head-switch delay
+    static CVS_HD void stage_modulate_first(const K422 &K, const Row422 &rc, Lane422 &ln, int b, bool warp_hs) {
+        const int x0 = b * kB;
+        uint8_t *yb = yblk(ln.ry, b);
+        int yo[kB];
+        modulate8(rc, ldw(yb), ldw(yb + 4), ldw(cblk(ln.ru, b)), ldw(cblk(ln.rv, b)), yo);
+        if (K.vnoise != 0) {                                                   // (:653-665)
+            uint32_t *grp = ln.rngL.group_ptr(kRngBase + (uint32_t)x0);
+            const uint32_t *grp_next = ln.rngL.group_ptr(kRngBase + (uint32_t)x0 + kB);
+            CVS_UNROLL
+            for (int j = 0; j < kB; j++) {
+                yo[j] = sat1(yo[j]) + ln.nY;
+                const int d = draw_mod(ln.rngL.next_in_group(grp, grp_next, j, kB), (uint32_t)(2 * K.vnoise + 1), K.vmagic, K.vshift);
+                ln.nY = noise_step(ln.nY, d, K.vnoise);
+            }
+        }
+        uint32_t w0 = sat4(yo[0], yo[1], yo[2], yo[3]), w1 = sat4(yo[4], yo[5], yo[6], yo[7]);
+        if (warp_hs) {                                                         // (:697-731) as a delay line; x >= delay here
+            uint8_t *ab = ln.rya + (x0 & (kRingA - 1));
+            stw(ab, w0);
+            stw(ab + 4, w1);
+            if (rc.hs_delay > 0) {
+                const int p = x0 - rc.hs_delay, sh = 8 * (p & 3);
+                const uint32_t a0 = ldw(ln.rya + (p & (kRingA - 4))), a1 = ldw(ln.rya + ((p + 4) & (kRingA - 4))),
+                               a2 = ldw(ln.rya + ((p + 8) & (kRingA - 4)));
+                w0 = sh ? funnel_r(a0, a1, sh) : a0;
+                w1 = sh ? funnel_r(a1, a2, sh) : a1;
+            }
+        }
+        stw(yb, w0);
+        stw(yb + 4, w1);
+    }
+    // re-modulation of a block whose luma is final (VHS recombine)
+    static CVS_HD void stage_remodulate(const Row422 &rc, Lane422 &ln, int b) {
+        uint8_t *yb = yblk(ln.ry, b);
+        int yo[kB];
+        modulate8(rc, ldw(yb), ldw(yb + 4), ldw(cblk(ln.ru, b)), ldw(cblk(ln.rv, b)), yo);
+        stw(yb, sat4(yo[0], yo[1], yo[2], yo[3]));
+        stw(yb + 4, sat4(yo[4], yo[5], yo[6], yo[7]));
+    }
+
+    // VHS luma: lowpass + boost, then sharpen (:810-828, :888-901), 8 pixels in yw0:yw1 -> the same words
+    static CVS_HD void luma8(const K422 &K, Lane422 &ln, uint32_t &yw0, uint32_t &yw1) {
+        uint32_t o0 = 0, o1 = 0;
+        CVS_ROLLED
+        for (int it = 0; it < kB / CVS422_LU; it++) {
+            int q[CVS422_LU];
+            CVS_UNROLL
+            for (int j = 0; j < CVS422_LU; j++) {
+                double s = fu2d((uint32_t)byte_of(j < 4 ? yw0 : yw1, j & 3));
+                s = pole(ln.lum[0], s, K.a_luma);
+                s = pole(ln.lum[1], s, K.a_luma);
+                s = pole(ln.lum[2], s, K.a_luma);
+                const double lpv = pole(ln.lum[3], s, K.a_luma);
+                s = dadd(s, dmul(dsub(s, lpv), 1.6));
+                const double y1d = fu2d((uint32_t)sat1(fq(s)));
+                double ts = pole(ln.lsh[0], y1d, K.a_lsharp);
+                ts = pole(ln.lsh[1], ts, K.a_lsharp);
+                ts = pole(ln.lsh[2], ts, K.a_lsharp);
+                q[j] = fq(dadd(y1d, dmul(dsub(y1d, ts), K.sharpen)));
+            }
+            if (CVS422_LU == 8) {
+                o0 = sat4(q[0], q[1 % CVS422_LU], q[2 % CVS422_LU], q[3 % CVS422_LU]);
+                o1 = sat4(q[4 % CVS422_LU], q[5 % CVS422_LU], q[6 % CVS422_LU], q[7 % CVS422_LU]);
+            } else if (CVS422_LU == 4) {
+                o0 = o1;
+                o1 = sat4(q[0], q[1 % CVS422_LU], q[2 % CVS422_LU], q[3 % CVS422_LU]);
+                yw0 = yw1;
+            } else {
+                const int sh = (8 * CVS422_LU) & 31;
+                const uint32_t nb = (CVS422_LU == 2) ? sat_pack2(q[1 % CVS422_LU], q[0], 0u) : (uint32_t)sat1(q[0]);
+                o0 = funnel_r(o0, o1, sh);
+                o1 = funnel_r(o1, nb, sh);
+                yw0 = funnel_r(yw0, yw1, sh);
+                yw1 >>= sh;
+            }
+        }
+        yw0 = o0;
+        yw1 = o1;
+    }
+
+    // G3
+    static CVS_HD void stage_separate(const K422 &K, const Row422 &rc, Lane422 &ln, int b) {
+        const int c0 = b * kBC;
+        uint8_t *yb = yblk(ln.ry, b), *ub = cblk(ln.ru, b), *vb = cblk(ln.rv, b);
+        int Yn[kB], U[kBC], V[kBC];
+        Pipe422<false>::demod8(K, rc, ln.dm1, b, ldw(yb), ldw(yb + 4), ldw(yblk(ln.ry, b + 1)), 50, 0u, 0u, Yn, U, V);
+        if (K.cnoise != 0) {                                                   // (:738-754)
+            uint32_t *grp = ln.rngC.group_ptr(kRngBase + (uint32_t)(2 * c0));
+            const uint32_t *grp_next = ln.rngC.group_ptr(kRngBase + (uint32_t)(2 * c0) + 2 * kBC);
+            CVS_UNROLL
+            for (int k = 0; k < kBC; k++) {
+                U[k] = sat1(U[k] + ln.nU);
+                V[k] = sat1(V[k] + ln.nV);
+                const int du = draw_mod(ln.rngC.next_in_group(grp, grp_next, 2 * k, 2 * kBC), (uint32_t)(2 * K.cnoise + 1), K.cmagic, K.cshift);
+                ln.nU = noise_step(ln.nU, du, K.cnoise);
+                const int dv = draw_mod(ln.rngC.next_in_group(grp, grp_next, 2 * k + 1, 2 * kBC), (uint32_t)(2 * K.cnoise + 1), K.cmagic, K.cshift);
+                ln.nV = noise_step(ln.nV, dv, K.cnoise);
+            }
+        }
+        if (K.flags & G_PHASE) {                                               // (:755-783)
+            CVS_UNROLL
+            for (int k = 0; k < kBC; k++) {
+                const double u = i2d(U[k] - 128), v = i2d(V[k] - 128);
+                const double u_ = dsub(dmul(u, rc.cosp), dmul(u, rc.sinp));
+                const double v_ = dadd(dmul(v, rc.cosp), dmul(v, rc.sinp));
+                U[k] = fq(dadd(u_, 128.0));
+                V[k] = fq(dadd(v_, 128.0));
+            }
+        }
+        const uint32_t uw = sat4(U[0], U[1], U[2], U[3]), vw = sat4(V[0], V[1], V[2], V[3]);
+        stw(ub, uw);                                                           // unfiltered: see Pipe422::stage_separate
+        stw(vb, vw);
+        uint32_t yw0 = sat4(Yn[0], Yn[1], Yn[2], Yn[3]), yw1 = sat4(Yn[4], Yn[5], Yn[6], Yn[7]);
+        if (K.flags & G_VHS) {
+            luma8(K, ln, yw0, yw1);
+            stw(yb, yw0);
+            stw(yb + 4, yw1);
+            uint32_t ou, ov;
+            lp_pair<false>(uw, vw, nullptr, ln.chU, nullptr, ln.chV, K.a_ch, 0.0, K.a_ch, 0.0, ou, ov);
+            put_delayed(ln.ru, b, K.cd, ou, ln.cCh[0]);
+            put_delayed(ln.rv, b, K.cd, ov, ln.cCh[1]);
+        } else {
+            stw(yb, yw0);
+            stw(yb + 4, yw1);
+        }
+    }
+
+    // G4: vertical blend (:858-883), chroma sharpen (:904-925), re-modulation (:927-930)
+    static CVS_HD void stage_vhs_chroma(const K422 &K, const Row422 &rc, Lane422 &ln, int b, uint32_t pu, uint32_t pv,
+                                        uint32_t au, uint32_t av) {
+        if ((K.flags & G_VBLEND) && rc.row >= 1) {
+            if (rc.row == 1) au = av = 0x80808080u;                            // the delay line starts at 128
+            pu = avg4_up(au, pu);
+            pv = avg4_up(av, pv);
+        }
+        uint32_t ou = 0, ov = 0;
+        CVS_ROLLED
+        for (int it = 0; it < kBC / CVS422_CU; it++) {
+            int qu[CVS422_CU], qv[CVS422_CU];
+            CVS_UNROLL
+            for (int j = 0; j < CVS422_CU; j++) {
+                const double s = fu2d((uint32_t)byte_of(pu, j)), t = fu2d((uint32_t)byte_of(pv, j));
+                double ts = pole(ln.csU[0], s, K.a_csharp), tt = pole(ln.csV[0], t, K.a_csharp);
+                ts = pole(ln.csU[1], ts, K.a_csharp); tt = pole(ln.csV[1], tt, K.a_csharp);
+                ts = pole(ln.csU[2], ts, K.a_csharp); tt = pole(ln.csV[2], tt, K.a_csharp);
+                qu[j] = fq(dadd(s, dmul(dsub(s, ts), K.sharpen_c)));
+                qv[j] = fq(dadd(t, dmul(dsub(t, tt), K.sharpen_c)));
+            }
+            push_c(ou, qu);
+            push_c(ov, qv);
+            if (CVS422_CU < 4) { pu >>= (8 * CVS422_CU) & 31; pv >>= (8 * CVS422_CU) & 31; }
+        }
+        stw(cblk(ln.ru, b), ou);
+        stw(cblk(ln.rv, b), ov);
+        if (!(K.flags & G_SVIDEO)) stage_remodulate(rc, ln, b);
+    }
+
+    // G5
+    static CVS_HD void stage_redemod(const K422 &K, const Row422 &rc, Lane422 &ln, int b) {
+        uint8_t *yb = yblk(ln.ry, b);
+        int Yn[kB], U[kBC], V[kBC];
+        Pipe422<false>::demod8(K, rc, ln.dm2, b, ldw(yb), ldw(yb + 4), ldw(yblk(ln.ry, b + 1)), 50, 0u, 0u, Yn, U, V);
+        stw(yb, sat4(Yn[0], Yn[1], Yn[2], Yn[3]));
+        stw(yb + 4, sat4(Yn[4], Yn[5], Yn[6], Yn[7]));
+        stw(cblk(ln.ru, b), sat4(U[0], U[1], U[2], U[3]));
+        stw(cblk(ln.rv, b), sat4(V[0], V[1], V[2], V[3]));
+    }
+
+    // GO
+    static CVS_HD void stage_out(const K422 &K, Lane422 &ln, int b) {
+        const uint32_t uw = ldw(cblk(ln.ru, b)), vw = ldw(cblk(ln.rv, b));
+        uint32_t ou, ov;
+        if (K.flags & G_OUT_FULL) lp_pair<true>(uw, vw, &ln.outU[0], &ln.outU[1], &ln.outV[0], &ln.outV[1], K.a_out[0], K.a_outhp[0], K.a_out[1], K.a_outhp[1], ou, ov);
+        else lp_pair<false>(uw, vw, nullptr, &ln.outU[1], nullptr, &ln.outV[1], K.a_out[0], 0.0, K.a_out[1], 0.0, ou, ov);
+        put_delayed(ln.ru, b, K.d_out[0], ou, ln.cOut[0]);
+        put_delayed(ln.rv, b, K.d_out[1], ov, ln.cOut[1]);
+    }
+};
+
+// The interior variant is entered at step s0 and left after step s1 - 1 (s1 > s0); the delayed filters' carries
+// are picked up from / handed back to the rings the edge variant works on.
+CVS_HD void interior_enter(const K422 &K, const Lags &L, Lane422 &ln, int s0) {
+    if (K.flags & G_IN_LP) {
+        Fast422::carry_enter(ln.ru, s0, K.d_in[0], ln.cIn[0]);
+        Fast422::carry_enter(ln.rv, s0, K.d_in[1], ln.cIn[1]);
+    }
+    if (K.flags & G_VHS) {
+        Fast422::carry_enter(ln.ru, s0 - L.bD, K.cd, ln.cCh[0]);
+        Fast422::carry_enter(ln.rv, s0 - L.bD, K.cd, ln.cCh[1]);
+    }
+    if (K.flags & (G_OUT_FULL | G_OUT_LITE)) {
+        Fast422::carry_enter(ln.ru, s0 - L.bF, K.d_out[0], ln.cOut[0]);
+        Fast422::carry_enter(ln.rv, s0 - L.bF, K.d_out[1], ln.cOut[1]);
+    }
+}
+CVS_HD void interior_leave(const K422 &K, const Lags &L, Lane422 &ln, int s1) {
+    const int s = s1 - 1;
+    if (K.flags & G_IN_LP) {
+        Fast422::carry_leave(ln.ru, s, K.d_in[0], ln.cIn[0]);
+        Fast422::carry_leave(ln.rv, s, K.d_in[1], ln.cIn[1]);
+    }
+    if (K.flags & G_VHS) {
+        Fast422::carry_leave(ln.ru, s - L.bD, K.cd, ln.cCh[0]);
+        Fast422::carry_leave(ln.rv, s - L.bD, K.cd, ln.cCh[1]);
+    }
+    if (K.flags & (G_OUT_FULL | G_OUT_LITE)) {
+        Fast422::carry_leave(ln.ru, s - L.bF, K.d_out[0], ln.cOut[0]);
+        Fast422::carry_leave(ln.rv, s - L.bF, K.d_out[1], ln.cOut[1]);
+    }
+}
+
+// interior step, front half: G0..G3 and the fetch of G4
+CVS_HD void fast_front(const K422 &K, const Lags &L, const Row422 &rc, Lane422 &ln, int s, const StepIO &in, bool warp_hs,
+                       uint32_t &pu, uint32_t &pv) {
+    Fast422::stage_load(K, ln, s, in);
+    Fast422::stage_modulate_first(K, rc, ln, s - L.bM, warp_hs);
+    Fast422::stage_separate(K, rc, ln, s - L.bD);
+    pu = pv = 0;
+    if (K.flags & G_VHS) Pipe422<false>::blend_fetch(ln, s - L.bV, pu, pv);
+}
+// back half: G4..store; `out` = block s - L.bS of the finished row
+CVS_HD void fast_back(const K422 &K, const Lags &L, const Row422 &rc, Lane422 &ln, int s, uint32_t pu, uint32_t pv, uint32_t au,
+                      uint32_t av, StepIO &out, int &bs) {
+    if (K.flags & G_VHS) {
+        Fast422::stage_vhs_chroma(K, rc, ln, s - L.bV, pu, pv, au, av);
+        if (!(K.flags & G_SVIDEO)) Fast422::stage_redemod(K, rc, ln, s - L.bD2);
+    }
+    if (rc.rflags & RG_DROPOUT) Pipe422<false>::stage_dropout(ln, s - L.bE);
+    if (K.flags & (G_OUT_FULL | G_OUT_LITE)) Fast422::stage_out(K, ln, s - L.bF);
+    bs = s - L.bS;
+    const uint8_t *yb = yblk(ln.ry, bs);
+    out.y0 = ldw(yb);
+    out.y1 = ldw(yb + 4);
+    out.u = ldw(cblk(ln.ru, bs));
+    out.v = ldw(cblk(ln.rv, bs));
+}
 
 // G0..G3 (+ the fetch of G4)
 template <bool EDGE>

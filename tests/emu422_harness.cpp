@@ -128,6 +128,8 @@ int emu422_process(const cvs422_params *p, unsigned long long rng_pos,
         }
         for (int s = 0; s < nsteps; s++) {
             const bool fast = s >= s_lo && s < s_hi;
+            if (s_hi > s_lo && s == s_lo) for (int lane = 0; lane < 32; lane++) interior_enter(K, LG, ln[lane], s_lo);
+            if (s_hi > s_lo && s == s_hi) for (int lane = 0; lane < 32; lane++) interior_leave(K, LG, ln[lane], s_hi);
             uint32_t pu[32], pv[32];
             for (int lane = 0; lane < 32; lane++) {
                 const long long y = (long long)field + 2 * rows[lane];
@@ -138,7 +140,7 @@ int emu422_process(const cvs422_params *p, unsigned long long rng_pos,
                 in.y1 = load_word(sy.data(), by, y * ly + x0 + 4, w + 2 - x0 - 4);
                 in.u = load_word(su.data(), bu, y * lu + c0, K.cw - c0);
                 in.v = load_word(sv.data(), bv, y * lv + c0, K.cw - c0);
-                if (fast) step_front<false>(K, LG, GE, dv, rc[lane], ln[lane], s, in, warp_hs, hsrow[lane], pu[lane], pv[lane]);
+                if (fast) fast_front(K, LG, rc[lane], ln[lane], s, in, warp_hs, pu[lane], pv[lane]);
                 else step_front<true>(K, LG, GE, dv, rc[lane], ln[lane], s, in, warp_hs, hsrow[lane], pu[lane], pv[lane]);
                 // first demodulation of a -yc-recomb round: its box starts from the row's first two luma samples
                 // as they are when that stage reaches block 0 (handled inside demod_block via b == 0)
@@ -148,7 +150,7 @@ int emu422_process(const cvs422_params *p, unsigned long long rng_pos,
                 StepIO out;
                 int bs;
                 bool have;
-                if (fast) have = step_back<false>(K, LG, GE, dv, rc[lane], ln[lane], s, pu[lane], pv[lane], au, av, out, bs);
+                if (fast) { fast_back(K, LG, rc[lane], ln[lane], s, pu[lane], pv[lane], au, av, out, bs); have = true; }
                 else have = step_back<true>(K, LG, GE, dv, rc[lane], ln[lane], s, pu[lane], pv[lane], au, av, out, bs);
                 if (have && valid[lane]) {
                     const long long y = (long long)field + 2 * rows[lane];
