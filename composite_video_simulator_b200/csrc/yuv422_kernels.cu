@@ -15,8 +15,7 @@ cudaError_t launch_yuv422(const Launch422 &a, const HsItem422 *d_items, int nite
         k_yuv422_headswitch<<<(nitems + kHsNT - 1) / kHsNT, kHsNT, 0, st>>>(a, d_items, nitems);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
-    const int ctas = (a.total_warps + kWarps - 1) / kWarps;
-    k_yuv422<<<ctas, kNT, Smem422::total(a.K), st>>>(a);
+    k_yuv422<<<a.total_warps, kNT, Smem422::total(a.K), st>>>(a);
     return cudaGetLastError();
 }
 

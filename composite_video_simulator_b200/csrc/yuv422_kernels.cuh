@@ -20,17 +20,21 @@
 
 namespace cvs422 {
 
-#ifndef CVS422_NT
-#define CVS422_NT 128
-#endif
 #ifndef CVS422_MIN_CTAS
-#define CVS422_MIN_CTAS 2
+#define CVS422_MIN_CTAS 4
 #endif
-// Measured on B200 (1080p VHS-SP, 296 fields): 128 threads x 2 CTAs/SM (208 registers) 4.32 ms; 64 x 4 4.48 ms;
-// 64 x 5 (168 registers, spills) 5.30 ms: the third warp per scheduler does not pay for the register squeeze.
-constexpr int kNT = CVS422_NT;           // threads per CTA
-constexpr int kWarps = kNT / 32;
-constexpr int kRowsPerWarp = 31;         // lane 0 is the halo row
+#ifndef CVS422_ROTATE_ROLES
+#define CVS422_ROTATE_ROLES 0
+#endif
+// One CTA = one group of 31 consecutive rows (+ the halo lane) = kRoles warps: warp r runs role r (yuv422_pipeline.cuh,
+// "roles") for all rows of the group, the rings in shared memory are the group's, and the four warps meet at a
+// barrier after every step.  Why: a lane that runs every stage of its row needs ~210 registers (35 doubles of
+// filter state) -- 2 warps per scheduler, each of them an in-order stream of dependent 8-cycle FP64 operations and
+// 4-cycle integer chains that the FP64 pipe (one instruction per 2 cycles per scheduler) spends half its time
+// waiting for (round 1 / 2: 0.45 of the pipe, scripts/probes/fp64_probe.cu).  Split by role, a warp holds a
+// quarter of the state, so 16+ warps fit on an SM and the pipe always finds a ready warp.
+constexpr int kNT = 32 * kRoles;         // threads per CTA
+constexpr int kRowsPerWarp = 31;         // rows per group; lane 0 is the halo row
 constexpr int kStrideY = kRingY + 4;     // per-lane ring strides: +1 word so that equal offsets of the 32 lanes
 constexpr int kStrideC = kRingC + 4;     // fall into 32 different banks
 constexpr int kStrideA = kRingA + 4;
@@ -68,14 +72,13 @@ struct Launch422 {
     int32_t *status;
 };
 
-// Dynamic shared memory of k_yuv422: the per-lane rings, then one generator ring per noise stream that is ON
-// (16 KB each for 128 lanes: with the default -chroma-noise 0 a third CTA fits on an SM).
+// Dynamic shared memory of k_yuv422: the group's rings, then one generator ring per noise stream that is ON
 struct Smem422 {
-    static constexpr size_t rng1 = (size_t)kRngSlots * kNT * sizeof(uint32_t);            // one stream
-    static constexpr size_t wins = (size_t)kWarps * 128 * sizeof(uint32_t);   // two fields can meet in a warp
-    static constexpr size_t ry = (size_t)kNT * kStrideY, rya = (size_t)kNT * kStrideA;
-    static constexpr size_t rc = (size_t)kNT * kStrideC;
-    static constexpr size_t rcomb = (size_t)kNT * 3 * kMaxRecombine * sizeof(int32_t);
+    static constexpr size_t rng1 = (size_t)kRngSlots * 32 * sizeof(uint32_t);             // one stream
+    static constexpr size_t wins = (size_t)2 * 128 * sizeof(uint32_t);        // per stream; two fields can meet in a group
+    static constexpr size_t ry = (size_t)32 * kStrideY, rya = (size_t)32 * kStrideA;
+    static constexpr size_t rc = (size_t)32 * kStrideC;
+    static constexpr size_t rcomb = (size_t)32 * 3 * kMaxRecombine * sizeof(int32_t);
     static constexpr size_t off_wins = 0, off_ry = off_wins + wins, off_rya = off_ry + ry, off_ru = off_rya + rya,
                             off_rv = off_ru + rc, off_rcomb = off_rv + rc, off_rng = off_rcomb + rcomb;
     static constexpr size_t total_max = off_rng + 2 * rng1;
@@ -197,23 +200,6 @@ __device__ __forceinline__ void store_block(uint8_t *y, uint8_t *u, uint8_t *v, 
     }
 }
 
-template <bool EDGE>
-__device__ __forceinline__ void one_step(const K422 &K, const Lags &L, const Geo &G, const DivPair &dv, const Row422 &rc, Lane422 &ln, int s,
-                                         const StepIO &in, bool warp_hs, const uint8_t *hsrow, bool valid,
-                                         uint8_t *dy, uint8_t *du, uint8_t *dvp, bool vec) {
-    uint32_t pu, pv;
-    step_front<EDGE>(K, L, G, dv, rc, ln, s, in, warp_hs, hsrow, pu, pv);
-    uint32_t au = 0, av = 0;
-    if (K.flags & G_VHS) {
-        au = __shfl_up_sync(0xffffffffu, pu, 1);
-        av = __shfl_up_sync(0xffffffffu, pv, 1);
-    }
-    StepIO out;
-    int bs;
-    const bool have = step_back<EDGE>(K, L, G, dv, rc, ln, s, pu, pv, au, av, out, bs);
-    if (have && valid) store_block<EDGE>(dy, du, dvp, K, bs, vec, out);
-}
-
 __device__ __forceinline__ void load_block_vec(const LaneSrc &src, int s, StepIO &io) {
     const uint2 yy = *reinterpret_cast<const uint2 *>(src.y + s * kB);
     io.y0 = yy.x; io.y1 = yy.y;
@@ -221,38 +207,50 @@ __device__ __forceinline__ void load_block_vec(const LaneSrc &src, int s, StepIO
     io.v = *reinterpret_cast<const uint32_t *>(src.v + s * kBC);
 }
 
-// one step of the interior variant (whole blocks, aligned rows): yuv422_pipeline.cuh, Fast422
-__device__ __forceinline__ void interior_step(const K422 &K, const Lags &L, const Row422 &rc, Lane422 &ln, int s, const StepIO &in,
-                                              bool warp_hs, bool valid, uint8_t *dy, uint8_t *du, uint8_t *dvp) {
-    uint32_t pu, pv;
-    fast_front(K, L, rc, ln, s, in, warp_hs, pu, pv);
-    uint32_t au = 0, av = 0;
-    if (K.flags & G_VHS) {
-        au = __shfl_up_sync(0xffffffffu, pu, 1);
-        av = __shfl_up_sync(0xffffffffu, pv, 1);
+__device__ __forceinline__ void group_barrier() { asm volatile("bar.sync 0;" ::: "memory"); }
+
+// what every role of a row knows
+struct RowCtx {
+    const K422 *K;
+    const DivPair *dv;
+    Lags L;
+    Geo G;
+    Row422 rc;
+    int nsteps, lo, hi;                   // steps of a row; the role's interior range
+};
+
+// The step loop of a role: general steps up to lo, interior steps [lo, hi), general steps to the end, a barrier of
+// the group after every step.  STEP(s, edge) is the role's step.
+#define CVS422_ROLE_LOOP(ROLE, STEP_EDGE, STEP_FAST)                                    \
+    {                                                                                   \
+        int s = 0;                                                                      \
+        const int s_a = cx.lo < cx.nsteps ? cx.lo : cx.nsteps;                          \
+        _Pragma("unroll 1") for (; s < s_a; s++) { STEP_EDGE; group_barrier(); }        \
+        if (s < cx.hi) {                                                                \
+            role_enter(K, cx.L, ln, ROLE, s);                                           \
+            _Pragma("unroll 1") for (; s < cx.hi; s++) { STEP_FAST; group_barrier(); }  \
+            role_leave(K, cx.L, ln, ROLE, s);                                           \
+        }                                                                               \
+        _Pragma("unroll 1") for (; s < cx.nsteps; s++) { STEP_EDGE; group_barrier(); }  \
     }
-    StepIO o;
-    int bs;
-    fast_back(K, L, rc, ln, s, pu, pv, au, av, o, bs);
-    if (valid) {
-        *reinterpret_cast<uint2 *>(dy + bs * kB) = make_uint2(o.y0, o.y1);
-        *reinterpret_cast<uint32_t *>(du + bs * kBC) = o.u;
-        *reinterpret_cast<uint32_t *>(dvp + bs * kBC) = o.v;
-    }
-}
 
 __global__ void __launch_bounds__(kNT, CVS422_MIN_CTAS) k_yuv422(const __grid_constant__ Launch422 a) {
     extern __shared__ __align__(16) unsigned char smem[];
-    uint32_t *wins = reinterpret_cast<uint32_t *>(smem + Smem422::off_wins);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int gw = blockIdx.x * kWarps + warp;
-    if (gw >= a.total_warps) return;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int gw = blockIdx.x;            // the group of rows
+    // Warp k of a CTA sits on scheduler k: with role = warp every role-0 warp of an SM would share ONE scheduler (and
+    // the roles are not equally long), so the assignment rotates with the group.
+#if CVS422_ROTATE_ROLES
+    const int role = ((tid >> 5) + gw) & (kRoles - 1);
+#else
+    const int role = tid >> 5;
+#endif
     const K422 &K = a.K;
     const int w = K.w;
     // which field row this lane computes (lane 0 = the halo row: the row above lane 1's)
     int fi, row;
     bool valid;
-    const uint8_t *halo_rec;             // this warp's halo record
+    const uint8_t *halo_rec;             // this group's halo record
     if (a.packed) {
         int g = kRowsPerWarp * gw + lane - 1;
         valid = (lane >= 1) && g < a.total_rows;
@@ -266,7 +264,7 @@ __global__ void __launch_bounds__(kNT, CVS422_MIN_CTAS) k_yuv422(const __grid_co
     } else {
         fi = gw / a.warps_per_field;
         const int wp = gw - fi * a.warps_per_field, nlw = a.fields[fi].nl;
-        if (kRowsPerWarp * wp >= nlw) return;
+        if (kRowsPerWarp * wp >= nlw) return;                 // (the whole group)
         row = kRowsPerWarp * wp + lane - 1;
         valid = (lane >= 1) && row < nlw;
         row = row < 0 ? 0 : (row > nlw - 1 ? nlw - 1 : row);
@@ -275,10 +273,34 @@ __global__ void __launch_bounds__(kNT, CVS422_MIN_CTAS) k_yuv422(const __grid_co
     const FieldDesc422 &fd = a.fields[fi];
     // lane 0 re-reads the row above lane 1's row from the copy k_yuv422_halo took, unless lane 1 is row 0
     const bool halo_copy = __shfl_sync(0xffffffffu, row, 1) >= 1;
+    const long long y = (long long)fd.field + 2 * row;
 
-    // generator windows of the (at most two) fields of this warp: [0,64) the field of lane 1, [64,128) that of lane 31
-    uint32_t *win = wins + warp * 128;
+    Lane422 ln;
+    ln.reset();
+    ln.ry = smem + Smem422::off_ry + (size_t)lane * kStrideY;
+    ln.rya = smem + Smem422::off_rya + (size_t)lane * kStrideA;
+    ln.ru = smem + Smem422::off_ru + (size_t)lane * kStrideC;
+    ln.rv = smem + Smem422::off_rv + (size_t)lane * kStrideC;
+    ln.rcomb = reinterpret_cast<int32_t *>(smem + Smem422::off_rcomb) + (size_t)lane * 3 * kMaxRecombine;
+
+    RowCtx cx;
+    cx.K = &K;
+    cx.dv = &a.dv;
+    cx.L = lags_of(K);
+    cx.G = geo_of(K);
+    cx.nsteps = line_steps(K);
+    row_setup(K, (unsigned)fd.field, fd.fieldno, row, __ldg(fd.rowinfo + row), cx.rc);
+    const Row422 &rc = cx.rc;
     {
+        const RoleRange rr = role_interior(K, cx.L, role);
+        cx.lo = rr.lo;
+        cx.hi = a.vec ? rr.hi : rr.lo;    // the interior variant moves whole words; unaligned pictures take the general one
+    }
+
+    // the generator of a noise stream lives in the role that draws from it: luma in role 0, chroma in role 1
+    if ((role == 0 && K.vnoise != 0) || (role == 1 && K.cnoise != 0)) {
+        // generator windows of the (at most two) fields of this group: [0,64) the field of lane 1, [64,128) that of lane 31
+        uint32_t *win = reinterpret_cast<uint32_t *>(smem + Smem422::off_wins) + role * 128;
         const int fiA = __shfl_sync(0xffffffffu, fi, 1), fiB = __shfl_sync(0xffffffffu, fi, 31);
         win[lane] = a.fields[fiA].window[lane];
         win[lane + 32] = a.fields[fiA].window[lane + 32];
@@ -286,97 +308,69 @@ __global__ void __launch_bounds__(kNT, CVS422_MIN_CTAS) k_yuv422(const __grid_co
         win[lane + 96] = a.fields[fiB].window[lane + 32];
         __syncwarp();
         if (fi != fiA) win += 64;
-    }
-    const long long y = (long long)fd.field + 2 * row;
-
-    Lane422 ln;
-    ln.reset();
-    ln.ry = smem + Smem422::off_ry + (size_t)tid * kStrideY;
-    ln.rya = smem + Smem422::off_rya + (size_t)tid * kStrideA;
-    ln.ru = smem + Smem422::off_ru + (size_t)tid * kStrideC;
-    ln.rv = smem + Smem422::off_rv + (size_t)tid * kStrideC;
-    ln.rcomb = reinterpret_cast<int32_t *>(smem + Smem422::off_rcomb) + (size_t)tid * 3 * kMaxRecombine;
-    for (int i = 0; i < 3 * kMaxRecombine; i++) ln.rcomb[i] = 16;
-
-    Row422 rc;
-    row_setup(K, (unsigned)fd.field, fd.fieldno, row, __ldg(fd.rowinfo + row), rc);
-
-    // rows: lanes 1..31 read the picture; the halo lane of warps 1.. reads the copy k_yuv422_halo took
-    LaneSrc src;
-    if (lane == 0 && halo_copy) {
-        const uint8_t *hr = halo_rec;
-        src.y = hr; src.u = hr + a.halo_u; src.v = hr + a.halo_v;
-        src.y_avail = w + 2;
-    } else {
-        src.y = fd.y + y * a.ly; src.u = fd.u + y * a.lu; src.v = fd.v + y * a.lv;
-        const long long left = a.by - y * a.ly;            // bytes of the plane from the row start
-        src.y_avail = (int)(left < (long long)(w + 2) ? left : (long long)(w + 2));
-    }
-    uint8_t *dy = fd.y + y * a.ly, *du = fd.u + y * a.lu, *dvp = fd.v + y * a.lv;
-    const uint8_t *hsrow = (rc.rflags & RG_HEADSW_PRE) ? fd.hs_scratch + (size_t)(row - fd.hs_first) * (size_t)w : nullptr;
-
-    {
-        bool ok = true;
         uint32_t hist[31];
-        if (K.vnoise != 0) {
+        bool ok;
+        if (role == 0) {
             const long long pre = (long long)row * w;
             const int nd = (int)(pre < kWarm ? pre : kWarm);
             rebase422(win, fd.seek + (size_t)row * 62, hist);
-            ln.rngL.init(reinterpret_cast<uint32_t *>(smem + Smem422::off_rng) + tid, kNT, hist, kRngBase - (uint32_t)nd);
-            ok &= cvs::warm_luma((uint32_t)(2 * K.vnoise + 1), K.vmagic, K.vshift, K.vnoise, ln.rngL, nd, pre <= kWarm, ln.nY);
-        }
-        if (K.cnoise != 0) {
+            ln.rngL.init(reinterpret_cast<uint32_t *>(smem + Smem422::off_rng) + lane, 32, hist, kRngBase - (uint32_t)nd);
+            ok = cvs::warm_luma((uint32_t)(2 * K.vnoise + 1), K.vmagic, K.vshift, K.vnoise, ln.rngL, nd, pre <= kWarm, ln.nY);
+        } else {
             const long long pre = (long long)row * K.cw;
             const int nd = (int)(pre < kWarm ? pre : kWarm);
             rebase422(win, fd.seek + (size_t)row * 62 + 31, hist);
-            ln.rngC.init(reinterpret_cast<uint32_t *>(smem + Smem422::off_rng_chroma(K)) + tid, kNT, hist, kRngBase - 2u * (uint32_t)nd);
-            ok &= cvs::warm_chroma((uint32_t)(2 * K.cnoise + 1), K.cmagic, K.cshift, K.cnoise, ln.rngC, nd, pre <= kWarm, ln.nU, ln.nV);
+            ln.rngC.init(reinterpret_cast<uint32_t *>(smem + Smem422::off_rng_chroma(K)) + lane, 32, hist, kRngBase - 2u * (uint32_t)nd);
+            ok = cvs::warm_chroma((uint32_t)(2 * K.cnoise + 1), K.cmagic, K.cshift, K.cnoise, ln.rngC, nd, pre <= kWarm, ln.nU, ln.nV);
         }
         if (!ok) atomicOr(a.status, 1);
     }
 
-    const int nsteps = line_steps(K);
-    const Lags LG = lags_of(K);
-    const Geo GE = geo_of(K);
-    int s_lo, s_hi;
-    interior_steps(K, s_lo, s_hi);
-    const bool warp_hs = __any_sync(0xffffffffu, rc.hs_delay > 0);
-    if (__any_sync(0xffffffffu, hsrow != nullptr)) s_hi = s_lo;      // pre-pass rows only exist in the general variant
-    const bool vec = a.vec != 0;          // (halo records are 16-byte aligned, so the halo lane qualifies too)
-    const bool vec_ld = vec;
-    if (!vec) s_hi = s_lo;                // the interior variant moves whole words; unaligned pictures take the general one
-
-    StepIO cur;
-    load_block<true>(src, K, 0, vec_ld, cur);
-    int s = 0;
-#pragma unroll 1
-    for (int pass = 0; pass < 2; pass++) {
-        const int s_end = (pass == 0) ? (s_lo < nsteps ? s_lo : nsteps) : nsteps;
-#pragma unroll 1
-        for (; s < s_end; s++) {
-            StepIO nxt;
-            load_block<true>(src, K, s + 1, vec_ld, nxt);
-            one_step<true>(K, LG, GE, a.dv, rc, ln, s, cur, warp_hs, hsrow, valid, dy, du, dvp, vec);
-            cur = nxt;
+    if (role == 0) {
+        // rows: lanes 1..31 read the picture; the halo lane of groups 1.. reads the copy k_yuv422_halo took
+        LaneSrc src;
+        if (lane == 0 && halo_copy) {
+            const uint8_t *hr = halo_rec;
+            src.y = hr; src.u = hr + a.halo_u; src.v = hr + a.halo_v;
+            src.y_avail = w + 2;
+        } else {
+            src.y = fd.y + y * a.ly; src.u = fd.u + y * a.lu; src.v = fd.v + y * a.lv;
+            const long long left = a.by - y * a.ly;            // bytes of the plane from the row start
+            src.y_avail = (int)(left < (long long)(w + 2) ? left : (long long)(w + 2));
         }
-        if (pass == 0 && s < s_hi) {
-            interior_enter(K, LG, ln, s);
-#pragma unroll 1
-            for (; s < s_hi - 1; s++) {
-                StepIO nxt;
-                load_block_vec(src, s + 1, nxt);
-                interior_step(K, LG, rc, ln, s, cur, warp_hs, valid, dy, du, dvp);
-                cur = nxt;
-            }
-            {
-                StepIO nxt;
-                load_block<true>(src, K, s + 1, vec_ld, nxt);
-                interior_step(K, LG, rc, ln, s, cur, warp_hs, valid, dy, du, dvp);
-                cur = nxt;
-                s++;
-            }
-            interior_leave(K, LG, ln, s);
-        }
+        const uint8_t *hsrow = (rc.rflags & RG_HEADSW_PRE) ? fd.hs_scratch + (size_t)(row - fd.hs_first) * (size_t)w : nullptr;
+        const bool warp_hs = __any_sync(0xffffffffu, rc.hs_delay > 0);
+        if (__any_sync(0xffffffffu, hsrow != nullptr)) cx.hi = cx.lo;    // pre-pass rows only exist in the general variant
+        const bool vec = a.vec != 0;      // (halo records are 16-byte aligned, so the halo lane qualifies too)
+        StepIO cur, nxt;
+        load_block<true>(src, K, 0, vec, cur);
+        CVS422_ROLE_LOOP(0,
+            (load_block<true>(src, K, s + 1, vec, nxt), role0_step<true>(K, cx.L, cx.G, rc, ln, s, cur, warp_hs, hsrow), cur = nxt),
+            ((s + 1 < cx.hi ? load_block_vec(src, s + 1, nxt) : load_block<true>(src, K, s + 1, vec, nxt)),
+             role0_step<false>(K, cx.L, cx.G, rc, ln, s, cur, warp_hs, hsrow), cur = nxt))
+    } else if (role == 1) {
+        CVS422_ROLE_LOOP(1, role1_step<true>(K, cx.L, cx.G, a.dv, rc, ln, s), role1_step<false>(K, cx.L, cx.G, a.dv, rc, ln, s))
+    } else if (role == 2) {
+        uint32_t pu, pv, au, av;
+        CVS422_ROLE_LOOP(2,
+            (role2_front<true>(K, cx.L, cx.G, ln, s, pu, pv), au = __shfl_up_sync(0xffffffffu, pu, 1), av = __shfl_up_sync(0xffffffffu, pv, 1),
+             role2_back<true>(K, cx.L, cx.G, rc, ln, s, pu, pv, au, av)),
+            (role2_front<false>(K, cx.L, cx.G, ln, s, pu, pv), au = __shfl_up_sync(0xffffffffu, pu, 1), av = __shfl_up_sync(0xffffffffu, pv, 1),
+             role2_back<false>(K, cx.L, cx.G, rc, ln, s, pu, pv, au, av)))
+    } else {
+        for (int i = 0; i < 3 * kMaxRecombine; i++) ln.rcomb[i] = 16;
+        uint8_t *dy = fd.y + y * a.ly, *du = fd.u + y * a.lu, *dvp = fd.v + y * a.lv;
+        const bool vec = a.vec != 0;
+        StepIO o;
+        int bs;
+        CVS422_ROLE_LOOP(3,
+            { if (role3_step<true>(K, cx.L, cx.G, a.dv, rc, ln, s, o, bs) && valid) store_block<true>(dy, du, dvp, K, bs, vec, o); },
+            { role3_step<false>(K, cx.L, cx.G, a.dv, rc, ln, s, o, bs);
+              if (valid) {
+                  *reinterpret_cast<uint2 *>(dy + bs * kB) = make_uint2(o.y0, o.y1);
+                  *reinterpret_cast<uint32_t *>(du + bs * kBC) = o.u;
+                  *reinterpret_cast<uint32_t *>(dvp + bs * kBC) = o.v;
+              } })
     }
 }
 

@@ -95,18 +95,26 @@ struct K422 {
     int32_t w, h, cw;
 };
 
-// block lags of a configuration (blocks behind the load front)
+// Block lags of a configuration (blocks behind the load front: a stage works on block s - lag at step s).
+// A row is worked on by FOUR warps at once, one per ROLE (a group of consecutive stages); the roles of a row meet at
+// a barrier after every step, so a role reads what the previous role wrote in an EARLIER step: one extra block of
+// lag at every role boundary.
+//   role 0: G0 G1 G2      load, input chroma lowpass, first modulation (luma noise, head switch)
+//   role 1: G3            Y/C separation, chroma / phase noise, VHS luma lowpass + boost, VHS chroma lowpass
+//   role 2: G4            VHS luma sharpen, vertical blend, chroma sharpen
+//   role 3: G5 GE GO ST   re-modulation, second demodulation, dropout, -yc-recomb, output chroma lowpass, store
+constexpr int kRoles = 4;
 struct Lags {
     int bM, bD, bV, bD2, bE, bF, bS;      // as offsets: block = s - lag
 };
 CVS_HD Lags lags_of(const K422 &K) {
     Lags L;
-    L.bM = 1;
-    L.bD = 2;
-    L.bV = L.bD + K.lagV;
-    L.bD2 = L.bV + 1;
     const bool vhs = (K.flags & G_VHS) != 0, sv = (K.flags & G_SVIDEO) != 0;
-    L.bE = vhs ? (sv ? L.bV : L.bD2) : L.bD;
+    L.bM = 1;                             // the input lowpass writes up to 4 samples back
+    L.bD = L.bM + 2;                      // demodulation reads two bytes of the next block; role boundary
+    L.bV = L.bD + K.lagV + 1;             // the VHS chroma lowpass writes 4..6 samples back; role boundary
+    L.bD2 = L.bV + 2;                     // as bD
+    L.bE = vhs ? (sv ? L.bV + 1 : L.bD2) : L.bD + 1;
     L.bF = L.bE + K.recombine;
     L.bS = L.bF + 1;
     return L;
@@ -569,27 +577,41 @@ struct Pipe422 {
         stw(vb, vw);
         if (K.flags & G_VHS) {
             CVS_UNROLL
-            for (int j = 0; j < kB; j++) {                                     // luma lowpass + boost, then sharpen
+            for (int j = 0; j < kB; j++) {                                     // luma lowpass + boost (:810-828)
                 if (in(x0 + j, K.w)) {
                     double s = u2d((uint32_t)Yn[j]);
                     s = pole(ln.lum[0], s, K.a_luma);
                     s = pole(ln.lum[1], s, K.a_luma);
                     s = pole(ln.lum[2], s, K.a_luma);
                     const double lpv = pole(ln.lum[3], s, K.a_luma);
-                    s = dadd(s, dmul(dsub(s, lpv), 1.6));
-                    const double y1d = u2d((uint32_t)q8(s));
-                    double ts = pole(ln.lsh[0], y1d, K.a_lsharp);
-                    ts = pole(ln.lsh[1], ts, K.a_lsharp);
-                    ts = pole(ln.lsh[2], ts, K.a_lsharp);
-                    Yn[j] = q8(dadd(y1d, dmul(dsub(y1d, ts), K.sharpen)));
+                    Yn[j] = q8(dadd(s, dmul(dsub(s, lpv), 1.6)));
                 }
             }
             store_luma(K, yb, x0, Yn, y0, y1);
-            chroma_lp4(K, ln.ru, b, uw, nullptr, ln.chU, K.a_ch, 0.0, K.cd);   // written cd samples back
+            chroma_lp4(K, ln.ru, b, uw, nullptr, ln.chU, K.a_ch, 0.0, K.cd);   // written cd samples back (:830-851)
             chroma_lp4(K, ln.rv, b, vw, nullptr, ln.chV, K.a_ch, 0.0, K.cd);
         } else {
             store_luma(K, yb, x0, Yn, y0, y1);
         }
+    }
+    // G4a: VHS luma sharpen of block b (:888-901); the lowpassed luma is an 8-bit plane in the reference too
+    static CVS_HD void stage_luma_sharpen(const K422 &K, Lane422 &ln, int b) {
+        const int x0 = b * kB;
+        uint8_t *yb = yblk(ln.ry, b);
+        const uint32_t y0 = ldw(yb), y1 = ldw(yb + 4);
+        int Yn[kB];
+        CVS_UNROLL
+        for (int j = 0; j < kB; j++) {
+            Yn[j] = byte_of(j < 4 ? y0 : y1, j & 3);
+            if (in(x0 + j, K.w)) {
+                const double y1d = u2d((uint32_t)Yn[j]);
+                double ts = pole(ln.lsh[0], y1d, K.a_lsharp);
+                ts = pole(ln.lsh[1], ts, K.a_lsharp);
+                ts = pole(ln.lsh[2], ts, K.a_lsharp);
+                Yn[j] = q8(dadd(y1d, dmul(dsub(y1d, ts), K.sharpen)));
+            }
+        }
+        store_luma(K, yb, x0, Yn, y0, y1);
     }
 
     // G4 part 1: the lane's own chroma of block b before the vertical blend (what the lane below needs)
@@ -624,7 +646,6 @@ struct Pipe422 {
         }
         stw(cblk(ln.ru, b), pack4(U[0], U[1], U[2], U[3]));
         stw(cblk(ln.rv, b), pack4(V[0], V[1], V[2], V[3]));
-        if (!(K.flags & G_SVIDEO)) stage_modulate<false>(K, rc, ln, b, false, nullptr);
     }
 
     // a demodulation whose result goes straight back into the rings (VHS recombine, -yc-recomb)
@@ -771,26 +792,15 @@ struct Fast422 {
         stw(yb + 4, sat4(yo[4], yo[5], yo[6], yo[7]));
     }
 
-    // VHS luma: lowpass + boost, then sharpen (:810-828, :888-901), 8 pixels in yw0:yw1 -> the same words
-    static CVS_HD void luma8(const K422 &K, Lane422 &ln, uint32_t &yw0, uint32_t &yw1) {
+    // 8 luma pixels in yw0:yw1 -> the same words through a rolled per-pixel loop; F(double) -> double is the filter
+    template <class F>
+    static CVS_HD void luma8(uint32_t &yw0, uint32_t &yw1, F f) {
         uint32_t o0 = 0, o1 = 0;
         CVS_ROLLED
         for (int it = 0; it < kB / CVS422_LU; it++) {
             int q[CVS422_LU];
             CVS_UNROLL
-            for (int j = 0; j < CVS422_LU; j++) {
-                double s = fu2d((uint32_t)byte_of(j < 4 ? yw0 : yw1, j & 3));
-                s = pole(ln.lum[0], s, K.a_luma);
-                s = pole(ln.lum[1], s, K.a_luma);
-                s = pole(ln.lum[2], s, K.a_luma);
-                const double lpv = pole(ln.lum[3], s, K.a_luma);
-                s = dadd(s, dmul(dsub(s, lpv), 1.6));
-                const double y1d = fu2d((uint32_t)sat1(fq(s)));
-                double ts = pole(ln.lsh[0], y1d, K.a_lsharp);
-                ts = pole(ln.lsh[1], ts, K.a_lsharp);
-                ts = pole(ln.lsh[2], ts, K.a_lsharp);
-                q[j] = fq(dadd(y1d, dmul(dsub(y1d, ts), K.sharpen)));
-            }
+            for (int j = 0; j < CVS422_LU; j++) q[j] = fq(f(fu2d((uint32_t)byte_of(j < 4 ? yw0 : yw1, j & 3))));
             if (CVS422_LU == 8) {
                 o0 = sat4(q[0], q[1 % CVS422_LU], q[2 % CVS422_LU], q[3 % CVS422_LU]);
                 o1 = sat4(q[4 % CVS422_LU], q[5 % CVS422_LU], q[6 % CVS422_LU], q[7 % CVS422_LU]);
@@ -809,6 +819,33 @@ struct Fast422 {
         }
         yw0 = o0;
         yw1 = o1;
+    }
+    struct LumaLp {                       // VHS luma lowpass + boost (:810-828)
+        Lane422 &ln; const K422 &K;
+        CVS_HD double operator()(double s) const {
+            s = pole(ln.lum[0], s, K.a_luma);
+            s = pole(ln.lum[1], s, K.a_luma);
+            s = pole(ln.lum[2], s, K.a_luma);
+            const double lpv = pole(ln.lum[3], s, K.a_luma);
+            return dadd(s, dmul(dsub(s, lpv), 1.6));
+        }
+    };
+    struct LumaSharpen {                  // VHS luma sharpen (:888-901)
+        Lane422 &ln; const K422 &K;
+        CVS_HD double operator()(double y1d) const {
+            double ts = pole(ln.lsh[0], y1d, K.a_lsharp);
+            ts = pole(ln.lsh[1], ts, K.a_lsharp);
+            ts = pole(ln.lsh[2], ts, K.a_lsharp);
+            return dadd(y1d, dmul(dsub(y1d, ts), K.sharpen));
+        }
+    };
+    // G4a
+    static CVS_HD void stage_luma_sharpen(const K422 &K, Lane422 &ln, int b) {
+        uint8_t *yb = yblk(ln.ry, b);
+        uint32_t yw0 = ldw(yb), yw1 = ldw(yb + 4);
+        luma8(yw0, yw1, LumaSharpen{ln, K});
+        stw(yb, yw0);
+        stw(yb + 4, yw1);
     }
 
     // G3
@@ -845,7 +882,7 @@ struct Fast422 {
         stw(vb, vw);
         uint32_t yw0 = sat4(Yn[0], Yn[1], Yn[2], Yn[3]), yw1 = sat4(Yn[4], Yn[5], Yn[6], Yn[7]);
         if (K.flags & G_VHS) {
-            luma8(K, ln, yw0, yw1);
+            luma8(yw0, yw1, LumaLp{ln, K});
             stw(yb, yw0);
             stw(yb + 4, yw1);
             uint32_t ou, ov;
@@ -858,7 +895,7 @@ struct Fast422 {
         }
     }
 
-    // G4: vertical blend (:858-883), chroma sharpen (:904-925), re-modulation (:927-930)
+    // G4: vertical blend (:858-883), chroma sharpen (:904-925)
     static CVS_HD void stage_vhs_chroma(const K422 &K, const Row422 &rc, Lane422 &ln, int b, uint32_t pu, uint32_t pv,
                                         uint32_t au, uint32_t av) {
         if ((K.flags & G_VBLEND) && rc.row >= 1) {
@@ -885,7 +922,6 @@ struct Fast422 {
         }
         stw(cblk(ln.ru, b), ou);
         stw(cblk(ln.rv, b), ov);
-        if (!(K.flags & G_SVIDEO)) stage_remodulate(rc, ln, b);
     }
 
     // G5
@@ -910,122 +946,153 @@ struct Fast422 {
     }
 };
 
-// The interior variant is entered at step s0 and left after step s1 - 1 (s1 > s0); the delayed filters' carries
-// are picked up from / handed back to the rings the edge variant works on.
-CVS_HD void interior_enter(const K422 &K, const Lags &L, Lane422 &ln, int s0) {
-    if (K.flags & G_IN_LP) {
+// ---- roles -------------------------------------------------------------------------------------------------
+// One step of each role, in the general (EDGE: any block, any switch) and the interior variant.  A role enters its
+// interior range [lo, hi) with role_enter() and leaves it with role_leave(): the delayed filters' carries are
+// picked up from / handed back to the rings the general variant works on.
+struct RoleRange {
+    int lo, hi;                           // interior steps of a role: every block it touches is a whole block >= 2
+};
+CVS_HD RoleRange role_interior(const K422 &K, const Lags &L, int role) {
+    const int nb_full = K.w / kB;
+    const bool vhs = (K.flags & G_VHS) != 0, sv = (K.flags & G_SVIDEO) != 0;
+    int lmin, lmax;                       // youngest / oldest block of the role
+    if (role == 0) { lmin = 0; lmax = L.bM; }
+    else if (role == 1) { lmin = lmax = L.bD; }
+    else if (role == 2) { lmin = lmax = L.bV; }
+    else { lmin = (vhs && !sv) ? L.bV + 1 : L.bE; lmax = L.bS; }
+    RoleRange r;
+    r.lo = lmax + 2;
+    if (role == 0) r.lo = L.bM + kHsMaxDelay / kB + 1;          // the head-switch delay line reads up to kHsMaxDelay pixels back
+    r.hi = nb_full + lmin;
+    if (r.hi < r.lo || (K.flags & G_GENERAL)) r.hi = r.lo;      // rare switches only exist in the general variant
+    return r;
+}
+CVS_HD void role_enter(const K422 &K, const Lags &L, Lane422 &ln, int role, int s0) {
+    if (role == 0 && (K.flags & G_IN_LP)) {
         Fast422::carry_enter(ln.ru, s0, K.d_in[0], ln.cIn[0]);
         Fast422::carry_enter(ln.rv, s0, K.d_in[1], ln.cIn[1]);
     }
-    if (K.flags & G_VHS) {
+    if (role == 1 && (K.flags & G_VHS)) {
         Fast422::carry_enter(ln.ru, s0 - L.bD, K.cd, ln.cCh[0]);
         Fast422::carry_enter(ln.rv, s0 - L.bD, K.cd, ln.cCh[1]);
     }
-    if (K.flags & (G_OUT_FULL | G_OUT_LITE)) {
+    if (role == 3 && (K.flags & (G_OUT_FULL | G_OUT_LITE))) {
         Fast422::carry_enter(ln.ru, s0 - L.bF, K.d_out[0], ln.cOut[0]);
         Fast422::carry_enter(ln.rv, s0 - L.bF, K.d_out[1], ln.cOut[1]);
     }
 }
-CVS_HD void interior_leave(const K422 &K, const Lags &L, Lane422 &ln, int s1) {
-    const int s = s1 - 1;
-    if (K.flags & G_IN_LP) {
+CVS_HD void role_leave(const K422 &K, const Lags &L, Lane422 &ln, int role, int s1) {
+    const int s = s1 - 1;                 // the last interior step
+    if (role == 0 && (K.flags & G_IN_LP)) {
         Fast422::carry_leave(ln.ru, s, K.d_in[0], ln.cIn[0]);
         Fast422::carry_leave(ln.rv, s, K.d_in[1], ln.cIn[1]);
     }
-    if (K.flags & G_VHS) {
+    if (role == 1 && (K.flags & G_VHS)) {
         Fast422::carry_leave(ln.ru, s - L.bD, K.cd, ln.cCh[0]);
         Fast422::carry_leave(ln.rv, s - L.bD, K.cd, ln.cCh[1]);
     }
-    if (K.flags & (G_OUT_FULL | G_OUT_LITE)) {
+    if (role == 3 && (K.flags & (G_OUT_FULL | G_OUT_LITE))) {
         Fast422::carry_leave(ln.ru, s - L.bF, K.d_out[0], ln.cOut[0]);
         Fast422::carry_leave(ln.rv, s - L.bF, K.d_out[1], ln.cOut[1]);
     }
 }
 
-// interior step, front half: G0..G3 and the fetch of G4
-CVS_HD void fast_front(const K422 &K, const Lags &L, const Row422 &rc, Lane422 &ln, int s, const StepIO &in, bool warp_hs,
-                       uint32_t &pu, uint32_t &pv) {
-    Fast422::stage_load(K, ln, s, in);
-    Fast422::stage_modulate_first(K, rc, ln, s - L.bM, warp_hs);
-    Fast422::stage_separate(K, rc, ln, s - L.bD);
-    pu = pv = 0;
-    if (K.flags & G_VHS) Pipe422<false>::blend_fetch(ln, s - L.bV, pu, pv);
-}
-// back half: G4..store; `out` = block s - L.bS of the finished row
-CVS_HD void fast_back(const K422 &K, const Lags &L, const Row422 &rc, Lane422 &ln, int s, uint32_t pu, uint32_t pv, uint32_t au,
-                      uint32_t av, StepIO &out, int &bs) {
-    if (K.flags & G_VHS) {
-        Fast422::stage_vhs_chroma(K, rc, ln, s - L.bV, pu, pv, au, av);
-        if (!(K.flags & G_SVIDEO)) Fast422::stage_redemod(K, rc, ln, s - L.bD2);
-    }
-    if (rc.rflags & RG_DROPOUT) Pipe422<false>::stage_dropout(ln, s - L.bE);
-    if (K.flags & (G_OUT_FULL | G_OUT_LITE)) Fast422::stage_out(K, ln, s - L.bF);
-    bs = s - L.bS;
-    const uint8_t *yb = yblk(ln.ry, bs);
-    out.y0 = ldw(yb);
-    out.y1 = ldw(yb + 4);
-    out.u = ldw(cblk(ln.ru, bs));
-    out.v = ldw(cblk(ln.rv, bs));
-}
-
-// G0..G3 (+ the fetch of G4)
+// role 0: block s of the source row comes in
 template <bool EDGE>
-CVS_HD void step_front(const K422 &K, const Lags &L, const Geo &G, const DivPair &dv, const Row422 &rc, Lane422 &ln, int s,
-                       const StepIO &in, bool warp_hs, const uint8_t *hsrow, uint32_t &pu, uint32_t &pv) {
-    typedef Pipe422<EDGE> P;
-    P::stage_load(K, G, ln, s, in);
+CVS_HD void role0_step(const K422 &K, const Lags &L, const Geo &G, const Row422 &rc, Lane422 &ln, int s, const StepIO &in,
+                       bool warp_hs, const uint8_t *hsrow) {
     const int bM = s - L.bM;
-    if (!EDGE || (bM >= 0 && bM < G.nb)) P::template stage_modulate<true>(K, rc, ln, bM, warp_hs, hsrow);
-    const int bD = s - L.bD;
-    if (!EDGE || (bD >= 0 && bD < G.nb)) P::stage_separate(K, rc, ln, bD, dv.back_magic, dv.back_shift);
-    pu = pv = 0;
-    if (K.flags & G_VHS) {
-        const int bV = s - L.bV;
-        if (!EDGE || (bV >= 0 && bV < G.nb)) P::blend_fetch(ln, bV, pu, pv);
+    if (EDGE) {
+        Pipe422<true>::stage_load(K, G, ln, s, in);
+        if (bM >= 0 && bM < G.nb) Pipe422<true>::template stage_modulate<true>(K, rc, ln, bM, warp_hs, hsrow);
+    } else {
+        Fast422::stage_load(K, ln, s, in);
+        Fast422::stage_modulate_first(K, rc, ln, bM, warp_hs);
     }
 }
-
-// G4..store.  Returns true when `out` holds block bs of the finished row.
+// role 1
 template <bool EDGE>
-CVS_HD bool step_back(const K422 &K, const Lags &L, const Geo &G, const DivPair &dv, const Row422 &rc, Lane422 &ln, int s,
-                      uint32_t pu, uint32_t pv, uint32_t au, uint32_t av, StepIO &out, int &bs) {
-    typedef Pipe422<EDGE> P;
+CVS_HD void role1_step(const K422 &K, const Lags &L, const Geo &G, const DivPair &dv, const Row422 &rc, Lane422 &ln, int s) {
+    const int bD = s - L.bD;
+    if (EDGE) {
+        if (bD >= 0 && bD < G.nb) Pipe422<true>::stage_separate(K, rc, ln, bD, dv.back_magic, dv.back_shift);
+    } else {
+        Fast422::stage_separate(K, rc, ln, bD);
+    }
+}
+// role 2, front half: luma sharpen; (pu, pv) = the lane's chroma of block s - bV before the vertical blend, which
+// the lane below needs between the two halves
+template <bool EDGE>
+CVS_HD void role2_front(const K422 &K, const Lags &L, const Geo &G, Lane422 &ln, int s, uint32_t &pu, uint32_t &pv) {
+    pu = pv = 0;
+    if (!(K.flags & G_VHS)) return;
+    const int bV = s - L.bV;
+    if (EDGE) {
+        if (bV >= 0 && bV < G.nb) {
+            Pipe422<true>::stage_luma_sharpen(K, ln, bV);
+            Pipe422<true>::blend_fetch(ln, bV, pu, pv);
+        }
+    } else {
+        Fast422::stage_luma_sharpen(K, ln, bV);
+        Pipe422<false>::blend_fetch(ln, bV, pu, pv);
+    }
+}
+template <bool EDGE>
+CVS_HD void role2_back(const K422 &K, const Lags &L, const Geo &G, const Row422 &rc, Lane422 &ln, int s, uint32_t pu, uint32_t pv,
+                       uint32_t au, uint32_t av) {
+    if (!(K.flags & G_VHS)) return;
+    const int bV = s - L.bV;
+    if (EDGE) {
+        if (bV >= 0 && bV < G.nb) Pipe422<true>::stage_vhs_chroma(K, rc, ln, bV, pu, pv, au, av);
+    } else {
+        Fast422::stage_vhs_chroma(K, rc, ln, bV, pu, pv, au, av);
+    }
+}
+// role 3.  Returns true when `out` holds block bs of the finished row.
+template <bool EDGE>
+CVS_HD bool role3_step(const K422 &K, const Lags &L, const Geo &G, const DivPair &dv, const Row422 &rc, Lane422 &ln, int s,
+                       StepIO &out, int &bs) {
     const int nb = G.nb;
-    if (K.flags & G_VHS) {
-        const int bV = s - L.bV;
-        if (!EDGE || (bV >= 0 && bV < nb)) P::stage_vhs_chroma(K, rc, ln, bV, pu, pv, au, av);
-        if (!(K.flags & G_SVIDEO)) {
-            const int b2 = s - L.bD2;
-            if (!EDGE || (b2 >= 0 && b2 < nb)) P::stage_redemod(K, rc, ln, ln.dm2, b2, dv.amp_magic, dv.amp_shift);
-        }
-    }
-    const int bE = s - L.bE;
-    if ((rc.rflags & RG_DROPOUT) && (!EDGE || (bE >= 0 && bE < nb))) P::stage_dropout(ln, bE);
-    for (int i = 0; EDGE && i < K.recombine; i++) {    // -yc-recomb: rare, state lives in shared memory
-        const int bm = bE - i, bd = bE - i - 1;
-        if (bm >= 0 && bm < nb) Pipe422<true>::template stage_modulate<false>(K, rc, ln, bm, false, nullptr);
-        if (bd >= 0 && bd < nb) {
-            Demod dm;
-            dm.o1 = ln.rcomb[3 * i]; dm.o2 = ln.rcomb[3 * i + 1]; dm.o3 = ln.rcomb[3 * i + 2];
-            Pipe422<true>::stage_redemod(K, rc, ln, dm, bd, dv.amp_magic, dv.amp_shift);
-            ln.rcomb[3 * i] = dm.o1; ln.rcomb[3 * i + 1] = dm.o2; ln.rcomb[3 * i + 2] = dm.o3;
-        }
-    }
-    const int bF = s - L.bF;
-    if (!EDGE || (bF >= 0 && bF < nb)) {
-        if (K.flags & (G_OUT_FULL | G_OUT_LITE)) {
-            const uint32_t uw = ldw(cblk(ln.ru, bF)), vw = ldw(cblk(ln.rv, bF));
-            if (K.flags & G_OUT_FULL) {
-                P::chroma_lp4(K, ln.ru, bF, uw, &ln.outU[0], &ln.outU[1], K.a_out[0], K.a_outhp[0], K.d_out[0]);
-                P::chroma_lp4(K, ln.rv, bF, vw, &ln.outV[0], &ln.outV[1], K.a_out[1], K.a_outhp[1], K.d_out[1]);
-            } else {
-                P::chroma_lp4(K, ln.ru, bF, uw, nullptr, &ln.outU[1], K.a_out[0], 0.0, K.d_out[0]);
-                P::chroma_lp4(K, ln.rv, bF, vw, nullptr, &ln.outV[1], K.a_out[1], 0.0, K.d_out[1]);
+    const bool redemod = (K.flags & G_VHS) && !(K.flags & G_SVIDEO);
+    const int bR = s - L.bV - 1, b2 = s - L.bD2, bE = s - L.bE, bF = s - L.bF;
+    bs = s - L.bS;
+    if (EDGE) {
+        typedef Pipe422<true> P;
+        if (redemod && bR >= 0 && bR < nb) P::template stage_modulate<false>(K, rc, ln, bR, false, nullptr);   // (:927-930)
+        if (redemod && b2 >= 0 && b2 < nb) P::stage_redemod(K, rc, ln, ln.dm2, b2, dv.amp_magic, dv.amp_shift);
+        if ((rc.rflags & RG_DROPOUT) && bE >= 0 && bE < nb) P::stage_dropout(ln, bE);
+        for (int i = 0; i < K.recombine; i++) {            // -yc-recomb: rare, state lives in shared memory
+            const int bm = bE - i, bd = bE - i - 1;
+            if (bm >= 0 && bm < nb) P::template stage_modulate<false>(K, rc, ln, bm, false, nullptr);
+            if (bd >= 0 && bd < nb) {
+                Demod dm;
+                dm.o1 = ln.rcomb[3 * i]; dm.o2 = ln.rcomb[3 * i + 1]; dm.o3 = ln.rcomb[3 * i + 2];
+                P::stage_redemod(K, rc, ln, dm, bd, dv.amp_magic, dv.amp_shift);
+                ln.rcomb[3 * i] = dm.o1; ln.rcomb[3 * i + 1] = dm.o2; ln.rcomb[3 * i + 2] = dm.o3;
             }
         }
+        if (bF >= 0 && bF < nb) {
+            if (K.flags & (G_OUT_FULL | G_OUT_LITE)) {
+                const uint32_t uw = ldw(cblk(ln.ru, bF)), vw = ldw(cblk(ln.rv, bF));
+                if (K.flags & G_OUT_FULL) {
+                    P::chroma_lp4(K, ln.ru, bF, uw, &ln.outU[0], &ln.outU[1], K.a_out[0], K.a_outhp[0], K.d_out[0]);
+                    P::chroma_lp4(K, ln.rv, bF, vw, &ln.outV[0], &ln.outV[1], K.a_out[1], K.a_outhp[1], K.d_out[1]);
+                } else {
+                    P::chroma_lp4(K, ln.ru, bF, uw, nullptr, &ln.outU[1], K.a_out[0], 0.0, K.d_out[0]);
+                    P::chroma_lp4(K, ln.rv, bF, vw, nullptr, &ln.outV[1], K.a_out[1], 0.0, K.d_out[1]);
+                }
+            }
+        }
+        if (bs < 0 || bs >= nb) return false;
+    } else {
+        if (redemod) {
+            Fast422::stage_remodulate(rc, ln, bR);
+            Fast422::stage_redemod(K, rc, ln, b2);
+        }
+        if (rc.rflags & RG_DROPOUT) Pipe422<false>::stage_dropout(ln, bE);
+        if (K.flags & (G_OUT_FULL | G_OUT_LITE)) Fast422::stage_out(K, ln, bF);
     }
-    bs = s - L.bS;
-    if (EDGE && (bs < 0 || bs >= nb)) return false;
     const uint8_t *yb = yblk(ln.ry, bs);
     out.y0 = ldw(yb);
     out.y1 = ldw(yb + 4);
@@ -1076,16 +1143,6 @@ CVS_HD void headswitch_row(const K422 &K, const Row422 &rc_in, Lane422 &ln, cons
             }
         }
     }
-}
-
-// steps [s_lo, s_hi) touch only whole interior blocks in every stage (no line start / end special cases)
-CVS_HD void interior_steps(const K422 &K, int &s_lo, int &s_hi) {
-    const Lags L = lags_of(K);
-    const int nb_full = K.w / kB;                     // complete blocks
-    s_lo = L.bS + 2;                                  // the oldest stage is past block 1 (c >= max delay, x >= first flip)
-    s_hi = nb_full;                                   // the load front is a complete block inside the row
-    if (s_hi < s_lo) s_hi = s_lo;
-    if (K.flags & G_GENERAL) s_hi = s_lo;             // rare switches only exist in the general variant
 }
 
 }  // namespace cvs422

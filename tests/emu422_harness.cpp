@@ -32,7 +32,8 @@ uint32_t load_word(const uint8_t *plane, long long plane_bytes, long long off, i
 
 extern "C" {
 
-// force_general: 0 = kernel's own choice of fast/edge steps, 1 = edge variant everywhere
+// force_general: bit 0: 0 = kernel's own choice of interior / general steps, 1 = general variant everywhere;
+// bit 1: the roles of a step in forward instead of reverse order (they must not depend on each other)
 int emu422_process(const cvs422_params *p, unsigned long long rng_pos,
                    uint8_t *yp, int ly, uint8_t *up, int lu, uint8_t *vp, int lv,
                    int w, int h, unsigned field, unsigned long long fieldno, int force_general,
@@ -82,9 +83,12 @@ int emu422_process(const cvs422_params *p, unsigned long long rng_pos,
     const int nl = g.nl, nsteps = line_steps(K);
     const Lags LG = lags_of(K);
     const Geo GE = geo_of(K);
-    int s_lo, s_hi;
-    interior_steps(K, s_lo, s_hi);
-    if (force_general || fs.hs_count > 0) s_hi = s_lo;     // (pre-pass rows only exist in the general variant)
+    RoleRange rr[kRoles];
+    for (int r = 0; r < kRoles; r++) {
+        rr[r] = role_interior(K, LG, r);
+        if (force_general & 1) rr[r].hi = rr[r].lo;
+    }
+    if (fs.hs_count > 0) rr[0].hi = rr[0].lo;              // (pre-pass rows only exist in the general variant)
     int status = CVS_OK;
     for (int wp = 0; wp * 31 < nl; wp++) {
         std::vector<LaneMem> mem(32);
@@ -126,43 +130,62 @@ int emu422_process(const cvs422_params *p, unsigned long long rng_pos,
             if (!ok) status = CVS_ERR_NOISE_SYNC;
             for (int i = 0; i < K.recombine; i++) { L.rcomb[3 * i] = 16; L.rcomb[3 * i + 1] = 16; L.rcomb[3 * i + 2] = 16; }
         }
+        // The four roles of a row run concurrently on the GPU and meet at a barrier after every step, so within a
+        // step no role may depend on another one: run them in REVERSE order here.
         for (int s = 0; s < nsteps; s++) {
-            const bool fast = s >= s_lo && s < s_hi;
-            if (s_hi > s_lo && s == s_lo) for (int lane = 0; lane < 32; lane++) interior_enter(K, LG, ln[lane], s_lo);
-            if (s_hi > s_lo && s == s_hi) for (int lane = 0; lane < 32; lane++) interior_leave(K, LG, ln[lane], s_hi);
-            uint32_t pu[32], pv[32];
-            for (int lane = 0; lane < 32; lane++) {
-                const long long y = (long long)field + 2 * rows[lane];
-                StepIO in;
-                const int x0 = s * kB, c0 = s * kBC;
-                // luma: bytes up to w+1 count (the reference's read past the row), chroma: cw samples
-                in.y0 = load_word(sy.data(), by, y * ly + x0, w + 2 - x0);
-                in.y1 = load_word(sy.data(), by, y * ly + x0 + 4, w + 2 - x0 - 4);
-                in.u = load_word(su.data(), bu, y * lu + c0, K.cw - c0);
-                in.v = load_word(sv.data(), bv, y * lv + c0, K.cw - c0);
-                if (fast) fast_front(K, LG, rc[lane], ln[lane], s, in, warp_hs, pu[lane], pv[lane]);
-                else step_front<true>(K, LG, GE, dv, rc[lane], ln[lane], s, in, warp_hs, hsrow[lane], pu[lane], pv[lane]);
-                // first demodulation of a -yc-recomb round: its box starts from the row's first two luma samples
-                // as they are when that stage reaches block 0 (handled inside demod_block via b == 0)
-            }
-            for (int lane = 0; lane < 32; lane++) {
-                const uint32_t au = lane ? pu[lane - 1] : 0, av = lane ? pv[lane - 1] : 0;
-                StepIO out;
-                int bs;
-                bool have;
-                if (fast) { fast_back(K, LG, rc[lane], ln[lane], s, pu[lane], pv[lane], au, av, out, bs); have = true; }
-                else have = step_back<true>(K, LG, GE, dv, rc[lane], ln[lane], s, pu[lane], pv[lane], au, av, out, bs);
-                if (have && valid[lane]) {
-                    const long long y = (long long)field + 2 * rows[lane];
-                    for (int j = 0; j < kB; j++) {
-                        const int x = bs * kB + j;
-                        if (x < w) yp[y * ly + x] = (uint8_t)(((j < 4 ? out.y0 : out.y1) >> (8 * (j & 3))) & 0xFF);
+            for (int ri = 0; ri < kRoles; ri++) {
+                const int role = (force_general & 2) ? ri : kRoles - 1 - ri;
+                const bool fast = s >= rr[role].lo && s < rr[role].hi;
+                if (rr[role].hi > rr[role].lo && s == rr[role].lo) for (int lane = 0; lane < 32; lane++) role_enter(K, LG, ln[lane], role, s);
+                if (rr[role].hi > rr[role].lo && s == rr[role].hi) for (int lane = 0; lane < 32; lane++) role_leave(K, LG, ln[lane], role, s);
+                if (role == 0) {
+                    for (int lane = 0; lane < 32; lane++) {
+                        const long long y = (long long)field + 2 * rows[lane];
+                        StepIO in;
+                        const int x0 = s * kB, c0 = s * kBC;
+                        // luma: bytes up to w+1 count (the reference's read past the row), chroma: cw samples
+                        in.y0 = load_word(sy.data(), by, y * ly + x0, w + 2 - x0);
+                        in.y1 = load_word(sy.data(), by, y * ly + x0 + 4, w + 2 - x0 - 4);
+                        in.u = load_word(su.data(), bu, y * lu + c0, K.cw - c0);
+                        in.v = load_word(sv.data(), bv, y * lv + c0, K.cw - c0);
+                        if (fast) role0_step<false>(K, LG, GE, rc[lane], ln[lane], s, in, warp_hs, hsrow[lane]);
+                        else role0_step<true>(K, LG, GE, rc[lane], ln[lane], s, in, warp_hs, hsrow[lane]);
                     }
-                    for (int k = 0; k < kBC; k++) {
-                        const int c = bs * kBC + k;
-                        if (c < K.cw) {
-                            up[y * lu + c] = (uint8_t)((out.u >> (8 * k)) & 0xFF);
-                            vp[y * lv + c] = (uint8_t)((out.v >> (8 * k)) & 0xFF);
+                } else if (role == 1) {
+                    for (int lane = 0; lane < 32; lane++) {
+                        if (fast) role1_step<false>(K, LG, GE, dv, rc[lane], ln[lane], s);
+                        else role1_step<true>(K, LG, GE, dv, rc[lane], ln[lane], s);
+                    }
+                } else if (role == 2) {
+                    uint32_t pu[32], pv[32];
+                    for (int lane = 0; lane < 32; lane++) {
+                        if (fast) role2_front<false>(K, LG, GE, ln[lane], s, pu[lane], pv[lane]);
+                        else role2_front<true>(K, LG, GE, ln[lane], s, pu[lane], pv[lane]);
+                    }
+                    for (int lane = 0; lane < 32; lane++) {
+                        const uint32_t au = lane ? pu[lane - 1] : 0, av = lane ? pv[lane - 1] : 0;
+                        if (fast) role2_back<false>(K, LG, GE, rc[lane], ln[lane], s, pu[lane], pv[lane], au, av);
+                        else role2_back<true>(K, LG, GE, rc[lane], ln[lane], s, pu[lane], pv[lane], au, av);
+                    }
+                } else {
+                    for (int lane = 0; lane < 32; lane++) {
+                        StepIO out;
+                        int bs;
+                        const bool have = fast ? role3_step<false>(K, LG, GE, dv, rc[lane], ln[lane], s, out, bs)
+                                               : role3_step<true>(K, LG, GE, dv, rc[lane], ln[lane], s, out, bs);
+                        if (have && valid[lane]) {
+                            const long long y = (long long)field + 2 * rows[lane];
+                            for (int j = 0; j < kB; j++) {
+                                const int x = bs * kB + j;
+                                if (x < w) yp[y * ly + x] = (uint8_t)(((j < 4 ? out.y0 : out.y1) >> (8 * (j & 3))) & 0xFF);
+                            }
+                            for (int k = 0; k < kBC; k++) {
+                                const int c = bs * kBC + k;
+                                if (c < K.cw) {
+                                    up[y * lu + c] = (uint8_t)((out.u >> (8 * k)) & 0xFF);
+                                    vp[y * lv + c] = (uint8_t)((out.v >> (8 * k)) & 0xFF);
+                                }
+                            }
                         }
                     }
                 }
