@@ -2,7 +2,16 @@
 #define CVS_YUV422_DEFINE_KERNELS
 #include "yuv422_kernels.cuh"
 
+#include <cstdlib>
+
 namespace cvs422 {
+
+// CVS422_GENERAL=1 forces the general kernel (read at every launch, so a test can switch it inside one process:
+// both kernels must give the same pictures)
+static bool getenv_general() {
+    const char *e = std::getenv("CVS422_GENERAL");
+    return e && e[0] == '1';
+}
 
 cudaError_t launch_yuv422(const Launch422 &a, const HsItem422 *d_items, int nitems, cudaStream_t st) {
     cudaError_t e = cudaFuncSetAttribute(k_yuv422, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem422::total_max);
@@ -15,7 +24,9 @@ cudaError_t launch_yuv422(const Launch422 &a, const HsItem422 *d_items, int nite
         k_yuv422_headswitch<<<(nitems + kHsNT - 1) / kHsNT, kHsNT, 0, st>>>(a, d_items, nitems);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
-    k_yuv422<<<a.total_warps, kNT, Smem422::total(a.K), st>>>(a);
+    // the fast kernel where it applies (aligned planes, whole blocks, common switches, no pre-pass rows)
+    if (fast_row_ok(a.K) && a.vec && nitems == 0 && !getenv_general()) k_yuv422_fast<<<a.total_warps, kNT, Smem422::total(a.K), st>>>(a);
+    else k_yuv422<<<a.total_warps, kNT, Smem422::total(a.K), st>>>(a);
     return cudaGetLastError();
 }
 

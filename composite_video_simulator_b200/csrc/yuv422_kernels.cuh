@@ -21,10 +21,10 @@
 namespace cvs422 {
 
 #ifndef CVS422_MIN_CTAS
-#define CVS422_MIN_CTAS 4
+#define CVS422_MIN_CTAS 5
 #endif
 #ifndef CVS422_ROTATE_ROLES
-#define CVS422_ROTATE_ROLES 0
+#define CVS422_ROTATE_ROLES 1
 #endif
 // One CTA = one group of 31 consecutive rows (+ the halo lane) = kRoles warps: warp r runs role r (yuv422_pipeline.cuh,
 // "roles") for all rows of the group, the rings in shared memory are the group's, and the four warps meet at a
@@ -371,6 +371,142 @@ __global__ void __launch_bounds__(kNT, CVS422_MIN_CTAS) k_yuv422(const __grid_co
                   *reinterpret_cast<uint32_t *>(du + bs * kBC) = o.u;
                   *reinterpret_cast<uint32_t *>(dvp + bs * kBC) = o.v;
               } })
+    }
+}
+
+// The fast kernel: rows of whole blocks with the common switches (fast_row_ok), aligned planes, no pre-pass rows.
+// Same mapping as k_yuv422 (one CTA = one group of 31 rows + halo lane = four role warps), but a single code path per
+// role -- no general variant, so the loops of the four roles (~25 KB) are all an SM ever executes.
+__global__ void __launch_bounds__(kNT, CVS422_MIN_CTAS) k_yuv422_fast(const __grid_constant__ Launch422 a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int gw = blockIdx.x;
+    // Warp k of a CTA sits on scheduler k, and a role costs about 2 F + N scheduler cycles per step (F FP64, N other
+    // instructions) -- different for every role.  Rotating the assignment with the group gives every scheduler the same
+    // mix; the four loops together fit the SM's instruction cache, so the mix costs nothing there.
+#if CVS422_ROTATE_ROLES
+    const int role = ((tid >> 5) + gw) & (kRoles - 1);
+#else
+    const int role = tid >> 5;
+#endif
+    const K422 &K = a.K;
+    const int w = K.w;
+    int fi, row;
+    bool valid;
+    const uint8_t *halo_rec;
+    if (a.packed) {
+        int g = kRowsPerWarp * gw + lane - 1;
+        valid = (lane >= 1) && g < a.total_rows;
+        g = g < 0 ? 0 : (g > a.total_rows - 1 ? a.total_rows - 1 : g);
+        fi = g / a.max_nl;
+        while (g >= a.fields[fi].row_start + a.fields[fi].nl) fi++;
+        row = g - a.fields[fi].row_start;
+        const int fi1 = __shfl_sync(0xffffffffu, fi, 1);
+        if (lane == 0 && fi != fi1) { fi = fi1; row = 0; }
+        halo_rec = a.halo_base + (size_t)gw * (size_t)a.halo_pitch;
+    } else {
+        fi = gw / a.warps_per_field;
+        const int wp = gw - fi * a.warps_per_field, nlw = a.fields[fi].nl;
+        if (kRowsPerWarp * wp >= nlw) return;
+        row = kRowsPerWarp * wp + lane - 1;
+        valid = (lane >= 1) && row < nlw;
+        row = row < 0 ? 0 : (row > nlw - 1 ? nlw - 1 : row);
+        halo_rec = a.fields[fi].halo + (size_t)wp * (size_t)a.halo_pitch;
+    }
+    const FieldDesc422 &fd = a.fields[fi];
+    const bool halo_copy = __shfl_sync(0xffffffffu, row, 1) >= 1;
+    const long long y = (long long)fd.field + 2 * row;
+
+    Lane422 ln;
+    ln.reset();
+    ln.ry = smem + Smem422::off_ry + (size_t)lane * kStrideY;
+    ln.rya = smem + Smem422::off_rya + (size_t)lane * kStrideA;
+    ln.ru = smem + Smem422::off_ru + (size_t)lane * kStrideC;
+    ln.rv = smem + Smem422::off_rv + (size_t)lane * kStrideC;
+    ln.rcomb = nullptr;
+
+    const Lags L = lags_of(K);
+    const int nb = w / kB, nsteps = line_steps(K);
+    Row422 rc;
+    row_setup(K, (unsigned)fd.field, fd.fieldno, row, __ldg(fd.rowinfo + row), rc);
+
+    if ((role == 0 && K.vnoise != 0) || (role == 1 && K.cnoise != 0)) {
+        uint32_t *win = reinterpret_cast<uint32_t *>(smem + Smem422::off_wins) + role * 128;
+        const int fiA = __shfl_sync(0xffffffffu, fi, 1), fiB = __shfl_sync(0xffffffffu, fi, 31);
+        win[lane] = a.fields[fiA].window[lane];
+        win[lane + 32] = a.fields[fiA].window[lane + 32];
+        win[lane + 64] = a.fields[fiB].window[lane];
+        win[lane + 96] = a.fields[fiB].window[lane + 32];
+        __syncwarp();
+        if (fi != fiA) win += 64;
+        uint32_t hist[31];
+        bool ok;
+        if (role == 0) {
+            const long long pre = (long long)row * w;
+            const int nd = (int)(pre < kWarm ? pre : kWarm);
+            rebase422(win, fd.seek + (size_t)row * 62, hist);
+            ln.rngL.init(reinterpret_cast<uint32_t *>(smem + Smem422::off_rng) + lane, 32, hist, kRngBase - (uint32_t)nd);
+            ok = cvs::warm_luma((uint32_t)(2 * K.vnoise + 1), K.vmagic, K.vshift, K.vnoise, ln.rngL, nd, pre <= kWarm, ln.nY);
+        } else {
+            const long long pre = (long long)row * K.cw;
+            const int nd = (int)(pre < kWarm ? pre : kWarm);
+            rebase422(win, fd.seek + (size_t)row * 62 + 31, hist);
+            ln.rngC.init(reinterpret_cast<uint32_t *>(smem + Smem422::off_rng_chroma(K)) + lane, 32, hist, kRngBase - 2u * (uint32_t)nd);
+            ok = cvs::warm_chroma((uint32_t)(2 * K.cnoise + 1), K.cmagic, K.cshift, K.cnoise, ln.rngC, nd, pre <= kWarm, ln.nU, ln.nV);
+        }
+        if (!ok) atomicOr(a.status, 1);
+    }
+
+    if (role == 0) {
+        LaneSrc src;
+        if (lane == 0 && halo_copy) {
+            src.y = halo_rec; src.u = halo_rec + a.halo_u; src.v = halo_rec + a.halo_v;
+            src.y_avail = w + 2;
+        } else {
+            src.y = fd.y + y * a.ly; src.u = fd.u + y * a.lu; src.v = fd.v + y * a.lv;
+            const long long left = a.by - y * a.ly;
+            src.y_avail = (int)(left < (long long)(w + 2) ? left : (long long)(w + 2));
+        }
+        const bool warp_hs = __any_sync(0xffffffffu, rc.hs_delay > 0);
+        StepIO cur, nxt;
+        load_block_vec(src, 0, cur);
+#pragma unroll 1
+        for (int s = 0; s < nsteps; s++) {
+            nxt.y0 = nxt.y1 = nxt.u = nxt.v = 0;
+            if (s + 1 < nb) load_block_vec(src, s + 1, nxt);
+            else if (s + 1 == nb) nxt.y0 = gather4(src.y + w, src.y_avail - w);       // the two bytes past the row
+            frow0_step(K, L, nb, rc, ln, s, cur, warp_hs);
+            cur = nxt;
+            group_barrier();
+        }
+    } else if (role == 1) {
+#pragma unroll 1
+        for (int s = 0; s < nsteps; s++) {
+            frow1_step(K, L, nb, rc, ln, s);
+            group_barrier();
+        }
+    } else if (role == 2) {
+#pragma unroll 1
+        for (int s = 0; s < nsteps; s++) {
+            uint32_t pu, pv;
+            frow2_front(K, L, nb, ln, s, pu, pv);
+            const uint32_t au = __shfl_up_sync(0xffffffffu, pu, 1), av = __shfl_up_sync(0xffffffffu, pv, 1);
+            frow2_back(K, L, nb, rc, ln, s, pu, pv, au, av);
+            group_barrier();
+        }
+    } else {
+        uint8_t *dy = fd.y + y * a.ly, *du = fd.u + y * a.lu, *dvp = fd.v + y * a.lv;
+#pragma unroll 1
+        for (int s = 0; s < nsteps; s++) {
+            StepIO o;
+            int bs;
+            if (frow3_step(K, L, nb, rc, ln, s, o, bs) && valid) {
+                *reinterpret_cast<uint2 *>(dy + bs * kB) = make_uint2(o.y0, o.y1);
+                *reinterpret_cast<uint32_t *>(du + bs * kBC) = o.u;
+                *reinterpret_cast<uint32_t *>(dvp + bs * kBC) = o.v;
+            }
+            group_barrier();
+        }
     }
 }
 

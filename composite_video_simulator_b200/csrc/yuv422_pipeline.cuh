@@ -100,19 +100,20 @@ struct K422 {
 // a barrier after every step, so a role reads what the previous role wrote in an EARLIER step: one extra block of
 // lag at every role boundary.
 //   role 0: G0 G1 G2      load, input chroma lowpass, first modulation (luma noise, head switch)
-//   role 1: G3            Y/C separation, chroma / phase noise, VHS luma lowpass + boost, VHS chroma lowpass
-//   role 2: G4            VHS luma sharpen, vertical blend, chroma sharpen
+//   role 1: G3a           Y/C separation, chroma / phase noise, VHS luma lowpass + boost
+//   role 2: G3b G4        VHS chroma lowpass, VHS luma sharpen, vertical blend, chroma sharpen
 //   role 3: G5 GE GO ST   re-modulation, second demodulation, dropout, -yc-recomb, output chroma lowpass, store
 constexpr int kRoles = 4;
 struct Lags {
-    int bM, bD, bV, bD2, bE, bF, bS;      // as offsets: block = s - lag
+    int bM, bD, bC, bV, bD2, bE, bF, bS;  // as offsets: block = s - lag
 };
 CVS_HD Lags lags_of(const K422 &K) {
     Lags L;
     const bool vhs = (K.flags & G_VHS) != 0, sv = (K.flags & G_SVIDEO) != 0;
     L.bM = 1;                             // the input lowpass writes up to 4 samples back
     L.bD = L.bM + 2;                      // demodulation reads two bytes of the next block; role boundary
-    L.bV = L.bD + K.lagV + 1;             // the VHS chroma lowpass writes 4..6 samples back; role boundary
+    L.bC = L.bD + 1;                      // role boundary
+    L.bV = L.bC + K.lagV;                 // the VHS chroma lowpass writes 4..6 samples back
     L.bD2 = L.bV + 2;                     // as bD
     L.bE = vhs ? (sv ? L.bV + 1 : L.bD2) : L.bD + 1;
     L.bF = L.bE + K.recombine;
@@ -204,7 +205,7 @@ CVS_HD int div50(int v) {                // exact for every 32-bit magnitude
 #define CVS422_CU 2                      // chroma samples per iteration of a rolled filter loop: 1, 2 or 4
 #endif
 #ifndef CVS422_LU
-#define CVS422_LU 2                      // luma pixels per iteration: 1, 2, 4 or 8
+#define CVS422_LU 4                      // luma pixels per iteration: 1, 2, 4 or 8
 #endif
 #if defined(__CUDA_ARCH__)
 #define CVS_ROLLED _Pragma("unroll 1")
@@ -250,6 +251,17 @@ CVS_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, int sh) {             // low 
     return (lo >> sh) | (hi << (32 - sh));
 #endif
 }
+// __byte_perm for selectors whose nibbles are 0..7
+CVS_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(a, b, sel);
+#else
+    const uint64_t ab = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int k = 0; k < 4; k++) r |= (uint32_t)((ab >> (8 * ((sel >> (4 * k)) & 7))) & 0xFFu) << (8 * k);
+    return r;
+#endif
+}
 // per-byte (a + b + 1) >> 1
 CVS_HD uint32_t avg4_up(uint32_t a, uint32_t b) { return (a | b) - (((a ^ b) & 0xFEFEFEFEu) >> 1); }
 
@@ -261,6 +273,8 @@ struct Row422 {
     int hs_delay;          // RG_HEADSW: Y[x] = Y[x - hs_delay], 16 for x < hs_delay
     int mU[4], mV[4];      // carrier taps for (x & 3): Umult / Vmult rotated by xi (:438-439)
     int fl[4];             // 0xFF where the demodulator flips the sign of the chroma sample (x & 3), else 0 (:527-530)
+    uint32_t flx;          // ~(fl[0..3] as bytes): chroma word ^ flx = 255 - (flipped) chroma for four pixels at once
+    uint32_t selU, selV;   // byte selectors that pick the U / V samples out of eight demodulated pixels
     double cosp, sinp;     // phase noise rotation of this row
 };
 
@@ -284,6 +298,9 @@ CVS_HD void row_setup(const K422 &K, unsigned field, unsigned long long fieldno,
         rc.mV[j] = (ph == 1) ? 1 : ((ph == 3) ? -1 : 0);
         rc.fl[j] = (((j + rc.xi + 2) & 3) < 2) ? 0xFF : 0;
     }
+    rc.flx = ~((uint32_t)rc.fl[0] | ((uint32_t)rc.fl[1] << 8) | ((uint32_t)rc.fl[2] << 16) | ((uint32_t)rc.fl[3] << 24));
+    rc.selU = (rc.xi & 1) ? 0x7531u : 0x6420u;
+    rc.selV = (rc.xi & 1) ? 0x6420u : 0x7531u;
     if (K.flags & G_PHASE) {
         const int st = (int)(int16_t)(rowinfo & 0xFFFFu);
         rc.cosp = K.phase_lut[2 * (st + K.pnoise)];
@@ -320,6 +337,7 @@ struct Lane422 {
         for (int i = 0; i < 3; i++) { lsh[i] = 16; chU[i] = chV[i] = 128; csU[i] = csV[i] = 128; }
         pre = 16;
         nY = nU = nV = 0;
+        cIn[0] = cIn[1] = cCh[0] = cCh[1] = cOut[0] = cOut[1] = 0;
         dm1.reset(16, 16);
         dm2.reset(16, 16);
     }
@@ -588,11 +606,15 @@ struct Pipe422 {
                 }
             }
             store_luma(K, yb, x0, Yn, y0, y1);
-            chroma_lp4(K, ln.ru, b, uw, nullptr, ln.chU, K.a_ch, 0.0, K.cd);   // written cd samples back (:830-851)
-            chroma_lp4(K, ln.rv, b, vw, nullptr, ln.chV, K.a_ch, 0.0, K.cd);
         } else {
             store_luma(K, yb, x0, Yn, y0, y1);
         }
+    }
+    // G3b: VHS chroma lowpass of block b, written cd samples back (:830-851)
+    static CVS_HD void stage_chroma_lp(const K422 &K, Lane422 &ln, int b) {
+        const uint32_t uw = ldw(cblk(ln.ru, b)), vw = ldw(cblk(ln.rv, b));
+        chroma_lp4(K, ln.ru, b, uw, nullptr, ln.chU, K.a_ch, 0.0, K.cd);
+        chroma_lp4(K, ln.rv, b, vw, nullptr, ln.chV, K.a_ch, 0.0, K.cd);
     }
     // G4a: VHS luma sharpen of block b (:888-901); the lowpassed luma is an 8-bit plane in the reference too
     static CVS_HD void stage_luma_sharpen(const K422 &K, Lane422 &ln, int b) {
@@ -768,7 +790,7 @@ struct Fast422 {
             }
         }
         uint32_t w0 = sat4(yo[0], yo[1], yo[2], yo[3]), w1 = sat4(yo[4], yo[5], yo[6], yo[7]);
-        if (warp_hs) {                                                         // (:697-731) as a delay line; x >= delay here
+        if (warp_hs) {                                                         // (:697-731) as a delay line
             uint8_t *ab = ln.rya + (x0 & (kRingA - 1));
             stw(ab, w0);
             stw(ab + 4, w1);
@@ -778,6 +800,13 @@ struct Fast422 {
                                a2 = ldw(ln.rya + ((p + 8) & (kRingA - 4)));
                 w0 = sh ? funnel_r(a0, a1, sh) : a0;
                 w1 = sh ? funnel_r(a1, a2, sh) : a1;
+                const int n16 = -p;                                            // pixels of this block before x = delay: 16
+                if (n16 > 0) {
+                    const uint32_t m0 = n16 >= 4 ? 0xFFFFFFFFu : ((1u << (8 * n16)) - 1u);
+                    const uint32_t m1 = n16 >= 8 ? 0xFFFFFFFFu : (n16 > 4 ? ((1u << (8 * (n16 - 4))) - 1u) : 0u);
+                    w0 = (w0 & ~m0) | (0x10101010u & m0);
+                    w1 = (w1 & ~m1) | (0x10101010u & m1);
+                }
             }
         }
         stw(yb, w0);
@@ -848,51 +877,83 @@ struct Fast422 {
         stw(yb + 4, yw1);
     }
 
+    // composite_ntsc_to_yuv on one whole block (:480-553), words in, words out.  Block 0 starts the box filter from the
+    // row's first two samples and leaves the pixels before the first flip index alone (:487-499, :527).
+    static CVS_HD void demod_w(const Row422 &rc, Demod &dm, int b, uint32_t y0, uint32_t y1, uint32_t y2,
+                               uint32_t &yw0, uint32_t &yw1, uint32_t &uw, uint32_t &vw) {
+        uint32_t f_lo = rc.flx, f_hi = rc.flx;
+        if (b == 0) {
+            dm.reset(byte_of(y0, 0), byte_of(y0, 1));
+            const int xflip0 = ((4 - rc.xi) & 3) + 2;                         // 2..5
+            f_lo |= (xflip0 >= 4) ? 0xFFFFFFFFu : ((1u << (8 * xflip0)) - 1u);
+            f_hi |= (xflip0 > 4) ? 0xFFu : 0u;
+        }
+        int yn[kB], cv[kB];
+        CVS_UNROLL
+        for (int j = 0; j < kB; j++) {
+            const int c = (j < 2) ? byte_of(y0, j + 2) : ((j < 6) ? byte_of(y1, j - 2) : byte_of(y2, j - 6));
+            const int sum = dm.o1 + dm.o2 + dm.o3 + c;
+            dm.o1 = dm.o2; dm.o2 = dm.o3; dm.o3 = c;
+            yn[j] = sum >> 2;
+            cv[j] = c + 128 - yn[j];
+        }
+        yw0 = sat4(yn[0], yn[1], yn[2], yn[3]);
+        yw1 = sat4(yn[4], yn[5], yn[6], yn[7]);
+        const uint32_t c_lo = sat4(cv[0], cv[1], cv[2], cv[3]) ^ f_lo, c_hi = sat4(cv[4], cv[5], cv[6], cv[7]) ^ f_hi;
+        uw = prmt(c_lo, c_hi, rc.selU);                                       // 255 - chroma (:539-548)
+        vw = prmt(c_lo, c_hi, rc.selV);
+    }
+
     // G3
     static CVS_HD void stage_separate(const K422 &K, const Row422 &rc, Lane422 &ln, int b) {
         const int c0 = b * kBC;
         uint8_t *yb = yblk(ln.ry, b), *ub = cblk(ln.ru, b), *vb = cblk(ln.rv, b);
-        int Yn[kB], U[kBC], V[kBC];
-        Pipe422<false>::demod8(K, rc, ln.dm1, b, ldw(yb), ldw(yb + 4), ldw(yblk(ln.ry, b + 1)), 50, 0u, 0u, Yn, U, V);
-        if (K.cnoise != 0) {                                                   // (:738-754)
-            uint32_t *grp = ln.rngC.group_ptr(kRngBase + (uint32_t)(2 * c0));
-            const uint32_t *grp_next = ln.rngC.group_ptr(kRngBase + (uint32_t)(2 * c0) + 2 * kBC);
+        uint32_t yw0, yw1, uw, vw;
+        demod_w(rc, ln.dm1, b, ldw(yb), ldw(yb + 4), ldw(yblk(ln.ry, b + 1)), yw0, yw1, uw, vw);
+        if (K.cnoise != 0 || (K.flags & G_PHASE)) {
+            int U[kBC], V[kBC];
             CVS_UNROLL
-            for (int k = 0; k < kBC; k++) {
-                U[k] = sat1(U[k] + ln.nU);
-                V[k] = sat1(V[k] + ln.nV);
-                const int du = draw_mod(ln.rngC.next_in_group(grp, grp_next, 2 * k, 2 * kBC), (uint32_t)(2 * K.cnoise + 1), K.cmagic, K.cshift);
-                ln.nU = noise_step(ln.nU, du, K.cnoise);
-                const int dv = draw_mod(ln.rngC.next_in_group(grp, grp_next, 2 * k + 1, 2 * kBC), (uint32_t)(2 * K.cnoise + 1), K.cmagic, K.cshift);
-                ln.nV = noise_step(ln.nV, dv, K.cnoise);
+            for (int k = 0; k < kBC; k++) { U[k] = byte_of(uw, k); V[k] = byte_of(vw, k); }
+            if (K.cnoise != 0) {                                               // (:738-754)
+                uint32_t *grp = ln.rngC.group_ptr(kRngBase + (uint32_t)(2 * c0));
+                const uint32_t *grp_next = ln.rngC.group_ptr(kRngBase + (uint32_t)(2 * c0) + 2 * kBC);
+                CVS_UNROLL
+                for (int k = 0; k < kBC; k++) {
+                    U[k] = sat1(U[k] + ln.nU);
+                    V[k] = sat1(V[k] + ln.nV);
+                    const int du = draw_mod(ln.rngC.next_in_group(grp, grp_next, 2 * k, 2 * kBC), (uint32_t)(2 * K.cnoise + 1), K.cmagic, K.cshift);
+                    ln.nU = noise_step(ln.nU, du, K.cnoise);
+                    const int dv = draw_mod(ln.rngC.next_in_group(grp, grp_next, 2 * k + 1, 2 * kBC), (uint32_t)(2 * K.cnoise + 1), K.cmagic, K.cshift);
+                    ln.nV = noise_step(ln.nV, dv, K.cnoise);
+                }
             }
-        }
-        if (K.flags & G_PHASE) {                                               // (:755-783)
-            CVS_UNROLL
-            for (int k = 0; k < kBC; k++) {
-                const double u = i2d(U[k] - 128), v = i2d(V[k] - 128);
-                const double u_ = dsub(dmul(u, rc.cosp), dmul(u, rc.sinp));
-                const double v_ = dadd(dmul(v, rc.cosp), dmul(v, rc.sinp));
-                U[k] = fq(dadd(u_, 128.0));
-                V[k] = fq(dadd(v_, 128.0));
+            if (K.flags & G_PHASE) {                                           // (:755-783)
+                CVS_UNROLL
+                for (int k = 0; k < kBC; k++) {
+                    const double u = i2d(U[k] - 128), v = i2d(V[k] - 128);
+                    const double u_ = dsub(dmul(u, rc.cosp), dmul(u, rc.sinp));
+                    const double v_ = dadd(dmul(v, rc.cosp), dmul(v, rc.sinp));
+                    U[k] = fq(dadd(u_, 128.0));
+                    V[k] = fq(dadd(v_, 128.0));
+                }
             }
+            uw = sat4(U[0], U[1], U[2], U[3]);
+            vw = sat4(V[0], V[1], V[2], V[3]);
         }
-        const uint32_t uw = sat4(U[0], U[1], U[2], U[3]), vw = sat4(V[0], V[1], V[2], V[3]);
         stw(ub, uw);                                                           // unfiltered: see Pipe422::stage_separate
         stw(vb, vw);
-        uint32_t yw0 = sat4(Yn[0], Yn[1], Yn[2], Yn[3]), yw1 = sat4(Yn[4], Yn[5], Yn[6], Yn[7]);
         if (K.flags & G_VHS) {
             luma8(yw0, yw1, LumaLp{ln, K});
-            stw(yb, yw0);
-            stw(yb + 4, yw1);
-            uint32_t ou, ov;
-            lp_pair<false>(uw, vw, nullptr, ln.chU, nullptr, ln.chV, K.a_ch, 0.0, K.a_ch, 0.0, ou, ov);
-            put_delayed(ln.ru, b, K.cd, ou, ln.cCh[0]);
-            put_delayed(ln.rv, b, K.cd, ov, ln.cCh[1]);
-        } else {
-            stw(yb, yw0);
-            stw(yb + 4, yw1);
         }
+        stw(yb, yw0);
+        stw(yb + 4, yw1);
+    }
+    // G3b
+    static CVS_HD void stage_chroma_lp(const K422 &K, Lane422 &ln, int b) {
+        uint32_t ou, ov;
+        lp_pair<false>(ldw(cblk(ln.ru, b)), ldw(cblk(ln.rv, b)), nullptr, ln.chU, nullptr, ln.chV, K.a_ch, 0.0, K.a_ch, 0.0, ou, ov);
+        put_delayed(ln.ru, b, K.cd, ou, ln.cCh[0]);
+        put_delayed(ln.rv, b, K.cd, ov, ln.cCh[1]);
     }
 
     // G4: vertical blend (:858-883), chroma sharpen (:904-925)
@@ -925,14 +986,14 @@ struct Fast422 {
     }
 
     // G5
-    static CVS_HD void stage_redemod(const K422 &K, const Row422 &rc, Lane422 &ln, int b) {
+    static CVS_HD void stage_redemod(const Row422 &rc, Lane422 &ln, int b) {
         uint8_t *yb = yblk(ln.ry, b);
-        int Yn[kB], U[kBC], V[kBC];
-        Pipe422<false>::demod8(K, rc, ln.dm2, b, ldw(yb), ldw(yb + 4), ldw(yblk(ln.ry, b + 1)), 50, 0u, 0u, Yn, U, V);
-        stw(yb, sat4(Yn[0], Yn[1], Yn[2], Yn[3]));
-        stw(yb + 4, sat4(Yn[4], Yn[5], Yn[6], Yn[7]));
-        stw(cblk(ln.ru, b), sat4(U[0], U[1], U[2], U[3]));
-        stw(cblk(ln.rv, b), sat4(V[0], V[1], V[2], V[3]));
+        uint32_t yw0, yw1, uw, vw;
+        demod_w(rc, ln.dm2, b, ldw(yb), ldw(yb + 4), ldw(yblk(ln.ry, b + 1)), yw0, yw1, uw, vw);
+        stw(yb, yw0);
+        stw(yb + 4, yw1);
+        stw(cblk(ln.ru, b), uw);
+        stw(cblk(ln.rv, b), vw);
     }
 
     // GO
@@ -959,7 +1020,7 @@ CVS_HD RoleRange role_interior(const K422 &K, const Lags &L, int role) {
     int lmin, lmax;                       // youngest / oldest block of the role
     if (role == 0) { lmin = 0; lmax = L.bM; }
     else if (role == 1) { lmin = lmax = L.bD; }
-    else if (role == 2) { lmin = lmax = L.bV; }
+    else if (role == 2) { lmin = L.bC; lmax = L.bV; }
     else { lmin = (vhs && !sv) ? L.bV + 1 : L.bE; lmax = L.bS; }
     RoleRange r;
     r.lo = lmax + 2;
@@ -973,9 +1034,9 @@ CVS_HD void role_enter(const K422 &K, const Lags &L, Lane422 &ln, int role, int 
         Fast422::carry_enter(ln.ru, s0, K.d_in[0], ln.cIn[0]);
         Fast422::carry_enter(ln.rv, s0, K.d_in[1], ln.cIn[1]);
     }
-    if (role == 1 && (K.flags & G_VHS)) {
-        Fast422::carry_enter(ln.ru, s0 - L.bD, K.cd, ln.cCh[0]);
-        Fast422::carry_enter(ln.rv, s0 - L.bD, K.cd, ln.cCh[1]);
+    if (role == 2 && (K.flags & G_VHS)) {
+        Fast422::carry_enter(ln.ru, s0 - L.bC, K.cd, ln.cCh[0]);
+        Fast422::carry_enter(ln.rv, s0 - L.bC, K.cd, ln.cCh[1]);
     }
     if (role == 3 && (K.flags & (G_OUT_FULL | G_OUT_LITE))) {
         Fast422::carry_enter(ln.ru, s0 - L.bF, K.d_out[0], ln.cOut[0]);
@@ -988,9 +1049,9 @@ CVS_HD void role_leave(const K422 &K, const Lags &L, Lane422 &ln, int role, int 
         Fast422::carry_leave(ln.ru, s, K.d_in[0], ln.cIn[0]);
         Fast422::carry_leave(ln.rv, s, K.d_in[1], ln.cIn[1]);
     }
-    if (role == 1 && (K.flags & G_VHS)) {
-        Fast422::carry_leave(ln.ru, s - L.bD, K.cd, ln.cCh[0]);
-        Fast422::carry_leave(ln.rv, s - L.bD, K.cd, ln.cCh[1]);
+    if (role == 2 && (K.flags & G_VHS)) {
+        Fast422::carry_leave(ln.ru, s - L.bC, K.cd, ln.cCh[0]);
+        Fast422::carry_leave(ln.rv, s - L.bC, K.cd, ln.cCh[1]);
     }
     if (role == 3 && (K.flags & (G_OUT_FULL | G_OUT_LITE))) {
         Fast422::carry_leave(ln.ru, s - L.bF, K.d_out[0], ln.cOut[0]);
@@ -1021,19 +1082,21 @@ CVS_HD void role1_step(const K422 &K, const Lags &L, const Geo &G, const DivPair
         Fast422::stage_separate(K, rc, ln, bD);
     }
 }
-// role 2, front half: luma sharpen; (pu, pv) = the lane's chroma of block s - bV before the vertical blend, which
+// role 2, front half: chroma lowpass, luma sharpen; (pu, pv) = the lane's chroma of block s - bV before the vertical blend, which
 // the lane below needs between the two halves
 template <bool EDGE>
 CVS_HD void role2_front(const K422 &K, const Lags &L, const Geo &G, Lane422 &ln, int s, uint32_t &pu, uint32_t &pv) {
     pu = pv = 0;
     if (!(K.flags & G_VHS)) return;
-    const int bV = s - L.bV;
+    const int bC = s - L.bC, bV = s - L.bV;
     if (EDGE) {
+        if (bC >= 0 && bC < G.nb) Pipe422<true>::stage_chroma_lp(K, ln, bC);
         if (bV >= 0 && bV < G.nb) {
             Pipe422<true>::stage_luma_sharpen(K, ln, bV);
             Pipe422<true>::blend_fetch(ln, bV, pu, pv);
         }
     } else {
+        Fast422::stage_chroma_lp(K, ln, bC);
         Fast422::stage_luma_sharpen(K, ln, bV);
         Pipe422<false>::blend_fetch(ln, bV, pu, pv);
     }
@@ -1088,11 +1151,92 @@ CVS_HD bool role3_step(const K422 &K, const Lags &L, const Geo &G, const DivPair
     } else {
         if (redemod) {
             Fast422::stage_remodulate(rc, ln, bR);
-            Fast422::stage_redemod(K, rc, ln, b2);
+            Fast422::stage_redemod(rc, ln, b2);
         }
         if (rc.rflags & RG_DROPOUT) Pipe422<false>::stage_dropout(ln, bE);
         if (K.flags & (G_OUT_FULL | G_OUT_LITE)) Fast422::stage_out(K, ln, bF);
     }
+    const uint8_t *yb = yblk(ln.ry, bs);
+    out.y0 = ldw(yb);
+    out.y1 = ldw(yb + 4);
+    out.u = ldw(cblk(ln.ru, bs));
+    out.v = ldw(cblk(ln.rv, bs));
+    return true;
+}
+
+// ---- the fast kernel's steps ------------------------------------------------------------------------------
+// Rows whose width is a multiple of 8 and that use the common switches only (fast_row_ok) never need the general
+// variant: every block is whole, the line start is block 0 of the interior code (demod_w, the head-switch fill) and
+// a role simply skips the steps in which its block does not exist.  One code path per role keeps what an SM
+// executes inside its 32 KB instruction cache (scripts/probes/ifetch_probe.cu: 1.0 instruction per cycle and
+// scheduler below that, 0.4 above) -- the general variant's line-end code alone is larger than that.
+CVS_HD bool fast_row_ok(const K422 &K) { return !(K.flags & G_GENERAL) && (K.w % kB) == 0; }
+CVS_HD bool blk_ok(int b, int nb) { return (unsigned)b < (unsigned)nb; }
+
+CVS_HD void frow0_step(const K422 &K, const Lags &L, int nb, const Row422 &rc, Lane422 &ln, int s, const StepIO &in, bool warp_hs) {
+    if (s <= nb) {                        // block nb: the two luma bytes past the row (:496)
+        uint8_t *yb = yblk(ln.ry, s);
+        stw(yb, in.y0);
+        stw(yb + 4, in.y1);
+        stw(cblk(ln.ru, s), in.u);
+        stw(cblk(ln.rv, s), in.v);
+    }
+    if (s < nb && (K.flags & G_IN_LP)) {
+        uint32_t ou, ov;
+        Fast422::lp_pair<true>(in.u, in.v, &ln.inU[0], &ln.inU[1], &ln.inV[0], &ln.inV[1], K.a_in[0], K.a_inhp[0], K.a_in[1], K.a_inhp[1], ou, ov);
+        Fast422::put_delayed(ln.ru, s, K.d_in[0], ou, ln.cIn[0]);
+        Fast422::put_delayed(ln.rv, s, K.d_in[1], ov, ln.cIn[1]);
+        if (s == nb - 1) {
+            Fast422::carry_leave(ln.ru, s, K.d_in[0], ln.cIn[0]);
+            Fast422::carry_leave(ln.rv, s, K.d_in[1], ln.cIn[1]);
+        }
+    }
+    const int bM = s - L.bM;
+    if (blk_ok(bM, nb)) Fast422::stage_modulate_first(K, rc, ln, bM, warp_hs);
+}
+CVS_HD void frow1_step(const K422 &K, const Lags &L, int nb, const Row422 &rc, Lane422 &ln, int s) {
+    const int b = s - L.bD;
+    if (!blk_ok(b, nb)) return;
+    Fast422::stage_separate(K, rc, ln, b);
+}
+CVS_HD void frow2_front(const K422 &K, const Lags &L, int nb, Lane422 &ln, int s, uint32_t &pu, uint32_t &pv) {
+    pu = pv = 0;
+    if (!(K.flags & G_VHS)) return;
+    const int bC = s - L.bC, b = s - L.bV;
+    if (blk_ok(bC, nb)) {
+        Fast422::stage_chroma_lp(K, ln, bC);
+        if (bC == nb - 1) {
+            Fast422::carry_leave(ln.ru, bC, K.cd, ln.cCh[0]);
+            Fast422::carry_leave(ln.rv, bC, K.cd, ln.cCh[1]);
+        }
+    }
+    if (!blk_ok(b, nb)) return;
+    Fast422::stage_luma_sharpen(K, ln, b);
+    Pipe422<false>::blend_fetch(ln, b, pu, pv);
+}
+CVS_HD void frow2_back(const K422 &K, const Lags &L, int nb, const Row422 &rc, Lane422 &ln, int s, uint32_t pu, uint32_t pv,
+                       uint32_t au, uint32_t av) {
+    const int b = s - L.bV;
+    if (!(K.flags & G_VHS) || !blk_ok(b, nb)) return;
+    Fast422::stage_vhs_chroma(K, rc, ln, b, pu, pv, au, av);
+}
+CVS_HD bool frow3_step(const K422 &K, const Lags &L, int nb, const Row422 &rc, Lane422 &ln, int s, StepIO &out, int &bs) {
+    if ((K.flags & G_VHS) && !(K.flags & G_SVIDEO)) {
+        const int bR = s - L.bV - 1, b2 = s - L.bD2;
+        if (blk_ok(bR, nb)) Fast422::stage_remodulate(rc, ln, bR);
+        if (blk_ok(b2, nb)) Fast422::stage_redemod(rc, ln, b2);
+    }
+    const int bE = s - L.bE, bF = s - L.bF;
+    if ((rc.rflags & RG_DROPOUT) && blk_ok(bE, nb)) Pipe422<false>::stage_dropout(ln, bE);
+    if ((K.flags & (G_OUT_FULL | G_OUT_LITE)) && blk_ok(bF, nb)) {
+        Fast422::stage_out(K, ln, bF);
+        if (bF == nb - 1) {
+            Fast422::carry_leave(ln.ru, bF, K.d_out[0], ln.cOut[0]);
+            Fast422::carry_leave(ln.rv, bF, K.d_out[1], ln.cOut[1]);
+        }
+    }
+    bs = s - L.bS;
+    if (!blk_ok(bs, nb)) return false;
     const uint8_t *yb = yblk(ln.ry, bs);
     out.y0 = ldw(yb);
     out.y1 = ldw(yb + 4);

@@ -33,6 +33,7 @@ uint32_t load_word(const uint8_t *plane, long long plane_bytes, long long off, i
 extern "C" {
 
 // force_general: bit 0: 0 = kernel's own choice of interior / general steps, 1 = general variant everywhere;
+// bit 2: the general kernel (with its interior steps) also where the fast kernel would run;
 // bit 1: the roles of a step in forward instead of reverse order (they must not depend on each other)
 int emu422_process(const cvs422_params *p, unsigned long long rng_pos,
                    uint8_t *yp, int ly, uint8_t *up, int lu, uint8_t *vp, int lv,
@@ -129,6 +130,48 @@ int emu422_process(const cvs422_params *p, unsigned long long rng_pos,
             }
             if (!ok) status = CVS_ERR_NOISE_SYNC;
             for (int i = 0; i < K.recombine; i++) { L.rcomb[3 * i] = 16; L.rcomb[3 * i + 1] = 16; L.rcomb[3 * i + 2] = 16; }
+        }
+        // the fast kernel (k_yuv422_fast): one code path per role, no general steps
+        if (!(force_general & 5) && fast_row_ok(K) && fs.hs_count == 0) {
+            const int nb = GE.nb;
+            for (int s = 0; s < nsteps; s++) {
+                for (int ri = 0; ri < kRoles; ri++) {
+                    const int role = (force_general & 2) ? ri : kRoles - 1 - ri;
+                    if (role == 0) {
+                        for (int lane = 0; lane < 32; lane++) {
+                            const long long y = (long long)field + 2 * rows[lane];
+                            StepIO in;
+                            const int x0 = s * kB, c0 = s * kBC;
+                            in.y0 = load_word(sy.data(), by, y * ly + x0, w + 2 - x0);
+                            in.y1 = load_word(sy.data(), by, y * ly + x0 + 4, w + 2 - x0 - 4);
+                            in.u = load_word(su.data(), bu, y * lu + c0, K.cw - c0);
+                            in.v = load_word(sv.data(), bv, y * lv + c0, K.cw - c0);
+                            frow0_step(K, LG, nb, rc[lane], ln[lane], s, in, warp_hs);
+                        }
+                    } else if (role == 1) {
+                        for (int lane = 0; lane < 32; lane++) frow1_step(K, LG, nb, rc[lane], ln[lane], s);
+                    } else if (role == 2) {
+                        uint32_t pu[32], pv[32];
+                        for (int lane = 0; lane < 32; lane++) frow2_front(K, LG, nb, ln[lane], s, pu[lane], pv[lane]);
+                        for (int lane = 0; lane < 32; lane++)
+                            frow2_back(K, LG, nb, rc[lane], ln[lane], s, pu[lane], pv[lane], lane ? pu[lane - 1] : 0, lane ? pv[lane - 1] : 0);
+                    } else {
+                        for (int lane = 0; lane < 32; lane++) {
+                            StepIO out;
+                            int bs;
+                            if (frow3_step(K, LG, nb, rc[lane], ln[lane], s, out, bs) && valid[lane]) {
+                                const long long y = (long long)field + 2 * rows[lane];
+                                for (int j = 0; j < kB; j++) yp[y * ly + bs * kB + j] = (uint8_t)(((j < 4 ? out.y0 : out.y1) >> (8 * (j & 3))) & 0xFF);
+                                for (int k = 0; k < kBC; k++) {
+                                    up[y * lu + bs * kBC + k] = (uint8_t)((out.u >> (8 * k)) & 0xFF);
+                                    vp[y * lv + bs * kBC + k] = (uint8_t)((out.v >> (8 * k)) & 0xFF);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            continue;
         }
         // The four roles of a row run concurrently on the GPU and meet at a barrier after every step, so within a
         // step no role may depend on another one: run them in REVERSE order here.

@@ -47,13 +47,35 @@ CASES = [
     (102, 67, 2, ["-vhs", "-vhs-speed", "lp"]),
     (8, 3, 2, []),
     (2, 2, 2, ["-vhs"]),
+    (64, 32, 2, ["-vhs"]),
+    (24, 10, 3, ["-vhs", "-vhs-speed", "ep"]),
+    (16, 40, 2, ["-vhs", "-vhs-speed", "lp", "-chroma-dropout", "2000"]),
+    (720, 480, 2, ["-vhs", "-vhs-speed", "ep"]),
     (1920, 1080, 2, ["-vhs", "-vhs-speed", "sp"]),
     (3840, 2160, 1, ["-vhs", "-vhs-speed", "ep"]),
 ]
 
 
+@pytest.fixture(params=["fast", "general"])
+def kernel(request):
+    """Rows of whole blocks with the common switches run k_yuv422_fast; CVS422_GENERAL=1 sends them through the
+    general kernel k_yuv422 as well (the library reads the variable at every launch)."""
+    if request.param == "general":
+        os.environ["CVS422_GENERAL"] = "1"
+    yield request.param
+    os.environ.pop("CVS422_GENERAL", None)
+
+
+def fast_kernel_applies(w, argv):
+    general = ("-subcarrier-amp", "-nocolor-subcarrier", "-nocolor-subcarrier-after-yc-sep", "-yc-recomb", "-comp-pre", "-comp-catv",
+               "-comp-catv2", "-comp-catv3", "-comp-catv4")
+    return w % 8 == 0 and not any(a in general for a in argv)
+
+
 @pytest.mark.parametrize("w,h,n,argv", CASES)
-def test_seam_equals_oracle(orc, y422, w, h, n, argv):
+def test_seam_equals_oracle(orc, y422, w, h, n, argv, kernel):
+    if kernel == "general" and not fast_kernel_applies(w, argv):
+        pytest.skip("already the general kernel")
     p = helpers.params422(*argv)
     want, g = helpers.run_oracle422(orc, p, w, h, n)
     with y422.Yuv422Engine(argv, max_w=w, max_h=h, max_batch=1) as eng:

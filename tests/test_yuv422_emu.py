@@ -42,12 +42,16 @@ CASES = [
     (16, 6, 2, ["-vhs"]),
     (8, 3, 2, []),
     (2, 2, 2, ["-vhs"]),
+    (64, 32, 2, ["-vhs"]),
+    (24, 10, 3, ["-vhs", "-vhs-speed", "ep"]),
+    (16, 40, 2, ["-vhs", "-vhs-speed", "lp", "-chroma-dropout", "2000"]),
+    (720, 480, 2, ["-vhs", "-vhs-speed", "ep"]),
     (1920, 1080, 1, ["-vhs", "-vhs-speed", "sp"]),
 ]
 
 
 @pytest.mark.parametrize("w,h,n,argv", CASES)
-@pytest.mark.parametrize("general", [0, 1, 2])
+@pytest.mark.parametrize("general", [0, 1, 2, 4, 6])
 def test_emulated_kernel_equals_oracle(orc, emu, w, h, n, argv, general):
     if general == 1 and w >= 1920:
         pytest.skip("covered by the kernel's own choice")
