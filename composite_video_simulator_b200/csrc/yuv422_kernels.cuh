@@ -1,13 +1,15 @@
 // yuv422_kernels.cuh -- sm_100a kernels around yuv422_pipeline.cuh (the reference's 4:2:2 path,
 // ffmpeg_to_composite.cpp:629-952 and :1001-1129).
 //
-//   k_yuv422             one launch processes a batch of fields IN PLACE: a warp owns 31 consecutive
-//                        rows of one field (+ a halo lane), a lane streams its row through every stage
-//                        of composite_video_process(); stages talk through per-lane byte rings in
-//                        shared memory.  HBM traffic = one read + one write of the field's rows
-//                        (2 bytes per pixel each way).
-//   k_yuv422_halo        copies the one row per warp that a halo lane re-reads (the last row of the
-//                        warp above) before the in-place pass overwrites it.
+//   k_yuv422_fast        one launch processes a batch of fields IN PLACE.  One CTA = one group of 31 consecutive
+//                        rows (+ a halo lane) = four warps, one per role; a lane streams its row through the
+//                        stages of its role, the roles talk through the group's byte rings in shared memory and
+//                        meet at a barrier after every step.  HBM traffic = one read + one write of the field's
+//                        rows (2 bytes per pixel each way).  Takes rows of whole blocks (w % 8 == 0) with the
+//                        common switches on aligned planes.
+//   k_yuv422             the general kernel (same mapping, the general variant of every stage): everything else.
+//   k_yuv422_halo        copies the one row per group that a halo lane re-reads (the last row of the group
+//                        above) before the in-place pass overwrites it.
 //   k_yuv422_headswitch  pre-pass for head-switch rotations that are not a short delay.
 //   k_render_field       render_field(): vertical 8.8 resampling of a source picture onto field rows.
 #ifndef CVS_YUV422_KERNELS_CUH
@@ -24,15 +26,14 @@ namespace cvs422 {
 #define CVS422_MIN_CTAS 5
 #endif
 #ifndef CVS422_ROTATE_ROLES
-#define CVS422_ROTATE_ROLES 1
+#define CVS422_ROTATE_ROLES 0
 #endif
 // One CTA = one group of 31 consecutive rows (+ the halo lane) = kRoles warps: warp r runs role r (yuv422_pipeline.cuh,
-// "roles") for all rows of the group, the rings in shared memory are the group's, and the four warps meet at a
-// barrier after every step.  Why: a lane that runs every stage of its row needs ~210 registers (35 doubles of
-// filter state) -- 2 warps per scheduler, each of them an in-order stream of dependent 8-cycle FP64 operations and
-// 4-cycle integer chains that the FP64 pipe (one instruction per 2 cycles per scheduler) spends half its time
-// waiting for (round 1 / 2: 0.45 of the pipe, scripts/probes/fp64_probe.cu).  Split by role, a warp holds a
-// quarter of the state, so 16+ warps fit on an SM and the pipe always finds a ready warp.
+// "roles") for all rows of the group.  Why (measured on B200, profiles/ab_variants_r2.txt section 6, profiles/probes_r2.txt):
+// a lane that runs every stage of its row needs ~210 registers (35 doubles of filter state), i.e. 2 warps per
+// scheduler, each an in-order stream of dependent 8.65-cycle FP64 operations and 4-cycle integer chains, and a
+// 37 KB loop that does not fit the SM's 32 KB instruction cache (issue slots 52 % busy whatever else was tried).
+// Split by role a warp needs 90 registers (5 groups = 20 warps per SM) and the four loops together are 25 KB.
 constexpr int kNT = 32 * kRoles;         // threads per CTA
 constexpr int kRowsPerWarp = 31;         // rows per group; lane 0 is the halo row
 constexpr int kStrideY = kRingY + 4;     // per-lane ring strides: +1 word so that equal offsets of the 32 lanes
@@ -207,33 +208,17 @@ __device__ __forceinline__ void load_block_vec(const LaneSrc &src, int s, StepIO
     io.v = *reinterpret_cast<const uint32_t *>(src.v + s * kBC);
 }
 
-__device__ __forceinline__ void group_barrier() { asm volatile("bar.sync 0;" ::: "memory"); }
+#ifndef CVS422_NO_BARRIER
+#define CVS422_NO_BARRIER 0              // 1: TIMING EXPERIMENT ONLY (wrong pictures): how much the per-step barrier costs
+#endif
+__device__ __forceinline__ void group_barrier() {
+#if !CVS422_NO_BARRIER
+    asm volatile("bar.sync 0;" ::: "memory");
+#endif
+}
 
-// what every role of a row knows
-struct RowCtx {
-    const K422 *K;
-    const DivPair *dv;
-    Lags L;
-    Geo G;
-    Row422 rc;
-    int nsteps, lo, hi;                   // steps of a row; the role's interior range
-};
-
-// The step loop of a role: general steps up to lo, interior steps [lo, hi), general steps to the end, a barrier of
-// the group after every step.  STEP(s, edge) is the role's step.
-#define CVS422_ROLE_LOOP(ROLE, STEP_EDGE, STEP_FAST)                                    \
-    {                                                                                   \
-        int s = 0;                                                                      \
-        const int s_a = cx.lo < cx.nsteps ? cx.lo : cx.nsteps;                          \
-        _Pragma("unroll 1") for (; s < s_a; s++) { STEP_EDGE; group_barrier(); }        \
-        if (s < cx.hi) {                                                                \
-            role_enter(K, cx.L, ln, ROLE, s);                                           \
-            _Pragma("unroll 1") for (; s < cx.hi; s++) { STEP_FAST; group_barrier(); }  \
-            role_leave(K, cx.L, ln, ROLE, s);                                           \
-        }                                                                               \
-        _Pragma("unroll 1") for (; s < cx.nsteps; s++) { STEP_EDGE; group_barrier(); }  \
-    }
-
+// The general kernel: any width, any switch, pre-pass rows; every step is the general variant of its role
+// (yuv422_pipeline.cuh, "roles").  Rows the fast kernel below can take never come here (launch_yuv422).
 __global__ void __launch_bounds__(kNT, CVS422_MIN_CTAS) k_yuv422(const __grid_constant__ Launch422 a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31;
@@ -283,19 +268,11 @@ __global__ void __launch_bounds__(kNT, CVS422_MIN_CTAS) k_yuv422(const __grid_co
     ln.rv = smem + Smem422::off_rv + (size_t)lane * kStrideC;
     ln.rcomb = reinterpret_cast<int32_t *>(smem + Smem422::off_rcomb) + (size_t)lane * 3 * kMaxRecombine;
 
-    RowCtx cx;
-    cx.K = &K;
-    cx.dv = &a.dv;
-    cx.L = lags_of(K);
-    cx.G = geo_of(K);
-    cx.nsteps = line_steps(K);
-    row_setup(K, (unsigned)fd.field, fd.fieldno, row, __ldg(fd.rowinfo + row), cx.rc);
-    const Row422 &rc = cx.rc;
-    {
-        const RoleRange rr = role_interior(K, cx.L, role);
-        cx.lo = rr.lo;
-        cx.hi = a.vec ? rr.hi : rr.lo;    // the interior variant moves whole words; unaligned pictures take the general one
-    }
+    const Lags L = lags_of(K);
+    const Geo G = geo_of(K);
+    const int nsteps = line_steps(K);
+    Row422 rc;
+    row_setup(K, (unsigned)fd.field, fd.fieldno, row, __ldg(fd.rowinfo + row), rc);
 
     // the generator of a noise stream lives in the role that draws from it: luma in role 0, chroma in role 1
     if ((role == 0 && K.vnoise != 0) || (role == 1 && K.cnoise != 0)) {
@@ -340,37 +317,42 @@ __global__ void __launch_bounds__(kNT, CVS422_MIN_CTAS) k_yuv422(const __grid_co
         }
         const uint8_t *hsrow = (rc.rflags & RG_HEADSW_PRE) ? fd.hs_scratch + (size_t)(row - fd.hs_first) * (size_t)w : nullptr;
         const bool warp_hs = __any_sync(0xffffffffu, rc.hs_delay > 0);
-        if (__any_sync(0xffffffffu, hsrow != nullptr)) cx.hi = cx.lo;    // pre-pass rows only exist in the general variant
         const bool vec = a.vec != 0;      // (halo records are 16-byte aligned, so the halo lane qualifies too)
         StepIO cur, nxt;
         load_block<true>(src, K, 0, vec, cur);
-        CVS422_ROLE_LOOP(0,
-            (load_block<true>(src, K, s + 1, vec, nxt), role0_step<true>(K, cx.L, cx.G, rc, ln, s, cur, warp_hs, hsrow), cur = nxt),
-            ((s + 1 < cx.hi ? load_block_vec(src, s + 1, nxt) : load_block<true>(src, K, s + 1, vec, nxt)),
-             role0_step<false>(K, cx.L, cx.G, rc, ln, s, cur, warp_hs, hsrow), cur = nxt))
+#pragma unroll 1
+        for (int s = 0; s < nsteps; s++) {
+            load_block<true>(src, K, s + 1, vec, nxt);
+            role0_step(K, L, G, rc, ln, s, cur, warp_hs, hsrow);
+            cur = nxt;
+            group_barrier();
+        }
     } else if (role == 1) {
-        CVS422_ROLE_LOOP(1, role1_step<true>(K, cx.L, cx.G, a.dv, rc, ln, s), role1_step<false>(K, cx.L, cx.G, a.dv, rc, ln, s))
+#pragma unroll 1
+        for (int s = 0; s < nsteps; s++) {
+            role1_step(K, L, G, a.dv, rc, ln, s);
+            group_barrier();
+        }
     } else if (role == 2) {
-        uint32_t pu, pv, au, av;
-        CVS422_ROLE_LOOP(2,
-            (role2_front<true>(K, cx.L, cx.G, ln, s, pu, pv), au = __shfl_up_sync(0xffffffffu, pu, 1), av = __shfl_up_sync(0xffffffffu, pv, 1),
-             role2_back<true>(K, cx.L, cx.G, rc, ln, s, pu, pv, au, av)),
-            (role2_front<false>(K, cx.L, cx.G, ln, s, pu, pv), au = __shfl_up_sync(0xffffffffu, pu, 1), av = __shfl_up_sync(0xffffffffu, pv, 1),
-             role2_back<false>(K, cx.L, cx.G, rc, ln, s, pu, pv, au, av)))
+#pragma unroll 1
+        for (int s = 0; s < nsteps; s++) {
+            uint32_t pu, pv;
+            role2_front(K, L, G, ln, s, pu, pv);
+            const uint32_t au = __shfl_up_sync(0xffffffffu, pu, 1), av = __shfl_up_sync(0xffffffffu, pv, 1);
+            role2_back(K, L, G, rc, ln, s, pu, pv, au, av);
+            group_barrier();
+        }
     } else {
         for (int i = 0; i < 3 * kMaxRecombine; i++) ln.rcomb[i] = 16;
         uint8_t *dy = fd.y + y * a.ly, *du = fd.u + y * a.lu, *dvp = fd.v + y * a.lv;
         const bool vec = a.vec != 0;
-        StepIO o;
-        int bs;
-        CVS422_ROLE_LOOP(3,
-            { if (role3_step<true>(K, cx.L, cx.G, a.dv, rc, ln, s, o, bs) && valid) store_block<true>(dy, du, dvp, K, bs, vec, o); },
-            { role3_step<false>(K, cx.L, cx.G, a.dv, rc, ln, s, o, bs);
-              if (valid) {
-                  *reinterpret_cast<uint2 *>(dy + bs * kB) = make_uint2(o.y0, o.y1);
-                  *reinterpret_cast<uint32_t *>(du + bs * kBC) = o.u;
-                  *reinterpret_cast<uint32_t *>(dvp + bs * kBC) = o.v;
-              } })
+#pragma unroll 1
+        for (int s = 0; s < nsteps; s++) {
+            StepIO o;
+            int bs;
+            if (role3_step(K, L, G, a.dv, rc, ln, s, o, bs) && valid) store_block<true>(dy, du, dvp, K, bs, vec, o);
+            group_barrier();
+        }
     }
 }
 
@@ -424,6 +406,7 @@ __global__ void __launch_bounds__(kNT, CVS422_MIN_CTAS) k_yuv422_fast(const __gr
     ln.ru = smem + Smem422::off_ru + (size_t)lane * kStrideC;
     ln.rv = smem + Smem422::off_rv + (size_t)lane * kStrideC;
     ln.rcomb = nullptr;
+    Fast422::prime(K, ln);
 
     const Lags L = lags_of(K);
     const int nb = w / kB, nsteps = line_steps(K);

@@ -32,8 +32,7 @@ uint32_t load_word(const uint8_t *plane, long long plane_bytes, long long off, i
 
 extern "C" {
 
-// force_general: bit 0: 0 = kernel's own choice of interior / general steps, 1 = general variant everywhere;
-// bit 2: the general kernel (with its interior steps) also where the fast kernel would run;
+// force_general: bit 0: 0 = the fast kernel where it applies, 1 = the general kernel everywhere;
 // bit 1: the roles of a step in forward instead of reverse order (they must not depend on each other)
 int emu422_process(const cvs422_params *p, unsigned long long rng_pos,
                    uint8_t *yp, int ly, uint8_t *up, int lu, uint8_t *vp, int lv,
@@ -84,12 +83,6 @@ int emu422_process(const cvs422_params *p, unsigned long long rng_pos,
     const int nl = g.nl, nsteps = line_steps(K);
     const Lags LG = lags_of(K);
     const Geo GE = geo_of(K);
-    RoleRange rr[kRoles];
-    for (int r = 0; r < kRoles; r++) {
-        rr[r] = role_interior(K, LG, r);
-        if (force_general & 1) rr[r].hi = rr[r].lo;
-    }
-    if (fs.hs_count > 0) rr[0].hi = rr[0].lo;              // (pre-pass rows only exist in the general variant)
     int status = CVS_OK;
     for (int wp = 0; wp * 31 < nl; wp++) {
         std::vector<LaneMem> mem(32);
@@ -132,8 +125,9 @@ int emu422_process(const cvs422_params *p, unsigned long long rng_pos,
             for (int i = 0; i < K.recombine; i++) { L.rcomb[3 * i] = 16; L.rcomb[3 * i + 1] = 16; L.rcomb[3 * i + 2] = 16; }
         }
         // the fast kernel (k_yuv422_fast): one code path per role, no general steps
-        if (!(force_general & 5) && fast_row_ok(K) && fs.hs_count == 0) {
+        if (!(force_general & 1) && fast_row_ok(K) && fs.hs_count == 0) {
             const int nb = GE.nb;
+            for (int lane = 0; lane < 32; lane++) Fast422::prime(K, ln[lane]);
             for (int s = 0; s < nsteps; s++) {
                 for (int ri = 0; ri < kRoles; ri++) {
                     const int role = (force_general & 2) ? ri : kRoles - 1 - ri;
@@ -173,14 +167,11 @@ int emu422_process(const cvs422_params *p, unsigned long long rng_pos,
             }
             continue;
         }
-        // The four roles of a row run concurrently on the GPU and meet at a barrier after every step, so within a
-        // step no role may depend on another one: run them in REVERSE order here.
+        // The general kernel (k_yuv422).  The four roles of a row run concurrently on the GPU and meet at a barrier after
+        // every step, so within a step no role may depend on another one: run them in REVERSE order here.
         for (int s = 0; s < nsteps; s++) {
             for (int ri = 0; ri < kRoles; ri++) {
                 const int role = (force_general & 2) ? ri : kRoles - 1 - ri;
-                const bool fast = s >= rr[role].lo && s < rr[role].hi;
-                if (rr[role].hi > rr[role].lo && s == rr[role].lo) for (int lane = 0; lane < 32; lane++) role_enter(K, LG, ln[lane], role, s);
-                if (rr[role].hi > rr[role].lo && s == rr[role].hi) for (int lane = 0; lane < 32; lane++) role_leave(K, LG, ln[lane], role, s);
                 if (role == 0) {
                     for (int lane = 0; lane < 32; lane++) {
                         const long long y = (long long)field + 2 * rows[lane];
@@ -191,32 +182,20 @@ int emu422_process(const cvs422_params *p, unsigned long long rng_pos,
                         in.y1 = load_word(sy.data(), by, y * ly + x0 + 4, w + 2 - x0 - 4);
                         in.u = load_word(su.data(), bu, y * lu + c0, K.cw - c0);
                         in.v = load_word(sv.data(), bv, y * lv + c0, K.cw - c0);
-                        if (fast) role0_step<false>(K, LG, GE, rc[lane], ln[lane], s, in, warp_hs, hsrow[lane]);
-                        else role0_step<true>(K, LG, GE, rc[lane], ln[lane], s, in, warp_hs, hsrow[lane]);
+                        role0_step(K, LG, GE, rc[lane], ln[lane], s, in, warp_hs, hsrow[lane]);
                     }
                 } else if (role == 1) {
-                    for (int lane = 0; lane < 32; lane++) {
-                        if (fast) role1_step<false>(K, LG, GE, dv, rc[lane], ln[lane], s);
-                        else role1_step<true>(K, LG, GE, dv, rc[lane], ln[lane], s);
-                    }
+                    for (int lane = 0; lane < 32; lane++) role1_step(K, LG, GE, dv, rc[lane], ln[lane], s);
                 } else if (role == 2) {
                     uint32_t pu[32], pv[32];
-                    for (int lane = 0; lane < 32; lane++) {
-                        if (fast) role2_front<false>(K, LG, GE, ln[lane], s, pu[lane], pv[lane]);
-                        else role2_front<true>(K, LG, GE, ln[lane], s, pu[lane], pv[lane]);
-                    }
-                    for (int lane = 0; lane < 32; lane++) {
-                        const uint32_t au = lane ? pu[lane - 1] : 0, av = lane ? pv[lane - 1] : 0;
-                        if (fast) role2_back<false>(K, LG, GE, rc[lane], ln[lane], s, pu[lane], pv[lane], au, av);
-                        else role2_back<true>(K, LG, GE, rc[lane], ln[lane], s, pu[lane], pv[lane], au, av);
-                    }
+                    for (int lane = 0; lane < 32; lane++) role2_front(K, LG, GE, ln[lane], s, pu[lane], pv[lane]);
+                    for (int lane = 0; lane < 32; lane++)
+                        role2_back(K, LG, GE, rc[lane], ln[lane], s, pu[lane], pv[lane], lane ? pu[lane - 1] : 0, lane ? pv[lane - 1] : 0);
                 } else {
                     for (int lane = 0; lane < 32; lane++) {
                         StepIO out;
                         int bs;
-                        const bool have = fast ? role3_step<false>(K, LG, GE, dv, rc[lane], ln[lane], s, out, bs)
-                                               : role3_step<true>(K, LG, GE, dv, rc[lane], ln[lane], s, out, bs);
-                        if (have && valid[lane]) {
+                        if (role3_step(K, LG, GE, dv, rc[lane], ln[lane], s, out, bs) && valid[lane]) {
                             const long long y = (long long)field + 2 * rows[lane];
                             for (int j = 0; j < kB; j++) {
                                 const int x = bs * kB + j;

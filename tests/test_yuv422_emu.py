@@ -51,9 +51,9 @@ CASES = [
 
 
 @pytest.mark.parametrize("w,h,n,argv", CASES)
-@pytest.mark.parametrize("general", [0, 1, 2, 4, 6])
+@pytest.mark.parametrize("general", [0, 1, 2, 3])
 def test_emulated_kernel_equals_oracle(orc, emu, w, h, n, argv, general):
-    if general == 1 and w >= 1920:
+    if general in (1, 3) and w >= 1920:
         pytest.skip("covered by the kernel's own choice")
     p = helpers.params422(*argv)
     want, g = helpers.run_oracle422(orc, p, w, h, n)
