@@ -394,7 +394,7 @@ def measure_yuv422(torch, timed, dev, local_rank, w, h, argv, max_batch, steps, 
     torch.cuda.empty_cache()
     return {"workload": "%dx%d planar 4:2:2, ffmpeg_to_composite %s, in place" % (w, h, " ".join(argv)),
             "value": n * steps / (ms / 1e3), "unit": "fields/s", "fields_per_step": n, "steps": steps,
-            "kernel": "cvs422::k_yuv422 (fp64, bit-exact)", "kernel_ms_per_launch": kms, "gpu_launches": launches,
+            "kernel": "cvs422::k_yuv422_fast (fp64, bit-exact; four role warps per group of 31 rows)", "kernel_ms_per_launch": kms, "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "algorithmic_bytes_per_launch": alg}}
 

@@ -935,28 +935,9 @@ int cvs_field_loop_host(cvs_ctx *ctx, const cvs_field_loop *d, int n, unsigned l
     CVS_CUDA(grow(&c->fl_yuv, &c->fl_yuv_cap, yuv_pic * (size_t)n));
     CVS_CUDA(grow(&c->fl_last_row, &c->fl_last_row_cap, (size_t)dstride, true));     // the zeroed ring (:2069-2092)
 
-    // 1. decoder pictures up (s_in), 2. scaled to BGRA at the output size (frame_copy_scale)
-    for (int q = 0; q < d->nsrc; q++)
-        for (int i = 0; i < nplanes; i++)
-            CVS_CUDA(cudaMemcpy2DAsync(c->fl_src + (size_t)q * src_pic + plane_off[i], (size_t)dl[i],
-                                       (const uint8_t *)d->src[i] + (size_t)q * (size_t)d->src_pic_stride[i], (size_t)d->src_linesize[i],
-                                       (size_t)rowb[i], (size_t)rows[i], cudaMemcpyHostToDevice, c->s_in));
-    while (c->ev_in.empty()) {
-        cudaEvent_t a, b;
-        CVS_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
-        CVS_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
-        c->ev_in.push_back(a);
-        c->ev_k.push_back(b);
-    }
-    CVS_CUDA(cudaEventRecord(c->ev_in[0], c->s_in));
-    CVS_CUDA(cudaStreamWaitEvent(c->stream, c->ev_in[0], 0));
-    {
-        const void *sp[3] = {c->fl_src + plane_off[0], nplanes >= 2 ? c->fl_src + plane_off[1] : nullptr,
-                             nplanes == 3 ? c->fl_src + plane_off[2] : nullptr};
-        const long long sps[3] = {(long long)src_pic, (long long)src_pic, (long long)src_pic};
-        const int rc = cvs_scale_to_bgra_device(c, c->fl_scaled, dstride, (long long)dpic, w, h, sp, dl, sps, sw, sh, fmt, d->nsrc);
-        if (rc != CVS_OK) return rc;
-    }
+    // 1. decoder pictures up (s_in) and 2. scaled to BGRA at the output size (frame_copy_scale) happen chunk by chunk below,
+    // just ahead of the fields that need them: the uploads of later chunks then overlap the kernels and the downloads
+    // of earlier ones (PCIe is full duplex; uploading everything first cost the upload time on top).
     // 3. per chunk: composite_layer() + line doubling, the inherited ring row, the encoder's YUV; 4. pictures down
     std::vector<int32_t> index((size_t)n);
     for (int k = 0; k < n; k++) index[(size_t)k] = d->src_of_field ? d->src_of_field[k] : (int32_t)(((long long)k * d->nsrc) / n);
@@ -965,9 +946,36 @@ int cvs_field_loop_host(cvs_ctx *ctx, const cvs_field_loop *d, int n, unsigned l
     c->bob = 1;
     int rc = CVS_OK;
     const int chunk = c->host_chunk;
-    int ci = 0;
+    int ci = 0, up = 0;                   // sources [0, up) are on the device and scaled
     for (int k0 = 0; k0 < n && rc == CVS_OK; k0 += chunk, ci++) {
         const int m = n - k0 < chunk ? n - k0 : chunk;
+        while ((int)c->ev_k.size() <= ci) {
+            cudaEvent_t a, b;
+            if (cudaEventCreateWithFlags(&a, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&b, cudaEventDisableTiming) != cudaSuccess) { rc = CVS_ERR_CUDA; break; }
+            c->ev_in.push_back(a);
+            c->ev_k.push_back(b);
+        }
+        if (rc != CVS_OK) break;
+        int need = 0;
+        for (int k = k0; k < k0 + m; k++) need = index[(size_t)k] + 1 > need ? index[(size_t)k] + 1 : need;
+        if (need > up) {
+            cudaError_t e = cudaSuccess;
+            for (int q = up; q < need && e == cudaSuccess; q++)
+                for (int i = 0; i < nplanes && e == cudaSuccess; i++)
+                    e = cudaMemcpy2DAsync(c->fl_src + (size_t)q * src_pic + plane_off[i], (size_t)dl[i],
+                                          (const uint8_t *)d->src[i] + (size_t)q * (size_t)d->src_pic_stride[i], (size_t)d->src_linesize[i],
+                                          (size_t)rowb[i], (size_t)rows[i], cudaMemcpyHostToDevice, c->s_in);
+            if (e == cudaSuccess) e = cudaEventRecord(c->ev_in[ci], c->s_in);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(c->stream, c->ev_in[ci], 0);
+            if (e != cudaSuccess) { rc = CVS_ERR_CUDA; break; }
+            const uint8_t *base = c->fl_src + (size_t)up * src_pic;
+            const void *sp[3] = {base + plane_off[0], nplanes >= 2 ? base + plane_off[1] : nullptr, nplanes == 3 ? base + plane_off[2] : nullptr};
+            const long long sps[3] = {(long long)src_pic, (long long)src_pic, (long long)src_pic};
+            rc = cvs_scale_to_bgra_device(c, c->fl_scaled + (size_t)up * dpic, dstride, (long long)dpic, w, h, sp, dl, sps, sw, sh, fmt, need - up);
+            if (rc != CVS_OK) break;
+            up = need;
+        }
         uint8_t *out = c->fl_out + (size_t)k0 * dpic;
         rc = run_device(c, out, dpic, dstride, c->fl_scaled, dpic, dstride, w, h, 0, 0, m, first_fieldno + (unsigned long long)k0, -1,
                         index.data() + k0);
@@ -982,14 +990,6 @@ int cvs_field_loop_host(cvs_ctx *ctx, const cvs_field_loop *d, int n, unsigned l
         uint8_t *yv = c->fl_yuv + (size_t)k0 * yuv_pic;
         rc = cvs_bgra_to_yuv_device(c, yv, yl, (long long)yuv_pic, yv + ypl, cl, (long long)yuv_pic, yv + ypl + cpl, cl, (long long)yuv_pic,
                                     out, dstride, (long long)dpic, w, h, m, d->out_format);
-        if (rc != CVS_OK) break;
-        while ((int)c->ev_k.size() <= ci) {
-            cudaEvent_t a, b;
-            if (cudaEventCreateWithFlags(&a, cudaEventDisableTiming) != cudaSuccess ||
-                cudaEventCreateWithFlags(&b, cudaEventDisableTiming) != cudaSuccess) { rc = CVS_ERR_CUDA; break; }
-            c->ev_in.push_back(a);
-            c->ev_k.push_back(b);
-        }
         if (rc != CVS_OK) break;
         if (cudaEventRecord(c->ev_k[ci], c->stream) != cudaSuccess || cudaStreamWaitEvent(c->s_out, c->ev_k[ci], 0) != cudaSuccess) { rc = CVS_ERR_CUDA; break; }
         for (int k = k0; k < k0 + m && rc == CVS_OK; k++) {

@@ -9,7 +9,9 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <atomic>
 #include <cstring>
+#include <thread>
 #include <memory>
 #include <new>
 #include <vector>
@@ -77,6 +79,7 @@ struct cvs422_ctx {
     uint8_t *d_scratch = nullptr, *d_halo = nullptr;
     int32_t *d_status = nullptr, *h_status = nullptr;
     double *d_lut = nullptr;
+    int plan_threads = 4;                         // host threads that build the per-row side tables of a batch (CVS_PLAN_THREADS)
     size_t lut_cap = 0;
     std::vector<double> lut_host;                 // what d_lut currently holds
     uint8_t *d_planes = nullptr;                  // device pictures of the host-pointer entry points
@@ -155,7 +158,9 @@ int run_device(cvs422_ctx *c, uint8_t *y, uint8_t *u, uint8_t *v, long long psy,
     std::vector<double> lut;
     int rc = make_k422(c->p, w, h, a.K, a.dv, lut);
     if (rc != CVS_OK) return rc;
-    if (lut != c->lut_host || !c->d_lut) {
+    // (bytes, not values: the byte tables behind the cos / sin pairs can look like NaNs, which never compare equal)
+    const bool same = lut.size() == c->lut_host.size() && (lut.empty() || std::memcmp(lut.data(), c->lut_host.data(), lut.size() * sizeof(double)) == 0);
+    if (!same || !c->d_lut) {
         if (lut.size() > c->lut_cap || !c->d_lut) {
             if (c->d_lut) { CVS_CUDA(cudaStreamSynchronize(c->stream)); cudaFree(c->d_lut); c->d_lut = nullptr; }
             c->lut_cap = lut.size() > 64 ? lut.size() : 64;
@@ -182,37 +187,75 @@ int run_device(cvs422_ctx *c, uint8_t *y, uint8_t *u, uint8_t *v, long long psy,
     const int halo_y = round_up(w + 2, 16), halo_c = round_up(w / 2, 16);
     const int halo_pitch = halo_y + 2 * halo_c;
     int nitems = 0, total_rows = 0, max_nl = 0, min_nl = 1 << 30;
-    FieldSide fs;
+    // pass 1 (sequential, cheap): where every field starts in the rand() stream and in the batch's sequence of rows
+    std::vector<RandCursor> at((size_t)n);
     for (int k = 0; k < n; k++) {
         const unsigned long long fieldno = first_fieldno + (unsigned long long)k;
         const unsigned field = (unsigned)((fieldno & 1ULL) ^ 1ULL);          // bottom field first (:1784)
         if (!plan[field]) { rc = get_plan(c, w, h, field, &plan[field]); if (rc != CVS_OK) return rc; }
         const GeomPlan &g = plan[field]->g;
-        build_field_side_at(c->p, g, c->cur, fs);
+        at[(size_t)k] = c->cur;
         c->cur.jump(g.jumpN, g.ndraws);
         FieldDesc422 &fd = sl.h_fields[k];
-        fd.y = y + (long long)k * psy; fd.u = u + (long long)k * psu; fd.v = v + (long long)k * psv;
-        fd.rowinfo = sl.d_rowinfo + (size_t)k * (size_t)c->nl_max;
-        fd.seek = plan[field]->d_seek;
-        fd.hs_scratch = c->d_scratch + (size_t)k * (size_t)c->hs_max * (size_t)c->max_w;
-        fd.hs_shift = sl.d_hsshift + (size_t)k * (size_t)c->hs_max;
-        fd.halo = c->d_halo + (size_t)k * (size_t)c->wpf_max * (size_t)c->halo_pitch_max;
-        fd.fieldno = fieldno;
-        fd.field = (int32_t)field; fd.nl = g.nl; fd.hs_first = fs.hs_first; fd.hs_count = fs.hs_count;
         fd.row_start = total_rows; fd.pad_ = 0;
         total_rows += g.nl;
         if (g.nl > max_nl) max_nl = g.nl;
         if (g.nl < min_nl) min_nl = g.nl;
-        std::memcpy(fd.window, fs.window, sizeof(fs.window));
-        if (g.nl > 0) std::memcpy(sl.h_rowinfo + (size_t)k * (size_t)c->nl_max, fs.rowinfo.data(), (size_t)g.nl * sizeof(uint32_t));
-        if (fs.hs_count > c->hs_max) return CVS_ERR_CAPACITY;
-        for (int i = 0; i < fs.hs_count; i++) {
-            sl.h_hsshift[(size_t)k * (size_t)c->hs_max + (size_t)i] = fs.hs_shift[(size_t)i];
+    }
+    // pass 2: the per-row side tables of the fields, on a few host threads (a field costs ~12 us; one thread kept a
+    // 339-field launch waiting once the kernel took less than 4 ms)
+    std::atomic<bool> capacity_error{false};
+    auto plan_range = [&](int k0, int k1) {
+        FieldSide fs;
+        for (int k = k0; k < k1; k++) {
+            const unsigned long long fieldno = first_fieldno + (unsigned long long)k;
+            const unsigned field = (unsigned)((fieldno & 1ULL) ^ 1ULL);
+            const GeomPlan &g = plan[field]->g;
+            build_field_side_at(c->p, g, at[(size_t)k], fs);
+            FieldDesc422 &fd = sl.h_fields[k];
+            fd.y = y + (long long)k * psy; fd.u = u + (long long)k * psu; fd.v = v + (long long)k * psv;
+            fd.rowinfo = sl.d_rowinfo + (size_t)k * (size_t)c->nl_max;
+            fd.seek = plan[field]->d_seek;
+            fd.hs_scratch = c->d_scratch + (size_t)k * (size_t)c->hs_max * (size_t)c->max_w;
+            fd.hs_shift = sl.d_hsshift + (size_t)k * (size_t)c->hs_max;
+            fd.halo = c->d_halo + (size_t)k * (size_t)c->wpf_max * (size_t)c->halo_pitch_max;
+            fd.fieldno = fieldno;
+            fd.field = (int32_t)field; fd.nl = g.nl; fd.hs_first = fs.hs_first; fd.hs_count = fs.hs_count;
+            std::memcpy(fd.window, fs.window, sizeof(fs.window));
+            if (g.nl > 0) std::memcpy(sl.h_rowinfo + (size_t)k * (size_t)c->nl_max, fs.rowinfo.data(), (size_t)g.nl * sizeof(uint32_t));
+            if (fs.hs_count > c->hs_max) { capacity_error = true; fd.hs_count = 0; continue; }
+            for (int i = 0; i < fs.hs_count; i++) sl.h_hsshift[(size_t)k * (size_t)c->hs_max + (size_t)i] = fs.hs_shift[(size_t)i];
+        }
+    };
+    const int nthreads = (n >= 64) ? c->plan_threads : 1;
+    if (nthreads <= 1) {
+        plan_range(0, n);
+    } else {
+        // a thread that cannot be started (std::system_error must not cross the C ABI) leaves its range, and every
+        // later one, to this thread
+        std::vector<std::thread> pool;
+        const int per = (n + nthreads - 1) / nthreads;
+        int done_to = per < n ? per : n;
+        try {
+            pool.reserve((size_t)nthreads);
+            for (int t = 1; t < nthreads && t * per < n; t++) {
+                const int k1 = (t + 1) * per < n ? (t + 1) * per : n;
+                pool.emplace_back(plan_range, t * per, k1);
+                done_to = k1;
+            }
+        } catch (...) {
+        }
+        plan_range(0, per < n ? per : n);
+        for (auto &th : pool) th.join();
+        for (int k0 = done_to; k0 < n; k0 += per) plan_range(k0, k0 + per < n ? k0 + per : n);
+    }
+    if (capacity_error.load()) return CVS_ERR_CAPACITY;
+    for (int k = 0; k < n; k++)
+        for (int i = 0; i < sl.h_fields[k].hs_count; i++) {
             sl.h_items[nitems].field_idx = k;
             sl.h_items[nitems].slot = i;
             nitems++;
         }
-    }
     CVS_CUDA(cudaMemcpyAsync(sl.d_fields, sl.h_fields, (size_t)n * sizeof(FieldDesc422), cudaMemcpyHostToDevice, c->s_tab));
     CVS_CUDA(cudaMemcpyAsync(sl.d_rowinfo, sl.h_rowinfo, (size_t)n * (size_t)c->nl_max * sizeof(uint32_t), cudaMemcpyHostToDevice, c->s_tab));
     if (nitems > 0) {
@@ -286,6 +329,14 @@ int cvs422_create(cvs422_ctx **out, const cvs422_params *p, int device, int max_
     if (cudaSetDevice(device) != cudaSuccess) return CVS_ERR_CUDA;
     cvs422_ctx *c = new (std::nothrow) cvs422_ctx();
     if (!c) return CVS_ERR_NOMEM;
+    {
+        unsigned hw = std::thread::hardware_concurrency();
+        if (hw > 0 && (int)hw < c->plan_threads) c->plan_threads = (int)hw;
+        if (const char *e = std::getenv("CVS_PLAN_THREADS")) {
+            const int v = std::atoi(e);
+            if (v >= 1 && v <= 64) c->plan_threads = v;
+        }
+    }
     c->p = *p;
     c->device = device;
     c->max_w = max_w; c->max_h = max_h; c->max_batch = max_batch;

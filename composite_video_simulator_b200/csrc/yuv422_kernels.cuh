@@ -33,7 +33,7 @@ namespace cvs422 {
 // a lane that runs every stage of its row needs ~210 registers (35 doubles of filter state), i.e. 2 warps per
 // scheduler, each an in-order stream of dependent 8.65-cycle FP64 operations and 4-cycle integer chains, and a
 // 37 KB loop that does not fit the SM's 32 KB instruction cache (issue slots 52 % busy whatever else was tried).
-// Split by role a warp needs 90 registers (5 groups = 20 warps per SM) and the four loops together are 25 KB.
+// Split by role a warp needs ~95 registers (5 groups = 20 warps per SM) and the four loops together are 25 KB.
 constexpr int kNT = 32 * kRoles;         // threads per CTA
 constexpr int kRowsPerWarp = 31;         // rows per group; lane 0 is the halo row
 constexpr int kStrideY = kRingY + 4;     // per-lane ring strides: +1 word so that equal offsets of the 32 lanes
@@ -82,9 +82,10 @@ struct Smem422 {
     static constexpr size_t rcomb = (size_t)32 * 3 * kMaxRecombine * sizeof(int32_t);
     static constexpr size_t off_wins = 0, off_ry = off_wins + wins, off_rya = off_ry + ry, off_ru = off_rya + rya,
                             off_rv = off_ru + rc, off_rcomb = off_rv + rc, off_rng = off_rcomb + rcomb;
-    static constexpr size_t total_max = off_rng + 2 * rng1;
+    static constexpr size_t total_max = off_rng + 2 * rng1 + (size_t)(2 * kPhaseMapMax + 1) * 512;
     static CVS_HD size_t off_rng_chroma(const K422 &K) { return off_rng + (K.vnoise != 0 ? rng1 : 0); }
-    static CVS_HD size_t total(const K422 &K) { return off_rng_chroma(K) + (K.cnoise != 0 ? rng1 : 0); }
+    static CVS_HD size_t off_pmap(const K422 &K) { return off_rng_chroma(K) + (K.cnoise != 0 ? rng1 : 0); }
+    static CVS_HD size_t total(const K422 &K) { return off_pmap(K) + phase_maps_bytes(K); }   // (only the fast kernel uses the maps)
 };
 
 // what a lane reads its row from
@@ -226,7 +227,7 @@ __global__ void __launch_bounds__(kNT, CVS422_MIN_CTAS) k_yuv422(const __grid_co
     // Warp k of a CTA sits on scheduler k: with role = warp every role-0 warp of an SM would share ONE scheduler (and
     // the roles are not equally long), so the assignment rotates with the group.
 #if CVS422_ROTATE_ROLES
-    const int role = ((tid >> 5) + gw) & (kRoles - 1);
+    const int role = ((tid >> 5) + gw) % kRoles;
 #else
     const int role = tid >> 5;
 #endif
@@ -367,7 +368,7 @@ __global__ void __launch_bounds__(kNT, CVS422_MIN_CTAS) k_yuv422_fast(const __gr
     // instructions) -- different for every role.  Rotating the assignment with the group gives every scheduler the same
     // mix; the four loops together fit the SM's instruction cache, so the mix costs nothing there.
 #if CVS422_ROTATE_ROLES
-    const int role = ((tid >> 5) + gw) & (kRoles - 1);
+    const int role = ((tid >> 5) + gw) % kRoles;
 #else
     const int role = tid >> 5;
 #endif
@@ -412,6 +413,12 @@ __global__ void __launch_bounds__(kNT, CVS422_MIN_CTAS) k_yuv422_fast(const __gr
     const int nb = w / kB, nsteps = line_steps(K);
     Row422 rc;
     row_setup(K, (unsigned)fd.field, fd.fieldno, row, __ldg(fd.rowinfo + row), rc);
+    if (K.flags & G_PHASE_MAP) {          // the rotation tables into shared memory (first used after the first barrier)
+        uint8_t *maps = smem + Smem422::off_pmap(K);
+        const uint4 *from = reinterpret_cast<const uint4 *>(phase_maps(K));
+        for (int i = tid; i < (int)(phase_maps_bytes(K) / 16); i += kNT) reinterpret_cast<uint4 *>(maps)[i] = __ldg(from + i);
+        rc.pmap = row_phase_map(K, maps, __ldg(fd.rowinfo + row));
+    }
 
     if ((role == 0 && K.vnoise != 0) || (role == 1 && K.cnoise != 0)) {
         uint32_t *win = reinterpret_cast<uint32_t *>(smem + Smem422::off_wins) + role * 128;

@@ -10,7 +10,7 @@
 // launch constants (lags_of).
 //
 // The stages of a row are shared out to FOUR ROLES, one warp each (see lags_of and yuv422_kernels.cuh): a warp then
-// holds a quarter of the filter state (90 registers instead of 210), five groups fit on an SM, and the roles of a
+// holds a quarter of the filter state (~95 registers instead of 210), five groups of four warps fit on an SM, and the roles of a
 // group meet at a barrier after every step.
 //
 // Arithmetic: the reference's filters are IEEE doubles and their results are truncated to 8 bits, and a float
@@ -62,6 +62,7 @@ constexpr int kMaxRecombine = 4;         // -yc-recomb rounds the rings have roo
 constexpr int kRingA = 64;               // per-lane ring of the composite signal for the in-ring head-switch delay
 constexpr int kHsMaxDelay = kRingA - 2 * kB;   // largest head-switch delay that ring can express
 constexpr int kWarm = 64;                // noise warm-up length (samples), see cvs::warm_luma
+constexpr int kPhaseMapMax = 15;         // largest -chroma-phase-noise whose rotation is tabulated (31 states x 512 bytes)
 
 enum : uint32_t {
     G_IN_LP = 1u << 0,        // composite_in_chroma_lowpass
@@ -74,7 +75,8 @@ enum : uint32_t {
     G_VBLEND = 1u << 7,       // vhs_chroma_vert_blend && output_ntsc
     G_SVIDEO = 1u << 8,
     G_PHASE = 1u << 9,        // video_chroma_phase_noise != 0
-    G_GENERAL = 1u << 10,     // a rarely used switch is on: every step takes the general (edge) variant
+    G_GENERAL = 1u << 10,     // a rarely used switch is on: the general kernel
+    G_PHASE_MAP = 1u << 11,   // the phase-noise rotation of a byte is tabulated behind phase_lut (pnoise <= kPhaseMapMax)
 };
 
 // per-row flags in the host side table (same packing as cvs::rowinfo_pack)
@@ -93,6 +95,8 @@ struct K422 {
     double a_ch;                          // VHS chroma lowpass                                           (:837-841)
     double a_csharp, sharpen_c;           // VHS chroma sharpen (2x chroma cut)                           (:910-921)
     const double *phase_lut;              // [2*pnoise+1][2] = {cos, sin}(state*pi/100)                   (:765,:772-773)
+                                          // G_PHASE_MAP: followed by [2*pnoise+1][2][256] bytes, the rotated U / V byte of
+                                          // every input byte and state (the rotation's input is an 8-bit sample)
     uint32_t flags;
     int32_t d_in[2], d_out[2];            // write delays of the input / output lowpass (samples)
     int32_t cd;                           // VHS chroma delay 4 / 5 / 6                                   (:793-803)
@@ -108,14 +112,15 @@ struct K422 {
 // Block lags of a configuration (blocks behind the load front: a stage works on block s - lag at step s).
 // A row is worked on by FOUR warps at once, one per ROLE (a group of consecutive stages); the roles of a row meet at
 // a barrier after every step, so a role reads what the previous role wrote in an EARLIER step: one extra block of
-// lag at every role boundary.
+// lag at every role boundary.  (Five roles -- role 2 split after the luma sharpen -- were measured too: 3.65 ms
+// against 3.53 ms per launch; more code for the same instruction cache, profiles/ab_variants_r2.txt.)
 //   role 0: G0 G1 G2      load, input chroma lowpass, first modulation (luma noise, head switch)
 //   role 1: G3a           Y/C separation, chroma / phase noise, VHS luma lowpass + boost
-//   role 2: G3b G4        VHS chroma lowpass, VHS luma sharpen, vertical blend, chroma sharpen
+//   role 2: G3b G4        VHS chroma lowpass, VHS luma sharpen, vertical chroma blend, chroma sharpen
 //   role 3: G5 GE GO ST   re-modulation, second demodulation, dropout, -yc-recomb, output chroma lowpass, store
 constexpr int kRoles = 4;
 struct Lags {
-    int bM, bD, bC, bV, bD2, bE, bF, bS;  // as offsets: block = s - lag
+    int bM, bD, bC, bV, bR, bD2, bE, bF, bS;   // as offsets: block = s - lag
 };
 CVS_HD Lags lags_of(const K422 &K) {
     Lags L;
@@ -124,8 +129,9 @@ CVS_HD Lags lags_of(const K422 &K) {
     L.bD = L.bM + 2;                      // demodulation reads two bytes of the next block; role boundary
     L.bC = L.bD + 1;                      // role boundary
     L.bV = L.bC + K.lagV;                 // the VHS chroma lowpass writes 4..6 samples back
-    L.bD2 = L.bV + 2;                     // as bD
-    L.bE = vhs ? (sv ? L.bV + 1 : L.bD2) : L.bD + 1;
+    L.bR = L.bV + 1;                      // role boundary
+    L.bD2 = L.bR + 1;                     // as bD
+    L.bE = vhs ? (sv ? L.bR : L.bD2) : L.bD + 1;
     L.bF = L.bE + K.recombine;
     L.bS = L.bF + 1;
     return L;
@@ -230,8 +236,11 @@ CVS_HD int div50(int v) {                // exact for every 32-bit magnitude
 #ifndef CVS422_CU
 #define CVS422_CU 2                      // chroma samples per iteration of a rolled filter loop: 1, 2 or 4
 #endif
+#ifndef CVS422_CU_MID
+#define CVS422_CU_MID CVS422_CU          // the same for the VHS chroma lowpass and the chroma sharpen (role 2, the longest role)
+#endif
 #ifndef CVS422_LU
-#define CVS422_LU 4                      // luma pixels per iteration: 1, 2, 4 or 8
+#define CVS422_LU 8                      // luma pixels per iteration: 1, 2, 4 or 8
 #endif
 #if defined(__CUDA_ARCH__)
 #define CVS_ROLLED _Pragma("unroll 1")
@@ -301,7 +310,10 @@ struct Row422 {
     int fl[4];             // 0xFF where the demodulator flips the sign of the chroma sample (x & 3), else 0 (:527-530)
     uint32_t flx;          // ~(fl[0..3] as bytes): chroma word ^ flx = 255 - (flipped) chroma for four pixels at once
     uint32_t selU, selV;   // byte selectors that pick the U / V samples out of eight demodulated pixels
+    uint32_t selM;         // byte selector: the chroma sample (U or V) that rides on pixels 0..3 of a block; + 0x2222: 4..7
+    int mX[4], mC[4];      // modulation of pixel (x & 3) without a multiply: y + (t ^ mX) + mC = y +- (t - 128)
     double cosp, sinp;     // phase noise rotation of this row
+    const uint8_t *pmap;   // fast kernel: the row's 512-byte rotation table (U then V), or null
 };
 
 CVS_HD int line_phase(const K422 &K, unsigned long long fieldno, unsigned y) {
@@ -325,8 +337,17 @@ CVS_HD void row_setup(const K422 &K, unsigned field, unsigned long long fieldno,
         rc.fl[j] = (((j + rc.xi + 2) & 3) < 2) ? 0xFF : 0;
     }
     rc.flx = ~((uint32_t)rc.fl[0] | ((uint32_t)rc.fl[1] << 8) | ((uint32_t)rc.fl[2] << 16) | ((uint32_t)rc.fl[3] << 24));
+    rc.selM = 0;
+    CVS_UNROLL
+    for (int j = 0; j < 4; j++) {
+        const int ph = (rc.xi + j) & 3;                       // 0: +U, 1: +V, 2: -U, 3: -V
+        rc.selM |= (uint32_t)(((ph & 1) ? 4 : 0) + (j >> 1)) << (4 * j);
+        rc.mX[j] = (ph & 2) ? -1 : 0;
+        rc.mC[j] = (ph & 2) ? 129 : -128;
+    }
     rc.selU = (rc.xi & 1) ? 0x7531u : 0x6420u;
     rc.selV = (rc.xi & 1) ? 0x6420u : 0x7531u;
+    rc.pmap = nullptr;
     if (K.flags & G_PHASE) {
         const int st = (int)(int16_t)(rowinfo & 0xFFFFu);
         rc.cosp = K.phase_lut[2 * (st + K.pnoise)];
@@ -335,6 +356,13 @@ CVS_HD void row_setup(const K422 &K, unsigned field, unsigned long long fieldno,
         rc.cosp = 1;
         rc.sinp = 0;
     }
+}
+
+// the byte tables behind phase_lut (G_PHASE_MAP) and a row's table in a copy of them
+CVS_HD const uint8_t *phase_maps(const K422 &K) { return reinterpret_cast<const uint8_t *>(K.phase_lut + 2 * (2 * K.pnoise + 1)); }
+CVS_HD size_t phase_maps_bytes(const K422 &K) { return (K.flags & G_PHASE_MAP) ? (size_t)(2 * K.pnoise + 1) * 512 : 0; }
+CVS_HD const uint8_t *row_phase_map(const K422 &K, const uint8_t *maps, uint32_t rowinfo) {
+    return maps + (size_t)((int)(int16_t)(rowinfo & 0xFFFFu) + K.pnoise) * 512;
 }
 
 // ---- per-lane state -----------------------------------------------------------------------------------
@@ -758,15 +786,15 @@ struct Fast422 {
     }
 
     // three-pole lowpass (BOOST: preceded by s += s - highpass(s)) on the four samples of wu and of wv
-    template <bool BOOST>
+    template <bool BOOST, int CU = CVS422_CU>
     static CVS_HD void lp_pair(uint32_t wu, uint32_t wv, double *hpU, double *lpU, double *hpV, double *lpV, double aU, double ahU,
                                double aV, double ahV, uint32_t &ou, uint32_t &ov) {
         ou = ov = 0;
         CVS_ROLLED
-        for (int it = 0; it < kBC / CVS422_CU; it++) {
-            int qu[CVS422_CU], qv[CVS422_CU];
+        for (int it = 0; it < kBC / CU; it++) {
+            int qu[CU], qv[CU];
             CVS_UNROLL
-            for (int j = 0; j < CVS422_CU; j++) {
+            for (int j = 0; j < CU; j++) {
                 double s = fu2d((uint32_t)byte_of(wu, j)), t = fu2d((uint32_t)byte_of(wv, j));
                 if (BOOST) {
                     const double lu = cascade<1>(hpU, s, ahU), lv = cascade<1>(hpV, t, ahV);
@@ -778,25 +806,25 @@ struct Fast422 {
                 qu[j] = fq(s);
                 qv[j] = fq(t);
             }
-            push_c(ou, qu);
-            push_c(ov, qv);
-            if (CVS422_CU < 4) { wu >>= (8 * CVS422_CU) & 31; wv >>= (8 * CVS422_CU) & 31; }
+            push_c<CU>(ou, qu);
+            push_c<CU>(ov, qv);
+            if (CU < 4) { wu >>= (8 * CU) & 31; wv >>= (8 * CU) & 31; }
         }
     }
-    // CVS422_CU clamped bytes enter a word from the top (after 4 / CU pushes the first one is byte 0)
+    // CU clamped bytes enter a word from the top (after 4 / CU pushes the first one is byte 0)
+    template <int CU>
     static CVS_HD void push_c(uint32_t &acc, const int *q) {
-        if (CVS422_CU == 4) acc = sat4(q[0], q[1], q[2], q[3 % CVS422_CU]);
-        else if (CVS422_CU == 2) acc = funnel_r(acc, sat_pack2(q[1 % CVS422_CU], q[0], 0u), 16);
+        if (CU == 4) acc = sat4(q[0], q[1 % CU], q[2 % CU], q[3 % CU]);
+        else if (CU == 2) acc = funnel_r(acc, sat_pack2(q[1 % CU], q[0], 0u), 16);
         else acc = funnel_r(acc, (uint32_t)sat1(q[0]), 8);
     }
 
     // y + chroma on the carrier for the 8 pixels of a block (amp == 50), not yet clamped
     static CVS_HD void modulate8(const Row422 &rc, uint32_t y0, uint32_t y1, uint32_t uw, uint32_t vw, int yo[kB]) {
+        const uint32_t t_lo = prmt(uw, vw, rc.selM), t_hi = prmt(uw, vw, rc.selM + 0x2222u);
         CVS_UNROLL
-        for (int j = 0; j < kB; j++) {
-            const int u = byte_of(uw, j >> 1) - 128, v = byte_of(vw, j >> 1) - 128;
-            yo[j] = byte_of(j < 4 ? y0 : y1, j & 3) + u * rc.mU[j & 3] + v * rc.mV[j & 3];
-        }
+        for (int j = 0; j < kB; j++)
+            yo[j] = byte_of(j < 4 ? y0 : y1, j & 3) + (byte_of(j < 4 ? t_lo : t_hi, j & 3) ^ rc.mX[j & 3]) + rc.mC[j & 3];
     }
 
     // G2, first modulation: + luma noise, + head-switch delay
@@ -811,8 +839,7 @@ struct Fast422 {
             CVS_UNROLL
             for (int j = 0; j < kB; j++) {
                 yo[j] = sat1(yo[j]) + ln.nY;
-                const int d = draw_mod(ln.rngL.next_in_group(grp, grp_next, j, kB), (uint32_t)(2 * K.vnoise + 1), K.vmagic, K.vshift);
-                ln.nY = noise_step(ln.nY, d, K.vnoise);
+                ln.nY = cvs::noise_draw(ln.nY, ln.rngL.next_in_group(grp, grp_next, j, kB), (uint32_t)(2 * K.vnoise + 1), K.vmagic, K.vshift, K.vnoise);
             }
         }
         uint32_t w0 = sat4(yo[0], yo[1], yo[2], yo[3]), w1 = sat4(yo[4], yo[5], yo[6], yo[7]);
@@ -950,13 +977,17 @@ struct Fast422 {
                 for (int k = 0; k < kBC; k++) {
                     U[k] = sat1(U[k] + ln.nU);
                     V[k] = sat1(V[k] + ln.nV);
-                    const int du = draw_mod(ln.rngC.next_in_group(grp, grp_next, 2 * k, 2 * kBC), (uint32_t)(2 * K.cnoise + 1), K.cmagic, K.cshift);
-                    ln.nU = noise_step(ln.nU, du, K.cnoise);
-                    const int dv = draw_mod(ln.rngC.next_in_group(grp, grp_next, 2 * k + 1, 2 * kBC), (uint32_t)(2 * K.cnoise + 1), K.cmagic, K.cshift);
-                    ln.nV = noise_step(ln.nV, dv, K.cnoise);
+                    ln.nU = cvs::noise_draw(ln.nU, ln.rngC.next_in_group(grp, grp_next, 2 * k, 2 * kBC), (uint32_t)(2 * K.cnoise + 1), K.cmagic, K.cshift, K.cnoise);
+                    ln.nV = cvs::noise_draw(ln.nV, ln.rngC.next_in_group(grp, grp_next, 2 * k + 1, 2 * kBC), (uint32_t)(2 * K.cnoise + 1), K.cmagic, K.cshift, K.cnoise);
                 }
             }
-            if (K.flags & G_PHASE) {                                           // (:755-783)
+            if ((K.flags & G_PHASE) && rc.pmap) {                              // (:755-783), tabulated
+                CVS_UNROLL
+                for (int k = 0; k < kBC; k++) {
+                    U[k] = rc.pmap[U[k]];
+                    V[k] = rc.pmap[256 + V[k]];
+                }
+            } else if (K.flags & G_PHASE) {
                 CVS_UNROLL
                 for (int k = 0; k < kBC; k++) {
                     const double u = i2d(U[k] - 128), v = i2d(V[k] - 128);
@@ -980,7 +1011,7 @@ struct Fast422 {
     // G3b
     static CVS_HD void stage_chroma_lp(const K422 &K, Lane422 &ln, int b) {
         uint32_t ou, ov;
-        lp_pair<false>(ldw(cblk(ln.ru, b)), ldw(cblk(ln.rv, b)), nullptr, ln.chU, nullptr, ln.chV, K.a_ch, 0.0, K.a_ch, 0.0, ou, ov);
+        lp_pair<false, CVS422_CU_MID>(ldw(cblk(ln.ru, b)), ldw(cblk(ln.rv, b)), nullptr, ln.chU, nullptr, ln.chV, K.a_ch, 0.0, K.a_ch, 0.0, ou, ov);
         put_delayed(ln.ru, b, K.cd, ou, ln.cCh[0]);
         put_delayed(ln.rv, b, K.cd, ov, ln.cCh[1]);
     }
@@ -995,18 +1026,18 @@ struct Fast422 {
         }
         uint32_t ou = 0, ov = 0;
         CVS_ROLLED
-        for (int it = 0; it < kBC / CVS422_CU; it++) {
-            int qu[CVS422_CU], qv[CVS422_CU];
+        for (int it = 0; it < kBC / CVS422_CU_MID; it++) {
+            int qu[CVS422_CU_MID], qv[CVS422_CU_MID];
             CVS_UNROLL
-            for (int j = 0; j < CVS422_CU; j++) {
+            for (int j = 0; j < CVS422_CU_MID; j++) {
                 const double s = fu2d((uint32_t)byte_of(pu, j)), t = fu2d((uint32_t)byte_of(pv, j));
                 const double ts = cascade<3>(ln.csU, s, K.a_csharp), tt = cascade<3>(ln.csV, t, K.a_csharp);
                 qu[j] = fq(dadd(s, dmul(dsub(s, ts), K.sharpen_c)));
                 qv[j] = fq(dadd(t, dmul(dsub(t, tt), K.sharpen_c)));
             }
-            push_c(ou, qu);
-            push_c(ov, qv);
-            if (CVS422_CU < 4) { pu >>= (8 * CVS422_CU) & 31; pv >>= (8 * CVS422_CU) & 31; }
+            push_c<CVS422_CU_MID>(ou, qu);
+            push_c<CVS422_CU_MID>(ov, qv);
+            if (CVS422_CU_MID < 4) { pu >>= (8 * CVS422_CU_MID) & 31; pv >>= (8 * CVS422_CU_MID) & 31; }
         }
         stw(cblk(ln.ru, b), ou);
         stw(cblk(ln.rv, b), ov);
@@ -1054,11 +1085,11 @@ CVS_HD void role2_front(const K422 &K, const Lags &L, const Geo &G, Lane422 &ln,
     pu = pv = 0;
     if (!(K.flags & G_VHS)) return;
     const int bC = s - L.bC, bV = s - L.bV;
-    if (bC >= 0 && bC < G.nb) Pipe422<true>::stage_chroma_lp(K, ln, bC);
-    if (bV >= 0 && bV < G.nb) {
-        Pipe422<true>::stage_luma_sharpen(K, ln, bV);
-        Pipe422<true>::blend_fetch(ln, bV, pu, pv);
+    if (bC >= 0 && bC < G.nb) {
+        Pipe422<true>::stage_chroma_lp(K, ln, bC);
+        Pipe422<true>::stage_luma_sharpen(K, ln, bC);
     }
+    if (bV >= 0 && bV < G.nb) Pipe422<true>::blend_fetch(ln, bV, pu, pv);
 }
 CVS_HD void role2_back(const K422 &K, const Lags &L, const Geo &G, const Row422 &rc, Lane422 &ln, int s, uint32_t pu, uint32_t pv,
                        uint32_t au, uint32_t av) {
@@ -1072,7 +1103,7 @@ CVS_HD bool role3_step(const K422 &K, const Lags &L, const Geo &G, const DivPair
     typedef Pipe422<true> P;
     const int nb = G.nb;
     const bool redemod = (K.flags & G_VHS) && !(K.flags & G_SVIDEO);
-    const int bR = s - L.bV - 1, b2 = s - L.bD2, bE = s - L.bE, bF = s - L.bF;
+    const int bR = s - L.bR, b2 = s - L.bD2, bE = s - L.bE, bF = s - L.bF;
     bs = s - L.bS;
     if (redemod && bR >= 0 && bR < nb) P::template stage_modulate<false>(K, rc, ln, bR, false, nullptr);   // (:927-930)
     if (redemod && b2 >= 0 && b2 < nb) P::stage_redemod(K, rc, ln, ln.dm2, b2, dv.amp_magic, dv.amp_shift);
@@ -1151,10 +1182,9 @@ CVS_HD void frow2_front(const K422 &K, const Lags &L, int nb, Lane422 &ln, int s
             Fast422::carry_leave(ln.ru, bC, K.cd, ln.cCh[0]);
             Fast422::carry_leave(ln.rv, bC, K.cd, ln.cCh[1]);
         }
+        Fast422::stage_luma_sharpen(K, ln, bC);
     }
-    if (!blk_ok(b, nb)) return;
-    Fast422::stage_luma_sharpen(K, ln, b);
-    Pipe422<false>::blend_fetch(ln, b, pu, pv);
+    if (blk_ok(b, nb)) Pipe422<false>::blend_fetch(ln, b, pu, pv);
 }
 CVS_HD void frow2_back(const K422 &K, const Lags &L, int nb, const Row422 &rc, Lane422 &ln, int s, uint32_t pu, uint32_t pv,
                        uint32_t au, uint32_t av) {
@@ -1164,7 +1194,7 @@ CVS_HD void frow2_back(const K422 &K, const Lags &L, int nb, const Row422 &rc, L
 }
 CVS_HD bool frow3_step(const K422 &K, const Lags &L, int nb, const Row422 &rc, Lane422 &ln, int s, StepIO &out, int &bs) {
     if ((K.flags & G_VHS) && !(K.flags & G_SVIDEO)) {
-        const int bR = s - L.bV - 1, b2 = s - L.bD2;
+        const int bR = s - L.bR, b2 = s - L.bD2;
         if (blk_ok(bR, nb)) Fast422::stage_remodulate(rc, ln, bR);
         if (blk_ok(b2, nb)) Fast422::stage_redemod(rc, ln, b2);
     }

@@ -95,6 +95,28 @@ int make_k422(const cvs422_params &p, int w, int h, K422 &K, DivPair &dv, std::v
         lut.push_back(std::cos(pi));
         lut.push_back(std::sin(pi));
     }
+    if (K.pnoise != 0 && K.pnoise <= kPhaseMapMax) {
+        // The rotation's input is an 8-bit sample: tabulate its output byte for every state, U then V, with the
+        // reference's operations in the reference's order (:772-779; this file is compiled with -ffp-contract=off)
+        const size_t nst = (size_t)(2 * K.pnoise + 1);
+        std::vector<uint8_t> maps(nst * 512);
+        for (size_t i = 0; i < nst; i++) {
+            const double c = lut[2 * i], sn = lut[2 * i + 1];
+            for (int b = 0; b < 256; b++) {
+                const double x = (double)(b - 128);
+                const double xc = x * c, xs = x * sn;
+                const double u_ = xc - xs, v_ = xc + xs;
+                const double uo = u_ + 128.0, vo = v_ + 128.0;
+                const int ui = (int)uo, vi = (int)vo;
+                maps[i * 512 + (size_t)b] = (uint8_t)(ui < 0 ? 0 : (ui > 255 ? 255 : ui));
+                maps[i * 512 + 256 + (size_t)b] = (uint8_t)(vi < 0 ? 0 : (vi > 255 ? 255 : vi));
+            }
+        }
+        const size_t nd = lut.size();
+        lut.resize(nd + maps.size() / sizeof(double));
+        std::memcpy(lut.data() + nd, maps.data(), maps.size());
+        K.flags |= G_PHASE_MAP;
+    }
     K.phase_lut = lut.data();
     return CVS_OK;
 }

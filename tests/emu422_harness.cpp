@@ -127,7 +127,10 @@ int emu422_process(const cvs422_params *p, unsigned long long rng_pos,
         // the fast kernel (k_yuv422_fast): one code path per role, no general steps
         if (!(force_general & 1) && fast_row_ok(K) && fs.hs_count == 0) {
             const int nb = GE.nb;
-            for (int lane = 0; lane < 32; lane++) Fast422::prime(K, ln[lane]);
+            for (int lane = 0; lane < 32; lane++) {
+                Fast422::prime(K, ln[lane]);
+                if (K.flags & G_PHASE_MAP) rc[lane].pmap = row_phase_map(K, phase_maps(K), fs.rowinfo[(size_t)rows[lane]]);
+            }
             for (int s = 0; s < nsteps; s++) {
                 for (int ri = 0; ri < kRoles; ri++) {
                     const int role = (force_general & 2) ? ri : kRoles - 1 - ri;
@@ -167,7 +170,7 @@ int emu422_process(const cvs422_params *p, unsigned long long rng_pos,
             }
             continue;
         }
-        // The general kernel (k_yuv422).  The four roles of a row run concurrently on the GPU and meet at a barrier after
+        // The general kernel (k_yuv422).  The roles of a row run concurrently on the GPU and meet at a barrier after
         // every step, so within a step no role may depend on another one: run them in REVERSE order here.
         for (int s = 0; s < nsteps; s++) {
             for (int ri = 0; ri < kRoles; ri++) {
