@@ -1,0 +1,25 @@
+"""Generates tests/golden/swscale_bgra_yuv.npz: outputs of the REAL libswscale (the 9.1.100 build of this image,
+tests/swscale_ref.py) for the reference's encoder-side call -- sws_getContext(w, h, BGRA, w, h, YUV420P | YUV422P,
+SWS_BILINEAR, NULL, NULL, NULL) + sws_scale (ffmpeg_ntsc.cpp:2118-2131, 2266-2274) -- with the library's portable C
+code selected (av_force_cpu_flags(0)).  Run from the repo root:  python tests/golden/make_golden_swscale.py"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+import swscale_ref  # noqa: E402
+
+assert swscale_ref.available(), "no libswscale here"
+out = {}
+rng = np.random.default_rng(20260101)
+for w, h in ((64, 48), (101, 67), (100, 47), (33, 21), (160, 120)):
+    src = rng.integers(0, 1 << 32, size=(h, w), dtype=np.uint32)
+    for fmt in ("yuv420p", "yuv422p"):
+        y, u, v = swscale_ref.scale([src.view(np.uint8).reshape(h, 4 * w)], "bgra", w, h, fmt, w, h, c_code=True)
+        n = "%s_%dx%d" % (fmt, w, h)
+        out[n + "_src"], out[n + "_y"], out[n + "_u"], out[n + "_v"] = src, y, u, v
+out["libswscale_version"] = np.array(swscale_ref.version())
+np.savez_compressed(os.path.join(HERE, "swscale_bgra_yuv.npz"), **out)
+print("wrote", len(out), "arrays, libswscale", swscale_ref.version())

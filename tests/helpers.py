@@ -370,6 +370,16 @@ def oracle_bgra_to_yuv(bgra, v420):
     return y, u, v
 
 
+def oracle_sws_filter(srcn, dstn, one, max_taps=16):
+    """The bilinear filter bank of one axis as libswscale builds it (oracle/convert_oracle.c) -> (pos[dstn], coef[dstn, taps])."""
+    lib = load_convert_oracle()
+    pos = np.zeros(dstn, np.int32)
+    coef = np.zeros(dstn * max_taps, np.int32)
+    n = lib.oracle_sws_bilinear_filter(srcn, dstn, one, _ptr(pos), _ptr(coef), max_taps)
+    assert n > 0, n
+    return pos, coef[:dstn * n].reshape(dstn, n).copy()
+
+
 def oracle_scale_to_bgra(planes, sw, sh, fmt, dw, dh):
     """planes: list of uint8 arrays (BGRA: one [sh, sw*4]); -> uint32[dh, dw]."""
     lib = load_convert_oracle()

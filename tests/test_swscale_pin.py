@@ -1,0 +1,95 @@
+"""The encoder-side picture conversion (ffmpeg_ntsc.cpp:2118-2131, 2266-2274: sws_getContext(.., BGRA -> YUV420P |
+YUV422P, SWS_BILINEAR) + sws_scale) PINNED against libswscale itself.
+
+oracle/convert_oracle.c::oracle_bgra_to_yuv restates what the library's portable C code does for that call; here it
+is compared byte for byte with the library (libswscale 9.1.100 of this image, tests/swscale_ref.py) where that
+exists, and with outputs of the library committed as tests/golden/swscale_bgra_yuv.npz everywhere."""
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+import swscale_ref
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+need_lib = pytest.mark.skipif(not swscale_ref.available(), reason="no libswscale on this machine (golden fixtures cover it)")
+
+SIZES = [(64, 48), (720, 480), (66, 50), (100, 47), (101, 48), (101, 67), (33, 21), (8, 6), (1920, 1080), (719, 575)]
+
+
+def picture(w, h, kind, seed=0):
+    if kind == "random":
+        return np.random.default_rng(seed).integers(0, 1 << 32, size=(h, w), dtype=np.uint32)
+    if kind == "bars":
+        return helpers.stream_frame(w, h, 3).astype(np.uint32)
+    if kind == "extremes":                      # saturated primaries and their complements, two pixels wide
+        cols = np.array([0xFF000000, 0xFFFFFFFF, 0xFFFF0000, 0xFF00FF00, 0xFF0000FF, 0xFFFFFF00, 0xFF00FFFF, 0xFFFF00FF], np.uint32)
+        return np.broadcast_to(np.repeat(cols, 2)[np.arange(w) % 16], (h, w)).copy()
+    raise ValueError(kind)
+
+
+def lib_planes(src, fmt, c_code=True, flags=swscale_ref.SWS_BILINEAR):
+    h, w = src.shape
+    return swscale_ref.scale([src.view(np.uint8).reshape(h, 4 * w)], "bgra", w, h, fmt, w, h, flags=flags, c_code=c_code)
+
+
+@need_lib
+@pytest.mark.parametrize("w,h", SIZES)
+@pytest.mark.parametrize("fmt", ["yuv420p", "yuv422p"])
+def test_oracle_equals_libswscale_c_code(w, h, fmt):
+    for kind in ("random", "bars", "extremes"):
+        src = picture(w, h, kind, seed=w * 31 + h)
+        want = lib_planes(src, fmt)
+        got = helpers.oracle_bgra_to_yuv(src, fmt == "yuv420p")
+        for name, a, b in zip("yuv", got, want):
+            assert np.array_equal(a, b), (kind, name, int(np.abs(a.astype(int) - b.astype(int)).max()))
+
+
+@need_lib
+def test_bitexact_flags_select_the_same_code_with_cpu_extensions_on():
+    """SWS_ACCURATE_RND | SWS_BITEXACT with the CPU's extensions enabled == the C code the oracle is pinned to."""
+    src = picture(720, 480, "random", 5)
+    for fmt in ("yuv420p", "yuv422p"):
+        a = lib_planes(src, fmt, c_code=False,
+                       flags=swscale_ref.SWS_BILINEAR | swscale_ref.SWS_ACCURATE_RND | swscale_ref.SWS_BITEXACT)
+        b = helpers.oracle_bgra_to_yuv(src, fmt == "yuv420p")
+        assert all(np.array_equal(x, y) for x, y in zip(a, b)), fmt
+
+
+@need_lib
+def test_x86_code_of_the_library_stays_within_one_code_of_its_c_code():
+    """What the reference gets on an x86 host with plain SWS_BILINEAR: the library's SIMD vertical scaler rounds
+    differently from its C code -- luma and 4:2:2 identical, 4:2:0 chroma +-1 on a few percent of the samples."""
+    src = picture(720, 480, "random", 6)
+    for fmt in ("yuv420p", "yuv422p"):
+        simd, ccode = lib_planes(src, fmt, c_code=False), lib_planes(src, fmt, c_code=True)
+        assert np.array_equal(simd[0], ccode[0])
+        for a, b in zip(simd[1:], ccode[1:]):
+            d = np.abs(a.astype(int) - b.astype(int))
+            assert d.max() <= 1 and (d > 0).mean() < 0.15
+            if fmt == "yuv422p":
+                assert d.max() == 0
+
+
+def test_oracle_equals_golden_outputs_of_libswscale():
+    g = np.load(os.path.join(HERE, "golden", "swscale_bgra_yuv.npz"))
+    names = sorted({k[:-4] for k in g.files if k.endswith("_src")})
+    assert len(names) >= 8
+    for n in names:
+        src = g[n + "_src"]
+        got = helpers.oracle_bgra_to_yuv(src, "yuv420p" in n)
+        for pl, a in zip("yuv", got):
+            assert np.array_equal(a, g["%s_%s" % (n, pl)]), (n, pl)
+
+
+@pytest.mark.parametrize("srcn,dstn,one", [(480, 240, 4096), (1080, 540, 4096), (67, 34, 4096), (101, 51, 16384), (5, 3, 4096)])
+def test_filter_bank_properties(srcn, dstn, one):
+    """Every row of the bilinear filter bank sums to `one`, taps stay inside the picture, positions are monotonic;
+    an exact 2:1 reduction is 1/8 3/8 3/8 1/8 away from the borders."""
+    pos, coef = helpers.oracle_sws_filter(srcn, dstn, one)
+    assert (coef.sum(axis=1) == one).all()
+    assert pos.min() >= 0 and (pos + coef.shape[1]).max() <= srcn and (np.diff(pos) >= 0).all()
+    if srcn == 2 * dstn:
+        assert coef[dstn // 2].tolist() == [one // 8, 3 * one // 8, 3 * one // 8, one // 8]
+        assert coef[0].tolist()[:3] == [one // 2, 3 * one // 8, one // 8] and pos[0] == 0
