@@ -40,6 +40,7 @@ def load():
         "cvs_set_noise_mode": (C.c_int, [vp, C.c_int]),
         "cvs_bgra_to_yuv_device": (C.c_int, [vp, vp, C.c_int, C.c_longlong, vp, C.c_int, C.c_longlong, vp, C.c_int,
                                              C.c_longlong, vp, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int]),
+        "cvs_sws_bilinear_bank": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int]),
         "cvs_scale_to_bgra_device": (C.c_int, [vp, vp, C.c_int, C.c_longlong, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(C.c_int),
                                                C.POINTER(C.c_longlong), C.c_int, C.c_int, C.c_int, C.c_int]),
         "cvs_field_loop_host": (C.c_int, [vp, vp, C.c_int, C.c_ulonglong]),
@@ -78,7 +79,7 @@ EXPORTED_SYMBOLS = [
     "cvs_abi_version", "cvs_strerror", "cvs_params_default_ntsc", "cvs_params_preset_pal",
     "cvs_params_apply_argv", "cvs_draws_per_field", "cvs_create", "cvs_destroy", "cvs_set_params",
     "cvs_set_precision", "cvs_set_bob", "cvs_set_noise_mode", "cvs_scale_to_bgra_device", "cvs_field_loop_host", "cvs_audio_channels", "cvs_audio_create", "cvs_audio_process",
-    "cvs_audio_destroy", "cvs_bgra_to_yuv_device", "cvs_preferred_batch", "cvs_composite_layer", "cvs_composite_fields_device", "cvs_composite_fields_host",
+    "cvs_audio_destroy", "cvs_bgra_to_yuv_device", "cvs_sws_bilinear_bank", "cvs_preferred_batch", "cvs_composite_layer", "cvs_composite_fields_device", "cvs_composite_fields_host",
     "cvs_composite_fields_host_async",
     "cvs_synchronize", "cvs_alloc_host", "cvs_free_host", "cvs_rng_seek", "cvs_rng_tell", "cvs_kernel_launches", "cvs_kernel_time_reset",
     "cvs_kernel_time_query", "cvs_set_stream",

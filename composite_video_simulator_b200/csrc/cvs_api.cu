@@ -22,6 +22,7 @@
 #include "scanline_kernels.cuh"
 #include "scale_convert.cuh"
 #include "yuv_convert.cuh"
+#include "sws_filter.h"
 
 using namespace cvs;
 
@@ -113,6 +114,13 @@ struct cvs_ctx {
     // cvs_field_loop_host: device buffers of the chain and the ring row that field-0 pictures inherit
     uint8_t *fl_src = nullptr, *fl_scaled = nullptr, *fl_out = nullptr, *fl_yuv = nullptr, *fl_last_row = nullptr;
     size_t fl_src_cap = 0, fl_scaled_cap = 0, fl_out_cap = 0, fl_yuv_cap = 0, fl_last_row_cap = 0;
+    // cvs_bgra_to_yuv_device: the filter banks of a geometry on the device (sws_filter.h), built on first use
+    struct YuvBanks {
+        int w = 0, h = 0, v420 = 0, vtaps = 0, htaps = 0;
+        int32_t *d = nullptr;                      // vpos | vcoef | hpos | hcoef
+        size_t off_vcoef = 0, off_hpos = 0, off_hcoef = 0;
+    };
+    std::vector<YuvBanks> yuv_banks;
 };
 
 namespace {
@@ -133,6 +141,8 @@ int head_switch_rows_bound(int w) {
 
 void free_all(cvs_ctx *c) {
     if (!c) return;
+    for (auto &b : c->yuv_banks) if (b.d) cudaFree(b.d);
+    c->yuv_banks.clear();
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto &pl : c->plans) if (pl && pl->d_seek) cudaFree(pl->d_seek);
@@ -781,20 +791,74 @@ int cvs_bgra_to_yuv_device(cvs_ctx *ctx, void *y, int ly, long long y_pic_stride
     if (stride < 4 * w || (stride & 3) || ((uintptr_t)bgra & 3) || ly < w || lu < cw || lv < cw) return CVS_ERR_INVALID_ARG;
     if (n == 0) return CVS_OK;
     if (cudaSetDevice(ctx->device) != cudaSuccess) return CVS_ERR_CUDA;
+    const bool v420 = format == CVS_YUV420P;
+    const cvs_ctx::YuvBanks *bk = nullptr;
+    for (const auto &b : ctx->yuv_banks) if (b.w == w && b.h == h && b.v420 == (int)v420) { bk = &b; break; }
+    if (!bk) {
+        // the library's filter banks for this geometry: chroma rows (4:2:0: 2:1 bilinear; 4:2:2: the unit filter) and,
+        // for odd widths only, chroma columns
+        const int crows_ = v420 ? (h + 1) / 2 : h;
+        const FilterBank vb = bilinear_bank(h, crows_, 1 << 12);
+        FilterBank hb;
+        if (w & 1) hb = bilinear_bank(w, cw, 1 << 14);
+        auto inside = [](const FilterBank &f, int srcn) {
+            for (int32_t q : f.pos) if (q < 0 || q + f.taps > srcn) return false;
+            return f.taps >= 1 && f.taps <= kYuvMaxTaps;
+        };
+        if (!inside(vb, h) || ((w & 1) && !inside(hb, w))) return CVS_ERR_UNSUPPORTED;
+        cvs_ctx::YuvBanks nb;
+        nb.w = w; nb.h = h; nb.v420 = v420; nb.vtaps = vb.taps; nb.htaps = hb.taps;
+        std::vector<int32_t> blob(vb.pos);
+        nb.off_vcoef = blob.size(); blob.insert(blob.end(), vb.coef.begin(), vb.coef.end());
+        nb.off_hpos = blob.size(); blob.insert(blob.end(), hb.pos.begin(), hb.pos.end());
+        nb.off_hcoef = blob.size(); blob.insert(blob.end(), hb.coef.begin(), hb.coef.end());
+        CVS_CUDA(cudaMalloc((void **)&nb.d, blob.size() * sizeof(int32_t)));
+        // pageable source: the copy has left the host buffer when the call returns
+        if (cudaMemcpyAsync(nb.d, blob.data(), blob.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
+            cudaFree(nb.d);
+            return CVS_ERR_CUDA;
+        }
+        if (ctx->yuv_banks.size() >= 8) {                  // a handful of geometries per context at most
+            CVS_CUDA(cudaStreamSynchronize(ctx->stream));
+            cudaFree(ctx->yuv_banks.front().d);
+            ctx->yuv_banks.erase(ctx->yuv_banks.begin());
+        }
+        ctx->yuv_banks.push_back(nb);
+        bk = &ctx->yuv_banks.back();
+    }
     YuvArgs a;
     a.bgra = (const uint8_t *)bgra; a.y = (uint8_t *)y; a.u = (uint8_t *)u; a.v = (uint8_t *)v;
     a.sp_bgra = bgra_pic_stride; a.sp_y = y_pic_stride; a.sp_u = u_pic_stride; a.sp_v = v_pic_stride;
     a.stride = stride; a.ly = ly; a.lu = lu; a.lv = lv;
-    a.w = w; a.h = h; a.n = n; a.v420 = format == CVS_YUV420P;
+    a.w = w; a.h = h; a.n = n; a.v420 = v420;
+    a.vpos = bk->d; a.vcoef = bk->d + bk->off_vcoef; a.hpos = bk->d + bk->off_hpos; a.hcoef = bk->d + bk->off_hcoef;
+    a.vtaps = bk->vtaps; a.htaps = bk->htaps;
     a.c = yuv_coef_bt601();
-    const int groups = (w + 7) / 8, crows = a.v420 ? (h + 1) / 2 : h;
-    const dim3 block(groups < 256 ? ((groups + 31) / 32) * 32 : 256);
-    const dim3 grid((groups + block.x - 1) / block.x, crows, n);
+    const int crows = v420 ? (h + 1) / 2 : h;
     if (crows > 65535 || n > 65535) return CVS_ERR_CAPACITY;
-    k_bgra_to_yuv<<<grid, block, 0, ctx->stream>>>(a);
+    if (w & 1) {
+        const dim3 block(cw < 256 ? ((cw + 31) / 32) * 32 : 256);
+        const dim3 grid((cw + block.x - 1) / block.x, crows, n);
+        k_bgra_to_yuv_oddw<<<grid, block, 0, ctx->stream>>>(a);
+    } else {
+        const int groups = (w + 7) / 8;
+        const dim3 block(groups < 256 ? ((groups + 31) / 32) * 32 : 256);
+        const dim3 grid((groups + block.x - 1) / block.x, crows, n);
+        k_bgra_to_yuv<<<grid, block, 0, ctx->stream>>>(a);
+    }
     CVS_CUDA(cudaGetLastError());
     ctx->launches++;
     return CVS_OK;
+}
+
+// The filter bank of one axis as the conversions use it (for tests and for hosts that want to see the taps).
+int cvs_sws_bilinear_bank(int srcn, int dstn, int one, int32_t *pos, int32_t *coef, int max_taps) {
+    if (srcn <= 0 || dstn <= 0 || one <= 0 || !pos || !coef) return CVS_ERR_INVALID_ARG;
+    const FilterBank f = bilinear_bank(srcn, dstn, one);
+    if (f.taps > max_taps) return CVS_ERR_CAPACITY;
+    std::copy(f.pos.begin(), f.pos.end(), pos);
+    std::copy(f.coef.begin(), f.coef.end(), coef);
+    return f.taps;
 }
 
 int cvs_scale_to_bgra_device(cvs_ctx *ctx, void *dst, int dst_stride, long long dst_pic_stride, int dw, int dh,

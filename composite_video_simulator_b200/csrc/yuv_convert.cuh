@@ -1,15 +1,22 @@
-// yuv_convert.cuh -- BGRA -> planar YUV 4:2:0 / 4:2:2 (BT.601, limited range) on the device.
+// yuv_convert.cuh -- BGRA -> planar YUV 4:2:0 / 4:2:2 on the device, bit for bit what libswscale's C code produces.
 //
 // The step after the field loop of ffmpeg_ntsc: the BGRA picture goes through sws_scale() to the encoder's pixel
-// format (ffmpeg_ntsc.cpp:2266-2274; context created at :2118-2131 with SWS_BILINEAR, frame tagged SMPTE170M /
-// MPEG range at :2100-2101).  SURVEY section 8f-1.  libswscale is a third-party dependency that is absent here (no
-// FFmpeg in this environment), so this is NOT pinned against the reference: the arithmetic below is the
-// published 15-bit fixed-point form of the BT.601 limited-range matrix that swscale's C path uses for RGB input
-// (coefficients c * 219/255 * 2^15 for luma and c * 224/255 * 2^15 for chroma, rounded to nearest), with
-// the chroma sample taken from the mean of the 2x1 (4:2:2) or 2x2 (4:2:0) pixels it covers, rounded to nearest.
-// swscale's bilinear chroma scaler and its chroma siting are not reproduced.  oracle/convert_oracle.c restates the
-// conversion independently of this file; tests/test_gpu_yuv_convert.py compares the two bit for bit and checks
-// both within +-1 of the real-valued BT.601 conversion.
+// format (ffmpeg_ntsc.cpp:2266-2274; context created at :2118-2131 with SWS_BILINEAR, same size both sides; frame
+// tagged SMPTE170M / MPEG range at :2100-2101).  SURVEY section 8f-1.
+//
+// PINNED: oracle/convert_oracle.c restates what the library does for that call and is compared byte for byte with
+// libswscale 9.1.100 itself (tests/test_swscale_pin.py, library C code = SWS_ACCURATE_RND | SWS_BITEXACT); the kernels
+// below are compared with the oracle, with the library (where the GPU box has it) and with its committed outputs
+// (tests/test_gpu_yuv_convert.py).  The arithmetic, all integer:
+//   luma    y14 = (RY r + GY g + BY b + (16 << 15) + 256) >> 9;   s15 = min(2 y14, 32767);   Y = clip8((s15 + 64) >> 7)
+//   chroma  even width: c14 = (RU (r0 + r1) + GU (g0 + g1) + BU (b0 + b1) + (256 << 15) + 512) >> 10 from the two pixels
+//                       of a chroma sample;  s15 = min(2 c14, 32767)
+//           odd width:  c14 = (RU r + GU g + BU b + (256 << 14) + 256) >> 9 per PIXEL, then the library's horizontal
+//                       bilinear bank (14-bit weights, sws_filter.cpp):  s15 = min((sum c14 w) >> 13, 32767)
+//           4:2:2:      C = clip8((s15 + 64) >> 7)
+//           4:2:0:      the vertical bank over 2:1 (12-bit weights: 512 1536 1536 512 on rows 2cy-1 .. 2cy+2, folded at
+//                       the picture's edges):  C = clip8(((64 << 12) + sum s15 w) >> 19)
+//   matrix  R/G/B -> Y: (int)(c 219/255 2^15 + .5), -> U/V: c 224/255, negative ones negated after rounding (BT.601).
 #ifndef CVS_YUV_CONVERT_CUH
 #define CVS_YUV_CONVERT_CUH
 
@@ -19,15 +26,14 @@
 namespace cvs {
 
 constexpr int kYuvShift = 15;
+constexpr int kYuvMaxTaps = 8;
 struct YuvCoef { int ry, gy, by, ru, gu, bu, rv, gv, bv; };
 inline YuvCoef yuv_coef_bt601() {
     YuvCoef c;
-    // rounded to NEAREST, also the negative ones (so that the U and V rows each sum to zero: grey stays 128)
-    auto q = [](double v) { const double t = v * (double)(1 << kYuvShift); return (int)(t < 0 ? -(long long)(-t + 0.5) : (long long)(t + 0.5)); };
-    const double ys = 219.0 / 255.0, cs = 224.0 / 255.0;
-    c.ry = q(0.299 * ys); c.gy = q(0.587 * ys); c.by = q(0.114 * ys);
-    c.ru = q(-0.169 * cs); c.gu = q(-0.331 * cs); c.bu = q(0.500 * cs);
-    c.rv = q(0.500 * cs); c.gv = q(-0.419 * cs); c.bv = q(-0.081 * cs);
+    auto q = [](double v) { return (int)(v * (double)(1 << kYuvShift) + 0.5); };
+    c.ry = q(0.299 * 219 / 255); c.gy = q(0.587 * 219 / 255); c.by = q(0.114 * 219 / 255);
+    c.ru = -q(0.169 * 224 / 255); c.gu = -q(0.331 * 224 / 255); c.bu = q(0.500 * 224 / 255);
+    c.rv = q(0.500 * 224 / 255); c.gv = -q(0.419 * 224 / 255); c.bv = -q(0.081 * 224 / 255);
     return c;
 }
 
@@ -36,67 +42,130 @@ struct YuvArgs {
     long long sp_bgra, sp_y, sp_u, sp_v;     // picture strides (bytes) of a batch
     int stride, ly, lu, lv;                  // row strides (bytes)
     int w, h, n, v420;                       // v420: chroma is subsampled vertically too
+    const int32_t *vpos, *vcoef;             // vertical chroma bank: crows x vtaps
+    const int32_t *hpos, *hcoef;             // horizontal chroma bank of odd widths: cw x htaps
+    int vtaps, htaps;
     YuvCoef c;
 };
 
-// one thread = 8 pixels x (2 rows for 4:2:0 / 1 row for 4:2:2): 32-byte loads, 8-byte luma stores, 4-byte chroma stores
+__device__ __forceinline__ int yuv_clip8(int v) { return min(max(v, 0), 255); }
+__device__ __forceinline__ int yuv_luma(const YuvCoef &c, uint32_t px) {
+    const int b = px & 0xFF, g = (px >> 8) & 0xFF, r = (px >> 16) & 0xFF;
+    const int y14 = (c.ry * r + c.gy * g + c.by * b + (16 << kYuvShift) + 256) >> 9;
+    return yuv_clip8((min(2 * y14, 32767) + 64) >> 7);
+}
+
+// Even widths.  One thread = 8 pixels x one chroma row: the rows its vertical taps cover (4 of them for 4:2:0, of
+// which two are also its luma rows; 1 for 4:2:2) as 32-byte loads, 8-byte luma stores, 4-byte chroma stores.
+// Neighbouring chroma rows share source rows; the second read comes from L2.
 __global__ void __launch_bounds__(256) k_bgra_to_yuv(const __grid_constant__ YuvArgs a) {
     const int gx = blockIdx.x * blockDim.x + threadIdx.x;          // group of 8 pixels
-    const int ry = blockIdx.y;                                     // chroma row
+    const int cy = blockIdx.y;                                     // chroma row
     const int k = blockIdx.z;
     const int x0 = gx * 8;
     if (x0 >= a.w) return;
-    const int rows = a.v420 ? 2 : 1;
-    const int y0 = ry * rows;
+    const int l0 = a.v420 ? 2 * cy : cy, l1 = a.v420 ? min(2 * cy + 1, a.h - 1) : cy;      // luma rows of this thread
+    const int p = a.vpos[cy], nt = a.vtaps;
+    const int32_t *vc = a.vcoef + (size_t)cy * nt;
     const uint8_t *src = a.bgra + (long long)k * a.sp_bgra;
-    int sr[4] = {0, 0, 0, 0}, sg[4] = {0, 0, 0, 0}, sb[4] = {0, 0, 0, 0};
     const bool full = x0 + 8 <= a.w;
-    for (int r = 0; r < rows; r++) {
-        const int yy = y0 + r < a.h ? y0 + r : a.h - 1;            // (odd heights: the last row stands for the missing one)
-        const uint32_t *row = reinterpret_cast<const uint32_t *>(src + (long long)yy * a.stride);
+    int au[4], av[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) au[j] = av[j] = nt > 1 ? (64 << 12) : 64;
+    const int lo = min(p, l0), hi = max(p + nt - 1, l1);
+    for (int r = lo; r <= hi; r++) {
+        const int t = r - p;
+        const int wgt = (t >= 0 && t < nt) ? vc[t] : 0;
+        const bool luma = r == l0 || r == l1;
+        if (wgt == 0 && !luma) continue;
+        const uint32_t *row = reinterpret_cast<const uint32_t *>(src + (long long)r * a.stride);
         uint32_t px[8];
         if (full && ((reinterpret_cast<uintptr_t>(row + x0) & 15) == 0)) {
             const uint4 p0 = *reinterpret_cast<const uint4 *>(row + x0), p1 = *reinterpret_cast<const uint4 *>(row + x0 + 4);
             px[0] = p0.x; px[1] = p0.y; px[2] = p0.z; px[3] = p0.w; px[4] = p1.x; px[5] = p1.y; px[6] = p1.z; px[7] = p1.w;
         } else {
 #pragma unroll
-            for (int i = 0; i < 8; i++) px[i] = row[x0 + i < a.w ? x0 + i : a.w - 1];
+            for (int i = 0; i < 8; i++) px[i] = x0 + i < a.w ? row[x0 + i] : 0u;
         }
-        uint32_t yw[2] = {0, 0};
+        if (luma) {
+            uint32_t yw[2] = {0, 0};
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const int b = px[i] & 0xFF, g = (px[i] >> 8) & 0xFF, rr = (px[i] >> 16) & 0xFF;
-            const int yv = (a.c.ry * rr + a.c.gy * g + a.c.by * b + (16 << kYuvShift) + (1 << (kYuvShift - 1))) >> kYuvShift;
-            yw[i >> 2] |= (uint32_t)yv << (8 * (i & 3));
-            sr[i >> 1] += rr; sg[i >> 1] += g; sb[i >> 1] += b;
-        }
-        if (y0 + r < a.h) {
-            uint8_t *yd = a.y + (long long)k * a.sp_y + (long long)(y0 + r) * a.ly + x0;
+            for (int i = 0; i < 8; i++) yw[i >> 2] |= (uint32_t)yuv_luma(a.c, px[i]) << (8 * (i & 3));
+            uint8_t *yd = a.y + (long long)k * a.sp_y + (long long)r * a.ly + x0;
             if (full && ((reinterpret_cast<uintptr_t>(yd) & 7) == 0)) *reinterpret_cast<uint2 *>(yd) = make_uint2(yw[0], yw[1]);
             else
                 for (int i = 0; i < 8 && x0 + i < a.w; i++) yd[i] = (uint8_t)(yw[i >> 2] >> (8 * (i & 3)));
         }
+        if (wgt != 0) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t q0 = px[2 * j], q1 = px[2 * j + 1];
+                const int sb = (q0 & 0xFF) + (q1 & 0xFF), sg = ((q0 >> 8) & 0xFF) + ((q1 >> 8) & 0xFF), sr = ((q0 >> 16) & 0xFF) + ((q1 >> 16) & 0xFF);
+                const int u14 = (a.c.ru * sr + a.c.gu * sg + a.c.bu * sb + (256 << kYuvShift) + 512) >> 10;
+                const int v14 = (a.c.rv * sr + a.c.gv * sg + a.c.bv * sb + (256 << kYuvShift) + 512) >> 10;
+                const int u15 = min(2 * u14, 32767), v15 = min(2 * v14, 32767);
+                if (nt > 1) { au[j] += u15 * wgt; av[j] += v15 * wgt; }
+                else { au[j] += u15; av[j] += v15; }
+            }
+        }
     }
-    // chroma: mean of the 2 x rows covered pixels, rounded to nearest
-    const int sh = kYuvShift + (a.v420 ? 2 : 1);
-    const int nsum = a.v420 ? 4 : 2;
+    const int sh = nt > 1 ? 19 : 7;
     uint32_t uw = 0, vw = 0;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        const int uu = (a.c.ru * sr[j] + a.c.gu * sg[j] + a.c.bu * sb[j] + ((128 * nsum) << kYuvShift) + (1 << (sh - 1))) >> sh;
-        const int vv = (a.c.rv * sr[j] + a.c.gv * sg[j] + a.c.bv * sb[j] + ((128 * nsum) << kYuvShift) + (1 << (sh - 1))) >> sh;
-        uw |= (uint32_t)uu << (8 * j);
-        vw |= (uint32_t)vv << (8 * j);
+        uw |= (uint32_t)yuv_clip8(au[j] >> sh) << (8 * j);
+        vw |= (uint32_t)yuv_clip8(av[j] >> sh) << (8 * j);
     }
-    const int cw = (a.w + 1) / 2, cx0 = gx * 4;
-    uint8_t *ud = a.u + (long long)k * a.sp_u + (long long)ry * a.lu + cx0;
-    uint8_t *vd = a.v + (long long)k * a.sp_v + (long long)ry * a.lv + cx0;
+    const int cw = a.w / 2, cx0 = gx * 4;
+    uint8_t *ud = a.u + (long long)k * a.sp_u + (long long)cy * a.lu + cx0;
+    uint8_t *vd = a.v + (long long)k * a.sp_v + (long long)cy * a.lv + cx0;
     if (cx0 + 4 <= cw && ((reinterpret_cast<uintptr_t>(ud) & 3) == 0) && ((reinterpret_cast<uintptr_t>(vd) & 3) == 0)) {
         *reinterpret_cast<uint32_t *>(ud) = uw;
         *reinterpret_cast<uint32_t *>(vd) = vw;
     } else {
         for (int j = 0; j < 4 && cx0 + j < cw; j++) { ud[j] = (uint8_t)(uw >> (8 * j)); vd[j] = (uint8_t)(vw >> (8 * j)); }
     }
+}
+
+// Odd widths: the library keeps chroma at full width on the source side and resamples it horizontally, so every
+// chroma sample is a small 2-D filter.  One thread = one chroma sample and the luma pixels under it.  (Encoders do
+// not take odd widths; this path exists so that every size the library accepts gives the library's bytes.)
+__global__ void __launch_bounds__(256) k_bgra_to_yuv_oddw(const __grid_constant__ YuvArgs a) {
+    const int cx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int cy = blockIdx.y;
+    const int k = blockIdx.z;
+    const int cw = (a.w + 1) / 2;
+    if (cx >= cw) return;
+    const uint8_t *src = a.bgra + (long long)k * a.sp_bgra;
+    const int l0 = a.v420 ? 2 * cy : cy, l1 = a.v420 ? min(2 * cy + 1, a.h - 1) : cy;
+    for (int r = l0; r <= l1; r++) {
+        const uint32_t *row = reinterpret_cast<const uint32_t *>(src + (long long)r * a.stride);
+        uint8_t *yd = a.y + (long long)k * a.sp_y + (long long)r * a.ly;
+        for (int x = 2 * cx; x < min(2 * cx + 2, a.w); x++) yd[x] = (uint8_t)yuv_luma(a.c, row[x]);
+    }
+    const int p = a.vpos[cy], nt = a.vtaps, hp = a.hpos[cx], ht = a.htaps;
+    const int32_t *vc = a.vcoef + (size_t)cy * nt, *hc = a.hcoef + (size_t)cx * ht;
+    int au = nt > 1 ? (64 << 12) : 64, av = au;
+    for (int t = 0; t < nt; t++) {
+        const int wgt = vc[t];
+        if (wgt == 0) continue;
+        const uint32_t *row = reinterpret_cast<const uint32_t *>(src + (long long)(p + t) * a.stride);
+        int su = 0, sv = 0;
+        for (int j = 0; j < ht; j++) {
+            const int hw = hc[j];
+            if (hw == 0) continue;
+            const uint32_t px = row[hp + j];
+            const int b = px & 0xFF, g = (px >> 8) & 0xFF, r = (px >> 16) & 0xFF;
+            su += ((a.c.ru * r + a.c.gu * g + a.c.bu * b + (256 << (kYuvShift - 1)) + 256) >> 9) * hw;
+            sv += ((a.c.rv * r + a.c.gv * g + a.c.bv * b + (256 << (kYuvShift - 1)) + 256) >> 9) * hw;
+        }
+        const int u15 = min(su >> 13, 32767), v15 = min(sv >> 13, 32767);
+        if (nt > 1) { au += u15 * wgt; av += v15 * wgt; }
+        else { au += u15; av += v15; }
+    }
+    const int sh = nt > 1 ? 19 : 7;
+    a.u[(long long)k * a.sp_u + (long long)cy * a.lu + cx] = (uint8_t)yuv_clip8(au >> sh);
+    a.v[(long long)k * a.sp_v + (long long)cy * a.lv + cx] = (uint8_t)yuv_clip8(av >> sh);
 }
 
 }  // namespace cvs

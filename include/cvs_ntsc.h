@@ -155,13 +155,23 @@ int  cvs_set_noise_mode(cvs_ctx *ctx, int mode);
  * MPEG range, :2100-2101) before encoding.  This entry point does that conversion on the device, for n pictures,
  * asynchronously on the context's stream: y is w x h, u and v are ceil(w/2) x ceil(h/2) (CVS_YUV420P) or
  * ceil(w/2) x h (CVS_YUV422P); *_pic_stride are the byte distances between consecutive pictures of a plane.
- * NOT pinned against libswscale (absent here): the arithmetic is the published 15-bit fixed-point BT.601
- * limited-range matrix, chroma = rounded mean of the covered pixels (csrc/yuv_convert.cuh says exactly what).
+ * PINNED against libswscale: the bytes are those of the library's own C code (= SWS_ACCURATE_RND | SWS_BITEXACT) for
+ * sws_getContext(w, h, BGRA, w, h, YUV420P | YUV422P, SWS_BILINEAR, ...), including its chroma treatment (even widths:
+ * chroma from the sum of the two pixels under a sample; 4:2:0: a 1-3-3-1 filter over the rows 2cy-1 .. 2cy+2, folded
+ * at the edges; odd widths: full-width chroma through the library's horizontal bilinear bank) and its rounding
+ * (csrc/yuv_convert.cuh states the arithmetic; checked against libswscale 9.1.100, tests/test_swscale_pin.py).  The
+ * library's x86 SIMD code, which a plain SWS_BILINEAR context uses on x86 hosts, differs from its C code by +-1 on a few
+ * percent of the 4:2:0 chroma samples and nowhere else.  CVS_ERR_UNSUPPORTED for pictures too small for the library's
+ * filter (fewer than 3 rows / columns on a resampled axis).
  */
 enum { CVS_YUV420P = 0, CVS_YUV422P = 1 };
 int  cvs_bgra_to_yuv_device(cvs_ctx *ctx, void *y, int ly, long long y_pic_stride, void *u, int lu, long long u_pic_stride,
                             void *v, int lv, long long v_pic_stride, const void *bgra, int stride,
                             long long bgra_pic_stride, int w, int h, int n, int format);
+/* The integer filter bank libswscale builds for one bilinear-resampled axis with centred sampling (srcn -> dstn samples;
+ * one = 1 << 12 for rows, 1 << 14 for columns), as cvs_bgra_to_yuv_device applies it: pos[dstn] = first source sample,
+ * coef[dstn * taps], every row summing to `one`.  Returns taps (<= max_taps) or a negative status.  Host only. */
+int  cvs_sws_bilinear_bank(int srcn, int dstn, int one, int32_t *pos, int32_t *coef, int max_taps);
 
 /* ---- the whole field loop around the seam, host pictures in, host pictures out ----------
  * What ffmpeg_ntsc's main loop does per output field (ffmpeg_ntsc.cpp:2190-2282), with only the decoder's pictures
@@ -177,8 +187,8 @@ int  cvs_bgra_to_yuv_device(cvs_ctx *ctx, void *y, int ly, long long y_pic_strid
  *   y, u, v         n output pictures in HOST memory, w x h luma, chroma per out_format (CVS_YUV420P / CVS_YUV422P)
  * The line doubling leaves row h-1 of an even-height picture of field 0 as the frame ring had it (:2247): the context
  * keeps that row from call to call (the default ring of one picture, `-d 1`), starting from the zeroed ring (:2069-2092).
- * Conversions as specified at cvs_scale_to_bgra_device / cvs_bgra_to_yuv_device (not pinned against libswscale); the
- * composite_layer() step is the pinned hot path.  Synchronous; the rand() position advances as for n
+ * Conversions as specified at cvs_scale_to_bgra_device (not pinned against libswscale) and cvs_bgra_to_yuv_device
+ * (pinned); the composite_layer() step is the pinned hot path.  Synchronous; the rand() position advances as for n
  * cvs_composite_layer() calls.
  */
 typedef struct cvs_field_loop {

@@ -93,3 +93,23 @@ def test_filter_bank_properties(srcn, dstn, one):
     if srcn == 2 * dstn:
         assert coef[dstn // 2].tolist() == [one // 8, 3 * one // 8, 3 * one // 8, one // 8]
         assert coef[0].tolist()[:3] == [one // 2, 3 * one // 8, one // 8] and pos[0] == 0
+
+
+def test_product_filter_bank_equals_the_oracles():
+    """The table builder of the product (csrc/sws_filter.cpp, through the C ABI; no GPU involved) against the oracle's
+    restatement, which is pinned above: every geometry a conversion can ask for in a sweep of sizes."""
+    import ctypes as C
+    from composite_video_simulator_b200 import _lib
+    lib = _lib.load()
+    cases = [(h, (h + 1) // 2, 1 << 12) for h in list(range(3, 80)) + [240, 480, 486, 575, 576, 720, 1080, 1081, 2160]]
+    cases += [(w, (w + 1) // 2, 1 << 14) for w in list(range(3, 80, 2)) + [719, 721, 1919, 3839]]
+    cases += [(h, h, 1 << 12) for h in (1, 2, 5, 480)]
+    for srcn, dstn, one in cases:
+        pos = np.zeros(dstn, np.int32)
+        coef = np.zeros(dstn * 16, np.int32)
+        taps = lib.cvs_sws_bilinear_bank(srcn, dstn, one, pos.ctypes.data_as(C.POINTER(C.c_int32)),
+                                         coef.ctypes.data_as(C.POINTER(C.c_int32)), 16)
+        assert taps > 0, (srcn, dstn, taps)
+        opos, ocoef = helpers.oracle_sws_filter(srcn, dstn, one)
+        assert taps == ocoef.shape[1], (srcn, dstn, taps, ocoef.shape)
+        assert np.array_equal(pos, opos) and np.array_equal(coef[:dstn * taps].reshape(dstn, taps), ocoef), (srcn, dstn)
