@@ -71,12 +71,127 @@ static int plane_sample(const uint8_t *plane, int linesize, int pw, int ph, int 
     return clamp8((int)(acc >> 21));
 }
 
+typedef struct { int size; int *pos; int *coef; } swsfilter;      /* coef[i * size + j] applies to sample pos[i] + j */
+static int sws_bilinear_filter(swsfilter *f, int srcn, int dstn, int one, int srcpos, int dstpos);
+static void swsfilter_free(swsfilter *f);
+
+/* ---- planar YUV -> BGRA at another size: libswscale's C path, restated ------------------------------------------------
+ *
+ * PINNED against libswscale 9.1.100 (tests/test_swscale_pin.py: sws_getContext(sw, sh, YUV420P | YUV422P | NV12, dw, dh,
+ * BGRA, SWS_BILINEAR, NULL, NULL, NULL) + sws_scale(), the reference's call at ffmpeg_ntsc.cpp:574-585, 603-610, library
+ * C code) for EVEN destination widths.  What the library does (its function names, for orientation):
+ *   horizontal  swscale.c hScale8To15_c: every source row of Y to dw samples, of U and V to ceil(dw/2) samples -- the
+ *               library keeps ONE chroma sample per pair of output pixels -- with the bilinear banks of utils.c
+ *               initFilter (14-bit weights), s15 = min(sum >> 7, 32767);
+ *   vertical    banks with 12-bit weights, luma sh -> dh, chroma rows -> dh; vscale.c packed_vscale picks the output
+ *               routine by the banks' tap counts:
+ *                 1 luma tap, 1 chroma tap   (s + 64) >> 7 for Y, U, V                              (output.c yuv2rgb_1_c_template)
+ *                 1 luma tap, 2 chroma taps  Y as above; C = (c0 (4096 - a) + c1 a + (128 << 11)) >> 19     (same, a = 2nd weight)
+ *                 2 and 2                    (s0 (4096 - a) + s1 a) >> 19, no rounding term               (yuv2rgb_2_c_template)
+ *                 anything else              ((1 << 18) + sum s_j w_j) >> 19                              (yuv2rgb_X_c_template)
+ *   colour      yuv2rgb.c ff_yuv2rgb_c_init_tables (ITU-R 601, MPEG range in): with cy = 65536 * 255 / 219 and
+ *               c' = (c * 65536 + 32768) / cy for c = 104597 (V->R), 132201 (U->B), -25675 (U->G), -53279 (V->G),
+ *               channel = clip8((k cy - (384 << 16) - (16 << 16) + 326 cy + 32768) >> 16) at
+ *               k = Y + (c' C >> 16) - (c' >> 9) (both chroma terms for G), C clipped to 0..255; alpha = 255.
+ *   exception   YUV420P at the SAME size with an even height takes the library's direct converter (yuv2rgb.c
+ *               yuv2rgb_c_32): no filtering at all, the chroma sample of a 2x2 block serves its four pixels.
+ * Odd destination widths make the library switch to its full-chroma-interpolation routines and BGRA sources go through
+ * an RGB -> YUV -> RGB round trip inside the library; neither is restated: those cases use this repository's own
+ * resampler below (NOT pinned, stated in include/cvs_ntsc.h).
+ */
+static int sws_rgb_k(long long k) {
+    const long long cy = (65536LL * 255) / 219;
+    long long v = (k * cy - (384LL << 16) - (16LL << 16) + 326 * cy + 32768) >> 16;
+    return clamp8((int)v);
+}
+static uint32_t sws_pixel(int Y, int U, int V) {
+    const long long cy = (65536LL * 255) / 219;
+    const long long crv = (104597LL * 65536 + 32768) / cy, cbu = (132201LL * 65536 + 32768) / cy;
+    const long long cgu = -((25675LL * 65536 - 32768) / cy), cgv = -((53279LL * 65536 - 32768) / cy);   /* C division of a negative numerator */
+    U = clamp8(U); V = clamp8(V);
+    const int r = sws_rgb_k(Y + ((crv * V) >> 16) - (crv >> 9));
+    const int b = sws_rgb_k(Y + ((cbu * U) >> 16) - (cbu >> 9));
+    const int g = sws_rgb_k(Y + ((cgu * U) >> 16) - (cgu >> 9) + ((cgv * V) >> 16) - (cgv >> 9));
+    return 0xFF000000u | ((uint32_t)r << 16) | ((uint32_t)g << 8) | (uint32_t)b;
+}
+/* all rows of one plane scaled horizontally to 15 bits; `step` bytes between the samples of a source row */
+static int *sws_hscale(const uint8_t *plane, int linesize, int step, int rows, const swsfilter *f, int dstn) {
+    int *out = (int *)malloc(sizeof(int) * (size_t)rows * (size_t)dstn);
+    for (int y = 0; y < rows; y++)
+        for (int x = 0; x < dstn; x++) {
+            long long v = 0;
+            for (int j = 0; j < f->size; j++)
+                v += (long long)plane[(size_t)y * (size_t)linesize + (size_t)(f->pos[x] + j) * (size_t)step] * f->coef[(size_t)x * f->size + j];
+            v >>= 7;
+            out[(size_t)y * dstn + x] = (int)(v < 32767 ? v : 32767);
+        }
+    return out;
+}
+static int sws_yuv_to_bgra(uint8_t *dst, int dst_stride, int dw, int dh, const uint8_t *p0, const uint8_t *p1, const uint8_t *p2,
+                           int l0, int l1, int l2, int sw, int sh, int format) {
+    const int cw = (sw + 1) / 2, ch = (format == 2) ? sh : (sh + 1) / 2, cdw = (dw + 1) / 2;
+    const uint8_t *pu = p1, *pv = (format == 3) ? p1 + 1 : p2;
+    const int lu = l1, lv = (format == 3) ? l1 : l2, cstep = (format == 3) ? 2 : 1;
+    if (format == 1 && sw == dw && sh == dh && (dh & 1) == 0) {            /* the direct converter */
+        for (int y = 0; y < dh; y++)
+            for (int x = 0; x < dw; x++)
+                ((uint32_t *)(dst + (size_t)y * (size_t)dst_stride))[x] =
+                    sws_pixel(p0[(size_t)y * l0 + x], pu[(size_t)(y / 2) * lu + x / 2], pv[(size_t)(y / 2) * lv + x / 2]);
+        return 0;
+    }
+    swsfilter hl, hc, vl, vc;
+    sws_bilinear_filter(&hl, sw, dw, 1 << 14, 128, 128);
+    sws_bilinear_filter(&hc, cw, cdw, 1 << 14, 128, 128);
+    sws_bilinear_filter(&vl, sh, dh, 1 << 12, 128, 128);
+    sws_bilinear_filter(&vc, ch, dh, 1 << 12, 128, 128);
+    int *L = sws_hscale(p0, l0, 1, sh, &hl, dw), *CU = sws_hscale(pu, lu, cstep, ch, &hc, cdw), *CV = sws_hscale(pv, lv, cstep, ch, &hc, cdw);
+    for (int y = 0; y < dh; y++) {
+        const int *lw = vl.coef + (size_t)y * vl.size, *cwt = vc.coef + (size_t)y * vc.size;
+        const int *l_ = L + (size_t)vl.pos[y] * dw, *u_ = CU + (size_t)vc.pos[y] * cdw, *v_ = CV + (size_t)vc.pos[y] * cdw;
+        const int two_c = vc.size == 2 && cwt[0] + cwt[1] == 4096 && cwt[1] >= 0 && cwt[1] <= 4096;
+        const int two_l = vl.size == 2 && lw[0] + lw[1] == 4096 && lw[1] >= 0 && lw[1] <= 4096;
+        int mode;
+        if (vl.size == 1 && vc.size == 1) mode = 0;
+        else if (vl.size == 1 && two_c) mode = 1;
+        else if (two_l && two_c) mode = 2;
+        else mode = 3;
+        uint32_t *row = (uint32_t *)(dst + (size_t)y * (size_t)dst_stride);
+        for (int x = 0; x < dw; x++) {
+            const int i = x >> 1;
+            int Y, U, V;
+            if (mode == 0) {
+                Y = (l_[x] + 64) >> 7; U = (u_[i] + 64) >> 7; V = (v_[i] + 64) >> 7;
+            } else if (mode == 1) {
+                const int a = cwt[1];
+                Y = (l_[x] + 64) >> 7;
+                U = (u_[i] * (4096 - a) + u_[cdw + i] * a + (128 << 11)) >> 19;
+                V = (v_[i] * (4096 - a) + v_[cdw + i] * a + (128 << 11)) >> 19;
+            } else if (mode == 2) {
+                const int a = lw[1], c = cwt[1];
+                Y = (l_[x] * (4096 - a) + l_[dw + x] * a) >> 19;
+                U = (u_[i] * (4096 - c) + u_[cdw + i] * c) >> 19;
+                V = (v_[i] * (4096 - c) + v_[cdw + i] * c) >> 19;
+            } else {
+                Y = U = V = 1 << 18;
+                for (int j = 0; j < vl.size; j++) Y += l_[(size_t)j * dw + x] * lw[j];
+                for (int j = 0; j < vc.size; j++) { U += u_[(size_t)j * cdw + i] * cwt[j]; V += v_[(size_t)j * cdw + i] * cwt[j]; }
+                Y >>= 19; U >>= 19; V >>= 19;
+            }
+            row[x] = sws_pixel(Y, U, V);
+        }
+    }
+    free(L); free(CU); free(CV);
+    swsfilter_free(&hl); swsfilter_free(&hc); swsfilter_free(&vl); swsfilter_free(&vc);
+    return 0;
+}
+
 /* format: 0 BGRA, 1 YUV420P, 2 YUV422P, 3 NV12 (the product's enum); dst: BGRA */
 int oracle_scale_to_bgra(uint8_t *dst, int dst_stride, int dw, int dh,
                          const uint8_t *p0, const uint8_t *p1, const uint8_t *p2, int l0, int l1, int l2,
                          int sw, int sh, int format) {
     if (!dst || !p0 || dw <= 0 || dh <= 0 || sw <= 0 || sh <= 0 || format < 0 || format > 3) return -1;
     if (sw > 16 * dw || sh > 16 * dh) return -5;          /* more taps than the tables hold */
+    if (format != 0 && (dw & 1) == 0) return sws_yuv_to_bgra(dst, dst_stride, dw, dh, p0, p1, p2, l0, l1, l2, sw, sh, format);
     const int cw = (sw + 1) / 2, ch = (format == 2) ? sh : (sh + 1) / 2;
     const int suby = (format == 2) ? 1 : 2, offy = (format == 2) ? 0 : 1;
     for (int y = 0; y < dh; y++) {
@@ -129,8 +244,6 @@ int oracle_scale_to_bgra(uint8_t *dst, int dst_stride, int dw, int dh,
  *   matrix  utils.c fill_rgb2yuv_table, the SWS_CS_DEFAULT (ITU-R 601) special case: (int)(c * 219 / 255 * 2^15 + .5)
  *           for luma, c * 224 / 255 for chroma, negative ones negated after rounding.
  */
-typedef struct { int size; int *pos; int *coef; } swsfilter;      /* coef[i * size + j] applies to sample pos[i] + j */
-
 static long long rounded_div(long long a, long long b) { return a >= 0 ? (a + (b >> 1)) / b : -((-a + (b >> 1)) / b); }
 static int ilog2(unsigned v) { int n = 0; while (v >>= 1) n++; return n; }
 

@@ -1,4 +1,4 @@
-"""Generates tests/golden/swscale_bgra_yuv.npz: outputs of the REAL libswscale (the 9.1.100 build of this image,
+"""Generates tests/golden/swscale_bgra_yuv.npz and swscale_to_bgra.npz: outputs of the REAL libswscale (the 9.1.100 build of this image,
 tests/swscale_ref.py) for the reference's encoder-side call -- sws_getContext(w, h, BGRA, w, h, YUV420P | YUV422P,
 SWS_BILINEAR, NULL, NULL, NULL) + sws_scale (ffmpeg_ntsc.cpp:2118-2131, 2266-2274) -- with the library's portable C
 code selected (av_force_cpu_flags(0)).  Run from the repo root:  python tests/golden/make_golden_swscale.py"""
@@ -23,3 +23,18 @@ for w, h in ((64, 48), (101, 67), (100, 47), (33, 21), (160, 120)):
 out["libswscale_version"] = np.array(swscale_ref.version())
 np.savez_compressed(os.path.join(HERE, "swscale_bgra_yuv.npz"), **out)
 print("wrote", len(out), "arrays, libswscale", swscale_ref.version())
+
+# the input side: sws_getContext(sw, sh, fmt, dw, dh, BGRA, SWS_BILINEAR, ...) + sws_scale (ffmpeg_ntsc.cpp:574-585, 603-610)
+out = {}
+for fmt in ("yuv420p", "yuv422p", "nv12"):
+    for sw, sh, dw, dh in ((64, 48, 64, 48), (64, 47, 64, 47), (40, 30, 64, 48), (176, 144, 64, 48), (90, 72, 64, 48), (33, 21, 80, 60)):
+        shapes = swscale_ref.plane_shapes(fmt, sw, sh)
+        planes = [rng.integers(0, 256, size=s, dtype=np.uint8) for s in shapes]
+        bgra = swscale_ref.scale(planes, fmt, sw, sh, "bgra", dw, dh, c_code=True)[0].view(np.uint32).reshape(dh, dw)
+        n = "%s_%dx%d_%dx%d" % (fmt, sw, sh, dw, dh)
+        for i, pl in enumerate(planes):
+            out["%s_p%d" % (n, i)] = pl
+        out[n + "_bgra"] = bgra
+out["libswscale_version"] = np.array(swscale_ref.version())
+np.savez_compressed(os.path.join(HERE, "swscale_to_bgra.npz"), **out)
+print("wrote", len(out), "arrays")

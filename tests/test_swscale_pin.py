@@ -1,9 +1,10 @@
-"""The encoder-side picture conversion (ffmpeg_ntsc.cpp:2118-2131, 2266-2274: sws_getContext(.., BGRA -> YUV420P |
-YUV422P, SWS_BILINEAR) + sws_scale) PINNED against libswscale itself.
-
-oracle/convert_oracle.c::oracle_bgra_to_yuv restates what the library's portable C code does for that call; here it
-is compared byte for byte with the library (libswscale 9.1.100 of this image, tests/swscale_ref.py) where that
-exists, and with outputs of the library committed as tests/golden/swscale_bgra_yuv.npz everywhere."""
+"""The two picture conversions either side of the hot path PINNED against libswscale itself:
+  * encoder side (ffmpeg_ntsc.cpp:2118-2131, 2266-2274): sws_getContext(w, h, BGRA -> YUV420P | YUV422P, SWS_BILINEAR) + sws_scale;
+  * input side, InputFile::frame_copy_scale (:574-585, 603-610): sws_getContext(sw, sh, YUV420P | YUV422P | NV12 -> dw, dh,
+    BGRA, SWS_BILINEAR) + sws_scale, for even destination widths.
+oracle/convert_oracle.c restates what the library's portable C code does for those calls; here it is compared byte
+for byte with the library (libswscale 9.1.100 of this image, tests/swscale_ref.py) where that exists, and with outputs
+of the library committed as tests/golden/swscale_*.npz everywhere."""
 import os
 
 import numpy as np
@@ -113,3 +114,52 @@ def test_product_filter_bank_equals_the_oracles():
         opos, ocoef = helpers.oracle_sws_filter(srcn, dstn, one)
         assert taps == ocoef.shape[1], (srcn, dstn, taps, ocoef.shape)
         assert np.array_equal(pos, opos) and np.array_equal(coef[:dstn * taps].reshape(dstn, taps), ocoef), (srcn, dstn)
+
+
+# ---- the input side ---------------------------------------------------------------------------------------------
+FMT_CODE = {"yuv420p": 1, "yuv422p": 2, "nv12": 3}          # the product's CVS_PIX_* / the oracle's format argument
+SCALES = [(720, 480, 720, 480), (720, 481, 720, 481), (640, 480, 720, 480), (352, 288, 720, 480), (1920, 1080, 720, 480),
+          (720, 576, 720, 480), (720, 480, 360, 240), (351, 287, 720, 480), (20, 10, 320, 240), (5, 3, 8, 8), (1280, 720, 1920, 1080)]
+
+
+def source_planes(fmt, w, h, seed, legal=False):
+    rng = np.random.default_rng(seed)
+    lo, hi = (16, 236) if legal else (0, 256)
+    return [rng.integers(lo, hi, size=s, dtype=np.uint8) for s in swscale_ref.plane_shapes(fmt, w, h)]
+
+
+@need_lib
+@pytest.mark.parametrize("sw,sh,dw,dh", SCALES)
+@pytest.mark.parametrize("fmt", sorted(FMT_CODE))
+def test_scaler_oracle_equals_libswscale_c_code(fmt, sw, sh, dw, dh):
+    for legal in (False, True):
+        planes = source_planes(fmt, sw, sh, sw + 3 * dh + legal, legal)
+        want = swscale_ref.scale(planes, fmt, sw, sh, "bgra", dw, dh, c_code=True)[0].view(np.uint32).reshape(dh, dw)
+        got = helpers.oracle_scale_to_bgra(planes, sw, sh, FMT_CODE[fmt], dw, dh)
+        assert np.array_equal(got, want), int((got != want).sum())
+
+
+@need_lib
+def test_colour_tables_on_every_yuv_triple():
+    """YUV420P at the same size takes the library's direct converter, a pure function of (Y, U, V): all 2^24 triples."""
+    W = H = 4096
+    bx, by = np.meshgrid(np.arange(W // 2), np.arange(H // 2))
+    U, V = (bx % 256).astype(np.uint8), (by % 256).astype(np.uint8)
+    xx, yy = np.meshgrid(np.arange(W), np.arange(H))
+    Y = (((xx // 2) // 256) * 32 + ((yy // 2) // 256) * 4 + (yy % 2) * 2 + (xx % 2)).astype(np.uint8)
+    assert len(np.unique(Y)) == 256
+    want = swscale_ref.scale([Y, U, V], "yuv420p", W, H, "bgra", W, H, c_code=True)[0].view(np.uint32).reshape(H, W)
+    got = helpers.oracle_scale_to_bgra([Y, U, V], W, H, 1, W, H)
+    assert np.array_equal(got, want)
+
+
+def test_scaler_oracle_equals_golden_outputs_of_libswscale():
+    g = np.load(os.path.join(HERE, "golden", "swscale_to_bgra.npz"))
+    names = sorted({k[:-5] for k in g.files if k.endswith("_bgra")})
+    assert len(names) >= 18
+    for n in names:
+        fmt, s, d = n.split("_")
+        (sw, sh), (dw, dh) = [tuple(int(v) for v in q.split("x")) for q in (s, d)]
+        planes = [g["%s_p%d" % (n, i)] for i in range(2 if fmt == "nv12" else 3)]
+        got = helpers.oracle_scale_to_bgra(planes, sw, sh, FMT_CODE[fmt], dw, dh)
+        assert np.array_equal(got, g[n + "_bgra"]), n
