@@ -40,6 +40,11 @@ struct ScalePlan {
     int16_t *d_w = nullptr;          // wx | wy | cwx | cwy
     size_t off_first[4] = {0, 0, 0, 0}, off_w[4] = {0, 0, 0, 0};
     int taps[4] = {0, 0, 0, 0};
+    // the libswscale-exact path (k_sws_yuv_to_bgra): four banks in one allocation, pos then weights per bank
+    bool sws = false, direct = false;
+    int32_t *d_sws = nullptr;
+    size_t sws_pos[4] = {0, 0, 0, 0}, sws_w[4] = {0, 0, 0, 0};
+    int sws_taps[4] = {0, 0, 0, 0};
 };
 
 struct DevPlan {
@@ -147,7 +152,7 @@ void free_all(cvs_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto &pl : c->plans) if (pl && pl->d_seek) cudaFree(pl->d_seek);
     c->plans.clear();
-    for (auto &sp : c->scale_plans) if (sp) { cudaFree(sp->d_first); cudaFree(sp->d_w); }
+    for (auto &sp : c->scale_plans) if (sp) { cudaFree(sp->d_first); cudaFree(sp->d_w); cudaFree(sp->d_sws); }
     c->scale_plans.clear();
     for (auto &s : c->slots) {
         if (s.h_fields) cudaFreeHost(s.h_fields);
@@ -886,6 +891,25 @@ int cvs_scale_to_bgra_device(cvs_ctx *ctx, void *dst, int dst_stride, long long 
         std::unique_ptr<ScalePlan> q(new (std::nothrow) ScalePlan());
         if (!q) return CVS_ERR_NOMEM;
         q->dw = dw; q->dh = dh; q->sw = sw; q->sh = sh; q->format = format;
+        // planar YUV to an even width: libswscale's own banks (sws_filter.cpp); otherwise the repository's resampler
+        q->sws = format != CVS_PIX_BGRA && (dw & 1) == 0;
+        q->direct = q->sws && format == CVS_PIX_YUV420P && sw == dw && sh == dh && (dh & 1) == 0;
+        if (q->sws && !q->direct) {
+            const FilterBank banks[4] = {bilinear_bank(sw, dw, 1 << 14), bilinear_bank(cw, (dw + 1) / 2, 1 << 14),
+                                         bilinear_bank(sh, dh, 1 << 12), bilinear_bank(ch, dh, 1 << 12)};
+            const int srcn[4] = {sw, cw, sh, ch};
+            std::vector<int32_t> blob;
+            for (int i = 0; i < 4; i++) {
+                for (int32_t v : banks[i].pos) if (v < 0 || v + banks[i].taps > srcn[i]) return CVS_ERR_UNSUPPORTED;
+                q->sws_taps[i] = banks[i].taps;
+                q->sws_pos[i] = blob.size(); blob.insert(blob.end(), banks[i].pos.begin(), banks[i].pos.end());
+                q->sws_w[i] = blob.size(); blob.insert(blob.end(), banks[i].coef.begin(), banks[i].coef.end());
+            }
+            CVS_CUDA(dev_alloc(&q->d_sws, blob.size()));
+            CVS_CUDA(cudaMemcpyAsync(q->d_sws, blob.data(), blob.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+            CVS_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+        if (!q->sws) {
         ScaleAxis ax[4];
         const int suby = format == CVS_PIX_YUV422P ? 1 : 2;
         scale_build_axis(dw, sw, 1, 0, ax[0]);
@@ -906,8 +930,32 @@ int cvs_scale_to_bgra_device(cvs_ctx *ctx, void *dst, int dst_stride, long long 
         CVS_CUDA(cudaMemcpyAsync(q->d_first, first.data(), first.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
         CVS_CUDA(cudaMemcpyAsync(q->d_w, wts.data(), wts.size() * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
         CVS_CUDA(cudaStreamSynchronize(ctx->stream));                // the tables are pageable temporaries
+        }
         sp = q.get();
         ctx->scale_plans.push_back(std::move(q));
+    }
+    if (sp->sws) {
+        SwsScaleArgs b;
+        b.dst = (uint8_t *)dst; b.dst_pic_stride = dst_pic_stride; b.dst_stride = dst_stride; b.dw = dw; b.dh = dh;
+        b.y = (const uint8_t *)src[0]; b.u = (const uint8_t *)src[1];
+        b.v = format == CVS_PIX_NV12 ? (const uint8_t *)src[1] + 1 : (const uint8_t *)src[2];
+        b.sp_y = src_pic_stride[0]; b.sp_c = src_pic_stride[1];
+        b.ly = src_linesize[0]; b.lc = src_linesize[1]; b.cstep = format == CVS_PIX_NV12 ? 2 : 1;
+        if (format != CVS_PIX_NV12 && (src_linesize[2] != src_linesize[1] || src_pic_stride[2] != src_pic_stride[1]))
+            return CVS_ERR_UNSUPPORTED;                              // U and V planes of one layout (every decoder's)
+        b.direct = sp->direct;
+        const int32_t *t = sp->d_sws;
+        b.hl_pos = t + sp->sws_pos[0]; b.hl_w = t + sp->sws_w[0]; b.hc_pos = t + sp->sws_pos[1]; b.hc_w = t + sp->sws_w[1];
+        b.vl_pos = t + sp->sws_pos[2]; b.vl_w = t + sp->sws_w[2]; b.vc_pos = t + sp->sws_pos[3]; b.vc_w = t + sp->sws_w[3];
+        b.hl_t = sp->sws_taps[0]; b.hc_t = sp->sws_taps[1]; b.vl_t = sp->sws_taps[2]; b.vc_t = sp->sws_taps[3];
+        b.n = n;
+        const int pairs = dw / 2;
+        const dim3 block(pairs < 256 ? ((pairs + 31) / 32) * 32 : 256);
+        const dim3 grid((pairs + block.x - 1) / block.x, dh, n);
+        k_sws_yuv_to_bgra<<<grid, block, 0, ctx->stream>>>(b);
+        CVS_CUDA(cudaGetLastError());
+        ctx->launches++;
+        return CVS_OK;
     }
     ScaleArgs a;
     a.dst = (uint8_t *)dst; a.dst_pic_stride = dst_pic_stride; a.dst_stride = dst_stride; a.dw = dw; a.dh = dh;

@@ -2,11 +2,30 @@
 // output size, InputFile::frame_copy_scale() (ffmpeg_ntsc.cpp:544-613: sws_getContext(src w, h, format -> output
 // w, h, BGRA, SWS_BILINEAR) at :574-585, sws_scale() at :603-610).  SURVEY section 8f-1.
 //
-// libswscale is a third-party dependency that is absent from this environment (no FFmpeg headers, libraries or
-// binary), so this is NOT pinned against the reference: it implements the resampler written down below, which
-// oracle/convert_oracle.c restates independently and tests/test_gpu_scale.py compares bit for bit.
+// Two kernels:
 //
-// The resampler ("bilinear" in swscale's sense: a triangle kernel that widens when shrinking), all in integers:
+//  k_sws_yuv_to_bgra   YUV420P / YUV422P / NV12 sources, even output width: the bytes of libswscale's C code (9.1.100;
+//      = SWS_ACCURATE_RND | SWS_BITEXACT).  PINNED: oracle/convert_oracle.c restates the library and is compared with it
+//      byte for byte (tests/test_swscale_pin.py); the kernel is compared with the oracle, the library and its committed
+//      outputs (tests/test_gpu_scale.py).  All integer:
+//        horizontal   every source row through the library's bilinear banks (sws_filter.cpp, 14-bit weights): Y to dw
+//                     samples, U and V to dw/2 samples (ONE chroma sample per pair of output pixels),
+//                     s15 = min(sum >> 7, 32767);
+//        vertical     banks with 12-bit weights (luma rows -> dh, chroma rows -> dh); the combination depends on the banks'
+//                     tap counts exactly as in the library:  1/1 taps: (s + 64) >> 7;  1 luma / 2 chroma: chroma
+//                     (c0 (4096 - a) + c1 a + (128 << 11)) >> 19;  2/2: (s0 (4096 - a) + s1 a) >> 19 without a rounding
+//                     term;  otherwise ((1 << 18) + sum s w) >> 19;
+//        colour       the library's ITU-R 601 tables as arithmetic: cy = 65536 * 255 / 219, c' = (c 65536 + 32768) / cy for
+//                     c = 104597 (V->R), 132201 (U->B), -25675 (U->G), -53279 (V->G); k = Y + (c' C >> 16) - (c' >> 9);
+//                     channel = clip8((k cy - (400 << 16) + 326 cy + 32768) >> 16); alpha 255;
+//        exception    YUV420P at the same size and an even height: the library's direct converter, no filtering, the chroma
+//                     sample of a 2x2 block serves its four pixels.
+//      One thread = one pair of output pixels; it filters the few source samples it needs itself (2 x 2 taps when
+//      enlarging), so no intermediate picture exists.
+//
+//  k_scale_to_bgra     BGRA sources and odd output widths (the library then takes other routes -- an RGB -> YUV -> RGB
+//      round trip, its full-chroma-interpolation writers -- which are not restated): the repository's OWN resampler,
+//      NOT pinned, specified here and restated independently in oracle/convert_oracle.c:
 //  * per axis, destination sample i of n_dst takes its value at source position P / D (centre aligned),
 //        D = 2 n_dst sub,   P = (2 i + 1) n_src - n_dst - off n_dst,
 //    n_src the LUMA size of the source along the axis, sub = 1 for luma / BGRA planes and 2 for a subsampled chroma
@@ -19,8 +38,9 @@
 //  * planar YUV input is scaled plane by plane to full resolution and then converted, BT.601 limited range ->
 //    full-range RGB:  c = 298 (Y - 16),  R = clamp8((c + 409 (V-128) + 128) >> 8),
 //    G = clamp8((c - 100 (U-128) - 208 (V-128) + 128) >> 8),  B = clamp8((c + 516 (U-128) + 128) >> 8),  A = 255;
-//    BGRA input is scaled channel by channel (alpha included).
-// Tap tables are built on the host once per geometry (scale_build_axis) and shared by all pictures.
+//    BGRA input is scaled channel by channel (alpha included); a BGRA source of the output size is copied, as the
+//    library does.
+// Tap tables are built on the host once per geometry and shared by all pictures.
 #ifndef CVS_SCALE_CONVERT_CUH
 #define CVS_SCALE_CONVERT_CUH
 
@@ -149,6 +169,105 @@ __global__ void __launch_bounds__(256) k_scale_to_bgra(const __grid_constant__ S
     }
     uint32_t *drow = reinterpret_cast<uint32_t *>(a.dst + (long long)k * a.dst_pic_stride + (long long)y * a.dst_stride);
     drow[x] = out;
+}
+
+// ---- libswscale's bytes for planar YUV sources (see the header comment) --------------------------------------------
+struct SwsScaleArgs {
+    uint8_t *dst;
+    long long dst_pic_stride;
+    int dst_stride, dw, dh;
+    const uint8_t *y, *u, *v;           // NV12: u = the interleaved plane, v = u + 1
+    long long sp_y, sp_c;               // picture strides
+    int ly, lc, cstep;                  // line sizes; bytes between chroma samples (1 planar, 2 NV12)
+    int direct;                         // same-size YUV420P, even height: no filtering
+    // banks: luma columns, chroma columns, luma rows, chroma rows
+    const int32_t *hl_pos, *hl_w, *hc_pos, *hc_w, *vl_pos, *vl_w, *vc_pos, *vc_w;
+    int hl_t, hc_t, vl_t, vc_t;
+    int n;
+};
+
+__device__ __forceinline__ int sws_h15(const uint8_t *row, int step, const int32_t *w, int pos, int taps) {
+    int acc = 0;
+    for (int j = 0; j < taps; j++) acc += (int)row[(size_t)(pos + j) * (size_t)step] * w[j];
+    return min(acc >> 7, 32767);
+}
+__device__ __forceinline__ int sws_chan(int k) {
+    constexpr int cy = (65536 * 255) / 219;
+    return scale_clampi((k * cy - (400 << 16) + 326 * cy + 32768) >> 16, 0, 255);
+}
+__device__ __forceinline__ uint32_t sws_pixel(int Y, int U, int V) {
+    constexpr long long cy = (65536LL * 255) / 219;
+    constexpr int crv = (int)((104597LL * 65536 + 32768) / cy), cbu = (int)((132201LL * 65536 + 32768) / cy);
+    constexpr int cgu = -(int)((25675LL * 65536 - 32768) / cy), cgv = -(int)((53279LL * 65536 - 32768) / cy);
+    U = scale_clampi(U, 0, 255);
+    V = scale_clampi(V, 0, 255);
+    const int r = sws_chan(Y + ((crv * V) >> 16) - (crv >> 9));
+    const int b = sws_chan(Y + ((cbu * U) >> 16) - (cbu >> 9));
+    const int g = sws_chan(Y + ((cgu * U) >> 16) - (cgu >> 9) + ((cgv * V) >> 16) - (cgv >> 9));
+    return 0xFF000000u | ((uint32_t)r << 16) | ((uint32_t)g << 8) | (uint32_t)b;
+}
+
+__global__ void __launch_bounds__(256) k_sws_yuv_to_bgra(const __grid_constant__ SwsScaleArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, k = blockIdx.z;     // i: pair of output pixels
+    if (2 * i >= a.dw) return;
+    const uint8_t *py = a.y + (long long)k * a.sp_y, *pu = a.u + (long long)k * a.sp_c, *pv = a.v + (long long)k * a.sp_c;
+    uint32_t *out = reinterpret_cast<uint32_t *>(a.dst + (long long)k * a.dst_pic_stride + (long long)y * a.dst_stride) + 2 * i;
+    if (a.direct) {
+        const uint8_t *ry = py + (size_t)y * a.ly + 2 * i;
+        const int U = pu[(size_t)(y >> 1) * a.lc + (size_t)i * a.cstep], V = pv[(size_t)(y >> 1) * a.lc + (size_t)i * a.cstep];
+        out[0] = sws_pixel(ry[0], U, V);
+        out[1] = sws_pixel(ry[1], U, V);
+        return;
+    }
+    const int x0 = 2 * i, x1 = 2 * i + 1;
+    const int32_t *wl0 = a.hl_w + (size_t)x0 * a.hl_t, *wl1 = a.hl_w + (size_t)x1 * a.hl_t, *wc = a.hc_w + (size_t)i * a.hc_t;
+    const int pl0 = a.hl_pos[x0], pl1 = a.hl_pos[x1], pc = a.hc_pos[i];
+    const int32_t *vl = a.vl_w + (size_t)y * a.vl_t, *vc = a.vc_w + (size_t)y * a.vc_t;
+    const int rl = a.vl_pos[y], rc = a.vc_pos[y];
+    const bool two_c = a.vc_t == 2 && vc[0] + vc[1] == 4096 && vc[1] >= 0 && vc[1] <= 4096;
+    const bool two_l = a.vl_t == 2 && vl[0] + vl[1] == 4096 && vl[1] >= 0 && vl[1] <= 4096;
+    auto L = [&](int r, int which) {
+        const uint8_t *row = py + (size_t)(rl + r) * a.ly;
+        return which ? sws_h15(row, 1, wl1, pl1, a.hl_t) : sws_h15(row, 1, wl0, pl0, a.hl_t);
+    };
+    auto CU = [&](int r) { return sws_h15(pu + (size_t)(rc + r) * a.lc, a.cstep, wc, pc, a.hc_t); };
+    auto CV = [&](int r) { return sws_h15(pv + (size_t)(rc + r) * a.lc, a.cstep, wc, pc, a.hc_t); };
+    int Y0, Y1, U, V;
+    if (a.vl_t == 1 && (a.vc_t == 1 || two_c)) {
+        Y0 = (L(0, 0) + 64) >> 7;
+        Y1 = (L(0, 1) + 64) >> 7;
+        if (a.vc_t == 1) {
+            U = (CU(0) + 64) >> 7;
+            V = (CV(0) + 64) >> 7;
+        } else {
+            const int c = vc[1];
+            U = (CU(0) * (4096 - c) + CU(1) * c + (128 << 11)) >> 19;
+            V = (CV(0) * (4096 - c) + CV(1) * c + (128 << 11)) >> 19;
+        }
+    } else if (two_l && two_c) {
+        const int l = vl[1], c = vc[1];
+        Y0 = (L(0, 0) * (4096 - l) + L(1, 0) * l) >> 19;
+        Y1 = (L(0, 1) * (4096 - l) + L(1, 1) * l) >> 19;
+        U = (CU(0) * (4096 - c) + CU(1) * c) >> 19;
+        V = (CV(0) * (4096 - c) + CV(1) * c) >> 19;
+    } else {
+        Y0 = Y1 = U = V = 1 << 18;
+        for (int j = 0; j < a.vl_t; j++) {
+            const int w = vl[j];
+            if (w == 0) continue;
+            Y0 += L(j, 0) * w;
+            Y1 += L(j, 1) * w;
+        }
+        for (int j = 0; j < a.vc_t; j++) {
+            const int w = vc[j];
+            if (w == 0) continue;
+            U += CU(j) * w;
+            V += CV(j) * w;
+        }
+        Y0 >>= 19; Y1 >>= 19; U >>= 19; V >>= 19;
+    }
+    out[0] = sws_pixel(Y0, U, V);
+    out[1] = sws_pixel(Y1, U, V);
 }
 #endif
 

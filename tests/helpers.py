@@ -139,7 +139,7 @@ def load_golden():
     """name -> (argv, w, h, n, dst) fixtures produced by the reference's own code (make_golden.py)."""
     out = {}
     for fn in sorted(os.listdir(GOLDEN_DIR)):
-        if fn.endswith(".npz") and not fn.startswith(("yuv422_", "audio_")):   # (those have their own loaders)
+        if fn.endswith(".npz") and not fn.startswith(("yuv422_", "audio_", "swscale_")):   # (those have their own loaders)
             z = np.load(os.path.join(GOLDEN_DIR, fn))
             out[fn[:-4]] = ([str(a) for a in z["argv"]], int(z["w"]), int(z["h"]), int(z["n"]), z["dst"])
     return out

@@ -1,11 +1,15 @@
 """cvs_scale_to_bgra_device (the input side: InputFile::frame_copy_scale(), ffmpeg_ntsc.cpp:544-613):
-decoder picture -> BGRA at the output size on the device.  NOT pinned against libswscale (absent here); the kernel
-is compared bit for bit with oracle/convert_oracle.c, which restates the resampler from its specification
-(csrc/scale_convert.cuh header) independently of the kernel; tests/test_convert_oracle.py checks the oracle itself."""
+decoder picture -> BGRA at the output size on the device.  Planar YUV sources to an even output width are PINNED:
+the kernel is compared bit for bit with oracle/convert_oracle.c (which tests/test_swscale_pin.py pins against libswscale
+9.1.100 itself), with the library directly when the GPU box has it, and with its committed outputs.  BGRA sources and
+odd output widths use the repository's own resampler (not pinned; same oracle file, restated from its specification)."""
+import os
+
 import numpy as np
 import pytest
 
 import helpers
+import swscale_ref
 import composite_video_simulator_b200 as cvs
 
 pytestmark = pytest.mark.gpu
@@ -39,6 +43,44 @@ def test_scaler_matches_the_oracle(sw, sh, dw, dh, fmt):
         eng.scale_to_bgra_device(dst, dw, dh, dev, [p.shape[1] for p in planes], sw, sh, fmt)
         eng.synchronize()
     assert np.array_equal(dst.cpu().numpy().view(np.uint32), want)
+
+
+def _scale_on_gpu(planes, sw, sh, fmt, dw, dh):
+    import torch
+    dev = [torch.from_numpy(np.ascontiguousarray(p)).cuda() for p in planes]
+    dst = torch.zeros((dh, dw), dtype=torch.int32, device="cuda")
+    with cvs.Engine([], max_w=dw, max_h=dh, max_batch=1) as eng:
+        eng.scale_to_bgra_device(dst, dw, dh, dev, [p.shape[1] for p in planes], sw, sh, fmt)
+        eng.synchronize()
+    return dst.cpu().numpy().view(np.uint32)
+
+
+FMT_NAME = {YUV420P: "yuv420p", YUV422P: "yuv422p", NV12: "nv12"}
+
+
+@pytest.mark.skipif(not swscale_ref.available(), reason="no libswscale on this machine (golden fixtures cover it)")
+@pytest.mark.parametrize("sw,sh,dw,dh", [(720, 480, 720, 480), (720, 481, 720, 481), (640, 480, 720, 480), (352, 288, 720, 480),
+                                         (1920, 1080, 720, 480), (720, 576, 720, 480), (1280, 720, 1920, 1080), (351, 287, 720, 480)])
+@pytest.mark.parametrize("fmt", [YUV420P, YUV422P, NV12])
+def test_scaler_equals_libswscale_itself(sw, sh, dw, dh, fmt):
+    """sws_getContext(sw, sh, fmt, dw, dh, BGRA, SWS_BILINEAR, ...) + sws_scale() of the library on this machine (its C
+    code) against the kernel, byte for byte: every tap-count combination of the library's vertical dispatch."""
+    planes = source(sw, sh, fmt, sw + dh + fmt)
+    want = swscale_ref.scale(planes, FMT_NAME[fmt], sw, sh, "bgra", dw, dh, c_code=True)[0].view(np.uint32).reshape(dh, dw)
+    got = _scale_on_gpu(planes, sw, sh, fmt, dw, dh)
+    assert np.array_equal(got, want), int((got != want).sum())
+
+
+def test_scaler_equals_golden_outputs_of_libswscale():
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "swscale_to_bgra.npz"))
+    names = sorted({k[:-5] for k in g.files if k.endswith("_bgra")})
+    assert len(names) >= 18
+    code = {v: k for k, v in FMT_NAME.items()}
+    for nm in names:
+        fmt, s_, d_ = nm.split("_")
+        (sw, sh), (dw, dh) = [tuple(int(v) for v in q.split("x")) for q in (s_, d_)]
+        planes = [g["%s_p%d" % (nm, i)] for i in range(2 if fmt == "nv12" else 3)]
+        assert np.array_equal(_scale_on_gpu(planes, sw, sh, code[fmt], dw, dh), g[nm + "_bgra"]), nm
 
 
 def test_scaler_batches_strides_and_errors():
