@@ -122,6 +122,7 @@ struct cvs_ctx {
     // cvs_bgra_to_yuv_device: the filter banks of a geometry on the device (sws_filter.h), built on first use
     struct YuvBanks {
         int w = 0, h = 0, v420 = 0, vtaps = 0, htaps = 0;
+        bool tile_ok = false;                      // every tile of k_bgra_to_yuv420_tiled fits its shared rows
         int32_t *d = nullptr;                      // vpos | vcoef | hpos | hcoef
         size_t off_vcoef = 0, off_hpos = 0, off_hcoef = 0;
     };
@@ -813,6 +814,13 @@ int cvs_bgra_to_yuv_device(cvs_ctx *ctx, void *y, int ly, long long y_pic_stride
         if (!inside(vb, h) || ((w & 1) && !inside(hb, w))) return CVS_ERR_UNSUPPORTED;
         cvs_ctx::YuvBanks nb;
         nb.w = w; nb.h = h; nb.v420 = v420; nb.vtaps = vb.taps; nb.htaps = hb.taps;
+        nb.tile_ok = v420;
+        for (int c0 = 0; v420 && c0 < crows_; c0 += kTileC) {
+            const int c1 = std::min(c0 + kTileC, crows_) - 1;
+            const int lo = std::min(vb.pos[(size_t)c0], 2 * c0), hi = std::max(vb.pos[(size_t)c1] + vb.taps - 1, std::min(2 * c1 + 1, h - 1));
+            if (hi - lo + 1 > kTileRows) nb.tile_ok = false;
+            for (int c = c0; c <= c1; c++) if (vb.pos[(size_t)c] < lo) nb.tile_ok = false;
+        }
         std::vector<int32_t> blob(vb.pos);
         nb.off_vcoef = blob.size(); blob.insert(blob.end(), vb.coef.begin(), vb.coef.end());
         nb.off_hpos = blob.size(); blob.insert(blob.end(), hb.pos.begin(), hb.pos.end());
@@ -847,9 +855,23 @@ int cvs_bgra_to_yuv_device(cvs_ctx *ctx, void *y, int ly, long long y_pic_stride
         k_bgra_to_yuv_oddw<<<grid, block, 0, ctx->stream>>>(a);
     } else {
         const int groups = (w + 7) / 8;
-        const dim3 block(groups < 256 ? ((groups + 31) / 32) * 32 : 256);
-        const dim3 grid((groups + block.x - 1) / block.x, crows, n);
-        k_bgra_to_yuv<<<grid, block, 0, ctx->stream>>>(a);
+        // the streaming kernels want whole 8-pixel groups and aligned rows: what encoders' frames have
+        const bool aligned = (w % 8) == 0 && ((uintptr_t)bgra % 16) == 0 && (stride % 16) == 0 && (bgra_pic_stride % 16) == 0 &&
+                             ((uintptr_t)y % 8) == 0 && (ly % 8) == 0 && (y_pic_stride % 8) == 0 &&
+                             ((uintptr_t)u % 4) == 0 && (lu % 4) == 0 && (u_pic_stride % 4) == 0 &&
+                             ((uintptr_t)v % 4) == 0 && (lv % 4) == 0 && (v_pic_stride % 4) == 0;
+        if (aligned && !v420) {
+            const dim3 block(groups < 256 ? ((groups + 31) / 32) * 32 : 256);
+            const dim3 grid((groups + block.x - 1) / block.x, h, n);
+            k_bgra_to_yuv422_fast<<<grid, block, 0, ctx->stream>>>(a);
+        } else if (aligned && v420 && bk->tile_ok) {
+            const dim3 grid((groups + 31) / 32, (crows + kTileC - 1) / kTileC, n);
+            k_bgra_to_yuv420_tiled<<<grid, 256, 0, ctx->stream>>>(a);
+        } else {
+            const dim3 block(groups < 256 ? ((groups + 31) / 32) * 32 : 256);
+            const dim3 grid((groups + block.x - 1) / block.x, crows, n);
+            k_bgra_to_yuv<<<grid, block, 0, ctx->stream>>>(a);
+        }
     }
     CVS_CUDA(cudaGetLastError());
     ctx->launches++;

@@ -55,9 +55,10 @@ __device__ __forceinline__ int yuv_luma(const YuvCoef &c, uint32_t px) {
     return yuv_clip8((min(2 * y14, 32767) + 64) >> 7);
 }
 
-// Even widths.  One thread = 8 pixels x one chroma row: the rows its vertical taps cover (4 of them for 4:2:0, of
-// which two are also its luma rows; 1 for 4:2:2) as 32-byte loads, 8-byte luma stores, 4-byte chroma stores.
-// Neighbouring chroma rows share source rows; the second read comes from L2.
+// Even widths, any alignment, any bank (the general form; the two streaming kernels below take the common cases).
+// One thread = 8 pixels x one chroma row: the rows its vertical taps cover (4 of them for 4:2:0, of which two are also
+// its luma rows; 1 for 4:2:2) as 32-byte loads, 8-byte luma stores, 4-byte chroma stores.  Neighbouring chroma rows
+// share source rows; the second read comes from L2.
 __global__ void __launch_bounds__(256) k_bgra_to_yuv(const __grid_constant__ YuvArgs a) {
     const int gx = blockIdx.x * blockDim.x + threadIdx.x;          // group of 8 pixels
     const int cy = blockIdx.y;                                     // chroma row
@@ -125,6 +126,105 @@ __global__ void __launch_bounds__(256) k_bgra_to_yuv(const __grid_constant__ Yuv
     } else {
         for (int j = 0; j < 4 && cx0 + j < cw; j++) { ud[j] = (uint8_t)(uw >> (8 * j)); vd[j] = (uint8_t)(vw >> (8 * j)); }
     }
+}
+
+// ---- the two common cases as streaming kernels ----------------------------------------------------------------------
+// Shared by both: 8 pixels of one source row -> 8 luma bytes and the 15-bit chroma of the 4 samples they carry.
+struct Yuv8 { uint32_t y0, y1; int u[4], v[4]; };
+__device__ __forceinline__ Yuv8 yuv_row8(const YuvCoef &c, const uint32_t px[8], bool want_luma, bool want_chroma) {
+    Yuv8 o;
+    o.y0 = o.y1 = 0;
+    if (want_luma) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t yv = (uint32_t)yuv_luma(c, px[i]) << (8 * (i & 3));
+            if (i < 4) o.y0 |= yv; else o.y1 |= yv;
+        }
+    }
+    if (want_chroma) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t q0 = px[2 * j], q1 = px[2 * j + 1];
+            const int sb = (q0 & 0xFF) + (q1 & 0xFF), sg = ((q0 >> 8) & 0xFF) + ((q1 >> 8) & 0xFF), sr = ((q0 >> 16) & 0xFF) + ((q1 >> 16) & 0xFF);
+            o.u[j] = min(2 * ((c.ru * sr + c.gu * sg + c.bu * sb + (256 << kYuvShift) + 512) >> 10), 32767);
+            o.v[j] = min(2 * ((c.rv * sr + c.gv * sg + c.bv * sb + (256 << kYuvShift) + 512) >> 10), 32767);
+        }
+    }
+    return o;
+}
+__device__ __forceinline__ void yuv_load8(const uint8_t *rowp, int x0, uint32_t px[8]) {
+    const uint4 p0 = *reinterpret_cast<const uint4 *>(rowp + 4 * (size_t)x0), p1 = *reinterpret_cast<const uint4 *>(rowp + 4 * (size_t)x0 + 16);
+    px[0] = p0.x; px[1] = p0.y; px[2] = p0.z; px[3] = p0.w; px[4] = p1.x; px[5] = p1.y; px[6] = p1.z; px[7] = p1.w;
+}
+
+// 4:2:2, widths that are multiples of 8, 16-byte aligned rows: nothing is shared between rows; one thread = 8 pixels.
+__global__ void __launch_bounds__(256) k_bgra_to_yuv422_fast(const __grid_constant__ YuvArgs a) {
+    const int gx = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y, k = blockIdx.z;
+    const int x0 = gx * 8;
+    if (x0 >= a.w) return;
+    uint32_t px[8];
+    yuv_load8(a.bgra + (long long)k * a.sp_bgra + (long long)r * a.stride, x0, px);
+    const Yuv8 o = yuv_row8(a.c, px, true, true);
+    *reinterpret_cast<uint2 *>(a.y + (long long)k * a.sp_y + (long long)r * a.ly + x0) = make_uint2(o.y0, o.y1);
+    uint32_t uw = 0, vw = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        uw |= (uint32_t)yuv_clip8((o.u[j] + 64) >> 7) << (8 * j);
+        vw |= (uint32_t)yuv_clip8((o.v[j] + 64) >> 7) << (8 * j);
+    }
+    *reinterpret_cast<uint32_t *>(a.u + (long long)k * a.sp_u + (long long)r * a.lu + gx * 4) = uw;
+    *reinterpret_cast<uint32_t *>(a.v + (long long)k * a.sp_v + (long long)r * a.lv + gx * 4) = vw;
+}
+
+// 4:2:0, same conditions.  A block owns 256 pixels x kTileC chroma rows: every source row the tile's vertical taps cover
+// (2 kTileC + 2 of them away from the edges) is loaded ONCE, its luma stored and its 15-bit chroma parked in shared
+// memory; after a barrier each thread weighs the rows of one chroma row.  Source rows are read 1 + 2 / (2 kTileC)
+// times instead of twice, and the chroma matrix runs once per row.
+constexpr int kTileC = 8, kTileRows = 2 * kTileC + 4;
+__global__ void __launch_bounds__(256) k_bgra_to_yuv420_tiled(const __grid_constant__ YuvArgs a) {
+    __shared__ uint4 su[kTileRows][32], sv[kTileRows][32];       // per row and 8-pixel group: u15[4], v15[4]
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 groups x 8 rows
+    const int gx = blockIdx.x * 32 + tx, x0 = gx * 8, k = blockIdx.z;
+    const int crows = (a.h + 1) / 2;
+    const int c0 = blockIdx.y * kTileC, c1 = min(c0 + kTileC, crows) - 1;
+    const int nt = a.vtaps;
+    const int l_lo = 2 * c0, l_hi = min(2 * c1 + 1, a.h - 1);    // luma rows of the tile
+    const int lo = min(a.vpos[c0], l_lo), hi = max(a.vpos[c1] + nt - 1, l_hi);   // hi - lo < kTileRows: checked by the host
+    const bool live = x0 < a.w;
+    const uint8_t *src = a.bgra + (long long)k * a.sp_bgra;
+    for (int r = lo + ty; r <= hi; r += 8) {
+        if (!live) continue;
+        uint32_t px[8];
+        yuv_load8(src + (long long)r * a.stride, x0, px);
+        const bool luma = r >= l_lo && r <= l_hi;
+        const Yuv8 o = yuv_row8(a.c, px, luma, true);
+        if (luma) *reinterpret_cast<uint2 *>(a.y + (long long)k * a.sp_y + (long long)r * a.ly + x0) = make_uint2(o.y0, o.y1);
+        su[r - lo][tx] = make_uint4((uint32_t)o.u[0], (uint32_t)o.u[1], (uint32_t)o.u[2], (uint32_t)o.u[3]);
+        sv[r - lo][tx] = make_uint4((uint32_t)o.v[0], (uint32_t)o.v[1], (uint32_t)o.v[2], (uint32_t)o.v[3]);
+    }
+    __syncthreads();
+    const int cy = c0 + ty;
+    if (!live || cy > c1) return;
+    const int p = a.vpos[cy] - lo;
+    const int32_t *vc = a.vcoef + (size_t)cy * nt;
+    int au[4], av[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) au[j] = av[j] = 64 << 12;
+    for (int t = 0; t < nt; t++) {
+        const int wgt = vc[t];
+        if (wgt == 0) continue;
+        const uint4 u4 = su[p + t][tx], v4 = sv[p + t][tx];
+        au[0] += (int)u4.x * wgt; au[1] += (int)u4.y * wgt; au[2] += (int)u4.z * wgt; au[3] += (int)u4.w * wgt;
+        av[0] += (int)v4.x * wgt; av[1] += (int)v4.y * wgt; av[2] += (int)v4.z * wgt; av[3] += (int)v4.w * wgt;
+    }
+    uint32_t uw = 0, vw = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        uw |= (uint32_t)yuv_clip8(au[j] >> 19) << (8 * j);
+        vw |= (uint32_t)yuv_clip8(av[j] >> 19) << (8 * j);
+    }
+    *reinterpret_cast<uint32_t *>(a.u + (long long)k * a.sp_u + (long long)cy * a.lu + gx * 4) = uw;
+    *reinterpret_cast<uint32_t *>(a.v + (long long)k * a.sp_v + (long long)cy * a.lv + gx * 4) = vw;
 }
 
 // Odd widths: the library keeps chroma at full width on the source side and resamples it horizontally, so every

@@ -34,7 +34,10 @@ def real_bt601(bgra, v420):
     return y, mean(cb), mean(cr)
 
 
-@pytest.mark.parametrize("w,h,n", [(64, 32, 1), (720, 480, 3), (1920, 1080, 2), (101, 67, 2), (8, 2, 1), (1366, 768, 1)])
+# (widths that are multiples of 8 take the streaming kernels -- 4:2:2 direct, 4:2:0 tiled over 8 chroma rows: tile edges, odd
+#  heights and pictures smaller than a tile are in the list; the others take the general kernel / the odd-width kernel)
+@pytest.mark.parametrize("w,h,n", [(64, 32, 1), (720, 480, 3), (1920, 1080, 2), (101, 67, 2), (8, 2, 1), (1366, 768, 1),
+                                   (720, 481, 2), (256, 67, 1), (64, 6, 1), (64, 3, 2), (512, 17, 1), (264, 34, 1)])
 @pytest.mark.parametrize("v420", [True, False])
 def test_bgra_to_yuv_matches_the_formula(w, h, n, v420):
     import torch
