@@ -21,7 +21,8 @@ A step = one pass of the hot path over one batch of synthetic pictures:
   roofline  k_fields alone: algorithmic bytes (8 B per processed pixel) / mean launch duration from
          CUDA events recorded around every launch in the timed region (cvs_kernel_time_query).
   config.other_workloads  the other BASELINE configurations and the 4:2:2 sibling path, measured the same
-         way (device-resident, kernel events), N = 1 only.
+         way (device-resident, kernel events), the whole field loop host to host (cvs_field_loop_host), and
+         the two picture conversions either side of the path (`conversions`: libswscale's bytes), N = 1 only.
   cpu_baseline  the reference's own composite_layer() (oracle/_ref/libref.so, extracted at build
          time) on ONE host thread -- the reference is single-threaded -- median of 3 bounded samples.
 Multi-GPU: fields are independent given the rand() position (closed-form seek), so rank r of N takes
@@ -430,6 +431,57 @@ def measure_field_loop(torch, cvs, local_rank, w, h, preset, n, calls):
             "checksum": int(y.numpy()[-1].astype(np.uint32).sum() & 0xFFFFFFFF)}
 
 
+def measure_conversions(torch, cvs, local_rank, peak, steps=10):
+    """The two picture conversions either side of the path (libswscale's bytes, tests/test_swscale_pin.py) as
+    device-resident streaming kernels: 1080p pictures, CUDA events on the launching stream, algorithmic bytes = 4 B/px BGRA
+    + the planar bytes of the other side."""
+    out = {}
+    w, h, n = 1920, 1080, 128
+    src = torch.randint(0, 1 << 24, (n, h, w), dtype=torch.int32, device="cuda")
+    with cvs.Engine([], device=local_rank, max_w=w, max_h=h, max_batch=1) as eng:
+        st = torch.cuda.Stream()
+        eng.set_stream(st.cuda_stream)
+
+        def timed_launches(fn):
+            with torch.cuda.stream(st):
+                for _ in range(3):
+                    fn()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(st)
+                for _ in range(steps):
+                    fn()
+                e1.record(st)
+                e1.synchronize()
+            return e0.elapsed_time(e1) / steps
+
+        for v420 in (True, False):
+            ch = h // 2 if v420 else h
+            y = torch.empty((n, h, w), dtype=torch.uint8, device="cuda")
+            u = torch.empty((n, ch, w // 2), dtype=torch.uint8, device="cuda")
+            v = torch.empty_like(u)
+            ms = timed_launches(lambda: eng.bgra_to_yuv_device(y, u, v, src, w, h, n, fmt420=v420))
+            gbs = n * w * h * (4 + (1.5 if v420 else 2.0)) / (ms / 1e3) / 1e9
+            out["bgra_to_%s_1080p" % ("yuv420p" if v420 else "yuv422p")] = {
+                "kernel": "k_bgra_to_yuv420_tiled" if v420 else "k_bgra_to_yuv422_fast", "value": n / (ms / 1e3), "unit": "pictures/s",
+                "kernel_ms_per_launch": ms, "pictures_per_launch": n, "gpu_launches": steps,
+                "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak if peak else None}}
+            del y, u, v
+        for sw, sh in ((720, 480), (1920, 1080)):
+            ns = 64
+            Y = torch.randint(0, 256, (ns, sh, sw), dtype=torch.uint8, device="cuda")
+            UV = torch.randint(0, 256, (ns, sh // 2, sw), dtype=torch.uint8, device="cuda")
+            dst = torch.empty((ns, h, w), dtype=torch.int32, device="cuda")
+            ms = timed_launches(lambda: eng.scale_to_bgra_device(dst, w, h, [Y, UV], [sw, sw], sw, sh, 3, n=ns))
+            gbs = ns * (sw * sh * 1.5 + w * h * 4.0) / (ms / 1e3) / 1e9
+            out["nv12_%dx%d_to_bgra_1080p" % (sw, sh)] = {
+                "kernel": "k_sws_yuv_to_bgra", "value": ns / (ms / 1e3), "unit": "pictures/s", "kernel_ms_per_launch": ms,
+                "pictures_per_launch": ns, "gpu_launches": steps,
+                "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak if peak else None}}
+            del Y, UV, dst
+        eng.set_stream(0)
+    return out
+
+
 def copy_ceiling(torch, dist, dev, w, h, Be, steps, chunk, contiguous=False):
     """What the box moves with the e2e path's copies alone: per field the rows of one parity up (pitch 2 x stride ->
     the device picture) and down, in chunks on two streams, no kernel in between.  Same sizes, pitches and pinned
@@ -689,7 +741,8 @@ def run_own_arm(args):
                 continue
             others[name] = measure_other_bgra(torch, cvs, sharding, timed, dev, local_rank, name, w2, h2, pr2, mb, st2,
                                               args.warmup, peak)
-        others["field_loop_nv12_to_yuv420p_1080p"] = measure_field_loop(torch, cvs, local_rank, 1920, 1080, "sp", 128, 3)
+        others["field_loop_nv12_to_yuv420p_1080p"] = measure_field_loop(torch, cvs, local_rank, 1920, 1080, "sp", 256, 3)
+        others["conversions"] = measure_conversions(torch, cvs, local_rank, peak)
         others["yuv422_sp_1080p"] = measure_yuv422(torch, timed, dev, local_rank, 1920, 1080, ["-vhs", "-vhs-speed", "sp"],
                                                    339, st2, args.warmup, peak)
 

@@ -62,5 +62,5 @@ with cvs.Engine([], max_w=w, max_h=h, max_batch=1) as eng:
         ms = e0.elapsed_time(e1) / steps
         bytes_ = ns * (sw * sh * 1.5 + w * h * 4.0)
         gbs = bytes_ / (ms / 1e3) / 1e9
-        print(json.dumps({"kernel": "k_scale_to_bgra", "format": "nv12 %dx%d -> bgra %dx%d" % (sw, sh, w, h),
+        print(json.dumps({"kernel": "k_sws_yuv_to_bgra", "format": "nv12 %dx%d -> bgra %dx%d" % (sw, sh, w, h),
                           "frames_per_s": ns / (ms / 1e3), "algorithmic_GBps": gbs, "frac_of_measured_hbm_peak": gbs / peak if peak else None}))
