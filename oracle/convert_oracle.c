@@ -7,12 +7,19 @@
  *   - the encoder-side sws_scale()   (ffmpeg_ntsc.cpp:2266-2274, context :2118-2131, SMPTE170M / MPEG range
  *     :2100-2101):  finished BGRA picture -> planar YUV 4:2:0 / 4:2:2.
  *
- * PARITY UNPINNED: both are calls into libswscale, a third-party dependency that is absent from this environment
- * (no FFmpeg headers, libraries or binary; the reference needs FFmpeg 3.x).  What is restated here is the algorithm
- * as this repository specifies it (include/cvs_ntsc.h, "picture conversions"), written from that text and NOT from
- * the kernels, so that the kernels are checked against something they were not derived from.  It is the swscale
- * family of algorithms (triangle-kernel resampling with 14-bit weights and a 15-bit intermediate, BT.601 integer
- * matrices) but bit-equality with any libswscale build is not claimed.
+ * Both are calls into libswscale, a third-party dependency of the reference (it needs FFmpeg 3.x; no FFmpeg source or
+ * headers exist in this environment).  PARITY PINNED for the library's default route: libswscale 9.1.100 (FFmpeg 8.0) is
+ * present in this image as a binary (inside opencv-python-headless); tests/swscale_ref.py binds it with ctypes, makes the
+ * reference's own calls, and tests/test_swscale_pin.py compares the functions below with it byte for byte (library C
+ * code; tests/golden/swscale_*.npz carry its outputs elsewhere).  What each function restates is written above it, with
+ * the names of the library routines that do it; the text was written from the library's documented structure and
+ * validated against the binary -- none of it is the library's source.
+ *
+ * PARITY UNPINNED for what the library routes differently and this file does not restate: BGRA sources at another size
+ * (an RGB -> YUV -> RGB round trip inside the library) and odd destination widths (its full-chroma-interpolation
+ * writers).  Those use the repository's own resampler (first part of this file: triangle-kernel resampling with 14-bit
+ * weights and a 15-bit intermediate, BT.601 integer matrices), restated here from its specification in
+ * csrc/scale_convert.cuh and NOT from the kernel.
  */
 #include <stdint.h>
 #include <stdlib.h>
