@@ -78,6 +78,7 @@ struct cvs422_ctx {
     int next_slot = 0;
     uint8_t *d_scratch = nullptr, *d_halo = nullptr;
     int32_t *d_status = nullptr, *h_status = nullptr;
+    int rotate_roles = 1;              // CVS422_ROTATE=0: warp k of every group runs role k (A/B switch)
     double *d_lut = nullptr;
     int plan_threads = 4;                         // host threads that build the per-row side tables of a batch (CVS_PLAN_THREADS)
     size_t lut_cap = 0;
@@ -284,6 +285,8 @@ int run_device(cvs422_ctx *c, uint8_t *y, uint8_t *u, uint8_t *v, long long psy,
     };
     a.vec = al(y, psy, ly, 8) && al(u, psu, lu, 4) && al(v, psv, lv, 4);
     a.status = c->d_status;
+    a.sm_slots = c->d_status + 1;
+    a.rotate = c->rotate_roles;
 
     // the head-switch pre-pass and the halo copy read the pictures before the in-place pass writes them
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -346,6 +349,7 @@ int cvs422_create(cvs422_ctx **out, const cvs422_params *p, int device, int max_
     c->halo_pitch_max = round_up(max_w + 2, 16) + 2 * round_up(max_w / 2, 16);
     c->cur.seed(1);
     if (const char *e = std::getenv("CVS_PACKED_ROWS")) c->packed_rows = std::atoi(e) != 0;
+    if (const char *e = std::getenv("CVS422_ROTATE")) c->rotate_roles = std::atoi(e) != 0;
     bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&c->s_tab, cudaStreamNonBlocking) == cudaSuccess;
     for (auto &s : c->slots) {
@@ -365,9 +369,10 @@ int cvs422_create(cvs422_ctx **out, const cvs422_params *p, int device, int max_
     }
     ok = ok && cudaMalloc((void **)&c->d_scratch, (size_t)max_batch * (size_t)c->hs_max * (size_t)max_w) == cudaSuccess;
     ok = ok && cudaMalloc((void **)&c->d_halo, (size_t)max_batch * (size_t)c->wpf_max * (size_t)c->halo_pitch_max) == cudaSuccess;
-    ok = ok && cudaMalloc((void **)&c->d_status, sizeof(int32_t)) == cudaSuccess;
+    // d_status[0]: the noise warm-up flag; d_status[1 ..]: per-SM arrival counters (role rotation, yuv422_kernels.cuh)
+    ok = ok && cudaMalloc((void **)&c->d_status, (size_t)(1 + kSmSlots) * sizeof(int32_t)) == cudaSuccess;
     ok = ok && cudaMallocHost((void **)&c->h_status, sizeof(int32_t)) == cudaSuccess;
-    ok = ok && cudaMemsetAsync(c->d_status, 0, sizeof(int32_t), c->stream) == cudaSuccess;
+    ok = ok && cudaMemsetAsync(c->d_status, 0, (size_t)(1 + kSmSlots) * sizeof(int32_t), c->stream) == cudaSuccess;
     ok = ok && cudaStreamSynchronize(c->stream) == cudaSuccess;
     if (!ok) { free_all(c); delete c; return CVS_ERR_CUDA; }
     *out = c;

@@ -25,9 +25,7 @@ namespace cvs422 {
 #ifndef CVS422_MIN_CTAS
 #define CVS422_MIN_CTAS 5
 #endif
-#ifndef CVS422_ROTATE_ROLES
-#define CVS422_ROTATE_ROLES 0
-#endif
+constexpr int kSmSlots = 256;            // >= SMs of the device (148 on B200)
 // One CTA = one group of 31 consecutive rows (+ the halo lane) = kRoles warps: warp r runs role r (yuv422_pipeline.cuh,
 // "roles") for all rows of the group.  Why (measured on B200, profiles/ab_variants_r2.txt section 6, profiles/probes_r2.txt):
 // a lane that runs every stage of its row needs ~210 registers (35 doubles of filter state), i.e. 2 warps per
@@ -71,6 +69,8 @@ struct Launch422 {
     int32_t halo_pitch, halo_u, halo_v;  // halo record: [Y: w + 2 bytes][U at halo_u][V at halo_v]
     int32_t vec;                         // planes, linesizes and picture strides allow 8 / 4 byte accesses
     int32_t *status;
+    int32_t *sm_slots;                   // kSmSlots arrival counters, one per SM (role_of)
+    int32_t rotate;
 };
 
 // Dynamic shared memory of k_yuv422: the group's rings, then one generator ring per noise stream that is ON
@@ -218,19 +218,33 @@ __device__ __forceinline__ void group_barrier() {
 #endif
 }
 
+// Which role a warp of this group runs.  Warp k of a CTA sits on scheduler k of its SM, and the roles are not equally long
+// (role 2 issues 276 FP64 instructions per step, the others 123; the FP64 pipe takes one warp instruction per two cycles
+// and scheduler): with role = warp, the role-2 warps of all five resident groups share ONE scheduler, whose FP64 pipe is
+// then ~76 % busy while the SM's average is 48 % -- and every other role waits for it at the step barrier.  So the
+// assignment rotates from group to group.  The rotation must differ between the groups RESIDENT ON ONE SM, and the block
+// index does not do that: blocks are dealt to the 148 SMs round robin and 148 is a multiple of 4, so (warp + blockIdx) % 4
+// gives every group of an SM the same assignment (which is why the round-2 experiment with it showed no difference).
+// Each group therefore draws the next number of ITS SM: consecutive arrivals get consecutive rotations.
+__device__ __forceinline__ int role_of(const Launch422 &a, int tid) {
+    __shared__ int s_rot;
+    if (!a.rotate) return tid >> 5;
+    if (tid == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        s_rot = atomicAdd(a.sm_slots + (smid % kSmSlots), 1);
+    }
+    __syncthreads();
+    return ((tid >> 5) + s_rot) % kRoles;
+}
+
 // The general kernel: any width, any switch, pre-pass rows; every step is the general variant of its role
 // (yuv422_pipeline.cuh, "roles").  Rows the fast kernel below can take never come here (launch_yuv422).
 __global__ void __launch_bounds__(kNT, CVS422_MIN_CTAS) k_yuv422(const __grid_constant__ Launch422 a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31;
     const int gw = blockIdx.x;            // the group of rows
-    // Warp k of a CTA sits on scheduler k: with role = warp every role-0 warp of an SM would share ONE scheduler (and
-    // the roles are not equally long), so the assignment rotates with the group.
-#if CVS422_ROTATE_ROLES
-    const int role = ((tid >> 5) + gw) % kRoles;
-#else
-    const int role = tid >> 5;
-#endif
+    const int role = role_of(a, tid);
     const K422 &K = a.K;
     const int w = K.w;
     // which field row this lane computes (lane 0 = the halo row: the row above lane 1's)
@@ -364,14 +378,7 @@ __global__ void __launch_bounds__(kNT, CVS422_MIN_CTAS) k_yuv422_fast(const __gr
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31;
     const int gw = blockIdx.x;
-    // Warp k of a CTA sits on scheduler k, and a role costs about 2 F + N scheduler cycles per step (F FP64, N other
-    // instructions) -- different for every role.  Rotating the assignment with the group gives every scheduler the same
-    // mix; the four loops together fit the SM's instruction cache, so the mix costs nothing there.
-#if CVS422_ROTATE_ROLES
-    const int role = ((tid >> 5) + gw) % kRoles;
-#else
-    const int role = tid >> 5;
-#endif
+    const int role = role_of(a, tid);         // (the four loops together fit the SM's instruction cache: the mix costs nothing there)
     const K422 &K = a.K;
     const int w = K.w;
     int fi, row;
