@@ -127,6 +127,7 @@ struct cvs_ctx {
         size_t off_vcoef = 0, off_hpos = 0, off_hcoef = 0;
     };
     std::vector<YuvBanks> yuv_banks;
+    int sws_rows_kernel = 1;                       // CVS_SWS_ROWS=0: always the one-row kernel (A/B, fallback)
 };
 
 namespace {
@@ -595,6 +596,7 @@ int cvs_create(cvs_ctx **out, const cvs_params *p, int device, int max_w, int ma
         }
     }
     if (const char *e = std::getenv("CVS_PACKED_ROWS")) c->packed_rows = std::atoi(e) != 0;   // experiments / tests
+    if (const char *e = std::getenv("CVS_SWS_ROWS")) c->sws_rows_kernel = std::atoi(e) != 0;
     if (const char *e = std::getenv("CVS_WARM_PX")) {           // tests: a short warm-up makes the first attempt fail
         const int v = std::atoi(e);
         if (v >= 0 && v <= kWarmPx) c->warm_px = v;
@@ -973,8 +975,15 @@ int cvs_scale_to_bgra_device(cvs_ctx *ctx, void *dst, int dst_stride, long long 
         b.n = n;
         const int pairs = dw / 2;
         const dim3 block(pairs < 256 ? ((pairs + 31) / 32) * 32 : 256);
-        const dim3 grid((pairs + block.x - 1) / block.x, dh, n);
-        k_sws_yuv_to_bgra<<<grid, block, 0, ctx->stream>>>(b);
+        // at most two taps per axis and plane (same size or enlarging): the kernel that filters every source row once
+        const bool few_taps = !sp->direct && b.hl_t <= 2 && b.hc_t <= 2 && b.vl_t <= 2 && b.vc_t <= 2 && ctx->sws_rows_kernel;
+        if (few_taps) {
+            const dim3 grid((pairs + block.x - 1) / block.x, (dh + kSwsRows - 1) / kSwsRows, n);
+            k_sws_yuv_to_bgra_rows<<<grid, block, 0, ctx->stream>>>(b);
+        } else {
+            const dim3 grid((pairs + block.x - 1) / block.x, dh, n);
+            k_sws_yuv_to_bgra<<<grid, block, 0, ctx->stream>>>(b);
+        }
         CVS_CUDA(cudaGetLastError());
         ctx->launches++;
         return CVS_OK;

@@ -269,6 +269,100 @@ __global__ void __launch_bounds__(256) k_sws_yuv_to_bgra(const __grid_constant__
     out[0] = sws_pixel(Y0, U, V);
     out[1] = sws_pixel(Y1, U, V);
 }
+
+// The same conversion for the enlarging / same-size geometries (at most two taps per axis and plane), where neighbouring
+// output rows share their source rows: one thread = one pair of output pixels over kSwsRows consecutive output rows.
+// Its horizontal taps stay in registers, and the horizontally filtered samples of the two most recent source rows are
+// kept (the vertical taps of the next output row are the same rows or the next one), so every source row is filtered
+// once per thread instead of once per output row.  Bit for bit the arithmetic of k_sws_yuv_to_bgra.
+constexpr int kSwsRows = 8;
+__global__ void __launch_bounds__(256) k_sws_yuv_to_bgra_rows(const __grid_constant__ SwsScaleArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.z;
+    if (2 * i >= a.dw) return;
+    const int ya = blockIdx.y * kSwsRows, yb = min(ya + kSwsRows, a.dh);
+    const uint8_t *py = a.y + (long long)k * a.sp_y, *pu = a.u + (long long)k * a.sp_c, *pv = a.v + (long long)k * a.sp_c;
+    // horizontal taps of the two pixels and of their chroma sample; a missing second tap re-reads the first with weight 0
+    const int x0 = 2 * i, x1 = 2 * i + 1;
+    const int pl0 = a.hl_pos[x0], pl1 = a.hl_pos[x1], pc = a.hc_pos[i];
+    const int wl0a = a.hl_w[(size_t)x0 * a.hl_t], wl0b = a.hl_t > 1 ? a.hl_w[(size_t)x0 * a.hl_t + 1] : 0;
+    const int wl1a = a.hl_w[(size_t)x1 * a.hl_t], wl1b = a.hl_t > 1 ? a.hl_w[(size_t)x1 * a.hl_t + 1] : 0;
+    const int wca = a.hc_w[(size_t)i * a.hc_t], wcb = a.hc_t > 1 ? a.hc_w[(size_t)i * a.hc_t + 1] : 0;
+    const int dl = a.hl_t > 1 ? 1 : 0, dc = a.hc_t > 1 ? a.cstep : 0;
+    // the two most recent source rows, horizontally filtered (scalars: indexed arrays would live in local memory)
+    int lr0 = -1, lr1 = -1, la0 = 0, la1 = 0, lb0 = 0, lb1 = 0;      // luma: source row, pixel 0, pixel 1
+    int cr0 = -1, cr1 = -1, cu0 = 0, cu1 = 0, cv0 = 0, cv1 = 0;      // chroma
+    auto luma = [&](int r, int &A, int &B) {
+        if (lr0 == r) { A = la0; B = lb0; return; }
+        if (lr1 == r) { A = la1; B = lb1; return; }
+        const uint8_t *row = py + (size_t)r * a.ly;
+        A = min(((int)row[pl0] * wl0a + (int)row[pl0 + dl] * wl0b) >> 7, 32767);
+        B = min(((int)row[pl1] * wl1a + (int)row[pl1 + dl] * wl1b) >> 7, 32767);
+        if (lr0 <= lr1) { lr0 = r; la0 = A; lb0 = B; }             // replace the older row
+        else { lr1 = r; la1 = A; lb1 = B; }
+    };
+    auto chroma = [&](int r, int &U, int &V) {
+        if (cr0 == r) { U = cu0; V = cv0; return; }
+        if (cr1 == r) { U = cu1; V = cv1; return; }
+        const uint8_t *ru = pu + (size_t)r * a.lc + (size_t)pc * a.cstep, *rv = pv + (size_t)r * a.lc + (size_t)pc * a.cstep;
+        U = min(((int)ru[0] * wca + (int)ru[dc] * wcb) >> 7, 32767);
+        V = min(((int)rv[0] * wca + (int)rv[dc] * wcb) >> 7, 32767);
+        if (cr0 <= cr1) { cr0 = r; cu0 = U; cv0 = V; }
+        else { cr1 = r; cu1 = U; cv1 = V; }
+    };
+    for (int y = ya; y < yb; y++) {
+        const int32_t *vl = a.vl_w + (size_t)y * a.vl_t, *vc = a.vc_w + (size_t)y * a.vc_t;
+        const int rl = a.vl_pos[y], rc = a.vc_pos[y];
+        const bool two_c = a.vc_t == 2 && vc[0] + vc[1] == 4096 && vc[1] >= 0 && vc[1] <= 4096;
+        const bool two_l = a.vl_t == 2 && vl[0] + vl[1] == 4096 && vl[1] >= 0 && vl[1] <= 4096;
+        int Y0, Y1, U, V;
+        if (a.vl_t == 1 && (a.vc_t == 1 || two_c)) {
+            int A, B, u0, v0;
+            luma(rl, A, B);
+            Y0 = (A + 64) >> 7;
+            Y1 = (B + 64) >> 7;
+            chroma(rc, u0, v0);
+            if (a.vc_t == 1) {
+                U = (u0 + 64) >> 7;
+                V = (v0 + 64) >> 7;
+            } else {
+                int u1, v1;
+                chroma(rc + 1, u1, v1);
+                const int c = vc[1];
+                U = (u0 * (4096 - c) + u1 * c + (128 << 11)) >> 19;
+                V = (v0 * (4096 - c) + v1 * c + (128 << 11)) >> 19;
+            }
+        } else if (two_l && two_c) {
+            int A0, B0, A1, B1, u0, v0, u1, v1;
+            luma(rl, A0, B0);
+            luma(rl + 1, A1, B1);
+            chroma(rc, u0, v0);
+            chroma(rc + 1, u1, v1);
+            const int l = vl[1], c = vc[1];
+            Y0 = (A0 * (4096 - l) + A1 * l) >> 19;
+            Y1 = (B0 * (4096 - l) + B1 * l) >> 19;
+            U = (u0 * (4096 - c) + u1 * c) >> 19;
+            V = (v0 * (4096 - c) + v1 * c) >> 19;
+        } else {
+            Y0 = Y1 = U = V = 1 << 18;
+            for (int j = 0; j < a.vl_t; j++) {
+                int A, B;
+                luma(rl + j, A, B);
+                Y0 += A * vl[j];
+                Y1 += B * vl[j];
+            }
+            for (int j = 0; j < a.vc_t; j++) {
+                int u0, v0;
+                chroma(rc + j, u0, v0);
+                U += u0 * vc[j];
+                V += v0 * vc[j];
+            }
+            Y0 >>= 19; Y1 >>= 19; U >>= 19; V >>= 19;
+        }
+        uint32_t *out = reinterpret_cast<uint32_t *>(a.dst + (long long)k * a.dst_pic_stride + (long long)y * a.dst_stride) + 2 * i;
+        out[0] = sws_pixel(Y0, U, V);
+        out[1] = sws_pixel(Y1, U, V);
+    }
+}
 #endif
 
 }  // namespace cvs
