@@ -78,7 +78,7 @@ struct cvs422_ctx {
     int next_slot = 0;
     uint8_t *d_scratch = nullptr, *d_halo = nullptr;
     int32_t *d_status = nullptr, *h_status = nullptr;
-    int rotate_roles = 1;              // CVS422_ROTATE=0: warp k of every group runs role k (A/B switch)
+    int rotate_roles = 0;              // CVS422_ROTATE=1: the role assignment rotates from group to group on an SM (measured slower)
     double *d_lut = nullptr;
     int plan_threads = 4;                         // host threads that build the per-row side tables of a batch (CVS_PLAN_THREADS)
     size_t lut_cap = 0;

@@ -218,14 +218,19 @@ __device__ __forceinline__ void group_barrier() {
 #endif
 }
 
-// Which role a warp of this group runs.  Warp k of a CTA sits on scheduler k of its SM, and the roles are not equally long
-// (role 2 issues 276 FP64 instructions per step, the others 123; the FP64 pipe takes one warp instruction per two cycles
-// and scheduler): with role = warp, the role-2 warps of all five resident groups share ONE scheduler, whose FP64 pipe is
-// then ~76 % busy while the SM's average is 48 % -- and every other role waits for it at the step barrier.  So the
-// assignment rotates from group to group.  The rotation must differ between the groups RESIDENT ON ONE SM, and the block
-// index does not do that: blocks are dealt to the 148 SMs round robin and 148 is a multiple of 4, so (warp + blockIdx) % 4
-// gives every group of an SM the same assignment (which is why the round-2 experiment with it showed no difference).
-// Each group therefore draws the next number of ITS SM: consecutive arrivals get consecutive rotations.
+// Which role a warp of this group runs: role = warp, unless the launch asks for a rotation (CVS422_ROTATE=1, an experiment
+// that is kept because its result is the opposite of what the arithmetic suggests).  Warp k of a CTA sits on scheduler k
+// of its SM and the roles are not equally long (role 2 issues 276 FP64 instructions per step, the others 123; the FP64
+// pipe takes one warp instruction per two cycles and scheduler), so with role = warp the role-2 warps of all five
+// resident groups share ONE scheduler, whose FP64 pipe is ~76 % busy while the SM's average is 48 %.  Mixing the roles
+// over the schedulers should even that out.  The block index cannot do it -- blocks are dealt to the 148 SMs round robin
+// and 148 is a multiple of 4, so (warp + blockIdx) % 4 gives every group of an SM the same assignment, which is why the
+// first experiment with it showed no difference -- so a group draws the next number of ITS SM.  Measured (B200, 1080p
+// -vhs -vhs-speed sp, profiles/ab_variants_r2.txt section 7): 83.2 k fields/s rotated against 90.2 k with role = warp.
+// One role per scheduler keeps that scheduler's instruction stream to ONE loop of ~6 KB (each scheduler fetches through
+// its own small L0 instruction cache in front of the SM's 32 KB); four loops per scheduler cost more than the idle FP64
+// cycles they win back.  What would pay instead is equal FP64 work per ROLE (the stages re-dealt: 161 FP64 instructions
+// per role and step instead of 123 / 123 / 276 / 123) with the assignment left alone; DESIGN.md section 9.
 __device__ __forceinline__ int role_of(const Launch422 &a, int tid) {
     __shared__ int s_rot;
     if (!a.rotate) return tid >> 5;
