@@ -741,10 +741,17 @@ def run_own_arm(args):
                 continue
             others[name] = measure_other_bgra(torch, cvs, sharding, timed, dev, local_rank, name, w2, h2, pr2, mb, st2,
                                               args.warmup, peak)
-        others["field_loop_nv12_to_yuv420p_1080p"] = measure_field_loop(torch, cvs, local_rank, 1920, 1080, "sp", 256, 3)
-        others["conversions"] = measure_conversions(torch, cvs, local_rank, peak)
-        others["yuv422_sp_1080p"] = measure_yuv422(torch, timed, dev, local_rank, 1920, 1080, ["-vhs", "-vhs-speed", "sp"],
-                                                   339, st2, args.warmup, peak)
+        # side measurements: a failure here is reported in its key and never takes the headline line with it
+        def side(key, fn):
+            try:
+                others[key] = fn()
+            except Exception as e:      # noqa: BLE001
+                others[key] = {"error": "%s: %s" % (type(e).__name__, e)}
+                torch.cuda.empty_cache()
+        side("field_loop_nv12_to_yuv420p_1080p", lambda: measure_field_loop(torch, cvs, local_rank, 1920, 1080, "sp", 256, 3))
+        side("conversions", lambda: measure_conversions(torch, cvs, local_rank, peak))
+        side("yuv422_sp_1080p", lambda: measure_yuv422(torch, timed, dev, local_rank, 1920, 1080, ["-vhs", "-vhs-speed", "sp"],
+                                                      339, st2, args.warmup, peak))
 
     # ---- CPU baseline: the reference's own code, one thread, median of 3 bounded samples ----
     cpu = None
