@@ -163,3 +163,30 @@ def test_scaler_oracle_equals_golden_outputs_of_libswscale():
         planes = [g["%s_p%d" % (n, i)] for i in range(2 if fmt == "nv12" else 3)]
         got = helpers.oracle_scale_to_bgra(planes, sw, sh, FMT_CODE[fmt], dw, dh)
         assert np.array_equal(got, g[n + "_bgra"]), n
+
+
+@need_lib
+def test_random_geometries_against_the_library():
+    """A seeded sweep over sizes no case above names: 40 scaler geometries (ratios from 1/6 to 6, odd source sizes, tiny
+    pictures) and 20 encoder-side sizes, every format, oracle == library."""
+    rng = np.random.default_rng(20261017)
+    fmts = sorted(FMT_CODE)
+    for k in range(40):
+        sw, sh = int(rng.integers(3, 400)), int(rng.integers(3, 300))
+        dw = 2 * int(rng.integers(max(2, sw // 12), 3 * sw + 2))           # even: the pinned route
+        dh = int(rng.integers(max(2, sh // 6), 6 * sh + 1))
+        dw, dh = min(dw, 1200), min(dh, 900)
+        if sw > 16 * dw or sh > 16 * dh:
+            continue
+        fmt = fmts[k % 3]
+        planes = source_planes(fmt, sw, sh, 1000 + k)
+        want = swscale_ref.scale(planes, fmt, sw, sh, "bgra", dw, dh, c_code=True)[0].view(np.uint32).reshape(dh, dw)
+        got = helpers.oracle_scale_to_bgra(planes, sw, sh, FMT_CODE[fmt], dw, dh)
+        assert np.array_equal(got, want), (fmt, sw, sh, dw, dh, int((got != want).sum()))
+    for k in range(20):
+        w, h = int(rng.integers(3, 500)), int(rng.integers(3, 400))
+        src = picture(w, h, "random", 2000 + k)
+        fmt = ("yuv420p", "yuv422p")[k % 2]
+        want = lib_planes(src, fmt)
+        got = helpers.oracle_bgra_to_yuv(src, fmt == "yuv420p")
+        assert all(np.array_equal(a, b) for a, b in zip(got, want)), (fmt, w, h)
