@@ -858,7 +858,8 @@ int cvs_bgra_to_yuv_device(cvs_ctx *ctx, void *y, int ly, long long y_pic_stride
     } else {
         const int groups = (w + 7) / 8;
         // the streaming kernels want whole 8-pixel groups and aligned rows: what encoders' frames have
-        const bool aligned = (w % 8) == 0 && ((uintptr_t)bgra % 16) == 0 && (stride % 16) == 0 && (bgra_pic_stride % 16) == 0 &&
+        static const bool no_clip = yuv_bounds_ok(yuv_coef_bt601());     // what lets the streaming kernels drop min / max
+        const bool aligned = no_clip && (w % 8) == 0 && ((uintptr_t)bgra % 16) == 0 && (stride % 16) == 0 && (bgra_pic_stride % 16) == 0 &&
                              ((uintptr_t)y % 8) == 0 && (ly % 8) == 0 && (y_pic_stride % 8) == 0 &&
                              ((uintptr_t)u % 4) == 0 && (lu % 4) == 0 && (u_pic_stride % 4) == 0 &&
                              ((uintptr_t)v % 4) == 0 && (lv % 4) == 0 && (v_pic_stride % 4) == 0;

@@ -129,25 +129,41 @@ __global__ void __launch_bounds__(256) k_bgra_to_yuv(const __grid_constant__ Yuv
 }
 
 // ---- the two common cases as streaming kernels ----------------------------------------------------------------------
+// Both are bound by the integer ALU pipe (ncu, profiles/ncu_r2_convert.md), so they drop what the library's arithmetic
+// cannot reach with this matrix: with 0 <= r, g, b <= 255 the 14-bit luma lies in [1024, 15040] and the 14-bit chroma of
+// a pixel pair in [1024, 15360] (yuv_bounds_ok checks exactly that on the host, from the coefficients), so
+// min(2 s14, 32767) never clips, the bytes (s15 + 64) >> 7 = (s14 + 32) >> 6 stay inside [16, 240], and so does a
+// weighted mean of such samples with non-negative weights.  Same bytes, no min / max.
+inline bool yuv_bounds_ok(const YuvCoef &c) {
+    auto lo = [](int a, int b, int d) { return (a < 0 ? a : 0) + (b < 0 ? b : 0) + (d < 0 ? d : 0); };
+    auto hi = [](int a, int b, int d) { return (a > 0 ? a : 0) + (b > 0 ? b : 0) + (d > 0 ? d : 0); };
+    const long long y_lo = ((long long)lo(c.ry, c.gy, c.by) * 255 + (16 << kYuvShift) + 256) >> 9, y_hi = ((long long)hi(c.ry, c.gy, c.by) * 255 + (16 << kYuvShift) + 256) >> 9;
+    const long long u_lo = ((long long)lo(c.ru, c.gu, c.bu) * 510 + (256 << kYuvShift) + 512) >> 10, u_hi = ((long long)hi(c.ru, c.gu, c.bu) * 510 + (256 << kYuvShift) + 512) >> 10;
+    const long long v_lo = ((long long)lo(c.rv, c.gv, c.bv) * 510 + (256 << kYuvShift) + 512) >> 10, v_hi = ((long long)hi(c.rv, c.gv, c.bv) * 510 + (256 << kYuvShift) + 512) >> 10;
+    auto fits = [](long long a, long long b) { return a >= 0 && 2 * b <= 32767 && ((2 * b + 64) >> 7) <= 255; };
+    return fits(y_lo, y_hi) && fits(u_lo, u_hi) && fits(v_lo, v_hi);
+}
 // Shared by both: 8 pixels of one source row -> 8 luma bytes and the 15-bit chroma of the 4 samples they carry.
 struct Yuv8 { uint32_t y0, y1; int u[4], v[4]; };
 __device__ __forceinline__ Yuv8 yuv_row8(const YuvCoef &c, const uint32_t px[8], bool want_luma, bool want_chroma) {
     Yuv8 o;
     o.y0 = o.y1 = 0;
-    if (want_luma) {
+    int b[8], g[8], r[8];
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const uint32_t yv = (uint32_t)yuv_luma(c, px[i]) << (8 * (i & 3));
-            if (i < 4) o.y0 |= yv; else o.y1 |= yv;
-        }
+    for (int i = 0; i < 8; i++) { b[i] = px[i] & 0xFF; g[i] = (px[i] >> 8) & 0xFF; r[i] = (px[i] >> 16) & 0xFF; }
+    if (want_luma) {
+        int y[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) y[i] = (((c.ry * r[i] + c.gy * g[i] + c.by * b[i] + (16 << kYuvShift) + 256) >> 9) + 32) >> 6;
+        o.y0 = (uint32_t)(y[0] + (y[1] << 8) + (y[2] << 16) + (y[3] << 24));
+        o.y1 = (uint32_t)(y[4] + (y[5] << 8) + (y[6] << 16) + (y[7] << 24));
     }
     if (want_chroma) {
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            const uint32_t q0 = px[2 * j], q1 = px[2 * j + 1];
-            const int sb = (q0 & 0xFF) + (q1 & 0xFF), sg = ((q0 >> 8) & 0xFF) + ((q1 >> 8) & 0xFF), sr = ((q0 >> 16) & 0xFF) + ((q1 >> 16) & 0xFF);
-            o.u[j] = min(2 * ((c.ru * sr + c.gu * sg + c.bu * sb + (256 << kYuvShift) + 512) >> 10), 32767);
-            o.v[j] = min(2 * ((c.rv * sr + c.gv * sg + c.bv * sb + (256 << kYuvShift) + 512) >> 10), 32767);
+            const int sb = b[2 * j] + b[2 * j + 1], sg = g[2 * j] + g[2 * j + 1], sr = r[2 * j] + r[2 * j + 1];
+            o.u[j] = 2 * ((c.ru * sr + c.gu * sg + c.bu * sb + (256 << kYuvShift) + 512) >> 10);
+            o.v[j] = 2 * ((c.rv * sr + c.gv * sg + c.bv * sb + (256 << kYuvShift) + 512) >> 10);
         }
     }
     return o;
@@ -169,8 +185,8 @@ __global__ void __launch_bounds__(256) k_bgra_to_yuv422_fast(const __grid_consta
     uint32_t uw = 0, vw = 0;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        uw |= (uint32_t)yuv_clip8((o.u[j] + 64) >> 7) << (8 * j);
-        vw |= (uint32_t)yuv_clip8((o.v[j] + 64) >> 7) << (8 * j);
+        uw |= (uint32_t)((o.u[j] + 64) >> 7) << (8 * j);
+        vw |= (uint32_t)((o.v[j] + 64) >> 7) << (8 * j);
     }
     *reinterpret_cast<uint32_t *>(a.u + (long long)k * a.sp_u + (long long)r * a.lu + gx * 4) = uw;
     *reinterpret_cast<uint32_t *>(a.v + (long long)k * a.sp_v + (long long)r * a.lv + gx * 4) = vw;
@@ -179,8 +195,8 @@ __global__ void __launch_bounds__(256) k_bgra_to_yuv422_fast(const __grid_consta
 // 4:2:0, same conditions.  A block owns 256 pixels x kTileC chroma rows: every source row the tile's vertical taps cover
 // (2 kTileC + 2 of them away from the edges) is loaded ONCE, its luma stored and its 15-bit chroma parked in shared
 // memory; after a barrier each thread weighs the rows of one chroma row.  Source rows are read 1 + 2 / (2 kTileC)
-// times instead of twice, and the chroma matrix runs once per row.  (Measured with kTileC = 8, 18 rows = three passes of
-// which the last is a quarter full: 0.47 of the HBM peak against 0.36 for the general kernel.)
+// times instead of twice, and the chroma matrix runs once per row.  (0.47 of the HBM peak against 0.36 for the general
+// kernel, the same with tiles of 8 or of 7 chroma rows: the kernel is bound by the ALU pipe, 81 % busy, not by its passes.)
 constexpr int kTileC = 7, kTileRows = 2 * kTileC + 4;    // 7 chroma rows need 16 source rows: two full passes of the block's 8 row slots
 __global__ void __launch_bounds__(256) k_bgra_to_yuv420_tiled(const __grid_constant__ YuvArgs a) {
     __shared__ uint4 su[kTileRows][32], sv[kTileRows][32];       // per row and 8-pixel group: u15[4], v15[4]
@@ -221,8 +237,8 @@ __global__ void __launch_bounds__(256) k_bgra_to_yuv420_tiled(const __grid_const
     uint32_t uw = 0, vw = 0;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        uw |= (uint32_t)yuv_clip8(au[j] >> 19) << (8 * j);
-        vw |= (uint32_t)yuv_clip8(av[j] >> 19) << (8 * j);
+        uw |= (uint32_t)(au[j] >> 19) << (8 * j);
+        vw |= (uint32_t)(av[j] >> 19) << (8 * j);
     }
     *reinterpret_cast<uint32_t *>(a.u + (long long)k * a.sp_u + (long long)cy * a.lu + gx * 4) = uw;
     *reinterpret_cast<uint32_t *>(a.v + (long long)k * a.sp_v + (long long)cy * a.lv + gx * 4) = vw;
