@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(256) k_bgra_to_yuv422_fast(const __grid_consta
 // times instead of twice, and the chroma matrix runs once per row.  (0.47 of the HBM peak against 0.36 for the general
 // kernel, the same with tiles of 8 or of 7 chroma rows: the kernel is bound by the ALU pipe, 81 % busy, not by its passes.)
 constexpr int kTileC = 7, kTileRows = 2 * kTileC + 4;    // 7 chroma rows need 16 source rows: two full passes of the block's 8 row slots
-__global__ void __launch_bounds__(256) k_bgra_to_yuv420_tiled(const __grid_constant__ YuvArgs a) {
+__global__ void __launch_bounds__(256, 6) k_bgra_to_yuv420_tiled(const __grid_constant__ YuvArgs a) {
     __shared__ uint4 su[kTileRows][32], sv[kTileRows][32];       // per row and 8-pixel group: u15[4], v15[4]
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 groups x 8 rows
     const int gx = blockIdx.x * 32 + tx, x0 = gx * 8, k = blockIdx.z;
