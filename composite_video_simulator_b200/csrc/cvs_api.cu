@@ -41,7 +41,7 @@ struct ScalePlan {
     size_t off_first[4] = {0, 0, 0, 0}, off_w[4] = {0, 0, 0, 0};
     int taps[4] = {0, 0, 0, 0};
     // the libswscale-exact path (k_sws_yuv_to_bgra): four banks in one allocation, pos then weights per bank
-    bool sws = false, direct = false;
+    bool sws = false, direct = false, full = false;
     int32_t *d_sws = nullptr;
     size_t sws_pos[4] = {0, 0, 0, 0}, sws_w[4] = {0, 0, 0, 0};
     int sws_taps[4] = {0, 0, 0, 0};
@@ -916,11 +916,12 @@ int cvs_scale_to_bgra_device(cvs_ctx *ctx, void *dst, int dst_stride, long long 
         std::unique_ptr<ScalePlan> q(new (std::nothrow) ScalePlan());
         if (!q) return CVS_ERR_NOMEM;
         q->dw = dw; q->dh = dh; q->sw = sw; q->sh = sh; q->format = format;
-        // planar YUV to an even width: libswscale's own banks (sws_filter.cpp); otherwise the repository's resampler
-        q->sws = format != CVS_PIX_BGRA && (dw & 1) == 0;
-        q->direct = q->sws && format == CVS_PIX_YUV420P && sw == dw && sh == dh && (dh & 1) == 0;
+        // planar YUV: libswscale's own banks (sws_filter.cpp); BGRA sources: the repository's resampler
+        q->sws = format != CVS_PIX_BGRA;
+        q->full = q->sws && (dw & 1) != 0;         // odd width: the library's full-chroma writers, one chroma sample per pixel
+        q->direct = q->sws && !q->full && format == CVS_PIX_YUV420P && sw == dw && sh == dh && (dh & 1) == 0;
         if (q->sws && !q->direct) {
-            const FilterBank banks[4] = {bilinear_bank(sw, dw, 1 << 14), bilinear_bank(cw, (dw + 1) / 2, 1 << 14),
+            const FilterBank banks[4] = {bilinear_bank(sw, dw, 1 << 14), bilinear_bank(cw, q->full ? dw : (dw + 1) / 2, 1 << 14),
                                          bilinear_bank(sh, dh, 1 << 12), bilinear_bank(ch, dh, 1 << 12)};
             const int srcn[4] = {sw, cw, sh, ch};
             std::vector<int32_t> blob;
@@ -974,6 +975,14 @@ int cvs_scale_to_bgra_device(cvs_ctx *ctx, void *dst, int dst_stride, long long 
         b.vl_pos = t + sp->sws_pos[2]; b.vl_w = t + sp->sws_w[2]; b.vc_pos = t + sp->sws_pos[3]; b.vc_w = t + sp->sws_w[3];
         b.hl_t = sp->sws_taps[0]; b.hc_t = sp->sws_taps[1]; b.vl_t = sp->sws_taps[2]; b.vc_t = sp->sws_taps[3];
         b.n = n;
+        if (sp->full) {
+            const dim3 block(dw < 256 ? ((dw + 31) / 32) * 32 : 256);
+            const dim3 grid((dw + block.x - 1) / block.x, dh, n);
+            k_sws_yuv_to_bgra_full<<<grid, block, 0, ctx->stream>>>(b);
+            CVS_CUDA(cudaGetLastError());
+            ctx->launches++;
+            return CVS_OK;
+        }
         const int pairs = dw / 2;
         const dim3 block(pairs < 256 ? ((pairs + 31) / 32) * 32 : 256);
         // at most two taps per axis and plane (same size or enlarging): the kernel that filters every source row once

@@ -4,7 +4,7 @@
 //
 // Two kernels:
 //
-//  k_sws_yuv_to_bgra   YUV420P / YUV422P / NV12 sources, even output width: the bytes of libswscale's C code (9.1.100;
+//  k_sws_yuv_to_bgra   YUV420P / YUV422P / NV12 sources: the bytes of libswscale's C code (9.1.100;
 //      = SWS_ACCURATE_RND | SWS_BITEXACT).  PINNED: oracle/convert_oracle.c restates the library and is compared with it
 //      byte for byte (tests/test_swscale_pin.py); the kernel is compared with the oracle, the library and its committed
 //      outputs (tests/test_gpu_scale.py).  All integer:
@@ -21,11 +21,13 @@
 //        exception    YUV420P at the same size and an even height: the library's direct converter, no filtering, the chroma
 //                     sample of a 2x2 block serves its four pixels.
 //      One thread = one pair of output pixels; it filters the few source samples it needs itself (2 x 2 taps when
-//      enlarging), so no intermediate picture exists.
+//      enlarging), so no intermediate picture exists.  Odd output widths take the library's other writers
+//      (k_sws_yuv_to_bgra_full, further down).
 //
-//  k_scale_to_bgra     BGRA sources and odd output widths (the library then takes other routes -- an RGB -> YUV -> RGB
-//      round trip, its full-chroma-interpolation writers -- which are not restated): the repository's OWN resampler,
-//      NOT pinned, specified here and restated independently in oracle/convert_oracle.c:
+//  k_scale_to_bgra     BGRA sources at another size (the library scales packed RGB through a cascade over planar RGB with a
+//      high-precision YUV round trip inside, which is not restated): the repository's OWN resampler, NOT pinned -- measured
+//      against the library: +-1 per colour channel on 3 - 14 % of the values when enlarging, more when shrinking (the library
+//      halves the chroma of the round trip there) -- specified here and restated independently in oracle/convert_oracle.c:
 //  * per axis, destination sample i of n_dst takes its value at source position P / D (centre aligned),
 //        D = 2 n_dst sub,   P = (2 i + 1) n_src - n_dst - off n_dst,
 //    n_src the LUMA size of the source along the axis, sub = 1 for luma / BGRA planes and 2 for a subsampled chroma
@@ -268,6 +270,61 @@ __global__ void __launch_bounds__(256) k_sws_yuv_to_bgra(const __grid_constant__
     }
     out[0] = sws_pixel(Y0, U, V);
     out[1] = sws_pixel(Y1, U, V);
+}
+
+// Odd output widths: the library turns on full horizontal chroma interpolation -- chroma is scaled to dw samples, one per
+// pixel -- and writes with 32-bit integer arithmetic instead of its tables (output.c yuv2rgb_full_{1,2,X}_c_template +
+// yuv2rgb_write_full): samples at 2^9 per code, chroma minus 128;
+//     Y' = (Y - 8192) 9539 + 2^21;  R = Y' + 13075 V;  G = Y' - 6660 V - 3209 U;  B = Y' + 16525 U     (mod 2^32),
+// clipped to 30 bits when any of the three leaves that range, >> 22.  The sums wrap at 32 bits BEFORE the clip, so a
+// far-out-of-gamut sample (Y = U = 255) comes out 0 where 255 would be expected: the library's behaviour, reproduced.
+// One thread = one output pixel.  (Encoders do not take odd widths; this exists so that every size gives the library's bytes.)
+__device__ __forceinline__ int sws_clip30(int a) { return (a & ~((1 << 30) - 1)) ? ((~a) >> 31) & ((1 << 30) - 1) : a; }
+__device__ __forceinline__ uint32_t sws_pixel_full(int Y, int U, int V) {
+    const uint32_t y = (uint32_t)(Y - 8192) * 9539u + (1u << 21);
+    int R = (int)(y + (uint32_t)V * 13075u);
+    int G = (int)(y + (uint32_t)V * (uint32_t)-6660 + (uint32_t)U * (uint32_t)-3209);
+    int B = (int)(y + (uint32_t)U * 16525u);
+    if ((R | G | B) & 0xC0000000) { R = sws_clip30(R); G = sws_clip30(G); B = sws_clip30(B); }
+    return 0xFF000000u | ((uint32_t)(R >> 22) << 16) | ((uint32_t)(G >> 22) << 8) | (uint32_t)(B >> 22);
+}
+__global__ void __launch_bounds__(256) k_sws_yuv_to_bgra_full(const __grid_constant__ SwsScaleArgs a) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, k = blockIdx.z;
+    if (x >= a.dw) return;
+    const uint8_t *py = a.y + (long long)k * a.sp_y, *pu = a.u + (long long)k * a.sp_c, *pv = a.v + (long long)k * a.sp_c;
+    const int32_t *wl = a.hl_w + (size_t)x * a.hl_t, *wc = a.hc_w + (size_t)x * a.hc_t;      // the chroma bank has dw entries here
+    const int pl = a.hl_pos[x], pc = a.hc_pos[x];
+    const int32_t *vl = a.vl_w + (size_t)y * a.vl_t, *vc = a.vc_w + (size_t)y * a.vc_t;
+    const int rl = a.vl_pos[y], rc = a.vc_pos[y];
+    const bool two_c = a.vc_t == 2 && vc[0] + vc[1] == 4096 && vc[1] >= 0 && vc[1] <= 4096;
+    const bool two_l = a.vl_t == 2 && vl[0] + vl[1] == 4096 && vl[1] >= 0 && vl[1] <= 4096;
+    auto L = [&](int r) { return sws_h15(py + (size_t)(rl + r) * a.ly, 1, wl, pl, a.hl_t); };
+    auto CU = [&](int r) { return sws_h15(pu + (size_t)(rc + r) * a.lc, a.cstep, wc, pc, a.hc_t); };
+    auto CV = [&](int r) { return sws_h15(pv + (size_t)(rc + r) * a.lc, a.cstep, wc, pc, a.hc_t); };
+    int Y, U, V;
+    if (a.vl_t == 1 && (a.vc_t == 1 || two_c)) {
+        Y = L(0) * 4;
+        if (a.vc_t == 1) {
+            U = (CU(0) - (128 << 7)) * 4;
+            V = (CV(0) - (128 << 7)) * 4;
+        } else {
+            const int c = vc[1];
+            U = (CU(0) * (4096 - c) + CU(1) * c - (128 << 19)) >> 10;
+            V = (CV(0) * (4096 - c) + CV(1) * c - (128 << 19)) >> 10;
+        }
+    } else if (two_l && two_c) {
+        const int l = vl[1], c = vc[1];
+        Y = (L(0) * (4096 - l) + L(1) * l) >> 10;
+        U = (CU(0) * (4096 - c) + CU(1) * c - (128 << 19)) >> 10;
+        V = (CV(0) * (4096 - c) + CV(1) * c - (128 << 19)) >> 10;
+    } else {
+        Y = 1 << 9;
+        U = V = (1 << 9) - (128 << 19);
+        for (int j = 0; j < a.vl_t; j++) if (vl[j] != 0) Y += L(j) * vl[j];
+        for (int j = 0; j < a.vc_t; j++) if (vc[j] != 0) { U += CU(j) * vc[j]; V += CV(j) * vc[j]; }
+        Y >>= 10; U >>= 10; V >>= 10;
+    }
+    reinterpret_cast<uint32_t *>(a.dst + (long long)k * a.dst_pic_stride + (long long)y * a.dst_stride)[x] = sws_pixel_full(Y, U, V);
 }
 
 // The same conversion for the enlarging / same-size geometries (at most two taps per axis and plane), where neighbouring

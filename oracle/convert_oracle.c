@@ -86,7 +86,7 @@ static void swsfilter_free(swsfilter *f);
  *
  * PINNED against libswscale 9.1.100 (tests/test_swscale_pin.py: sws_getContext(sw, sh, YUV420P | YUV422P | NV12, dw, dh,
  * BGRA, SWS_BILINEAR, NULL, NULL, NULL) + sws_scale(), the reference's call at ffmpeg_ntsc.cpp:574-585, 603-610, library
- * C code) for EVEN destination widths.  What the library does (its function names, for orientation):
+ * C code).  What the library does for EVEN destination widths (its function names, for orientation; odd ones further down):
  *   horizontal  swscale.c hScale8To15_c: every source row of Y to dw samples, of U and V to ceil(dw/2) samples -- the
  *               library keeps ONE chroma sample per pair of output pixels -- with the bilinear banks of utils.c
  *               initFilter (14-bit weights), s15 = min(sum >> 7, 32767);
@@ -102,9 +102,8 @@ static void swsfilter_free(swsfilter *f);
  *               k = Y + (c' C >> 16) - (c' >> 9) (both chroma terms for G), C clipped to 0..255; alpha = 255.
  *   exception   YUV420P at the SAME size with an even height takes the library's direct converter (yuv2rgb.c
  *               yuv2rgb_c_32): no filtering at all, the chroma sample of a 2x2 block serves its four pixels.
- * Odd destination widths make the library switch to its full-chroma-interpolation routines and BGRA sources go through
- * an RGB -> YUV -> RGB round trip inside the library; neither is restated: those cases use this repository's own
- * resampler below (NOT pinned, stated in include/cvs_ntsc.h).
+ * BGRA sources at another size go through an RGB -> YUV -> RGB round trip inside the library, which is not restated: that
+ * case uses this repository's own resampler below (NOT pinned, stated in include/cvs_ntsc.h).
  */
 static int sws_rgb_k(long long k) {
     const long long cy = (65536LL * 255) / 219;
@@ -134,12 +133,30 @@ static int *sws_hscale(const uint8_t *plane, int linesize, int step, int rows, c
         }
     return out;
 }
+/* Odd destination widths: the library turns on full horizontal chroma interpolation (utils.c, "Forcing full internal H
+ * chroma due to odd output size"): chroma is scaled to dw samples and the writers are output.c yuv2rgb_full_{1,2,X}_c_template
+ * + yuv2rgb_write_full -- no tables but 32-bit integer arithmetic with the coefficients of yuv2rgb.c rounded to 16 bits
+ * (y 9539, offset 8192, V->R 13075, V->G -6660, U->G -3209, U->B 16525), on samples at 2^9 per code:
+ *     Y' = (Y - 8192) 9539 + 2^21;  R = Y' + V 13075;  G = Y' + V (-6660) + U (-3209);  B = Y' + U 16525   (mod 2^32)
+ * clipped to 30 bits when any of them leaves that range, then >> 22.  The sums wrap at 32 bits before they are clipped, so
+ * a far-out-of-gamut sample (Y = U = 255) comes out 0 where 255 would be expected: the library's behaviour, kept. */
+static int clip_uintp2_30(int32_t a) { return (a & ~((1 << 30) - 1)) ? ((~a) >> 31) & ((1 << 30) - 1) : a; }
+static uint32_t sws_pixel_full(int Y, int U, int V) {
+    const uint32_t y = (uint32_t)(Y - 8192) * 9539u + (1u << 21);
+    int32_t R = (int32_t)(y + (uint32_t)V * 13075u);
+    int32_t G = (int32_t)(y + (uint32_t)V * (uint32_t)-6660 + (uint32_t)U * (uint32_t)-3209);
+    int32_t B = (int32_t)(y + (uint32_t)U * 16525u);
+    if ((R | G | B) & 0xC0000000) { R = clip_uintp2_30(R); G = clip_uintp2_30(G); B = clip_uintp2_30(B); }
+    return 0xFF000000u | ((uint32_t)(R >> 22) << 16) | ((uint32_t)(G >> 22) << 8) | (uint32_t)(B >> 22);
+}
+
 static int sws_yuv_to_bgra(uint8_t *dst, int dst_stride, int dw, int dh, const uint8_t *p0, const uint8_t *p1, const uint8_t *p2,
                            int l0, int l1, int l2, int sw, int sh, int format) {
-    const int cw = (sw + 1) / 2, ch = (format == 2) ? sh : (sh + 1) / 2, cdw = (dw + 1) / 2;
+    const int full = dw & 1;                                   /* full horizontal chroma: one chroma sample per pixel */
+    const int cw = (sw + 1) / 2, ch = (format == 2) ? sh : (sh + 1) / 2, cdw = full ? dw : (dw + 1) / 2;
     const uint8_t *pu = p1, *pv = (format == 3) ? p1 + 1 : p2;
     const int lu = l1, lv = (format == 3) ? l1 : l2, cstep = (format == 3) ? 2 : 1;
-    if (format == 1 && sw == dw && sh == dh && (dh & 1) == 0) {            /* the direct converter */
+    if (format == 1 && sw == dw && sh == dh && (dh & 1) == 0 && !full) {   /* the direct converter */
         for (int y = 0; y < dh; y++)
             for (int x = 0; x < dw; x++)
                 ((uint32_t *)(dst + (size_t)y * (size_t)dst_stride))[x] =
@@ -163,7 +180,28 @@ static int sws_yuv_to_bgra(uint8_t *dst, int dst_stride, int dw, int dh, const u
         else if (two_l && two_c) mode = 2;
         else mode = 3;
         uint32_t *row = (uint32_t *)(dst + (size_t)y * (size_t)dst_stride);
-        for (int x = 0; x < dw; x++) {
+        for (int x = 0; x < dw && full; x++) {                 /* yuv2rgb_full_{1,2,X}: samples at 2^9 per code, chroma minus 128 */
+            int Y, U, V;
+            if (mode == 0 || mode == 1) {
+                const int a = mode == 1 ? cwt[1] : 0;
+                Y = l_[x] * 4;
+                U = mode == 1 ? (u_[x] * (4096 - a) + u_[cdw + x] * a - (128 << 19)) >> 10 : (u_[x] - (128 << 7)) * 4;
+                V = mode == 1 ? (v_[x] * (4096 - a) + v_[cdw + x] * a - (128 << 19)) >> 10 : (v_[x] - (128 << 7)) * 4;
+            } else if (mode == 2) {
+                const int a = lw[1], c = cwt[1];
+                Y = (l_[x] * (4096 - a) + l_[dw + x] * a) >> 10;
+                U = (u_[x] * (4096 - c) + u_[cdw + x] * c - (128 << 19)) >> 10;
+                V = (v_[x] * (4096 - c) + v_[cdw + x] * c - (128 << 19)) >> 10;
+            } else {
+                Y = 1 << 9;
+                U = V = (1 << 9) - (128 << 19);
+                for (int j = 0; j < vl.size; j++) Y += l_[(size_t)j * dw + x] * lw[j];
+                for (int j = 0; j < vc.size; j++) { U += u_[(size_t)j * cdw + x] * cwt[j]; V += v_[(size_t)j * cdw + x] * cwt[j]; }
+                Y >>= 10; U >>= 10; V >>= 10;
+            }
+            row[x] = sws_pixel_full(Y, U, V);
+        }
+        for (int x = 0; x < dw && !full; x++) {
             const int i = x >> 1;
             int Y, U, V;
             if (mode == 0) {
@@ -198,7 +236,7 @@ int oracle_scale_to_bgra(uint8_t *dst, int dst_stride, int dw, int dh,
                          int sw, int sh, int format) {
     if (!dst || !p0 || dw <= 0 || dh <= 0 || sw <= 0 || sh <= 0 || format < 0 || format > 3) return -1;
     if (sw > 16 * dw || sh > 16 * dh) return -5;          /* more taps than the tables hold */
-    if (format != 0 && (dw & 1) == 0) return sws_yuv_to_bgra(dst, dst_stride, dw, dh, p0, p1, p2, l0, l1, l2, sw, sh, format);
+    if (format != 0) return sws_yuv_to_bgra(dst, dst_stride, dw, dh, p0, p1, p2, l0, l1, l2, sw, sh, format);
     const int cw = (sw + 1) / 2, ch = (format == 2) ? sh : (sh + 1) / 2;
     const int suby = (format == 2) ? 1 : 2, offy = (format == 2) ? 0 : 1;
     for (int y = 0; y < dh; y++) {

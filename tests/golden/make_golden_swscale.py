@@ -27,7 +27,8 @@ print("wrote", len(out), "arrays, libswscale", swscale_ref.version())
 # the input side: sws_getContext(sw, sh, fmt, dw, dh, BGRA, SWS_BILINEAR, ...) + sws_scale (ffmpeg_ntsc.cpp:574-585, 603-610)
 out = {}
 for fmt in ("yuv420p", "yuv422p", "nv12"):
-    for sw, sh, dw, dh in ((64, 48, 64, 48), (64, 47, 64, 47), (40, 30, 64, 48), (176, 144, 64, 48), (90, 72, 64, 48), (33, 21, 80, 60)):
+    for sw, sh, dw, dh in ((64, 48, 64, 48), (64, 47, 64, 47), (40, 30, 64, 48), (176, 144, 64, 48), (90, 72, 64, 48), (33, 21, 80, 60),
+                           (40, 30, 65, 48), (64, 48, 63, 48), (176, 144, 65, 47)):       # (odd widths: the full-chroma writers)
         shapes = swscale_ref.plane_shapes(fmt, sw, sh)
         planes = [rng.integers(0, 256, size=s, dtype=np.uint8) for s in shapes]
         bgra = swscale_ref.scale(planes, fmt, sw, sh, "bgra", dw, dh, c_code=True)[0].view(np.uint32).reshape(dh, dw)

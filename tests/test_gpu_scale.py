@@ -1,8 +1,8 @@
 """cvs_scale_to_bgra_device (the input side: InputFile::frame_copy_scale(), ffmpeg_ntsc.cpp:544-613):
-decoder picture -> BGRA at the output size on the device.  Planar YUV sources to an even output width are PINNED:
+decoder picture -> BGRA at the output size on the device.  Planar YUV sources are PINNED (even and odd output widths):
 the kernel is compared bit for bit with oracle/convert_oracle.c (which tests/test_swscale_pin.py pins against libswscale
-9.1.100 itself), with the library directly when the GPU box has it, and with its committed outputs.  BGRA sources and
-odd output widths use the repository's own resampler (not pinned; same oracle file, restated from its specification)."""
+9.1.100 itself), with the library directly when the GPU box has it, and with its committed outputs.  BGRA sources at
+another size use the repository's own resampler (not pinned; same oracle file, restated from its specification)."""
 import os
 
 import numpy as np
@@ -60,7 +60,8 @@ FMT_NAME = {YUV420P: "yuv420p", YUV422P: "yuv422p", NV12: "nv12"}
 
 @pytest.mark.skipif(not swscale_ref.available(), reason="no libswscale on this machine (golden fixtures cover it)")
 @pytest.mark.parametrize("sw,sh,dw,dh", [(720, 480, 720, 480), (720, 481, 720, 481), (640, 480, 720, 480), (352, 288, 720, 480),
-                                         (1920, 1080, 720, 480), (720, 576, 720, 480), (1280, 720, 1920, 1080), (351, 287, 720, 480)])
+                                         (1920, 1080, 720, 480), (720, 576, 720, 480), (1280, 720, 1920, 1080), (351, 287, 720, 480),
+                                         (640, 480, 721, 480), (353, 289, 353, 289), (1920, 1080, 721, 481)])   # odd widths
 @pytest.mark.parametrize("fmt", [YUV420P, YUV422P, NV12])
 def test_scaler_equals_libswscale_itself(sw, sh, dw, dh, fmt):
     """sws_getContext(sw, sh, fmt, dw, dh, BGRA, SWS_BILINEAR, ...) + sws_scale() of the library on this machine (its C

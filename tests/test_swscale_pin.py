@@ -1,7 +1,7 @@
 """The two picture conversions either side of the hot path PINNED against libswscale itself:
   * encoder side (ffmpeg_ntsc.cpp:2118-2131, 2266-2274): sws_getContext(w, h, BGRA -> YUV420P | YUV422P, SWS_BILINEAR) + sws_scale;
   * input side, InputFile::frame_copy_scale (:574-585, 603-610): sws_getContext(sw, sh, YUV420P | YUV422P | NV12 -> dw, dh,
-    BGRA, SWS_BILINEAR) + sws_scale, for even destination widths.
+    BGRA, SWS_BILINEAR) + sws_scale (even destination widths: the table writers; odd ones: the full-chroma writers).
 oracle/convert_oracle.c restates what the library's portable C code does for those calls; here it is compared byte
 for byte with the library (libswscale 9.1.100 of this image, tests/swscale_ref.py) where that exists, and with outputs
 of the library committed as tests/golden/swscale_*.npz everywhere."""
@@ -119,7 +119,10 @@ def test_product_filter_bank_equals_the_oracles():
 # ---- the input side ---------------------------------------------------------------------------------------------
 FMT_CODE = {"yuv420p": 1, "yuv422p": 2, "nv12": 3}          # the product's CVS_PIX_* / the oracle's format argument
 SCALES = [(720, 480, 720, 480), (720, 481, 720, 481), (640, 480, 720, 480), (352, 288, 720, 480), (1920, 1080, 720, 480),
-          (720, 576, 720, 480), (720, 480, 360, 240), (351, 287, 720, 480), (20, 10, 320, 240), (5, 3, 8, 8), (1280, 720, 1920, 1080)]
+          (720, 576, 720, 480), (720, 480, 360, 240), (351, 287, 720, 480), (20, 10, 320, 240), (5, 3, 8, 8), (1280, 720, 1920, 1080),
+          # odd destination widths: the library's full-chroma-interpolation writers (32-bit arithmetic, no tables)
+          (352, 288, 721, 480), (353, 289, 353, 289), (640, 480, 721, 480), (1920, 1080, 721, 480), (720, 576, 719, 480),
+          (720, 480, 361, 240), (5, 3, 9, 8)]
 
 
 def source_planes(fmt, w, h, seed, legal=False):
@@ -173,7 +176,7 @@ def test_random_geometries_against_the_library():
     fmts = sorted(FMT_CODE)
     for k in range(40):
         sw, sh = int(rng.integers(3, 400)), int(rng.integers(3, 300))
-        dw = 2 * int(rng.integers(max(2, sw // 12), 3 * sw + 2))           # even: the pinned route
+        dw = 2 * int(rng.integers(max(2, sw // 12), 3 * sw + 2)) + (k % 4 == 3)     # every fourth one odd
         dh = int(rng.integers(max(2, sh // 6), 6 * sh + 1))
         dw, dh = min(dw, 1200), min(dh, 900)
         if sw > 16 * dw or sh > 16 * dh:
