@@ -188,7 +188,7 @@ int  cvs_sws_bilinear_bank(int srcn, int dstn, int one, int32_t *pos, int32_t *c
  * The line doubling leaves row h-1 of an even-height picture of field 0 as the frame ring had it (:2247): the context
  * keeps that row from call to call (the default ring of one picture, `-d 1`), starting from the zeroed ring (:2069-2092).
  * Conversions as specified at cvs_scale_to_bgra_device and cvs_bgra_to_yuv_device (libswscale's bytes for planar YUV
- * sources and even widths); the composite_layer() step is the pinned hot path.  Synchronous; the rand() position advances as for n
+ * sources); the composite_layer() step is the pinned hot path.  Synchronous; the rand() position advances as for n
  * cvs_composite_layer() calls.
  */
 typedef struct cvs_field_loop {
@@ -231,15 +231,19 @@ void cvs_audio_destroy(cvs_audio *a);
  *   format     CVS_PIX_BGRA (src[0]), CVS_PIX_YUV420P / CVS_PIX_YUV422P (src[0..2] = Y, U, V; chroma planes are
  *              ceil(sw/2) wide and ceil(sh/2) / sh high), CVS_PIX_NV12 (src[0] = Y, src[1] = interleaved UV)
  *   dst        n BGRA pictures, dw x dh, rows dst_stride bytes (multiple of 4), pictures dst_pic_stride bytes apart
- * Planar YUV sources (CVS_PIX_YUV420P / YUV422P / NV12; U and V planes of one layout) to an EVEN dw: PINNED against
- * libswscale -- the bytes of the library's own C code (= SWS_ACCURATE_RND | SWS_BITEXACT) for sws_getContext(sw, sh, fmt,
- * dw, dh, BGRA, SWS_BILINEAR, ...): its bilinear banks, one chroma sample per pair of output pixels, its vertical
- * dispatch by tap counts, its ITU-R 601 colour tables, alpha 255, and its direct converter (no filtering) for YUV420P at
- * the same size with an even height (csrc/scale_convert.cuh states the arithmetic; checked against libswscale 9.1.100,
- * tests/test_swscale_pin.py; the library's x86 SIMD converter differs from its C code by up to 3 codes).
- * CVS_PIX_BGRA sources and odd dw: the repository's own resampler, NOT pinned (triangle kernel with 14-bit weights,
- * centre-aligned, 15-bit intermediate; BT.601 limited range -> full-range RGB; a BGRA source of the output size is
- * copied, as the library does), specified in the same header and restated independently in oracle/convert_oracle.c.
+ * Planar YUV sources (CVS_PIX_YUV420P / YUV422P / NV12; U and V planes of one layout): PINNED against libswscale -- the
+ * bytes of the library's own C code (= SWS_ACCURATE_RND | SWS_BITEXACT) for sws_getContext(sw, sh, fmt, dw, dh, BGRA,
+ * SWS_BILINEAR, ...).  Even dw: its bilinear banks, one chroma sample per pair of output pixels, its vertical dispatch
+ * by tap counts, its ITU-R 601 colour tables, and its direct converter (no filtering) for YUV420P at the same size with
+ * an even height.  Odd dw: its full-chroma-interpolation writers (one chroma sample per pixel, 32-bit integer matrix,
+ * including their wrap-around for far-out-of-gamut samples).  Alpha 255.  (csrc/scale_convert.cuh states the arithmetic;
+ * checked against libswscale 9.1.100, tests/test_swscale_pin.py; the library's x86 SIMD converter differs from its C code
+ * by up to 3 codes.)
+ * CVS_PIX_BGRA sources: a source of the output size is copied, as the library does; at another size the repository's
+ * own resampler, NOT pinned (triangle kernel with 14-bit weights, centre-aligned, 15-bit intermediate, channel by
+ * channel; measured against the library, which scales packed RGB through a planar-RGB cascade: +-1 per colour channel on
+ * 3 - 14 % of the values when enlarging, more when shrinking), specified in the same header and restated independently
+ * in oracle/convert_oracle.c.
  * Shrinking by more than 16x per axis returns CVS_ERR_CAPACITY.
  */
 enum { CVS_PIX_BGRA = 0, CVS_PIX_YUV420P = 1, CVS_PIX_YUV422P = 2, CVS_PIX_NV12 = 3 };
