@@ -42,6 +42,7 @@ struct ScalePlan {
     int taps[4] = {0, 0, 0, 0};
     // the libswscale-exact path (k_sws_yuv_to_bgra): four banks in one allocation, pos then weights per bank
     bool sws = false, direct = false, full = false;
+    bool rgb = false, rgb_half = false;          // BGRA source at another size through the library's route (k_sws_bgra_to_bgra)
     int32_t *d_sws = nullptr;
     size_t sws_pos[4] = {0, 0, 0, 0}, sws_w[4] = {0, 0, 0, 0};
     int sws_taps[4] = {0, 0, 0, 0};
@@ -920,6 +921,24 @@ int cvs_scale_to_bgra_device(cvs_ctx *ctx, void *dst, int dst_stride, long long 
         q->sws = format != CVS_PIX_BGRA;
         q->full = q->sws && (dw & 1) != 0;         // odd width: the library's full-chroma writers, one chroma sample per pixel
         q->direct = q->sws && !q->full && format == CVS_PIX_YUV420P && sw == dw && sh == dh && (dh & 1) == 0;
+        // BGRA at another size: the library's RGB -> YUV(A) -> RGB route, except the one geometry it reads past the row for
+        q->rgb = format == CVS_PIX_BGRA && (sw != dw || sh != dh) && !((sw & 1) && dw <= (sw >> 1));
+        q->rgb_half = q->rgb && dw <= (sw >> 1);
+        if (q->rgb) {
+            const int ccw = q->rgb_half ? sw / 2 : sw;
+            const FilterBank banks[3] = {bilinear_bank(sw, dw, 1 << 14), bilinear_bank(ccw, dw, 1 << 14), bilinear_bank(sh, dh, 1 << 12)};
+            const int srcn[3] = {sw, ccw, sh};
+            std::vector<int32_t> blob;
+            for (int i = 0; i < 3; i++) {
+                for (int32_t v : banks[i].pos) if (v < 0 || v + banks[i].taps > srcn[i]) return CVS_ERR_UNSUPPORTED;
+                q->sws_taps[i] = banks[i].taps;
+                q->sws_pos[i] = blob.size(); blob.insert(blob.end(), banks[i].pos.begin(), banks[i].pos.end());
+                q->sws_w[i] = blob.size(); blob.insert(blob.end(), banks[i].coef.begin(), banks[i].coef.end());
+            }
+            CVS_CUDA(dev_alloc(&q->d_sws, blob.size()));
+            CVS_CUDA(cudaMemcpyAsync(q->d_sws, blob.data(), blob.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+            CVS_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
         if (q->sws && !q->direct) {
             const FilterBank banks[4] = {bilinear_bank(sw, dw, 1 << 14), bilinear_bank(cw, q->full ? dw : (dw + 1) / 2, 1 << 14),
                                          bilinear_bank(sh, dh, 1 << 12), bilinear_bank(ch, dh, 1 << 12)};
@@ -935,7 +954,7 @@ int cvs_scale_to_bgra_device(cvs_ctx *ctx, void *dst, int dst_stride, long long 
             CVS_CUDA(cudaMemcpyAsync(q->d_sws, blob.data(), blob.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
             CVS_CUDA(cudaStreamSynchronize(ctx->stream));
         }
-        if (!q->sws) {
+        if (!q->sws && !q->rgb) {
         ScaleAxis ax[4];
         const int suby = format == CVS_PIX_YUV422P ? 1 : 2;
         scale_build_axis(dw, sw, 1, 0, ax[0]);
@@ -959,6 +978,23 @@ int cvs_scale_to_bgra_device(cvs_ctx *ctx, void *dst, int dst_stride, long long 
         }
         sp = q.get();
         ctx->scale_plans.push_back(std::move(q));
+    }
+    if (sp->rgb) {
+        SwsRgbArgs r;
+        r.dst = (uint8_t *)dst; r.dst_pic_stride = dst_pic_stride; r.dst_stride = dst_stride; r.dw = dw; r.dh = dh;
+        r.src = (const uint8_t *)src[0]; r.sp = src_pic_stride[0]; r.ls = src_linesize[0]; r.half = sp->rgb_half;
+        const int32_t *t = sp->d_sws;
+        r.hl_pos = t + sp->sws_pos[0]; r.hl_w = t + sp->sws_w[0]; r.hc_pos = t + sp->sws_pos[1]; r.hc_w = t + sp->sws_w[1];
+        r.v_pos = t + sp->sws_pos[2]; r.v_w = t + sp->sws_w[2];
+        r.hl_t = sp->sws_taps[0]; r.hc_t = sp->sws_taps[1]; r.v_t = sp->sws_taps[2];
+        const YuvCoef c = yuv_coef_bt601();
+        r.ry = c.ry; r.gy = c.gy; r.by = c.by; r.ru = c.ru; r.gu = c.gu; r.bu = c.bu; r.rv = c.rv; r.gv = c.gv; r.bv = c.bv;
+        const dim3 block(dw < 256 ? ((dw + 31) / 32) * 32 : 256);
+        const dim3 grid((dw + block.x - 1) / block.x, dh, n);
+        k_sws_bgra_to_bgra<<<grid, block, 0, ctx->stream>>>(r);
+        CVS_CUDA(cudaGetLastError());
+        ctx->launches++;
+        return CVS_OK;
     }
     if (sp->sws) {
         SwsScaleArgs b;

@@ -139,35 +139,17 @@ __device__ __forceinline__ int scale_sample(const uint8_t *plane, int linesize, 
     return scale_clampi(acc >> 21, 0, 255);
 }
 
-// one thread = one destination pixel (the tap tables and the few source rows a block touches stay in L1 / L2)
+// one thread = one destination pixel (the tap tables and the few source rows a block touches stay in L1 / L2); BGRA sources
+// only: the same size (the weights are then the identity: a copy) and the one geometry the pinned kernels do not take
 __global__ void __launch_bounds__(256) k_scale_to_bgra(const __grid_constant__ ScaleArgs a) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, k = blockIdx.z;
     if (x >= a.dw) return;
     uint32_t out;
-    if (a.format == SCALE_BGRA) {
+    {
         const uint8_t *p = a.src[0] + (long long)k * a.src_pic_stride[0];
         out = 0;
         for (int c = 0; c < 4; c++)
             out |= (uint32_t)scale_sample(p + c, a.src_linesize[0], a.sw, a.sh, 4, a.fx, a.wx, a.tx, x, a.fy, a.wy, a.ty, y) << (8 * c);
-    } else {
-        const int Y = scale_sample(a.src[0] + (long long)k * a.src_pic_stride[0], a.src_linesize[0], a.sw, a.sh, 1,
-                                   a.fx, a.wx, a.tx, x, a.fy, a.wy, a.ty, y);
-        int U, V;
-        if (a.format == SCALE_NV12) {
-            const uint8_t *uv = a.src[1] + (long long)k * a.src_pic_stride[1];
-            U = scale_sample(uv, a.src_linesize[1], a.cw, a.ch, 2, a.cfx, a.cwx, a.ctx_, x, a.cfy, a.cwy, a.cty, y);
-            V = scale_sample(uv + 1, a.src_linesize[1], a.cw, a.ch, 2, a.cfx, a.cwx, a.ctx_, x, a.cfy, a.cwy, a.cty, y);
-        } else {
-            U = scale_sample(a.src[1] + (long long)k * a.src_pic_stride[1], a.src_linesize[1], a.cw, a.ch, 1,
-                             a.cfx, a.cwx, a.ctx_, x, a.cfy, a.cwy, a.cty, y);
-            V = scale_sample(a.src[2] + (long long)k * a.src_pic_stride[2], a.src_linesize[2], a.cw, a.ch, 1,
-                             a.cfx, a.cwx, a.ctx_, x, a.cfy, a.cwy, a.cty, y);
-        }
-        const int c = 298 * (Y - 16), d = U - 128, e = V - 128;
-        const int r = scale_clampi((c + 409 * e + 128) >> 8, 0, 255);
-        const int g = scale_clampi((c - 100 * d - 208 * e + 128) >> 8, 0, 255);
-        const int b = scale_clampi((c + 516 * d + 128) >> 8, 0, 255);
-        out = 0xFF000000u | ((uint32_t)r << 16) | ((uint32_t)g << 8) | (uint32_t)b;
     }
     uint32_t *drow = reinterpret_cast<uint32_t *>(a.dst + (long long)k * a.dst_pic_stride + (long long)y * a.dst_stride);
     drow[x] = out;
@@ -325,6 +307,95 @@ __global__ void __launch_bounds__(256) k_sws_yuv_to_bgra_full(const __grid_const
         Y >>= 10; U >>= 10; V >>= 10;
     }
     reinterpret_cast<uint32_t *>(a.dst + (long long)k * a.dst_pic_stride + (long long)y * a.dst_stride)[x] = sws_pixel_full(Y, U, V);
+}
+
+// BGRA sources at another size.  Packed RGB on both sides makes the library go to YUV(A) at the precision of its 15-bit
+// intermediates and back through the same full-chroma writers, alpha as a fourth plane:
+//   input       y14 = (RY r + GY g + BY b + (16 << 15) + 256) >> 9, chroma per PIXEL c14 = (RU r + .. + (256 << 14) + 256) >> 9,
+//               a14 = a << 6 | a >> 2; when the width shrinks to half or less (dw <= sw / 2) chroma comes from the SUM of a pixel
+//               pair instead, (.. + (256 << 15) + 512) >> 10;
+//   horizontal  min(sum >> 13, 32767) for Y, U, V, A alike (banks sw -> dw; chroma: its own width);
+//   vertical    ONE bank sh -> dh for all four planes, writer by its tap count: 1 tap: Y = s 4, C = (c - (128 << 7)) 4,
+//               A = (a + 64) >> 7;  2 taps: (s0 (4096 - w) + s1 w) >> 10 without a rounding term, A = (.. + 2^18) >> 19;
+//               otherwise (2^9 + sum) >> 10, A = (2^18 + sum) >> 19;  colour by sws_pixel_full, alpha clipped to a byte.
+// One thread = one output pixel, the RGB -> YUV of its taps on the fly.  (A source of the output size never comes here:
+// it is a copy.  An odd source width reduced to half or less is the one geometry left on k_scale_to_bgra.)
+struct SwsRgbArgs {
+    uint8_t *dst;
+    long long dst_pic_stride;
+    int dst_stride, dw, dh;
+    const uint8_t *src;
+    long long sp;
+    int ls, half;
+    const int32_t *hl_pos, *hl_w, *hc_pos, *hc_w, *v_pos, *v_w;
+    int hl_t, hc_t, v_t;
+    int ry, gy, by, ru, gu, bu, rv, gv, bv;
+};
+__global__ void __launch_bounds__(256) k_sws_bgra_to_bgra(const __grid_constant__ SwsRgbArgs a) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, k = blockIdx.z;
+    if (x >= a.dw) return;
+    const uint8_t *src = a.src + (long long)k * a.sp;
+    const int32_t *wl = a.hl_w + (size_t)x * a.hl_t, *wc = a.hc_w + (size_t)x * a.hc_t, *wv = a.v_w + (size_t)y * a.v_t;
+    const int pl = a.hl_pos[x], pc = a.hc_pos[x], r0 = a.v_pos[y];
+    // the four horizontally filtered 15-bit samples of source row r
+    auto row15 = [&](int r, int &Y, int &U, int &V, int &A) {
+        const uint8_t *rowb = src + (size_t)r * a.ls;
+        auto px = [&](int i) {                     // (byte loads: a BGRA row need not be 4-byte aligned)
+            const uint8_t *q = rowb + 4 * (size_t)i;
+            return (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
+        };
+        int sy = 0, sa = 0, su = 0, sv = 0;
+        for (int j = 0; j < a.hl_t; j++) {
+            const uint32_t p = px(pl + j);
+            const int b = p & 0xFF, g = (p >> 8) & 0xFF, rr = (p >> 16) & 0xFF, al = p >> 24;
+            sy += ((a.ry * rr + a.gy * g + a.by * b + (16 << 15) + 256) >> 9) * wl[j];
+            sa += ((al << 6) | (al >> 2)) * wl[j];
+        }
+        for (int j = 0; j < a.hc_t; j++) {
+            int cu, cv;
+            if (a.half) {
+                const uint32_t p = px(2 * (pc + j)), q = px(2 * (pc + j) + 1);
+                const int b = (p & 0xFF) + (q & 0xFF), g = ((p >> 8) & 0xFF) + ((q >> 8) & 0xFF), rr = ((p >> 16) & 0xFF) + ((q >> 16) & 0xFF);
+                cu = (a.ru * rr + a.gu * g + a.bu * b + (256 << 15) + 512) >> 10;
+                cv = (a.rv * rr + a.gv * g + a.bv * b + (256 << 15) + 512) >> 10;
+            } else {
+                const uint32_t p = px(pc + j);
+                const int b = p & 0xFF, g = (p >> 8) & 0xFF, rr = (p >> 16) & 0xFF;
+                cu = (a.ru * rr + a.gu * g + a.bu * b + (256 << 14) + 256) >> 9;
+                cv = (a.rv * rr + a.gv * g + a.bv * b + (256 << 14) + 256) >> 9;
+            }
+            su += cu * wc[j];
+            sv += cv * wc[j];
+        }
+        Y = min(sy >> 13, 32767); A = min(sa >> 13, 32767); U = min(su >> 13, 32767); V = min(sv >> 13, 32767);
+    };
+    int Y, U, V, A;
+    if (a.v_t == 1) {
+        int y0, u0, v0, a0;
+        row15(r0, y0, u0, v0, a0);
+        Y = y0 * 4; U = (u0 - (128 << 7)) * 4; V = (v0 - (128 << 7)) * 4;
+        A = (a0 + 64) >> 7;
+    } else if (a.v_t == 2 && wv[0] + wv[1] == 4096 && wv[1] >= 0 && wv[1] <= 4096) {
+        int y0, u0, v0, a0, y1, u1, v1, a1;
+        row15(r0, y0, u0, v0, a0);
+        row15(r0 + 1, y1, u1, v1, a1);
+        const int w1 = wv[1], w0 = 4096 - w1;
+        Y = (y0 * w0 + y1 * w1) >> 10;
+        U = (u0 * w0 + u1 * w1 - (128 << 19)) >> 10;
+        V = (v0 * w0 + v1 * w1 - (128 << 19)) >> 10;
+        A = (a0 * w0 + a1 * w1 + (1 << 18)) >> 19;
+    } else {
+        Y = 1 << 9; U = V = (1 << 9) - (128 << 19); A = 1 << 18;
+        for (int j = 0; j < a.v_t; j++) {
+            if (wv[j] == 0) continue;
+            int yj, uj, vj, aj;
+            row15(r0 + j, yj, uj, vj, aj);
+            Y += yj * wv[j]; U += uj * wv[j]; V += vj * wv[j]; A += aj * wv[j];
+        }
+        Y >>= 10; U >>= 10; V >>= 10; A >>= 19;
+    }
+    reinterpret_cast<uint32_t *>(a.dst + (long long)k * a.dst_pic_stride + (long long)y * a.dst_stride)[x] =
+        (sws_pixel_full(Y, U, V) & 0x00FFFFFFu) | ((uint32_t)scale_clampi(A, 0, 255) << 24);
 }
 
 // The same conversion for the enlarging / same-size geometries (at most two taps per axis and plane), where neighbouring

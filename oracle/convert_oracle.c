@@ -15,11 +15,10 @@
  * the names of the library routines that do it; the text was written from the library's documented structure and
  * validated against the binary -- none of it is the library's source.
  *
- * PARITY UNPINNED for what the library routes differently and this file does not restate: BGRA sources at another size
- * (an RGB -> YUV -> RGB round trip inside the library) and odd destination widths (its full-chroma-interpolation
- * writers).  Those use the repository's own resampler (first part of this file: triangle-kernel resampling with 14-bit
- * weights and a 15-bit intermediate, BT.601 integer matrices), restated here from its specification in
- * csrc/scale_convert.cuh and NOT from the kernel.
+ * PARITY UNPINNED for one corner this file does not restate: a BGRA source of ODD width reduced to half its width or less
+ * (the library's chroma pairs then reach past the row).  It uses the repository's own resampler (first part of this file:
+ * triangle-kernel resampling with 14-bit weights and a 15-bit intermediate, channel by channel), restated here from its
+ * specification in csrc/scale_convert.cuh and NOT from the kernel; a BGRA source of the output size is a copy in both.
  */
 #include <stdint.h>
 #include <stdlib.h>
@@ -81,6 +80,7 @@ static int plane_sample(const uint8_t *plane, int linesize, int pw, int ph, int 
 typedef struct { int size; int *pos; int *coef; } swsfilter;      /* coef[i * size + j] applies to sample pos[i] + j */
 static int sws_bilinear_filter(swsfilter *f, int srcn, int dstn, int one, int srcpos, int dstpos);
 static void swsfilter_free(swsfilter *f);
+static int sws_q(double c);
 
 /* ---- planar YUV -> BGRA at another size: libswscale's C path, restated ------------------------------------------------
  *
@@ -102,8 +102,7 @@ static void swsfilter_free(swsfilter *f);
  *               k = Y + (c' C >> 16) - (c' >> 9) (both chroma terms for G), C clipped to 0..255; alpha = 255.
  *   exception   YUV420P at the SAME size with an even height takes the library's direct converter (yuv2rgb.c
  *               yuv2rgb_c_32): no filtering at all, the chroma sample of a 2x2 block serves its four pixels.
- * BGRA sources at another size go through an RGB -> YUV -> RGB round trip inside the library, which is not restated: that
- * case uses this repository's own resampler below (NOT pinned, stated in include/cvs_ntsc.h).
+ * BGRA sources: sws_bgra_to_bgra further down.
  */
 static int sws_rgb_k(long long k) {
     const long long cy = (65536LL * 255) / 219;
@@ -230,6 +229,94 @@ static int sws_yuv_to_bgra(uint8_t *dst, int dst_stride, int dw, int dh, const u
     return 0;
 }
 
+/* ---- BGRA -> BGRA at another size: libswscale's C path, restated ---------------------------------------------------------
+ *
+ * PINNED like the rest (tests/test_swscale_pin.py).  Packed RGB on both sides makes the library convert to YUV(A) at the
+ * precision of its 15-bit intermediates and back with the full-chroma writers, alpha as a fourth plane:
+ *   input       input.c rgb16_32ToY_c_template / rgb16_32ToUV_c_template (14-bit samples; chroma per PIXEL) and rgbaToA_c
+ *               (a14 = a << 6 | a >> 2); when the width shrinks to half or less (dw <= sw / 2) chroma comes from the SUM of
+ *               pixel pairs instead (rgb16_32ToUV_half_c_template);
+ *   horizontal  swscale.c hScale16To15_c for Y, U, V, A alike: min(sum >> 13, 32767), banks sw -> dw (chroma: its own width);
+ *   vertical    one bank sh -> dh for all four planes; output.c yuv2rgb_full_{1,2,X}_c_template (hasAlpha) by its tap count:
+ *               1 tap   Y = s 4, C = (c - (128 << 7)) 4, A = (a + 64) >> 7
+ *               2 taps  (s0 (4096 - w) + s1 w) >> 10 without a rounding term (chroma minus 128 << 19), A = (.. + 2^18) >> 19
+ *               else    (2^9 + sum) >> 10, A = (2^18 + sum) >> 19
+ *   colour      yuv2rgb_write_full as above (sws_pixel_full), alpha clipped to 0..255.
+ * A source of the same size is copied (the library does not convert at all).  Not restated: an ODD source width together
+ * with dw <= sw / 2 (the pair of the last column reaches past the row in the library); the repository's resampler below
+ * serves that case. */
+static int *sws_hscale16(const long long *plane, int srcn, int rows, const swsfilter *f, int dstn) {
+    int *out = (int *)malloc(sizeof(int) * (size_t)rows * (size_t)dstn);
+    for (int y = 0; y < rows; y++)
+        for (int x = 0; x < dstn; x++) {
+            long long v = 0;
+            for (int j = 0; j < f->size; j++) v += plane[(size_t)y * srcn + f->pos[x] + j] * f->coef[(size_t)x * f->size + j];
+            v >>= 13;
+            out[(size_t)y * dstn + x] = (int)(v < 32767 ? v : 32767);
+        }
+    return out;
+}
+static int sws_bgra_to_bgra(uint8_t *dst, int dst_stride, int dw, int dh, const uint8_t *src, int ls, int sw, int sh) {
+    const int ry = sws_q(0.299 * 219 / 255), gy = sws_q(0.587 * 219 / 255), by = sws_q(0.114 * 219 / 255);
+    const int ru = -sws_q(0.169 * 224 / 255), gu = -sws_q(0.331 * 224 / 255), bu = sws_q(0.500 * 224 / 255);
+    const int rv = sws_q(0.500 * 224 / 255), gv = -sws_q(0.419 * 224 / 255), bv = -sws_q(0.081 * 224 / 255);
+    const int half = dw <= (sw >> 1), cw = half ? sw / 2 : sw;              /* (even sw when half: checked by the caller) */
+    long long *Y = (long long *)malloc(sizeof(long long) * (size_t)sw * sh), *A = (long long *)malloc(sizeof(long long) * (size_t)sw * sh);
+    long long *U = (long long *)malloc(sizeof(long long) * (size_t)cw * sh), *V = (long long *)malloc(sizeof(long long) * (size_t)cw * sh);
+    for (int y = 0; y < sh; y++) {
+        const uint8_t *row = src + (size_t)y * (size_t)ls;
+        for (int x = 0; x < sw; x++) {
+            const uint8_t *p = row + 4 * (size_t)x;
+            Y[(size_t)y * sw + x] = ((long long)ry * p[2] + (long long)gy * p[1] + (long long)by * p[0] + (16LL << 15) + 256) >> 9;
+            A[(size_t)y * sw + x] = (p[3] << 6) | (p[3] >> 2);
+            if (!half) {
+                U[(size_t)y * cw + x] = ((long long)ru * p[2] + (long long)gu * p[1] + (long long)bu * p[0] + (256LL << 14) + 256) >> 9;
+                V[(size_t)y * cw + x] = ((long long)rv * p[2] + (long long)gv * p[1] + (long long)bv * p[0] + (256LL << 14) + 256) >> 9;
+            } else if ((x & 1) == 0) {
+                const int r = p[2] + p[6], g = p[1] + p[5], b = p[0] + p[4];
+                U[(size_t)y * cw + x / 2] = ((long long)ru * r + (long long)gu * g + (long long)bu * b + (256LL << 15) + 512) >> 10;
+                V[(size_t)y * cw + x / 2] = ((long long)rv * r + (long long)gv * g + (long long)bv * b + (256LL << 15) + 512) >> 10;
+            }
+        }
+    }
+    swsfilter hl, hc, vf;
+    sws_bilinear_filter(&hl, sw, dw, 1 << 14, 128, 128);
+    sws_bilinear_filter(&hc, cw, dw, 1 << 14, 128, 128);
+    sws_bilinear_filter(&vf, sh, dh, 1 << 12, 128, 128);
+    int *L = sws_hscale16(Y, sw, sh, &hl, dw), *AL = sws_hscale16(A, sw, sh, &hl, dw);
+    int *CU = sws_hscale16(U, cw, sh, &hc, dw), *CV = sws_hscale16(V, cw, sh, &hc, dw);
+    for (int y = 0; y < dh; y++) {
+        const int *w = vf.coef + (size_t)y * vf.size;
+        const size_t o = (size_t)vf.pos[y] * dw;
+        const int two = vf.size == 2 && w[0] + w[1] == 4096 && w[1] >= 0 && w[1] <= 4096;
+        uint32_t *row = (uint32_t *)(dst + (size_t)y * (size_t)dst_stride);
+        for (int x = 0; x < dw; x++) {
+            int yv, uv, vv, av;
+            if (vf.size == 1) {
+                yv = L[o + x] * 4; uv = (CU[o + x] - (128 << 7)) * 4; vv = (CV[o + x] - (128 << 7)) * 4;
+                av = (AL[o + x] + 64) >> 7;
+            } else if (two) {
+                const int a = w[1], a1 = 4096 - w[1];
+                yv = (L[o + x] * a1 + L[o + dw + x] * a) >> 10;
+                uv = (CU[o + x] * a1 + CU[o + dw + x] * a - (128 << 19)) >> 10;
+                vv = (CV[o + x] * a1 + CV[o + dw + x] * a - (128 << 19)) >> 10;
+                av = (AL[o + x] * a1 + AL[o + dw + x] * a + (1 << 18)) >> 19;
+            } else {
+                yv = 1 << 9; uv = vv = (1 << 9) - (128 << 19); av = 1 << 18;
+                for (int j = 0; j < vf.size; j++) {
+                    yv += L[o + (size_t)j * dw + x] * w[j]; uv += CU[o + (size_t)j * dw + x] * w[j];
+                    vv += CV[o + (size_t)j * dw + x] * w[j]; av += AL[o + (size_t)j * dw + x] * w[j];
+                }
+                yv >>= 10; uv >>= 10; vv >>= 10; av >>= 19;
+            }
+            row[x] = (sws_pixel_full(yv, uv, vv) & 0x00FFFFFFu) | ((uint32_t)clamp8(av) << 24);
+        }
+    }
+    free(Y); free(A); free(U); free(V); free(L); free(AL); free(CU); free(CV);
+    swsfilter_free(&hl); swsfilter_free(&hc); swsfilter_free(&vf);
+    return 0;
+}
+
 /* format: 0 BGRA, 1 YUV420P, 2 YUV422P, 3 NV12 (the product's enum); dst: BGRA */
 int oracle_scale_to_bgra(uint8_t *dst, int dst_stride, int dw, int dh,
                          const uint8_t *p0, const uint8_t *p1, const uint8_t *p2, int l0, int l1, int l2,
@@ -237,6 +324,7 @@ int oracle_scale_to_bgra(uint8_t *dst, int dst_stride, int dw, int dh,
     if (!dst || !p0 || dw <= 0 || dh <= 0 || sw <= 0 || sh <= 0 || format < 0 || format > 3) return -1;
     if (sw > 16 * dw || sh > 16 * dh) return -5;          /* more taps than the tables hold */
     if (format != 0) return sws_yuv_to_bgra(dst, dst_stride, dw, dh, p0, p1, p2, l0, l1, l2, sw, sh, format);
+    if ((sw != dw || sh != dh) && !((sw & 1) && dw <= (sw >> 1))) return sws_bgra_to_bgra(dst, dst_stride, dw, dh, p0, l0, sw, sh);
     const int cw = (sw + 1) / 2, ch = (format == 2) ? sh : (sh + 1) / 2;
     const int suby = (format == 2) ? 1 : 2, offy = (format == 2) ? 0 : 1;
     for (int y = 0; y < dh; y++) {

@@ -36,6 +36,11 @@ for fmt in ("yuv420p", "yuv422p", "nv12"):
         for i, pl in enumerate(planes):
             out["%s_p%d" % (n, i)] = pl
         out[n + "_bgra"] = bgra
+for sw, sh, dw, dh in ((40, 30, 64, 48), (90, 72, 64, 48), (176, 144, 64, 48), (64, 48, 65, 50), (64, 48, 64, 30)):   # BGRA sources
+    img = rng.integers(0, 256, size=(sh, 4 * sw), dtype=np.uint8)
+    n = "bgra_%dx%d_%dx%d" % (sw, sh, dw, dh)
+    out[n + "_p0"] = img
+    out[n + "_bgra"] = swscale_ref.scale([img], "bgra", sw, sh, "bgra", dw, dh, c_code=True)[0].view(np.uint32).reshape(dh, dw)
 out["libswscale_version"] = np.array(swscale_ref.version())
 np.savez_compressed(os.path.join(HERE, "swscale_to_bgra.npz"), **out)
 print("wrote", len(out), "arrays")

@@ -1,8 +1,8 @@
 """cvs_scale_to_bgra_device (the input side: InputFile::frame_copy_scale(), ffmpeg_ntsc.cpp:544-613):
-decoder picture -> BGRA at the output size on the device.  Planar YUV sources are PINNED (even and odd output widths):
+decoder picture -> BGRA at the output size on the device.  PINNED (planar YUV and BGRA sources, even and odd output widths):
 the kernel is compared bit for bit with oracle/convert_oracle.c (which tests/test_swscale_pin.py pins against libswscale
-9.1.100 itself), with the library directly when the GPU box has it, and with its committed outputs.  BGRA sources at
-another size use the repository's own resampler (not pinned; same oracle file, restated from its specification)."""
+9.1.100 itself), with the library directly when the GPU box has it, and with its committed outputs.  One corner stays on
+the repository's own resampler (not pinned; same oracle file): a BGRA source of odd width reduced to half or less."""
 import os
 
 import numpy as np
@@ -72,15 +72,27 @@ def test_scaler_equals_libswscale_itself(sw, sh, dw, dh, fmt):
     assert np.array_equal(got, want), int((got != want).sum())
 
 
+@pytest.mark.skipif(not swscale_ref.available(), reason="no libswscale on this machine (golden fixtures cover it)")
+@pytest.mark.parametrize("sw,sh,dw,dh", [(640, 480, 720, 480), (352, 288, 720, 480), (1920, 1080, 720, 480), (720, 576, 720, 480),
+                                         (720, 480, 720, 482), (720, 480, 359, 240), (100, 67, 50, 40), (101, 67, 51, 40), (64, 48, 81, 61)])
+def test_bgra_source_equals_libswscale_itself(sw, sh, dw, dh):
+    """BGRA -> BGRA at another size: the library's RGB -> YUV(A) -> RGB route (k_sws_bgra_to_bgra), alpha included."""
+    planes = source(sw, sh, BGRA, sw + dh)
+    want = swscale_ref.scale(planes, "bgra", sw, sh, "bgra", dw, dh, c_code=True)[0].view(np.uint32).reshape(dh, dw)
+    got = _scale_on_gpu(planes, sw, sh, BGRA, dw, dh)
+    assert np.array_equal(got, want), int((got != want).sum())
+
+
 def test_scaler_equals_golden_outputs_of_libswscale():
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "swscale_to_bgra.npz"))
     names = sorted({k[:-5] for k in g.files if k.endswith("_bgra")})
     assert len(names) >= 18
     code = {v: k for k, v in FMT_NAME.items()}
+    code["bgra"] = BGRA
     for nm in names:
         fmt, s_, d_ = nm.split("_")
         (sw, sh), (dw, dh) = [tuple(int(v) for v in q.split("x")) for q in (s_, d_)]
-        planes = [g["%s_p%d" % (nm, i)] for i in range(2 if fmt == "nv12" else 3)]
+        planes = [g["%s_p%d" % (nm, i)] for i in range({"nv12": 2, "bgra": 1}.get(fmt, 3))]
         assert np.array_equal(_scale_on_gpu(planes, sw, sh, code[fmt], dw, dh), g[nm + "_bgra"]), nm
 
 

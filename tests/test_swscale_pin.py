@@ -1,7 +1,8 @@
 """The two picture conversions either side of the hot path PINNED against libswscale itself:
   * encoder side (ffmpeg_ntsc.cpp:2118-2131, 2266-2274): sws_getContext(w, h, BGRA -> YUV420P | YUV422P, SWS_BILINEAR) + sws_scale;
-  * input side, InputFile::frame_copy_scale (:574-585, 603-610): sws_getContext(sw, sh, YUV420P | YUV422P | NV12 -> dw, dh,
-    BGRA, SWS_BILINEAR) + sws_scale (even destination widths: the table writers; odd ones: the full-chroma writers).
+  * input side, InputFile::frame_copy_scale (:574-585, 603-610): sws_getContext(sw, sh, YUV420P | YUV422P | NV12 | BGRA -> dw,
+    dh, BGRA, SWS_BILINEAR) + sws_scale (even destination widths: the table writers; odd ones and BGRA sources: the
+    full-chroma writers).
 oracle/convert_oracle.c restates what the library's portable C code does for those calls; here it is compared byte
 for byte with the library (libswscale 9.1.100 of this image, tests/swscale_ref.py) where that exists, and with outputs
 of the library committed as tests/golden/swscale_*.npz everywhere."""
@@ -163,8 +164,8 @@ def test_scaler_oracle_equals_golden_outputs_of_libswscale():
     for n in names:
         fmt, s, d = n.split("_")
         (sw, sh), (dw, dh) = [tuple(int(v) for v in q.split("x")) for q in (s, d)]
-        planes = [g["%s_p%d" % (n, i)] for i in range(2 if fmt == "nv12" else 3)]
-        got = helpers.oracle_scale_to_bgra(planes, sw, sh, FMT_CODE[fmt], dw, dh)
+        planes = [g["%s_p%d" % (n, i)] for i in range({"nv12": 2, "bgra": 1}.get(fmt, 3))]
+        got = helpers.oracle_scale_to_bgra(planes, sw, sh, {"bgra": 0, **FMT_CODE}[fmt], dw, dh)
         assert np.array_equal(got, g[n + "_bgra"]), n
 
 
@@ -193,3 +194,20 @@ def test_random_geometries_against_the_library():
         want = lib_planes(src, fmt)
         got = helpers.oracle_bgra_to_yuv(src, fmt == "yuv420p")
         assert all(np.array_equal(a, b) for a, b in zip(got, want)), (fmt, w, h)
+
+
+# ---- BGRA sources at another size (the library's RGB -> YUV(A) -> RGB route) -------------------------------------------
+BGRA_SCALES = [(640, 480, 720, 480), (352, 288, 720, 480), (720, 576, 720, 480), (720, 480, 720, 482), (64, 48, 81, 61),
+               (1920, 1080, 720, 480), (720, 480, 360, 240), (720, 480, 400, 480), (720, 480, 359, 240), (100, 67, 50, 40),
+               (100, 67, 51, 40), (101, 67, 51, 40), (5, 3, 9, 8), (720, 480, 720, 480)]
+
+
+@need_lib
+@pytest.mark.parametrize("sw,sh,dw,dh", BGRA_SCALES)
+def test_bgra_source_oracle_equals_libswscale_c_code(sw, sh, dw, dh):
+    """Alpha included: random bytes in all four channels (full chroma when the width shrinks by less than 2, chroma from
+    pixel pairs otherwise; every writer variant of the vertical bank; a same-size source is a copy)."""
+    img = np.random.default_rng(sw * 3 + dh).integers(0, 256, size=(sh, 4 * sw), dtype=np.uint8)
+    want = swscale_ref.scale([img], "bgra", sw, sh, "bgra", dw, dh, c_code=True)[0].view(np.uint32).reshape(dh, dw)
+    got = helpers.oracle_scale_to_bgra([img], sw, sh, 0, dw, dh)
+    assert np.array_equal(got, want), int((got != want).sum())
