@@ -2,7 +2,7 @@
 // output size, InputFile::frame_copy_scale() (ffmpeg_ntsc.cpp:544-613: sws_getContext(src w, h, format -> output
 // w, h, BGRA, SWS_BILINEAR) at :574-585, sws_scale() at :603-610).  SURVEY section 8f-1.
 //
-// Two kernels:
+// The kernels:
 //
 //  k_sws_yuv_to_bgra   YUV420P / YUV422P / NV12 sources: the bytes of libswscale's C code (9.1.100;
 //      = SWS_ACCURATE_RND | SWS_BITEXACT).  PINNED: oracle/convert_oracle.c restates the library and is compared with it
@@ -24,10 +24,11 @@
 //      enlarging), so no intermediate picture exists.  Odd output widths take the library's other writers
 //      (k_sws_yuv_to_bgra_full, further down).
 //
-//  k_scale_to_bgra     BGRA sources at another size (the library scales packed RGB through a cascade over planar RGB with a
-//      high-precision YUV round trip inside, which is not restated): the repository's OWN resampler, NOT pinned -- measured
-//      against the library: +-1 per colour channel on 3 - 14 % of the values when enlarging, more when shrinking (the library
-//      halves the chroma of the round trip there) -- specified here and restated independently in oracle/convert_oracle.c:
+//  k_sws_bgra_to_bgra  BGRA sources at another size: the library's RGB -> YUV(A) -> RGB route (further down), pinned too.
+//
+//  k_scale_to_bgra     BGRA sources of the output size (a copy, as in the library) and the ONE geometry the pinned kernels do
+//      not take -- a BGRA source of odd width reduced to half its width or less, where the library's chroma pairs reach past
+//      the row: the repository's OWN resampler, NOT pinned, specified here and restated independently in the oracle:
 //  * per axis, destination sample i of n_dst takes its value at source position P / D (centre aligned),
 //        D = 2 n_dst sub,   P = (2 i + 1) n_src - n_dst - off n_dst,
 //    n_src the LUMA size of the source along the axis, sub = 1 for luma / BGRA planes and 2 for a subsampled chroma

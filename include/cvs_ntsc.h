@@ -239,11 +239,13 @@ void cvs_audio_destroy(cvs_audio *a);
  * including their wrap-around for far-out-of-gamut samples).  Alpha 255.  (csrc/scale_convert.cuh states the arithmetic;
  * checked against libswscale 9.1.100, tests/test_swscale_pin.py; the library's x86 SIMD converter differs from its C code
  * by up to 3 codes.)
- * CVS_PIX_BGRA sources: a source of the output size is copied, as the library does; at another size the repository's
- * own resampler, NOT pinned (triangle kernel with 14-bit weights, centre-aligned, 15-bit intermediate, channel by
- * channel; measured against the library, which scales packed RGB through a planar-RGB cascade: +-1 per colour channel on
- * 3 - 14 % of the values when enlarging, more when shrinking), specified in the same header and restated independently
- * in oracle/convert_oracle.c.
+ * CVS_PIX_BGRA sources: PINNED likewise.  A source of the output size is copied, as the library does; at another size
+ * the library converts packed RGB to YUV(A) at the precision of its 15-bit intermediates and back (chroma per pixel, or
+ * from pixel pairs when the width shrinks to half or less; alpha a << 6 | a >> 2 as a fourth plane; the full-chroma
+ * writers), which is what this does.  The one geometry left on the repository's own resampler, NOT pinned (triangle
+ * kernel with 14-bit weights, channel by channel; specified in csrc/scale_convert.cuh, restated in
+ * oracle/convert_oracle.c): a BGRA source of ODD width reduced to half its width or less, where the library's chroma
+ * pairs reach past the row.
  * Shrinking by more than 16x per axis returns CVS_ERR_CAPACITY.
  */
 enum { CVS_PIX_BGRA = 0, CVS_PIX_YUV420P = 1, CVS_PIX_YUV422P = 2, CVS_PIX_NV12 = 3 };
