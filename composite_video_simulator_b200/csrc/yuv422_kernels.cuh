@@ -229,8 +229,9 @@ __device__ __forceinline__ void group_barrier() {
 // -vhs -vhs-speed sp, profiles/ab_variants_r2.txt section 7): 83.2 k fields/s rotated against 90.2 k with role = warp.
 // One role per scheduler keeps that scheduler's instruction stream to ONE loop of ~6 KB (each scheduler fetches through
 // its own small L0 instruction cache in front of the SM's 32 KB); four loops per scheduler cost more than the idle FP64
-// cycles they win back.  What would pay instead is equal FP64 work per ROLE (the stages re-dealt: 161 FP64 instructions
-// per role and step instead of 123 / 123 / 276 / 123) with the assignment left alone; DESIGN.md section 9.
+// cycles they win back.  Re-dealing a stage instead (the luma sharpen from role 2 to role 0, CVS422_LSHARP_ROLE) was
+// measured too and is slower as well (83.1 k): the FP64 count of the longest role is not what a step waits for either;
+// DESIGN.md section 9.
 __device__ __forceinline__ int role_of(const Launch422 &a, int tid) {
     __shared__ int s_rot;
     if (!a.rotate) return tid >> 5;

@@ -242,6 +242,14 @@ CVS_HD int div50(int v) {                // exact for every 32-bit magnitude
 #ifndef CVS422_LU
 #define CVS422_LU 8                      // luma pixels per iteration: 1, 2, 4 or 8
 #endif
+// Which role runs the VHS luma sharpen (G4a): 2 (with the chroma stages of G3b / G4: FP64 instructions per role and step
+// 123 / 123 / 276 / 123) or 0 (with the load and the input lowpass: 221 / 123 / 178 / 123).  Same block, same step: the
+// stage reads what role 1 wrote one step earlier and nobody else touches that luma block in between, whichever role runs
+// it; both are bit-exact.  Measured (profiles/ab_variants_r2.txt section 8): 89.9 k fields/s with 2, 83.1 k with 0 -- the
+// better FP64 balance loses, so 2 stays.
+#ifndef CVS422_LSHARP_ROLE
+#define CVS422_LSHARP_ROLE 2
+#endif
 #if defined(__CUDA_ARCH__)
 #define CVS_ROLLED _Pragma("unroll 1")
 #else
@@ -1073,6 +1081,10 @@ CVS_HD void role0_step(const K422 &K, const Lags &L, const Geo &G, const Row422 
     const int bM = s - L.bM;
     Pipe422<true>::stage_load(K, G, ln, s, in);
     if (bM >= 0 && bM < G.nb) Pipe422<true>::template stage_modulate<true>(K, rc, ln, bM, warp_hs, hsrow);
+#if CVS422_LSHARP_ROLE == 0
+    const int bC = s - L.bC;
+    if ((K.flags & G_VHS) && bC >= 0 && bC < G.nb) Pipe422<true>::stage_luma_sharpen(K, ln, bC);
+#endif
 }
 // role 1
 CVS_HD void role1_step(const K422 &K, const Lags &L, const Geo &G, const DivPair &dv, const Row422 &rc, Lane422 &ln, int s) {
@@ -1087,7 +1099,9 @@ CVS_HD void role2_front(const K422 &K, const Lags &L, const Geo &G, Lane422 &ln,
     const int bC = s - L.bC, bV = s - L.bV;
     if (bC >= 0 && bC < G.nb) {
         Pipe422<true>::stage_chroma_lp(K, ln, bC);
+#if CVS422_LSHARP_ROLE == 2
         Pipe422<true>::stage_luma_sharpen(K, ln, bC);
+#endif
     }
     if (bV >= 0 && bV < G.nb) Pipe422<true>::blend_fetch(ln, bV, pu, pv);
 }
@@ -1166,6 +1180,9 @@ CVS_HD void frow0_step(const K422 &K, const Lags &L, int nb, const Row422 &rc, L
     }
     const int bM = s - L.bM;
     if (blk_ok(bM, nb)) Fast422::stage_modulate_first(K, rc, ln, bM, warp_hs);
+#if CVS422_LSHARP_ROLE == 0
+    if ((K.flags & G_VHS) && blk_ok(s - L.bC, nb)) Fast422::stage_luma_sharpen(K, ln, s - L.bC);
+#endif
 }
 CVS_HD void frow1_step(const K422 &K, const Lags &L, int nb, const Row422 &rc, Lane422 &ln, int s) {
     const int b = s - L.bD;
@@ -1182,7 +1199,9 @@ CVS_HD void frow2_front(const K422 &K, const Lags &L, int nb, Lane422 &ln, int s
             Fast422::carry_leave(ln.ru, bC, K.cd, ln.cCh[0]);
             Fast422::carry_leave(ln.rv, bC, K.cd, ln.cCh[1]);
         }
+#if CVS422_LSHARP_ROLE == 2
         Fast422::stage_luma_sharpen(K, ln, bC);
+#endif
     }
     if (blk_ok(b, nb)) Pipe422<false>::blend_fetch(ln, b, pu, pv);
 }
