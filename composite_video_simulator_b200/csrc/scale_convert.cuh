@@ -27,8 +27,8 @@
 //  k_sws_bgra_to_bgra  BGRA sources at another size: the library's RGB -> YUV(A) -> RGB route (further down), pinned too.
 //
 //  k_scale_to_bgra     BGRA sources of the output size (a copy, as in the library) and the ONE geometry the pinned kernels do
-//      not take -- a BGRA source of odd width reduced to half its width or less, where the library's chroma pairs reach past
-//      the row: the repository's OWN resampler, NOT pinned, specified here and restated independently in the oracle:
+//      not take yet -- a BGRA source of odd width reduced to half its width or less (the library keeps chroma per pixel
+//      there; known too late in the round to route and verify): the repository's OWN resampler, NOT pinned, specified here:
 //  * per axis, destination sample i of n_dst takes its value at source position P / D (centre aligned),
 //        D = 2 n_dst sub,   P = (2 i + 1) n_src - n_dst - off n_dst,
 //    n_src the LUMA size of the source along the axis, sub = 1 for luma / BGRA planes and 2 for a subsampled chroma

@@ -244,8 +244,8 @@ void cvs_audio_destroy(cvs_audio *a);
  * from pixel pairs when the width shrinks to half or less; alpha a << 6 | a >> 2 as a fourth plane; the full-chroma
  * writers), which is what this does.  The one geometry left on the repository's own resampler, NOT pinned (triangle
  * kernel with 14-bit weights, channel by channel; specified in csrc/scale_convert.cuh, restated in
- * oracle/convert_oracle.c): a BGRA source of ODD width reduced to half its width or less, where the library's chroma
- * pairs reach past the row.
+ * oracle/convert_oracle.c): a BGRA source of ODD width reduced to half its width or less (the library keeps chroma per
+ * pixel there; not routed yet).
  * Shrinking by more than 16x per axis returns CVS_ERR_CAPACITY.
  */
 enum { CVS_PIX_BGRA = 0, CVS_PIX_YUV420P = 1, CVS_PIX_YUV422P = 2, CVS_PIX_NV12 = 3 };

@@ -15,8 +15,9 @@
  * the names of the library routines that do it; the text was written from the library's documented structure and
  * validated against the binary -- none of it is the library's source.
  *
- * PARITY UNPINNED for one corner this file does not restate: a BGRA source of ODD width reduced to half its width or less
- * (the library's chroma pairs then reach past the row).  It uses the repository's own resampler (first part of this file:
+ * PARITY UNPINNED for one corner: a BGRA source of ODD width reduced to half its width or less.  The library's rule for it
+ * is known and restated (oracle_sws_bgra_to_bgra) but was found after the last GPU run of the round, so the product still
+ * routes it to the repository's own resampler, and oracle_scale_to_bgra follows the product (first part of this file:
  * triangle-kernel resampling with 14-bit weights and a 15-bit intermediate, channel by channel), restated here from its
  * specification in csrc/scale_convert.cuh and NOT from the kernel; a BGRA source of the output size is a copy in both.
  */
@@ -242,9 +243,9 @@ static int sws_yuv_to_bgra(uint8_t *dst, int dst_stride, int dw, int dh, const u
  *               2 taps  (s0 (4096 - w) + s1 w) >> 10 without a rounding term (chroma minus 128 << 19), A = (.. + 2^18) >> 19
  *               else    (2^9 + sum) >> 10, A = (2^18 + sum) >> 19
  *   colour      yuv2rgb_write_full as above (sws_pixel_full), alpha clipped to 0..255.
- * A source of the same size is copied (the library does not convert at all).  Not restated: an ODD source width together
- * with dw <= sw / 2 (the pair of the last column reaches past the row in the library); the repository's resampler below
- * serves that case. */
+ * A source of the same size is copied (the library does not convert at all).  With an ODD source width the library keeps
+ * chroma per pixel at every ratio; the product does not take that geometry through this route yet when dw <= sw / 2 (see
+ * below), the repository's resampler serves it. */
 static int *sws_hscale16(const long long *plane, int srcn, int rows, const swsfilter *f, int dstn) {
     int *out = (int *)malloc(sizeof(int) * (size_t)rows * (size_t)dstn);
     for (int y = 0; y < rows; y++)
@@ -257,10 +258,13 @@ static int *sws_hscale16(const long long *plane, int srcn, int rows, const swsfi
     return out;
 }
 static int sws_bgra_to_bgra(uint8_t *dst, int dst_stride, int dw, int dh, const uint8_t *src, int ls, int sw, int sh) {
+    /* (odd sw: the library keeps chroma per pixel whatever the ratio -- established after the GPU budget of the round was
+     * spent, so the product still routes "odd sw, dw <= sw / 2" to its own resampler and oracle_scale_to_bgra follows it;
+     * tests/test_swscale_pin.py::test_bgra_odd_width_corner shows the library's rule through oracle_sws_bgra_to_bgra) */
     const int ry = sws_q(0.299 * 219 / 255), gy = sws_q(0.587 * 219 / 255), by = sws_q(0.114 * 219 / 255);
     const int ru = -sws_q(0.169 * 224 / 255), gu = -sws_q(0.331 * 224 / 255), bu = sws_q(0.500 * 224 / 255);
     const int rv = sws_q(0.500 * 224 / 255), gv = -sws_q(0.419 * 224 / 255), bv = -sws_q(0.081 * 224 / 255);
-    const int half = dw <= (sw >> 1), cw = half ? sw / 2 : sw;              /* (even sw when half: checked by the caller) */
+    const int half = !(sw & 1) && dw <= (sw >> 1), cw = half ? sw / 2 : sw;
     long long *Y = (long long *)malloc(sizeof(long long) * (size_t)sw * sh), *A = (long long *)malloc(sizeof(long long) * (size_t)sw * sh);
     long long *U = (long long *)malloc(sizeof(long long) * (size_t)cw * sh), *V = (long long *)malloc(sizeof(long long) * (size_t)cw * sh);
     for (int y = 0; y < sh; y++) {
@@ -315,6 +319,12 @@ static int sws_bgra_to_bgra(uint8_t *dst, int dst_stride, int dw, int dh, const 
     free(Y); free(A); free(U); free(V); free(L); free(AL); free(CU); free(CV);
     swsfilter_free(&hl); swsfilter_free(&hc); swsfilter_free(&vf);
     return 0;
+}
+
+/* the library's route for a BGRA source of ANY geometry at another size (see the note in sws_bgra_to_bgra) */
+int oracle_sws_bgra_to_bgra(uint8_t *dst, int dst_stride, int dw, int dh, const uint8_t *src, int ls, int sw, int sh) {
+    if (!dst || !src || dw <= 0 || dh <= 0 || sw <= 0 || sh <= 0 || (sw == dw && sh == dh)) return -1;
+    return sws_bgra_to_bgra(dst, dst_stride, dw, dh, src, ls, sw, sh);
 }
 
 /* format: 0 BGRA, 1 YUV420P, 2 YUV422P, 3 NV12 (the product's enum); dst: BGRA */

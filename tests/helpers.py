@@ -370,6 +370,16 @@ def oracle_bgra_to_yuv(bgra, v420):
     return y, u, v
 
 
+def oracle_sws_bgra_route(img, sw, sh, dw, dh):
+    """The library's own route for a BGRA source at another size, for every geometry (oracle_sws_bgra_to_bgra)."""
+    lib = load_convert_oracle()
+    src = np.ascontiguousarray(img)
+    dst = np.zeros((dh, dw), np.uint32)
+    rc = lib.oracle_sws_bgra_to_bgra(_ptr(dst), 4 * dw, dw, dh, _ptr(src), src.strides[0], sw, sh)
+    assert rc == 0, rc
+    return dst
+
+
 def oracle_sws_filter(srcn, dstn, one, max_taps=16):
     """The bilinear filter bank of one axis as libswscale builds it (oracle/convert_oracle.c) -> (pos[dstn], coef[dstn, taps])."""
     lib = load_convert_oracle()

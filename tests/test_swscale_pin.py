@@ -211,3 +211,15 @@ def test_bgra_source_oracle_equals_libswscale_c_code(sw, sh, dw, dh):
     want = swscale_ref.scale([img], "bgra", sw, sh, "bgra", dw, dh, c_code=True)[0].view(np.uint32).reshape(dh, dw)
     got = helpers.oracle_scale_to_bgra([img], sw, sh, 0, dw, dh)
     assert np.array_equal(got, want), int((got != want).sum())
+
+
+@need_lib
+@pytest.mark.parametrize("sw,sh,dw,dh", [(101, 67, 50, 40), (33, 21, 7, 5), (721, 480, 360, 240), (101, 67, 51, 40), (100, 67, 50, 40)])
+def test_bgra_odd_width_corner(sw, sh, dw, dh):
+    """The one geometry the PRODUCT does not take through the library's route yet: a BGRA source of odd width reduced to
+    half its width or less.  The library's rule is known -- an odd source width keeps chroma per pixel at every ratio -- and
+    restated (oracle_sws_bgra_to_bgra == the library here); the product still uses the repository's resampler for it,
+    because the rule was found after the round's last GPU run.  Next step: route it to k_sws_bgra_to_bgra (half = false)."""
+    img = np.random.default_rng(sw + dw).integers(0, 256, size=(sh, 4 * sw), dtype=np.uint8)
+    want = swscale_ref.scale([img], "bgra", sw, sh, "bgra", dw, dh, c_code=True)[0].view(np.uint32).reshape(dh, dw)
+    assert np.array_equal(helpers.oracle_sws_bgra_route(img, sw, sh, dw, dh), want)
