@@ -34,6 +34,7 @@
 #include <vector>
 
 #include "../include/cvs_ntsc.h"
+#include "field_schedule.h"
 
 #if defined(CVS_WITH_FFMPEG) || __has_include(<libavformat/avformat.h>)
 extern "C" {
@@ -284,45 +285,41 @@ int main(int argc, char **argv) {
     uint8_t *const o = (uint8_t *)obuf;
 
     PictureStore store;
-    std::vector<int32_t> src_of_field;            // per gathered field: index of the picture it shows
-    unsigned long long current = 0;               // next output field (the reference's `current`, :2144)
+    FieldSchedule sched(batch);                   // which stored picture every output field shows (tools/field_schedule.h)
     const AVRational field_tb = p.output_ntsc ? AVRational{1001, 60000} : AVRational{1, 50};
 
     auto flush = [&]() {                          // the gathered fields through the GPU, then to the encoder
-        const int n = (int)src_of_field.size();
-        if (n == 0) return;
-        cvs_field_loop d;
-        memset(&d, 0, sizeof d);
-        d.struct_size = (int32_t)sizeof d;
-        d.src_format = store.fmt; d.src_w = store.w; d.src_h = store.h;
-        for (int k = 0; k < 3; k++) { d.src[k] = store.base[k]; d.src_linesize[k] = store.linesize[k]; d.src_pic_stride[k] = store.stride[k]; }
-        d.nsrc = store.n;
-        d.src_of_field = src_of_field.data();
-        d.w = w; d.h = h;
-        d.out_format = yuv422 ? CVS_YUV422P : CVS_YUV420P;
-        d.y = o; d.u = o + ysz; d.v = o + ysz + csz;
-        d.ly = w; d.lu = cw; d.lv = cw;
-        d.y_pic_stride = d.u_pic_stride = d.v_pic_stride = (long long)opic;
-        const int rc2 = cvs_field_loop_host(ctx, &d, n, current);
-        if (rc2 != CVS_OK) fail("cvs_field_loop_host", rc2);
-        for (int k = 0; k < n; k++) out.video(o + (size_t)k * opic, o + (size_t)k * opic + ysz, o + (size_t)k * opic + ysz + csz, w, cw, current + (unsigned long long)k);
-        current += (unsigned long long)n;
+        const int n = (int)sched.src_of_field.size();
+        if (n > 0) {
+            cvs_field_loop d;
+            memset(&d, 0, sizeof d);
+            d.struct_size = (int32_t)sizeof d;
+            d.src_format = store.fmt; d.src_w = store.w; d.src_h = store.h;
+            for (int k = 0; k < 3; k++) { d.src[k] = store.base[k]; d.src_linesize[k] = store.linesize[k]; d.src_pic_stride[k] = store.stride[k]; }
+            d.nsrc = sched.stored;
+            d.src_of_field = sched.src_of_field.data();
+            d.w = w; d.h = h;
+            d.out_format = yuv422 ? CVS_YUV422P : CVS_YUV420P;
+            d.y = o; d.u = o + ysz; d.v = o + ysz + csz;
+            d.ly = w; d.lu = cw; d.lv = cw;
+            d.y_pic_stride = d.u_pic_stride = d.v_pic_stride = (long long)opic;
+            const int rc2 = cvs_field_loop_host(ctx, &d, n, (unsigned long long)sched.current);
+            if (rc2 != CVS_OK) fail("cvs_field_loop_host", rc2);
+            for (int k = 0; k < n; k++)
+                out.video(o + (size_t)k * opic, o + (size_t)k * opic + ysz, o + (size_t)k * opic + ysz + csz, w, cw,
+                          (unsigned long long)sched.current + (unsigned long long)k);
+        }
         // the picture still on show stays in the store as picture 0
-        if (store.n > 0) {
-            const int last = store.n - 1;
-            if (last != 0)
-                for (int pl = 0; pl < 3 && store.base[pl]; pl++)
-                    memmove(store.base[pl], store.base[pl] + (size_t)last * (size_t)store.stride[pl], (size_t)store.stride[pl]);
-            store.n = 1;
-        }
-        src_of_field.clear();
+        if (sched.stored > 1)
+            for (int pl = 0; pl < 3 && store.base[pl]; pl++)
+                memmove(store.base[pl], store.base[pl] + (size_t)(sched.stored - 1) * (size_t)store.stride[pl], (size_t)store.stride[pl]);
+        sched.flushed();
+        store.n = sched.stored;
     };
-    // fields [current + gathered, upto) show the newest picture of the store
-    auto show_until = [&](long long upto) {
-        while ((long long)(current + src_of_field.size()) < upto && store.n > 0) {
-            src_of_field.push_back(store.n - 1);
-            if ((int)src_of_field.size() == batch) flush();
-        }
+    // the zeroed frame the reference starts with (:556-561), in the decoder's format
+    auto black = [&](int slot) {
+        for (int pl = 0; pl < 3 && store.base[pl]; pl++)
+            memset(store.base[pl] + (size_t)slot * (size_t)store.stride[pl], (store.fmt == CVS_PIX_BGRA) ? 0 : (pl == 0 ? 16 : 128), (size_t)store.stride[pl]);
     };
 
     std::vector<int16_t> pcm;
@@ -338,7 +335,7 @@ int main(int argc, char **argv) {
             AVFrame *f = in.frame;
             if (dec == in.adec) {
                 // audio in demux order: whatever was gathered so far draws first (one rand() stream, :952 / :1640)
-                flush();
+                if (!sched.src_of_field.empty()) flush();
                 if (!in.swr) {
                     AVChannelLayout lay;
                     av_channel_layout_default(&lay, channels);
@@ -359,10 +356,9 @@ int main(int argc, char **argv) {
                 continue;
             }
             // a decoded picture: its pts in output fields (:2170-2176)
-            long long at = (long long)(current + src_of_field.size());
+            long long at = -1;
             const long long pts = f->best_effort_timestamp;
             if (pts != AV_NOPTS_VALUE) at = av_rescale_q(pts, in.fmt->streams[in.vidx]->time_base, field_tb);
-            show_until(at);                       // the previous picture lasts until this one starts (:2203)
             int fmt = pix_of(f->format);
             uint8_t *const *data = f->data;
             const int *ls = f->linesize;
@@ -378,15 +374,16 @@ int main(int argc, char **argv) {
                 fmt = CVS_PIX_BGRA; data = in.bgra->data; ls = in.bgra->linesize; sw = w; sh = h;
             }
             if (store.fmt != fmt || store.w != sw || store.h != sh) {       // first picture, or the stream changed shape (:565-572)
-                flush();
+                // what is on show belongs to the old shape: it ends here
+                if (sched.stored > 0) { sched.show_until(at < 0 ? sched.next_field() : at, flush); flush(); sched.stored = 0; }
                 store.shape(ctx, fmt, sw, sh, batch + 1);
             }
-            if (store.n == store.cap) flush();
+            const int slot = sched.picture(at, flush, black);
+            store.n = slot;
             store.add(data, ls);
         }
     }
-    show_until((long long)(current + src_of_field.size()) + 2);            // the last picture: one frame = two fields
-    flush();
+    sched.finish(flush);                          // the last picture: one frame = two fields
     fprintf(stderr, "\n");
     out.close();
     in.close();
