@@ -24,8 +24,9 @@
 // decoder formats other than YUV420P / YUV422P / NV12 / BGRA).  Where they are absent -- as in the image this
 // repository is developed in -- it compiles to a stub that says so; `make ffmpeg-host` in csrc/ builds the real thing
 // (pkg-config), and tests/test_ffmpeg_host_syntax.py compiles this source against tests/ffmpeg_decl/ (declarations of
-// the API subset used here, written for that check; not FFmpeg's headers).  The raw-frame host tools/cvs_ntsc_raw.cpp
-// is the one exercised on the GPU box.
+// the API subset used here, written for that check; not FFmpeg's headers); the field schedule lives in tools/field_schedule.h
+// and is checked on the CPU (tests/test_field_schedule.py).  The raw-frame host tools/cvs_ntsc_raw.cpp is the one exercised
+// on the GPU box.
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
